@@ -1,0 +1,221 @@
+"""
+Pins the CPU oracle on every known-answer the reference's own test-suite holds for the hot path
+(citations: file:line under /root/reference/test).  CPU only.
+"""
+import math
+
+import numpy as np
+import pytest
+
+PI = math.pi
+
+
+# ------------------------------------------------------------------ test_grids.jl:11-148
+def test_grid_sizes_bounds_spacing(oracle):
+    o = oracle
+    nx, ny = 5, 20
+    g = o.Grid((-1.0, -2.0), (2.0, 4.0), (nx, ny))
+    assert g.size(o.CENTER) == (nx, ny)                                   # :31-39
+    assert g.size(o.VERTEX) == (nx + 1, ny + 1)
+    assert g.size((o.CENTER, o.VERTEX)) == (nx, ny + 1)
+    assert g.size((o.VERTEX, o.CENTER)) == (nx + 1, ny)
+    assert np.allclose(g.bounds(0, o.VERTEX), (-1.0, 1.0))                # :41-46
+    assert np.allclose(g.bounds(1, o.VERTEX), (-2.0, 2.0))
+    assert np.allclose(g.bounds(0, o.CENTER), (-0.8, 0.8))
+    assert np.allclose(g.bounds(1, o.CENTER), (-1.9, 1.9))
+    assert np.isclose(g.extent_at(0, o.CENTER), 1.6) and np.isclose(g.extent_at(1, o.CENTER), 3.8)   # :48-62
+    assert np.isclose(g.origin_at(0, o.CENTER), -0.8) and np.isclose(g.origin_at(1, o.CENTER), -1.9)  # :64-78
+    assert np.allclose(g.spacing, (0.4, 0.2))                             # :80-110
+    assert np.allclose(g.inv_spacing, (2.5, 5.0))
+    assert np.isclose(g.coord(0, o.VERTEX, 1), -1.0) and np.isclose(g.coord(1, o.VERTEX, 1), -2.0)   # :124-148
+    assert np.isclose(g.coord(0, o.VERTEX, nx + 1), 1.0) and np.isclose(g.coord(1, o.VERTEX, ny + 1), 2.0)
+    assert np.isclose(g.coord(0, o.CENTER, 1), -0.8) and np.isclose(g.coord(1, o.CENTER, 1), -1.9)
+    assert np.isclose(g.coord(0, o.CENTER, nx), 0.8) and np.isclose(g.coord(1, o.CENTER, ny), 1.9)
+    # default connectivity is Bounded (:20-24)
+    assert all(c == o.BOUNDED for side in g.conn for c in side)
+
+
+# ------------------------------------------------------------------ test_fields.jl:19-55 (exact == in the reference)
+def test_set_continuous_exact(oracle):
+    o = oracle
+    g = o.Grid((0.0, 0.0, 0.0), (1.0, 1.0, 1.0), (2, 2, 2))
+    f = o.Field(g, (o.CENTER, o.VERTEX, o.CENTER))
+    assert f.dims == (2, 3, 2)
+    f.data[...] = np.nan
+    f.set_fun(lambda x, y, z: y)
+    exp_y = np.zeros((2, 3, 2))
+    exp_y[:, 0, :], exp_y[:, 1, :], exp_y[:, 2, :] = 0.0, 0.5, 1.0
+    assert np.array_equal(f.interior(), exp_y)
+    f.data[...] = np.nan
+    f.set_fun(lambda x, y, z: x)
+    exp_x = np.zeros((2, 3, 2))
+    exp_x[0], exp_x[1] = 0.25, 0.75
+    assert np.array_equal(f.interior(), exp_x)
+    f.data[...] = np.nan
+    f.set_fun(lambda x, y, z, sc: y * sc, 2.0)
+    assert np.array_equal(f.interior(), 2.0 * exp_y)
+    # set! touches the interior only
+    assert np.isnan(f.data[0]).all() and np.isnan(f.data[:, 1]).all()
+
+
+# ------------------------------------------------------------------ test_boundary_conditions.jl:11-205
+CASES = [
+    ((8,), (0,)), ((8,), (1,)),                                    # 1D Center / Vertex      :11-89
+    ((8, 8), (0, 1)),                                              # 2D (Center, Vertex)     :91-141
+    ((8, 8, 6), (0, 1, 0)),                                        # 3D (C, V, C)            :143-205
+]
+
+
+def _face(a, dim, idx):
+    """a[..., idx, ...] restricted to 2:end-1 in the transverse dims (the reference excludes corners)."""
+    sl = [slice(1, -1)] * a.ndim
+    sl[dim] = idx
+    return a[tuple(sl)]
+
+
+@pytest.mark.parametrize("n,loc", CASES)
+def test_bc_known_answers(oracle, n, loc):
+    o = oracle
+    nd = len(n)
+    g = o.Grid((-PI,) * nd, (2 * PI,) * nd, n)
+    f = o.Field(g, loc)
+
+    def run(bc):
+        f.data[...] = 0.0
+        f.set(1.0)
+        o.bc_(g, (f, bc))
+        return f.interior(with_halo=True).copy()
+
+    a = run(o.Dirichlet())
+    for d in range(nd):
+        if loc[d] == o.CENTER:
+            assert np.allclose(_face(a, d, 0), -_face(a, d, 1)) and np.allclose(_face(a, d, -1), -_face(a, d, -2))
+        else:
+            assert np.allclose(_face(a, d, 1), 0.0) and np.allclose(_face(a, d, -2), 0.0)
+    a = run(o.Neumann())
+    for d in range(nd):
+        assert np.allclose(_face(a, d, 0), _face(a, d, 1)) and np.allclose(_face(a, d, -1), _face(a, d, -2))
+    v = 2.0
+    a = run(o.Dirichlet(v))
+    for d in range(nd):
+        if loc[d] == o.CENTER:
+            assert np.allclose(_face(a, d, 0), -_face(a, d, 1) + 2 * v)
+            assert np.allclose(_face(a, d, -1), -_face(a, d, -2) + 2 * v)
+        else:
+            assert np.allclose(_face(a, d, 1), v) and np.allclose(_face(a, d, -2), v)
+    q = 2.0
+    a = run(o.Neumann(q))
+    for d in range(nd):
+        h = g.spacing[d]
+        assert np.allclose((_face(a, d, 1) - _face(a, d, 0)) / h, q)
+        assert np.allclose((_face(a, d, -1) - _face(a, d, -2)) / h, q)
+
+
+# ------------------------------------------------------------------ test_grid_operators.jl:13-131
+def _gauss_grid(o):
+    g = o.Grid((-5.0,) * 3, (10.0,) * 3, (12, 10, 8))
+    Ci = o.Field(g, o.CENTER)
+    Ci.set_fun(lambda x, y, z: np.exp(-x ** 2 - y ** 2 - z ** 2))
+    return g, Ci
+
+
+def test_divg_identity_bit_exact(oracle):
+    """divg(V) == dx(V.x)+dy(V.y)+dz(V.z) with `==` (test_grid_operators.jl:41)."""
+    o = oracle
+    g, Ci = _gauss_grid(o)
+    V = o.VectorField(g)
+    nx, ny, nz = g.n
+    rng = range
+    for k in rng(0, nz + 2):
+        for j in rng(0, ny + 2):
+            for i in rng(0, nx + 2):
+                for d, c in enumerate("xyz"):
+                    V[c].data[i + 1, j + 1, k + 1] = o.partial(g, Ci, d, i, j, k)
+    # the stress kernel stores divg(V) into its second output: run it with zero rheology side effects
+    tau, tau_old = o.TensorField(g), o.TensorField(g)
+    Pr, dV = o.Field(g, o.CENTER), o.Field(g, o.CENTER)
+    L = o.Launcher(g)
+    o.launch(L, g, o.update_stress, (tau, Pr, dV, V, tau_old, 1.0, 1.0, 1.0, 1.0, 0.0, 0.0))
+    C1 = np.zeros(g.n)
+    for k in rng(1, nz + 1):
+        for j in rng(1, ny + 1):
+            for i in rng(1, nx + 1):
+                C1[i - 1, j - 1, k - 1] = (o.partial(g, V["x"], 0, i, j, k) + o.partial(g, V["y"], 1, i, j, k)) \
+                    + o.partial(g, V["z"], 2, i, j, k)
+    assert np.array_equal(dV.interior(), C1)
+    assert np.abs(C1).max() > 1e-3
+
+
+def test_lapl_and_divg_grad(oracle):
+    """lapl == sum d2 (bit exact, :61); divg_grad ~ d(lerp(chi) d C) for chi at Center and Vertex (:98,110)."""
+    o = oracle
+    g, Ci = _gauss_grid(o)
+    nx, ny, nz = g.n
+    for chi_loc in (o.CENTER, o.VERTEX):
+        chi = o.Field(g, chi_loc)
+        chi.set_fun(lambda x, y, z: np.exp(-x ** 2 - y ** 2 - z ** 2))
+        V = o.VectorField(g)
+        for k in range(0, nz + 2):
+            for j in range(0, ny + 2):
+                for i in range(0, nx + 2):
+                    for d, c in enumerate("xyz"):
+                        V[c].data[i + 1, j + 1, k + 1] = o.lerp(g, chi, V[c].loc, i, j, k) * o.partial(g, Ci, d, i, j, k)
+        for k in range(1, nz + 1, 3):
+            for j in range(1, ny + 1, 2):
+                for i in range(1, nx + 1):
+                    c1 = o.partial(g, V["x"], 0, i, j, k) + o.partial(g, V["y"], 1, i, j, k) + o.partial(g, V["z"], 2, i, j, k)
+                    c2 = (o.dkd(g, Ci, chi, 0, i, j, k) + o.dkd(g, Ci, chi, 1, i, j, k)) + o.dkd(g, Ci, chi, 2, i, j, k)
+                    assert math.isclose(c1, c2, rel_tol=1e-8, abs_tol=1e-14)
+    # second derivative against the explicit three-point formula
+    idx = g.inv_spacing
+    for (i, j, k) in [(1, 1, 1), (6, 5, 4), (12, 10, 8)]:
+        for d in range(3):
+            e = [0, 0, 0]
+            e[d] = 1
+            a = Ci.at(i + e[0], j + e[1], k + e[2]); b = Ci.at(i, j, k); c = Ci.at(i - e[0], j - e[1], k - e[2])
+            assert o.partial2(g, Ci, d, i, j, k) == ((a - b) * idx[d] - (b - c) * idx[d]) * idx[d]
+
+
+def test_vmag_constant(oracle):
+    """vmag of the constant (2,2,2) field = 3.4641 to 5 significant digits (:113-131)."""
+    o = oracle
+    g, _ = _gauss_grid(o)
+    V = o.VectorField(g)
+    for c in "xyz":
+        V[c].set(2.0)
+    s = 0.0
+    vals = [o.lerp(g, V[c], o.CENTER, 3, 3, 3) for c in "xyz"]
+    s = math.sqrt((vals[0] ** 2 + vals[1] ** 2) + vals[2] ** 2)
+    assert float(f"{s:.5g}") == 3.4641
+
+
+# ------------------------------------------------------------------ test_interpolations.jl:15-74
+def test_lerp_known_answers(oracle):
+    o = oracle
+    g = o.Grid((0.0, 0.0), (1.0, 1.0), (2, 2))
+    av4 = lambda A: 0.25 * (A[:-1, :-1] + A[1:, :-1] + A[1:, 1:] + A[:-1, 1:])
+    avx = lambda A: 0.5 * (A[:-1, :] + A[1:, :])
+    avy = lambda A: 0.5 * (A[:, :-1] + A[:, 1:])
+
+    def interp(src, to):
+        dst = o.Field(g, to)
+        out = np.zeros(dst.dims)
+        for j in range(1, dst.dims[1] + 1):
+            for i in range(1, dst.dims[0] + 1):
+                out[i - 1, j - 1] = o.lerp(g, src, to, i, j)
+        return out
+
+    fc = o.Field(g, o.CENTER)
+    fc.set(np.arange(1, 5, dtype=float).reshape((2, 2), order="F"))
+    fci = fc.interior().copy()
+    assert np.allclose(interp(fc, o.VERTEX)[1:-1, 1:-1], av4(fci))
+    assert np.allclose(interp(fc, o.CENTER), fci)
+    assert np.allclose(interp(fc, (o.CENTER, o.VERTEX))[:, 1:-1], avy(fci))
+    assert np.allclose(interp(fc, (o.VERTEX, o.CENTER))[1:-1, :], avx(fci))
+    fv = o.Field(g, o.VERTEX)
+    fv.set(np.arange(1, 10, dtype=float).reshape((3, 3), order="F"))
+    fvi = fv.interior().copy()
+    assert np.allclose(interp(fv, o.CENTER), av4(fvi))
+    assert np.allclose(interp(fv, o.VERTEX), fvi)
+    assert np.allclose(interp(fv, (o.CENTER, o.VERTEX)), avx(fvi))
+    assert np.allclose(interp(fv, (o.VERTEX, o.CENTER)), avy(fvi))
