@@ -1,0 +1,24 @@
+"""
+chmy_b200 -- B200-native hot path of PTsolvers/Chmy.jl behind the reference's own API names.
+
+Julia `f!` is spelled `f_` here; `op => args` is the tuple `(op, args)`; 1-based Dim/Side are kept.
+Everything computes through libchmy_b200.so (hand-written CUDA for sm_100a, include/chmy_b200.h).
+"""
+from ._lib import ChmyError, LIB_PATH, lib as load_library
+from .utils import Dim, Side, Left, Right, remove_dim, insert_dim
+from .architectures import (Architecture, SingleDeviceArchitecture, DistributedArchitecture, B200Backend, Arch,
+                            get_backend, get_device, activate_, synchronize, launch_count, topology,
+                            event_record, event_elapsed_ms)
+from .grids import (Location, Center, Vertex, flip, Bounded, Connected, UniformAxis, StructuredGrid, UniformGrid,
+                    connectivity, spacing, inv_spacing, coord, coords, centers, vertices, origin, extent, bounds,
+                    axes_names)
+from .fields import (AbstractField, Field, FieldTuple, VectorField, TensorField, FunctionField, init_incl, set_,
+                     interior, parent, fill_parent_, halo, location, maxabs, vector_location)
+from .boundary_conditions import (FirstOrderBC, Dirichlet, Neumann, EmptyBatch, FieldBatch, ExchangeBatch, batch, bc_)
+from .kernel_launch import (Launcher, worksize, outer_width, inner_worksize, inner_offset, outer_worksize,
+                            outer_offset)
+from .distributed import (CartesianTopology, TorchDistComm, dims_create, exchange_halo_, allreduce_max, barrier,
+                          global_rank, shared_rank, node_name, dims, cart_coords, neighbors, neighbor, has_neighbor,
+                          global_size, node_size, PROC_NULL)
+from .ops import (KernelOp, compute_q_, update_C_, update_old_, update_stress_, update_velocity_,
+                  update_thermal_flux_, update_thermal_)

@@ -1,0 +1,131 @@
+"""
+Architectures: device + stream ownership behind the C ABI.
+Mirrors src/Architectures.jl:14-89, ext/ChmyCUDAExt/ChmyCUDAExt.jl:7-23 and
+src/Distributed/distributed_architecture.jl:6-75.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _lib as L
+
+
+class B200Backend:
+    """The KernelAbstractions-style backend tag of this path (stands where `CUDABackend()` stands in the
+    reference's drivers).  There is exactly one backend: hand-written CUDA for sm_100a."""
+
+    def __repr__(self):
+        return "B200Backend()"
+
+
+class Architecture:
+    pass
+
+
+class SingleDeviceArchitecture(Architecture):
+    """SingleDeviceArchitecture{B,D} (Architectures.jl:21-28): owns the device context and its streams."""
+
+    def __init__(self, backend: B200Backend, device_id: int = 1):
+        if not isinstance(backend, B200Backend):
+            raise TypeError("this path has a single backend: B200Backend()")
+        self.backend = backend
+        self.device_id = int(device_id)
+        h = C.c_void_p()
+        L.check(L.lib().chmy_ctx_create(self.device_id, C.byref(h)))   # set_device! + streams
+        self._ctx = h
+
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            raise L.ChmyError("architecture was destroyed")
+        return self._ctx
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None:
+            L.lib().chmy_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DistributedArchitecture(Architecture):
+    """DistributedArchitecture (distributed_architecture.jl:6-34): child single-device arch + CartesianTopology."""
+
+    def __init__(self, child_arch: SingleDeviceArchitecture, topology, gpu_aware: bool = True):
+        self.child_arch = child_arch
+        self.topology = topology
+        self.gpu_aware = gpu_aware      # device buffers go straight into NCCL: always "GPU-aware"
+
+    @property
+    def ctx(self):
+        return self.child_arch.ctx
+
+    @property
+    def backend(self):
+        return self.child_arch.backend
+
+    @property
+    def device_id(self):
+        return self.child_arch.device_id
+
+    def close(self):
+        self.child_arch.close()
+
+
+def Arch(backend, comm=None, dims=None, *, device_id=None, gpu_aware=True) -> Architecture:
+    """Arch(backend; device_id=1)                          -- Architectures.jl:46-49
+    Arch(backend, comm, dims; device_id, gpu_aware)     -- distributed_architecture.jl:27-34
+    (device defaults to the node-local rank + 1)."""
+    if comm is None:
+        return SingleDeviceArchitecture(backend, 1 if device_id is None else device_id)
+    from .distributed import CartesianTopology
+    topo = CartesianTopology(comm, tuple(dims))
+    dev = topo.shared_rank + 1 if device_id is None else device_id
+    child = SingleDeviceArchitecture(backend, dev)
+    topo._attach(child)
+    return DistributedArchitecture(child, topo, gpu_aware)
+
+
+def get_backend(arch: Architecture):
+    return arch.backend
+
+
+def get_device(arch: Architecture):
+    return arch.device_id
+
+
+def activate_(arch: Architecture, priority: str = "normal"):
+    """activate!(arch; priority) (Architectures.jl:71-74).  Stream priorities are fixed inside the context
+    (main = normal, boundary = high), so this only validates its argument."""
+    if priority not in ("normal", "low", "high"):
+        raise ValueError("priority must be :normal, :low or :high")
+
+
+def synchronize(arch: Architecture):
+    """KernelAbstractions.synchronize(backend)."""
+    L.check(L.lib().chmy_synchronize(arch.ctx))
+
+
+def launch_count(arch: Architecture) -> int:
+    n = C.c_uint64()
+    L.check(L.lib().chmy_ctx_launch_count(arch.ctx, C.byref(n)))
+    return int(n.value)
+
+
+def topology(arch: DistributedArchitecture):
+    return arch.topology
+
+
+def event_record(arch: Architecture, slot: int):
+    """CUDA event on the architecture's main stream (device-side timing for benchmarks)."""
+    L.check(L.lib().chmy_event_record(arch.ctx, int(slot)))
+
+
+def event_elapsed_ms(arch: Architecture, start: int, stop: int) -> float:
+    ms = C.c_float()
+    L.check(L.lib().chmy_event_elapsed_ms(arch.ctx, int(start), int(stop), C.byref(ms)))
+    return float(ms.value)

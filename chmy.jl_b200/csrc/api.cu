@@ -1,0 +1,431 @@
+// api.cu -- C-ABI entry points of libchmy_b200.so: context (device + streams), fields, launch orchestration.
+// Interface contract and reference citations: include/chmy_b200.h.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+// declared in bc.cu / ops.cu / ops_fast.cu
+int chmy_box_from(const chmy_field* f, const int64_t* lo, const int64_t* hi, Box* out);
+int chmy_fill_box(chmy_ctx* ctx, chmy_field* f, double v, const Box& b, cudaStream_t st);
+int chmy_copy_box(chmy_ctx* ctx, chmy_field* d, const chmy_field* s, const Box& b, cudaStream_t st);
+int chmy_incl_box(chmy_ctx* ctx, chmy_field* f, const InclDev& q, const Box& b, cudaStream_t st);
+int chmy_maxabs_box(chmy_ctx* ctx, const chmy_field* f, const Box& b, unsigned long long* d_out, cudaStream_t st);
+int chmy_run_op_generic(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st);
+int chmy_run_op_fast(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st, int* handled);
+
+// ---------------------------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+
+void chmy_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* chmy_last_error(void) { return g_err; }
+extern "C" int chmy_abi_version(void) { return CHMY_ABI_VERSION; }
+
+extern "C" size_t chmy_struct_size(int which) {
+    switch (which) {
+    case 0: return sizeof(chmy_grid_desc);
+    case 1: return sizeof(chmy_batch_desc);
+    case 2: return sizeof(chmy_inclusion);
+    case 3: return sizeof(chmy_launch_desc);
+    case 4: return sizeof(chmy_field_info);
+    default: return 0;
+    }
+}
+
+extern "C" int chmy_device_count(int* count) {
+    CHMY_REQUIRE(count != nullptr, "count is NULL");
+    CHMY_CUDA(cudaGetDeviceCount(count));
+    return CHMY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- context
+extern "C" int chmy_ctx_create(int device_id, chmy_ctx** out) {
+    CHMY_REQUIRE(out != nullptr, "out is NULL");
+    int ndev = 0;
+    CHMY_CUDA(cudaGetDeviceCount(&ndev));
+    // the reference's device ids are 1-based: CuDevice(id - 1)  (ext/ChmyCUDAExt/ChmyCUDAExt.jl:17)
+    CHMY_REQUIRE(device_id >= 1 && device_id <= ndev, "device_id %d out of range 1..%d", device_id, ndev);
+    chmy_ctx* c = (chmy_ctx*)calloc(1, sizeof(chmy_ctx));
+    if (!c) { chmy_set_error("out of host memory"); return CHMY_ERR_NOMEM; }
+    c->device = device_id - 1;
+    CHMY_CUDA(cudaSetDevice(c->device));
+    int lo = 0, hi = 0;   // numerically lowest value = highest priority
+    CHMY_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    // activate!(arch; priority=:high) for the boundary workers (KernelLaunch.jl:44-47)
+    CHMY_CUDA(cudaStreamCreateWithPriority(&c->s_main, cudaStreamNonBlocking, lo));
+    CHMY_CUDA(cudaStreamCreateWithPriority(&c->s_bnd, cudaStreamNonBlocking, hi));
+    CHMY_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CHMY_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CHMY_CUDA(cudaMalloc(&c->d_red, 64 * sizeof(unsigned long long)));
+    CHMY_CUDA(cudaMallocHost(&c->h_red, 64 * sizeof(unsigned long long)));
+    CHMY_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+    *out = c;
+    return CHMY_OK;
+}
+
+extern "C" int chmy_ctx_destroy(chmy_ctx* c) {
+    if (!c) return CHMY_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->comm) chmy_comm_destroy(c->comm);
+    cudaFree(c->d_red);
+    cudaFreeHost(c->h_red);
+    if (c->ev_time) {
+        for (int i = 0; i < CHMY_MAX_EVENTS; ++i) if (c->ev_time[i]) cudaEventDestroy(c->ev_time[i]);
+        free(c->ev_time);
+    }
+    cudaEventDestroy(c->ev_fork);
+    cudaEventDestroy(c->ev_join);
+    cudaStreamDestroy(c->s_main);
+    cudaStreamDestroy(c->s_bnd);
+    free(c);
+    return CHMY_OK;
+}
+
+extern "C" int chmy_ctx_device(const chmy_ctx* c, int* device_id) {
+    CHMY_REQUIRE(c && device_id, "NULL argument");
+    *device_id = c->device + 1;
+    return CHMY_OK;
+}
+
+extern "C" int chmy_synchronize(chmy_ctx* c) {
+    CHMY_REQUIRE(c != nullptr, "ctx is NULL");
+    CHMY_CUDA(cudaSetDevice(c->device));
+    CHMY_CUDA(cudaStreamSynchronize(c->s_bnd));
+    CHMY_CUDA(cudaStreamSynchronize(c->s_main));
+    return CHMY_OK;
+}
+
+extern "C" int chmy_ctx_launch_count(const chmy_ctx* c, uint64_t* kernels) {
+    CHMY_REQUIRE(c && kernels, "NULL argument");
+    *kernels = c->n_launches;
+    return CHMY_OK;
+}
+
+extern "C" int chmy_event_record(chmy_ctx* c, int slot) {
+    CHMY_REQUIRE(c && slot >= 0 && slot < CHMY_MAX_EVENTS, "bad event slot");
+    CHMY_CUDA(cudaSetDevice(c->device));
+    if (!c->ev_time) {
+        c->ev_time = (cudaEvent_t*)calloc(CHMY_MAX_EVENTS, sizeof(cudaEvent_t));
+        if (!c->ev_time) { chmy_set_error("out of host memory"); return CHMY_ERR_NOMEM; }
+    }
+    if (!c->ev_time[slot]) CHMY_CUDA(cudaEventCreate(&c->ev_time[slot]));
+    CHMY_CUDA(cudaEventRecord(c->ev_time[slot], c->s_main));
+    return CHMY_OK;
+}
+
+extern "C" int chmy_event_elapsed_ms(chmy_ctx* c, int a, int b, float* ms) {
+    CHMY_REQUIRE(c && ms && c->ev_time && a >= 0 && b >= 0 && a < CHMY_MAX_EVENTS && b < CHMY_MAX_EVENTS &&
+                     c->ev_time[a] && c->ev_time[b], "event slots not recorded");
+    CHMY_CUDA(cudaEventSynchronize(c->ev_time[b]));
+    CHMY_CUDA(cudaEventElapsedTime(ms, c->ev_time[a], c->ev_time[b]));
+    return CHMY_OK;
+}
+
+extern "C" int chmy_ctx_streams(const chmy_ctx* c, void** main_stream, void** boundary_stream) {
+    CHMY_REQUIRE(c != nullptr, "ctx is NULL");
+    if (main_stream) *main_stream = (void*)c->s_main;
+    if (boundary_stream) *boundary_stream = (void*)c->s_bnd;
+    return CHMY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- fields
+static inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+extern "C" int chmy_field_create(chmy_ctx* ctx, int ndims, const int64_t* dims, const int32_t* loc, int layout,
+                                 chmy_field** out) {
+    CHMY_REQUIRE(ctx && dims && loc && out, "NULL argument");
+    CHMY_REQUIRE(ndims >= 1 && ndims <= 3, "ndims %d not in 1..3", ndims);
+    CHMY_REQUIRE(layout == CHMY_LAYOUT_PITCHED || layout == CHMY_LAYOUT_DENSE, "bad layout %d", layout);
+    chmy_field* f = (chmy_field*)calloc(1, sizeof(chmy_field));
+    if (!f) { chmy_set_error("out of host memory"); return CHMY_ERR_NOMEM; }
+    f->ctx = ctx; f->nd = ndims; f->layout = layout;
+    for (int a = 0; a < 3; ++a) {
+        if (a < ndims) {
+            CHMY_REQUIRE(dims[a] >= 1 && dims[a] < (1ll << 30), "bad field size %lld along dim %d", (long long)dims[a], a + 1);
+            CHMY_REQUIRE(loc[a] == CHMY_CENTER || loc[a] == CHMY_VERTEX, "bad location along dim %d", a + 1);
+            f->loc[a] = loc[a]; f->d[a] = dims[a]; f->sd[a] = dims[a] + 4;   // field.jl:58 (halo = 1)
+        } else {
+            f->loc[a] = CHMY_CENTER; f->d[a] = 1; f->sd[a] = 1;
+        }
+    }
+    // PITCHED: row pitch a multiple of 16 doubles and a 15-element lead-in, so that logical index 0 of every row
+    // sits on a 128-byte boundary (storage element 0 is logical -1).
+    const long long pitch = layout == CHMY_LAYOUT_PITCHED ? round_up(f->sd[0], 16) : f->sd[0];
+    f->lead      = layout == CHMY_LAYOUT_PITCHED ? 15 : 0;
+    f->stride[0] = 1;
+    f->stride[1] = pitch;
+    f->stride[2] = pitch * f->sd[1];
+    const long long elems = f->lead + pitch * f->sd[1] * f->sd[2] + 32;
+    f->bytes = (size_t)elems * sizeof(double);
+    CHMY_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(&f->alloc, f->bytes);
+    if (e != cudaSuccess) {
+        free(f);
+        chmy_set_error("cudaMalloc of %zu bytes failed: %s", (size_t)elems * 8, cudaGetErrorString(e));
+        return CHMY_ERR_NOMEM;
+    }
+    CHMY_CUDA(cudaMemsetAsync(f->alloc, 0, f->bytes, ctx->s_main));   // KernelAbstractions.zeros, field.jl:59
+    f->p0 = f->alloc + f->lead + 1 + (ndims > 1 ? f->stride[1] : 0) + (ndims > 2 ? f->stride[2] : 0);
+    *out = f;
+    return CHMY_OK;
+}
+
+extern "C" int chmy_field_destroy(chmy_field* f) {
+    if (!f) return CHMY_OK;
+    cudaSetDevice(f->ctx->device);
+    cudaFree(f->alloc);
+    free(f);
+    return CHMY_OK;
+}
+
+extern "C" int chmy_field_get_info(const chmy_field* f, chmy_field_info* out) {
+    CHMY_REQUIRE(f && out, "NULL argument");
+    memset(out, 0, sizeof(*out));
+    out->ndims = f->nd; out->layout = f->layout;
+    for (int a = 0; a < 3; ++a) { out->loc[a] = f->loc[a]; out->dims[a] = f->d[a]; out->stride[a] = f->stride[a]; }
+    out->origin_ptr = (void*)f->at(1, 1, 1);
+    out->base_ptr   = (void*)f->at(-1, -1, -1);
+    out->bytes      = f->bytes;
+    return CHMY_OK;
+}
+
+extern "C" int chmy_field_fill(chmy_ctx* ctx, chmy_field* f, double v, const int64_t* lo, const int64_t* hi) {
+    CHMY_REQUIRE(ctx && f && lo && hi, "NULL argument");
+    Box b;
+    CHMY_TRY(chmy_box_from(f, lo, hi, &b));
+    CHMY_CUDA(cudaSetDevice(ctx->device));
+    return chmy_fill_box(ctx, f, v, b, ctx->s_main);
+}
+
+extern "C" int chmy_field_copy(chmy_ctx* ctx, chmy_field* dst, const chmy_field* src, const int64_t* lo, const int64_t* hi) {
+    CHMY_REQUIRE(ctx && dst && src && lo && hi, "NULL argument");
+    CHMY_REQUIRE(dst->nd == src->nd, "set!(f, other): dimensionality mismatch");
+    Box b, b2;
+    CHMY_TRY(chmy_box_from(dst, lo, hi, &b));
+    CHMY_TRY(chmy_box_from(src, lo, hi, &b2));
+    CHMY_CUDA(cudaSetDevice(ctx->device));
+    return chmy_copy_box(ctx, dst, src, b, ctx->s_main);
+}
+
+static int copy_box_host(chmy_ctx* ctx, const chmy_field* f, double* host, const int64_t* lo, const int64_t* hi, bool to_host) {
+    Box b;
+    CHMY_TRY(chmy_box_from(f, lo, hi, &b));
+    if (b.n[0] <= 0 || b.n[1] <= 0 || b.n[2] <= 0) return CHMY_OK;
+    CHMY_CUDA(cudaSetDevice(ctx->device));
+    double* dev = f->at(b.lo[0], f->nd > 1 ? b.lo[1] : 0, f->nd > 2 ? b.lo[2] : 0);
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    const size_t w = (size_t)b.n[0] * sizeof(double);
+    cudaPitchedPtr hp = make_cudaPitchedPtr(host, w, (size_t)b.n[0], (size_t)b.n[1]);
+    cudaPitchedPtr dp = make_cudaPitchedPtr(dev, (size_t)f->stride[1] * sizeof(double), (size_t)f->sd[0], (size_t)f->sd[1]);
+    p.srcPtr = to_host ? dp : hp;
+    p.dstPtr = to_host ? hp : dp;
+    p.extent = make_cudaExtent(w, (size_t)b.n[1], (size_t)b.n[2]);
+    p.kind   = to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+    if (to_host) CHMY_CUDA(cudaStreamSynchronize(ctx->s_bnd));
+    CHMY_CUDA(cudaMemcpy3DAsync(&p, ctx->s_main));
+    CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));
+    return CHMY_OK;
+}
+
+extern "C" int chmy_field_copy_from_host(chmy_ctx* ctx, chmy_field* f, const double* src, const int64_t* lo, const int64_t* hi) {
+    CHMY_REQUIRE(ctx && f && src && lo && hi, "NULL argument");
+    return copy_box_host(ctx, f, const_cast<double*>(src), lo, hi, false);
+}
+
+extern "C" int chmy_field_copy_to_host(chmy_ctx* ctx, const chmy_field* f, double* dst, const int64_t* lo, const int64_t* hi) {
+    CHMY_REQUIRE(ctx && f && dst && lo && hi, "NULL argument");
+    return copy_box_host(ctx, f, dst, lo, hi, true);
+}
+
+static InclDev incl_from(const chmy_grid_desc* g, const chmy_inclusion* inc, const int* loc) {
+    InclDev q;
+    memset(&q, 0, sizeof(q));
+    q.active = 1; q.nd = g->ndims;
+    for (int a = 0; a < 3; ++a) {
+        q.loc[a] = loc[a]; q.origin[a] = g->origin[a]; q.spacing[a] = g->spacing[a]; q.c0[a] = inc->c0[a];
+    }
+    q.r2 = inc->r * inc->r; q.in = inc->in; q.out = inc->out;
+    return q;
+}
+
+extern "C" int chmy_field_set_inclusion(chmy_ctx* ctx, chmy_field* f, const chmy_grid_desc* g, const chmy_inclusion* inc) {
+    CHMY_REQUIRE(ctx && f && g && inc, "NULL argument");
+    CHMY_REQUIRE(f->nd == g->ndims, "set!: field/grid dimensionality mismatch");
+    int64_t lo[3] = {1, 1, 1}, hi[3] = {f->d[0], f->d[1], f->d[2]};
+    Box b;
+    CHMY_TRY(chmy_box_from(f, lo, hi, &b));
+    CHMY_CUDA(cudaSetDevice(ctx->device));
+    return chmy_incl_box(ctx, f, incl_from(g, inc, f->loc), b, ctx->s_main);
+}
+
+extern "C" int chmy_field_maxabs(chmy_ctx* ctx, const chmy_field* f, const int64_t* lo, const int64_t* hi, double* out) {
+    CHMY_REQUIRE(ctx && f && lo && hi && out, "NULL argument");
+    Box b;
+    CHMY_TRY(chmy_box_from(f, lo, hi, &b));
+    CHMY_CUDA(cudaSetDevice(ctx->device));
+    CHMY_CUDA(cudaStreamSynchronize(ctx->s_bnd));
+    CHMY_CUDA(cudaMemsetAsync(ctx->d_red, 0, sizeof(unsigned long long), ctx->s_main));
+    if (b.n[0] > 0 && b.n[1] > 0 && b.n[2] > 0) CHMY_TRY(chmy_maxabs_box(ctx, f, b, ctx->d_red, ctx->s_main));
+    CHMY_CUDA(cudaMemcpyAsync(ctx->h_red, ctx->d_red, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->s_main));
+    CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));
+    memcpy(out, ctx->h_red, sizeof(double));
+    return CHMY_OK;
+}
+
+extern "C" int chmy_halo_slab_len(const chmy_field* f, int dim, int64_t* len) {
+    CHMY_REQUIRE(f && len && dim >= 0 && dim < f->nd, "bad argument");
+    *len = chmy_slab_len(f, dim);
+    return CHMY_OK;
+}
+
+static int halo_host(chmy_ctx* ctx, chmy_field* f, int dim, int side, double* host, bool pack) {
+    CHMY_REQUIRE(ctx && f && host && dim >= 0 && dim < f->nd && (side == 0 || side == 1), "bad argument");
+    const size_t bytes = (size_t)chmy_slab_len(f, dim) * sizeof(double);
+    double* dbuf = nullptr;
+    CHMY_CUDA(cudaSetDevice(ctx->device));
+    CHMY_CUDA(cudaMalloc(&dbuf, bytes));
+    int rc = CHMY_OK;
+    chmy_field* fs[1] = {f};
+    if (pack) {
+        rc = chmy_pack_fields(ctx, dim, side, 1, fs, dbuf, ctx->s_main);
+        if (rc == CHMY_OK && cudaMemcpyAsync(host, dbuf, bytes, cudaMemcpyDeviceToHost, ctx->s_main) != cudaSuccess) rc = CHMY_ERR_CUDA;
+    } else {
+        if (cudaMemcpyAsync(dbuf, host, bytes, cudaMemcpyHostToDevice, ctx->s_main) != cudaSuccess) rc = CHMY_ERR_CUDA;
+        if (rc == CHMY_OK) rc = chmy_unpack_fields(ctx, dim, side, 1, fs, dbuf, ctx->s_main);
+    }
+    cudaStreamSynchronize(ctx->s_main);
+    cudaFree(dbuf);
+    return rc;
+}
+
+extern "C" int chmy_halo_pack(chmy_ctx* ctx, const chmy_field* f, int dim, int side, double* host_buf) {
+    return halo_host(ctx, const_cast<chmy_field*>(f), dim, side, host_buf, true);
+}
+extern "C" int chmy_halo_unpack(chmy_ctx* ctx, chmy_field* f, int dim, int side, const double* host_buf) {
+    return halo_host(ctx, f, dim, side, const_cast<double*>(host_buf), false);
+}
+
+// ---------------------------------------------------------------------------------------------- launch
+static int run_op(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st) {
+    if (box.n[0] <= 0 || box.n[1] <= 0 || box.n[2] <= 0) return CHMY_OK;
+    int handled = 0;
+    CHMY_TRY(chmy_run_op_fast(ctx, d, box, st, &handled));
+    if (handled) return CHMY_OK;
+    return chmy_run_op_generic(ctx, d, box, st);
+}
+
+static int validate_grid(const chmy_grid_desc* g) {
+    CHMY_REQUIRE(g->ndims >= 1 && g->ndims <= 3, "grid.ndims %d not in 1..3", g->ndims);
+    for (int a = 0; a < g->ndims; ++a) {
+        CHMY_REQUIRE(g->n[a] >= 1 && g->n[a] < (1ll << 30), "bad grid size along dim %d", a + 1);
+        for (int s = 0; s < 2; ++s)
+            CHMY_REQUIRE(g->connectivity[a][s] == CHMY_BOUNDED || g->connectivity[a][s] == CHMY_CONNECTED,
+                         "bad connectivity (only Bounded and Connected are implemented, as in the reference)");
+    }
+    return CHMY_OK;
+}
+
+// bc!(side, dim, ...) for both sides of one dim: FieldBatch sides -> BC kernel, ExchangeBatch sides -> halo exchange
+static int bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int D, const chmy_batch_desc* l, const chmy_batch_desc* r,
+                  cudaStream_t st) {
+    CHMY_TRY(chmy_run_bc_dim(ctx, g, D, l, r, st));
+    if (l->kind == CHMY_BATCH_EXCHANGE || r->kind == CHMY_BATCH_EXCHANGE) CHMY_TRY(chmy_exchange_dim(ctx, g, D, l, r, st));
+    return CHMY_OK;
+}
+
+static int validate_batches(const chmy_grid_desc* g, const chmy_batch_desc bc[CHMY_MAX_DIMS][2], bool* any_exchange) {
+    *any_exchange = false;
+    for (int D = 0; D < g->ndims; ++D)
+        for (int s = 0; s < 2; ++s) {
+            const chmy_batch_desc& b = bc[D][s];
+            CHMY_REQUIRE(b.kind == CHMY_BATCH_EMPTY || b.kind == CHMY_BATCH_FIELD || b.kind == CHMY_BATCH_EXCHANGE, "bad batch kind");
+            if (b.kind == CHMY_BATCH_EXCHANGE) {
+                // batch_impl(::Connected, ...) is the only producer of ExchangeBatch (batch.jl:98-101)
+                CHMY_REQUIRE(g->connectivity[D][s] == CHMY_CONNECTED, "ExchangeBatch on a Bounded side");
+                *any_exchange = true;
+            }
+        }
+    return CHMY_OK;
+}
+
+extern "C" int chmy_bc(chmy_ctx* ctx, const chmy_grid_desc* g, const chmy_batch_desc bc[CHMY_MAX_DIMS][2], int flags) {
+    CHMY_REQUIRE(ctx && g && bc, "NULL argument");
+    CHMY_TRY(validate_grid(g));
+    bool any_ex = false;
+    CHMY_TRY(validate_batches(g, bc, &any_ex));
+    CHMY_CUDA(cudaSetDevice(ctx->device));
+    for (int D = g->ndims - 1; D >= 0; --D)               // D = N..1, side 1 then 2 (batch.jl:20-29)
+        CHMY_TRY(bc_dim(ctx, g, D, &bc[D][0], &bc[D][1], ctx->s_main));
+    if (flags & CHMY_LAUNCH_BLOCKING) CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));
+    return CHMY_OK;
+}
+
+extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
+    CHMY_REQUIRE(ctx && d, "NULL argument");
+    const chmy_grid_desc* g = &d->grid;
+    CHMY_TRY(validate_grid(g));
+    CHMY_TRY(chmy_validate_op(d));
+    CHMY_REQUIRE(d->op != CHMY_OP_NONE, "chmy_launch needs an op (use chmy_bc for a bare batch set)");
+    CHMY_CUDA(cudaSetDevice(ctx->device));
+    const int N = g->ndims;
+    // worksize = ncenters + 2, I = J + Offset(-1)  ->  I in 0..n+1   (KernelLaunch.jl:41,109)
+    Box full;
+    for (int a = 0; a < 3; ++a) { full.lo[a] = 0; full.n[a] = a < N ? (int)g->n[a] + 2 : 1; }
+
+    if (!d->has_bc) {   // launch_without_bc: one full-range kernel even when the Launcher has an outer_width (:121-126)
+        CHMY_TRY(run_op(ctx, d, full, ctx->s_main));
+    } else {
+        bool any_ex = false;
+        CHMY_TRY(validate_batches(g, d->bc, &any_ex));
+        bool split = d->has_outer_width != 0;
+        if (split) {
+            for (int a = 0; a < N; ++a) {
+                CHMY_REQUIRE(d->outer_width[a] >= 0, "negative outer_width");
+                // the slabs must contain everything the batches touch: halo, first/last interior and send planes
+                if (d->outer_width[a] < 3 || 2 * d->outer_width[a] > g->n[a] + 2) split = false;
+            }
+            // outer_width is a scheduling hint (results do not depend on it, the ops are pointwise): without a
+            // neighbour to talk to there is nothing to overlap, so run one full-range kernel.
+            if (!any_ex && !(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) split = false;
+        }
+        if (!split) {   // KernelLaunch.jl:156-159
+            CHMY_TRY(run_op(ctx, d, full, ctx->s_main));
+            for (int D = N - 1; D >= 0; --D) CHMY_TRY(bc_dim(ctx, g, D, &d->bc[D][0], &d->bc[D][1], ctx->s_main));
+        } else {        // KernelLaunch.jl:160-181: inner region on the main stream, slabs + batches on the boundary stream
+            const int64_t* ow = d->outer_width;
+            CHMY_CUDA(cudaEventRecord(ctx->ev_fork, ctx->s_main));
+            CHMY_CUDA(cudaStreamWaitEvent(ctx->s_bnd, ctx->ev_fork, 0));
+            for (int D = N - 1; D >= 0; --D) {
+                for (int S = 0; S < 2; ++S) {
+                    Box b;   // outer_worksize / outer_offset, KernelLaunch.jl:63-87
+                    for (int a = 0; a < 3; ++a) {
+                        if (a >= N) { b.lo[a] = 0; b.n[a] = 1; }
+                        else if (a < D) { b.lo[a] = 0; b.n[a] = full.n[a]; }
+                        else if (a == D) { b.lo[a] = S == 0 ? 0 : full.n[a] - (int)ow[a]; b.n[a] = (int)ow[a]; }
+                        else { b.lo[a] = (int)ow[a]; b.n[a] = full.n[a] - 2 * (int)ow[a]; }
+                    }
+                    CHMY_TRY(run_op(ctx, d, b, ctx->s_bnd));
+                }
+                CHMY_TRY(bc_dim(ctx, g, D, &d->bc[D][0], &d->bc[D][1], ctx->s_bnd));
+            }
+            Box in;      // inner_worksize / inner_offset, KernelLaunch.jl:60-61
+            for (int a = 0; a < 3; ++a) {
+                in.lo[a] = a < N ? (int)ow[a] : 0;
+                in.n[a]  = a < N ? full.n[a] - 2 * (int)ow[a] : 1;
+            }
+            CHMY_TRY(run_op(ctx, d, in, ctx->s_main));
+            CHMY_CUDA(cudaEventRecord(ctx->ev_join, ctx->s_bnd));
+            CHMY_CUDA(cudaStreamWaitEvent(ctx->s_main, ctx->ev_join, 0));
+        }
+    }
+    if (d->flags & CHMY_LAUNCH_BLOCKING) CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));   // KernelLaunch.jl:117
+    return CHMY_OK;
+}

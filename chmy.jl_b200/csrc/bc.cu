@@ -1,0 +1,288 @@
+// bc.cu -- boundary-condition batches, halo slab pack/unpack and the small field utilities (sm_100a).
+//
+// Boundary rules: src/BoundaryConditions/first_order_boundary_condition.jl:34-84 on a uniform grid
+//   Dirichlet, field Vertex along D : f[b] = v                          b  = 1 | d      (the boundary node)
+//   Dirichlet, field Center along D : f[h] = muladd(2, v - f[nb], f[nb])  h = 0 | d+1 ; nb = 1 | d
+//   Neumann  , any location         : f[h] = muladd(spacing_D, -/+q, f[nb])
+// Face range: src/BoundaryConditions/batch.jl:159-184 -- transverse index I_t = J-1 in 0..n_t+2, fields of a batch
+// applied in batch order.  Halo slabs: src/Distributed/communication_views.jl:1-34.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------- BC batches
+struct BcEntry {
+    FV     f;
+    int    kind;      // chmy_bc_kind
+    int    vertex;    // location of the field along the BC dim
+    int    d;         // logical size of the field along the BC dim
+    int    side;      // 0 | 1
+    double value;
+};
+
+struct BcBatchDev {
+    int     n;                                   // entries (both sides of one dim)
+    int     dim;
+    int     nt[2];                               // transverse extents (n_t + 3 points each; 1 when absent)
+    double  spacing;
+    BcEntry e[2 * CHMY_MAX_BATCH_FIELDS];
+};
+
+// One thread per face point; both sides and all fields of a dimension in one launch.  Entries of different sides
+// touch disjoint cells and different fields are independent, so the reference's sequential order
+// (side 1 then 2, fields in batch order) is preserved per cell.
+__global__ void __launch_bounds__(256) k_bc_dim(const BcBatchDev b) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;   // first transverse index  (0..nt0-1)
+    const int c = blockIdx.y;                              // second transverse index (0..nt1-1)
+    if (a >= b.nt[0]) return;
+    for (int q = 0; q < b.n; ++q) {
+        const BcEntry& e = b.e[q];
+        int I[3], N[3];
+        // insert_dim(dim, (a, c), idx)  -- src/utils.jl:47-51
+        int t = 0;
+        const int tr[2] = {a, c};
+        const int bnode = e.side == 0 ? 1 : e.d;
+        const int hnode = e.side == 0 ? 0 : e.d + 1;
+        for (int dd = 0; dd < 3; ++dd) {
+            if (dd == b.dim) { I[dd] = hnode; N[dd] = bnode; }
+            else { I[dd] = N[dd] = (t < 2 ? tr[t] : 0); ++t; }
+        }
+        if (e.kind == CHMY_DIRICHLET) {
+            if (e.vertex) {
+                fv_st(e.f, N[0], N[1], N[2], e.value);
+            } else {
+                const double nb = fv_ld(e.f, N[0], N[1], N[2]);
+                fv_st(e.f, I[0], I[1], I[2], fma(2.0, e.value - nb, nb));
+            }
+        } else {
+            const double qs = e.side == 0 ? -e.value : e.value;
+            fv_st(e.f, I[0], I[1], I[2], fma(b.spacing, qs, fv_ld(e.f, N[0], N[1], N[2])));
+        }
+    }
+}
+
+int chmy_run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_batch_desc* left,
+                    const chmy_batch_desc* right, cudaStream_t st) {
+    BcBatchDev b;
+    memset(&b, 0, sizeof(b));
+    b.dim     = dim;
+    b.spacing = g->spacing[dim];
+    const chmy_batch_desc* sides[2] = {left, right};
+    for (int s = 0; s < 2; ++s) {
+        const chmy_batch_desc* bd = sides[s];
+        if (!bd || bd->kind != CHMY_BATCH_FIELD) continue;
+        CHMY_REQUIRE(bd->nfields >= 0 && bd->nfields <= CHMY_MAX_BATCH_FIELDS, "FieldBatch with %d fields (max %d)",
+                     bd->nfields, CHMY_MAX_BATCH_FIELDS);
+        for (int q = 0; q < bd->nfields; ++q) {
+            const chmy_field* f = bd->fields[q];
+            CHMY_REQUIRE(f != nullptr && f->nd == g->ndims, "FieldBatch: bad field %d", q);
+            CHMY_REQUIRE(bd->bc_kind[q] == CHMY_DIRICHLET || bd->bc_kind[q] == CHMY_NEUMANN, "FieldBatch: bad bc kind");
+            for (int a = 0; a < g->ndims; ++a)
+                CHMY_REQUIRE(f->d[a] == g->n[a] + (f->loc[a] == CHMY_VERTEX ? 1 : 0), "FieldBatch: field/grid size mismatch");
+            BcEntry& e = b.e[b.n++];
+            e.f = f->view(); e.kind = bd->bc_kind[q]; e.vertex = f->loc[dim] == CHMY_VERTEX; e.d = (int)f->d[dim];
+            e.side = s; e.value = bd->value[q];
+        }
+    }
+    if (b.n == 0) return CHMY_OK;
+    int t = 0;
+    b.nt[0] = b.nt[1] = 1;
+    for (int a = 0; a < g->ndims; ++a)
+        if (a != dim) b.nt[t++] = (int)g->n[a] + 3;      // remove_dim(dim, nvertices + 2), batch.jl:181
+    const dim3 blk(128, 1, 1);
+    const dim3 grd((b.nt[0] + 127) / 128, b.nt[1], 1);
+    k_bc_dim<<<grd, blk, 0, st>>>(b);
+    ctx->n_launches++;
+    CHMY_CUDA(cudaGetLastError());
+    return CHMY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- halo slabs
+// send index: side 1 -> 1+overlap, side 2 -> d-overlap (overlap = 1 for Vertex, 0 for Center);
+// recv index: side 1 -> 0, side 2 -> d+1; every other dimension spans the whole padded extent -1..d+2.
+long long chmy_slab_len(const chmy_field* f, int dim) {
+    long long len = 1;
+    for (int a = 0; a < f->nd; ++a)
+        if (a != dim) len *= f->sd[a];
+    return len;
+}
+
+struct SlabEntry {
+    FV        f;
+    int       idx;        // logical index of the slab along dim
+    int       e0, e1;     // transverse extents (sd_t), 1 when absent
+    long long off;        // element offset of this field's slab in the buffer
+};
+struct SlabBatch {
+    int       n, dim, nd;
+    SlabEntry e[CHMY_MAX_BATCH_FIELDS];
+};
+
+template <bool PACK>
+__global__ void __launch_bounds__(256) k_slab(const SlabBatch b, double* __restrict__ buf) {
+    const SlabEntry& e = b.e[blockIdx.z];
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y * blockDim.y + threadIdx.y;
+    if (a >= e.e0 || c >= e.e1) return;
+    int I[3], t = 0;
+    const int tr[2] = {a - 1, c - 1};           // storage 0 <-> logical -1
+    for (int dd = 0; dd < 3; ++dd) {
+        if (dd == b.dim) I[dd] = e.idx;
+        else if (dd >= b.nd) I[dd] = 0;          // inactive dimension
+        else { I[dd] = tr[t]; ++t; }
+    }
+    const long long p = e.off + (long long)a + (long long)c * e.e0;
+    if (PACK) buf[p] = fv_ld(e.f, I[0], I[1], I[2]);
+    else fv_st(e.f, I[0], I[1], I[2], buf[p]);
+}
+
+static int make_slab_batch(int dim, int side, int nf, chmy_field* const* fs, bool send, SlabBatch* out) {
+    CHMY_REQUIRE(nf >= 1 && nf <= CHMY_MAX_BATCH_FIELDS, "exchange with %d fields (max %d)", nf, CHMY_MAX_BATCH_FIELDS);
+    SlabBatch& b = *out;
+    memset(&b, 0, sizeof(b));
+    b.n = nf; b.dim = dim; b.nd = fs[0] ? fs[0]->nd : 0;
+    long long off = 0;
+    for (int q = 0; q < nf; ++q) {
+        const chmy_field* f = fs[q];
+        CHMY_REQUIRE(f != nullptr && dim < f->nd, "exchange: bad field %d", q);
+        const int ov = f->loc[dim] == CHMY_VERTEX ? 1 : 0;
+        SlabEntry& e = b.e[q];
+        e.f   = f->view();
+        e.idx = send ? (side == 0 ? 1 + ov : (int)f->d[dim] - ov) : (side == 0 ? 0 : (int)f->d[dim] + 1);
+        int t = 0, ext[2] = {1, 1};
+        for (int a = 0; a < f->nd; ++a)
+            if (a != dim) ext[t++] = (int)f->sd[a];
+        e.e0 = ext[0]; e.e1 = ext[1];
+        e.off = off;
+        off += chmy_slab_len(f, dim);
+    }
+    return CHMY_OK;
+}
+
+template <bool PACK>
+static int run_slab(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, double* dbuf, cudaStream_t st) {
+    SlabBatch b;
+    for (int q = 0; q < nf; ++q)
+        CHMY_REQUIRE(fs[q] != nullptr && fs[q]->nd >= 2 && fs[q]->nd == fs[0]->nd,
+                     "halo exchange needs fields of equal dimensionality >= 2 on this path");
+    CHMY_TRY(make_slab_batch(dim, side, nf, fs, PACK, &b));
+    int m0 = 1, m1 = 1;
+    for (int q = 0; q < nf; ++q) { m0 = b.e[q].e0 > m0 ? b.e[q].e0 : m0; m1 = b.e[q].e1 > m1 ? b.e[q].e1 : m1; }
+    const dim3 blk(64, m1 > 1 ? 4 : 1, 1);
+    const dim3 grd((m0 + blk.x - 1) / blk.x, (m1 + blk.y - 1) / blk.y, nf);
+    k_slab<PACK><<<grd, blk, 0, st>>>(b, dbuf);
+    ctx->n_launches++;
+    CHMY_CUDA(cudaGetLastError());
+    return CHMY_OK;
+}
+
+int chmy_pack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, double* dbuf, cudaStream_t st) {
+    return run_slab<true>(ctx, dim, side, nf, fs, dbuf, st);
+}
+int chmy_unpack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, const double* dbuf,
+                       cudaStream_t st) {
+    return run_slab<false>(ctx, dim, side, nf, fs, const_cast<double*>(dbuf), st);
+}
+
+// ---------------------------------------------------------------------------------------------- field utilities
+struct FillF {
+    FV f; double v;
+    __device__ void operator()(int i, int j, int k) const { fv_st(f, i, j, k, v); }
+};
+struct CopyF {
+    FV d, s;
+    __device__ void operator()(int i, int j, int k) const { fv_st(d, i, j, k, fv_ld(s, i, j, k)); }
+};
+struct InclF {
+    FV f; InclDev q;
+    __device__ void operator()(int i, int j, int k) const { fv_st(f, i, j, k, incl_eval(q, i, j, k)); }
+};
+
+template <class F>
+__global__ void __launch_bounds__(256) k_box_util(const F f, const Box b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i < b.n[0] && j < b.n[1]) f(b.lo[0] + i, b.lo[1] + j, b.lo[2] + k);
+}
+
+template <class F>
+static int launch_util(chmy_ctx* ctx, const F& f, const Box& b, cudaStream_t st) {
+    if (b.n[0] <= 0 || b.n[1] <= 0 || b.n[2] <= 0) return CHMY_OK;
+    const dim3 blk(64, b.n[1] > 1 ? 4 : 1, 1);
+    k_box_util<F><<<grid_for(b, blk), blk, 0, st>>>(f, b);
+    ctx->n_launches++;
+    CHMY_CUDA(cudaGetLastError());
+    return CHMY_OK;
+}
+
+int chmy_box_from(const chmy_field* f, const int64_t* lo, const int64_t* hi, Box* out) {
+    for (int a = 0; a < 3; ++a) {
+        if (a < f->nd) {
+            CHMY_REQUIRE(lo[a] >= -1 && hi[a] <= f->d[a] + 2, "box [%lld,%lld] outside the padded field along dim %d",
+                         (long long)lo[a], (long long)hi[a], a + 1);
+            out->lo[a] = (int)lo[a];
+            out->n[a]  = (int)(hi[a] - lo[a] + 1);
+        } else {
+            out->lo[a] = 0;
+            out->n[a]  = 1;
+        }
+    }
+    return CHMY_OK;
+}
+
+int chmy_fill_box(chmy_ctx* ctx, chmy_field* f, double v, const Box& b, cudaStream_t st) {
+    return launch_util(ctx, FillF{f->view(), v}, b, st);
+}
+int chmy_copy_box(chmy_ctx* ctx, chmy_field* d, const chmy_field* s, const Box& b, cudaStream_t st) {
+    return launch_util(ctx, CopyF{d->view(), s->view()}, b, st);
+}
+int chmy_incl_box(chmy_ctx* ctx, chmy_field* f, const InclDev& q, const Box& b, cudaStream_t st) {
+    return launch_util(ctx, InclF{f->view(), q}, b, st);
+}
+
+// ---------------------------------------------------------------------------------------------- max |f|
+// maximum(abs.(interior(f))): exact and order-independent.  |x| is compared through its bit pattern as an unsigned
+// integer (monotone for non-negative doubles; NaN patterns compare above +Inf, so a NaN propagates as in Julia).
+__global__ void __launch_bounds__(256) k_maxabs(const FV f, const Box b, unsigned long long* __restrict__ out) {
+    unsigned long long m = 0ull;
+    const long long rows   = (long long)b.n[1] * b.n[2];
+    const int       lane   = threadIdx.x & 31;
+    const int       warp   = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int       nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < rows; r += nwarps) {
+        const int j = b.lo[1] + (int)(r % b.n[1]);
+        const int k = b.lo[2] + (int)(r / b.n[1]);
+        for (int i = lane; i < b.n[0]; i += 32) {
+            const unsigned long long v = (unsigned long long)__double_as_longlong(fabs(fv_ld(f, b.lo[0] + i, j, k)));
+            m = v > m ? v : m;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long v = __shfl_xor_sync(0xffffffffu, m, o);
+        m = v > m ? v : m;
+    }
+    __shared__ unsigned long long sm[8];
+    if (lane == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        m = sm[threadIdx.x];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const unsigned long long v = __shfl_xor_sync(0xffu, m, o);
+            m = v > m ? v : m;
+        }
+        if (threadIdx.x == 0) atomicMax(out, m);
+    }
+}
+
+int chmy_maxabs_box(chmy_ctx* ctx, const chmy_field* f, const Box& b, unsigned long long* d_out, cudaStream_t st) {
+    const long long rows = (long long)b.n[1] * b.n[2];
+    long long want = (rows + 7) / 8;                        // 8 warps per block, one row per warp per pass
+    const long long cap = (long long)ctx->sm_count * 8;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    k_maxabs<<<(unsigned)want, 256, 0, st>>>(f->view(), b, d_out);
+    ctx->n_launches++;
+    CHMY_CUDA(cudaGetLastError());
+    return CHMY_OK;
+}

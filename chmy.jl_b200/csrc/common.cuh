@@ -1,0 +1,144 @@
+// common.cuh -- internal types shared by the translation units of libchmy_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/chmy_b200.h"
+
+// ---------------------------------------------------------------------------------------------- errors
+void chmy_set_error(const char* fmt, ...);
+
+#define CHMY_CUDA(call)                                                                               \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            chmy_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__,    \
+                           cudaGetErrorString(_e));                                                   \
+            return CHMY_ERR_CUDA;                                                                     \
+        }                                                                                             \
+    } while (0)
+
+#define CHMY_REQUIRE(cond, ...)                                                                       \
+    do {                                                                                              \
+        if (!(cond)) {                                                                                \
+            chmy_set_error(__VA_ARGS__);                                                              \
+            return CHMY_ERR_ARG;                                                                      \
+        }                                                                                             \
+    } while (0)
+
+#define CHMY_TRY(expr)                                                                                \
+    do {                                                                                              \
+        int _s = (expr);                                                                              \
+        if (_s != CHMY_OK) return _s;                                                                 \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------- device views
+
+// View of a Field on the device.  p addresses logical index 0 of every active dimension
+// (reference indexing: f[I] = data[I + 2H], src/Fields/field.jl:18); x stride is 1.
+struct FV {
+    double* __restrict__ p;
+    long long sy, sz;   // element strides of dims 2 and 3 (0 when inactive)
+};
+
+__device__ __forceinline__ double fv_ld(const FV& f, int i, int j, int k) {
+    return f.p[(long long)i + (long long)j * f.sy + (long long)k * f.sz];
+}
+__device__ __forceinline__ void fv_st(const FV& f, int i, int j, int k, double v) {
+    f.p[(long long)i + (long long)j * f.sy + (long long)k * f.sz] = v;
+}
+
+struct Box {
+    int lo[3];
+    int n[3];   // extents (>= 1 for inactive dims)
+};
+
+// FunctionField `init_incl` evaluated in-kernel (function_field.jl:49-59; uniform_axis.jl:18-19).
+struct InclDev {
+    int    active;
+    int    nd;
+    int    loc[3];
+    double origin[3], spacing[3], c0[3];
+    double r2, in, out;
+};
+
+__device__ __forceinline__ double coord_dev(double origin, double spacing, int loc, int i) {
+    const double im1 = (double)(i - 1);
+    return loc == CHMY_VERTEX ? fma(im1, spacing, origin) : fma(im1, spacing, fma(0.5, spacing, origin));
+}
+
+__device__ __forceinline__ double incl_eval(const InclDev& q, int i, int j, int k) {
+    const int I[3] = {i, j, k};
+    double s = 0.0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (d < q.nd) {
+            const double c  = coord_dev(q.origin[d], q.spacing[d], q.loc[d], I[d]) - q.c0[d];
+            const double c2 = c * c;
+            s = (d == 0) ? c2 : s + c2;
+        }
+    }
+    return s < q.r2 ? q.in : q.out;
+}
+
+// ---------------------------------------------------------------------------------------------- host objects
+
+struct chmy_field {
+    chmy_ctx* ctx;
+    int       nd;
+    int       layout;
+    int       loc[3];
+    long long d[3];        // logical dims (1 for inactive)
+    long long sd[3];       // logical storage dims d+4 (1 for inactive)
+    long long stride[3];   // element strides (stride[0] = 1)
+    long long lead;        // elements between the allocation base and storage element (-1,-1,-1)
+    double*   alloc;       // cudaMalloc'ed base
+    size_t    bytes;
+    double*   p0;          // address of logical (0,0,0) over active dims
+
+    FV view() const { return FV{p0, nd > 1 ? stride[1] : 0, nd > 2 ? stride[2] : 0}; }
+    double* at(long long i, long long j, long long k) const {
+        return p0 + i + (nd > 1 ? j * stride[1] : 0) + (nd > 2 ? k * stride[2] : 0);
+    }
+};
+
+struct chmy_comm;   // comm.cu
+
+struct chmy_ctx {
+    int          device;        // 0-based CUDA ordinal
+    cudaStream_t s_main;        // inner-domain work
+    cudaStream_t s_bnd;         // boundary slabs, BC, pack/exchange/unpack (highest priority)
+    cudaEvent_t  ev_fork, ev_join;
+    unsigned long long* d_red;  // device scratch for reductions (8 slots)
+    unsigned long long* h_red;  // pinned host mirror
+    double*      h_stage;       // pinned staging for small host transfers
+    size_t       h_stage_bytes;
+    uint64_t     n_launches;
+    int          sm_count;
+    chmy_comm*   comm;          // null on a single-device architecture
+    cudaEvent_t* ev_time;       // lazily created timing events (CHMY_MAX_EVENTS slots)
+};
+
+static inline dim3 grid_for(const Box& b, dim3 blk) {
+    return dim3((unsigned)((b.n[0] + blk.x - 1) / blk.x), (unsigned)((b.n[1] + blk.y - 1) / blk.y),
+                (unsigned)((b.n[2] + blk.z - 1) / blk.z));
+}
+
+// ops.cu
+int chmy_run_op(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st);
+int chmy_validate_op(const chmy_launch_desc* d);
+// bc.cu
+int chmy_run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_batch_desc* left,
+                    const chmy_batch_desc* right, cudaStream_t st);
+// comm.cu
+int chmy_comm_destroy(chmy_comm* c);
+int chmy_exchange_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_batch_desc* left,
+                      const chmy_batch_desc* right, cudaStream_t st);
+// halo.cu
+int chmy_pack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, double* dbuf, cudaStream_t st);
+int chmy_unpack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, const double* dbuf,
+                       cudaStream_t st);
+long long chmy_slab_len(const chmy_field* f, int dim);

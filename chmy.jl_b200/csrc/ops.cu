@@ -1,0 +1,415 @@
+// ops.cu -- the staggered-grid stencil kernels that `launch` runs (sm_100a).
+//
+// Arithmetic contract (DESIGN.md "Exact arithmetic"): every + - * / is one IEEE binary64 operation in the order the
+// reference's Julia source evaluates it; this file is compiled with -fmad=false so nvcc never contracts a*b+c.
+// fma() appears only where the reference writes muladd.  Formulas are the flattened forms of
+//   examples/diffusion_2d.jl:8-19, examples/stokes_2d_inc_ve_T.jl:11-60, examples/stokes_3d_inc_ve_T.jl:11-77
+// with the operator definitions of src/GridOperators/{GridOperators.jl:23-36,partial_derivatives.jl:2-5,
+// field_operators.jl:50-59}:   Vertex along d: left=f[I], right=f[I+e_d];  Center along d: left=f[I-e_d], right=f[I];
+// d_d f = (right-left)*inv_spacing_d;  n-ary + folds left.
+//
+// This translation unit holds the *generic* one-thread-per-cell kernels (any box, any layout); the tuned
+// z-marching / vectorised kernels for the headline configs live in ops_fast.cu and are selected in chmy_run_op.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------- generic box kernel
+template <class F>
+__global__ void __launch_bounds__(256) k_box(const F f, const Box b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i < b.n[0] && j < b.n[1]) f(b.lo[0] + i, b.lo[1] + j, b.lo[2] + k);
+}
+
+template <class F>
+static int launch_box(chmy_ctx* ctx, const F& f, const Box& b, cudaStream_t st) {
+    if (b.n[0] <= 0 || b.n[1] <= 0 || b.n[2] <= 0) return CHMY_OK;
+    const dim3 blk(64, b.n[1] > 1 ? 4 : 1, 1);
+    const dim3 grd = grid_for(b, blk);
+    k_box<F><<<grd, blk, 0, st>>>(f, b);
+    ctx->n_launches++;
+    CHMY_CUDA(cudaGetLastError());
+    return CHMY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- diffusion
+// examples/diffusion_2d.jl:8-13   q.x=(V,C) q.y=(C,V) C=(C,C)
+struct ComputeQ {
+    FV qx, qy, C;
+    double chi, idx, idy;
+    __device__ void operator()(int i, int j, int k) const {
+        const double c = fv_ld(C, i, j, k);
+        fv_st(qx, i, j, k, (-chi) * ((c - fv_ld(C, i - 1, j, k)) * idx));
+        fv_st(qy, i, j, k, (-chi) * ((c - fv_ld(C, i, j - 1, k)) * idy));
+    }
+};
+
+// examples/diffusion_2d.jl:15-19   C -= dt * (dx(q.x) + dy(q.y))
+struct UpdateC {
+    FV C, qx, qy;
+    double dt, idx, idy;
+    __device__ void operator()(int i, int j, int k) const {
+        const double dv = (fv_ld(qx, i + 1, j, k) - fv_ld(qx, i, j, k)) * idx +
+                          (fv_ld(qy, i, j + 1, k) - fv_ld(qy, i, j, k)) * idy;
+        fv_st(C, i, j, k, fv_ld(C, i, j, k) - dt * dv);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- update_old
+// stokes_3d_inc_ve_T.jl:11-21 / stokes_2d_inc_ve_T.jl:11-18 : same index I for every pair
+template <int NP>
+struct UpdateOld {
+    FV dst[NP], src[NP];
+    __device__ void operator()(int i, int j, int k) const {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) fv_st(dst[p], i, j, k, fv_ld(src[p], i, j, k));
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- stress
+__device__ __forceinline__ double stress_res(double t, double to, double e2, double Gdt, double eta) {
+    // r = -(tau - tau_old)/(G*dt) - tau/eta + 2.0*e      (stokes_3d_inc_ve_T.jl:34-39)
+    return ((-(t - to)) / Gdt - t / eta) + e2;
+}
+
+// stokes_2d_inc_ve_T.jl:20-34   tau.xy=(V,V), V.x=(V,C), V.y=(C,V)
+struct Stress2 {
+    FV txx, tyy, txy, Pr, dV, Vx, Vy, oxx, oyy, oxy;
+    double idx, idy, eta, eta_ve, Gdt, dtau_Pr, dtau_r;
+    __device__ void operator()(int i, int j, int k) const {
+        const double vx = fv_ld(Vx, i, j, k), vy = fv_ld(Vy, i, j, k);
+        const double exx = (fv_ld(Vx, i + 1, j, k) - vx) * idx;
+        const double eyy = (fv_ld(Vy, i, j + 1, k) - vy) * idy;
+        const double exy = 0.5 * ((vx - fv_ld(Vx, i, j - 1, k)) * idy + (vy - fv_ld(Vy, i - 1, j, k)) * idx);
+        const double dv  = exx + eyy;
+        fv_st(dV, i, j, k, dv);
+        fv_st(Pr, i, j, k, fv_ld(Pr, i, j, k) - (dv * eta_ve) * dtau_Pr);
+        const double dv3 = dv / 3.0;
+        const double a = fv_ld(txx, i, j, k), b = fv_ld(tyy, i, j, k), c = fv_ld(txy, i, j, k);
+        const double rxx = stress_res(a, fv_ld(oxx, i, j, k), 2.0 * (exx - dv3), Gdt, eta);
+        const double ryy = stress_res(b, fv_ld(oyy, i, j, k), 2.0 * (eyy - dv3), Gdt, eta);
+        const double rxy = stress_res(c, fv_ld(oxy, i, j, k), 2.0 * exy, Gdt, eta);
+        fv_st(txx, i, j, k, a + (rxx * eta_ve) * dtau_r);
+        fv_st(tyy, i, j, k, b + (ryy * eta_ve) * dtau_r);
+        fv_st(txy, i, j, k, c + (rxy * eta_ve) * dtau_r);
+    }
+};
+
+// stokes_3d_inc_ve_T.jl:23-46
+struct Stress3 {
+    FV t[6], Pr, dV, Vx, Vy, Vz, o[6];   // xx yy zz xy xz yz
+    double idx, idy, idz, eta, eta_ve, Gdt, dtau_Pr, dtau_r;
+    __device__ void operator()(int i, int j, int k) const {
+        const double vx = fv_ld(Vx, i, j, k), vy = fv_ld(Vy, i, j, k), vz = fv_ld(Vz, i, j, k);
+        const double exx = (fv_ld(Vx, i + 1, j, k) - vx) * idx;
+        const double eyy = (fv_ld(Vy, i, j + 1, k) - vy) * idy;
+        const double ezz = (fv_ld(Vz, i, j, k + 1) - vz) * idz;
+        const double exy = 0.5 * ((vx - fv_ld(Vx, i, j - 1, k)) * idy + (vy - fv_ld(Vy, i - 1, j, k)) * idx);
+        const double exz = 0.5 * ((vx - fv_ld(Vx, i, j, k - 1)) * idz + (vz - fv_ld(Vz, i - 1, j, k)) * idx);
+        const double eyz = 0.5 * ((vy - fv_ld(Vy, i, j, k - 1)) * idz + (vz - fv_ld(Vz, i, j - 1, k)) * idy);
+        const double dv  = (exx + eyy) + ezz;
+        fv_st(dV, i, j, k, dv);
+        fv_st(Pr, i, j, k, fv_ld(Pr, i, j, k) - (dv * eta_ve) * dtau_Pr);
+        const double dv3 = dv / 3.0;
+        const double e2[6] = {2.0 * (exx - dv3), 2.0 * (eyy - dv3), 2.0 * (ezz - dv3), 2.0 * exy, 2.0 * exz, 2.0 * eyz};
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const double a = fv_ld(t[c], i, j, k);
+            const double r = stress_res(a, fv_ld(o[c], i, j, k), e2[c], Gdt, eta);
+            fv_st(t[c], i, j, k, a + (r * eta_ve) * dtau_r);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- velocity
+// stokes_2d_inc_ve_T.jl:36-43
+struct Velocity2 {
+    FV Vx, Vy, rx, ry, Pr, txx, tyy, txy, rho;
+    InclDev inc;
+    double idx, idy, eta_ve, nudtau;
+    __device__ void operator()(int i, int j, int k) const {
+        const double p = fv_ld(Pr, i, j, k), sxy = fv_ld(txy, i, j, k);
+        const double rvx = ((-((p - fv_ld(Pr, i - 1, j, k)) * idx)) + (fv_ld(txx, i, j, k) - fv_ld(txx, i - 1, j, k)) * idx) +
+                           (fv_ld(txy, i, j + 1, k) - sxy) * idy;
+        const double rg  = inc.active ? incl_eval(inc, i, j, k) : fv_ld(rho, i, j, k);
+        const double rvy = (((-((p - fv_ld(Pr, i, j - 1, k)) * idy)) + (fv_ld(tyy, i, j, k) - fv_ld(tyy, i, j - 1, k)) * idy) +
+                            (fv_ld(txy, i + 1, j, k) - sxy) * idx) - rg;
+        fv_st(rx, i, j, k, rvx);
+        fv_st(ry, i, j, k, rvy);
+        fv_st(Vx, i, j, k, fv_ld(Vx, i, j, k) + (rvx * nudtau) / eta_ve);
+        fv_st(Vy, i, j, k, fv_ld(Vy, i, j, k) + (rvy * nudtau) / eta_ve);
+    }
+};
+
+// stokes_3d_inc_ve_T.jl:48-57
+struct Velocity3 {
+    FV Vx, Vy, Vz, rx, ry, rz, Pr, t[6], rho;   // t: xx yy zz xy xz yz
+    InclDev inc;
+    double idx, idy, idz, eta_ve, nudtau;
+    __device__ void operator()(int i, int j, int k) const {
+        const double p = fv_ld(Pr, i, j, k);
+        const double sxy = fv_ld(t[3], i, j, k), sxz = fv_ld(t[4], i, j, k), syz = fv_ld(t[5], i, j, k);
+        const double rvx = (((-((p - fv_ld(Pr, i - 1, j, k)) * idx)) + (fv_ld(t[0], i, j, k) - fv_ld(t[0], i - 1, j, k)) * idx) +
+                            (fv_ld(t[3], i, j + 1, k) - sxy) * idy) + (fv_ld(t[4], i, j, k + 1) - sxz) * idz;
+        const double rvy = (((-((p - fv_ld(Pr, i, j - 1, k)) * idy)) + (fv_ld(t[1], i, j, k) - fv_ld(t[1], i, j - 1, k)) * idy) +
+                            (fv_ld(t[3], i + 1, j, k) - sxy) * idx) + (fv_ld(t[5], i, j, k + 1) - syz) * idz;
+        const double rg  = inc.active ? incl_eval(inc, i, j, k) : fv_ld(rho, i, j, k);
+        const double rvz = ((((-((p - fv_ld(Pr, i, j, k - 1)) * idz)) + (fv_ld(t[2], i, j, k) - fv_ld(t[2], i, j, k - 1)) * idz) +
+                             (fv_ld(t[4], i + 1, j, k) - sxz) * idx) + (fv_ld(t[5], i, j + 1, k) - syz) * idy) - rg;
+        fv_st(rx, i, j, k, rvx);
+        fv_st(ry, i, j, k, rvy);
+        fv_st(rz, i, j, k, rvz);
+        fv_st(Vx, i, j, k, fv_ld(Vx, i, j, k) + (rvx * nudtau) / eta_ve);
+        fv_st(Vy, i, j, k, fv_ld(Vy, i, j, k) + (rvy * nudtau) / eta_ve);
+        fv_st(Vz, i, j, k, fv_ld(Vz, i, j, k) + (rvz * nudtau) / eta_ve);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- thermal
+// Julia Base.max/min on Float64 (NaN-propagating, max(-0.0,+0.0) = +0.0)
+__device__ __forceinline__ double jl_max0(double v) {
+    return (v != v) ? v : fmax(v, 0.0);
+}
+__device__ __forceinline__ double jl_min0(double v) {
+    return (v != v) ? v : fmin(v, 0.0);
+}
+
+// stokes_3d_inc_ve_T.jl:59-71 (2D: stokes_2d_inc_ve_T.jl:45-54)
+template <int ND>
+struct ThermalFlux {
+    FV q[3], T, V[3];
+    double lam, id[3];
+    __device__ void operator()(int i, int j, int k) const {
+        const double t = fv_ld(T, i, j, k);
+        const double tm[3] = {fv_ld(T, i - 1, j, k), fv_ld(T, i, j - 1, k), ND > 2 ? fv_ld(T, i, j, k - 1) : 0.0};
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const double v = fv_ld(V[d], i, j, k);
+            fv_st(q[d], i, j, k, ((-lam) * ((t - tm[d]) * id[d]) + jl_max0(v) * tm[d]) + jl_min0(v) * t);
+        }
+    }
+};
+
+// stokes_3d_inc_ve_T.jl:73-77
+template <int ND>
+struct Thermal {
+    FV T, To, q[3];
+    double dt, id[3];
+    __device__ void operator()(int i, int j, int k) const {
+        double dv = (fv_ld(q[0], i + 1, j, k) - fv_ld(q[0], i, j, k)) * id[0] +
+                    (fv_ld(q[1], i, j + 1, k) - fv_ld(q[1], i, j, k)) * id[1];
+        if (ND > 2) dv = dv + (fv_ld(q[2], i, j, k + 1) - fv_ld(q[2], i, j, k)) * id[2];
+        fv_st(T, i, j, k, fv_ld(To, i, j, k) - dt * dv);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- dispatch
+static int expect_fields(const chmy_launch_desc* d, int nf, int ns, int allow_null_last) {
+    CHMY_REQUIRE(d->nfields == nf, "op %d expects %d fields, got %d", d->op, nf, d->nfields);
+    CHMY_REQUIRE(d->nscalars == ns, "op %d expects %d scalars, got %d", d->op, ns, d->nscalars);
+    for (int i = 0; i < nf; ++i) {
+        if (d->fields[i] == nullptr) {
+            CHMY_REQUIRE(allow_null_last && i == nf - 1, "op %d: field %d is NULL", d->op, i);
+            continue;
+        }
+        CHMY_REQUIRE(d->fields[i]->nd == d->grid.ndims, "op %d: field %d has %d dims, grid has %d", d->op, i,
+                     d->fields[i]->nd, d->grid.ndims);
+    }
+    return CHMY_OK;
+}
+
+static int expect_loc(const chmy_launch_desc* d, int idx, int lx, int ly, int lz) {
+    const chmy_field* f = d->fields[idx];
+    const int want[3] = {lx, ly, lz};
+    for (int a = 0; a < d->grid.ndims; ++a) {
+        CHMY_REQUIRE(f->loc[a] == want[a], "op %d: field %d has the wrong staggered location along dim %d", d->op, idx, a + 1);
+        CHMY_REQUIRE(f->d[a] == d->grid.n[a] + (want[a] == CHMY_VERTEX ? 1 : 0),
+                     "op %d: field %d size %lld along dim %d does not match the grid", d->op, idx, f->d[a], a + 1);
+    }
+    return CHMY_OK;
+}
+
+enum { C_ = CHMY_CENTER, V_ = CHMY_VERTEX };
+
+// location tables: tensor components xx yy [zz] xy [xz yz]; vector components
+static const int TLOC3[6][3] = {{C_, C_, C_}, {C_, C_, C_}, {C_, C_, C_}, {V_, V_, C_}, {V_, C_, V_}, {C_, V_, V_}};
+static const int TLOC2[3][3] = {{C_, C_, C_}, {C_, C_, C_}, {V_, V_, C_}};
+static const int VLOC[3][3]  = {{V_, C_, C_}, {C_, V_, C_}, {C_, C_, V_}};
+
+static int expect_tensor(const chmy_launch_desc* d, int first, int nd) {
+    const int nt = nd == 2 ? 3 : 6;
+    for (int c = 0; c < nt; ++c) {
+        const int* L = nd == 2 ? TLOC2[c] : TLOC3[c];
+        CHMY_TRY(expect_loc(d, first + c, L[0], L[1], L[2]));
+    }
+    return CHMY_OK;
+}
+static int expect_vector(const chmy_launch_desc* d, int first, int nd) {
+    for (int c = 0; c < nd; ++c) CHMY_TRY(expect_loc(d, first + c, VLOC[c][0], VLOC[c][1], VLOC[c][2]));
+    return CHMY_OK;
+}
+
+int chmy_validate_op(const chmy_launch_desc* d) {
+    const int nd = d->grid.ndims;
+    const int nt = nd == 2 ? 3 : 6;
+    switch (d->op) {
+    case CHMY_OP_NONE: return CHMY_OK;
+    case CHMY_OP_COMPUTE_Q:
+        CHMY_REQUIRE(nd == 2, "compute_q! is defined for 2D grids");
+        CHMY_TRY(expect_fields(d, 3, 1, 0));
+        CHMY_TRY(expect_vector(d, 0, 2));
+        return expect_loc(d, 2, C_, C_, C_);
+    case CHMY_OP_UPDATE_C:
+        CHMY_REQUIRE(nd == 2, "update_C! is defined for 2D grids");
+        CHMY_TRY(expect_fields(d, 3, 1, 0));
+        CHMY_TRY(expect_loc(d, 0, C_, C_, C_));
+        return expect_vector(d, 1, 2);
+    case CHMY_OP_UPDATE_OLD:
+        CHMY_REQUIRE(nd == 2 || nd == 3, "update_old! is defined for 2D and 3D grids");
+        CHMY_TRY(expect_fields(d, 2 * (1 + nt), 0, 0));
+        CHMY_TRY(expect_loc(d, 0, C_, C_, C_));
+        CHMY_TRY(expect_tensor(d, 1, nd));
+        CHMY_TRY(expect_loc(d, 1 + nt, C_, C_, C_));
+        return expect_tensor(d, 2 + nt, nd);
+    case CHMY_OP_UPDATE_STRESS:
+        CHMY_REQUIRE(nd == 2 || nd == 3, "update_stress! is defined for 2D and 3D grids");
+        CHMY_TRY(expect_fields(d, 2 * nt + 2 + nd, 6, 0));
+        CHMY_TRY(expect_tensor(d, 0, nd));
+        CHMY_TRY(expect_loc(d, nt, C_, C_, C_));
+        CHMY_TRY(expect_loc(d, nt + 1, C_, C_, C_));
+        CHMY_TRY(expect_vector(d, nt + 2, nd));
+        return expect_tensor(d, nt + 2 + nd, nd);
+    case CHMY_OP_UPDATE_VELOCITY:
+        CHMY_REQUIRE(nd == 2 || nd == 3, "update_velocity! is defined for 2D and 3D grids");
+        CHMY_TRY(expect_fields(d, 2 * nd + 1 + nt + 1, 2, 1));
+        CHMY_TRY(expect_vector(d, 0, nd));
+        CHMY_TRY(expect_vector(d, nd, nd));
+        CHMY_TRY(expect_loc(d, 2 * nd, C_, C_, C_));
+        CHMY_TRY(expect_tensor(d, 2 * nd + 1, nd));
+        if (d->fields[2 * nd + 1 + nt] != nullptr) {
+            CHMY_REQUIRE(!d->rho_g.active, "update_velocity!: give rho_g either as a field or as a FunctionField");
+            return expect_loc(d, 2 * nd + 1 + nt, VLOC[nd - 1][0], VLOC[nd - 1][1], VLOC[nd - 1][2]);
+        }
+        CHMY_REQUIRE(d->rho_g.active, "update_velocity!: rho_g missing");
+        for (int a = 0; a < nd; ++a)
+            CHMY_REQUIRE(d->rho_g.loc[a] == VLOC[nd - 1][a], "update_velocity!: rho_g FunctionField location mismatch");
+        return CHMY_OK;
+    case CHMY_OP_UPDATE_THERMAL_FLUX:
+        CHMY_REQUIRE(nd == 2 || nd == 3, "update_thermal_flux! is defined for 2D and 3D grids");
+        CHMY_TRY(expect_fields(d, 2 * nd + 1, 1, 0));
+        CHMY_TRY(expect_vector(d, 0, nd));
+        CHMY_TRY(expect_loc(d, nd, C_, C_, C_));
+        return expect_vector(d, nd + 1, nd);
+    case CHMY_OP_UPDATE_THERMAL:
+        CHMY_REQUIRE(nd == 2 || nd == 3, "update_thermal! is defined for 2D and 3D grids");
+        CHMY_TRY(expect_fields(d, 2 + nd, 1, 0));
+        CHMY_TRY(expect_loc(d, 0, C_, C_, C_));
+        CHMY_TRY(expect_loc(d, 1, C_, C_, C_));
+        return expect_vector(d, 2, nd);
+    default: chmy_set_error("unknown op id %d", d->op); return CHMY_ERR_ARG;
+    }
+}
+
+static InclDev make_incl(const chmy_launch_desc* d) {
+    InclDev q;
+    memset(&q, 0, sizeof(q));
+    q.active = d->rho_g.active;
+    q.nd     = d->grid.ndims;
+    for (int a = 0; a < 3; ++a) {
+        q.loc[a]     = d->rho_g.loc[a];
+        q.origin[a]  = d->grid.origin[a];
+        q.spacing[a] = d->grid.spacing[a];
+        q.c0[a]      = d->rho_g.c0[a];
+    }
+    q.r2  = d->rho_g.r * d->rho_g.r;   // r^2 -> r*r (Base.literal_pow)
+    q.in  = d->rho_g.in;
+    q.out = d->rho_g.out;
+    return q;
+}
+
+int chmy_run_op_generic(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st) {
+    const int nd = d->grid.ndims;
+    const int nt = nd == 2 ? 3 : 6;
+    const double* id = d->grid.inv_spacing;
+    const double* s  = d->scalars;
+    chmy_field* const* F = d->fields;
+    switch (d->op) {
+    case CHMY_OP_COMPUTE_Q: {
+        ComputeQ f{F[0]->view(), F[1]->view(), F[2]->view(), s[0], id[0], id[1]};
+        return launch_box(ctx, f, box, st);
+    }
+    case CHMY_OP_UPDATE_C: {
+        UpdateC f{F[0]->view(), F[1]->view(), F[2]->view(), s[0], id[0], id[1]};
+        return launch_box(ctx, f, box, st);
+    }
+    case CHMY_OP_UPDATE_OLD: {
+        if (nd == 2) {
+            UpdateOld<4> f;
+            for (int p = 0; p < 4; ++p) { f.src[p] = F[p]->view(); f.dst[p] = F[4 + p]->view(); }
+            return launch_box(ctx, f, box, st);
+        }
+        UpdateOld<7> f;
+        for (int p = 0; p < 7; ++p) { f.src[p] = F[p]->view(); f.dst[p] = F[7 + p]->view(); }
+        return launch_box(ctx, f, box, st);
+    }
+    case CHMY_OP_UPDATE_STRESS: {
+        const double Gdt = s[2] * s[3];   // G*dt evaluated once per cell in the reference; same value
+        if (nd == 2) {
+            Stress2 f{F[0]->view(), F[1]->view(), F[2]->view(), F[3]->view(), F[4]->view(), F[5]->view(), F[6]->view(),
+                      F[7]->view(), F[8]->view(), F[9]->view(), id[0], id[1], s[0], s[1], Gdt, s[4], s[5]};
+            return launch_box(ctx, f, box, st);
+        }
+        Stress3 f;
+        for (int c = 0; c < 6; ++c) { f.t[c] = F[c]->view(); f.o[c] = F[11 + c]->view(); }
+        f.Pr = F[6]->view(); f.dV = F[7]->view();
+        f.Vx = F[8]->view(); f.Vy = F[9]->view(); f.Vz = F[10]->view();
+        f.idx = id[0]; f.idy = id[1]; f.idz = id[2];
+        f.eta = s[0]; f.eta_ve = s[1]; f.Gdt = Gdt; f.dtau_Pr = s[4]; f.dtau_r = s[5];
+        return launch_box(ctx, f, box, st);
+    }
+    case CHMY_OP_UPDATE_VELOCITY: {
+        const chmy_field* rho = F[2 * nd + 1 + nt];
+        const FV rv = rho ? rho->view() : FV{nullptr, 0, 0};
+        if (nd == 2) {
+            Velocity2 f{F[0]->view(), F[1]->view(), F[2]->view(), F[3]->view(), F[4]->view(), F[5]->view(),
+                        F[6]->view(), F[7]->view(), rv, make_incl(d), id[0], id[1], s[0], s[1]};
+            return launch_box(ctx, f, box, st);
+        }
+        Velocity3 f;
+        f.Vx = F[0]->view(); f.Vy = F[1]->view(); f.Vz = F[2]->view();
+        f.rx = F[3]->view(); f.ry = F[4]->view(); f.rz = F[5]->view();
+        f.Pr = F[6]->view();
+        for (int c = 0; c < 6; ++c) f.t[c] = F[7 + c]->view();
+        f.rho = rv; f.inc = make_incl(d);
+        f.idx = id[0]; f.idy = id[1]; f.idz = id[2]; f.eta_ve = s[0]; f.nudtau = s[1];
+        return launch_box(ctx, f, box, st);
+    }
+    case CHMY_OP_UPDATE_THERMAL_FLUX: {
+        if (nd == 2) {
+            ThermalFlux<2> f;
+            for (int c = 0; c < 2; ++c) { f.q[c] = F[c]->view(); f.V[c] = F[3 + c]->view(); f.id[c] = id[c]; }
+            f.T = F[2]->view(); f.lam = s[0];
+            return launch_box(ctx, f, box, st);
+        }
+        ThermalFlux<3> f;
+        for (int c = 0; c < 3; ++c) { f.q[c] = F[c]->view(); f.V[c] = F[4 + c]->view(); f.id[c] = id[c]; }
+        f.T = F[3]->view(); f.lam = s[0];
+        return launch_box(ctx, f, box, st);
+    }
+    case CHMY_OP_UPDATE_THERMAL: {
+        if (nd == 2) {
+            Thermal<2> f;
+            f.T = F[0]->view(); f.To = F[1]->view();
+            for (int c = 0; c < 2; ++c) { f.q[c] = F[2 + c]->view(); f.id[c] = id[c]; }
+            f.dt = s[0];
+            return launch_box(ctx, f, box, st);
+        }
+        Thermal<3> f;
+        f.T = F[0]->view(); f.To = F[1]->view();
+        for (int c = 0; c < 3; ++c) { f.q[c] = F[2 + c]->view(); f.id[c] = id[c]; }
+        f.dt = s[0];
+        return launch_box(ctx, f, box, st);
+    }
+    default: chmy_set_error("unknown op id %d", d->op); return CHMY_ERR_ARG;
+    }
+}

@@ -1,0 +1,248 @@
+"""
+Fields: padded device storage owned by the C ABI + the host-visible accessors of the reference.
+Mirrors src/Fields/{field.jl:6-209, function_field.jl:12-65}.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .grids import Center, Location, StructuredGrid, Vertex, expand_loc
+
+
+class AbstractField:
+    pass
+
+
+class Field(AbstractField):
+    """Field(backend|arch, grid, loc; halo=1) -- field.jl:56-74.  Storage is allocated (zero-filled) by
+    chmy_field_create; logical indexing follows field.jl:18-22."""
+
+    def __init__(self, arch, grid: StructuredGrid, loc=None, *, halo: int = 1, layout: int = L.LAYOUT_PITCHED):
+        if halo != 1:
+            raise NotImplementedError("this path implements the default halo=1 of the reference")
+        loc = Center() if loc is None else loc
+        self.arch = arch
+        self.grid = grid
+        self.loc = expand_loc(grid.ndims(), loc)
+        self.dims = grid.size(self.loc)
+        nd = len(self.dims)
+        h = C.c_void_p()
+        L.check(L.lib().chmy_field_create(arch.ctx, nd, L.i64x3(self.dims, 1), L.i32x3([l.code for l in self.loc]),
+                                          layout, C.byref(h)))
+        self._h = h
+
+    # ------------------------------------------------------------------ handles
+    @property
+    def handle(self):
+        if self._h is None:
+            raise L.ChmyError("field was freed")
+        return self._h
+
+    def info(self) -> L.FieldInfo:
+        fi = L.FieldInfo()
+        L.check(L.lib().chmy_field_get_info(self.handle, C.byref(fi)))
+        return fi
+
+    def free(self):
+        if getattr(self, "_h", None) is not None:
+            L.lib().chmy_field_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ AbstractArray-ish interface
+    def size(self):
+        return self.dims
+
+    def ndims(self):
+        return len(self.dims)
+
+    def _box(self, pad: int):
+        lo = [1 - pad] * self.ndims()
+        hi = [d + pad for d in self.dims]
+        return lo, hi
+
+    def to_host(self, lo, hi) -> np.ndarray:
+        shape = tuple(h - l + 1 for l, h in zip(lo, hi))
+        out = np.empty(shape, dtype=np.float64, order="F")
+        L.check(L.lib().chmy_field_copy_to_host(self.arch.ctx, self.handle, out.ctypes.data_as(C.c_void_p),
+                                                L.i64x3(lo), L.i64x3(hi)))
+        return out
+
+    def from_host(self, arr: np.ndarray, lo, hi):
+        shape = tuple(h - l + 1 for l, h in zip(lo, hi))
+        a = np.asfortranarray(np.broadcast_to(np.asarray(arr, dtype=np.float64), shape))
+        L.check(L.lib().chmy_field_copy_from_host(self.arch.ctx, self.handle, a.ctypes.data_as(C.c_void_p),
+                                                  L.i64x3(lo), L.i64x3(hi)))
+
+    def parent(self) -> np.ndarray:
+        """Array(parent(f)): the whole padded array dims+4 (field.jl:16)."""
+        return self.to_host(*self._box(2))
+
+    def __getitem__(self, I):
+        I = (I,) if isinstance(I, int) else tuple(I)
+        return float(self.to_host(I, I).reshape(-1)[0])
+
+
+def halo(f: Field) -> int:
+    return 1
+
+
+def location(f, dim=None):
+    return f.loc if dim is None else f.loc[dim - 1]
+
+
+def interior(f: Field, with_halo: bool = False) -> np.ndarray:
+    """Array(interior(f; with_halo)) -- field.jl:33-37 (host copy; the reference returns a device view)."""
+    return f.to_host(*f._box(1 if with_halo else 0))
+
+
+def parent(f: Field) -> np.ndarray:
+    return f.parent()
+
+
+def fill_parent_(f: Field, v: float):
+    """fill!(parent(f), v) as used by test/test_fields.jl:22."""
+    lo, hi = f._box(2)
+    L.check(L.lib().chmy_field_fill(f.arch.ctx, f.handle, float(v), L.i64x3(lo), L.i64x3(hi)))
+
+
+class _InitIncl:
+    """The `init_incl` closure of the Stokes drivers (examples/stokes_3d_inc_ve_T.jl:125):
+    ifelse(sum((x - x0)^2) < r^2, in, out).  It is the one function body evaluated on the device."""
+
+    def __call__(self, *a):
+        nd = (len(a) - 3) // 2
+        xs, c0, (r, inn, out) = a[:nd], a[nd:2 * nd], a[2 * nd:]
+        s = None
+        for x, c in zip(xs, c0):
+            t = (x - c) * (x - c)
+            s = t if s is None else s + t
+        return np.where(s < r * r, inn, out)
+
+
+init_incl = _InitIncl()
+
+
+def _incl_struct(nd, loc, parameters) -> L.Inclusion:
+    p = dict(parameters)
+    names = ["x0", "y0", "z0"][:nd]
+    s = L.Inclusion()
+    s.active = 1
+    for d in range(nd):
+        s.loc[d] = loc[d].code
+        s.c0[d] = float(p[names[d]])
+    s.r, s.inn, s.out = float(p["r"]), float(p["in"]), float(p["out"])
+    return s
+
+
+def set_(f, *args, discrete: bool = False, parameters=()):
+    """set!(f, val) / set!(f, A) / set!(f, other) / set!(f, grid, fun; parameters) -- field.jl:87-145."""
+    if isinstance(f, FieldTuple):
+        for c in f:
+            set_(c, *args, discrete=discrete, parameters=parameters)
+        return
+    lo, hi = f._box(0)
+    if len(args) == 1:
+        a = args[0]
+        if isinstance(a, Field):                                             # field.jl:109-119
+            if a.dims != f.dims:
+                raise ValueError("set!(f, other): size mismatch")
+            L.check(L.lib().chmy_field_copy(f.arch.ctx, f.handle, a.handle, L.i64x3(lo), L.i64x3(hi)))
+        elif np.isscalar(a):                                                 # field.jl:87
+            L.check(L.lib().chmy_field_fill(f.arch.ctx, f.handle, float(a), L.i64x3(lo), L.i64x3(hi)))
+        else:                                                                # field.jl:98
+            a = np.asarray(a, dtype=np.float64)
+            if a.shape != tuple(f.dims):
+                raise ValueError(f"set!(f, A): A has shape {a.shape}, interior is {f.dims}")
+            f.from_host(a, lo, hi)
+        return
+    grid, fun = args
+    if discrete:
+        raise NotImplementedError("set!(...; discrete=true) needs in-kernel Julia closures: not on this path")
+    if fun is init_incl:                                                     # device kernel, bit-identical coords
+        inc = _incl_struct(grid.ndims(), f.loc, parameters)
+        g = grid.desc()
+        L.check(L.lib().chmy_field_set_inclusion(f.arch.ctx, f.handle, C.byref(g), C.byref(inc)))
+        return
+    # any other host callable: evaluate on the host at the exact (muladd) coordinates and upload the bits
+    from .grids import coords
+    cs = [coords(grid, f.loc, d + 1) for d in range(grid.ndims())]
+    mesh = np.meshgrid(*cs, indexing="ij")
+    params = tuple(parameters.values()) if isinstance(parameters, dict) else tuple(parameters)
+    f.from_host(np.asarray(fun(*mesh, *params), dtype=np.float64), lo, hi)
+
+
+class FieldTuple:
+    """NamedTuple of Fields (VectorField / TensorField): attribute access + ordered iteration."""
+
+    def __init__(self, **fields):
+        self._names = tuple(fields)
+        self.__dict__.update(fields)
+
+    def __iter__(self):
+        return (getattr(self, n) for n in self._names)
+
+    def __len__(self):
+        return len(self._names)
+
+    def keys(self):
+        return self._names
+
+    def __getitem__(self, k):
+        return getattr(self, self._names[k] if isinstance(k, int) else k)
+
+
+def vector_location(dim: int, N: int):
+    """field.jl:148."""
+    return tuple(Vertex() if i == dim else Center() for i in range(1, N + 1))
+
+
+def VectorField(arch, grid: StructuredGrid, **kw) -> FieldTuple:
+    """field.jl:161-169."""
+    N = grid.ndims()
+    return FieldTuple(**{"xyz"[D - 1]: Field(arch, grid, vector_location(D, N), **kw) for D in range(1, N + 1)})
+
+
+def TensorField(arch, grid: StructuredGrid, **kw) -> FieldTuple:
+    """field.jl:182-206."""
+    Cn, Vx = Center(), Vertex()
+    if grid.ndims() == 2:
+        return FieldTuple(xx=Field(arch, grid, Cn, **kw), yy=Field(arch, grid, Cn, **kw), xy=Field(arch, grid, Vx, **kw))
+    if grid.ndims() == 3:
+        return FieldTuple(xx=Field(arch, grid, Cn, **kw), yy=Field(arch, grid, Cn, **kw), zz=Field(arch, grid, Cn, **kw),
+                          xy=Field(arch, grid, (Vx, Vx, Cn), **kw), xz=Field(arch, grid, (Vx, Cn, Vx), **kw),
+                          yz=Field(arch, grid, (Cn, Vx, Vx), **kw))
+    raise ValueError("TensorField is defined for 2D and 3D grids")
+
+
+class FunctionField(AbstractField):
+    """FunctionField(func, grid, loc; parameters) -- function_field.jl:12-43.  Values are computed in-kernel from
+    coordinates; the only body available on the device is `init_incl` (the one the named solvers use)."""
+
+    def __init__(self, func, grid: StructuredGrid, loc, *, discrete: bool = False, parameters=None):
+        if discrete or func is not init_incl:
+            raise NotImplementedError("only FunctionField(init_incl, ...; discrete=false) exists on the B200 path")
+        self.func = func
+        self.grid = grid
+        self.loc = expand_loc(grid.ndims(), loc)
+        self.parameters = dict(parameters or {})
+        self.dims = grid.size(self.loc)
+
+    def inclusion(self) -> L.Inclusion:
+        return _incl_struct(self.grid.ndims(), self.loc, self.parameters)
+
+
+def maxabs(f: Field, with_halo: bool = False) -> float:
+    """maximum(abs.(interior(f))) fused into one reduction kernel (drivers: stokes_3d_inc_ve_T.jl:158,172-175)."""
+    lo, hi = f._box(1 if with_halo else 0)
+    out = C.c_double()
+    L.check(L.lib().chmy_field_maxabs(f.arch.ctx, f.handle, L.i64x3(lo), L.i64x3(hi), C.byref(out)))
+    return float(out.value)

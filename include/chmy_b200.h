@@ -1,0 +1,205 @@
+/*
+ * chmy_b200.h -- C ABI of the B200-native hot path of PTsolvers/Chmy.jl (v0.1.25).
+ *
+ * The reference has no FFI: its backend seam is Julia multiple dispatch on the KernelAbstractions backend
+ * (ext/ChmyCUDAExt/ChmyCUDAExt.jl:1-25).  Because a C library cannot JIT arbitrary `@kernel` bodies, the seam moves
+ * up to the callers of KernelAbstractions: each entry point below replaces one reference interface (cited
+ * file:line, relative to the reference root) and is what a `ChmyB200Ext` Julia package `ccall`s.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative chmy_status; it never throws or aborts.
+ *     chmy_last_error() gives a thread-local message (the Julia glue turns non-zero into `error(msg)`,
+ *     matching the reference's plain `error`/`@assert`: exchange_halo.jl:19, stack_allocator.jl:42).
+ *   - one chmy_ctx per GPU / rank process, used by one host thread at a time.
+ *   - logical indices are the reference's: 1-based, I in 1..d is the interior, 0 and d+1 the halo, -1 and d+2
+ *     zero padding (src/Fields/field.jl:18-22,56-62).  Boxes are inclusive [lo, hi] in logical indices.
+ *   - Float64 only on this path (the reference also instantiates Float32: "next" row in DESIGN.md).
+ *   - all work is stream-ordered on the context's streams; results are visible to the host after a blocking
+ *     launch (CHMY_LAUNCH_BLOCKING, the reference's semantics, KernelLaunch.jl:117), any copy_to_host /
+ *     maxabs call, or chmy_synchronize().
+ */
+#ifndef CHMY_B200_H
+#define CHMY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHMY_ABI_VERSION 1
+
+#define CHMY_MAX_DIMS 3
+#define CHMY_MAX_BATCH_FIELDS 8
+#define CHMY_MAX_OP_FIELDS 24
+#define CHMY_MAX_SCALARS 8
+#define CHMY_UNIQUE_ID_BYTES 128
+
+typedef struct chmy_ctx chmy_ctx;       /* Architecture + its streams (+ topology and communicator) */
+typedef struct chmy_field chmy_field;   /* Field{Float64,N,L,1}: padded device storage               */
+
+typedef enum {
+    CHMY_OK = 0,
+    CHMY_ERR_ARG = -1,      /* invalid argument / descriptor                     */
+    CHMY_ERR_CUDA = -2,     /* CUDA runtime error                                */
+    CHMY_ERR_NCCL = -3,     /* NCCL error or NCCL not loadable                   */
+    CHMY_ERR_STATE = -4,    /* e.g. exchange requested without a topology        */
+    CHMY_ERR_NOMEM = -5
+} chmy_status;
+
+typedef enum { CHMY_CENTER = 0, CHMY_VERTEX = 1 } chmy_loc;            /* src/Grids/Grids.jl:26-43  */
+typedef enum { CHMY_BOUNDED = 0, CHMY_CONNECTED = 1 } chmy_conn;       /* src/Grids/Grids.jl:52-57  */
+typedef enum { CHMY_DIRICHLET = 0, CHMY_NEUMANN = 1 } chmy_bc_kind;    /* first_order_boundary_condition.jl:9-29 */
+typedef enum { CHMY_BATCH_EMPTY = 0, CHMY_BATCH_FIELD = 1, CHMY_BATCH_EXCHANGE = 2 } chmy_batch_kind;  /* batch.jl:36-66 */
+
+/* Field storage layout.  PITCHED (default): rows padded so that logical index 0 of every row is 128-byte
+ * aligned (vector loads, TMA-legal strides).  DENSE: exactly the reference's dense column-major
+ * array of dims+4 (field.jl:58-59).  Logical contents are identical; kernels accept both. */
+typedef enum { CHMY_LAYOUT_PITCHED = 0, CHMY_LAYOUT_DENSE = 1 } chmy_layout;
+
+/* The ops `launch` can run: the @kernel functions of the named example solvers. */
+typedef enum {
+    CHMY_OP_NONE = 0,            /* descriptor carries only boundary batches (bc!)                       */
+    CHMY_OP_COMPUTE_Q = 1,       /* examples/diffusion_2d.jl:8-13     fields: q.x q.y C          scalars: chi      */
+    CHMY_OP_UPDATE_C = 2,        /* examples/diffusion_2d.jl:15-19    fields: C q.x q.y          scalars: dt       */
+    CHMY_OP_UPDATE_OLD = 3,      /* stokes_3d_inc_ve_T.jl:11-21       fields: T tau[nt] T_old tau_old[nt]          */
+    CHMY_OP_UPDATE_STRESS = 4,   /* stokes_3d_inc_ve_T.jl:23-46       fields: tau[nt] Pr divV V[nd] tau_old[nt]
+                                                                       scalars: eta eta_ve G dt dtau_Pr dtau_r      */
+    CHMY_OP_UPDATE_VELOCITY = 5, /* stokes_3d_inc_ve_T.jl:48-57       fields: V[nd] r_V[nd] Pr tau[nt] rho_g|NULL
+                                                                       scalars: eta_ve nudtau                       */
+    CHMY_OP_UPDATE_THERMAL_FLUX = 6, /* stokes_3d_inc_ve_T.jl:59-71   fields: qT[nd] T V[nd]     scalars: lambda   */
+    CHMY_OP_UPDATE_THERMAL = 7   /* stokes_3d_inc_ve_T.jl:73-77       fields: T T_old qT[nd]     scalars: dt       */
+} chmy_op;                       /* nd = grid.ndims; nt = 3 (2D: xx yy xy) or 6 (3D: xx yy zz xy xz yz)            */
+
+/* UniformGrid: the numbers src/Grids/structured_grid.jl:27-39 (+ distributed_grid.jl:19-36) produces. */
+typedef struct {
+    int32_t ndims;
+    int32_t _pad;
+    int64_t n[CHMY_MAX_DIMS];               /* local number of cells                       */
+    double  origin[CHMY_MAX_DIMS];
+    double  extent[CHMY_MAX_DIMS];
+    double  spacing[CHMY_MAX_DIMS];         /* uniform_axis.jl:8                           */
+    double  inv_spacing[CHMY_MAX_DIMS];     /* uniform_axis.jl:9                           */
+    int32_t connectivity[CHMY_MAX_DIMS][2]; /* chmy_conn per (dim, side)                   */
+} chmy_grid_desc;
+
+/* One side of one dimension of a BatchSet (src/BoundaryConditions/batch.jl:8,36-66). */
+typedef struct {
+    int32_t     kind;                                 /* chmy_batch_kind                                  */
+    int32_t     nfields;
+    chmy_field* fields[CHMY_MAX_BATCH_FIELDS];
+    int32_t     bc_kind[CHMY_MAX_BATCH_FIELDS];       /* chmy_bc_kind (FIELD batches)                     */
+    double      value[CHMY_MAX_BATCH_FIELDS];         /* `nothing` -> 0.0, Number -> value                */
+} chmy_batch_desc;
+
+/* FunctionField with the drivers' `init_incl` body (function_field.jl:12-59,
+ * stokes_3d_inc_ve_T_mpi_perf.jl:141-142): value = (sum_d (x_d - c0_d)^2 < r^2) ? in : out. */
+typedef struct {
+    int32_t active;
+    int32_t loc[CHMY_MAX_DIMS];
+    double  c0[CHMY_MAX_DIMS];
+    double  r, in, out;
+} chmy_inclusion;
+
+typedef enum {
+    CHMY_LAUNCH_ASYNC = 0,        /* stream-ordered; host returns immediately                              */
+    CHMY_LAUNCH_BLOCKING = 1,     /* reference semantics: returns after completion (KernelLaunch.jl:117)   */
+    CHMY_LAUNCH_EXACT_SPLIT = 2   /* honour outer_width literally instead of treating it as a hint         */
+} chmy_launch_flags;
+
+/* `launcher(arch, grid, op => args; bc)`: src/KernelLaunch.jl:105-119,152-183. */
+typedef struct {
+    int32_t         op;                                     /* chmy_op                                    */
+    int32_t         flags;                                  /* chmy_launch_flags, OR-ed                   */
+    chmy_grid_desc  grid;
+    int32_t         nfields;
+    int32_t         nscalars;
+    chmy_field*     fields[CHMY_MAX_OP_FIELDS];
+    double          scalars[CHMY_MAX_SCALARS];
+    chmy_inclusion  rho_g;                                  /* UPDATE_VELOCITY when rho_g is a FunctionField */
+    int32_t         has_bc;                                 /* bc === nothing ? 0 : 1                     */
+    int32_t         has_outer_width;                        /* Launcher built with outer_width            */
+    int64_t         outer_width[CHMY_MAX_DIMS];
+    chmy_batch_desc bc[CHMY_MAX_DIMS][2];
+} chmy_launch_desc;
+
+typedef struct {
+    int32_t ndims;
+    int32_t layout;
+    int32_t loc[CHMY_MAX_DIMS];
+    int64_t dims[CHMY_MAX_DIMS];       /* logical size(grid, loc)                                         */
+    int64_t stride[CHMY_MAX_DIMS];     /* element strides; stride[0] == 1                                 */
+    void*   origin_ptr;                /* device address of logical index (1,1,1)                          */
+    void*   base_ptr;                  /* device address of storage element (-1,-1,-1)                     */
+    size_t  bytes;                     /* allocation size                                                  */
+} chmy_field_info;
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+int         chmy_abi_version(void);
+const char* chmy_last_error(void);
+int         chmy_device_count(int* count);
+size_t      chmy_struct_size(int which);   /* 0 grid_desc, 1 batch_desc, 2 inclusion, 3 launch_desc, 4 field_info:
+                                              lets a binding verify its struct layout against the library        */
+
+/* ---- Architecture: Arch(backend; device_id) src/Architectures.jl:46-49 ; activate! :71-74 ;
+ *      ext/ChmyCUDAExt/ChmyCUDAExt.jl:15-17 (set_device!/get_device) ------------------------------------ */
+int chmy_ctx_create(int device_id /* 1-based as in the reference */, chmy_ctx** out);
+int chmy_ctx_destroy(chmy_ctx* ctx);
+int chmy_ctx_device(const chmy_ctx* ctx, int* device_id);
+int chmy_synchronize(chmy_ctx* ctx);                      /* KernelAbstractions.synchronize(backend)        */
+int chmy_ctx_launch_count(const chmy_ctx* ctx, uint64_t* kernels); /* kernels launched so far (bench)       */
+/* device-side timing (CUDA events recorded on the context's main stream): slot in 0..CHMY_MAX_EVENTS-1 */
+#define CHMY_MAX_EVENTS 4096
+int chmy_event_record(chmy_ctx* ctx, int slot);
+int chmy_event_elapsed_ms(chmy_ctx* ctx, int slot_start, int slot_stop, float* ms);   /* synchronises on slot_stop */
+/* raw handles for tools that time or capture the context's work (cudaStream_t as void*) */
+int chmy_ctx_streams(const chmy_ctx* ctx, void** main_stream, void** boundary_stream);
+
+/* ---- Distributed: CartesianTopology src/Distributed/topology.jl:26-41 ;
+ *      Arch(backend, comm, dims) distributed_architecture.jl:27-34 -------------------------------------- */
+int chmy_dims_create(int nranks, int ndims, int32_t* dims /* in: 0 = free, out: filled */); /* MPI.Dims_create */
+int chmy_comm_unique_id(uint8_t out[CHMY_UNIQUE_ID_BYTES]);     /* rank 0; broadcast out-of-band (MPI.bcast)  */
+int chmy_topo_create(chmy_ctx* ctx, int nranks, int rank, int ndims, const int32_t* dims,
+                     const uint8_t unique_id[CHMY_UNIQUE_ID_BYTES]);
+int chmy_topo_coords(const chmy_ctx* ctx, int32_t coords[CHMY_MAX_DIMS]);               /* cart_coords :90   */
+int chmy_topo_neighbors(const chmy_ctx* ctx, int32_t nb[CHMY_MAX_DIMS][2]);             /* neighbors :99 ; -1 = PROC_NULL */
+int chmy_allreduce_max(chmy_ctx* ctx, double* inout, int n);    /* MPI.Allreduce(x, MAX) in the drivers       */
+int chmy_barrier(chmy_ctx* ctx);                                /* MPI.Barrier(cart_comm)                     */
+
+/* ---- Fields: Field(backend, grid, loc; halo=1) src/Fields/field.jl:56-62 ------------------------------ */
+int chmy_field_create(chmy_ctx* ctx, int ndims, const int64_t* dims, const int32_t* loc, int layout,
+                      chmy_field** out);                              /* zero-initialised                  */
+int chmy_field_destroy(chmy_field* f);
+int chmy_field_get_info(const chmy_field* f, chmy_field_info* out);
+int chmy_field_fill(chmy_ctx* ctx, chmy_field* f, double value, const int64_t* lo, const int64_t* hi);
+                       /* fill!(parent(f),v): lo=-1,hi=d+2 ; set!(f,v) field.jl:87: lo=1,hi=d               */
+int chmy_field_copy_from_host(chmy_ctx* ctx, chmy_field* f, const double* src, const int64_t* lo, const int64_t* hi);
+                       /* set!(f, A) field.jl:98: dense column-major host box                               */
+int chmy_field_copy_to_host(chmy_ctx* ctx, const chmy_field* f, double* dst, const int64_t* lo, const int64_t* hi);
+                       /* Array(interior(f; with_halo)) field.jl:33-37                                      */
+int chmy_field_copy(chmy_ctx* ctx, chmy_field* dst, const chmy_field* src, const int64_t* lo, const int64_t* hi);
+                       /* set!(f, other) field.jl:109-119                                                   */
+int chmy_field_set_inclusion(chmy_ctx* ctx, chmy_field* f, const chmy_grid_desc* grid, const chmy_inclusion* inc);
+                       /* set!(f, grid, init_incl; parameters) field.jl:121-142 (interior only)             */
+int chmy_field_maxabs(chmy_ctx* ctx, const chmy_field* f, const int64_t* lo, const int64_t* hi, double* out);
+                       /* maximum(abs.(interior(f))) in the drivers, e.g. stokes_3d_inc_ve_T.jl:158,172-175 */
+
+/* ---- the hot entry points ----------------------------------------------------------------------------- */
+int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* desc);           /* src/KernelLaunch.jl:105-119       */
+int chmy_bc(chmy_ctx* ctx, const chmy_grid_desc* grid,                  /* bc!(arch, grid, batchset)         */
+            const chmy_batch_desc bc[CHMY_MAX_DIMS][2], int flags);     /*   src/BoundaryConditions/batch.jl:20-29 */
+int chmy_exchange_halo(chmy_ctx* ctx, const chmy_grid_desc* grid, int dim, int side,   /* exchange_halo.jl:13-61 */
+                       int nfields, chmy_field* const* fields, int flags);
+int chmy_exchange_halo_all(chmy_ctx* ctx, const chmy_grid_desc* grid,                  /* exchange_halo.jl:73-84 */
+                           int nfields, chmy_field* const* fields, int flags);
+
+/* halo slab pack/unpack exposed for bit-exact parity tests of src/Distributed/communication_views.jl:1-34 */
+int chmy_halo_slab_len(const chmy_field* f, int dim, int64_t* len);
+int chmy_halo_pack(chmy_ctx* ctx, const chmy_field* f, int dim, int side, double* host_buf);
+int chmy_halo_unpack(chmy_ctx* ctx, chmy_field* f, int dim, int side, const double* host_buf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHMY_B200_H */

@@ -1,0 +1,331 @@
+"""
+Parity of the CUDA path (through the C ABI, via the host mirror) against the CPU oracle.  GPU only.
+Tolerances: integer/index/byte work (pack/unpack, BC index sets) bit-exact; Float64 fields: the north_star allows
+1e-12 relative -- the kernels are written to be bit-identical to the oracle, and these tests assert exactly that
+(tol = 0) wherever no division by a run-time scalar takes a different code path.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import assert_same, fill_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ch():
+    import chmy_b200
+    return chmy_b200
+
+
+@pytest.fixture(scope="module")
+def arch(ch):
+    a = ch.Arch(ch.B200Backend())
+    yield a
+    a.close()
+
+
+LOCS = {0: "Center", 1: "Vertex"}
+
+
+def mk_grids(ch, o, arch, n, origin=None, extent=None):
+    nd = len(n)
+    origin = origin or tuple(-1.0 - 0.1 * d for d in range(nd))
+    extent = extent or tuple(2.0 + 0.3 * d for d in range(nd))
+    return o.Grid(origin, extent, n), ch.UniformGrid(arch, origin=origin, extent=extent, dims=n)
+
+
+def bloc(ch, loc):
+    return tuple(ch.Vertex() if l else ch.Center() for l in loc)
+
+
+# ------------------------------------------------------------------------------------------------ fields
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("n,loc", [((7,), (1,)), ((33, 18), (0, 1)), ((12, 10, 8), (1, 0, 1)), ((5, 3, 2), (0, 0, 0))])
+def test_field_roundtrip_and_layout(ch, arch, oracle, n, loc, layout):
+    og, bg = mk_grids(ch, oracle, arch, n)
+    of = oracle.Field(og, loc)
+    bf = ch.Field(arch, bg, bloc(ch, loc), layout=layout)
+    assert bf.dims == of.dims
+    assert np.array_equal(bf.parent(), np.zeros(of.sdims))              # zero-initialised (field.jl:59)
+    rng = np.random.default_rng(1)
+    fill_pair(rng, of, bf)
+    assert_same(of, bf, "roundtrip")
+    assert np.array_equal(ch.interior(bf), of.interior())
+    assert np.array_equal(ch.interior(bf, with_halo=True), of.interior(with_halo=True))
+    info = bf.info()
+    assert info.stride[0] == 1 and info.layout == layout
+    if layout == 1 and len(n) > 1:
+        assert info.stride[1] == of.sdims[0]
+    if layout == 0:
+        assert (info.origin_ptr - 8) % 128 == 0                         # logical index 0 of each row is 128B aligned
+    # set!(f, val) touches the interior only
+    ch.set_(bf, 3.5)
+    of.set(3.5)
+    assert_same(of, bf, "set scalar")
+    A = rng.random(of.dims)
+    ch.set_(bf, A)
+    of.set(A)
+    assert_same(of, bf, "set array")
+    assert ch.maxabs(bf) == of.maxabs()
+    ch.fill_parent_(bf, float("nan"))
+    assert np.isnan(bf.parent()).all()
+
+
+def test_set_continuous_known_answers(ch, arch):
+    """test/test_fields.jl:19-55 through the CUDA path."""
+    g = ch.UniformGrid(arch, origin=(0.0, 0.0, 0.0), extent=(1.0, 1.0, 1.0), dims=(2, 2, 2))
+    f = ch.Field(arch, g, (ch.Center(), ch.Vertex(), ch.Center()))
+    ch.fill_parent_(f, float("nan"))
+    ch.set_(f, g, lambda x, y, z: y)
+    exp_y = np.zeros((2, 3, 2)); exp_y[:, 1, :], exp_y[:, 2, :] = 0.5, 1.0
+    assert np.array_equal(ch.interior(f), exp_y)
+    ch.set_(f, g, lambda x, y, z: x)
+    exp_x = np.zeros((2, 3, 2)); exp_x[0], exp_x[1] = 0.25, 0.75
+    assert np.array_equal(ch.interior(f), exp_x)
+    ch.set_(f, g, lambda x, y, z, sc: y * sc, parameters=(2.0,))
+    assert np.array_equal(ch.interior(f), 2 * exp_y)
+    assert np.isnan(f.parent()[0]).all()                                # halo/padding untouched
+
+
+@pytest.mark.parametrize("n", [(40, 27), (19, 14, 11)])
+def test_set_inclusion_device_vs_oracle(ch, arch, oracle, n):
+    og, bg = mk_grids(ch, oracle, arch, n, origin=(-1.0,) * len(n), extent=(2.0,) * len(n))
+    nd = len(n)
+    for loc in [(0,) * nd, tuple(1 if d == nd - 1 else 0 for d in range(nd))]:
+        of, bf = oracle.Field(og, loc), ch.Field(arch, bg, bloc(ch, loc))
+        oracle.set_inclusion(of, oracle.Inclusion(loc, (0.05,) * nd, 0.31, 1.0, 0.1))
+        par = dict(zip(("x0", "y0", "z0"), (0.05,) * nd))
+        ch.set_(bf, bg, ch.init_incl, parameters={**par, "r": 0.31, "in": 1.0, "out": 0.1})
+        assert_same(of, bf, "inclusion")
+        assert 0 < (of.interior() == 1.0).sum() < of.interior().size
+
+
+def test_maxabs_nan_and_exactness(ch, arch, oracle):
+    og, bg = mk_grids(ch, oracle, arch, (65, 33, 9))
+    of, bf = oracle.Field(og, 0), ch.Field(arch, bg, ch.Center())
+    rng = np.random.default_rng(5)
+    a = fill_pair(rng, of, bf, scale=1e-3)
+    assert ch.maxabs(bf) == np.abs(a[2:-2, 2:-2, 2:-2]).max() == of.maxabs()
+    assert ch.maxabs(bf, with_halo=True) == np.abs(a[1:-1, 1:-1, 1:-1]).max()
+    a[10, 10, 5] = np.nan
+    bf.from_host(a, [-1] * 3, [d + 2 for d in of.dims])
+    assert math.isnan(ch.maxabs(bf))                                    # Julia's maximum propagates NaN
+
+
+# ------------------------------------------------------------------------------------------------ BCs
+BC_CASES = [((8,), (0,)), ((8,), (1,)), ((8, 8), (0, 1)), ((8, 8, 6), (0, 1, 0)), ((13, 7, 5), (1, 1, 0))]
+
+
+@pytest.mark.parametrize("n,loc", BC_CASES)
+def test_bc_matches_oracle_bit_exact(ch, arch, oracle, n, loc):
+    """Dirichlet/Neumann x homogeneous/valued on random full arrays: every touched cell (incl. edges, corners and
+    padding rows, where the z->y->x order matters) must match the oracle exactly."""
+    nd = len(n)
+    og, bg = mk_grids(ch, oracle, arch, n, origin=(-math.pi,) * nd, extent=(2 * math.pi,) * nd)
+    of, bf = oracle.Field(og, loc), ch.Field(arch, bg, bloc(ch, loc))
+    rng = np.random.default_rng(7)
+    for mk_o, mk_b in [(oracle.Dirichlet, ch.Dirichlet), (oracle.Neumann, ch.Neumann)]:
+        for val in (None, 2.0):
+            fill_pair(rng, of, bf)
+            oracle.bc_(og, (of, mk_o(val)))
+            ch.bc_(arch, bg, (bf, mk_b(val)))
+            assert_same(of, bf, f"bc {mk_o.__name__}({val})")
+    # mixed per-axis spec with different left/right conditions
+    if nd >= 2:
+        fill_pair(rng, of, bf)
+        so = {"x": (oracle.Dirichlet(1.5), oracle.Neumann(-0.5)), "y": oracle.Neumann()}
+        sb = {"x": (ch.Dirichlet(1.5), ch.Neumann(-0.5)), "y": ch.Neumann()}
+        oracle.bc_(og, (of, so))
+        ch.bc_(arch, bg, (bf, sb))
+        assert_same(of, bf, "bc mixed")
+
+
+def test_bc_known_answers_cuda(ch, arch):
+    """test/test_boundary_conditions.jl:143-205 (3D, (C,V,C)) straight on the CUDA path."""
+    n = (8, 8, 6)
+    g = ch.UniformGrid(arch, origin=(-math.pi,) * 3, extent=(2 * math.pi,) * 3, dims=n)
+    f = ch.Field(arch, g, (ch.Center(), ch.Vertex(), ch.Center()))
+    loc = (0, 1, 0)
+
+    def face(a, d, idx):
+        sl = [slice(1, -1)] * 3
+        sl[d] = idx
+        return a[tuple(sl)]
+
+    ch.set_(f, 1.0); ch.bc_(arch, g, (f, ch.Dirichlet()))
+    a = ch.interior(f, with_halo=True)
+    for d in range(3):
+        if loc[d] == 0:
+            assert np.allclose(face(a, d, 0), -face(a, d, 1)) and np.allclose(face(a, d, -1), -face(a, d, -2))
+        else:
+            assert np.allclose(face(a, d, 1), 0.0) and np.allclose(face(a, d, -2), 0.0)
+    ch.set_(f, 1.0); ch.bc_(arch, g, (f, ch.Neumann(2.0)))
+    a = ch.interior(f, with_halo=True)
+    for d in range(3):
+        h = ch.spacing(g)[d]
+        assert np.allclose((face(a, d, 1) - face(a, d, 0)) / h, 2.0)
+        assert np.allclose((face(a, d, -1) - face(a, d, -2)) / h, 2.0)
+
+
+# ------------------------------------------------------------------------------------------------ halo slabs
+@pytest.mark.parametrize("n,loc", [((9, 6), (1, 0)), ((9, 6), (0, 0)), ((11, 7, 5), (1, 0, 0)), ((11, 7, 5), (0, 1, 1))])
+def test_halo_pack_unpack_bit_exact(ch, arch, oracle, n, loc):
+    """communication_views.jl:1-34: index-encoded fields (catches orientation errors), every (dim, side)."""
+    import ctypes as C
+    from chmy_b200 import _lib as L
+    og, bg = mk_grids(ch, oracle, arch, n)
+    of, bf = oracle.Field(og, loc), ch.Field(arch, bg, bloc(ch, loc))
+    enc = np.arange(of.data.size, dtype=np.float64).reshape(of.sdims, order="F") + 1e6
+    of.data[...] = enc
+    bf.from_host(enc, [-1] * len(n), [d + 2 for d in of.dims])
+    for D in range(len(n)):
+        for S in range(2):
+            ref = oracle.pack_send(of, D, S)
+            ln = C.c_int64()
+            L.check(L.lib().chmy_halo_slab_len(bf.handle, D, C.byref(ln)))
+            assert ln.value == ref.size
+            buf = np.empty(ref.size)
+            L.check(L.lib().chmy_halo_pack(arch.ctx, bf.handle, D, S, buf.ctypes.data_as(C.c_void_p)))
+            assert np.array_equal(buf, ref), (D, S)
+            # unpack a recognisable slab into the recv position
+            msg = -ref[::-1].copy()
+            oracle.unpack_recv(of, D, S, msg)
+            L.check(L.lib().chmy_halo_unpack(arch.ctx, bf.handle, D, S, msg.ctypes.data_as(C.c_void_p)))
+            assert_same(of, bf, f"unpack {D},{S}")
+
+
+# ------------------------------------------------------------------------------------------------ single ops
+def _stokes_pair(ch, o, arch, n, rng):
+    og, bg = mk_grids(ch, o, arch, n, origin=(-1.0,) * len(n), extent=(2.0,) * len(n))
+    O = dict(tau=o.TensorField(og), tau_old=o.TensorField(og), V=o.VectorField(og), rV=o.VectorField(og),
+             qT=o.VectorField(og), Pr=o.Field(og, 0), dV=o.Field(og, 0), T=o.Field(og, 0), To=o.Field(og, 0))
+    B = dict(tau=ch.TensorField(arch, bg), tau_old=ch.TensorField(arch, bg), V=ch.VectorField(arch, bg),
+             rV=ch.VectorField(arch, bg), qT=ch.VectorField(arch, bg), Pr=ch.Field(arch, bg), dV=ch.Field(arch, bg),
+             T=ch.Field(arch, bg), To=ch.Field(arch, bg))
+    rl = tuple(1 if d == len(n) - 1 else 0 for d in range(len(n)))
+    O["rho"], B["rho"] = o.Field(og, rl), ch.Field(arch, bg, bloc(ch, rl))
+    pairs = []
+    for k in O:
+        if isinstance(O[k], dict):
+            for c in O[k]:
+                pairs.append((f"{k}.{c}", O[k][c], getattr(B[k], c)))
+        else:
+            pairs.append((k, O[k], B[k]))
+    for _, a, b in pairs:
+        fill_pair(rng, a, b)
+    return og, bg, O, B, pairs
+
+
+@pytest.mark.parametrize("n", [(30, 22, 14), (17, 9, 5), (65, 33, 4), (126, 126), (37, 258)])
+def test_every_op_bit_exact(ch, arch, oracle, n):
+    o = oracle
+    rng = np.random.default_rng(11)
+    og, bg, O, B, pairs = _stokes_pair(ch, o, arch, n, rng)
+    Lo, Lb = o.Launcher(og), ch.Launcher(arch, bg)
+    sc = dict(eta=10.0, eta_ve=0.737, G=1.3, dt=0.0171, dPr=0.0213, dr=0.613, nud=0.00931, lam=3.3e-4)
+
+    def check(tag):
+        for name, a, b in pairs:
+            assert_same(a, b, f"{tag}:{name}")
+
+    o.launch(Lo, og, o.update_old, (O["T"], O["tau"], O["To"], O["tau_old"]))
+    Lb(arch, bg, (ch.update_old_, (B["T"], B["tau"], B["To"], B["tau_old"])))
+    check("update_old")
+    for _, a, b in pairs:
+        fill_pair(rng, a, b)
+    o.launch(Lo, og, o.update_stress, (O["tau"], O["Pr"], O["dV"], O["V"], O["tau_old"], sc["eta"], sc["eta_ve"], sc["G"],
+                                       sc["dt"], sc["dPr"], sc["dr"]))
+    Lb(arch, bg, (ch.update_stress_, (B["tau"], B["Pr"], B["dV"], B["V"], B["tau_old"], sc["eta"], sc["eta_ve"], sc["G"],
+                                      sc["dt"], sc["dPr"], sc["dr"], bg)))
+    check("update_stress")
+    o.launch(Lo, og, o.update_velocity, (O["V"], O["rV"], O["Pr"], O["tau"], O["rho"], sc["eta_ve"], sc["nud"]))
+    Lb(arch, bg, (ch.update_velocity_, (B["V"], B["rV"], B["Pr"], B["tau"], B["rho"], sc["eta_ve"], sc["nud"], bg)))
+    check("update_velocity(field rho)")
+    nd = len(n)
+    rl = tuple(1 if d == nd - 1 else 0 for d in range(nd))
+    inc_o = o.Inclusion(rl, (0.02,) * nd, 0.33, 1.0, 0.0)
+    par = dict(zip(("x0", "y0", "z0"), (0.02,) * nd))
+    inc_b = ch.FunctionField(ch.init_incl, bg, bloc(ch, rl), parameters={**par, "r": 0.33, "in": 1.0, "out": 0.0})
+    o.launch(Lo, og, o.update_velocity, (O["V"], O["rV"], O["Pr"], O["tau"], inc_o, sc["eta_ve"], sc["nud"]))
+    Lb(arch, bg, (ch.update_velocity_, (B["V"], B["rV"], B["Pr"], B["tau"], inc_b, sc["eta_ve"], sc["nud"], bg)))
+    check("update_velocity(FunctionField rho)")
+    o.launch(Lo, og, o.update_thermal_flux, (O["qT"], O["T"], O["V"], sc["lam"]))
+    Lb(arch, bg, (ch.update_thermal_flux_, (B["qT"], B["T"], B["V"], sc["lam"], bg)))
+    check("update_thermal_flux")
+    o.launch(Lo, og, o.update_thermal, (O["T"], O["To"], O["qT"], sc["dt"]))
+    Lb(arch, bg, (ch.update_thermal_, (B["T"], B["To"], B["qT"], sc["dt"], bg)))
+    check("update_thermal")
+
+
+@pytest.mark.parametrize("n", [(64, 48), (255, 257)])
+def test_diffusion_ops_bit_exact(ch, arch, oracle, n):
+    o = oracle
+    rng = np.random.default_rng(3)
+    og, bg = mk_grids(ch, o, arch, n)
+    Co, qo = o.Field(og, 0), o.VectorField(og)
+    Cb, qb = ch.Field(arch, bg), ch.VectorField(arch, bg)
+    for a, b in [(Co, Cb), (qo["x"], qb.x), (qo["y"], qb.y)]:
+        fill_pair(rng, a, b)
+    Lo, Lb = o.Launcher(og), ch.Launcher(arch, bg)
+    o.launch(Lo, og, o.compute_q, (qo, Co, 1.7))
+    Lb(arch, bg, (ch.compute_q_, (qb, Cb, 1.7, bg)))
+    o.launch(Lo, og, o.update_C, (Co, qo, 1e-3))
+    Lb(arch, bg, (ch.update_C_, (Cb, qb, 1e-3, bg)))
+    for nm, a, b in [("C", Co, Cb), ("qx", qo["x"], qb.x), ("qy", qo["y"], qb.y)]:
+        assert_same(a, b, nm)
+
+
+# ------------------------------------------------------------------------------------------------ whole solvers
+def test_config1_diffusion_256(ch, arch, oracle):
+    """BASELINE config 1: examples/diffusion_2d.jl, 256^2, outer_width (16, 8), nt = 100, C => Neumann()."""
+    import drivers as OD
+    from chmy_b200 import drivers as BD
+    C0 = np.random.default_rng(0).random((256, 256))
+    od = OD.Diffusion2D((256, 256), C0=C0)
+    bd = BD.Diffusion2D(arch, (256, 256), C0=C0)
+    od.run(100)
+    bd.run(100)
+    for k, f in od.fields().items():
+        assert_same(f, bd.fields()[k], k)
+    # the split launch (inner + 4 slabs on two streams) must give the same bits as the single launch
+    bs = BD.Diffusion2D(arch, (256, 256), C0=C0, exact_split=True)
+    bs.run(100)
+    for k, f in od.fields().items():
+        assert_same(f, bs.fields()[k], "split:" + k)
+
+
+@pytest.mark.parametrize("n,fun", [((30, 22, 14), False), ((24, 24, 24), True), ((126, 126), True), ((63, 40), False)])
+def test_stokes_solver_fields_and_residual_history(ch, arch, oracle, n, fun):
+    """Configs 3/4 at oracle-sized grids: 2 outer steps x 110 PT iterations (thermal on in step 2), residual check
+    every 22 iterations.  Full padded arrays and the whole residual history within 1e-12 relative."""
+    import drivers as OD
+    from chmy_b200 import drivers as BD
+    osol = OD.Stokes(n, rho_g_function=fun)
+    bsol = BD.Stokes(arch, n, rho_g_function=fun)
+    ho = osol.run(2, 110, 22)
+    hb = bsol.run(2, 110, 22)
+    assert len(ho) == len(hb) == 10
+    for a, b in zip(ho, hb):
+        assert a[:2] == b[:2]
+        for x, y in zip(a[2:], b[2:]):
+            assert abs(x - y) <= 1e-12 * abs(x), (a, b)
+    assert bsol.dt == osol.dt and bsol.eta_ve == osol.eta_ve
+    bf = bsol.fields()
+    for k, f in osol.fields().items():
+        assert_same(f, bf[k], k, tol=1e-12)
+
+
+def test_stokes_split_equals_unsplit(ch, arch):
+    """Launcher with outer_width honoured literally (two streams) vs one full-range kernel: identical bits."""
+    from chmy_b200 import drivers as BD
+    a = BD.Stokes(arch, (40, 36, 28), rho_g_function=True)
+    b = BD.Stokes(arch, (40, 36, 28), rho_g_function=True, outer_width=(8, 4, 3), exact_split=True, blocking=False)
+    a.run(2, 40, 20)
+    b.run(2, 40, 20)
+    assert a.history == b.history
+    fb = b.fields()
+    for k, f in a.fields().items():
+        assert np.array_equal(f.parent(), fb[k].parent()), k
