@@ -194,6 +194,16 @@ int chmy_exchange_halo(chmy_ctx* ctx, const chmy_grid_desc* grid, int dim, int s
 int chmy_exchange_halo_all(chmy_ctx* ctx, const chmy_grid_desc* grid,                  /* exchange_halo.jl:73-84 */
                            int nfields, chmy_field* const* fields, int flags);
 
+/* ---- self-test and tuning hooks (used by tests/ and bench.py; not part of the reference's surface) -------- */
+/* counts operands x (n pseudo-random ones from `seed`) for which the exact-division sequence used by the tuned
+ * kernels for kernel-uniform divisors differs bitwise from IEEE x / c; *markstein_used = 0 when c is routed to the
+ * true-division instantiation instead. */
+int chmy_selftest_division(chmy_ctx* ctx, double c, long long n, unsigned long long seed,
+                           unsigned long long* mismatches, int* markstein_used);
+/* -1 keeps a setting.  disable_fast_kernels: run every op with the generic one-thread-per-cell kernels (A/B
+ * parity of the tuned kernels); force_true_division: div.rn.f64 everywhere.  Env: CHMY_NO_FAST=1, CHMY_TRUE_DIV=1. */
+int chmy_set_tuning(int disable_fast_kernels, int force_true_division);
+
 /* halo slab pack/unpack exposed for bit-exact parity tests of src/Distributed/communication_views.jl:1-34 */
 int chmy_halo_slab_len(const chmy_field* f, int dim, int64_t* len);
 int chmy_halo_pack(chmy_ctx* ctx, const chmy_field* f, int dim, int side, double* host_buf);

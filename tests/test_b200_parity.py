@@ -329,3 +329,45 @@ def test_stokes_split_equals_unsplit(ch, arch):
     fb = b.fields()
     for k, f in a.fields().items():
         assert np.array_equal(f.parent(), fb[k].parent()), k
+
+
+# ------------------------------------------------------------------------------------------------ tuned kernels
+def _set_tuning(disable_fast=-1, true_div=-1):
+    from chmy_b200 import _lib as L
+    L.check(L.lib().chmy_set_tuning(disable_fast, true_div))
+
+
+@pytest.mark.parametrize("c", [3.0, 10.0, 0.0171 * 1.3, 0.737, 1.0 / 3.0, 6.02e23, 1.7e-19, 1.9999999999999998])
+def test_exact_division_by_uniform_scalar(ch, arch, c):
+    """The reciprocal + 2 FMA-correction sequence must equal IEEE division bit for bit (2^28 operands per divisor:
+    random significands over 120 binades, exact multiples of c and their 1-ulp neighbours)."""
+    import ctypes as C
+    from chmy_b200 import _lib as L
+    bad, used = C.c_ulonglong(1), C.c_int(-1)
+    L.check(L.lib().chmy_selftest_division(arch.ctx, c, 1 << 28, 12345, C.byref(bad), C.byref(used)))
+    if c == 1.9999999999999998:
+        assert used.value == 0                       # all-ones significand -> routed to true division
+    else:
+        assert used.value == 1 and bad.value == 0, (c, bad.value)
+
+
+@pytest.mark.parametrize("n", [(130, 19, 70), (63, 9, 5), (64, 8, 64), (65, 17, 65), (1, 1, 1)])
+@pytest.mark.parametrize("true_div", [0, 1])
+def test_fast_kernels_equal_generic_kernels(ch, arch, n, true_div):
+    """z-marching / vectorised stress+velocity kernels vs the one-thread-per-cell kernels: identical bits on the full
+    padded arrays for tile-edge sizes (x not a multiple of 64, odd y/z, single cells), incl. a split sub-box."""
+    from chmy_b200 import drivers as BD
+    res = []
+    for fast in (1, 0):
+        _set_tuning(disable_fast=0 if fast else 1, true_div=true_div)
+        s = BD.Stokes(arch, n, rho_g_function=(n[0] % 2 == 1))
+        rng = np.random.default_rng(42)
+        for f in s.fields().values():
+            f.from_host(rng.random(tuple(d + 4 for d in f.dims)) - 0.5, [-1] * 3, [d + 2 for d in f.dims])
+        s.begin_time_step()
+        for _ in range(3):
+            s.mechanics()
+        res.append({k: f.parent() for k, f in s.fields().items()})
+    _set_tuning(0, 0)
+    for k in res[0]:
+        assert np.array_equal(res[0][k], res[1][k]), k
