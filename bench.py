@@ -30,9 +30,22 @@ WORKLOADS = {
     "stokes3d": ((767, 767, 767), 37, "examples/stokes_3d_inc_ve_T_mpi_perf.jl 3D Stokes PT (mechanics), Float64, 767^3 per GPU"),
     "stokes2d": ((8191, 8191), 22, "examples/stokes_2d_inc_ve_T.jl 2D Stokes PT (mechanics), Float64, 8191^2"),
     "diffusion2d": ((16383, 16383), 7, "examples/diffusion_2d_perf.jl 2D diffusion, Float64, 16383^2"),
+    # outer steps it > 1: mechanics + thermal sub-step (nIO 37 + 9, stokes_3d_inc_ve_T_mpi.jl:206; 2D by the same rule)
+    "stokes3d_thermal": ((767, 767, 767), 46, "examples/stokes_3d_inc_ve_T.jl 3D Stokes PT + thermal sub-step, Float64, 767^3"),
+    "stokes2d_thermal": ((8191, 8191), 29, "examples/stokes_2d_inc_ve_T.jl 2D Stokes PT + thermal sub-step, Float64, 8191^2"),
 }
 # real (perfect-reuse) array passes of the dominant kernel, per cell of its (n+2)^N launch range
-DOMINANT = {"stokes3d": ("update_stress!", 24), "stokes2d": ("update_stress!", 14), "diffusion2d": ("update_C!", 4)}
+DOMINANT = {"stokes3d": ("update_stress!", 24), "stokes2d": ("update_stress!", 14), "diffusion2d": ("update_C!", 4),
+            "stokes3d_thermal": ("update_stress!", 24), "stokes2d_thermal": ("update_stress!", 14)}
+
+
+def measured_traffic(workload, n, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t[f"{workload}:{'x'.join(map(str, n))}:{kernel}"]["bytes"]
+    except Exception:
+        return None
 
 
 def parse():
@@ -131,7 +144,12 @@ def cpu_arm(workload, n_full, steps, warmup, budget_s=20.0):
         n = tuple(n_full[:-1]) + (min(n_full[-1], 24 if len(n_full) == 3 else 1024),)
         sol = OD.Stokes(n, re_m=2.5 * math.pi, rho_g_function=True, adv_coef=0.01)
         sol.begin_time_step()
-        step = sol.mechanics
+        if workload.endswith("_thermal"):
+            def step():
+                sol.mechanics()
+                sol.thermal()
+        else:
+            step = sol.mechanics
         sample = "x".join(map(str, n)) + " slab of the " + "x".join(map(str, n_full)) + " grid"
     for _ in range(max(1, min(warmup, 2))):
         step()
@@ -211,12 +229,21 @@ def run_b200(args):
         sol = BD.Stokes(arch, n, re_m=2.5 * math.pi, rho_g_function=True,
                         outer_width=(128, 8, 4) if len(n) == 3 else (128, 8), adv_coef=0.01, blocking=False)
         sol.begin_time_step()
-        step = sol.mechanics
         g = sol.grid
+        if wl.endswith("_thermal"):
+            def step():
+                sol.mechanics()
+                sol.thermal()
+        else:
+            step = sol.mechanics
         sub = [("update_stress!", lambda: sol.launch(arch, g, (ch.update_stress_, (sol.tau, sol.Pr, sol.divV, sol.V, sol.tau_old,
                                                      sol.eta, sol.eta_ve, sol.G, sol.dt, sol.dtau_Pr, sol.dtau_r, g)))),
                ("update_velocity!", lambda: sol.launch(arch, g, (ch.update_velocity_, (sol.V, sol.r_V, sol.Pr, sol.tau, sol.rho_g,
                                                        sol.eta_ve, sol.nudtau, g)), bc=ch.batch(g, *sol.bc_V, exchange=sol.exch_V)))]
+        if wl.endswith("_thermal"):
+            sub += [("update_thermal_flux!", lambda: sol.launch(arch, g, (ch.update_thermal_flux_, (sol.qT, sol.T, sol.V, sol.lam, g)))),
+                    ("update_thermal!", lambda: sol.launch(arch, g, (ch.update_thermal_, (sol.T, sol.T_old, sol.qT, sol.dt, g)),
+                                                           bc=ch.batch(g, *sol.bc_T, exchange=sol.T)))]
         metric_field = sol.divV
     ch.synchronize(arch)
 
@@ -265,7 +292,7 @@ def run_b200(args):
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (per[dom_name] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": measured_traffic(wl, n, dom_name), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": per[dom_name],
                 "step_kernels_ms": per, "share_of_step": per[dom_name] / sum(per.values())}
 

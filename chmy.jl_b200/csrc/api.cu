@@ -400,7 +400,16 @@ extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
             CHMY_TRY(run_op(ctx, d, full, ctx->s_main));
             for (int D = N - 1; D >= 0; --D) CHMY_TRY(bc_dim(ctx, g, D, &d->bc[D][0], &d->bc[D][1], ctx->s_main));
         } else {        // KernelLaunch.jl:160-181: inner region on the main stream, slabs + batches on the boundary stream
-            const int64_t* ow = d->outer_width;
+            // Slab widths per side.  outer_width is a hint (see above): unless EXACT_SPLIT is set the x widths are
+            // nudged so that the inner region and the right slab start on even x indices (the tuned kernels own
+            // aligned pairs of cells); every cell is still computed exactly once.
+            int wl[3] = {0, 0, 0}, wr[3] = {0, 0, 0};
+            for (int a = 0; a < N; ++a) wl[a] = wr[a] = (int)d->outer_width[a];
+            if (!(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) {
+                wl[0] += wl[0] & 1;
+                wr[0] += (full.n[0] - wr[0]) & 1;
+                if (wl[0] + wr[0] > full.n[0]) { wl[0] = (int)d->outer_width[0]; wr[0] = (int)d->outer_width[0]; }
+            }
             CHMY_CUDA(cudaEventRecord(ctx->ev_fork, ctx->s_main));
             CHMY_CUDA(cudaStreamWaitEvent(ctx->s_bnd, ctx->ev_fork, 0));
             for (int D = N - 1; D >= 0; --D) {
@@ -409,8 +418,8 @@ extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
                     for (int a = 0; a < 3; ++a) {
                         if (a >= N) { b.lo[a] = 0; b.n[a] = 1; }
                         else if (a < D) { b.lo[a] = 0; b.n[a] = full.n[a]; }
-                        else if (a == D) { b.lo[a] = S == 0 ? 0 : full.n[a] - (int)ow[a]; b.n[a] = (int)ow[a]; }
-                        else { b.lo[a] = (int)ow[a]; b.n[a] = full.n[a] - 2 * (int)ow[a]; }
+                        else if (a == D) { b.lo[a] = S == 0 ? 0 : full.n[a] - wr[a]; b.n[a] = S == 0 ? wl[a] : wr[a]; }
+                        else { b.lo[a] = wl[a]; b.n[a] = full.n[a] - wl[a] - wr[a]; }
                     }
                     CHMY_TRY(run_op(ctx, d, b, ctx->s_bnd));
                 }
@@ -418,8 +427,8 @@ extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
             }
             Box in;      // inner_worksize / inner_offset, KernelLaunch.jl:60-61
             for (int a = 0; a < 3; ++a) {
-                in.lo[a] = a < N ? (int)ow[a] : 0;
-                in.n[a]  = a < N ? full.n[a] - 2 * (int)ow[a] : 1;
+                in.lo[a] = a < N ? wl[a] : 0;
+                in.n[a]  = a < N ? full.n[a] - wl[a] - wr[a] : 1;
             }
             CHMY_TRY(run_op(ctx, d, in, ctx->s_main));
             CHMY_CUDA(cudaEventRecord(ctx->ev_join, ctx->s_bnd));

@@ -84,6 +84,14 @@ __device__ __forceinline__ double incl_eval(const InclDev& q, int i, int j, int 
     return s < q.r2 ? q.in : q.out;
 }
 
+// Julia Base.max/min on Float64 (NaN-propagating, max(-0.0,+0.0) = +0.0)
+__device__ __forceinline__ double jl_max0(double v) {
+    return (v != v) ? v : fmax(v, 0.0);
+}
+__device__ __forceinline__ double jl_min0(double v) {
+    return (v != v) ? v : fmin(v, 0.0);
+}
+
 // ---------------------------------------------------------------------------------------------- host objects
 
 struct chmy_field {

@@ -166,14 +166,6 @@ struct Velocity3 {
 };
 
 // ---------------------------------------------------------------------------------------------- thermal
-// Julia Base.max/min on Float64 (NaN-propagating, max(-0.0,+0.0) = +0.0)
-__device__ __forceinline__ double jl_max0(double v) {
-    return (v != v) ? v : fmax(v, 0.0);
-}
-__device__ __forceinline__ double jl_min0(double v) {
-    return (v != v) ? v : fmin(v, 0.0);
-}
-
 // stokes_3d_inc_ve_T.jl:59-71 (2D: stokes_2d_inc_ve_T.jl:45-54)
 template <int ND>
 struct ThermalFlux {

@@ -14,34 +14,7 @@
 //     significand is all ones, or that are not normal numbers, take the true-division instantiation.
 //
 // Arithmetic order is exactly that of ops.cu / the reference (compiled with -fmad=false; fma() only where written).
-#include <stdlib.h>
-
-#include "common.cuh"
-
-// ---------------------------------------------------------------------------------------------- exact division
-struct DivC {
-    double c, rc;   // divisor, RN(1/c)
-};
-
-static bool markstein_ok(double c) {
-    unsigned long long b;
-    memcpy(&b, &c, sizeof(b));
-    const unsigned long long mant = b & 0xFFFFFFFFFFFFFull, ex = (b >> 52) & 0x7FF;
-    if (ex == 0 || ex == 0x7FF) return false;            // zero, subnormal, inf, nan
-    if (mant == 0xFFFFFFFFFFFFFull) return false;        // the one significand Markstein's theorem excludes
-    if (ex < 200 || ex > 1800) return false;             // keep 1/c and the residuals far from under/overflow
-    return true;
-}
-
-template <bool TRUE_DIV>
-__device__ __forceinline__ double div_u(double x, const DivC d) {
-    if (TRUE_DIV) return x / d.c;
-    double q = x * d.rc;
-    double r = fma(-d.c, q, x);
-    q        = fma(r, d.rc, q);
-    r        = fma(-d.c, q, x);
-    return fma(r, d.rc, q);
-}
+#include "fast_common.cuh"
 
 // self-test kernel: counts operands for which the sequence differs from div.rn.f64 (bitwise, NaN == NaN)
 __global__ void k_divcheck(DivC d, unsigned long long seed, long long n, int mode, unsigned long long* bad) {
@@ -84,20 +57,6 @@ extern "C" int chmy_selftest_division(chmy_ctx* ctx, double c, long long n, unsi
     *mismatches = ctx->h_red[0];
     return CHMY_OK;
 }
-
-// ---------------------------------------------------------------------------------------------- helpers
-__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
-__device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
-
-#define FULL 0xffffffffu
-constexpr int TX = 32;    // lanes per row segment (2 cells each -> 64 cells)
-constexpr int TY = 8;     // rows per CTA
-constexpr int CZ = 64;    // z-planes marched by one CTA
-
-// element strides of the four (x-location, y-location) storage classes
-struct Strides {
-    int sy, sz;
-};
 
 // ---------------------------------------------------------------------------------------------- update_stress! 3D
 struct Stress3P {
@@ -334,18 +293,111 @@ __global__ void __launch_bounds__(TX* TY, 2) k_velocity3(const Velocity3P p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------- thermal pair 3D
+// update_thermal_flux! (stokes_3d_inc_ve_T.jl:59-71):
+//   q.d[I] = ((-lam)*((T[I]-T[I-e_d])*id_d) + max(V.d[I],0)*T[I-e_d]) + min(V.d[I],0)*T[I]
+struct Flux3P {
+    double *qx, *qy, *qz;
+    const double *T, *Vx, *Vy, *Vz;
+    Strides cc, vc, cv;                       // CC: T Vz qz ; VC: Vx qx ; CV: Vy qy
+    int lo[3], hi[3];
+    double lam, idx, idy, idz;
+};
+
+__device__ __forceinline__ double flux1(double nlam, double t, double tm, double v, double id) {
+    return (nlam * ((t - tm) * id) + jl_max0(v) * tm) + jl_min0(v) * t;
+}
+
+__global__ void __launch_bounds__(TX* TY) k_flux3(const Flux3P p) {
+    const int lane = threadIdx.x;
+    const int i = p.lo[0] + (blockIdx.x * TX + lane) * 2;
+    const int j = p.lo[1] + blockIdx.y * TY + threadIdx.y;
+    const int k0 = p.lo[2] + blockIdx.z * CZ;
+    const int k1 = min(k0 + CZ, p.hi[2]);
+    if (j >= p.hi[1]) return;
+    const int nact = min(max(p.hi[0] - i, 0), 2);
+    const bool act = nact > 0;
+    long long cc = (long long)i + (long long)j * p.cc.sy + (long long)k0 * p.cc.sz;
+    long long vc = (long long)i + (long long)j * p.vc.sy + (long long)k0 * p.vc.sz;
+    long long cv = (long long)i + (long long)j * p.cv.sy + (long long)k0 * p.cv.sz;
+    const double2 z2 = make_double2(0.0, 0.0);
+    const double nlam = -p.lam;
+    double2 T_km = act ? ld2(p.T + cc - p.cc.sz) : z2;
+#pragma unroll 2
+    for (int k = k0; k < k1; ++k) {
+        double2 T = z2, Tjm = z2, vx = z2, vy = z2, vz = z2;
+        double e = 0.0;
+        if (act) {
+            T   = ld2(p.T + cc);
+            Tjm = ld2(p.T + cc - p.cc.sy);
+            vx  = ld2(p.Vx + vc);
+            vy  = ld2(p.Vy + cv);
+            vz  = ld2(p.Vz + cc);
+            if (lane == 0) e = p.T[cc - 1];
+        }
+        const double T_im1 = nb_left(T.y, e, lane);
+        double2 qx, qy, qz;
+        qx.x = flux1(nlam, T.x, T_im1, vx.x, p.idx);
+        qx.y = flux1(nlam, T.y, T.x, vx.y, p.idx);
+        qy.x = flux1(nlam, T.x, Tjm.x, vy.x, p.idy);
+        qy.y = flux1(nlam, T.y, Tjm.y, vy.y, p.idy);
+        qz.x = flux1(nlam, T.x, T_km.x, vz.x, p.idz);
+        qz.y = flux1(nlam, T.y, T_km.y, vz.y, p.idz);
+        if (nact == 2) { st2(p.qx + vc, qx); st2(p.qy + cv, qy); st2(p.qz + cc, qz); }
+        else if (nact == 1) { p.qx[vc] = qx.x; p.qy[cv] = qy.x; p.qz[cc] = qz.x; }
+        T_km = T;
+        cc += p.cc.sz; vc += p.vc.sz; cv += p.cv.sz;
+    }
+}
+
+// update_thermal! (stokes_3d_inc_ve_T.jl:73-77): T[I] = T_old[I] - dt*(((dx qx) + (dy qy)) + (dz qz))
+struct Thermal3P {
+    double* T;
+    const double *To, *qx, *qy, *qz;
+    Strides cc, vc, cv;                       // CC: T To qz ; VC: qx ; CV: qy
+    int lo[3], hi[3];
+    double dt, idx, idy, idz;
+};
+
+__global__ void __launch_bounds__(TX* TY) k_thermal3(const Thermal3P p) {
+    const int lane = threadIdx.x;
+    const int i = p.lo[0] + (blockIdx.x * TX + lane) * 2;
+    const int j = p.lo[1] + blockIdx.y * TY + threadIdx.y;
+    const int k0 = p.lo[2] + blockIdx.z * CZ;
+    const int k1 = min(k0 + CZ, p.hi[2]);
+    if (j >= p.hi[1]) return;
+    const int nact = min(max(p.hi[0] - i, 0), 2);
+    const bool act = nact > 0;
+    const bool xlast = lane == TX - 1 || i + 2 >= p.hi[0];
+    long long cc = (long long)i + (long long)j * p.cc.sy + (long long)k0 * p.cc.sz;
+    long long vc = (long long)i + (long long)j * p.vc.sy + (long long)k0 * p.vc.sz;
+    long long cv = (long long)i + (long long)j * p.cv.sy + (long long)k0 * p.cv.sz;
+    const double2 z2 = make_double2(0.0, 0.0);
+    double2 qz = act ? ld2(p.qz + cc) : z2;
+#pragma unroll 2
+    for (int k = k0; k < k1; ++k) {
+        double2 to = z2, qx = z2, qy = z2, qyjp = z2, qzkp = z2;
+        double e = 0.0;
+        if (act) {
+            to   = ld2(p.To + cc);
+            qx   = ld2(p.qx + vc);
+            qy   = ld2(p.qy + cv);
+            qyjp = ld2(p.qy + cv + p.cv.sy);
+            qzkp = ld2(p.qz + cc + p.cc.sz);
+            if (xlast) e = p.qx[vc + 2];
+        }
+        const double qx_ip2 = nb_right(qx.x, e, xlast);
+        double2 o;
+        o.x = to.x - p.dt * (((qx.y - qx.x) * p.idx + (qyjp.x - qy.x) * p.idy) + (qzkp.x - qz.x) * p.idz);
+        o.y = to.y - p.dt * (((qx_ip2 - qx.y) * p.idx + (qyjp.y - qy.y) * p.idy) + (qzkp.y - qz.y) * p.idz);
+        if (nact == 2) st2(p.T + cc, o);
+        else if (nact == 1) p.T[cc] = o.x;
+        qz = qzkp;
+        cc += p.cc.sz; vc += p.vc.sz; cv += p.cv.sz;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- dispatch
-static bool aligned16(const chmy_field* f) {
-    return f->layout == CHMY_LAYOUT_PITCHED && ((uintptr_t)f->p0 % 16 == 0) && (f->stride[1] % 2 == 0) && (f->stride[2] % 2 == 0) &&
-           f->stride[2] * f->sd[2] < (1ll << 40);
-}
-
-static Strides strides_of(const chmy_field* f) { return Strides{(int)f->stride[1], (int)f->stride[2]}; }
-
-static bool same_strides(const chmy_field* a, const chmy_field* b) {
-    return a->stride[1] == b->stride[1] && a->stride[2] == b->stride[2];
-}
-
 static bool g_force_true_div = false, g_disable_fast = false, g_env_read = false;
 static void read_env() {
     if (g_env_read) return;
@@ -363,6 +415,9 @@ extern "C" int chmy_set_tuning(int disable_fast_kernels, int force_true_division
     return CHMY_OK;
 }
 
+bool chmy_fast_disabled() { read_env(); return g_disable_fast; }
+bool chmy_force_true_div() { read_env(); return g_force_true_div; }
+
 static dim3 march_grid(const Box& b) {
     return dim3((unsigned)((b.n[0] + 2 * TX - 1) / (2 * TX)), (unsigned)((b.n[1] + TY - 1) / TY), (unsigned)((b.n[2] + CZ - 1) / CZ));
 }
@@ -375,9 +430,39 @@ int chmy_run_op_fast(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, c
     chmy_field* const* F = d->fields;
     const double* s = d->scalars;
     const double* id = d->grid.inv_spacing;
+    if (nd == 2) return chmy_run_op_fast2d(ctx, d, box, st, handled);
     if (nd != 3 || (box.lo[0] & 1)) return CHMY_OK;
     for (int q = 0; q < d->nfields; ++q)
         if (F[q] && !aligned16(F[q])) return CHMY_OK;
+
+    if (d->op == CHMY_OP_UPDATE_THERMAL_FLUX) {     // fields: qT.x qT.y qT.z T V.x V.y V.z ; scalars: lambda
+        if (!same_strides(F[0], F[4]) || !same_strides(F[1], F[5]) || !same_strides(F[2], F[3]) || !same_strides(F[6], F[3]))
+            return CHMY_OK;
+        Flux3P p;
+        p.qx = F[0]->p0; p.qy = F[1]->p0; p.qz = F[2]->p0; p.T = F[3]->p0;
+        p.Vx = F[4]->p0; p.Vy = F[5]->p0; p.Vz = F[6]->p0;
+        p.cc = strides_of(F[3]); p.vc = strides_of(F[0]); p.cv = strides_of(F[1]);
+        for (int a = 0; a < 3; ++a) { p.lo[a] = box.lo[a]; p.hi[a] = box.lo[a] + box.n[a]; }
+        p.lam = s[0]; p.idx = id[0]; p.idy = id[1]; p.idz = id[2];
+        k_flux3<<<march_grid(box), dim3(TX, TY, 1), 0, st>>>(p);
+        ctx->n_launches++;
+        CHMY_CUDA(cudaGetLastError());
+        *handled = 1;
+        return CHMY_OK;
+    }
+    if (d->op == CHMY_OP_UPDATE_THERMAL) {          // fields: T T_old qT.x qT.y qT.z ; scalars: dt
+        if (!same_strides(F[0], F[1]) || !same_strides(F[4], F[0])) return CHMY_OK;
+        Thermal3P p;
+        p.T = F[0]->p0; p.To = F[1]->p0; p.qx = F[2]->p0; p.qy = F[3]->p0; p.qz = F[4]->p0;
+        p.cc = strides_of(F[0]); p.vc = strides_of(F[2]); p.cv = strides_of(F[3]);
+        for (int a = 0; a < 3; ++a) { p.lo[a] = box.lo[a]; p.hi[a] = box.lo[a] + box.n[a]; }
+        p.dt = s[0]; p.idx = id[0]; p.idy = id[1]; p.idz = id[2];
+        k_thermal3<<<march_grid(box), dim3(TX, TY, 1), 0, st>>>(p);
+        ctx->n_launches++;
+        CHMY_CUDA(cudaGetLastError());
+        *handled = 1;
+        return CHMY_OK;
+    }
 
     if (d->op == CHMY_OP_UPDATE_STRESS) {
         // storage classes must be consistent (they are, for fields created on the same grid)

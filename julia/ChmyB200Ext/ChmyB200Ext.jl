@@ -1,0 +1,229 @@
+# ChmyB200Ext -- Julia glue between Chmy.jl's public API and libchmy_b200.so (include/chmy_b200.h).
+#
+# STATUS: source only.  There is no Julia toolchain in the build image, so this file has never been executed; the
+# same C ABI is exercised by the Python host mirror (chmy.jl_b200/) that the test-suite drives.  It documents, in
+# the reference's own language, exactly which methods a maintainer adds to make the B200 path a drop-in
+# (INTEGRATION.md walks through it).  Struct layouts below must match include/chmy_b200.h; `__init__` verifies
+# them against chmy_struct_size() so that a mismatch fails loudly at load time.
+module ChmyB200Ext
+
+using Chmy
+using Chmy.Architectures, Chmy.Grids, Chmy.Fields, Chmy.BoundaryConditions, Chmy.KernelLaunch, Chmy.Distributed
+import Chmy.Architectures: Arch, get_backend, get_device, activate!, set_device!
+import Chmy.BoundaryConditions: bc!
+import Chmy.Distributed: exchange_halo!
+import KernelAbstractions
+
+const libchmy = get(ENV, "CHMY_B200_LIB", "libchmy_b200.so")
+
+# ------------------------------------------------------------------------------------------------ C structs
+const MAX_DIMS, MAX_BATCH_FIELDS, MAX_OP_FIELDS, MAX_SCALARS = 3, 8, 24, 8
+
+struct GridDesc                       # chmy_grid_desc
+    ndims::Int32
+    _pad::Int32
+    n::NTuple{3,Int64}
+    origin::NTuple{3,Float64}
+    extent::NTuple{3,Float64}
+    spacing::NTuple{3,Float64}
+    inv_spacing::NTuple{3,Float64}
+    connectivity::NTuple{6,Int32}     # [dim][side], row-major
+end
+
+struct BatchDesc                      # chmy_batch_desc
+    kind::Int32
+    nfields::Int32
+    fields::NTuple{8,Ptr{Cvoid}}
+    bc_kind::NTuple{8,Int32}
+    value::NTuple{8,Float64}
+end
+
+struct Inclusion                      # chmy_inclusion
+    active::Int32
+    loc::NTuple{3,Int32}
+    c0::NTuple{3,Float64}
+    r::Float64
+    in::Float64
+    out::Float64
+end
+
+struct LaunchDesc                     # chmy_launch_desc
+    op::Int32
+    flags::Int32
+    grid::GridDesc
+    nfields::Int32
+    nscalars::Int32
+    fields::NTuple{24,Ptr{Cvoid}}
+    scalars::NTuple{8,Float64}
+    rho_g::Inclusion
+    has_bc::Int32
+    has_outer_width::Int32
+    outer_width::NTuple{3,Int64}
+    bc::NTuple{6,BatchDesc}           # [dim][side]
+end
+
+function __init__()
+    for (i, T) in enumerate((GridDesc, BatchDesc, Inclusion, LaunchDesc))
+        want = ccall((:chmy_struct_size, libchmy), Csize_t, (Cint,), i - 1)
+        want == sizeof(T) || error("ChmyB200Ext: layout of $T ($(sizeof(T)) B) differs from the library ($want B)")
+    end
+end
+
+check(rc::Integer) = rc == 0 ? nothing :
+                     error(unsafe_string(ccall((:chmy_last_error, libchmy), Cstring, ())))   # reference style: plain error()
+
+# ------------------------------------------------------------------------------------------------ backend + architecture
+"""The KernelAbstractions-style tag of this path: `Arch(B200Backend(); device_id=1)`."""
+struct B200Backend <: KernelAbstractions.Backend end
+
+mutable struct B200Device              # what `get_device` returns; owns the chmy_ctx (device + streams)
+    ctx::Ptr{Cvoid}
+    id::Int
+end
+
+function get_device(::B200Backend, id::Integer)                       # src/Architectures.jl:46-49 via ChmyCUDAExt.jl:17
+    ref = Ref{Ptr{Cvoid}}()
+    check(ccall((:chmy_ctx_create, libchmy), Cint, (Cint, Ref{Ptr{Cvoid}}), id, ref))
+    dev = B200Device(ref[], id)
+    finalizer(d -> ccall((:chmy_ctx_destroy, libchmy), Cint, (Ptr{Cvoid},), d.ctx), dev)
+    return dev
+end
+set_device!(::B200Device) = nothing                                   # every entry point selects its own device
+KernelAbstractions.synchronize(arch::SingleDeviceArchitecture{B200Backend}) =
+    check(ccall((:chmy_synchronize, libchmy), Cint, (Ptr{Cvoid},), get_device(arch).ctx))
+KernelAbstractions.priority!(::B200Backend, ::Symbol) = nothing       # stream priorities are fixed inside the ctx
+ctx(arch) = get_device(arch).ctx
+
+# ------------------------------------------------------------------------------------------------ fields
+"""Device storage handle standing where the `CuArray` stands in `Field{T,N,L,H,A}` (src/Fields/field.jl:6-11)."""
+mutable struct B200Array{N} <: AbstractArray{Float64,N}
+    handle::Ptr{Cvoid}
+    dims::NTuple{N,Int}               # padded dims (dims .+ 4)
+    arch
+end
+Base.size(a::B200Array) = a.dims
+
+function Fields.Field(arch::SingleDeviceArchitecture{B200Backend}, grid::StructuredGrid{N}, loc, ::Type{Float64}=Float64;
+                      halo=1) where {N}                                # field.jl:56-74
+    halo == 1 || error("the B200 path implements halo = 1")
+    loc  = Fields.expand_loc(Val(N), loc)
+    dims = size(grid, loc)
+    ref  = Ref{Ptr{Cvoid}}()
+    check(ccall((:chmy_field_create, libchmy), Cint,
+                (Ptr{Cvoid}, Cint, Ref{NTuple{3,Int64}}, Ref{NTuple{3,Int32}}, Cint, Ref{Ptr{Cvoid}}),
+                ctx(arch), N, pad3(dims, 1), pad3(map(l -> Int32(l isa Vertex), loc), 0), 0, ref))
+    data = B200Array{N}(ref[], dims .+ 4, arch)
+    finalizer(a -> ccall((:chmy_field_destroy, libchmy), Cint, (Ptr{Cvoid},), a.handle), data)
+    return Field{typeof(loc),1}(data, dims)
+end
+
+pad3(t::NTuple{N}, fill) where {N} = ntuple(i -> i <= N ? Int64(t[i]) : Int64(fill), 3)
+handle(f::Field) = parent(f).handle
+
+# Array(interior(f)) / set!(f, A) / maximum(abs, interior(f)):  sub-box copies and the fused reduction
+function Base.Array(f::Field{Float64,N,L,H,<:B200Array}; with_halo=false) where {N,L,H}
+    lo = ntuple(_ -> with_halo ? 0 : 1, N); hi = size(f) .+ (with_halo ? 1 : 0)
+    out = Array{Float64,N}(undef, (hi .- lo .+ 1)...)
+    check(ccall((:chmy_field_copy_to_host, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ref{NTuple{3,Int64}}, Ref{NTuple{3,Int64}}),
+                ctx(parent(f).arch), handle(f), out, pad3(lo, 0), pad3(hi, 0)))
+    return out
+end
+function Fields.set!(f::Field{Float64,N,L,H,<:B200Array}, A::AbstractArray) where {N,L,H}     # field.jl:98
+    host = Array{Float64,N}(A)
+    check(ccall((:chmy_field_copy_from_host, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ref{NTuple{3,Int64}}, Ref{NTuple{3,Int64}}),
+                ctx(parent(f).arch), handle(f), host, pad3(ntuple(_ -> 1, N), 0), pad3(size(f), 0)))
+    return
+end
+function maxabs(f::Field{Float64,N,L,H,<:B200Array}) where {N,L,H}                             # drivers: maximum(abs.(interior(f)))
+    out = Ref{Float64}()
+    check(ccall((:chmy_field_maxabs, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{NTuple{3,Int64}}, Ref{NTuple{3,Int64}}, Ref{Float64}),
+                ctx(parent(f).arch), handle(f), pad3(ntuple(_ -> 1, N), 0), pad3(size(f), 0), out))
+    return out[]
+end
+
+# ------------------------------------------------------------------------------------------------ descriptors
+function GridDesc(grid::UniformGrid{N}) where {N}
+    conn = ntuple(i -> Int32(connectivity(grid, Dim(cld(i, 2)), Side(2 - i % 2)) isa Connected), 2N)
+    GridDesc(N, 0, pad3(size(grid, Center()), 0), pad3f(origin(grid, Vertex())), pad3f(extent(grid, Vertex())),
+             pad3f(spacing(grid)), pad3f(inv_spacing(grid)), ntuple(i -> i <= 2N ? conn[i] : Int32(0), 6))
+end
+pad3f(t::NTuple{N}) where {N} = ntuple(i -> i <= N ? Float64(t[i]) : 0.0, 3)
+
+const EMPTY_BATCH = BatchDesc(0, 0, ntuple(_ -> C_NULL, 8), ntuple(_ -> Int32(0), 8), ntuple(_ -> 0.0, 8))
+BatchDesc(::EmptyBatch) = EMPTY_BATCH
+BatchDesc(b::ExchangeBatch) = BatchDesc(2, length(b.fields), ntuple(i -> i <= length(b.fields) ? handle(b.fields[i]) : C_NULL, 8),
+                                        ntuple(_ -> Int32(0), 8), ntuple(_ -> 0.0, 8))
+function BatchDesc(b::FieldBatch)                                      # batch.jl:44-54
+    n = length(b.fields)
+    kind(c)  = Int32(c isa FirstOrderBC{<:Any,BoundaryConditions.Neumann})
+    value(c) = c.value === nothing ? 0.0 : Float64(c.value)            # Field- and function-valued BCs: "next" row
+    BatchDesc(1, n, ntuple(i -> i <= n ? handle(b.fields[i]) : C_NULL, 8), ntuple(i -> i <= n ? kind(b.conditions[i]) : Int32(0), 8),
+              ntuple(i -> i <= n ? value(b.conditions[i]) : 0.0, 8))
+end
+batchset(bc::NTuple{N}) where {N} = ntuple(i -> i <= 2N ? BatchDesc(bc[cld(i, 2)][2 - i % 2]) : EMPTY_BATCH, 6)
+
+# op registry: the @kernel functions of the example solvers, identified by name; `flatten` orders their arguments as
+# include/chmy_b200.h documents for each chmy_op.
+const OPS = Dict(:compute_q! => 1, :update_C! => 2, :update_old! => 3, :update_stress! => 4, :update_velocity! => 5,
+                 :update_thermal_flux! => 6, :update_thermal! => 7)
+flat(x::Field) = (handle(x),)
+flat(x::NamedTuple) = mapreduce(flat, (a, b) -> (a..., b...), values(x))     # VectorField / TensorField in declaration order
+flat(::FunctionField) = (C_NULL,)
+function flatten(args)
+    fields  = mapreduce(a -> a isa Union{Field,NamedTuple,FunctionField} ? flat(a) : (), (a, b) -> (a..., b...), args)
+    scalars = Tuple(Float64(a) for a in args if a isa Number)
+    incl    = something(findfirst(a -> a isa FunctionField, args), 0)
+    return fields, scalars, incl == 0 ? Inclusion(0, (0, 0, 0), (0.0, 0.0, 0.0), 0.0, 0.0, 0.0) : Inclusion(args[incl])
+end
+function Inclusion(f::FunctionField{T,N}) where {T,N}                  # FunctionField(init_incl, grid, loc; parameters=(x0, y0[, z0], r, in, out))
+    p = f.parameters
+    Inclusion(1, pad3(map(l -> Int32(l isa Vertex), location(f)), 0), pad3f(Tuple(p)[1:N]), p.r, p.in, p.out)
+end
+
+# ------------------------------------------------------------------------------------------------ the hot entry points
+function (launcher::Launcher)(arch::SingleDeviceArchitecture{B200Backend}, grid, kernel_and_args::Pair; bc=nothing)   # KernelLaunch.jl:105-119
+    kernel, args = kernel_and_args
+    op = get(OPS, nameof(kernel), 0)
+    op == 0 && error("the B200 backend runs the named solver kernels $(keys(OPS)); got $(nameof(kernel))")
+    fields, scalars, incl = flatten(args)
+    ow = outer_width(launcher)
+    desc = LaunchDesc(op, 1 #= BLOCKING: KernelLaunch.jl:117 =#, GridDesc(grid), length(fields), length(scalars),
+                      ntuple(i -> i <= length(fields) ? fields[i] : C_NULL, 24), ntuple(i -> i <= length(scalars) ? scalars[i] : 0.0, 8),
+                      incl, bc === nothing ? 0 : 1, ow === nothing ? 0 : 1, ow === nothing ? (0, 0, 0) : pad3(ow, 0),
+                      bc === nothing ? ntuple(_ -> EMPTY_BATCH, 6) : batchset(bc))
+    check(ccall((:chmy_launch, libchmy), Cint, (Ptr{Cvoid}, Ref{LaunchDesc}), ctx(arch), desc))
+    return
+end
+
+function bc!(arch::SingleDeviceArchitecture{B200Backend}, grid::StructuredGrid, batch::BoundaryConditions.BatchSet)   # batch.jl:20-29
+    check(ccall((:chmy_bc, libchmy), Cint, (Ptr{Cvoid}, Ref{GridDesc}, Ref{NTuple{6,BatchDesc}}, Cint),
+                ctx(arch), GridDesc(grid), batchset(batch), 1))
+    return
+end
+
+# Distributed: Arch(B200Backend(), comm, dims) builds the CartesianTopology with MPI exactly as the reference does
+# (topology.jl:26-41) and then hands rank/size/dims plus an MPI-broadcast NCCL id to chmy_topo_create; after that
+# exchange_halo! never touches MPI.
+function attach_topology!(arch, topo::CartesianTopology)
+    id = zeros(UInt8, 128)
+    global_rank(topo) == 0 && check(ccall((:chmy_comm_unique_id, libchmy), Cint, (Ptr{UInt8},), id))
+    Distributed.MPI.Bcast!(id, 0, cart_comm(topo))
+    d = Int32.(collect(dims(topo)))
+    check(ccall((:chmy_topo_create, libchmy), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int32}, Ptr{UInt8}),
+                ctx(arch), global_size(topo), global_rank(topo), length(d), d, id))
+end
+
+function exchange_halo!(side::Side{S}, dim::Dim{D}, arch::DistributedArchitecture, grid, fields::Vararg{Field,K}) where {S,D,K}   # exchange_halo.jl:13-61
+    hs = collect(map(handle, fields))
+    check(ccall((:chmy_exchange_halo, libchmy), Cint, (Ptr{Cvoid}, Ref{GridDesc}, Cint, Cint, Cint, Ptr{Ptr{Cvoid}}, Cint),
+                ctx(arch), GridDesc(grid), D - 1, S - 1, K, hs, 1))
+    return
+end
+function exchange_halo!(arch::DistributedArchitecture, grid::StructuredGrid, fields::Vararg{Field,K}) where {K}                  # exchange_halo.jl:73-84
+    hs = collect(map(handle, fields))
+    check(ccall((:chmy_exchange_halo_all, libchmy), Cint, (Ptr{Cvoid}, Ref{GridDesc}, Cint, Ptr{Ptr{Cvoid}}, Cint),
+                ctx(arch), GridDesc(grid), K, hs, 1))
+    return
+end
+
+end # module

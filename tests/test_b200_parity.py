@@ -351,23 +351,45 @@ def test_exact_division_by_uniform_scalar(ch, arch, c):
         assert used.value == 1 and bad.value == 0, (c, bad.value)
 
 
-@pytest.mark.parametrize("n", [(130, 19, 70), (63, 9, 5), (64, 8, 64), (65, 17, 65), (1, 1, 1)])
+@pytest.mark.parametrize("n", [(130, 19, 70), (63, 9, 5), (64, 8, 64), (65, 17, 65), (1, 1, 1),
+                               (300, 70), (257, 129), (256, 64), (255, 63), (1, 1), (515, 3)])
 @pytest.mark.parametrize("true_div", [0, 1])
 def test_fast_kernels_equal_generic_kernels(ch, arch, n, true_div):
-    """z-marching / vectorised stress+velocity kernels vs the one-thread-per-cell kernels: identical bits on the full
-    padded arrays for tile-edge sizes (x not a multiple of 64, odd y/z, single cells), incl. a split sub-box."""
+    """Marching / vectorised kernels (3D: ops_fast.cu, 2D: ops_fast2d.cu; stress, velocity, thermal pair) vs the
+    one-thread-per-cell kernels: identical bits on the full padded arrays for tile-edge sizes (x not a multiple of
+    64 or 256, odd y/z, single cells)."""
     from chmy_b200 import drivers as BD
+    nd = len(n)
     res = []
     for fast in (1, 0):
         _set_tuning(disable_fast=0 if fast else 1, true_div=true_div)
         s = BD.Stokes(arch, n, rho_g_function=(n[0] % 2 == 1))
         rng = np.random.default_rng(42)
         for f in s.fields().values():
-            f.from_host(rng.random(tuple(d + 4 for d in f.dims)) - 0.5, [-1] * 3, [d + 2 for d in f.dims])
+            f.from_host(rng.random(tuple(d + 4 for d in f.dims)) - 0.5, [-1] * nd, [d + 2 for d in f.dims])
         s.begin_time_step()
         for _ in range(3):
             s.mechanics()
+            s.thermal()
         res.append({k: f.parent() for k, f in s.fields().items()})
     _set_tuning(0, 0)
     for k in res[0]:
         assert np.array_equal(res[0][k], res[1][k]), k
+
+
+@pytest.mark.parametrize("n", [(300, 70), (257, 129), (64, 64), (3, 2)])
+def test_fast_diffusion_equals_generic(ch, arch, n):
+    """2D diffusion: tuned y-marching kernels vs generic kernels, with and without the split launch."""
+    from chmy_b200 import drivers as BD
+    C0 = np.random.default_rng(5).random(n)
+    res = []
+    for fast, split in ((1, False), (0, False), (1, True)):
+        _set_tuning(disable_fast=0 if fast else 1, true_div=0)
+        ow = (16, 8) if min(n) >= 32 else None
+        s = BD.Diffusion2D(arch, n, C0=C0, outer_width=ow, exact_split=split and ow is not None)
+        s.run(7)
+        res.append({k: f.parent() for k, f in s.fields().items()})
+    _set_tuning(0, 0)
+    for k in res[0]:
+        assert np.array_equal(res[0][k], res[1][k]), k
+        assert np.array_equal(res[0][k], res[2][k]), "split:" + k
