@@ -36,7 +36,7 @@ __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<do
 #define FULL 0xffffffffu
 constexpr int TX = 32;    // lanes per row segment (2 cells each -> 64 cells)
 constexpr int TY = 8;     // rows per CTA
-constexpr int CZ = 64;    // z-planes marched by one CTA
+constexpr int CZ = 16;    // target z-planes marched by one CTA (measured optimum at 767^3: short chunks, many CTAs)
 
 // element strides of the four (x-location, y-location) storage classes
 struct Strides {

@@ -66,6 +66,7 @@ struct Stress3P {
     int lo[3], hi[3];                         // box, hi exclusive
     double idx, idy, idz, eta_ve, dtau_Pr, dtau_r;
     DivC Gdt, eta, three;
+    int sync, cz;                             // sync: keep the warps of a CTA on the same plane (L1 reuse of neighbour rows)
 };
 
 template <bool TD>
@@ -75,15 +76,14 @@ __device__ __forceinline__ double stress_upd(double t, double to, double e2, con
     return t + (r * p.eta_ve) * p.dtau_r;
 }
 
-template <bool TD>
-__global__ void __launch_bounds__(TX* TY, 2) k_stress3(const Stress3P p) {
+template <bool TD, int TYB>
+__global__ void __launch_bounds__(TX* TYB, 16 / TYB) k_stress3(const Stress3P p) {
     const int lane = threadIdx.x;
     const int i = p.lo[0] + (blockIdx.x * TX + lane) * 2;
-    const int j = p.lo[1] + blockIdx.y * TY + threadIdx.y;
-    const int k0 = p.lo[2] + blockIdx.z * CZ;
-    const int k1 = min(k0 + CZ, p.hi[2]);
-    if (j >= p.hi[1]) return;                                  // warp-uniform
-    const int nact = min(max(p.hi[0] - i, 0), 2);              // cells of this lane inside the box
+    const int j = p.lo[1] + blockIdx.y * TYB + threadIdx.y;
+    const int k0 = p.lo[2] + blockIdx.z * p.cz;
+    const int k1 = min(k0 + p.cz, p.hi[2]);
+    const int nact = j < p.hi[1] ? min(max(p.hi[0] - i, 0), 2) : 0;   // cells of this lane inside the box
     const bool act = nact > 0;
     // the +x neighbour of a lane's second cell lives in the next lane unless that lane is outside the box / warp
     const bool xlast = lane == TX - 1 || i + 2 >= p.hi[0];
@@ -94,14 +94,16 @@ __global__ void __launch_bounds__(TX* TY, 2) k_stress3(const Stress3P p) {
     long long vv = (long long)i + (long long)j * p.vv.sy + (long long)k0 * p.vv.sz;
 
     const double2 z2 = make_double2(0.0, 0.0);
-    double2 vx_km = z2, vy_km = z2, vz_k = z2;
+    double2 vx_km = z2, vy_km = z2, vz_k = z2, vzjm = z2;
     if (act) {
         vx_km = ld2(p.Vx + vc - p.vc.sz);
         vy_km = ld2(p.Vy + cv - p.cv.sz);
         vz_k  = ld2(p.Vz + cc);
+        vzjm  = ld2(p.Vz + cc - p.cc.sy);
     }
     for (int k = k0; k < k1; ++k) {
-        double2 vx = z2, vxjm = z2, vy = z2, vyjp = z2, vzkp = z2, vzjm = z2, pr = z2;
+        if (p.sync) __syncthreads();
+        double2 vx = z2, vxjm = z2, vy = z2, vyjp = z2, vzkp = z2, vzjmkp = z2, pr = z2;
         double2 t[6], o[6];
         double  vx_e = 0.0, vy_e = 0.0, vz_e = 0.0;
         if (act) {
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(TX* TY, 2) k_stress3(const Stress3P p) {
             vy   = ld2(p.Vy + cv);
             vyjp = ld2(p.Vy + cv + p.cv.sy);
             vzkp = ld2(p.Vz + cc + p.cc.sz);
-            vzjm = ld2(p.Vz + cc - p.cc.sy);
+            vzjmkp = ld2(p.Vz + cc - p.cc.sy + p.cc.sz);       // same plane as vzkp: the row below loads it in this step
             pr   = ld2(p.Pr + cc);
 #pragma unroll
             for (int c = 0; c < 3; ++c) { t[c] = ld2(p.t[c] + cc); o[c] = ld2(p.o[c] + cc); }
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(TX* TY, 2) k_stress3(const Stress3P p) {
             p.t[4][vc] = tn[4].x;
             p.t[5][cv] = tn[5].x;
         }
-        vx_km = vx; vy_km = vy; vz_k = vzkp;
+        vx_km = vx; vy_km = vy; vz_k = vzkp; vzjm = vzjmkp;
         cc += p.cc.sz; vc += p.vc.sz; cv += p.cv.sz; vv += p.vv.sz;
     }
 }
@@ -186,17 +188,17 @@ struct Velocity3P {
     double idx, idy, idz, nudtau;
     DivC eta_ve;
     InclDev inc;
+    int sync, cz;
 };
 
-template <bool TD, bool FUN>
-__global__ void __launch_bounds__(TX* TY, 2) k_velocity3(const Velocity3P p) {
+template <bool TD, bool FUN, int TYB>
+__global__ void __launch_bounds__(TX* TYB, 16 / TYB) k_velocity3(const Velocity3P p) {
     const int lane = threadIdx.x;
     const int i = p.lo[0] + (blockIdx.x * TX + lane) * 2;
-    const int j = p.lo[1] + blockIdx.y * TY + threadIdx.y;
-    const int k0 = p.lo[2] + blockIdx.z * CZ;
-    const int k1 = min(k0 + CZ, p.hi[2]);
-    if (j >= p.hi[1]) return;
-    const int nact = min(max(p.hi[0] - i, 0), 2);
+    const int j = p.lo[1] + blockIdx.y * TYB + threadIdx.y;
+    const int k0 = p.lo[2] + blockIdx.z * p.cz;
+    const int k1 = min(k0 + p.cz, p.hi[2]);
+    const int nact = j < p.hi[1] ? min(max(p.hi[0] - i, 0), 2) : 0;
     const bool act = nact > 0;
     const bool xlast = lane == TX - 1 || i + 2 >= p.hi[0];
 
@@ -225,6 +227,7 @@ __global__ void __launch_bounds__(TX* TY, 2) k_velocity3(const Velocity3P p) {
         tyzjp_k = ld2(p.t[5] + cv + p.cv.sy);
     }
     for (int k = k0; k < k1; ++k) {
+        if (p.sync) __syncthreads();
         double2 pr = z2, prjm = z2, txx = z2, tyy = z2, tyyjm = z2, tzz = z2, txy = z2, txyjp = z2, txzkp = z2, tyzkp = z2,
                 tyzjpkp = z2, vx = z2, vy = z2, vz = z2, rho = z2;
         double pr_e = 0.0, txx_e = 0.0, txy_e = 0.0, txz_e = 0.0;
@@ -302,6 +305,7 @@ struct Flux3P {
     Strides cc, vc, cv;                       // CC: T Vz qz ; VC: Vx qx ; CV: Vy qy
     int lo[3], hi[3];
     double lam, idx, idy, idz;
+    int sync, cz;
 };
 
 __device__ __forceinline__ double flux1(double nlam, double t, double tm, double v, double id) {
@@ -312,10 +316,9 @@ __global__ void __launch_bounds__(TX* TY) k_flux3(const Flux3P p) {
     const int lane = threadIdx.x;
     const int i = p.lo[0] + (blockIdx.x * TX + lane) * 2;
     const int j = p.lo[1] + blockIdx.y * TY + threadIdx.y;
-    const int k0 = p.lo[2] + blockIdx.z * CZ;
-    const int k1 = min(k0 + CZ, p.hi[2]);
-    if (j >= p.hi[1]) return;
-    const int nact = min(max(p.hi[0] - i, 0), 2);
+    const int k0 = p.lo[2] + blockIdx.z * p.cz;
+    const int k1 = min(k0 + p.cz, p.hi[2]);
+    const int nact = j < p.hi[1] ? min(max(p.hi[0] - i, 0), 2) : 0;
     const bool act = nact > 0;
     long long cc = (long long)i + (long long)j * p.cc.sy + (long long)k0 * p.cc.sz;
     long long vc = (long long)i + (long long)j * p.vc.sy + (long long)k0 * p.vc.sz;
@@ -323,8 +326,8 @@ __global__ void __launch_bounds__(TX* TY) k_flux3(const Flux3P p) {
     const double2 z2 = make_double2(0.0, 0.0);
     const double nlam = -p.lam;
     double2 T_km = act ? ld2(p.T + cc - p.cc.sz) : z2;
-#pragma unroll 2
     for (int k = k0; k < k1; ++k) {
+        if (p.sync) __syncthreads();
         double2 T = z2, Tjm = z2, vx = z2, vy = z2, vz = z2;
         double e = 0.0;
         if (act) {
@@ -357,16 +360,16 @@ struct Thermal3P {
     Strides cc, vc, cv;                       // CC: T To qz ; VC: qx ; CV: qy
     int lo[3], hi[3];
     double dt, idx, idy, idz;
+    int sync, cz;
 };
 
 __global__ void __launch_bounds__(TX* TY) k_thermal3(const Thermal3P p) {
     const int lane = threadIdx.x;
     const int i = p.lo[0] + (blockIdx.x * TX + lane) * 2;
     const int j = p.lo[1] + blockIdx.y * TY + threadIdx.y;
-    const int k0 = p.lo[2] + blockIdx.z * CZ;
-    const int k1 = min(k0 + CZ, p.hi[2]);
-    if (j >= p.hi[1]) return;
-    const int nact = min(max(p.hi[0] - i, 0), 2);
+    const int k0 = p.lo[2] + blockIdx.z * p.cz;
+    const int k1 = min(k0 + p.cz, p.hi[2]);
+    const int nact = j < p.hi[1] ? min(max(p.hi[0] - i, 0), 2) : 0;
     const bool act = nact > 0;
     const bool xlast = lane == TX - 1 || i + 2 >= p.hi[0];
     long long cc = (long long)i + (long long)j * p.cc.sy + (long long)k0 * p.cc.sz;
@@ -374,8 +377,8 @@ __global__ void __launch_bounds__(TX* TY) k_thermal3(const Thermal3P p) {
     long long cv = (long long)i + (long long)j * p.cv.sy + (long long)k0 * p.cv.sz;
     const double2 z2 = make_double2(0.0, 0.0);
     double2 qz = act ? ld2(p.qz + cc) : z2;
-#pragma unroll 2
     for (int k = k0; k < k1; ++k) {
+        if (p.sync) __syncthreads();
         double2 to = z2, qx = z2, qy = z2, qyjp = z2, qzkp = z2;
         double e = 0.0;
         if (act) {
@@ -399,11 +402,18 @@ __global__ void __launch_bounds__(TX* TY) k_thermal3(const Thermal3P p) {
 
 // ---------------------------------------------------------------------------------------------- dispatch
 static bool g_force_true_div = false, g_disable_fast = false, g_env_read = false;
+static int  g_ty = 8, g_sync = 1, g_cz = 0;
 static void read_env() {
     if (g_env_read) return;
     g_env_read = true;
     const char* a = getenv("CHMY_TRUE_DIV");
     const char* b = getenv("CHMY_NO_FAST");
+    const char* h = getenv("CHMY_TY");
+    const char* y = getenv("CHMY_SYNC");
+    const char* z = getenv("CHMY_CZ");
+    if (h) g_ty = atoi(h) == 16 ? 16 : 8;
+    if (y) g_sync = atoi(y);
+    if (z) g_cz = atoi(z);
     g_force_true_div = a && a[0] == '1';
     g_disable_fast   = b && b[0] == '1';
 }
@@ -418,8 +428,13 @@ extern "C" int chmy_set_tuning(int disable_fast_kernels, int force_true_division
 bool chmy_fast_disabled() { read_env(); return g_disable_fast; }
 bool chmy_force_true_div() { read_env(); return g_force_true_div; }
 
-static dim3 march_grid(const Box& b) {
-    return dim3((unsigned)((b.n[0] + 2 * TX - 1) / (2 * TX)), (unsigned)((b.n[1] + TY - 1) / TY), (unsigned)((b.n[2] + CZ - 1) / CZ));
+// z-chunk length: balanced chunks of about `target` planes
+static int pick_cz(int nz, int target) {
+    const int nch = (nz + target - 1) / target;
+    return (nz + nch - 1) / nch;
+}
+static dim3 march_grid2(const Box& b, int ty, int cz) {
+    return dim3((unsigned)((b.n[0] + 2 * TX - 1) / (2 * TX)), (unsigned)((b.n[1] + ty - 1) / ty), (unsigned)((b.n[2] + cz - 1) / cz));
 }
 
 int chmy_run_op_fast(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st, int* handled) {
@@ -444,7 +459,8 @@ int chmy_run_op_fast(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, c
         p.cc = strides_of(F[3]); p.vc = strides_of(F[0]); p.cv = strides_of(F[1]);
         for (int a = 0; a < 3; ++a) { p.lo[a] = box.lo[a]; p.hi[a] = box.lo[a] + box.n[a]; }
         p.lam = s[0]; p.idx = id[0]; p.idy = id[1]; p.idz = id[2];
-        k_flux3<<<march_grid(box), dim3(TX, TY, 1), 0, st>>>(p);
+        p.sync = g_sync; p.cz = pick_cz(box.n[2], g_cz > 0 ? g_cz : CZ);
+        k_flux3<<<march_grid2(box, TY, p.cz), dim3(TX, TY, 1), 0, st>>>(p);
         ctx->n_launches++;
         CHMY_CUDA(cudaGetLastError());
         *handled = 1;
@@ -457,7 +473,8 @@ int chmy_run_op_fast(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, c
         p.cc = strides_of(F[0]); p.vc = strides_of(F[2]); p.cv = strides_of(F[3]);
         for (int a = 0; a < 3; ++a) { p.lo[a] = box.lo[a]; p.hi[a] = box.lo[a] + box.n[a]; }
         p.dt = s[0]; p.idx = id[0]; p.idy = id[1]; p.idz = id[2];
-        k_thermal3<<<march_grid(box), dim3(TX, TY, 1), 0, st>>>(p);
+        p.sync = g_sync; p.cz = pick_cz(box.n[2], g_cz > 0 ? g_cz : CZ);
+        k_thermal3<<<march_grid2(box, TY, p.cz), dim3(TX, TY, 1), 0, st>>>(p);
         ctx->n_launches++;
         CHMY_CUDA(cudaGetLastError());
         *handled = 1;
@@ -483,9 +500,17 @@ int chmy_run_op_fast(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, c
         const double Gdt = s[2] * s[3];
         p.Gdt = DivC{Gdt, 1.0 / Gdt}; p.eta = DivC{s[0], 1.0 / s[0]}; p.three = DivC{3.0, 1.0 / 3.0};
         const bool td = g_force_true_div || !markstein_ok(Gdt) || !markstein_ok(s[0]);
-        const dim3 blk(TX, TY, 1), grd = march_grid(box);
-        if (td) k_stress3<true><<<grd, blk, 0, st>>>(p);
-        else k_stress3<false><<<grd, blk, 0, st>>>(p);
+        const dim3 blk(TX, TY, 1);
+        p.sync = g_sync; p.cz = pick_cz(box.n[2], g_cz > 0 ? g_cz : CZ);
+        if (g_ty == 16) {
+            const dim3 b16(TX, 16, 1), g16 = march_grid2(box, 16, p.cz);
+            if (td) k_stress3<true, 16><<<g16, b16, 0, st>>>(p);
+            else k_stress3<false, 16><<<g16, b16, 0, st>>>(p);
+        } else {
+            const dim3 g8 = march_grid2(box, 8, p.cz);
+            if (td) k_stress3<true, 8><<<g8, blk, 0, st>>>(p);
+            else k_stress3<false, 8><<<g8, blk, 0, st>>>(p);
+        }
         ctx->n_launches++;
         CHMY_CUDA(cudaGetLastError());
         *handled = 1;
@@ -518,13 +543,26 @@ int chmy_run_op_fast(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, c
             p.inc.r2 = d->rho_g.r * d->rho_g.r; p.inc.in = d->rho_g.in; p.inc.out = d->rho_g.out;
         }
         const bool td = g_force_true_div || !markstein_ok(s[0]);
-        const dim3 blk(TX, TY, 1), grd = march_grid(box);
-        if (rho) {
-            if (td) k_velocity3<true, false><<<grd, blk, 0, st>>>(p);
-            else k_velocity3<false, false><<<grd, blk, 0, st>>>(p);
+        const dim3 blk(TX, TY, 1);
+        p.sync = g_sync; p.cz = pick_cz(box.n[2], g_cz > 0 ? g_cz : CZ);
+        if (g_ty == 16) {
+            const dim3 b16(TX, 16, 1), g16 = march_grid2(box, 16, p.cz);
+            if (rho) {
+                if (td) k_velocity3<true, false, 16><<<g16, b16, 0, st>>>(p);
+                else k_velocity3<false, false, 16><<<g16, b16, 0, st>>>(p);
+            } else {
+                if (td) k_velocity3<true, true, 16><<<g16, b16, 0, st>>>(p);
+                else k_velocity3<false, true, 16><<<g16, b16, 0, st>>>(p);
+            }
         } else {
-            if (td) k_velocity3<true, true><<<grd, blk, 0, st>>>(p);
-            else k_velocity3<false, true><<<grd, blk, 0, st>>>(p);
+            const dim3 g8 = march_grid2(box, 8, p.cz);
+            if (rho) {
+                if (td) k_velocity3<true, false, 8><<<g8, blk, 0, st>>>(p);
+                else k_velocity3<false, false, 8><<<g8, blk, 0, st>>>(p);
+            } else {
+                if (td) k_velocity3<true, true, 8><<<g8, blk, 0, st>>>(p);
+                else k_velocity3<false, true, 8><<<g8, blk, 0, st>>>(p);
+            }
         }
         ctx->n_launches++;
         CHMY_CUDA(cudaGetLastError());

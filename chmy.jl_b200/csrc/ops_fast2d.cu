@@ -11,10 +11,11 @@
 #include "fast_common.cuh"
 
 constexpr int WX = 4;      // warps per CTA, side by side in x
-constexpr int CY = 64;     // rows marched by one CTA
+constexpr int CY = 16;     // target rows marched by one CTA (measured optimum: short chunks, many CTAs)
 
 struct Geo2 {
     int lo[2], hi[2];      // box, hi exclusive
+    int cy;                // rows marched by one CTA
 };
 
 // per-thread geometry; returns false when the whole warp lies outside the box (warp-uniform)
@@ -27,8 +28,8 @@ struct Lane2 {
         const int i0  = g.lo[0] + seg * 64;
         if (i0 >= g.hi[0]) return false;
         i     = i0 + lane * 2;
-        j0    = g.lo[1] + blockIdx.y * CY;
-        j1    = min(j0 + CY, g.hi[1]);
+        j0    = g.lo[1] + blockIdx.y * g.cy;
+        j1    = min(j0 + g.cy, g.hi[1]);
         nact  = min(max(g.hi[0] - i, 0), 2);
         act   = nact > 0;
         xlast = lane == TX - 1 || i + 2 >= g.hi[0];
@@ -41,8 +42,8 @@ __device__ __forceinline__ void store_pair(double* p, double2 v, int nact) {
     else if (nact == 1) p[0] = v.x;
 }
 
-static dim3 grid2(const Box& b) {
-    return dim3((unsigned)((b.n[0] + 64 * WX - 1) / (64 * WX)), (unsigned)((b.n[1] + CY - 1) / CY), 1);
+static dim3 grid2(const Box& b, int cy) {
+    return dim3((unsigned)((b.n[0] + 64 * WX - 1) / (64 * WX)), (unsigned)((b.n[1] + cy - 1) / cy), 1);
 }
 
 // ---------------------------------------------------------------------------------------------- compute_q!
@@ -325,6 +326,10 @@ __global__ void __launch_bounds__(TX* WX) k_velocity2(const Velocity2P p) {
 static Geo2 geo_of(const Box& b) {
     Geo2 g;
     for (int a = 0; a < 2; ++a) { g.lo[a] = b.lo[a]; g.hi[a] = b.lo[a] + b.n[a]; }
+    static int target = 0;
+    if (!target) { const char* e = getenv("CHMY_CY"); target = e && atoi(e) > 0 ? atoi(e) : CY; }
+    const int nch = (b.n[1] + target - 1) / target;      // balanced chunks of about `target` rows
+    g.cy = (b.n[1] + nch - 1) / nch;
     return g;
 }
 
@@ -332,7 +337,7 @@ static bool same_sy(const chmy_field* a, const chmy_field* b) { return a->stride
 
 #define LAUNCH2(P, ...)                                               \
     do {                                                              \
-        __VA_ARGS__<<<grid2(box), dim3(TX, WX, 1), 0, st>>>(P);       \
+        __VA_ARGS__<<<grid2(box, g.cy), dim3(TX, WX, 1), 0, st>>>(P);       \
         ctx->n_launches++;                                            \
         CHMY_CUDA(cudaGetLastError());                                \
         *handled = 1;                                                 \
