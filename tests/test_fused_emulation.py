@@ -1,0 +1,158 @@
+"""
+CPU proof of the fused update_stress! + update_velocity! sweep (chmy.jl_b200/csrc/fused_sv.cuh).
+
+The kernel's phase functions are plain C++ shared by nvcc and the host compiler; tests/emul/fused_emul.cpp runs them
+thread by thread over every CTA / cluster of the launch grid with host arrays standing in for shared memory.  The
+result must be bit-identical to the oracle's update_stress! on [0, n+1]^3 followed by update_velocity! on the box
+(stokes_3d_inc_ve_T.jl:23-57): new tau / Pr / divV on the box, new V and r_V on the box, everything else untouched.
+This pins the tile / halo / z-chunk indexing, the "outside the op's range the stored value is the new value" rule and
+the arithmetic order without a GPU; the -m gpu suite then checks the compiled kernel against the same oracle.
+"""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emul", "fused_emul.cpp")
+LIB = os.path.join(HERE, "emul", "libfused_emul.so")
+HDR = os.path.join(HERE, "..", "chmy.jl_b200", "csrc", "fused_sv.cuh")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-march=x86-64-v3", "-shared", "-fPIC", "-Wall",
+                               "-Wno-unknown-pragmas", "-o", LIB, SRC])
+    lib = C.CDLL(LIB)
+    lib.fused_emul_run.restype = C.c_int
+    return lib
+
+
+class Pitched:
+    """A field in the library's PITCHED layout (api.cu chmy_field_create): pitch = roundup(sd0, 16), 15-element lead-in."""
+
+    def __init__(self, dense):
+        self.sd = dense.shape
+        self.pitch = (self.sd[0] + 15) // 16 * 16
+        self.lead = 15
+        n = self.lead + self.pitch * self.sd[1] * self.sd[2] + 32
+        self.flat = np.full(n, 777.25)                    # slack cells hold junk that must never matter
+        self.view()[...] = dense
+        self.sy, self.sz = self.pitch, self.pitch * self.sd[1]
+
+    def view(self):
+        body = self.flat[self.lead:self.lead + self.pitch * self.sd[1] * self.sd[2]]
+        return body.reshape((self.sd[2], self.sd[1], self.pitch)).transpose(2, 1, 0)[:self.sd[0]]
+
+    def p0(self):   # address of logical (0,0,0) = storage (1,1,1)
+        return self.flat.ctypes.data + 8 * (self.lead + 1 + self.sy + self.sz)
+
+    def copy(self):
+        q = Pitched.__new__(Pitched)
+        q.__dict__.update(self.__dict__)
+        q.flat = self.flat.copy()
+        return q
+
+
+def run_case(o, emul, n, box, cz, tyb, cl, td, fun, seed=0):
+    rng = np.random.default_rng(seed)
+    g = o.Grid((-1.0, -1.1, -1.2), (2.0, 2.3, 2.6), n)
+    tau, tau_old, V, rV = o.TensorField(g), o.TensorField(g), o.VectorField(g), o.VectorField(g)
+    Pr, dV = o.Field(g, 0), o.Field(g, 0)
+    rho = o.Field(g, (0, 0, 1))
+    for f in list(tau.values()) + list(tau_old.values()) + list(V.values()) + list(rV.values()) + [Pr, dV, rho]:
+        f.data[...] = rng.random(f.sdims) - 0.5            # interior, halo AND padding
+    eta, G, dt = 10.0, 1.3, 0.07
+    eta_ve = 1.0 / (1.0 / eta + 1.0 / (G * dt))
+    dtau_Pr, dtau_r, nudtau = 0.31, 0.23, 0.011
+    inc = o.Inclusion((0, 0, 1), (0.05, -0.1, 0.1), 0.45, 1.0, 0.25)
+    tn, vn = ("xx", "yy", "zz", "xy", "xz", "yz"), ("x", "y", "z")
+
+    # device-layout copies of the inputs: "current" buffers and shadow ("new") buffers that start as copies
+    cur = {k: Pitched(f.data) for k, f in [("t" + c, tau[c]) for c in tn] + [("o" + c, tau_old[c]) for c in tn] +
+           [("V" + c, V[c]) for c in vn] + [("r" + c, rV[c]) for c in vn] + [("Pr", Pr), ("dV", dV), ("rho", rho)]}
+    new = {k: cur[k].copy() for k in ["t" + c for c in tn] + ["V" + c for c in vn] + ["Pr"]}
+
+    # oracle: stress on the op's full range, velocity on the box
+    full_lo, full_hi = (0, 0, 0), tuple(x + 1 for x in n)
+    o.update_stress(g, (tau, Pr, dV, V, tau_old, eta, eta_ve, G, dt, dtau_Pr, dtau_r), full_lo, full_hi)
+    lo, hi = box
+    o.update_velocity(g, (V, rV, Pr, tau, inc if fun else rho, eta_ve, nudtau), lo, tuple(h - 1 for h in hi))
+
+    order = (["t" + c for c in tn], ["o" + c for c in tn], ["Pr"], ["V" + c for c in vn])
+    ptrs = [cur[k].p0() for grp in order for k in grp]
+    ptrs.append(0 if fun else cur["rho"].p0())
+    ptrs += [new["t" + c].p0() for c in tn] + [new["Pr"].p0(), cur["dV"].p0()] + [new["V" + c].p0() for c in vn]
+    ptrs += [cur["r" + c].p0() for c in vn]
+    assert len(ptrs) == 31
+    P = (C.c_void_p * 31)(*ptrs)
+    cc, vc, cv, vv = cur["Pr"], cur["Vx"], cur["Vy"], cur["txy"]
+    strides = (C.c_int * 8)(cc.sy, cc.sz, vc.sy, vc.sz, cv.sy, cv.sz, vv.sy, vv.sz)
+    assert (cur["txz"].sy, cur["txz"].sz) == (vc.sy, vc.sz) and (cur["tyz"].sy, cur["tyz"].sz) == (cv.sy, cv.sz)
+    bx = (C.c_int * 12)(*lo, *hi, 0, 0, 0, *(x + 2 for x in n))
+    sc = (C.c_double * 9)(*g.inv_spacing, eta_ve, dtau_Pr, dtau_r, nudtau, G * dt, eta)
+    incv = (C.c_double * 12)(*g.origin, *g.spacing, *inc.c0, inc.r * inc.r, inc.inn, inc.out)
+    incloc = (C.c_int * 3)(*inc.loc)
+    rc = emul.fused_emul_run(P, strides, bx, sc, incv, incloc, cz, tyb, cl, int(td))
+    assert rc == 0
+
+    def same(a, b, name):
+        ok = (a == b) | (np.isnan(a) & np.isnan(b))
+        if not ok.all():
+            idx = np.argwhere(~ok)
+            i = tuple(idx[0])
+            raise AssertionError(f"{name}: {len(idx)} cells differ, first at storage {i} (logical {tuple(x - 1 for x in i)}): "
+                                 f"oracle {a[i]!r} fused {b[i]!r}")
+
+    sl = tuple(slice(l + 1, h + 1) for l, h in zip(lo, hi))      # logical -> storage index (+1)
+    # stresses / Pr / divV: the box holds the oracle's new values in the shadow buffers; the rest of the shadow is untouched
+    for c in tn:
+        same(tau[c].data[sl], new["t" + c].view()[sl], "tau." + c)
+    same(Pr.data[sl], new["Pr"].view()[sl], "Pr")
+    same(dV.data[sl], cur["dV"].view()[sl], "divV")
+    for c in vn:
+        same(V[c].data[sl], new["V" + c].view()[sl], "V." + c)
+        same(rV[c].data[sl], cur["r" + c].view()[sl], "r_V." + c)
+    # nothing outside the box was written (compare with pristine copies taken from the inputs)
+    rng2 = np.random.default_rng(seed)
+    g2 = o.Grid((-1.0, -1.1, -1.2), (2.0, 2.3, 2.6), n)
+    tau2, tauo2, V2, rV2 = o.TensorField(g2), o.TensorField(g2), o.VectorField(g2), o.VectorField(g2)
+    Pr2, dV2, rho2 = o.Field(g2, 0), o.Field(g2, 0), o.Field(g2, (0, 0, 1))
+    for f in list(tau2.values()) + list(tauo2.values()) + list(V2.values()) + list(rV2.values()) + [Pr2, dV2, rho2]:
+        f.data[...] = rng2.random(f.sdims) - 0.5
+    pristine = dict([("t" + c, tau2[c]) for c in tn] + [("V" + c, V2[c]) for c in vn] + [("r" + c, rV2[c]) for c in vn] +
+                    [("Pr", Pr2), ("dV", dV2)])
+    for k, f in pristine.items():
+        buf = new[k] if k in new else cur[k]
+        a, b = f.data.copy(), buf.view().copy()
+        a[sl] = 0.0
+        b[sl] = 0.0
+        same(a, b, "outside-box " + k)
+        if k in new:                                       # the current buffers are read-only for the kernel
+            same(f.data, cur[k].view(), "current buffer " + k)
+
+
+CASES = [
+    # n, box (lo, hi exclusive) or None for the full range, cz, tyb, cl
+    ((70, 13, 9), None, 4, 4, 1),
+    ((70, 13, 9), None, 64, 8, 1),
+    ((125, 21, 7), None, 3, 4, 2),
+    ((61, 37, 6), None, 5, 4, 4),
+    ((9, 5, 4), None, 2, 8, 2),
+    ((130, 11, 10), ((6, 3, 2), (97, 9, 8)), 3, 4, 1),          # inner region of a split launch
+    ((130, 11, 10), ((0, 0, 0), (132, 13, 4)), 8, 4, 2),        # z slab
+    ((66, 30, 5), ((64, 0, 0), (68, 32, 7)), 16, 8, 1),         # right x slab
+    ((66, 30, 5), ((0, 4, 1), (8, 29, 6)), 2, 4, 2),            # left x slab, odd hi
+]
+
+
+@pytest.mark.parametrize("n,box,cz,tyb,cl", CASES)
+@pytest.mark.parametrize("td,fun", [(True, False), (False, True)])
+def test_fused_sweep_equals_stress_then_velocity(oracle, emul, n, box, cz, tyb, cl, td, fun):
+    if box is None:
+        box = ((0, 0, 0), tuple(x + 2 for x in n))
+    run_case(oracle, emul, n, box, cz, tyb, cl, td, fun, seed=sum(n) + cz)
