@@ -116,6 +116,22 @@ def launch_count(arch: Architecture) -> int:
     return int(n.value)
 
 
+def set_fusion(arch: Architecture, enable: bool = True):
+    """Lazily fuse `launch(update_stress!)` + `launch(update_velocity!; bc)` of a 3D PT iteration into one sweep
+    (include/chmy_b200.h: chmy_set_fusion).  Results are bit-identical with and without it."""
+    L.check(L.lib().chmy_set_fusion(arch.ctx, 1 if enable else 0))
+
+
+def fused_count(arch: Architecture) -> int:
+    n = C.c_uint64()
+    L.check(L.lib().chmy_fused_count(arch.ctx, C.byref(n)))
+    return int(n.value)
+
+
+def set_fused_tuning(rows_per_cta: int = 0, cluster_size: int = 0, z_chunk: int = 0):
+    L.check(L.lib().chmy_set_fused_tuning(int(rows_per_cta), int(cluster_size), int(z_chunk)))
+
+
 def topology(arch: DistributedArchitecture):
     return arch.topology
 

@@ -71,6 +71,7 @@ extern "C" int chmy_ctx_create(int device_id, chmy_ctx** out) {
 
 extern "C" int chmy_ctx_destroy(chmy_ctx* c) {
     if (!c) return CHMY_OK;
+    c->has_pending = 0;          // a deferred launch whose result nobody can observe any more
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     if (c->comm) chmy_comm_destroy(c->comm);
@@ -96,6 +97,7 @@ extern "C" int chmy_ctx_device(const chmy_ctx* c, int* device_id) {
 
 extern "C" int chmy_synchronize(chmy_ctx* c) {
     CHMY_REQUIRE(c != nullptr, "ctx is NULL");
+    CHMY_TRY(chmy_flush(c));
     CHMY_CUDA(cudaSetDevice(c->device));
     CHMY_CUDA(cudaStreamSynchronize(c->s_bnd));
     CHMY_CUDA(cudaStreamSynchronize(c->s_main));
@@ -110,6 +112,7 @@ extern "C" int chmy_ctx_launch_count(const chmy_ctx* c, uint64_t* kernels) {
 
 extern "C" int chmy_event_record(chmy_ctx* c, int slot) {
     CHMY_REQUIRE(c && slot >= 0 && slot < CHMY_MAX_EVENTS, "bad event slot");
+    CHMY_TRY(chmy_flush(c));
     CHMY_CUDA(cudaSetDevice(c->device));
     if (!c->ev_time) {
         c->ev_time = (cudaEvent_t*)calloc(CHMY_MAX_EVENTS, sizeof(cudaEvent_t));
@@ -179,8 +182,11 @@ extern "C" int chmy_field_create(chmy_ctx* ctx, int ndims, const int64_t* dims, 
 
 extern "C" int chmy_field_destroy(chmy_field* f) {
     if (!f) return CHMY_OK;
+    chmy_flush(f->ctx);
     cudaSetDevice(f->ctx->device);
+    cudaDeviceSynchronize();
     cudaFree(f->alloc);
+    if (f->alt_alloc) cudaFree(f->alt_alloc);
     free(f);
     return CHMY_OK;
 }
@@ -200,6 +206,7 @@ extern "C" int chmy_field_fill(chmy_ctx* ctx, chmy_field* f, double v, const int
     CHMY_REQUIRE(ctx && f && lo && hi, "NULL argument");
     Box b;
     CHMY_TRY(chmy_box_from(f, lo, hi, &b));
+    CHMY_TRY(chmy_flush(ctx));
     CHMY_CUDA(cudaSetDevice(ctx->device));
     return chmy_fill_box(ctx, f, v, b, ctx->s_main);
 }
@@ -210,6 +217,7 @@ extern "C" int chmy_field_copy(chmy_ctx* ctx, chmy_field* dst, const chmy_field*
     Box b, b2;
     CHMY_TRY(chmy_box_from(dst, lo, hi, &b));
     CHMY_TRY(chmy_box_from(src, lo, hi, &b2));
+    CHMY_TRY(chmy_flush(ctx));
     CHMY_CUDA(cudaSetDevice(ctx->device));
     return chmy_copy_box(ctx, dst, src, b, ctx->s_main);
 }
@@ -218,6 +226,8 @@ static int copy_box_host(chmy_ctx* ctx, const chmy_field* f, double* host, const
     Box b;
     CHMY_TRY(chmy_box_from(f, lo, hi, &b));
     if (b.n[0] <= 0 || b.n[1] <= 0 || b.n[2] <= 0) return CHMY_OK;
+    CHMY_TRY(chmy_flush(ctx));
+    if (!to_host) const_cast<chmy_field*>(f)->frame_synced = false;
     CHMY_CUDA(cudaSetDevice(ctx->device));
     double* dev = f->at(b.lo[0], f->nd > 1 ? b.lo[1] : 0, f->nd > 2 ? b.lo[2] : 0);
     cudaMemcpy3DParms p;
@@ -262,6 +272,7 @@ extern "C" int chmy_field_set_inclusion(chmy_ctx* ctx, chmy_field* f, const chmy
     int64_t lo[3] = {1, 1, 1}, hi[3] = {f->d[0], f->d[1], f->d[2]};
     Box b;
     CHMY_TRY(chmy_box_from(f, lo, hi, &b));
+    CHMY_TRY(chmy_flush(ctx));
     CHMY_CUDA(cudaSetDevice(ctx->device));
     return chmy_incl_box(ctx, f, incl_from(g, inc, f->loc), b, ctx->s_main);
 }
@@ -270,6 +281,7 @@ extern "C" int chmy_field_maxabs(chmy_ctx* ctx, const chmy_field* f, const int64
     CHMY_REQUIRE(ctx && f && lo && hi && out, "NULL argument");
     Box b;
     CHMY_TRY(chmy_box_from(f, lo, hi, &b));
+    CHMY_TRY(chmy_flush(ctx));
     CHMY_CUDA(cudaSetDevice(ctx->device));
     CHMY_CUDA(cudaStreamSynchronize(ctx->s_bnd));
     CHMY_CUDA(cudaMemsetAsync(ctx->d_red, 0, sizeof(unsigned long long), ctx->s_main));
@@ -289,6 +301,7 @@ extern "C" int chmy_halo_slab_len(const chmy_field* f, int dim, int64_t* len) {
 static int halo_host(chmy_ctx* ctx, chmy_field* f, int dim, int side, double* host, bool pack) {
     CHMY_REQUIRE(ctx && f && host && dim >= 0 && dim < f->nd && (side == 0 || side == 1), "bad argument");
     const size_t bytes = (size_t)chmy_slab_len(f, dim) * sizeof(double);
+    CHMY_TRY(chmy_flush(ctx));
     double* dbuf = nullptr;
     CHMY_CUDA(cudaSetDevice(ctx->device));
     CHMY_CUDA(cudaMalloc(&dbuf, bytes));
@@ -361,6 +374,7 @@ extern "C" int chmy_bc(chmy_ctx* ctx, const chmy_grid_desc* g, const chmy_batch_
     CHMY_TRY(validate_grid(g));
     bool any_ex = false;
     CHMY_TRY(validate_batches(g, bc, &any_ex));
+    CHMY_TRY(chmy_flush(ctx));
     CHMY_CUDA(cudaSetDevice(ctx->device));
     for (int D = g->ndims - 1; D >= 0; --D)               // D = N..1, side 1 then 2 (batch.jl:20-29)
         CHMY_TRY(bc_dim(ctx, g, D, &bc[D][0], &bc[D][1], ctx->s_main));
@@ -368,20 +382,17 @@ extern "C" int chmy_bc(chmy_ctx* ctx, const chmy_grid_desc* g, const chmy_batch_
     return CHMY_OK;
 }
 
-extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
-    CHMY_REQUIRE(ctx && d, "NULL argument");
+// Region orchestration of `launch` (KernelLaunch.jl:105-183); RUN(box, stream) executes the op on one region.
+template <class RUN>
+static int orchestrate(chmy_ctx* ctx, const chmy_launch_desc* d, const RUN& run) {
     const chmy_grid_desc* g = &d->grid;
-    CHMY_TRY(validate_grid(g));
-    CHMY_TRY(chmy_validate_op(d));
-    CHMY_REQUIRE(d->op != CHMY_OP_NONE, "chmy_launch needs an op (use chmy_bc for a bare batch set)");
-    CHMY_CUDA(cudaSetDevice(ctx->device));
     const int N = g->ndims;
     // worksize = ncenters + 2, I = J + Offset(-1)  ->  I in 0..n+1   (KernelLaunch.jl:41,109)
     Box full;
     for (int a = 0; a < 3; ++a) { full.lo[a] = 0; full.n[a] = a < N ? (int)g->n[a] + 2 : 1; }
 
     if (!d->has_bc) {   // launch_without_bc: one full-range kernel even when the Launcher has an outer_width (:121-126)
-        CHMY_TRY(run_op(ctx, d, full, ctx->s_main));
+        CHMY_TRY(run(full, ctx->s_main));
     } else {
         bool any_ex = false;
         CHMY_TRY(validate_batches(g, d->bc, &any_ex));
@@ -397,7 +408,7 @@ extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
             if (!any_ex && !(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) split = false;
         }
         if (!split) {   // KernelLaunch.jl:156-159
-            CHMY_TRY(run_op(ctx, d, full, ctx->s_main));
+            CHMY_TRY(run(full, ctx->s_main));
             for (int D = N - 1; D >= 0; --D) CHMY_TRY(bc_dim(ctx, g, D, &d->bc[D][0], &d->bc[D][1], ctx->s_main));
         } else {        // KernelLaunch.jl:160-181: inner region on the main stream, slabs + batches on the boundary stream
             // Slab widths per side.  outer_width is a hint (see above): unless EXACT_SPLIT is set the x widths are
@@ -421,7 +432,7 @@ extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
                         else if (a == D) { b.lo[a] = S == 0 ? 0 : full.n[a] - wr[a]; b.n[a] = S == 0 ? wl[a] : wr[a]; }
                         else { b.lo[a] = wl[a]; b.n[a] = full.n[a] - wl[a] - wr[a]; }
                     }
-                    CHMY_TRY(run_op(ctx, d, b, ctx->s_bnd));
+                    CHMY_TRY(run(b, ctx->s_bnd));
                 }
                 CHMY_TRY(bc_dim(ctx, g, D, &d->bc[D][0], &d->bc[D][1], ctx->s_bnd));
             }
@@ -430,11 +441,100 @@ extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
                 in.lo[a] = a < N ? wl[a] : 0;
                 in.n[a]  = a < N ? full.n[a] - wl[a] - wr[a] : 1;
             }
-            CHMY_TRY(run_op(ctx, d, in, ctx->s_main));
+            CHMY_TRY(run(in, ctx->s_main));
             CHMY_CUDA(cudaEventRecord(ctx->ev_join, ctx->s_bnd));
             CHMY_CUDA(cudaStreamWaitEvent(ctx->s_main, ctx->ev_join, 0));
         }
     }
     if (d->flags & CHMY_LAUNCH_BLOCKING) CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));   // KernelLaunch.jl:117
     return CHMY_OK;
+}
+
+// ---- lazily fused update_stress! -> update_velocity! (kernel: ops_fused.cu) -------------------
+// With fusion enabled, `launch(update_stress!)` (3D, no bc) is deferred; if the next call on the context is the
+// matching `launch(update_velocity!; bc)` the two run as ONE sweep, otherwise the deferred launch is executed first
+// (every entry point that can observe device state calls chmy_flush), so results never depend on the setting.
+extern "C" int chmy_set_fusion(chmy_ctx* ctx, int enable) {
+    CHMY_REQUIRE(ctx != nullptr, "ctx is NULL");
+    CHMY_TRY(chmy_flush(ctx));
+    ctx->fuse = enable ? 1 : 0;
+    return CHMY_OK;
+}
+
+extern "C" int chmy_fused_count(const chmy_ctx* ctx, uint64_t* sweeps) {
+    CHMY_REQUIRE(ctx && sweeps, "NULL argument");
+    *sweeps = ctx->n_fused;
+    return CHMY_OK;
+}
+
+static int run_plain(chmy_ctx* ctx, const chmy_launch_desc* d) {
+    return orchestrate(ctx, d, [&](const Box& b, cudaStream_t st) { return run_op(ctx, d, b, st); });
+}
+
+int chmy_flush(chmy_ctx* ctx) {
+    if (!ctx || !ctx->has_pending) return CHMY_OK;
+    ctx->has_pending = 0;
+    CHMY_CUDA(cudaSetDevice(ctx->device));
+    return run_plain(ctx, &ctx->pending);
+}
+
+static int ensure_shadow(chmy_ctx* ctx, chmy_field* f) {
+    if (f->alt_alloc) return CHMY_OK;
+    cudaError_t e = cudaMalloc(&f->alt_alloc, f->bytes);
+    if (e != cudaSuccess) {
+        f->alt_alloc = nullptr;
+        cudaGetLastError();
+        chmy_set_error("cudaMalloc of a %zu-byte shadow buffer failed: %s", f->bytes, cudaGetErrorString(e));
+        return CHMY_ERR_NOMEM;
+    }
+    CHMY_CUDA(cudaMemsetAsync(f->alt_alloc, 0, f->bytes, ctx->s_main));
+    f->frame_synced = false;
+    return CHMY_OK;
+}
+
+static int run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_desc* dv) {
+    // ping-pong fields: tau[6], Pr, V[3]
+    chmy_field* pp[10];
+    for (int c = 0; c < 6; ++c) pp[c] = ds->fields[c];
+    pp[6] = ds->fields[6];
+    for (int c = 0; c < 3; ++c) pp[7 + c] = dv->fields[c];
+    for (int q = 0; q < 10; ++q)
+        if (ensure_shadow(ctx, pp[q]) != CHMY_OK) return 1;      // out of memory: the caller falls back to two kernels
+    // cells outside [0, n+1]^3 are not produced by the sweep: carry them over where they may have changed
+    chmy_field* fr[10];
+    double *fsrc[10], *fdst[10];
+    int nfr = 0;
+    for (int q = 0; q < 10; ++q)
+        if (!pp[q]->frame_synced) { fr[nfr] = pp[q]; fsrc[nfr] = pp[q]->p0; fdst[nfr] = pp[q]->alt_p0(); ++nfr; pp[q]->frame_synced = true; }
+    CHMY_TRY(chmy_frame_copy(ctx, &ds->grid, nfr, fr, fsrc, fdst, ctx->s_main));
+    double *cur[10], *shadow[10];
+    for (int q = 0; q < 10; ++q) { cur[q] = pp[q]->p0; shadow[q] = pp[q]->alt_p0(); }
+    // from here on the fields ARE their new buffers: the boundary batches of this launch act on the new V
+    for (int q = 0; q < 10; ++q) pp[q]->swap_buffers();
+    ctx->n_fused++;
+    return orchestrate(ctx, dv, [&](const Box& b, cudaStream_t st) { return chmy_run_fused(ctx, ds, dv, b, cur, shadow, st); });
+}
+
+extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
+    CHMY_REQUIRE(ctx && d, "NULL argument");
+    const chmy_grid_desc* g = &d->grid;
+    CHMY_TRY(validate_grid(g));
+    CHMY_TRY(chmy_validate_op(d));
+    CHMY_REQUIRE(d->op != CHMY_OP_NONE, "chmy_launch needs an op (use chmy_bc for a bare batch set)");
+    CHMY_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->has_pending && d->op == CHMY_OP_UPDATE_VELOCITY && chmy_fused_eligible(&ctx->pending, d) &&
+        !((d->flags & CHMY_LAUNCH_EXACT_SPLIT) && d->has_outer_width && (d->outer_width[0] & 1))) {
+        ctx->has_pending = 0;
+        const int rc = run_fused(ctx, &ctx->pending, d);
+        if (rc <= 0) return rc;
+        CHMY_TRY(run_plain(ctx, &ctx->pending));    // no memory for the shadow buffers: two kernels
+        return run_plain(ctx, d);
+    }
+    CHMY_TRY(chmy_flush(ctx));
+    if (ctx->fuse && d->op == CHMY_OP_UPDATE_STRESS && g->ndims == 3 && !d->has_bc) {
+        ctx->pending = *d;
+        ctx->has_pending = 1;
+        return CHMY_OK;
+    }
+    return run_plain(ctx, d);
 }

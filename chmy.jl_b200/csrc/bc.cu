@@ -77,6 +77,7 @@ int chmy_run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_
             CHMY_REQUIRE(bd->bc_kind[q] == CHMY_DIRICHLET || bd->bc_kind[q] == CHMY_NEUMANN, "FieldBatch: bad bc kind");
             for (int a = 0; a < g->ndims; ++a)
                 CHMY_REQUIRE(f->d[a] == g->n[a] + (f->loc[a] == CHMY_VERTEX ? 1 : 0), "FieldBatch: field/grid size mismatch");
+            bd->fields[q]->frame_synced = false;      // a halo of a Vertex field lies outside the ops' index range
             BcEntry& e = b.e[b.n++];
             e.f = f->view(); e.kind = bd->bc_kind[q]; e.vertex = f->loc[dim] == CHMY_VERTEX; e.d = (int)f->d[dim];
             e.side = s; e.value = bd->value[q];
@@ -179,6 +180,8 @@ int chmy_pack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const
 }
 int chmy_unpack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, const double* dbuf,
                        cudaStream_t st) {
+    for (int q = 0; q < nf; ++q)
+        if (fs[q]) fs[q]->frame_synced = false;
     return run_slab<false>(ctx, dim, side, nf, fs, const_cast<double*>(dbuf), st);
 }
 
@@ -230,12 +233,15 @@ int chmy_box_from(const chmy_field* f, const int64_t* lo, const int64_t* hi, Box
 }
 
 int chmy_fill_box(chmy_ctx* ctx, chmy_field* f, double v, const Box& b, cudaStream_t st) {
+    f->frame_synced = false;
     return launch_util(ctx, FillF{f->view(), v}, b, st);
 }
 int chmy_copy_box(chmy_ctx* ctx, chmy_field* d, const chmy_field* s, const Box& b, cudaStream_t st) {
+    d->frame_synced = false;
     return launch_util(ctx, CopyF{d->view(), s->view()}, b, st);
 }
 int chmy_incl_box(chmy_ctx* ctx, chmy_field* f, const InclDev& q, const Box& b, cudaStream_t st) {
+    f->frame_synced = false;
     return launch_util(ctx, InclF{f->view(), q}, b, st);
 }
 

@@ -270,6 +270,7 @@ extern "C" int chmy_exchange_halo(chmy_ctx* ctx, const chmy_grid_desc* g, int di
     chmy_batch_desc b[2];
     memset(b, 0, sizeof(b));
     fill_exchange_batch(&b[side], nf, fields);
+    CHMY_TRY(chmy_flush(ctx));
     CHMY_CUDA(cudaSetDevice(ctx->device));
     CHMY_TRY(chmy_exchange_dim(ctx, g, dim, &b[0], &b[1], ctx->s_main));
     if (flags & CHMY_LAUNCH_BLOCKING) CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));
@@ -280,6 +281,7 @@ extern "C" int chmy_exchange_halo(chmy_ctx* ctx, const chmy_grid_desc* g, int di
 extern "C" int chmy_exchange_halo_all(chmy_ctx* ctx, const chmy_grid_desc* g, int nf, chmy_field* const* fields, int flags) {
     CHMY_REQUIRE(ctx && g && fields, "NULL argument");
     CHMY_REQUIRE(nf >= 1 && nf <= CHMY_MAX_BATCH_FIELDS, "bad field count %d", nf);
+    CHMY_TRY(chmy_flush(ctx));
     CHMY_CUDA(cudaSetDevice(ctx->device));
     for (int D = g->ndims - 1; D >= 0; --D) {
         chmy_batch_desc b[2];

@@ -106,6 +106,13 @@ struct chmy_field {
     double*   alloc;       // cudaMalloc'ed base
     size_t    bytes;
     double*   p0;          // address of logical (0,0,0) over active dims
+    // ping-pong shadow of the fused stress+velocity sweep (ops_fused.cu): lazily allocated twin of `alloc`; the two
+    // are swapped after every fused launch.  frame_synced: the cells outside the ops' index range [0, n+1]^N hold the
+    // same values in both buffers (cleared by everything that may write such cells: fill/copy/set!/bc!/halo unpack).
+    double*   alt_alloc;
+    bool      frame_synced;
+    double*   alt_p0() const { return alt_alloc + (p0 - alloc); }
+    void      swap_buffers() { double* a = alloc; const ptrdiff_t o = p0 - alloc; alloc = alt_alloc; alt_alloc = a; p0 = alloc + o; }
 
     FV view() const { return FV{p0, nd > 1 ? stride[1] : 0, nd > 2 ? stride[2] : 0}; }
     double* at(long long i, long long j, long long k) const {
@@ -128,7 +135,15 @@ struct chmy_ctx {
     int          sm_count;
     chmy_comm*   comm;          // null on a single-device architecture
     cudaEvent_t* ev_time;       // lazily created timing events (CHMY_MAX_EVENTS slots)
+    // lazily fused update_stress! -> update_velocity! (api.cu): a deferred stress launch waiting for its velocity launch
+    int               fuse;          // chmy_set_fusion
+    int               has_pending;
+    chmy_launch_desc  pending;
+    uint64_t          n_fused;       // fused sweeps launched so far
 };
+
+// api.cu: runs a deferred update_stress! launch now (every entry point that reads or writes device state calls it)
+int chmy_flush(chmy_ctx* ctx);
 
 static inline dim3 grid_for(const Box& b, dim3 blk) {
     return dim3((unsigned)((b.n[0] + blk.x - 1) / blk.x), (unsigned)((b.n[1] + blk.y - 1) / blk.y),
@@ -145,7 +160,13 @@ int chmy_run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_
 int chmy_comm_destroy(chmy_comm* c);
 int chmy_exchange_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_batch_desc* left,
                       const chmy_batch_desc* right, cudaStream_t st);
-// halo.cu
+// ops_fused.cu
+bool chmy_fused_eligible(const chmy_launch_desc* ds, const chmy_launch_desc* dv);
+int chmy_run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_desc* dv, const Box& box,
+                   double* const* cur, double* const* shadow, cudaStream_t st);
+int chmy_frame_copy(chmy_ctx* ctx, const chmy_grid_desc* g, int n, chmy_field* const* fs, double* const* src,
+                    double* const* dst, cudaStream_t st);
+// bc.cu (halo slabs)
 int chmy_pack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, double* dbuf, cudaStream_t st);
 int chmy_unpack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, const double* dbuf,
                        cudaStream_t st);

@@ -1,0 +1,239 @@
+// ops_fused.cu -- device side and launch glue of the fused update_stress! + update_velocity! sweep (design, data flow
+// and the phase functions: fused_sv.cuh).  One CTA = 32 lanes x TYB warp-rows; CL CTAs stacked along y form a
+// thread-block cluster whose members read each other's boundary rows through distributed shared memory, so only the
+// first and last row of a cluster recompute stresses for their neighbours.
+#include <cooperative_groups.h>
+
+#include "fused_sv.cuh"
+
+namespace cg = cooperative_groups;
+
+__device__ __forceinline__ void fsv_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fsv_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+template <bool TD, bool FUN, int TYB>
+__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB <= 8 ? 16 / TYB : 1)) k_fused_sv(const FusedP p, const int cl) {
+    extern __shared__ __align__(16) double xb[];
+    const int lane = threadIdx.x, ty = threadIdx.y;
+    int cr = 0;
+    const double *below = xb, *above = xb;
+    int rb = ty, ra = ty;
+    if (ty > 0) rb = ty - 1;
+    if (ty < TYB - 1) ra = ty + 1;
+    if (cl > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        cr = (int)cluster.block_rank();
+        if (ty == 0 && cr > 0) { below = cluster.map_shared_rank(xb, cr - 1); rb = TYB - 1; }
+        if (ty == TYB - 1 && cr < cl - 1) { above = cluster.map_shared_rank(xb, cr + 1); ra = 0; }
+    }
+    FusedT s;
+    fsv_init(s, p, lane, ty, cr * TYB + ty, blockIdx.x, blockIdx.y / cl, blockIdx.z, FUN);
+    if (cl > 1) fsv_cluster_arrive();
+    for (int kp = s.k0 - 1; kp <= s.k1; ++kp) {
+        d2 sn[FSV_NF];
+        fsv_phase_a<TD>(s, p, kp, sn);
+        // every thread of the cluster has finished reading the buffer that is about to be overwritten, and the
+        // stresses of plane kp-1 that phase B reads have been published
+        if (cl > 1) fsv_cluster_wait(); else __syncthreads();
+        fsv_phase_b<TD, FUN>(s, p, kp, sn, TYB, xb, below, rb, above, ra);
+        if (cl > 1) fsv_cluster_arrive();
+    }
+    if (cl > 1) fsv_cluster_wait();   // no CTA may exit while a neighbour can still read its shared memory
+}
+
+// ---------------------------------------------------------------------------------------------- frame copy
+// Cells of a ping-pong field that lie outside the op's index range [0, n+1]^N are never written by the sweep; they
+// are carried over from the current buffer to the shadow buffer so that the shadow is a complete field afterwards.
+struct FramePair {
+    const double* src;   // logical (0,0,0) of the current buffer
+    double*       dst;   // ... of the shadow buffer
+    int sy, sz;
+    int d[3];            // logical field dims
+};
+struct FrameBatch {
+    int       n;
+    int       nn[3];     // grid cells per dim: inside = [0, nn+1]
+    FramePair f[10];
+};
+
+__global__ void __launch_bounds__(256) k_frame_copy(const FrameBatch b) {
+    const FramePair& f = b.f[blockIdx.z];
+    // six slabs in logical indices [lo, hi] (inclusive); together they tile storage minus [0, n+1]^3
+    const int slab = blockIdx.y;
+    int lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) { lo[a] = -1; hi[a] = f.d[a] + 2; }
+    const int D = 2 - slab / 2, side = slab & 1;               // z slabs first, then y, then x
+    for (int a = D + 1; a < 3; ++a) { lo[a] = 0; hi[a] = b.nn[a] + 1; }
+    if (side == 0) hi[D] = -1; else lo[D] = b.nn[D] + 2;
+    const long long ex = hi[0] - lo[0] + 1, ey = hi[1] - lo[1] + 1, ez = hi[2] - lo[2] + 1;
+    const long long total = ex * ey * ez;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = lo[0] + (int)(t % ex), j = lo[1] + (int)((t / ex) % ey), k = lo[2] + (int)(t / (ex * ey));
+        const long long off = (long long)i + (long long)j * f.sy + (long long)k * f.sz;
+        f.dst[off] = f.src[off];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static int g_fuse_tyb = 8, g_fuse_cl = 4, g_fuse_cz = 64;
+static bool g_fuse_env = false;
+static void fuse_env() {
+    if (g_fuse_env) return;
+    g_fuse_env = true;
+    const char* a = getenv("CHMY_FUSE_TYB");
+    const char* b = getenv("CHMY_FUSE_CL");
+    const char* c = getenv("CHMY_FUSE_CZ");
+    if (a) { const int v = atoi(a); if (v == 4 || v == 8 || v == 16) g_fuse_tyb = v; }
+    if (b) { const int v = atoi(b); if (v == 1 || v == 2 || v == 4 || v == 8) g_fuse_cl = v; }
+    if (c) { const int v = atoi(c); if (v >= 1) g_fuse_cz = v; }
+}
+
+extern "C" int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_chunk) {
+    fuse_env();
+    if (rows_per_cta > 0) {
+        CHMY_REQUIRE(rows_per_cta == 4 || rows_per_cta == 8 || rows_per_cta == 16, "rows_per_cta must be 4, 8 or 16");
+        g_fuse_tyb = rows_per_cta;
+    }
+    if (cluster_size > 0) {
+        CHMY_REQUIRE(cluster_size == 1 || cluster_size == 2 || cluster_size == 4 || cluster_size == 8, "cluster_size must be 1, 2, 4 or 8");
+        g_fuse_cl = cluster_size;
+    }
+    if (z_chunk > 0) g_fuse_cz = z_chunk;
+    return CHMY_OK;
+}
+
+template <bool TD, bool FUN, int TYB>
+static int launch_fused(const FusedP& p, int cl, dim3 grid, cudaStream_t st) {
+    auto kern = k_fused_sv<TD, FUN, TYB>;
+    const size_t smem = fsv_smem_bytes(TYB);
+    static bool attr_done = false;   // per instantiation
+    if (!attr_done) {
+        CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(FSV_LANES, TYB, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = (unsigned)cl; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = cl > 1 ? 1 : 0;
+    CHMY_CUDA(cudaLaunchKernelEx(&cfg, kern, p, cl));
+    return CHMY_OK;
+}
+
+template <bool TD, bool FUN>
+static int launch_fused_tyb(const FusedP& p, int tyb, int cl, dim3 grid, cudaStream_t st) {
+    switch (tyb) {
+    case 4: return launch_fused<TD, FUN, 4>(p, cl, grid, st);
+    case 16: return launch_fused<TD, FUN, 16>(p, cl, grid, st);
+    default: return launch_fused<TD, FUN, 8>(p, cl, grid, st);
+    }
+}
+
+// fields of the two descriptors (ops.cu / include/chmy_b200.h):
+//   stress  : tau[6] Pr divV V[3] tau_old[6]   scalars eta eta_ve G dt dtau_Pr dtau_r
+//   velocity: V[3] r_V[3] Pr tau[6] rho_g|NULL  scalars eta_ve nudtau
+bool chmy_fused_eligible(const chmy_launch_desc* ds, const chmy_launch_desc* dv) {
+    if (chmy_fast_disabled()) return false;
+    if (ds->grid.ndims != 3 || dv->grid.ndims != 3) return false;
+    for (int a = 0; a < 3; ++a)
+        if (ds->grid.n[a] != dv->grid.n[a] || ds->grid.inv_spacing[a] != dv->grid.inv_spacing[a]) return false;
+    chmy_field* const* S = ds->fields;
+    chmy_field* const* V = dv->fields;
+    for (int c = 0; c < 6; ++c)
+        if (S[c] != V[7 + c]) return false;
+    if (S[6] != V[6]) return false;
+    for (int c = 0; c < 3; ++c)
+        if (S[8 + c] != V[c]) return false;
+    if (ds->scalars[1] != dv->scalars[0]) return false;        // eta_ve
+    for (int q = 0; q < ds->nfields; ++q)
+        if (!S[q] || !aligned16(S[q])) return false;
+    for (int q = 0; q < dv->nfields; ++q)
+        if (V[q] && !aligned16(V[q])) return false;
+    const chmy_field *CC = S[0], *VC = S[4], *CV = S[5], *rho = V[13];
+    if (!same_strides(S[1], CC) || !same_strides(S[2], CC) || !same_strides(S[6], CC) || !same_strides(S[7], CC) ||
+        !same_strides(S[10], CC) || !same_strides(S[8], VC) || !same_strides(S[9], CV) || !same_strides(V[5], CC) ||
+        !same_strides(V[3], VC) || !same_strides(V[4], CV) || (rho && !same_strides(rho, CC)))
+        return false;
+    for (int c = 0; c < 6; ++c)
+        if (!same_strides(S[11 + c], S[c])) return false;
+    return true;
+}
+
+// One sub-box of the fused op.  cur/shadow pointers are passed explicitly (the caller swaps the fields' buffers).
+int chmy_run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_desc* dv, const Box& box,
+                   double* const* cur /* tau[6] Pr V[3] */, double* const* shadow, cudaStream_t st) {
+    if (box.n[0] <= 0 || box.n[1] <= 0 || box.n[2] <= 0) return CHMY_OK;
+    fuse_env();
+    CHMY_REQUIRE((box.lo[0] & 1) == 0, "fused sweep needs an even x origin");
+    chmy_field* const* S = ds->fields;
+    chmy_field* const* V = dv->fields;
+    const double* s = ds->scalars;
+    const double* id = ds->grid.inv_spacing;
+    FusedP p;
+    memset(&p, 0, sizeof(p));
+    for (int c = 0; c < 6; ++c) { p.tc[c] = cur[c]; p.tn[c] = shadow[c]; p.to[c] = S[11 + c]->p0; }
+    p.Prc = cur[6]; p.Prn = shadow[6];
+    for (int c = 0; c < 3; ++c) { p.Vc[c] = cur[7 + c]; p.Vn[c] = shadow[7 + c]; p.r[c] = V[3 + c]->p0; }
+    p.dV = S[7]->p0;
+    const chmy_field* rho = V[13];
+    p.rho = rho ? rho->p0 : nullptr;
+    p.cc = strides_of(S[0]); p.vv = strides_of(S[3]); p.vc = strides_of(S[4]); p.cv = strides_of(S[5]);
+    for (int a = 0; a < 3; ++a) {
+        p.lo[a] = box.lo[a]; p.hi[a] = box.lo[a] + box.n[a];
+        p.flo[a] = 0; p.fhi[a] = (int)ds->grid.n[a] + 2;
+    }
+    p.idx = id[0]; p.idy = id[1]; p.idz = id[2];
+    p.eta_ve = s[1]; p.dtau_Pr = s[4]; p.dtau_r = s[5]; p.nudtau = dv->scalars[1];
+    const double Gdt = s[2] * s[3];
+    p.Gdt = DivC{Gdt, 1.0 / Gdt}; p.eta = DivC{s[0], 1.0 / s[0]}; p.three = DivC{3.0, 1.0 / 3.0};
+    p.eve = DivC{s[1], 1.0 / s[1]};
+    if (!rho) {
+        p.inc.active = 1; p.inc.nd = 3;
+        for (int a = 0; a < 3; ++a) {
+            p.inc.loc[a] = dv->rho_g.loc[a]; p.inc.origin[a] = dv->grid.origin[a];
+            p.inc.spacing[a] = dv->grid.spacing[a]; p.inc.c0[a] = dv->rho_g.c0[a];
+        }
+        p.inc.r2 = dv->rho_g.r * dv->rho_g.r; p.inc.in = dv->rho_g.in; p.inc.out = dv->rho_g.out;
+    }
+    const bool td = chmy_force_true_div() || !markstein_ok(Gdt) || !markstein_ok(s[0]) || !markstein_ok(s[1]);
+    // geometry: clusters shrink for short boxes (slabs of a split launch)
+    int tyb = g_fuse_tyb, cl = g_fuse_cl;
+    while (cl > 1 && (cl / 2) * tyb - 2 >= box.n[1]) cl /= 2;
+    while (tyb > 4 && cl == 1 && tyb / 2 - 2 >= box.n[1]) tyb /= 2;
+    p.rows_int = cl * tyb - 2;
+    const int nch = (box.n[2] + g_fuse_cz - 1) / g_fuse_cz;
+    p.cz = (box.n[2] + nch - 1) / nch;
+    const dim3 grid((unsigned)((box.n[0] + FSV_XI - 1) / FSV_XI), (unsigned)((box.n[1] + p.rows_int - 1) / p.rows_int * cl),
+                    (unsigned)((box.n[2] + p.cz - 1) / p.cz));
+    int rc;
+    if (rho) rc = td ? launch_fused_tyb<true, false>(p, tyb, cl, grid, st) : launch_fused_tyb<false, false>(p, tyb, cl, grid, st);
+    else     rc = td ? launch_fused_tyb<true, true>(p, tyb, cl, grid, st) : launch_fused_tyb<false, true>(p, tyb, cl, grid, st);
+    CHMY_TRY(rc);
+    ctx->n_launches++;
+    return CHMY_OK;
+}
+
+// carries the cells outside [0, n+1]^3 of the listed fields from src to dst (one launch)
+int chmy_frame_copy(chmy_ctx* ctx, const chmy_grid_desc* g, int n, chmy_field* const* fs, double* const* src, double* const* dst,
+                    cudaStream_t st) {
+    if (n <= 0) return CHMY_OK;
+    CHMY_REQUIRE(n <= 10, "too many fields for one frame copy");
+    FrameBatch b;
+    memset(&b, 0, sizeof(b));
+    b.n = n;
+    for (int a = 0; a < 3; ++a) b.nn[a] = (int)g->n[a];
+    for (int q = 0; q < n; ++q) {
+        b.f[q].src = src[q]; b.f[q].dst = dst[q];
+        b.f[q].sy = (int)fs[q]->stride[1]; b.f[q].sz = (int)fs[q]->stride[2];
+        for (int a = 0; a < 3; ++a) b.f[q].d[a] = (int)fs[q]->d[a];
+    }
+    k_frame_copy<<<dim3(64, 6, (unsigned)n), 256, 0, st>>>(b);
+    ctx->n_launches++;
+    CHMY_CUDA(cudaGetLastError());
+    return CHMY_OK;
+}

@@ -204,6 +204,21 @@ int chmy_selftest_division(chmy_ctx* ctx, double c, long long n, unsigned long l
  * parity of the tuned kernels); force_true_division: div.rn.f64 everywhere.  Env: CHMY_NO_FAST=1, CHMY_TRUE_DIV=1. */
 int chmy_set_tuning(int disable_fast_kernels, int force_true_division);
 
+/* ---- lazily fused update_stress! -> update_velocity! (cross-launch fusion) -----------------
+ * The reference runs the two kernels of a PT iteration as two `launch` calls (stokes_3d_inc_ve_T.jl:163-165); the
+ * velocity kernel re-reads what the stress kernel has just written.  With fusion enabled a 3D
+ * `launch(update_stress!)` without bc is deferred, and if the next call on the context is the matching
+ * `launch(update_velocity!; bc)` both run as one sweep that keeps the new stresses on chip (30 instead of 40 array
+ * passes).  Any other call executes the deferred launch first, so results are identical with and without fusion.
+ * The sweep writes tau, Pr and V into shadow buffers that are swapped with the fields' storage afterwards:
+ * pointers obtained from chmy_field_get_info are invalidated by a fused launch (PITCHED layout only; DENSE fields
+ * and anything the sweep cannot handle fall back to the two kernels). */
+int chmy_set_fusion(chmy_ctx* ctx, int enable);
+int chmy_fused_count(const chmy_ctx* ctx, uint64_t* sweeps);          /* fused sweeps launched so far            */
+/* rows of a CTA (4|8|16), CTAs per thread-block cluster along y (1|2|4|8), planes per z-chunk; 0 keeps a setting.
+ * Env: CHMY_FUSE_TYB, CHMY_FUSE_CL, CHMY_FUSE_CZ. */
+int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_chunk);
+
 /* halo slab pack/unpack exposed for bit-exact parity tests of src/Distributed/communication_views.jl:1-34 */
 int chmy_halo_slab_len(const chmy_field* f, int dim, int64_t* len);
 int chmy_halo_pack(chmy_ctx* ctx, const chmy_field* f, int dim, int side, double* host_buf);
