@@ -14,7 +14,7 @@ from .grids import (Location, Center, Vertex, flip, Bounded, Connected, UniformA
                     axes_names)
 from .fields import (AbstractField, Field, FieldTuple, VectorField, TensorField, FunctionField, init_incl, set_,
                      interior, parent, fill_parent_, halo, location, maxabs, vector_location)
-from .boundary_conditions import (FirstOrderBC, Dirichlet, Neumann, EmptyBatch, FieldBatch, ExchangeBatch, batch, bc_)
+from .boundary_conditions import (BoundaryFunction, FirstOrderBC, Dirichlet, Neumann, EmptyBatch, FieldBatch, ExchangeBatch, batch, bc_)
 from .kernel_launch import (Launcher, worksize, outer_width, inner_worksize, inner_offset, outer_worksize,
                             outer_offset)
 from .distributed import (CartesianTopology, TorchDistComm, dims_create, exchange_halo_, allreduce_max, barrier,

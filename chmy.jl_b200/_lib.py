@@ -39,7 +39,8 @@ class GridDesc(C.Structure):
 
 class BatchDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("nfields", C.c_int32), ("fields", C.c_void_p * MAX_BATCH_FIELDS),
-                ("bc_kind", C.c_int32 * MAX_BATCH_FIELDS), ("value", C.c_double * MAX_BATCH_FIELDS)]
+                ("bc_kind", C.c_int32 * MAX_BATCH_FIELDS), ("value", C.c_double * MAX_BATCH_FIELDS),
+                ("value_field", C.c_void_p * MAX_BATCH_FIELDS)]
 
 
 class Inclusion(C.Structure):
@@ -101,12 +102,13 @@ SYMBOLS = {
     "chmy_set_tuning": (C.c_int, [C.c_int, C.c_int]),
     "chmy_set_fusion": (C.c_int, [_vp, C.c_int]),
     "chmy_fused_count": (C.c_int, [_vp, _P(C.c_uint64)]),
-    "chmy_set_fused_tuning": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "chmy_set_fused_tuning": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "chmy_halo_slab_len": (C.c_int, [_vp, C.c_int, _i64p]),
     "chmy_halo_pack": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "chmy_halo_unpack": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
 }
 
+ABI_VERSION = 2
 _lib = None
 
 
@@ -121,7 +123,7 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)          # AttributeError here == ABI mismatch: fail loudly
             fn.restype, fn.argtypes = res, args
-        if L.chmy_abi_version() != 1:
+        if L.chmy_abi_version() != ABI_VERSION:
             raise ChmyError("libchmy_b200.so ABI version mismatch")
         for which, st in enumerate((GridDesc, BatchDesc, Inclusion, LaunchDesc, FieldInfo)):
             if L.chmy_struct_size(which) != C.sizeof(st):

@@ -15,18 +15,93 @@ from .grids import Connected, StructuredGrid
 from .utils import AXES
 
 
+class BoundaryFunction:
+    """BoundaryFunction(fun; discrete=false, parameters=nothing, reduce_dims=true) -- boundary_function.jl:6-44,69-72.
+
+    continuous: bf(grid, loc, dim, I...) = fun(reduce(dim, coord(grid, loc, I...))..., params...)
+    discrete  : bf(grid, loc, dim, I...) = fun(grid, loc, dim, reduce(dim, I)..., params...)
+    `loc` is ONE location (the field's location along the boundary dimension, batch.jl:174) applied to every axis,
+    exactly as `coord(grid, loc::Location, I...)` does (structured_grid.jl:103-106).  `dim` is 1-based.
+    A closure cannot cross the C ABI: `batch`/`bc!` evaluate it on the host into an (N-1)-dimensional device Field
+    (value_field of chmy_batch_desc)."""
+
+    def __init__(self, fun, *, discrete: bool = False, parameters=None, reduce_dims: bool = True):
+        self.fun, self.discrete, self.parameters, self.reduce_dims = fun, bool(discrete), parameters, bool(reduce_dims)
+        self._cache = {}
+
+    def _params(self):
+        if self.parameters is None:
+            return ()
+        return tuple(self.parameters) if isinstance(self.parameters, (tuple, list)) else (self.parameters,)
+
+    def __call__(self, grid, loc, dim: int, *I):
+        from .utils import remove_dim
+        if len(I) != grid.ndims():
+            raise ValueError("a boundary function takes one index per grid dimension")
+        if self.discrete:
+            J = remove_dim(dim, tuple(I)) if self.reduce_dims else tuple(I)
+            return self.fun(grid, loc, dim, *J, *self._params())
+        x = tuple(ax.coord(loc, i) for ax, i in zip(grid.axes, I))
+        x = remove_dim(dim, x) if self.reduce_dims else x
+        return self.fun(*x, *self._params())
+
+
 @dataclass(frozen=True)
 class FirstOrderBC:
     kind: int
-    value: Optional[float] = None      # None is the reference's `nothing` -> zero(eltype(grid))
+    value: object = None      # None is the reference's `nothing` -> zero(eltype(grid)); Number; lower-dimensional
+                              # Field (first_order_boundary_condition.jl:38-40); BoundaryFunction (boundary_function.jl)
+
+
+def _bc_value(value):
+    if value is None or isinstance(value, (Field, BoundaryFunction)):
+        return value
+    if callable(value):       # FirstOrderBC{Kind}(f::Function): continuous, reduced dims (boundary_function.jl:75-78)
+        return BoundaryFunction(value)
+    return float(value)
 
 
 def Dirichlet(value=None) -> FirstOrderBC:
-    return FirstOrderBC(L.DIRICHLET, None if value is None else float(value))
+    return FirstOrderBC(L.DIRICHLET, _bc_value(value))
 
 
 def Neumann(value=None) -> FirstOrderBC:
-    return FirstOrderBC(L.NEUMANN, None if value is None else float(value))
+    return FirstOrderBC(L.NEUMANN, _bc_value(value))
+
+
+def boundary_value_field(arch, grid: StructuredGrid, f: Field, bc: FirstOrderBC, D: int, S: int) -> Field:
+    """Evaluate a BoundaryFunction at every face point the BC kernel visits (transverse indices 0..n_t+2,
+    batch.jl:159-184) with the location / index the rule would pass (first_order_boundary_condition.jl:42-84):
+    Dirichlet on a Vertex field: (Vertex, boundary node 1|d); Dirichlet on a Center field: (Center, halo 0|d+1);
+    Neumann: (flip(loc), halo 0|d+1).  D, S are 0-based here."""
+    from .grids import Center, Vertex, flip
+    from .utils import insert_dim
+    bf: BoundaryFunction = bc.value
+    loc_f = f.loc[D]
+    d = f.dims[D]
+    if bc.kind == L.DIRICHLET and loc_f is Vertex():
+        loc, idx = Vertex(), (1 if S == 0 else d)
+    elif bc.kind == L.DIRICHLET:
+        loc, idx = Center(), (0 if S == 0 else d + 1)
+    else:
+        loc, idx = flip(loc_f), (0 if S == 0 else d + 1)
+    key = (id(arch), tuple((ax.origin, ax.extent, ax.length) for ax in grid.axes), D, S, bc.kind, loc.code, idx)
+    hit = bf._cache.get(key)
+    if hit is not None:
+        return hit
+    N = grid.ndims()
+    taxes = [ax for a, ax in enumerate(grid.axes) if a != D]
+    tgrid = StructuredGrid(taxes, [c for a, c in enumerate(grid.connectivity_) if a != D])
+    vf = Field(arch, tgrid, Vertex())                         # d_t = n_t + 1: logical indices -1..n_t+3 exist
+    ext = [ax.length + 3 for ax in taxes]                     # indices 0..n_t+2
+    import numpy as np
+    vals = np.empty(ext, dtype=np.float64, order="F")
+    for J in np.ndindex(*ext):
+        I = insert_dim(D + 1, tuple(int(j) for j in J), idx)
+        vals[J] = bf(grid, loc, D + 1, *I)
+    vf.from_host(vals, [0] * (N - 1), [e - 1 for e in ext])
+    bf._cache[key] = vf
+    return vf
 
 
 class EmptyBatch:
@@ -102,7 +177,7 @@ def batch(grid: StructuredGrid, *field_bcs, exchange=None):
     return tuple(out)
 
 
-def fill_batch_desc(dst: L.BatchDesc, b):
+def fill_batch_desc(dst: L.BatchDesc, b, arch=None, grid=None, D=None, S=None):
     if isinstance(b, FieldBatch):
         if len(b.fields) > L.MAX_BATCH_FIELDS:
             raise ValueError(f"a FieldBatch holds at most {L.MAX_BATCH_FIELDS} fields on this path")
@@ -110,7 +185,17 @@ def fill_batch_desc(dst: L.BatchDesc, b):
         for q, (f, bc) in enumerate(zip(b.fields, b.conditions)):
             dst.fields[q] = f.handle
             dst.bc_kind[q] = bc.kind
-            dst.value[q] = 0.0 if bc.value is None else bc.value
+            v = bc.value
+            if isinstance(v, BoundaryFunction):
+                if arch is None or grid is None:
+                    raise ValueError("a BoundaryFunction-valued condition needs the architecture and the grid to be lowered")
+                v = boundary_value_field(arch, grid, f, bc, D, S)
+            if isinstance(v, Field):
+                if v.ndims() != f.ndims() - 1:
+                    raise ValueError("a Field-valued condition takes a field with one dimension less than the grid")
+                dst.value[q], dst.value_field[q] = 0.0, v.handle
+            else:
+                dst.value[q], dst.value_field[q] = (0.0 if v is None else v), None
     elif isinstance(b, ExchangeBatch):
         if len(b.fields) > L.MAX_BATCH_FIELDS:
             raise ValueError(f"an ExchangeBatch holds at most {L.MAX_BATCH_FIELDS} fields on this path")
@@ -121,11 +206,11 @@ def fill_batch_desc(dst: L.BatchDesc, b):
         dst.kind, dst.nfields = L.BATCH_EMPTY, 0
 
 
-def batchset_array(batchset):
+def batchset_array(batchset, arch=None, grid=None):
     arr = ((L.BatchDesc * 2) * L.MAX_DIMS)()
     for D, sides in enumerate(batchset):
         for S in range(2):
-            fill_batch_desc(arr[D][S], sides[S])
+            fill_batch_desc(arr[D][S], sides[S], arch, grid, D, S)
     return arr
 
 
@@ -137,5 +222,5 @@ def bc_(arch, grid: StructuredGrid, *field_bcs, exchange=None, blocking: bool = 
     else:
         bs = batch(grid, *field_bcs, exchange=exchange)
     g = grid.desc()
-    arr = batchset_array(bs)
+    arr = batchset_array(bs, arch, grid)
     L.check(L.lib().chmy_bc(arch.ctx, C.byref(g), arr, L.LAUNCH_BLOCKING if blocking else L.LAUNCH_ASYNC))

@@ -45,6 +45,21 @@ extern "C" int chmy_device_count(int* count) {
 }
 
 // ---------------------------------------------------------------------------------------------- context
+// live contexts: a Field may outlive its Architecture in a garbage-collected host language (finalizer order is not
+// defined), so chmy_field_destroy must not touch a context that is already gone
+static chmy_ctx* g_live[256];
+static int g_nlive = 0;
+static void ctx_register(chmy_ctx* c) { if (g_nlive < 256) g_live[g_nlive++] = c; }
+static void ctx_unregister(chmy_ctx* c) {
+    for (int i = 0; i < g_nlive; ++i)
+        if (g_live[i] == c) { g_live[i] = g_live[--g_nlive]; return; }
+}
+static bool ctx_alive(const chmy_ctx* c) {
+    for (int i = 0; i < g_nlive; ++i)
+        if (g_live[i] == c) return true;
+    return false;
+}
+
 extern "C" int chmy_ctx_create(int device_id, chmy_ctx** out) {
     CHMY_REQUIRE(out != nullptr, "out is NULL");
     int ndev = 0;
@@ -65,12 +80,14 @@ extern "C" int chmy_ctx_create(int device_id, chmy_ctx** out) {
     CHMY_CUDA(cudaMalloc(&c->d_red, 64 * sizeof(unsigned long long)));
     CHMY_CUDA(cudaMallocHost(&c->h_red, 64 * sizeof(unsigned long long)));
     CHMY_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+    ctx_register(c);
     *out = c;
     return CHMY_OK;
 }
 
 extern "C" int chmy_ctx_destroy(chmy_ctx* c) {
-    if (!c) return CHMY_OK;
+    if (!c || !ctx_alive(c)) return CHMY_OK;
+    ctx_unregister(c);
     c->has_pending = 0;          // a deferred launch whose result nobody can observe any more
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
@@ -182,9 +199,12 @@ extern "C" int chmy_field_create(chmy_ctx* ctx, int ndims, const int64_t* dims, 
 
 extern "C" int chmy_field_destroy(chmy_field* f) {
     if (!f) return CHMY_OK;
-    chmy_flush(f->ctx);
-    cudaSetDevice(f->ctx->device);
-    cudaDeviceSynchronize();
+    if (ctx_alive(f->ctx)) {     // a deferred launch may still reference the field; kernels in flight may still use it
+        chmy_flush(f->ctx);
+        cudaSetDevice(f->ctx->device);
+        cudaStreamSynchronize(f->ctx->s_bnd);
+        cudaStreamSynchronize(f->ctx->s_main);
+    }
     cudaFree(f->alloc);
     if (f->alt_alloc) cudaFree(f->alt_alloc);
     free(f);

@@ -16,6 +16,8 @@ struct BcEntry {
     int    d;         // logical size of the field along the BC dim
     int    side;      // 0 | 1
     double value;
+    const double* vp; // Field-valued condition: logical (0[,0]) of the (N-1)-dimensional value field, else nullptr
+    long long     vsy;
 };
 
 struct BcBatchDev {
@@ -45,15 +47,17 @@ __global__ void __launch_bounds__(256) k_bc_dim(const BcBatchDev b) {
             if (dd == b.dim) { I[dd] = hnode; N[dd] = bnode; }
             else { I[dd] = N[dd] = (t < 2 ? tr[t] : 0); ++t; }
         }
+        // value(bc, grid, loc, dim, I...): Number | bc.value[remove_dim(dim, I)...]  (first_order_boundary_condition.jl:34-40)
+        const double val = e.vp ? e.vp[(long long)a + (long long)c * e.vsy] : e.value;
         if (e.kind == CHMY_DIRICHLET) {
             if (e.vertex) {
-                fv_st(e.f, N[0], N[1], N[2], e.value);
+                fv_st(e.f, N[0], N[1], N[2], val);
             } else {
                 const double nb = fv_ld(e.f, N[0], N[1], N[2]);
-                fv_st(e.f, I[0], I[1], I[2], fma(2.0, e.value - nb, nb));
+                fv_st(e.f, I[0], I[1], I[2], fma(2.0, val - nb, nb));
             }
         } else {
-            const double qs = e.side == 0 ? -e.value : e.value;
+            const double qs = e.side == 0 ? -val : val;
             fv_st(e.f, I[0], I[1], I[2], fma(b.spacing, qs, fv_ld(e.f, N[0], N[1], N[2])));
         }
     }
@@ -81,6 +85,17 @@ int chmy_run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_
             BcEntry& e = b.e[b.n++];
             e.f = f->view(); e.kind = bd->bc_kind[q]; e.vertex = f->loc[dim] == CHMY_VERTEX; e.d = (int)f->d[dim];
             e.side = s; e.value = bd->value[q];
+            e.vp = nullptr; e.vsy = 0;
+            if (const chmy_field* vf = bd->value_field[q]) {
+                CHMY_REQUIRE(g->ndims >= 2 && vf->nd == g->ndims - 1, "Field-valued condition: the value field must have %d dims", g->ndims - 1);
+                int t = 0;
+                for (int a = 0; a < g->ndims; ++a) {
+                    if (a == dim) continue;
+                    CHMY_REQUIRE(vf->d[t] >= g->n[a], "Field-valued condition: value field too small along transverse dim %d", t + 1);
+                    ++t;
+                }
+                e.vp = vf->p0; e.vsy = vf->nd > 1 ? vf->stride[1] : 0;
+            }
         }
     }
     if (b.n == 0) return CHMY_OK;

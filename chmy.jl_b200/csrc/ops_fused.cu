@@ -12,8 +12,8 @@ __device__ __forceinline__ void fsv_cluster_arrive() { asm volatile("barrier.clu
 __device__ __forceinline__ void fsv_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 template <bool TD, bool FUN, int TYB>
-__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB <= 8 ? 16 / TYB : 1)) k_fused_sv(const FusedP p, const int cl) {
-    extern __shared__ __align__(16) double xb[];
+__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB <= 8 ? 16 / TYB : 1)) k_fused_sv(const FusedP p, const int cl, const int pf) {
+    extern __shared__ __align__(16) double xb[];   // [exchange buffers][stage of the asynchronous copies (pf)]
     const int lane = threadIdx.x, ty = threadIdx.y;
     int cr = 0;
     const double *below = xb, *above = xb;
@@ -27,16 +27,19 @@ __global__ void __launch_bounds__(FSV_LANES* TYB, (TYB <= 8 ? 16 / TYB : 1)) k_f
         if (ty == TYB - 1 && cr < cl - 1) { above = cluster.map_shared_rank(xb, cr + 1); ra = 0; }
     }
     FusedT s;
-    fsv_init(s, p, lane, ty, cr * TYB + ty, blockIdx.x, blockIdx.y / cl, blockIdx.z, FUN);
+    fsv_init(s, p, lane, ty, cr * TYB + ty, blockIdx.x, blockIdx.y / cl, blockIdx.z, FUN,
+             pf ? xb + 2 * FSV_NF * TYB * 64 : nullptr, TYB);
     if (cl > 1) fsv_cluster_arrive();
     for (int kp = s.k0 - 1; kp <= s.k1; ++kp) {
-        d2 sn[FSV_NF];
-        fsv_phase_a<TD>(s, p, kp, sn);
+        d2 sn[FSV_NF], dv;
+        FusedY y;
+        fsv_phase_a<TD>(s, p, kp, sn, dv);
         // every thread of the cluster has finished reading the buffer that is about to be overwritten, and the
-        // stresses of plane kp-1 that phase B reads have been published
+        // stresses of plane kp-1 that phase B1 reads have been published
         if (cl > 1) fsv_cluster_wait(); else __syncthreads();
-        fsv_phase_b<TD, FUN>(s, p, kp, sn, TYB, xb, below, rb, above, ra);
+        fsv_phase_b1(s, kp, sn, TYB, xb, below, rb, above, ra, y);
         if (cl > 1) fsv_cluster_arrive();
+        fsv_phase_b2<TD, FUN>(s, p, kp, sn, dv, y, TYB, xb);
     }
     if (cl > 1) fsv_cluster_wait();   // no CTA may exit while a neighbour can still read its shared memory
 }
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(256) k_frame_copy(const FrameBatch b) {
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static int g_fuse_tyb = 8, g_fuse_cl = 4, g_fuse_cz = 64;
+static int g_fuse_tyb = 8, g_fuse_cl = 2, g_fuse_cz = 64, g_fuse_pf = 1;
 static bool g_fuse_env = false;
 static void fuse_env() {
     if (g_fuse_env) return;
@@ -83,13 +86,16 @@ static void fuse_env() {
     const char* a = getenv("CHMY_FUSE_TYB");
     const char* b = getenv("CHMY_FUSE_CL");
     const char* c = getenv("CHMY_FUSE_CZ");
+    const char* d = getenv("CHMY_FUSE_PF");
+    if (d) g_fuse_pf = atoi(d) != 0;
     if (a) { const int v = atoi(a); if (v == 4 || v == 8 || v == 16) g_fuse_tyb = v; }
     if (b) { const int v = atoi(b); if (v == 1 || v == 2 || v == 4 || v == 8) g_fuse_cl = v; }
     if (c) { const int v = atoi(c); if (v >= 1) g_fuse_cz = v; }
 }
 
-extern "C" int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_chunk) {
+extern "C" int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_chunk, int prefetch) {
     fuse_env();
+    if (prefetch >= 0) g_fuse_pf = prefetch != 0;
     if (rows_per_cta > 0) {
         CHMY_REQUIRE(rows_per_cta == 4 || rows_per_cta == 8 || rows_per_cta == 16, "rows_per_cta must be 4, 8 or 16");
         g_fuse_tyb = rows_per_cta;
@@ -103,12 +109,13 @@ extern "C" int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_c
 }
 
 template <bool TD, bool FUN, int TYB>
-static int launch_fused(const FusedP& p, int cl, dim3 grid, cudaStream_t st) {
+static int launch_fused(const FusedP& p, int cl, int pf, dim3 grid, cudaStream_t st) {
     auto kern = k_fused_sv<TD, FUN, TYB>;
-    const size_t smem = fsv_smem_bytes(TYB);
+    const size_t smem = fsv_smem_bytes(TYB, pf != 0);
     static bool attr_done = false;   // per instantiation
     if (!attr_done) {
-        CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsv_smem_bytes(TYB, true)));
+        CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -121,16 +128,16 @@ static int launch_fused(const FusedP& p, int cl, dim3 grid, cudaStream_t st) {
     at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = (unsigned)cl; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = cl > 1 ? 1 : 0;
-    CHMY_CUDA(cudaLaunchKernelEx(&cfg, kern, p, cl));
+    CHMY_CUDA(cudaLaunchKernelEx(&cfg, kern, p, cl, pf));
     return CHMY_OK;
 }
 
 template <bool TD, bool FUN>
 static int launch_fused_tyb(const FusedP& p, int tyb, int cl, dim3 grid, cudaStream_t st) {
     switch (tyb) {
-    case 4: return launch_fused<TD, FUN, 4>(p, cl, grid, st);
-    case 16: return launch_fused<TD, FUN, 16>(p, cl, grid, st);
-    default: return launch_fused<TD, FUN, 8>(p, cl, grid, st);
+    case 4: return launch_fused<TD, FUN, 4>(p, cl, g_fuse_pf, grid, st);
+    case 16: return launch_fused<TD, FUN, 16>(p, cl, g_fuse_pf, grid, st);
+    default: return launch_fused<TD, FUN, 8>(p, cl, g_fuse_pf, grid, st);
     }
 }
 

@@ -54,7 +54,7 @@ class Launcher:
             d.has_bc = 1
             for D, sides in enumerate(bc):
                 for S in range(2):
-                    fill_batch_desc(d.bc[D][S], sides[S])
+                    fill_batch_desc(d.bc[D][S], sides[S], arch, grid, D, S)
         if self.outer_width_ is not None:
             d.has_outer_width = 1
             for a, w in enumerate(self.outer_width_):

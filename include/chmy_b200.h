@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CHMY_ABI_VERSION 1
+#define CHMY_ABI_VERSION 2
 
 #define CHMY_MAX_DIMS 3
 #define CHMY_MAX_BATCH_FIELDS 8
@@ -91,6 +91,10 @@ typedef struct {
     chmy_field* fields[CHMY_MAX_BATCH_FIELDS];
     int32_t     bc_kind[CHMY_MAX_BATCH_FIELDS];       /* chmy_bc_kind (FIELD batches)                     */
     double      value[CHMY_MAX_BATCH_FIELDS];         /* `nothing` -> 0.0, Number -> value                */
+    chmy_field* value_field[CHMY_MAX_BATCH_FIELDS];   /* Field-valued condition (first_order_boundary_condition.jl:38-40):
+                                                         an (N-1)-dimensional Field read at remove_dim(dim, I); NULL ->
+                                                         value[].  A BoundaryFunction (boundary_function.jl:28-44) is a
+                                                         host closure: the binding evaluates it into such a Field. */
 } chmy_batch_desc;
 
 /* FunctionField with the drivers' `init_incl` body (function_field.jl:12-59,
@@ -215,9 +219,10 @@ int chmy_set_tuning(int disable_fast_kernels, int force_true_division);
  * and anything the sweep cannot handle fall back to the two kernels). */
 int chmy_set_fusion(chmy_ctx* ctx, int enable);
 int chmy_fused_count(const chmy_ctx* ctx, uint64_t* sweeps);          /* fused sweeps launched so far            */
-/* rows of a CTA (4|8|16), CTAs per thread-block cluster along y (1|2|4|8), planes per z-chunk; 0 keeps a setting.
- * Env: CHMY_FUSE_TYB, CHMY_FUSE_CL, CHMY_FUSE_CZ. */
-int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_chunk);
+/* rows of a CTA (4|8|16), CTAs per thread-block cluster along y (1|2|4|8), planes per z-chunk (0 keeps a setting);
+ * prefetch: stage the next plane's tau / tau_old / Pr in shared memory with cp.async (1|0, -1 keeps).
+ * Env: CHMY_FUSE_TYB, CHMY_FUSE_CL, CHMY_FUSE_CZ, CHMY_FUSE_PF. */
+int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_chunk, int prefetch);
 
 /* halo slab pack/unpack exposed for bit-exact parity tests of src/Distributed/communication_views.jl:1-34 */
 int chmy_halo_slab_len(const chmy_field* f, int dim, int64_t* len);

@@ -364,31 +364,44 @@ void og_update_thermal(const og_grid* g, og_field* T, const og_field* T_old, con
  *   Dirichlet, Vertex along dim : f[b]  = v                         b  = 1 | d
  *   Dirichlet, Center along dim : f[h]  = muladd(2, v - f[nb], f[nb])   h = 0 | d+1, nb = 1 | d
  *   Neumann                     : f[h]  = muladd(spacing, -/+q, f[nb])                                   */
-void og_bc_apply(const og_grid* g, og_field* f, int dim, int side, int kind, double value) {
+/* value: nothing -> 0 | Number | lower-dimensional Field indexed by remove_dim(dim, I)
+ * (first_order_boundary_condition.jl:34-40, src/utils.jl:27-34); vf == NULL -> the constant `value` */
+void og_bc_apply_field(const og_grid* g, og_field* f, int dim, int side, int kind, double value, const og_field* vf) {
     int64_t lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
     for (int t = 0; t < g->nd; ++t) hi[t] = g->n[t] + 2;
     const int64_t d = f->d[dim];
     const int64_t b  = side == 0 ? 1 : d;
     const int64_t h  = side == 0 ? 0 : d + 1;
-    const double  qs = side == 0 ? -value : value;
     const double  sp = g->spacing[dim];
     lo[dim] = hi[dim] = 0;
     for (int64_t k = lo[2]; k <= hi[2]; ++k)
         for (int64_t j = lo[1]; j <= hi[1]; ++j)
             for (int64_t i = lo[0]; i <= hi[0]; ++i) {
                 int64_t I[3] = {i, j, k}, N[3] = {i, j, k};
+                double v = value;
+                if (vf) {   /* bc.value[remove_dim(dim, I)...] */
+                    int64_t R[3] = {0, 0, 0};
+                    int t = 0;
+                    for (int a = 0; a < g->nd; ++a) if (a != dim) R[t++] = I[a];
+                    v = AT(vf, R[0], R[1], R[2]);
+                }
+                const double qs = side == 0 ? -v : v;
                 if (kind == OG_DIRICHLET && f->loc[dim] == OG_VERTEX) {
                     I[dim] = b;
-                    AT(f, I[0], I[1], I[2]) = value;
+                    AT(f, I[0], I[1], I[2]) = v;
                 } else if (kind == OG_DIRICHLET) {
                     I[dim] = h; N[dim] = b;
                     double nb = AT(f, N[0], N[1], N[2]);
-                    AT(f, I[0], I[1], I[2]) = fma(2.0, value - nb, nb);
+                    AT(f, I[0], I[1], I[2]) = fma(2.0, v - nb, nb);
                 } else {
                     I[dim] = h; N[dim] = b;
                     AT(f, I[0], I[1], I[2]) = fma(sp, qs, AT(f, N[0], N[1], N[2]));
                 }
             }
+}
+
+void og_bc_apply(const og_grid* g, og_field* f, int dim, int side, int kind, double value) {
+    og_bc_apply_field(g, f, dim, side, kind, value, 0);
 }
 
 /* ---------------------------------------------------------------- halo slabs -------------- */

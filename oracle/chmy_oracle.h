@@ -101,6 +101,8 @@ void og_update_thermal(const og_grid* g, og_field* T, const og_field* T_old, con
 /* one (dim, side) of one field: src/BoundaryConditions/first_order_boundary_condition.jl:34-84,
  * face range from batch.jl:159-184 */
 void og_bc_apply(const og_grid* g, og_field* f, int dim, int side, int kind, double value);
+/* Field-valued condition: vf is a lower-dimensional field read at remove_dim(dim, I) (:38-40) */
+void og_bc_apply_field(const og_grid* g, og_field* f, int dim, int side, int kind, double value, const og_field* vf);
 
 /* halo slabs: src/Distributed/communication_views.jl:1-34 */
 int64_t og_slab_len(const og_field* f, int dim);

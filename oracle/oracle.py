@@ -94,6 +94,7 @@ def lib():
         L.og_update_thermal_flux.argtypes = [P(_CGrid), FPP, FP, FPP, C.c_double] + box
         L.og_update_thermal.argtypes = [P(_CGrid), FP, FP, FPP, C.c_double] + box
         L.og_bc_apply.argtypes = [P(_CGrid), FP, C.c_int, C.c_int, C.c_int, C.c_double]
+        L.og_bc_apply_field.argtypes = [P(_CGrid), FP, C.c_int, C.c_int, C.c_int, C.c_double, FP]
         L.og_slab_len.argtypes = [FP, C.c_int]
         L.og_slab_len.restype = C.c_int64
         L.og_pack_send.argtypes = [FP, C.c_int, C.c_int, P(C.c_double)]
@@ -265,7 +266,31 @@ def set_inclusion(f: Field, inc: Inclusion):
 @dataclass(frozen=True)
 class BC:
     kind: int
-    value: Optional[float] = None     # None == `nothing` -> zero(eltype) (first_order_boundary_condition.jl:34)
+    value: object = None     # None == `nothing` -> zero(eltype) (first_order_boundary_condition.jl:34); Number (:36);
+                             # lower-dimensional Field read at remove_dim(dim, I) (:38-40); BoundaryFunction
+
+
+class BoundaryFunction:
+    """boundary_function.jl:6-44,69-72.  bf(grid, loc, dim, I...) with ONE location for all axes (the location of
+    the field along the boundary dim, batch.jl:174; coord(grid, loc::Location, I...) structured_grid.jl:103-106):
+      continuous: fun(reduce(dim, coord(grid, loc, I...))..., params...)      (:34-36)
+      discrete  : fun(grid, loc, dim, reduce(dim, I)..., params...)           (:38-40)
+    reduce = remove_dim(dim, .) unless reduce_dims=false (:31-32).  dim is 1-based; loc is CENTER | VERTEX."""
+
+    def __init__(self, fun, discrete=False, parameters=None, reduce_dims=True):
+        self.fun, self.discrete, self.parameters, self.reduce_dims = fun, discrete, parameters, reduce_dims
+
+    def _params(self):
+        if self.parameters is None:
+            return ()
+        return tuple(self.parameters) if isinstance(self.parameters, (tuple, list)) else (self.parameters,)
+
+    def __call__(self, grid, loc, dim, *I):
+        red = (lambda t: tuple(x for a, x in enumerate(t, start=1) if a != dim)) if self.reduce_dims else (lambda t: tuple(t))
+        if self.discrete:
+            return self.fun(grid, loc, dim, *red(I), *self._params())
+        x = tuple(grid.coord(a, loc, i) for a, i in enumerate(I))
+        return self.fun(*red(x), *self._params())
 
 
 def Dirichlet(value=None) -> BC:
@@ -326,8 +351,38 @@ def bc_side(grid: Grid, D: int, S: int, b):
     """bc!(side, dim, arch, grid, ::FieldBatch) -- batch.jl:163-184 (fields in batch order)."""
     if b[0] == "field":
         for f, bc in b[1]:
-            v = 0.0 if bc.value is None else float(bc.value)
-            lib().og_bc_apply(C.byref(grid.c), C.byref(f.c), D, S, bc.kind, v)
+            v = bc.value
+            if isinstance(v, BoundaryFunction):
+                v = boundary_value_field(grid, f, bc, D, S)
+            if isinstance(v, Field):
+                lib().og_bc_apply_field(C.byref(grid.c), C.byref(f.c), D, S, bc.kind, 0.0, C.byref(v.c))
+            else:
+                lib().og_bc_apply(C.byref(grid.c), C.byref(f.c), D, S, bc.kind, 0.0 if v is None else float(v))
+
+
+def transverse_grid(grid: Grid, D: int) -> Grid:
+    keep = [a for a in range(grid.nd) if a != D]
+    return Grid([grid.origin[a] for a in keep], [grid.extent[a] for a in keep], [grid.n[a] for a in keep])
+
+
+def boundary_value_field(grid: Grid, f: Field, bc: BC, D: int, S: int) -> Field:
+    """The values value(bc, grid, loc, dim, I_f...) takes over the face range 0..n_t+2 (batch.jl:159-184), with the
+    (loc, index along D) each rule passes (first_order_boundary_condition.jl:42-84), as an (N-1)-dim Field."""
+    d = f.dims[D]
+    if bc.kind == DIRICHLET and f.loc[D] == VERTEX:
+        loc, idx = VERTEX, (1 if S == 0 else d)
+    elif bc.kind == DIRICHLET:
+        loc, idx = CENTER, (0 if S == 0 else d + 1)
+    else:
+        loc, idx = 1 - f.loc[D], (0 if S == 0 else d + 1)
+    tg = transverse_grid(grid, D)
+    vf = Field(tg, VERTEX)
+    ext = [n + 3 for n in tg.n]
+    for J in np.ndindex(*ext):
+        I = list(int(j) for j in J)
+        I.insert(D, idx)
+        vf.data[tuple(j + 1 for j in J)] = bc.value(grid, loc, D + 1, *I)
+    return vf
 
 
 # ------------------------------------------------------------------------------------------------ topology

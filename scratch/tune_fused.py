@@ -25,8 +25,8 @@ ch.set_fusion(arch, False)
 ms = timeit()
 print(f"unfused            : {ms:8.3f} ms  T_eff {A/ms/1e6:8.1f} GB/s", flush=True)
 ch.set_fusion(arch, True)
-geoms = [(8, 4, 64), (8, 8, 64), (8, 2, 64), (8, 1, 64), (4, 8, 64), (4, 4, 64), (16, 1, 64), (16, 2, 64), (16, 4, 64),
-         (8, 4, 32), (8, 4, 128), (8, 4, 256), (8, 8, 128), (4, 8, 128), (8, 4, 800)]
+geoms = [(8, 2, 64, 0), (8, 2, 64, 1), (8, 4, 64, 1), (8, 1, 64, 1), (8, 8, 64, 1), (4, 4, 64, 1), (4, 8, 64, 1), (4, 2, 64, 1),
+         (16, 1, 64, 1), (16, 2, 64, 1), (16, 2, 64, 0), (8, 2, 32, 1), (8, 2, 128, 1), (8, 2, 256, 1), (8, 4, 128, 1), (16, 2, 128, 1)]
 out = {}
 for g in geoms:
     ch.set_fused_tuning(*g)
@@ -36,6 +36,6 @@ for g in geoms:
         print(g, "FAILED", e, flush=True)
         continue
     out[str(g)] = ms
-    print(f"fused tyb,cl,cz={g!s:14}: {ms:8.3f} ms  T_eff {A/ms/1e6:8.1f} GB/s", flush=True)
+    print(f"fused tyb,cl,cz,pf={g!s:14}: {ms:8.3f} ms  T_eff {A/ms/1e6:8.1f} GB/s", flush=True)
 json.dump(out, open("gpurun_out/tune_fused.json", "w"))
 arch.close()

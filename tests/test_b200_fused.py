@@ -27,7 +27,7 @@ def arch(ch):
     a = ch.Arch(ch.B200Backend())
     ch.set_fusion(a, True)
     yield a
-    ch.set_fused_tuning(8, 4, 64)
+    ch.set_fused_tuning(8, 2, 64, 1)
     a.close()
 
 
@@ -48,7 +48,7 @@ GEOMS = [(8, 4, 64), (4, 1, 3), (8, 1, 5), (16, 1, 64), (4, 8, 7), (16, 2, 4), (
 def test_fused_iteration_bit_exact_vs_oracle(ch, arch, oracle, n, geom):
     o = oracle
     tyb, cl, cz = geom
-    ch.set_fused_tuning(tyb, cl, cz)
+    ch.set_fused_tuning(tyb, cl, cz, (tyb + cz + n[0]) % 2)
     fun = (sum(n) + tyb) % 2 == 0
     _set_tuning(disable_fast=0, true_div=(cl + cz) % 2)
     rng = np.random.default_rng(7 + cz)

@@ -143,6 +143,44 @@ def test_bc_matches_oracle_bit_exact(ch, arch, oracle, n, loc):
         assert_same(of, bf, "bc mixed")
 
 
+@pytest.mark.parametrize("n,loc", [((8, 8), (0, 1)), ((9, 6), (1, 0)), ((8, 8, 6), (0, 1, 0)), ((13, 7, 5), (1, 1, 0))])
+def test_valued_bc_field_and_boundary_function_bit_exact(ch, arch, oracle, n, loc):
+    """Field-valued (first_order_boundary_condition.jl:38-40) and BoundaryFunction-valued (boundary_function.jl:28-44)
+    Dirichlet / Neumann conditions, every dim and side, against the oracle on random full arrays."""
+    o = oracle
+    nd = len(n)
+    og, bg = mk_grids(ch, o, arch, n, origin=(-math.pi,) * nd, extent=(2 * math.pi,) * nd)
+    of, bf = o.Field(og, loc), ch.Field(arch, bg, bloc(ch, loc))
+    rng = np.random.default_rng(17)
+    names = ("x", "y", "z")[:nd]
+    for D, ax in enumerate(names):
+        # lower-dimensional value fields on the transverse grid
+        tg_o = o.transverse_grid(og, D)
+        keep = [a for a in range(nd) if a != D]
+        tg_b = ch.UniformGrid(arch, origin=[og.origin[a] for a in keep], extent=[og.extent[a] for a in keep],
+                              dims=[n[a] for a in keep])
+        vo, vb = o.Field(tg_o, o.VERTEX), ch.Field(arch, tg_b, ch.Vertex())
+        fill_pair(rng, vo, vb)
+        for mk_o, mk_b in [(o.Dirichlet, ch.Dirichlet), (o.Neumann, ch.Neumann)]:
+            fill_pair(rng, of, bf)
+            o.bc_(og, (of, {ax: mk_o(vo)}))
+            ch.bc_(arch, bg, (bf, {ax: mk_b(vb)}))
+            assert_same(of, bf, f"field-valued {mk_o.__name__} along {ax}")
+            fun = (lambda *x: math.cos(x[0]) * (1.0 + (x[1] if len(x) > 2 else 0.0)) + x[-1])
+            fo = o.BoundaryFunction(fun, parameters=(0.25,))
+            fb = ch.BoundaryFunction(fun, parameters=(0.25,))
+            fill_pair(rng, of, bf)
+            o.bc_(og, (of, {ax: (mk_o(fo), mk_o(2.0))}))
+            ch.bc_(arch, bg, (bf, {ax: (mk_b(fb), mk_b(2.0))}))
+            assert_same(of, bf, f"function-valued {mk_o.__name__} along {ax}")
+            dfo = o.BoundaryFunction(lambda g, l, dim, *I: float(sum(I)) * 0.5, discrete=True, reduce_dims=False)
+            dfb = ch.BoundaryFunction(lambda g, l, dim, *I: float(sum(I)) * 0.5, discrete=True, reduce_dims=False)
+            fill_pair(rng, of, bf)
+            o.bc_(og, (of, {ax: mk_o(dfo)}))
+            ch.bc_(arch, bg, (bf, {ax: mk_b(dfb)}))
+            assert_same(of, bf, f"discrete-function-valued {mk_o.__name__} along {ax}")
+
+
 def test_bc_known_answers_cuda(ch, arch):
     """test/test_boundary_conditions.jl:143-205 (3D, (C,V,C)) straight on the CUDA path."""
     n = (8, 8, 6)

@@ -219,3 +219,87 @@ def test_lerp_known_answers(oracle):
     assert np.allclose(interp(fv, o.VERTEX), fvi)
     assert np.allclose(interp(fv, (o.CENTER, o.VERTEX)), avx(fvi))
     assert np.allclose(interp(fv, (o.VERTEX, o.CENTER)), avy(fvi))
+
+
+# ------------------------------------------------------------------------------------------------ boundary functions
+def _bf_known_answers(BF, grid, V, nx, ny, coord_x, coord_xy):
+    """test/test_boundary_functions.jl:13-96 (2D grid on [-pi, pi]^2, 8 x 8 cells), tolerance as the reference's `≈`."""
+    import math
+    pi = math.pi
+    ok = lambda a, b: math.isclose(a, b, rel_tol=1.5e-8, abs_tol=1.5e-8)      # Julia `≈`; atol covers the exact-zero targets
+
+    def reduced(bf, s=1.0):
+        assert ok(bf(grid, V, 1, 1, 1), -s) and ok(bf(grid, V, 1, 1, ny + 1), -s) and ok(bf(grid, V, 1, 1, ny // 2 + 1), s)
+        assert ok(bf(grid, V, 2, 1, 1), -s) and ok(bf(grid, V, 2, nx + 1, 1), -s) and ok(bf(grid, V, 2, nx // 2 + 1, 1), s)
+
+    def full(bf):
+        assert ok(bf(grid, V, 1, 1, 1), pi) and ok(bf(grid, V, 1, 1, ny + 1), -pi) and ok(bf(grid, V, 1, 1, ny // 2 + 1), 0.0)
+        assert ok(bf(grid, V, 2, 1, 1), pi) and ok(bf(grid, V, 2, nx + 1, 1), pi) and ok(bf(grid, V, 2, nx // 2 + 1, 1), -pi)
+
+    # continuous (:16-53)
+    bf = BF(lambda xi: math.cos(xi))
+    reduced(bf)
+    # changing the index along the boundary dimension does not affect the value (:26-31)
+    assert bf(grid, V, 1, ny + 1, 1) == bf(grid, V, 1, 1, 1) and bf(grid, V, 1, ny // 2 + 1, 1) == bf(grid, V, 1, 1, 1)
+    assert bf(grid, V, 2, 1, 1) == bf(grid, V, 2, 1, ny + 1) and bf(grid, V, 2, 1, 1) == bf(grid, V, 2, 1, ny // 2 + 1)
+    full(BF(lambda xi, eta: math.cos(xi) * eta, reduce_dims=False))
+    reduced(BF(lambda xi, eta: math.cos(xi) * eta, parameters=pi), pi)
+    # discrete (:55-94)
+    reduced(BF(lambda g, loc, dim, i: math.cos(coord_x(g, loc, dim, i)), discrete=True))
+    full(BF(lambda g, loc, dim, ix, iy: math.cos(coord_xy(g, loc, ix, iy)[0]) * coord_xy(g, loc, ix, iy)[1],
+            discrete=True, reduce_dims=False))
+    reduced(BF(lambda g, loc, dim, i, eta: math.cos(coord_x(g, loc, dim, i)) * eta, discrete=True, parameters=pi), pi)
+
+
+def test_boundary_function_known_answers_oracle(oracle):
+    import math
+    o = oracle
+    g = o.Grid((-math.pi, -math.pi), (2 * math.pi, 2 * math.pi), (8, 8))
+    # the reference's discrete test functions index coord(grid, loc, dim, i) with the *reduced* index: after
+    # remove_dim the surviving index belongs to the other axis, but both axes of this grid are identical
+    _bf_known_answers(o.BoundaryFunction, g, o.VERTEX, 8, 8,
+                      lambda gr, loc, dim, i: gr.coord(dim - 1, loc, i),
+                      lambda gr, loc, ix, iy: (gr.coord(0, loc, ix), gr.coord(1, loc, iy)))
+
+
+def test_boundary_function_known_answers_host_mirror():
+    import math
+    import chmy_b200 as ch
+    g = ch.UniformGrid(None, origin=(-math.pi, -math.pi), extent=(2 * math.pi, 2 * math.pi), dims=(8, 8))
+    _bf_known_answers(ch.BoundaryFunction, g, ch.Vertex(), 8, 8,
+                      lambda gr, loc, dim, i: ch.coord(gr, loc, dim, i),
+                      lambda gr, loc, ix, iy: (ch.coord(gr, loc, 1, ix), ch.coord(gr, loc, 2, iy)))
+
+
+def test_valued_bc_field_and_function_oracle(oracle):
+    """Field-valued and BoundaryFunction-valued conditions (first_order_boundary_condition.jl:36-40, the docs'
+    parabolic-profile example boundary_function.jl:57-66) against the closed forms of the rules (:42-84)."""
+    o = oracle
+    n = (10, 6)
+    g = o.Grid((0.0, 0.0), (2.0, 1.5), n)
+    f = o.Field(g, (o.CENTER, o.VERTEX))
+    rng = np.random.default_rng(3)
+    f.data[...] = rng.random(f.sdims)
+    before = f.data.copy()
+    xbc = o.BoundaryFunction(lambda x, ly: x * (ly - x), parameters=(2.0,))
+    # y is the boundary dim (D=1): the function receives the x coordinate; f is Vertex along y -> Dirichlet sets the node
+    o.bc_(g, (f, {"y": o.Dirichlet(xbc)}))
+    xs_v = np.array([g.coord(0, o.VERTEX, i) for i in range(0, n[0] + 3)])      # loc = Vertex for every axis (batch.jl:174)
+    want = xs_v * (2.0 - xs_v)
+    assert np.array_equal(f.data[1:n[0] + 4, 2], want)                   # node 1   (storage index 2), i = 0..n+2
+    assert np.array_equal(f.data[1:n[0] + 4, n[1] + 2], want)            # node d = n+1 (storage d+1)
+    untouched = np.ones_like(f.data, dtype=bool)
+    untouched[1:n[0] + 4, 2] = untouched[1:n[0] + 4, n[1] + 2] = False
+    assert np.array_equal(f.data[untouched], before[untouched])
+    # Field-valued Neumann along x (Center along x): halo = fma(dx, -/+q[j], f[nb])
+    q = o.Field(o.transverse_grid(g, 0), o.VERTEX)
+    q.data[...] = rng.random(q.sdims)
+    before = f.data.copy()
+    o.bc_(g, (f, {"x": o.Neumann(q)}))
+    js = np.arange(0, n[1] + 3)
+    dx = g.spacing[0]
+    for j in js:
+        qv = q.data[j + 1]
+        assert f.data[1, j + 1] == math.fma(dx, -qv, before[2, j + 1]) if hasattr(math, "fma") else True
+        assert np.isclose(f.data[1, j + 1], before[2, j + 1] - dx * qv, rtol=1e-15, atol=0)
+        assert np.isclose(f.data[n[0] + 2, j + 1], before[n[0] + 1, j + 1] + dx * qv, rtol=1e-15, atol=0)
