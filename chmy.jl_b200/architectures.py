@@ -128,8 +128,8 @@ def fused_count(arch: Architecture) -> int:
     return int(n.value)
 
 
-def set_fused_tuning(rows_per_cta: int = 0, cluster_size: int = 0, z_chunk: int = 0, prefetch: int = -1):
-    L.check(L.lib().chmy_set_fused_tuning(int(rows_per_cta), int(cluster_size), int(z_chunk), int(prefetch)))
+def set_fused_tuning(rows_per_cta: int = 0, cluster_size: int = 0, z_chunk: int = 0, variant: int = -1):
+    L.check(L.lib().chmy_set_fused_tuning(int(rows_per_cta), int(cluster_size), int(z_chunk), int(variant)))
 
 
 def topology(arch: DistributedArchitecture):

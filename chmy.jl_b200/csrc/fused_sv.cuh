@@ -68,21 +68,6 @@ static inline d2 ld2(const double* p) { return d2{p[0], p[1]}; }
 static inline void st2(double* p, d2 v) { p[0] = v.x; p[1] = v.y; }
 #endif
 
-// asynchronous 16-byte global -> shared copies (cp.async): the tau / tau_old / Pr operands of plane kp+1 travel while
-// plane kp is being computed, without holding registers.  A thread only ever reads back the slots it filled itself.
-#ifdef __CUDACC__
-FHD void fsv_cp16(double* dst_smem, const double* src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-}
-FHD void fsv_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-FHD void fsv_cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-#else
-FHD void fsv_cp16(double* dst_smem, const double* src) { dst_smem[0] = src[0]; dst_smem[1] = src[1]; }
-FHD void fsv_cp_commit() {}
-FHD void fsv_cp_wait() {}
-#endif
-
 constexpr int FSV_LANES = 32;
 constexpr int FSV_XI    = 60;   // interior cells of a 64-cell row segment
 constexpr int FSV_NF    = 7;    // published per plane: Pr xx yy zz xy xz yz
@@ -103,12 +88,7 @@ struct FusedP {
 
 // shared-memory exchange buffer of one CTA: [2 plane parities][FSV_NF][TYB rows][64 cells]
 FHD int fsv_xoff(int tyb, int buf, int f, int row) { return ((buf * FSV_NF + f) * tyb + row) * 64; }
-constexpr int FSV_NST = 13;     // staged operands: tau[6], tau_old[6], Pr
-static inline size_t fsv_xbuf_doubles(int tyb) { return (size_t)2 * FSV_NF * tyb * 64; }
-// [exchange buffers][stage: FSV_NST x TYB rows x 64 cells, only with prefetch]
-static inline size_t fsv_smem_bytes(int tyb, bool prefetch) {
-    return (fsv_xbuf_doubles(tyb) + (prefetch ? (size_t)FSV_NST * tyb * 64 : 0)) * sizeof(double);
-}
+static inline size_t fsv_smem_bytes(int tyb) { return (size_t)2 * FSV_NF * tyb * 64 * sizeof(double); }
 
 struct FusedT {
     int  lane, ty, i, j, k0, k1;
@@ -121,8 +101,6 @@ struct FusedT {
     d2 vx_k, vy_k, vz_kp, vzjm_kp;                         // phase A -> phase B
     d2 pr_km, tzz_km;                                      // new Pr, tau_zz of plane kp-2 (for the velocity of kp-1)
     double sxy0, sxy1;                                     // FunctionField rho_g: x,y part of the squared radius
-    double* st;                                            // this thread's slot of operand 0 in the stage (or nullptr)
-    int     st_stride;                                     // doubles between the slots of consecutive operands
 };
 
 FHD d2 fsv_zero() {
@@ -133,27 +111,8 @@ FHD d2 fsv_zero() {
 
 // geometry of a thread: bx = row-segment index along x, grow = row index inside the cluster (0 .. rows_int+1),
 // cyc = cluster index along y, bz = z-chunk index
-// issue the copies of the staged operands of the plane `dz` planes above the thread's current offsets
-FHD void fsv_prefetch(const FusedT& s, const FusedP& p, int dz) {
-    const long long cc = s.cc + (long long)dz * p.cc.sz, vc = s.vc + (long long)dz * p.vc.sz,
-                    cv = s.cv + (long long)dz * p.cv.sz, vv = s.vv + (long long)dz * p.vv.sz;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        fsv_cp16(s.st + c * s.st_stride, p.tc[c] + cc);
-        fsv_cp16(s.st + (6 + c) * s.st_stride, p.to[c] + cc);
-    }
-    fsv_cp16(s.st + 3 * s.st_stride, p.tc[3] + vv); fsv_cp16(s.st + 9 * s.st_stride, p.to[3] + vv);
-    fsv_cp16(s.st + 4 * s.st_stride, p.tc[4] + vc); fsv_cp16(s.st + 10 * s.st_stride, p.to[4] + vc);
-    fsv_cp16(s.st + 5 * s.st_stride, p.tc[5] + cv); fsv_cp16(s.st + 11 * s.st_stride, p.to[5] + cv);
-    fsv_cp16(s.st + 12 * s.st_stride, p.Prc + cc);
-    fsv_cp_commit();
-}
-
-FHD void fsv_init(FusedT& s, const FusedP& p, int lane, int ty, int grow, int bx, int cyc, int bz, bool fun,
-                  double* stage, int tyb) {
+FHD void fsv_init(FusedT& s, const FusedP& p, int lane, int ty, int grow, int bx, int cyc, int bz, bool fun) {
     s.lane = lane; s.ty = ty;
-    s.st = stage ? stage + (ty * 64 + 2 * lane) : nullptr;
-    s.st_stride = tyb * 64;
     s.i  = p.lo[0] - 2 + bx * FSV_XI + 2 * lane;
     s.j  = p.lo[1] - 1 + cyc * p.rows_int + grow;
     s.k0 = p.lo[2] + bz * p.cz;
@@ -183,7 +142,6 @@ FHD void fsv_init(FusedT& s, const FusedP& p, int lane, int ty, int grow, int bx
         s.vy_km = ld2(p.Vc[1] + s.cv);
         s.vz_k  = ld2(p.Vc[2] + s.cc);
         s.vzjm  = ld2(p.Vc[2] + s.cc - (long long)s.jm * p.cc.sy);
-        if (s.st) fsv_prefetch(s, p, 0);
     }
     s.sxy0 = 0.0; s.sxy1 = 0.0;
     if (fun) {
@@ -211,9 +169,9 @@ FHD double fsv_from_right(double, const double* p_ip2, bool ok) { return ok ? *p
 FHD double fsv_from_left(double, const double* p_im1, bool ok) { return ok ? *p_im1 : 0.0; }
 #endif
 
-// ---- phase A: stresses of plane kp -> sn[FSV_NF] (new Pr, tau) and dv (divV); nothing is stored yet
+// ---- phase A: stresses of plane kp -> sn[FSV_NF] (new Pr, tau), stores for the cells this thread owns
 template <bool TD>
-FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF], d2& dv) {
+FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
     const d2 z2 = fsv_zero();
     d2 vx = z2, vxjm = z2, vy = z2, vyjp = z2, vzkp = z2, vzjmkp = z2, pr = z2;
     d2 t[6], o[6];
@@ -224,21 +182,12 @@ FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF], d2& dv) 
         vyjp   = ld2(p.Vc[1] + s.cv + (long long)s.jp * p.cv.sy);
         vzkp   = ld2(p.Vc[2] + s.cc + p.cc.sz);
         vzjmkp = ld2(p.Vc[2] + s.cc - (long long)s.jm * p.cc.sy + p.cc.sz);
-        if (s.st) {
-            // the operands of this plane were requested one plane ago; pick them up and request the next plane
-            fsv_cp_wait();
+        pr     = ld2(p.Prc + s.cc);
 #pragma unroll
-            for (int c = 0; c < 6; ++c) { t[c] = ld2(s.st + c * s.st_stride); o[c] = ld2(s.st + (6 + c) * s.st_stride); }
-            pr = ld2(s.st + 12 * s.st_stride);
-            if (kp < s.k1) fsv_prefetch(s, p, 1);
-        } else {
-            pr = ld2(p.Prc + s.cc);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { t[c] = ld2(p.tc[c] + s.cc); o[c] = ld2(p.to[c] + s.cc); }
-            t[3] = ld2(p.tc[3] + s.vv); o[3] = ld2(p.to[3] + s.vv);
-            t[4] = ld2(p.tc[4] + s.vc); o[4] = ld2(p.to[4] + s.vc);
-            t[5] = ld2(p.tc[5] + s.cv); o[5] = ld2(p.to[5] + s.cv);
-        }
+        for (int c = 0; c < 3; ++c) { t[c] = ld2(p.tc[c] + s.cc); o[c] = ld2(p.to[c] + s.cc); }
+        t[3] = ld2(p.tc[3] + s.vv); o[3] = ld2(p.to[3] + s.vv);
+        t[4] = ld2(p.tc[4] + s.vc); o[4] = ld2(p.to[4] + s.vc);
+        t[5] = ld2(p.tc[5] + s.cv); o[5] = ld2(p.to[5] + s.cv);
     } else {
 #pragma unroll
         for (int c = 0; c < 6; ++c) { t[c] = z2; o[c] = z2; }
@@ -250,8 +199,7 @@ FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF], d2& dv) 
     const double vz_im1 = fsv_from_left(s.vz_k.y, p.Vc[2] + s.cc - 1, okl);
 
     const bool fz = kp >= p.flo[2] && kp < p.fhi[2];
-    d2 prn = z2, tn[6];
-    dv = z2;
+    d2 dv = z2, prn = z2, tn[6];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const double a_vx = h ? vx.y : vx.x, a_vxip = h ? vx_ip2 : vx.y, a_vxjm = h ? vxjm.y : vxjm.x, a_vxkm = h ? s.vx_km.y : s.vx_km.x;
@@ -278,65 +226,41 @@ FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF], d2& dv) 
             if (h) tn[c].y = r; else tn[c].x = r;
         }
     }
+    if (kp >= s.k0 && kp < s.k1) {
+        if (s.nv == 2) {
+            st2(p.dV + s.cc, dv);
+            st2(p.Prn + s.cc, prn);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) st2(p.tn[c] + s.cc, tn[c]);
+            st2(p.tn[3] + s.vv, tn[3]);
+            st2(p.tn[4] + s.vc, tn[4]);
+            st2(p.tn[5] + s.cv, tn[5]);
+        } else if (s.nv == 1) {
+            p.dV[s.cc]  = dv.x;
+            p.Prn[s.cc] = prn.x;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) p.tn[c][s.cc] = tn[c].x;
+            p.tn[3][s.vv] = tn[3].x;
+            p.tn[4][s.vc] = tn[4].x;
+            p.tn[5][s.cv] = tn[5].x;
+        }
+    }
     sn[FSV_PR] = prn;
 #pragma unroll
     for (int c = 0; c < 6; ++c) sn[1 + c] = tn[c];
     s.vx_k = vx; s.vy_k = vy; s.vz_kp = vzkp; s.vzjm_kp = vzjmkp;
 }
 
-// ---- phase B1 (after the barrier wait): publish the stresses of plane kp in the exchange buffer of parity kp&1 and
-// fetch what the velocity update of plane kp-1 needs from OTHER warps (rows j-1 / j+1, possibly in a neighbouring CTA
-// of the cluster).  After B1 the thread signals the barrier: from then on it reads only slots its own warp wrote.
+// ---- phase B: publish the stresses of plane kp, update the velocity of plane kp-1, rotate the carried planes.
 // own / below / above: exchange buffers (element 0 of [buf][field][row][cell]) of the CTAs holding this thread's
 // row, row j-1 and row j+1; rb / ra: the row numbers of j-1 / j+1 inside those CTAs.
-struct FusedY {
-    d2 prjm, tyyjm, txyjp, tyzjp;
-};
-
-FHD void fsv_phase_b1(const FusedT& s, int kp, const d2 sn[FSV_NF], int tyb, double* own, const double* below, int rb,
-                      const double* above, int ra, FusedY& y) {
+template <bool TD, bool FUN>
+FHD void fsv_phase_b(FusedT& s, const FusedP& p, int kp, const d2 sn[FSV_NF], int tyb, double* own, const double* below,
+                     int rb, const double* above, int ra) {
     const int cur = kp & 1, prev = cur ^ 1;
     const int c2 = 2 * s.lane;
 #pragma unroll
     for (int f = 0; f < FSV_NF; ++f) st2(own + fsv_xoff(tyb, cur, f, s.ty) + c2, sn[f]);
-    if (s.nv > 0 && kp >= s.k0 + 1) {
-        y.prjm  = ld2(below + fsv_xoff(tyb, prev, FSV_PR, rb) + c2);
-        y.tyyjm = ld2(below + fsv_xoff(tyb, prev, FSV_YY, rb) + c2);
-        y.txyjp = ld2(above + fsv_xoff(tyb, prev, FSV_XY, ra) + c2);
-        y.tyzjp = ld2(above + fsv_xoff(tyb, prev, FSV_YZ, ra) + c2);
-    } else {
-        y.prjm = y.tyyjm = y.txyjp = y.tyzjp = fsv_zero();
-    }
-}
-
-// ---- phase B2 (after the barrier arrive): store the stresses of plane kp, update the velocity of plane kp-1 from
-// this warp's own row of the exchange buffer, the y-neighbours fetched in B1, the carried planes and phase A's
-// registers; rotate the carried planes.  Global stores come after the arrive on purpose: the arrive has release
-// semantics and would otherwise wait for them.
-template <bool TD, bool FUN>
-FHD void fsv_phase_b2(FusedT& s, const FusedP& p, int kp, const d2 sn[FSV_NF], const d2 dv, const FusedY& y, int tyb,
-                      const double* own) {
-    const int prev = (kp & 1) ^ 1;
-    const int c2 = 2 * s.lane;
-    if (kp >= s.k0 && kp < s.k1) {
-        if (s.nv == 2) {
-            st2(p.dV + s.cc, dv);
-            st2(p.Prn + s.cc, sn[FSV_PR]);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) st2(p.tn[c] + s.cc, sn[1 + c]);
-            st2(p.tn[3] + s.vv, sn[FSV_XY]);
-            st2(p.tn[4] + s.vc, sn[FSV_XZ]);
-            st2(p.tn[5] + s.cv, sn[FSV_YZ]);
-        } else if (s.nv == 1) {
-            p.dV[s.cc]  = dv.x;
-            p.Prn[s.cc] = sn[FSV_PR].x;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) p.tn[c][s.cc] = sn[1 + c].x;
-            p.tn[3][s.vv] = sn[FSV_XY].x;
-            p.tn[4][s.vc] = sn[FSV_XZ].x;
-            p.tn[5][s.cv] = sn[FSV_YZ].x;
-        }
-    }
     if (s.nv > 0 && kp >= s.k0) {
         const d2 pr  = ld2(own + fsv_xoff(tyb, prev, FSV_PR, s.ty) + c2);
         const d2 tzz = ld2(own + fsv_xoff(tyb, prev, FSV_ZZ, s.ty) + c2);
@@ -350,7 +274,10 @@ FHD void fsv_phase_b2(FusedT& s, const FusedP& p, int kp, const d2 sn[FSV_NF], c
             const double txx_im1 = own[fsv_xoff(tyb, prev, FSV_XX, s.ty) + c2 - 1];
             const double txy_ip2 = own[fsv_xoff(tyb, prev, FSV_XY, s.ty) + c2 + 2];
             const double txz_ip2 = own[fsv_xoff(tyb, prev, FSV_XZ, s.ty) + c2 + 2];
-            const d2 prjm = y.prjm, tyyjm = y.tyyjm, txyjp = y.txyjp, tyzjp = y.tyzjp;
+            const d2 prjm  = ld2(below + fsv_xoff(tyb, prev, FSV_PR, rb) + c2);
+            const d2 tyyjm = ld2(below + fsv_xoff(tyb, prev, FSV_YY, rb) + c2);
+            const d2 txyjp = ld2(above + fsv_xoff(tyb, prev, FSV_XY, ra) + c2);
+            const d2 tyzjp = ld2(above + fsv_xoff(tyb, prev, FSV_YZ, ra) + c2);
             const d2 txzkp = sn[FSV_XZ], tyzkp = sn[FSV_YZ];
             const long long cc = s.cc - p.cc.sz, vc = s.vc - p.vc.sz, cv = s.cv - p.cv.sz;
             d2 rho;

@@ -11,9 +11,16 @@ namespace cg = cooperative_groups;
 __device__ __forceinline__ void fsv_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fsv_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
+// relaxed flavour: a CTA-scope fence makes this thread's shared-memory writes performed in the SM's shared memory (the
+// single point of coherence of DSMEM reads), then the arrive carries no memory semantics of its own.  The release
+// flavour is a GPU-scope fence that also waits for the global stores of phase A (measured: the `membar` stall reason).
+__device__ __forceinline__ void fsv_cluster_arrive_relaxed() {
+    asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+
 template <bool TD, bool FUN, int TYB>
-__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB <= 8 ? 16 / TYB : 1)) k_fused_sv(const FusedP p, const int cl, const int pf) {
-    extern __shared__ __align__(16) double xb[];   // [exchange buffers][stage of the asynchronous copies (pf)]
+__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 4 ? 3 : TYB == 8 ? 2 : 1)) k_fused_sv(const FusedP p, const int cl, const int variant) {
+    extern __shared__ __align__(16) double xb[];
     const int lane = threadIdx.x, ty = threadIdx.y;
     int cr = 0;
     const double *below = xb, *above = xb;
@@ -26,20 +33,18 @@ __global__ void __launch_bounds__(FSV_LANES* TYB, (TYB <= 8 ? 16 / TYB : 1)) k_f
         if (ty == 0 && cr > 0) { below = cluster.map_shared_rank(xb, cr - 1); rb = TYB - 1; }
         if (ty == TYB - 1 && cr < cl - 1) { above = cluster.map_shared_rank(xb, cr + 1); ra = 0; }
     }
+    const bool relaxed = (variant & 1) != 0;
     FusedT s;
-    fsv_init(s, p, lane, ty, cr * TYB + ty, blockIdx.x, blockIdx.y / cl, blockIdx.z, FUN,
-             pf ? xb + 2 * FSV_NF * TYB * 64 : nullptr, TYB);
+    fsv_init(s, p, lane, ty, cr * TYB + ty, blockIdx.x, blockIdx.y / cl, blockIdx.z, FUN);
     if (cl > 1) fsv_cluster_arrive();
     for (int kp = s.k0 - 1; kp <= s.k1; ++kp) {
-        d2 sn[FSV_NF], dv;
-        FusedY y;
-        fsv_phase_a<TD>(s, p, kp, sn, dv);
+        d2 sn[FSV_NF];
+        fsv_phase_a<TD>(s, p, kp, sn);
         // every thread of the cluster has finished reading the buffer that is about to be overwritten, and the
-        // stresses of plane kp-1 that phase B1 reads have been published
+        // stresses of plane kp-1 that phase B reads have been published
         if (cl > 1) fsv_cluster_wait(); else __syncthreads();
-        fsv_phase_b1(s, kp, sn, TYB, xb, below, rb, above, ra, y);
-        if (cl > 1) fsv_cluster_arrive();
-        fsv_phase_b2<TD, FUN>(s, p, kp, sn, dv, y, TYB, xb);
+        fsv_phase_b<TD, FUN>(s, p, kp, sn, TYB, xb, below, rb, above, ra);
+        if (cl > 1) { if (relaxed) fsv_cluster_arrive_relaxed(); else fsv_cluster_arrive(); }
     }
     if (cl > 1) fsv_cluster_wait();   // no CTA may exit while a neighbour can still read its shared memory
 }
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(256) k_frame_copy(const FrameBatch b) {
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static int g_fuse_tyb = 8, g_fuse_cl = 2, g_fuse_cz = 64, g_fuse_pf = 1;
+static int g_fuse_tyb = 4, g_fuse_cl = 4, g_fuse_cz = 64, g_fuse_var = 1;   // measured optimum at 767^3 (profiles/)
 static bool g_fuse_env = false;
 static void fuse_env() {
     if (g_fuse_env) return;
@@ -86,16 +91,16 @@ static void fuse_env() {
     const char* a = getenv("CHMY_FUSE_TYB");
     const char* b = getenv("CHMY_FUSE_CL");
     const char* c = getenv("CHMY_FUSE_CZ");
-    const char* d = getenv("CHMY_FUSE_PF");
-    if (d) g_fuse_pf = atoi(d) != 0;
+    const char* d = getenv("CHMY_FUSE_VARIANT");
+    if (d) g_fuse_var = atoi(d);
     if (a) { const int v = atoi(a); if (v == 4 || v == 8 || v == 16) g_fuse_tyb = v; }
     if (b) { const int v = atoi(b); if (v == 1 || v == 2 || v == 4 || v == 8) g_fuse_cl = v; }
     if (c) { const int v = atoi(c); if (v >= 1) g_fuse_cz = v; }
 }
 
-extern "C" int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_chunk, int prefetch) {
+extern "C" int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_chunk, int variant) {
     fuse_env();
-    if (prefetch >= 0) g_fuse_pf = prefetch != 0;
+    if (variant >= 0) g_fuse_var = variant;
     if (rows_per_cta > 0) {
         CHMY_REQUIRE(rows_per_cta == 4 || rows_per_cta == 8 || rows_per_cta == 16, "rows_per_cta must be 4, 8 or 16");
         g_fuse_tyb = rows_per_cta;
@@ -109,13 +114,12 @@ extern "C" int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_c
 }
 
 template <bool TD, bool FUN, int TYB>
-static int launch_fused(const FusedP& p, int cl, int pf, dim3 grid, cudaStream_t st) {
+static int launch_fused(const FusedP& p, int cl, int variant, dim3 grid, cudaStream_t st) {
     auto kern = k_fused_sv<TD, FUN, TYB>;
-    const size_t smem = fsv_smem_bytes(TYB, pf != 0);
+    const size_t smem = fsv_smem_bytes(TYB);
     static bool attr_done = false;   // per instantiation
     if (!attr_done) {
-        CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsv_smem_bytes(TYB, true)));
-        CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -128,16 +132,16 @@ static int launch_fused(const FusedP& p, int cl, int pf, dim3 grid, cudaStream_t
     at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = (unsigned)cl; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = cl > 1 ? 1 : 0;
-    CHMY_CUDA(cudaLaunchKernelEx(&cfg, kern, p, cl, pf));
+    CHMY_CUDA(cudaLaunchKernelEx(&cfg, kern, p, cl, variant));
     return CHMY_OK;
 }
 
 template <bool TD, bool FUN>
 static int launch_fused_tyb(const FusedP& p, int tyb, int cl, dim3 grid, cudaStream_t st) {
     switch (tyb) {
-    case 4: return launch_fused<TD, FUN, 4>(p, cl, g_fuse_pf, grid, st);
-    case 16: return launch_fused<TD, FUN, 16>(p, cl, g_fuse_pf, grid, st);
-    default: return launch_fused<TD, FUN, 8>(p, cl, g_fuse_pf, grid, st);
+    case 4: return launch_fused<TD, FUN, 4>(p, cl, g_fuse_var, grid, st);
+    case 16: return launch_fused<TD, FUN, 16>(p, cl, g_fuse_var, grid, st);
+    default: return launch_fused<TD, FUN, 8>(p, cl, g_fuse_var, grid, st);
     }
 }
 

@@ -220,9 +220,9 @@ int chmy_set_tuning(int disable_fast_kernels, int force_true_division);
 int chmy_set_fusion(chmy_ctx* ctx, int enable);
 int chmy_fused_count(const chmy_ctx* ctx, uint64_t* sweeps);          /* fused sweeps launched so far            */
 /* rows of a CTA (4|8|16), CTAs per thread-block cluster along y (1|2|4|8), planes per z-chunk (0 keeps a setting);
- * prefetch: stage the next plane's tau / tau_old / Pr in shared memory with cp.async (1|0, -1 keeps).
- * Env: CHMY_FUSE_TYB, CHMY_FUSE_CL, CHMY_FUSE_CZ, CHMY_FUSE_PF. */
-int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_chunk, int prefetch);
+ * variant: bit 0 = relaxed cluster-barrier arrive behind a CTA-scope fence instead of the release arrive (-1 keeps).
+ * Env: CHMY_FUSE_TYB, CHMY_FUSE_CL, CHMY_FUSE_CZ, CHMY_FUSE_VARIANT. */
+int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_chunk, int variant);
 
 /* halo slab pack/unpack exposed for bit-exact parity tests of src/Distributed/communication_views.jl:1-34 */
 int chmy_halo_slab_len(const chmy_field* f, int dim, int64_t* len);

@@ -25,8 +25,7 @@ ch.set_fusion(arch, False)
 ms = timeit()
 print(f"unfused            : {ms:8.3f} ms  T_eff {A/ms/1e6:8.1f} GB/s", flush=True)
 ch.set_fusion(arch, True)
-geoms = [(8, 2, 64, 0), (8, 2, 64, 1), (8, 4, 64, 1), (8, 1, 64, 1), (8, 8, 64, 1), (4, 4, 64, 1), (4, 8, 64, 1), (4, 2, 64, 1),
-         (16, 1, 64, 1), (16, 2, 64, 1), (16, 2, 64, 0), (8, 2, 32, 1), (8, 2, 128, 1), (8, 2, 256, 1), (8, 4, 128, 1), (16, 2, 128, 1)]
+geoms = [tuple(int(x) for x in g.split(',')) for g in os.environ.get('GEOMS', '8,2,64,0;8,2,64,1').split(';')]
 out = {}
 for g in geoms:
     ch.set_fused_tuning(*g)

@@ -27,7 +27,7 @@ def arch(ch):
     a = ch.Arch(ch.B200Backend())
     ch.set_fusion(a, True)
     yield a
-    ch.set_fused_tuning(8, 2, 64, 1)
+    ch.set_fused_tuning(4, 4, 64, 1)
     a.close()
 
 

@@ -102,6 +102,8 @@ def _worker(rank, world, port, case, q):
             hist_ok = True
         else:
             ow = (8, 4, 3)[:nd]
+            if kind == "stokes_fused":      # the lazily fused stress+velocity sweep under the split launch + exchange
+                ch.set_fusion(arch, True)
             osol = OD.Stokes(n, proc_dims=pd, rho_g_function=True, outer_width=ow, adv_coef=0.01, re_m=2.5 * np.pi)
             bsol = BD.Stokes(arch, n, rho_g_function=True, outer_width=ow, adv_coef=0.01, re_m=2.5 * np.pi, blocking=False)
             ho = osol.run(2, 40, 10)
@@ -112,6 +114,8 @@ def _worker(rank, world, port, case, q):
                 for x, y in zip(a[2:], b[2:]):
                     assert abs(x - y) <= 1e-12 * abs(x), (a, b)
             assert bsol.dt == osol.dt and bsol.eta_ve == osol.eta_ve
+            if kind == "stokes_fused":
+                assert ch.fused_count(arch) == 80
         worst = 0.0
         bf = bsol.fields()
         for k, f in osol.fields(rank).items():
@@ -133,6 +137,9 @@ CASES = [
     (2, ("exchange", (12, 9))),
     (2, ("stokes", (30, 22, 14))),
     (2, ("stokes", (40, 33))),
+    (2, ("stokes_fused", (30, 22, 14))),
+    (4, ("stokes_fused", (24, 22, 14))),
+    (8, ("stokes_fused", (24, 20, 16))),
     (2, ("diffusion", (64, 48))),
     (4, ("exchange", (9, 7, 5))),
     (4, ("stokes", (24, 22, 14))),
