@@ -403,8 +403,9 @@ extern "C" int chmy_bc(chmy_ctx* ctx, const chmy_grid_desc* g, const chmy_batch_
 }
 
 // Region orchestration of `launch` (KernelLaunch.jl:105-183); RUN(box, stream) executes the op on one region.
+// pref: slab widths the op's kernel prefers (outer_width is a hint unless EXACT_SPLIT), or nullptr
 template <class RUN>
-static int orchestrate(chmy_ctx* ctx, const chmy_launch_desc* d, const RUN& run) {
+static int orchestrate(chmy_ctx* ctx, const chmy_launch_desc* d, const RUN& run, const int* pref = nullptr) {
     const chmy_grid_desc* g = &d->grid;
     const int N = g->ndims;
     // worksize = ncenters + 2, I = J + Offset(-1)  ->  I in 0..n+1   (KernelLaunch.jl:41,109)
@@ -436,9 +437,14 @@ static int orchestrate(chmy_ctx* ctx, const chmy_launch_desc* d, const RUN& run)
             // aligned pairs of cells); every cell is still computed exactly once.
             int wl[3] = {0, 0, 0}, wr[3] = {0, 0, 0};
             for (int a = 0; a < N; ++a) wl[a] = wr[a] = (int)d->outer_width[a];
+            if (!(d->flags & CHMY_LAUNCH_EXACT_SPLIT) && pref) {
+                for (int a = 0; a < N; ++a)
+                    if (pref[a] >= 3 && 2 * pref[a] + 2 <= full.n[a]) wl[a] = wr[a] = pref[a];
+            }
             if (!(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) {
                 wl[0] += wl[0] & 1;
-                wr[0] += (full.n[0] - wr[0]) & 1;
+                wr[0] -= (full.n[0] - wr[0]) & 1;           // the right slab starts on an even index; never wider than asked
+                if (wr[0] < 3) wr[0] += 2;
                 if (wl[0] + wr[0] > full.n[0]) { wl[0] = (int)d->outer_width[0]; wr[0] = (int)d->outer_width[0]; }
             }
             CHMY_CUDA(cudaEventRecord(ctx->ev_fork, ctx->s_main));
@@ -532,7 +538,9 @@ static int run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launc
     // from here on the fields ARE their new buffers: the boundary batches of this launch act on the new V
     for (int q = 0; q < 10; ++q) pp[q]->swap_buffers();
     ctx->n_fused++;
-    return orchestrate(ctx, dv, [&](const Box& b, cudaStream_t st) { return chmy_run_fused(ctx, ds, dv, b, cur, shadow, st); });
+    // slabs of a split launch sized to the sweep's tiles: one 60-cell row segment along x, one 2-CTA cluster along y
+    const int pref[3] = {60, 6, 0};
+    return orchestrate(ctx, dv, [&](const Box& b, cudaStream_t st) { return chmy_run_fused(ctx, ds, dv, b, cur, shadow, st); }, pref);
 }
 
 extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {

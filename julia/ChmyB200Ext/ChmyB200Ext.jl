@@ -36,6 +36,7 @@ struct BatchDesc                      # chmy_batch_desc
     fields::NTuple{8,Ptr{Cvoid}}
     bc_kind::NTuple{8,Int32}
     value::NTuple{8,Float64}
+    value_field::NTuple{8,Ptr{Cvoid}}   # Field-valued conditions (ABI v2); C_NULL -> value
 end
 
 struct Inclusion                      # chmy_inclusion
@@ -149,18 +150,47 @@ function GridDesc(grid::UniformGrid{N}) where {N}
 end
 pad3f(t::NTuple{N}) where {N} = ntuple(i -> i <= N ? Float64(t[i]) : 0.0, 3)
 
-const EMPTY_BATCH = BatchDesc(0, 0, ntuple(_ -> C_NULL, 8), ntuple(_ -> Int32(0), 8), ntuple(_ -> 0.0, 8))
-BatchDesc(::EmptyBatch) = EMPTY_BATCH
-BatchDesc(b::ExchangeBatch) = BatchDesc(2, length(b.fields), ntuple(i -> i <= length(b.fields) ? handle(b.fields[i]) : C_NULL, 8),
-                                        ntuple(_ -> Int32(0), 8), ntuple(_ -> 0.0, 8))
-function BatchDesc(b::FieldBatch)                                      # batch.jl:44-54
-    n = length(b.fields)
-    kind(c)  = Int32(c isa FirstOrderBC{<:Any,BoundaryConditions.Neumann})
-    value(c) = c.value === nothing ? 0.0 : Float64(c.value)            # Field- and function-valued BCs: "next" row
-    BatchDesc(1, n, ntuple(i -> i <= n ? handle(b.fields[i]) : C_NULL, 8), ntuple(i -> i <= n ? kind(b.conditions[i]) : Int32(0), 8),
-              ntuple(i -> i <= n ? value(b.conditions[i]) : 0.0, 8))
+const NO_FIELDS = ntuple(_ -> C_NULL, 8)
+const EMPTY_BATCH = BatchDesc(0, 0, NO_FIELDS, ntuple(_ -> Int32(0), 8), ntuple(_ -> 0.0, 8), NO_FIELDS)
+BatchDesc(::EmptyBatch, args...) = EMPTY_BATCH
+BatchDesc(b::ExchangeBatch, args...) = BatchDesc(2, length(b.fields), ntuple(i -> i <= length(b.fields) ? handle(b.fields[i]) : C_NULL, 8),
+                                                 ntuple(_ -> Int32(0), 8), ntuple(_ -> 0.0, 8), NO_FIELDS)
+
+# value(bc, grid, loc, dim, I...) (first_order_boundary_condition.jl:34-40, boundary_function.jl:42-44):
+#   nothing -> 0, Number -> value[], lower-dimensional Field -> value_field[] (read at remove_dim(dim, I) by the BC
+#   kernel), BoundaryFunction -> evaluated HERE (a closure cannot cross the C ABI) over the face range 0..n_t+2 with the
+#   (loc, index) the rule passes (:42-84), uploaded into an (N-1)-dimensional Field that is cached on the arch.
+const BF_CACHE = IdDict{Any,Any}()
+function boundary_value_field(arch, grid::StructuredGrid{N}, f::Field, c::FirstOrderBC, dim::Dim{D}, side::Side{S}) where {N,D,S}
+    get!(BF_CACHE, (arch, grid, c.value, location(f, dim), typeof(c), D, S)) do
+        loc_f = location(f, dim)
+        d     = size(f, D)
+        loc, idx = c isa Dirichlet && loc_f isa Vertex ? (Vertex(), S == 1 ? 1 : d) :
+                   c isa Dirichlet                     ? (Center(), S == 1 ? 0 : d + 1) :
+                                                         (flip(loc_f), S == 1 ? 0 : d + 1)
+        tgrid = UniformGrid(arch; origin=remove_dim(dim, origin(grid, Vertex())), extent=remove_dim(dim, extent(grid, Vertex())),
+                            dims=remove_dim(dim, size(grid, Center())))
+        vf   = Field(arch, tgrid, Vertex())
+        ext  = remove_dim(dim, size(grid, Vertex()) .+ 2)                  # face points 0..n_t+2 (batch.jl:180-181)
+        vals = [c.value(grid, loc, dim, insert_dim(dim, Tuple(J) .- 1, idx)...) for J in CartesianIndices(ext)]
+        check(ccall((:chmy_field_copy_from_host, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ref{NTuple{3,Int64}}, Ref{NTuple{3,Int64}}),
+                    ctx(arch), handle(vf), Float64.(vals), pad3(ntuple(_ -> 0, N - 1), 0), pad3(ext .- 1, 0)))
+        vf
+    end
 end
-batchset(bc::NTuple{N}) where {N} = ntuple(i -> i <= 2N ? BatchDesc(bc[cld(i, 2)][2 - i % 2]) : EMPTY_BATCH, 6)
+
+function BatchDesc(b::FieldBatch, arch, grid, dim, side)               # batch.jl:44-54
+    n = length(b.fields)
+    kind(c)   = Int32(c isa FirstOrderBC{<:Any,BoundaryConditions.NeumannKind})
+    value(c)  = c.value isa Number ? Float64(c.value) : 0.0
+    vfield(f, c) = c.value isa AbstractField      ? handle(c.value) :
+                   c.value isa BoundaryFunction   ? handle(boundary_value_field(arch, grid, f, c, dim, side)) : C_NULL
+    BatchDesc(1, n, ntuple(i -> i <= n ? handle(b.fields[i]) : C_NULL, 8), ntuple(i -> i <= n ? kind(b.conditions[i]) : Int32(0), 8),
+              ntuple(i -> i <= n ? value(b.conditions[i]) : 0.0, 8),
+              ntuple(i -> i <= n ? vfield(b.fields[i], b.conditions[i]) : C_NULL, 8))
+end
+batchset(arch, grid, bc::NTuple{N}) where {N} =
+    ntuple(i -> i <= 2N ? BatchDesc(bc[cld(i, 2)][2 - i % 2], arch, grid, Dim(cld(i, 2)), Side(2 - i % 2)) : EMPTY_BATCH, 6)
 
 # op registry: the @kernel functions of the example solvers, identified by name; `flatten` orders their arguments as
 # include/chmy_b200.h documents for each chmy_op.
@@ -190,16 +220,23 @@ function (launcher::Launcher)(arch::SingleDeviceArchitecture{B200Backend}, grid,
     desc = LaunchDesc(op, 1 #= BLOCKING: KernelLaunch.jl:117 =#, GridDesc(grid), length(fields), length(scalars),
                       ntuple(i -> i <= length(fields) ? fields[i] : C_NULL, 24), ntuple(i -> i <= length(scalars) ? scalars[i] : 0.0, 8),
                       incl, bc === nothing ? 0 : 1, ow === nothing ? 0 : 1, ow === nothing ? (0, 0, 0) : pad3(ow, 0),
-                      bc === nothing ? ntuple(_ -> EMPTY_BATCH, 6) : batchset(bc))
+                      bc === nothing ? ntuple(_ -> EMPTY_BATCH, 6) : batchset(arch, grid, bc))
     check(ccall((:chmy_launch, libchmy), Cint, (Ptr{Cvoid}, Ref{LaunchDesc}), ctx(arch), desc))
     return
 end
 
 function bc!(arch::SingleDeviceArchitecture{B200Backend}, grid::StructuredGrid, batch::BoundaryConditions.BatchSet)   # batch.jl:20-29
     check(ccall((:chmy_bc, libchmy), Cint, (Ptr{Cvoid}, Ref{GridDesc}, Ref{NTuple{6,BatchDesc}}, Cint),
-                ctx(arch), GridDesc(grid), batchset(batch), 1))
+                ctx(arch), GridDesc(grid), batchset(arch, grid, batch), 1))
     return
 end
+
+# Lazily fused PT iteration (include/chmy_b200.h: chmy_set_fusion): `launch(update_stress!)` is deferred and runs with
+# the following `launch(update_velocity!; bc)` as one sweep; anything else on the context flushes it first, so drivers
+# stay exactly as the reference wrote them.  Device pointers cached from chmy_field_get_info go stale after a fused
+# launch (tau, Pr, V ping-pong between two buffers): B200Array re-queries its pointer instead of caching it.
+fuse!(arch::SingleDeviceArchitecture{B200Backend}, on::Bool=true) =
+    check(ccall((:chmy_set_fusion, libchmy), Cint, (Ptr{Cvoid}, Cint), ctx(arch), on))
 
 # Distributed: Arch(B200Backend(), comm, dims) builds the CartesianTopology with MPI exactly as the reference does
 # (topology.jl:26-41) and then hands rank/size/dims plus an MPI-broadcast NCCL id to chmy_topo_create; after that

@@ -56,6 +56,8 @@ def _cmp(name, a, b, tol):
 
 
 def _worker(rank, world, port, case, q):
+    # every rank also runs the oracle's lock-step world on the host: share the cores instead of oversubscribing them
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch.distributed as dist
