@@ -17,7 +17,7 @@ from .fields import (AbstractField, Field, FieldTuple, VectorField, TensorField,
 from .boundary_conditions import (BoundaryFunction, FirstOrderBC, Dirichlet, Neumann, EmptyBatch, FieldBatch, ExchangeBatch, batch, bc_)
 from .kernel_launch import (Launcher, worksize, outer_width, inner_worksize, inner_offset, outer_worksize,
                             outer_offset)
-from .distributed import (CartesianTopology, TorchDistComm, dims_create, exchange_halo_, allreduce_max, barrier,
+from .distributed import (CartesianTopology, TorchDistComm, dims_create, exchange_halo_, allreduce_max, barrier, gather_,
                           global_rank, shared_rank, node_name, dims, cart_coords, neighbors, neighbor, has_neighbor,
                           global_size, node_size, PROC_NULL)
 from .ops import (KernelOp, compute_q_, update_C_, update_old_, update_stress_, update_velocity_,

@@ -117,10 +117,12 @@ template <bool TD, bool FUN, int TYB>
 static int launch_fused(const FusedP& p, int cl, int variant, dim3 grid, cudaStream_t st) {
     auto kern = k_fused_sv<TD, FUN, TYB>;
     const size_t smem = fsv_smem_bytes(TYB);
-    static bool attr_done = false;   // per instantiation
-    if (!attr_done) {
+    static bool attr_done[64] = {};   // per instantiation and per device (function attributes are per device)
+    int dev = 0;
+    CHMY_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;

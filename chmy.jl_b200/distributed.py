@@ -178,3 +178,34 @@ def allreduce_max(arch, *values):
 
 def barrier(arch):
     L.check(L.lib().chmy_barrier(arch.ctx))
+
+
+def gather_(*args, root: int = 0):
+    """gather!(dst, src, comm; root=0) / gather!(arch, dst, src::Field; root) -- src/Distributed/gather.jl:9-42.
+
+    Every rank contributes its local array (for a Field: the interior, copied to the host); on `root` block
+    `cart_coords` of the Cartesian process grid lands at offset `cart_coords .* size(src)` of the column-major global
+    array `dst`, whose size must be `size(src) .* dims` (the MPI subarray/Gatherv arithmetic of :13-33).  Non-root ranks
+    pass `dst=None`.  Setup / output path of the reference (plots, dumps), not the PT loop: the blocks travel over the
+    bootstrap communicator."""
+    import numpy as np
+    from .fields import interior
+    if len(args) == 3 and hasattr(args[0], "topology"):
+        arch, dst, src = args
+        topo, local = arch.topology, np.asarray(interior(src))
+    else:
+        dst, src, topo = args
+        local = np.asarray(src)
+    blocks = topo.comm.allgather_obj((tuple(topo.cart_coords), local)) if topo.nprocs > 1 else [(tuple(topo.cart_coords), local)]
+    if topo.global_rank != root:
+        return
+    if dst is None:
+        raise ValueError("gather!: the root needs a destination array")
+    want = tuple(n * p for n, p in zip(local.shape, topo.dims))
+    if tuple(dst.shape) != want:
+        raise ValueError(f"gather!: size(dst) = {tuple(dst.shape)} but size(src) .* dims = {want}")
+    for coords, blk in blocks:
+        if blk.shape != local.shape:
+            raise ValueError("gather!: local arrays of different sizes")
+        sl = tuple(slice(c * n, (c + 1) * n) for c, n in zip(coords, blk.shape))
+        dst[sl] = blk

@@ -61,6 +61,25 @@ def _worker(rank, world, port, ndims, q):
             for s in range(2):
                 want = ExchangeBatch if og.conn[a][s] == o.CONNECTED else FieldBatch
                 assert isinstance(bs[a][s], want)
+        # gather!(dst, src, comm; root) -- gather.jl:9-33: index-encoded local blocks must land at coords .* size(src)
+        import numpy as np
+        loc_shape = (5, 4, 3)[:ndims]
+        glob_shape = tuple(a * p for a, p in zip(loc_shape, topo.dims))
+        G = np.arange(int(np.prod(glob_shape)), dtype=np.float64).reshape(glob_shape, order="F")
+        mine = G[tuple(slice(c * n, (c + 1) * n) for c, n in zip(topo.cart_coords, loc_shape))].copy(order="F")
+        for root in (0, world - 1):
+            dst = np.full(glob_shape, -1.0, order="F") if rank == root else None
+            ch.gather_(dst, mine, topo, root=root)
+            if rank == root:
+                assert np.array_equal(dst, G)
+        if rank == 0:
+            try:
+                ch.gather_(np.zeros((1,) * ndims), mine, topo)
+                raise AssertionError("size mismatch not detected")
+            except ValueError:
+                pass
+        else:
+            ch.gather_(None, mine, topo)
         q.put((rank, "ok"))
     except Exception as e:       # noqa
         import traceback
