@@ -1,4 +1,5 @@
 """
+(Named test_z_* so that it runs after the single-GPU suites: each case spawns one process per GPU.)
 Multi-GPU parity (NCCL over NVLink, one process per GPU) against the oracle's lock-step simulation of the same
 Cartesian process grid.  Needs >= 2 CUDA devices; skipped otherwise.
 
@@ -148,6 +149,8 @@ CASES = [
     (8, ("exchange", (9, 7, 5))),
     (8, ("stokes", (24, 20, 16))),
 ]
+# the fused sweep is the default of the drivers and the bench: it gets every world size
+CASES.sort(key=lambda c: (c[0], c[1][0]))
 
 
 @pytest.mark.parametrize("world,case", CASES, ids=[f"{w}gpu-{c[0]}-{'x'.join(map(str, c[1]))}" for w, c in CASES])
