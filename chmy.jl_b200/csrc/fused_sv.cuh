@@ -251,6 +251,95 @@ FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
     s.vx_k = vx; s.vy_k = vy; s.vz_kp = vzkp; s.vzjm_kp = vzjmkp;
 }
 
+// ---- software-pipelined flavour of phase A (EXPERIMENTAL, variant bit 1; not the default kernel): the operands of
+// plane kp+1 are requested into registers (fsv_load_a) right after the arithmetic of plane kp, so they are in flight
+// during the barrier and phase B; fsv_compute_a is phase A's arithmetic and stores on operands already in registers.
+struct FusedL {
+    d2 vx, vxjm, vy, vyjp, vzkp, vzjmkp, pr, t[6], o[6];
+};
+
+FHD void fsv_load_a(const FusedT& s, const FusedP& p, int dz, FusedL& L) {
+    const d2 z2 = fsv_zero();
+    L.vx = L.vxjm = L.vy = L.vyjp = L.vzkp = L.vzjmkp = L.pr = z2;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { L.t[c] = z2; L.o[c] = z2; }
+    if (s.s_act) {
+        const long long cc = s.cc + (long long)dz * p.cc.sz, vc = s.vc + (long long)dz * p.vc.sz,
+                        cv = s.cv + (long long)dz * p.cv.sz, vv = s.vv + (long long)dz * p.vv.sz;
+        L.vx     = ld2(p.Vc[0] + vc);
+        L.vxjm   = ld2(p.Vc[0] + vc - (long long)s.jm * p.vc.sy);
+        L.vy     = ld2(p.Vc[1] + cv);
+        L.vyjp   = ld2(p.Vc[1] + cv + (long long)s.jp * p.cv.sy);
+        L.vzkp   = ld2(p.Vc[2] + cc + p.cc.sz);
+        L.vzjmkp = ld2(p.Vc[2] + cc - (long long)s.jm * p.cc.sy + p.cc.sz);
+        L.pr     = ld2(p.Prc + cc);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { L.t[c] = ld2(p.tc[c] + cc); L.o[c] = ld2(p.to[c] + cc); }
+        L.t[3] = ld2(p.tc[3] + vv); L.o[3] = ld2(p.to[3] + vv);
+        L.t[4] = ld2(p.tc[4] + vc); L.o[4] = ld2(p.to[4] + vc);
+        L.t[5] = ld2(p.tc[5] + cv); L.o[5] = ld2(p.to[5] + cv);
+    }
+}
+
+template <bool TD>
+FHD void fsv_compute_a(FusedT& s, const FusedP& p, int kp, const FusedL& L, d2 sn[FSV_NF]) {
+    const d2 z2 = fsv_zero();
+    const bool okr = s.s_act && s.lane < FSV_LANES - 1, okl = s.s_act && s.lane > 0;
+    const double vx_ip2 = fsv_from_right(L.vx.x, p.Vc[0] + s.vc + 2, okr);
+    const double vy_im1 = fsv_from_left(L.vy.y, p.Vc[1] + s.cv - 1, okl);
+    const double vz_im1 = fsv_from_left(s.vz_k.y, p.Vc[2] + s.cc - 1, okl);
+    const bool fz = kp >= p.flo[2] && kp < p.fhi[2];
+    d2 dv = z2, prn = z2, tn[6];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const double a_vx = h ? L.vx.y : L.vx.x, a_vxip = h ? vx_ip2 : L.vx.y, a_vxjm = h ? L.vxjm.y : L.vxjm.x, a_vxkm = h ? s.vx_km.y : s.vx_km.x;
+        const double a_vy = h ? L.vy.y : L.vy.x, a_vyjp = h ? L.vyjp.y : L.vyjp.x, a_vyim = h ? L.vy.x : vy_im1, a_vykm = h ? s.vy_km.y : s.vy_km.x;
+        const double a_vz = h ? s.vz_k.y : s.vz_k.x, a_vzkp = h ? L.vzkp.y : L.vzkp.x, a_vzim = h ? s.vz_k.x : vz_im1, a_vzjm = h ? s.vzjm.y : s.vzjm.x;
+        const double exx = (a_vxip - a_vx) * p.idx;
+        const double eyy = (a_vyjp - a_vy) * p.idy;
+        const double ezz = (a_vzkp - a_vz) * p.idz;
+        const double exy = 0.5 * ((a_vx - a_vxjm) * p.idy + (a_vy - a_vyim) * p.idx);
+        const double exz = 0.5 * ((a_vx - a_vxkm) * p.idz + (a_vz - a_vzim) * p.idx);
+        const double eyz = 0.5 * ((a_vy - a_vykm) * p.idz + (a_vz - a_vzjm) * p.idy);
+        const double d   = (exx + eyy) + ezz;
+        const double d3  = div_u<TD>(d, p.three);
+        const double a_pr = h ? L.pr.y : L.pr.x;
+        const double e2[6] = {2.0 * (exx - d3), 2.0 * (eyy - d3), 2.0 * (ezz - d3), 2.0 * exy, 2.0 * exz, 2.0 * eyz};
+        const bool in = (h ? s.fx1 : s.fx0) && s.fy && fz;
+        const double n_pr = in ? a_pr - (d * p.eta_ve) * p.dtau_Pr : a_pr;
+        if (h) { dv.y = d; prn.y = n_pr; } else { dv.x = d; prn.x = n_pr; }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const double tc = h ? L.t[c].y : L.t[c].x;
+            const double r  = in ? fsv_stress_upd<TD>(tc, h ? L.o[c].y : L.o[c].x, e2[c], p) : tc;
+            if (h) tn[c].y = r; else tn[c].x = r;
+        }
+    }
+    if (kp >= s.k0 && kp < s.k1) {
+        if (s.nv == 2) {
+            st2(p.dV + s.cc, dv);
+            st2(p.Prn + s.cc, prn);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) st2(p.tn[c] + s.cc, tn[c]);
+            st2(p.tn[3] + s.vv, tn[3]);
+            st2(p.tn[4] + s.vc, tn[4]);
+            st2(p.tn[5] + s.cv, tn[5]);
+        } else if (s.nv == 1) {
+            p.dV[s.cc]  = dv.x;
+            p.Prn[s.cc] = prn.x;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) p.tn[c][s.cc] = tn[c].x;
+            p.tn[3][s.vv] = tn[3].x;
+            p.tn[4][s.vc] = tn[4].x;
+            p.tn[5][s.cv] = tn[5].x;
+        }
+    }
+    sn[FSV_PR] = prn;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) sn[1 + c] = tn[c];
+    s.vx_k = L.vx; s.vy_k = L.vy; s.vz_kp = L.vzkp; s.vzjm_kp = L.vzjmkp;
+}
+
 // ---- phase B: publish the stresses of plane kp, update the velocity of plane kp-1, rotate the carried planes.
 // own / below / above: exchange buffers (element 0 of [buf][field][row][cell]) of the CTAs holding this thread's
 // row, row j-1 and row j+1; rb / ra: the row numbers of j-1 / j+1 inside those CTAs.

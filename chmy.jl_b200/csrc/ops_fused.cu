@@ -19,7 +19,7 @@ __device__ __forceinline__ void fsv_cluster_arrive_relaxed() {
 }
 
 template <bool TD, bool FUN, int TYB>
-__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 4 ? 3 : TYB == 8 ? 2 : 1)) k_fused_sv(const FusedP p, const int cl, const int variant) {
+__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 2 ? 6 : TYB == 4 ? 3 : TYB == 8 ? 2 : 1)) k_fused_sv(const FusedP p, const int cl, const int variant) {
     extern __shared__ __align__(16) double xb[];
     const int lane = threadIdx.x, ty = threadIdx.y;
     int cr = 0;
@@ -47,6 +47,42 @@ __global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 4 ? 3 : TYB == 8 ? 2 :
         if (cl > 1) { if (relaxed) fsv_cluster_arrive_relaxed(); else fsv_cluster_arrive(); }
     }
     if (cl > 1) fsv_cluster_wait();   // no CTA may exit while a neighbour can still read its shared memory
+}
+
+// EXPERIMENTAL (variant bit 1, never the default): the same sweep with phase A software-
+// pipelined through registers -- the 19 operand loads of plane kp+1 are issued right after the arithmetic of plane kp and
+// stay in flight across the barrier and phase B.  Needs ~76 more registers, so 2 CTAs of 128 threads (or 4 of 64) per
+// SM at up to 255 registers.  Proven bit-exact by the host emulation; not yet measured on a GPU.
+template <bool TD, bool FUN, int TYB>
+__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 2 ? 4 : 2)) k_fused_sv_pl(const FusedP p, const int cl, const int variant) {
+    extern __shared__ __align__(16) double xb[];
+    const int lane = threadIdx.x, ty = threadIdx.y;
+    int cr = 0;
+    const double *below = xb, *above = xb;
+    int rb = ty, ra = ty;
+    if (ty > 0) rb = ty - 1;
+    if (ty < TYB - 1) ra = ty + 1;
+    if (cl > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        cr = (int)cluster.block_rank();
+        if (ty == 0 && cr > 0) { below = cluster.map_shared_rank(xb, cr - 1); rb = TYB - 1; }
+        if (ty == TYB - 1 && cr < cl - 1) { above = cluster.map_shared_rank(xb, cr + 1); ra = 0; }
+    }
+    const bool relaxed = (variant & 1) != 0;
+    FusedT s;
+    fsv_init(s, p, lane, ty, cr * TYB + ty, blockIdx.x, blockIdx.y / cl, blockIdx.z, FUN);
+    FusedL L;
+    fsv_load_a(s, p, 0, L);
+    if (cl > 1) fsv_cluster_arrive();
+    for (int kp = s.k0 - 1; kp <= s.k1; ++kp) {
+        d2 sn[FSV_NF];
+        fsv_compute_a<TD>(s, p, kp, L, sn);
+        if (kp < s.k1) fsv_load_a(s, p, 1, L);      // plane kp+1: in flight during the barrier and phase B
+        if (cl > 1) fsv_cluster_wait(); else __syncthreads();
+        fsv_phase_b<TD, FUN>(s, p, kp, sn, TYB, xb, below, rb, above, ra);
+        if (cl > 1) { if (relaxed) fsv_cluster_arrive_relaxed(); else fsv_cluster_arrive(); }
+    }
+    if (cl > 1) fsv_cluster_wait();
 }
 
 // ---------------------------------------------------------------------------------------------- frame copy
@@ -93,7 +129,7 @@ static void fuse_env() {
     const char* c = getenv("CHMY_FUSE_CZ");
     const char* d = getenv("CHMY_FUSE_VARIANT");
     if (d) g_fuse_var = atoi(d);
-    if (a) { const int v = atoi(a); if (v == 4 || v == 8 || v == 16) g_fuse_tyb = v; }
+    if (a) { const int v = atoi(a); if (v == 2 || v == 4 || v == 8 || v == 16) g_fuse_tyb = v; }
     if (b) { const int v = atoi(b); if (v == 1 || v == 2 || v == 4 || v == 8) g_fuse_cl = v; }
     if (c) { const int v = atoi(c); if (v >= 1) g_fuse_cz = v; }
 }
@@ -102,7 +138,7 @@ extern "C" int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_c
     fuse_env();
     if (variant >= 0) g_fuse_var = variant;
     if (rows_per_cta > 0) {
-        CHMY_REQUIRE(rows_per_cta == 4 || rows_per_cta == 8 || rows_per_cta == 16, "rows_per_cta must be 4, 8 or 16");
+        CHMY_REQUIRE(rows_per_cta == 2 || rows_per_cta == 4 || rows_per_cta == 8 || rows_per_cta == 16, "rows_per_cta must be 2, 4, 8 or 16");
         g_fuse_tyb = rows_per_cta;
     }
     if (cluster_size > 0) {
@@ -115,14 +151,18 @@ extern "C" int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_c
 
 template <bool TD, bool FUN, int TYB>
 static int launch_fused(const FusedP& p, int cl, int variant, dim3 grid, cudaStream_t st) {
-    auto kern = k_fused_sv<TD, FUN, TYB>;
+    void (*kern)(const FusedP, const int, const int) = k_fused_sv<TD, FUN, TYB>;
+    if constexpr (TYB <= 4) {
+        if (variant & 2) kern = k_fused_sv_pl<TD, FUN, TYB>;
+    }
     const size_t smem = fsv_smem_bytes(TYB);
-    static bool attr_done[64] = {};   // per instantiation and per device (function attributes are per device)
+    static bool attr_done[2][64] = {};   // per instantiation, flavour and device (function attributes are per device)
     int dev = 0;
+    const int fl = (variant & 2) ? 1 : 0;
     CHMY_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    if (dev < 0 || dev >= 64 || !attr_done[fl][dev]) {
         CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+        if (dev >= 0 && dev < 64) attr_done[fl][dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -141,6 +181,7 @@ static int launch_fused(const FusedP& p, int cl, int variant, dim3 grid, cudaStr
 template <bool TD, bool FUN>
 static int launch_fused_tyb(const FusedP& p, int tyb, int cl, dim3 grid, cudaStream_t st) {
     switch (tyb) {
+    case 2: return launch_fused<TD, FUN, 2>(p, cl, g_fuse_var, grid, st);
     case 4: return launch_fused<TD, FUN, 4>(p, cl, g_fuse_var, grid, st);
     case 16: return launch_fused<TD, FUN, 16>(p, cl, g_fuse_var, grid, st);
     default: return launch_fused<TD, FUN, 8>(p, cl, g_fuse_var, grid, st);
@@ -218,6 +259,7 @@ int chmy_run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_
     int tyb = g_fuse_tyb, cl = g_fuse_cl;
     while (cl > 1 && (cl / 2) * tyb - 2 >= box.n[1]) cl /= 2;
     while (tyb > 4 && cl == 1 && tyb / 2 - 2 >= box.n[1]) tyb /= 2;
+    if (tyb == 2 && cl == 1) { tyb = 4; }   // a lone 2-row CTA has no interior row
     p.rows_int = cl * tyb - 2;
     const int nch = (box.n[2] + g_fuse_cz - 1) / g_fuse_cz;
     p.cz = (box.n[2] + nch - 1) / nch;

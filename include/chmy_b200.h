@@ -219,8 +219,9 @@ int chmy_set_tuning(int disable_fast_kernels, int force_true_division);
  * and anything the sweep cannot handle fall back to the two kernels). */
 int chmy_set_fusion(chmy_ctx* ctx, int enable);
 int chmy_fused_count(const chmy_ctx* ctx, uint64_t* sweeps);          /* fused sweeps launched so far            */
-/* rows of a CTA (4|8|16), CTAs per thread-block cluster along y (1|2|4|8), planes per z-chunk (0 keeps a setting);
- * variant: bit 0 = relaxed cluster-barrier arrive behind a CTA-scope fence instead of the release arrive (-1 keeps).
+/* rows of a CTA (2|4|8|16), CTAs per thread-block cluster along y (1|2|4|8), planes per z-chunk (0 keeps a setting);
+ * variant: bit 0 = relaxed cluster-barrier arrive behind a CTA-scope fence instead of the release arrive,
+ *          bit 1 = EXPERIMENTAL software-pipelined phase A (2- and 4-row CTAs only) (-1 keeps).
  * Env: CHMY_FUSE_TYB, CHMY_FUSE_CL, CHMY_FUSE_CZ, CHMY_FUSE_VARIANT. */
 int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_chunk, int variant);
 

@@ -10,13 +10,14 @@
 #include "../../chmy.jl_b200/csrc/fused_sv.cuh"
 
 template <bool TD, bool FUN>
-static void run(const FusedP& p, int tyb, int cl) {
+static void run(const FusedP& p, int tyb, int cl, bool pipelined) {
     const int nx = p.hi[0] - p.lo[0], ny = p.hi[1] - p.lo[1], nz = p.hi[2] - p.lo[2];
     const int gx = (nx + FSV_XI - 1) / FSV_XI, gyc = (ny + p.rows_int - 1) / p.rows_int, gz = (nz + p.cz - 1) / p.cz;
     const int nthr = cl * tyb * FSV_LANES;
     const size_t per_cta = fsv_smem_bytes(tyb) / sizeof(double);
     std::vector<FusedT> T(nthr);
     std::vector<d2> SN((size_t)nthr * FSV_NF);
+    std::vector<FusedL> LD(nthr);
     std::vector<double> smem(per_cta * cl);
     for (int bz = 0; bz < gz; ++bz)
         for (int cyc = 0; cyc < gyc; ++cyc)
@@ -27,8 +28,17 @@ static void run(const FusedP& p, int tyb, int cl) {
                         for (int lane = 0; lane < FSV_LANES; ++lane)
                             fsv_init(T[(cr * tyb + ty) * FSV_LANES + lane], p, lane, ty, cr * tyb + ty, bx, cyc, bz, FUN);
                 const int k0 = T[0].k0, k1 = T[0].k1;
+                if (pipelined)
+                    for (int t = 0; t < nthr; ++t) fsv_load_a(T[t], p, 0, LD[t]);
                 for (int kp = k0 - 1; kp <= k1; ++kp) {
-                    for (int t = 0; t < nthr; ++t) fsv_phase_a<TD>(T[t], p, kp, &SN[(size_t)t * FSV_NF]);
+                    for (int t = 0; t < nthr; ++t) {
+                        if (pipelined) {
+                            fsv_compute_a<TD>(T[t], p, kp, LD[t], &SN[(size_t)t * FSV_NF]);
+                            if (kp < k1) fsv_load_a(T[t], p, 1, LD[t]);
+                        } else {
+                            fsv_phase_a<TD>(T[t], p, kp, &SN[(size_t)t * FSV_NF]);
+                        }
+                    }
                     // ---- barrier ----
                     for (int cr = 0; cr < cl; ++cr)
                         for (int ty = 0; ty < tyb; ++ty) {
@@ -52,7 +62,7 @@ static void run(const FusedP& p, int tyb, int cl) {
 // strides: cc.sy cc.sz vc.sy vc.sz cv.sy cv.sz vv.sy vv.sz ; box: lo[3] hi[3] flo[3] fhi[3]
 // sc: idx idy idz eta_ve dtau_Pr dtau_r nudtau Gdt eta ; inc: origin[3] spacing[3] c0[3] r2 in out
 extern "C" int fused_emul_run(double** ptrs, const int* strides, const int* box, const double* sc, const double* inc,
-                              const int* incloc, int cz, int tyb, int cl, int td) {
+                              const int* incloc, int cz, int tyb, int cl, int td, int pipelined) {
     FusedP p;
     memset(&p, 0, sizeof(p));
     int q = 0;
@@ -80,7 +90,8 @@ extern "C" int fused_emul_run(double** ptrs, const int* strides, const int* box,
     p.cz = cz; p.rows_int = cl * tyb - 2;
     if (p.lo[0] & 1) return -1;
     const bool fun = p.rho == nullptr;
-    if (td) { if (fun) run<true, true>(p, tyb, cl); else run<true, false>(p, tyb, cl); }
-    else    { if (fun) run<false, true>(p, tyb, cl); else run<false, false>(p, tyb, cl); }
+    const bool pl = pipelined != 0;
+    if (td) { if (fun) run<true, true>(p, tyb, cl, pl); else run<true, false>(p, tyb, cl, pl); }
+    else    { if (fun) run<false, true>(p, tyb, cl, pl); else run<false, false>(p, tyb, cl, pl); }
     return 0;
 }

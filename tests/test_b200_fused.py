@@ -76,6 +76,33 @@ def test_fused_iteration_bit_exact_vs_oracle(ch, arch, oracle, n, geom):
     _set_tuning(0, 0)
 
 
+EXPERIMENTAL = [(2, 8, 64, 1), (2, 4, 16, 0), (4, 4, 64, 3), (4, 2, 5, 2), (2, 8, 64, 3)]
+
+
+@pytest.mark.skipif(__import__("os").environ.get("CHMY_EXPERIMENTAL", "0") != "1",
+                    reason="round-2 candidates (2-row CTAs, software-pipelined phase A): proven by the host emulation, "
+                           "not yet run on a GPU; set CHMY_EXPERIMENTAL=1")
+@pytest.mark.parametrize("geom", EXPERIMENTAL)
+@pytest.mark.parametrize("n", [(70, 37, 9), (125, 64, 20), (17, 9, 5)])
+def test_experimental_variants_bit_exact_vs_two_kernels(ch, n, geom):
+    from chmy_b200 import drivers as BD
+    res = []
+    for fused in (True, False):
+        a = ch.Arch(ch.B200Backend())
+        ch.set_fusion(a, fused)
+        ch.set_fused_tuning(*geom)
+        s = BD.Stokes(a, n, rho_g_function=(n[0] % 2 == 0))
+        rng = np.random.default_rng(1)
+        for f in s.fields().values():
+            f.from_host(1e-3 * (rng.random(tuple(d + 4 for d in f.dims)) - 0.5), [-1] * 3, [d + 2 for d in f.dims])
+        s.run(1, 7, 7, eps=0.0)
+        res.append({k: f.parent() for k, f in s.fields().items()})
+        ch.set_fused_tuning(4, 4, 64, 1)
+        a.close()
+    for k in res[0]:
+        assert ((res[0][k] == res[1][k]) | (np.isnan(res[0][k]) & np.isnan(res[1][k]))).all(), k
+
+
 def test_deferred_stress_is_flushed_before_it_can_be_observed(ch, arch, oracle):
     o = oracle
     n = (33, 18, 7)

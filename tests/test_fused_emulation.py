@@ -58,7 +58,7 @@ class Pitched:
         return q
 
 
-def run_case(o, emul, n, box, cz, tyb, cl, td, fun, seed=0):
+def run_case(o, emul, n, box, cz, tyb, cl, td, fun, seed=0, pipelined=0):
     rng = np.random.default_rng(seed)
     g = o.Grid((-1.0, -1.1, -1.2), (2.0, 2.3, 2.6), n)
     tau, tau_old, V, rV = o.TensorField(g), o.TensorField(g), o.VectorField(g), o.VectorField(g)
@@ -97,7 +97,7 @@ def run_case(o, emul, n, box, cz, tyb, cl, td, fun, seed=0):
     sc = (C.c_double * 9)(*g.inv_spacing, eta_ve, dtau_Pr, dtau_r, nudtau, G * dt, eta)
     incv = (C.c_double * 12)(*g.origin, *g.spacing, *inc.c0, inc.r * inc.r, inc.inn, inc.out)
     incloc = (C.c_int * 3)(*inc.loc)
-    rc = emul.fused_emul_run(P, strides, bx, sc, incv, incloc, cz, tyb, cl, int(td))
+    rc = emul.fused_emul_run(P, strides, bx, sc, incv, incloc, cz, tyb, cl, int(td), int(pipelined))
     assert rc == 0
 
     def same(a, b, name):
@@ -147,12 +147,15 @@ CASES = [
     ((130, 11, 10), ((0, 0, 0), (132, 13, 4)), 8, 4, 2),        # z slab
     ((66, 30, 5), ((64, 0, 0), (68, 32, 7)), 16, 8, 1),         # right x slab
     ((66, 30, 5), ((0, 4, 1), (8, 29, 6)), 2, 4, 2),            # left x slab, odd hi
+    ((70, 33, 9), None, 4, 2, 8),                               # 64-thread CTAs, cluster of 8 (round-2 candidate)
+    ((61, 37, 6), None, 64, 4, 4),                              # the shipped geometry
 ]
 
 
 @pytest.mark.parametrize("n,box,cz,tyb,cl", CASES)
-@pytest.mark.parametrize("td,fun", [(True, False), (False, True)])
-def test_fused_sweep_equals_stress_then_velocity(oracle, emul, n, box, cz, tyb, cl, td, fun):
+@pytest.mark.parametrize("td,fun,pipelined", [(True, False, 0), (False, True, 0), (False, False, 1), (True, True, 1)])
+def test_fused_sweep_equals_stress_then_velocity(oracle, emul, n, box, cz, tyb, cl, td, fun, pipelined):
+    """pipelined=1: the software-pipelined flavour of phase A (operands of plane kp+1 requested one plane ahead)."""
     if box is None:
         box = ((0, 0, 0), tuple(x + 2 for x in n))
-    run_case(oracle, emul, n, box, cz, tyb, cl, td, fun, seed=sum(n) + cz)
+    run_case(oracle, emul, n, box, cz, tyb, cl, td, fun, seed=sum(n) + cz, pipelined=pipelined)
