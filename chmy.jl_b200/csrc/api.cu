@@ -550,8 +550,10 @@ extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
     CHMY_TRY(chmy_validate_op(d));
     CHMY_REQUIRE(d->op != CHMY_OP_NONE, "chmy_launch needs an op (use chmy_bc for a bare batch set)");
     CHMY_CUDA(cudaSetDevice(ctx->device));
-    if (ctx->has_pending && d->op == CHMY_OP_UPDATE_VELOCITY && chmy_fused_eligible(&ctx->pending, d) &&
-        !((d->flags & CHMY_LAUNCH_EXACT_SPLIT) && d->has_outer_width && (d->outer_width[0] & 1))) {
+    // a literal split (EXACT_SPLIT) whose x slabs do not start on even indices cannot feed the sweep's aligned cell pairs
+    const bool odd_exact_split = (d->flags & CHMY_LAUNCH_EXACT_SPLIT) && d->has_bc && d->has_outer_width &&
+                                 ((d->outer_width[0] & 1) || ((g->n[0] + 2 - d->outer_width[0]) & 1));
+    if (ctx->has_pending && d->op == CHMY_OP_UPDATE_VELOCITY && chmy_fused_eligible(&ctx->pending, d) && !odd_exact_split) {
         ctx->has_pending = 0;
         const int rc = run_fused(ctx, &ctx->pending, d);
         if (rc <= 0) return rc;
