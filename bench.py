@@ -58,9 +58,9 @@ def parse():
     ap.add_argument("--n", type=int, nargs="*", default=None, help="override the local grid size (parity/debug runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--fused", type=int, default=1, choices=[0, 1],
+    ap.add_argument("--fused", type=int, default=1, choices=[0, 1, 3],
                     help="3D Stokes: lazily fuse update_stress! + update_velocity! into one sweep (chmy_set_fusion); "
-                         "0 = the two tuned kernels")
+                         "0 = the two tuned kernels; 3 = additionally the EXPERIMENTAL 2D sweeps (2D workloads)")
     return ap.parse_args()
 
 
@@ -214,8 +214,9 @@ def run_b200(args):
 
     wl = args.workload
     n = tuple(args.n) if args.n else WORKLOADS[wl][0]
-    fused = bool(args.fused) and wl.startswith("stokes3d")
-    ch.set_fusion(arch, fused)
+    fused2d = args.fused == 3 and not wl.startswith("stokes3d")      # EXPERIMENTAL 2D sweeps (ops_fused2d.cu)
+    fused = (bool(args.fused) and wl.startswith("stokes3d")) or fused2d
+    ch.set_fusion(arch, 3 if fused2d else int(fused))
     if wl == "diffusion2d":
         sol = BD.Diffusion2D(arch, n, outer_width=(128, 8), C0=None, blocking=False)
         # uniform [0,1) initial condition generated on the host in strips (the reference uses rand())
@@ -229,6 +230,9 @@ def run_b200(args):
         sub = [("compute_q!", lambda: sol.launch(arch, sol.grid, (ch.compute_q_, (sol.q, sol.C, sol.chi, sol.grid)))),
                ("update_C!", lambda: sol.launch(arch, sol.grid, (ch.update_C_, (sol.C, sol.q, sol.dt, sol.grid)),
                                                 bc=ch.batch(sol.grid, (sol.C, ch.Neumann()), exchange=sol.C)))]
+        if fused:
+            q0, q1 = sub[0][1], sub[1][1]
+            sub = [("compute_q!+update_C! (fused sweep)", lambda: (q0(), q1()))]
         metric_field = sol.C
     else:
         sol = BD.Stokes(arch, n, re_m=2.5 * math.pi, rho_g_function=True,
@@ -252,6 +256,9 @@ def run_b200(args):
             sub += [("update_thermal_flux!", lambda: sol.launch(arch, g, (ch.update_thermal_flux_, (sol.qT, sol.T, sol.V, sol.lam, g)))),
                     ("update_thermal!", lambda: sol.launch(arch, g, (ch.update_thermal_, (sol.T, sol.T_old, sol.qT, sol.dt, g)),
                                                            bc=ch.batch(g, *sol.bc_T, exchange=sol.T)))]
+            if fused2d:
+                t0_, t1_ = sub[-2][1], sub[-1][1]
+                sub = sub[:-2] + [("update_thermal_flux!+update_thermal! (fused sweep)", lambda: (t0_(), t1_()))]
         metric_field = sol.divV
     ch.synchronize(arch)
 
@@ -296,8 +303,8 @@ def run_b200(args):
         s += 1
     per = {k: v / KK for k, v in per.items()}
     dom_name, dom_passes = DOMINANT[wl]
-    if fused:        # R16 + W14 array passes
-        dom_name, dom_passes = sub[0][0], 30
+    if fused:        # 3D: R16 + W14 array passes; 2D Stokes: R9 + W9; diffusion: R1 + W3
+        dom_name, dom_passes = sub[0][0], (30 if len(n) == 3 else (4 if wl == "diffusion2d" else 18))
     cells_launch = float(math.prod(x + 2 for x in n))
     alg_bytes = dom_passes * 8.0 * cells_launch
     peak, peak_src = measured_peaks()

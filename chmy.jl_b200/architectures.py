@@ -116,10 +116,11 @@ def launch_count(arch: Architecture) -> int:
     return int(n.value)
 
 
-def set_fusion(arch: Architecture, enable: bool = True):
+def set_fusion(arch: Architecture, enable=True):
     """Lazily fuse `launch(update_stress!)` + `launch(update_velocity!; bc)` of a 3D PT iteration into one sweep
-    (include/chmy_b200.h: chmy_set_fusion).  Results are bit-identical with and without it."""
-    L.check(L.lib().chmy_set_fusion(arch.ctx, 1 if enable else 0))
+    (include/chmy_b200.h: chmy_set_fusion).  Results are bit-identical with and without it.
+    `enable=3` additionally turns on the EXPERIMENTAL 2D sweeps (2D Stokes pair, compute_q!+update_C!, 2D thermal pair)."""
+    L.check(L.lib().chmy_set_fusion(arch.ctx, int(enable)))
 
 
 def fused_count(arch: Architecture) -> int:
@@ -130,6 +131,10 @@ def fused_count(arch: Architecture) -> int:
 
 def set_fused_tuning(rows_per_cta: int = 0, cluster_size: int = 0, z_chunk: int = 0, variant: int = -1):
     L.check(L.lib().chmy_set_fused_tuning(int(rows_per_cta), int(cluster_size), int(z_chunk), int(variant)))
+
+
+def set_fused2d_tuning(rows_per_chunk: int = 0, unroll: int = 0):
+    L.check(L.lib().chmy_set_fused2d_tuning(int(rows_per_chunk), int(unroll)))
 
 
 def topology(arch: DistributedArchitecture):

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libchmy_b200.so")
-SOURCES = ["api.cu", "ops.cu", "ops_fast.cu", "ops_fast2d.cu", "ops_fused.cu", "bc.cu", "comm.cu"]
+SOURCES = ["api.cu", "ops.cu", "ops_fast.cu", "ops_fast2d.cu", "ops_fused.cu", "ops_fused2d.cu", "bc.cu", "comm.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -483,7 +483,8 @@ static int orchestrate(chmy_ctx* ctx, const chmy_launch_desc* d, const RUN& run,
 extern "C" int chmy_set_fusion(chmy_ctx* ctx, int enable) {
     CHMY_REQUIRE(ctx != nullptr, "ctx is NULL");
     CHMY_TRY(chmy_flush(ctx));
-    ctx->fuse = enable ? 1 : 0;
+    // bit 0: the 3D stress+velocity sweep; bit 1: additionally the EXPERIMENTAL 2D sweeps (ops_fused2d.cu)
+    ctx->fuse = enable ? ((enable & 3) ? (enable & 3) : 1) : 0;
     return CHMY_OK;
 }
 
@@ -543,6 +544,27 @@ static int run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launc
     return orchestrate(ctx, dv, [&](const Box& b, cudaStream_t st) { return chmy_run_fused(ctx, ds, dv, b, cur, shadow, st); }, pref);
 }
 
+// EXPERIMENTAL 2D sweeps (ops_fused2d.cu): same protocol as run_fused -- shadow buffers, frame carry-over, swap, then the
+// usual region orchestration with the sweep as the region kernel.  Returns 1 when the shadow buffers cannot be allocated.
+static int run_fused2d(chmy_ctx* ctx, int kind, const chmy_launch_desc* dp, const chmy_launch_desc* dc) {
+    chmy_field* pp[6];
+    const int npp = chmy_fused2d_pingpong(kind, dp, dc, pp);
+    for (int q = 0; q < npp; ++q)
+        if (ensure_shadow(ctx, pp[q]) != CHMY_OK) return 1;
+    chmy_field* fr[6];
+    double *fsrc[6], *fdst[6];
+    int nfr = 0;
+    for (int q = 0; q < npp; ++q)
+        if (!pp[q]->frame_synced) { fr[nfr] = pp[q]; fsrc[nfr] = pp[q]->p0; fdst[nfr] = pp[q]->alt_p0(); ++nfr; pp[q]->frame_synced = true; }
+    CHMY_TRY(chmy_frame_copy2(ctx, &dp->grid, nfr, fr, fsrc, fdst, ctx->s_main));
+    double *cur[6], *shadow[6];
+    for (int q = 0; q < npp; ++q) { cur[q] = pp[q]->p0; shadow[q] = pp[q]->alt_p0(); }
+    for (int q = 0; q < npp; ++q) pp[q]->swap_buffers();
+    ctx->n_fused++;
+    const int pref[3] = {60, 0, 0};      // x slabs of a split launch: one 60-cell row segment; y slabs as asked
+    return orchestrate(ctx, dc, [&](const Box& b, cudaStream_t st) { return chmy_run_fused2d(ctx, kind, dp, dc, b, cur, shadow, st); }, pref);
+}
+
 extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
     CHMY_REQUIRE(ctx && d, "NULL argument");
     const chmy_grid_desc* g = &d->grid;
@@ -560,8 +582,24 @@ extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
         CHMY_TRY(run_plain(ctx, &ctx->pending));    // no memory for the shadow buffers: two kernels
         return run_plain(ctx, d);
     }
+    if (ctx->has_pending && (ctx->fuse & 2) && g->ndims == 2 && !odd_exact_split) {
+        const int kind = chmy_fused2d_kind(&ctx->pending, d);
+        if (kind) {
+            ctx->has_pending = 0;
+            const int rc = run_fused2d(ctx, kind, &ctx->pending, d);
+            if (rc <= 0) return rc;
+            CHMY_TRY(run_plain(ctx, &ctx->pending));    // no memory for the shadow buffers: two kernels
+            return run_plain(ctx, d);
+        }
+    }
     CHMY_TRY(chmy_flush(ctx));
     if (ctx->fuse && d->op == CHMY_OP_UPDATE_STRESS && g->ndims == 3 && !d->has_bc) {
+        ctx->pending = *d;
+        ctx->has_pending = 1;
+        return CHMY_OK;
+    }
+    if ((ctx->fuse & 2) && g->ndims == 2 && !d->has_bc &&
+        (d->op == CHMY_OP_UPDATE_STRESS || d->op == CHMY_OP_COMPUTE_Q || d->op == CHMY_OP_UPDATE_THERMAL_FLUX)) {
         ctx->pending = *d;
         ctx->has_pending = 1;
         return CHMY_OK;

@@ -136,7 +136,7 @@ struct chmy_ctx {
     chmy_comm*   comm;          // null on a single-device architecture
     cudaEvent_t* ev_time;       // lazily created timing events (CHMY_MAX_EVENTS slots)
     // lazily fused update_stress! -> update_velocity! (api.cu): a deferred stress launch waiting for its velocity launch
-    int               fuse;          // chmy_set_fusion
+    int               fuse;          // chmy_set_fusion: bit 0 = 3D stress+velocity sweep, bit 1 = + experimental 2D sweeps
     int               has_pending;
     chmy_launch_desc  pending;
     uint64_t          n_fused;       // fused sweeps launched so far
@@ -166,6 +166,13 @@ int chmy_run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_
                    double* const* cur, double* const* shadow, cudaStream_t st);
 int chmy_frame_copy(chmy_ctx* ctx, const chmy_grid_desc* g, int n, chmy_field* const* fs, double* const* src,
                     double* const* dst, cudaStream_t st);
+// ops_fused2d.cu (EXPERIMENTAL 2D sweeps)
+int chmy_fused2d_kind(const chmy_launch_desc* dp, const chmy_launch_desc* dc);
+int chmy_fused2d_pingpong(int kind, const chmy_launch_desc* dp, const chmy_launch_desc* dc, chmy_field** pp);
+int chmy_run_fused2d(chmy_ctx* ctx, int kind, const chmy_launch_desc* dp, const chmy_launch_desc* dc, const Box& box,
+                     double* const* cur, double* const* shadow, cudaStream_t st);
+int chmy_frame_copy2(chmy_ctx* ctx, const chmy_grid_desc* g, int n, chmy_field* const* fs, double* const* src,
+                     double* const* dst, cudaStream_t st);
 // bc.cu (halo slabs)
 int chmy_pack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, double* dbuf, cudaStream_t st);
 int chmy_unpack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, const double* dbuf,

@@ -1,0 +1,266 @@
+// ops_fused2d.cu -- EXPERIMENTAL (opt-in: chmy_set_fusion(ctx, 3); proven bit-exact by the host emulation in
+// tests/emul/fused_emul2d.cpp, NOT YET RUN ON A GPU): device side and launch glue of the 2D fused sweeps
+//   kind 1  update_stress! + update_velocity!        (fused_sv2d.cuh;   24 -> 18 array passes)
+//   kind 2  compute_q! + update_C!                   (fused_pairs2d.cuh; 7 ->  4)
+//   kind 3  update_thermal_flux! + update_thermal!   (fused_pairs2d.cuh; 9 ->  7)
+// Design and data flow: the two headers.  One warp = one 64-cell row segment (60 interior cells) marching along y over
+// one y-chunk; warps are independent (no shared memory, no barrier), a CTA is just F2_WARPS consecutive segments.
+#include "fused_sv2d.cuh"
+#include "fused_pairs2d.cuh"
+
+constexpr int F2_WARPS = 4;
+
+template <bool TD, bool FUN>
+__global__ void __launch_bounds__(FSV_LANES* F2_WARPS, 4) k_fused_sv2(const Fused2P p, const int gx) {
+    const int lane = threadIdx.x;
+    const int seg  = blockIdx.x * F2_WARPS + threadIdx.y;
+    if (seg >= gx) return;                    // whole warps leave; the kernel has no CTA-wide barrier
+    Fused2T s;
+    fsv2_init(s, p, lane, seg, blockIdx.y, FUN);
+    for (int jp = s.j0 - 1; jp <= s.j1; ++jp) {
+        d2 sn[4];
+        fsv2_phase_a<TD>(s, p, jp, sn);
+        // x-neighbours of the NEW values of row jp-1 (the carried registers, read before phase B rotates them)
+        const double pr_im1  = __shfl_up_sync(FULL, s.prC.y, 1);
+        const double txx_im1 = __shfl_up_sync(FULL, s.txxC.y, 1);
+        const double txy_ip2 = __shfl_down_sync(FULL, s.txyC.x, 1);
+        fsv2_phase_b<TD, FUN>(s, p, jp, sn, pr_im1, txx_im1, txy_ip2);
+    }
+}
+
+// U rows per group: the operands of the whole group are requested before its first row is computed (U loads per array
+// in flight per thread; the stores of a row cannot be reordered behind later loads by the compiler, they may alias)
+template <int KIND, int U>
+__global__ void __launch_bounds__(FSV_LANES* F2_WARPS, (KIND == 0 ? 8 : 4)) k_fused_q2(const FusedQ2P p, const int gx) {
+    const int lane = threadIdx.x;
+    const int seg  = blockIdx.x * F2_WARPS + threadIdx.y;
+    if (seg >= gx) return;
+    FusedQ2T s;
+    fq2_init(s, p, lane, seg, blockIdx.y);
+    for (int jg = s.j0; jg <= s.j1; jg += U) {
+        FusedQ2L L[U];
+#pragma unroll
+        for (int r = 0; r < U; ++r)
+            if (jg + r <= s.j1) fq2_load<KIND>(s, p, r, L[r]);
+#pragma unroll
+        for (int r = 0; r < U; ++r) {
+            if (jg + r <= s.j1) {             // warp-uniform
+                d2 sn[2];
+                fq2_phase_a<KIND>(s, p, jg + r, L[r], sn);
+                const double qx_ip2 = __shfl_down_sync(FULL, s.qxC.x, 1);
+                fq2_phase_b<KIND>(s, p, jg + r, sn, qx_ip2);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- frame copy (2D)
+// Cells of a ping-pong field outside the ops' index range [0, n+1]^2 are never written by a sweep; they are carried
+// over from the current buffer to the shadow buffer so that the shadow is a complete field afterwards.
+struct Frame2Pair {
+    const double* src;   // logical (0,0) of the current buffer
+    double*       dst;   // ... of the shadow buffer
+    int sy;
+    int d[2];            // logical field dims
+};
+struct Frame2Batch {
+    int        nn[2];    // grid cells per dim: inside = [0, nn+1]
+    Frame2Pair f[6];
+};
+
+__global__ void __launch_bounds__(256) k_frame_copy2(const Frame2Batch b) {
+    const Frame2Pair& f = b.f[blockIdx.z];
+    // four slabs in logical indices [lo, hi] (inclusive): y slabs over the whole x extent, then x slabs over rows 0..n+1
+    const int slab = blockIdx.y;
+    int lo[2] = {-1, -1}, hi[2] = {f.d[0] + 2, f.d[1] + 2};
+    const int D = 1 - slab / 2, side = slab & 1;
+    if (D == 0) { lo[1] = 0; hi[1] = b.nn[1] + 1; }
+    if (side == 0) hi[D] = -1; else lo[D] = b.nn[D] + 2;
+    const long long ex = hi[0] - lo[0] + 1, ey = hi[1] - lo[1] + 1;
+    const long long total = ex * ey;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = lo[0] + (int)(t % ex), j = lo[1] + (int)(t / ex);
+        const long long off = (long long)i + (long long)j * f.sy;
+        f.dst[off] = f.src[off];
+    }
+}
+
+int chmy_frame_copy2(chmy_ctx* ctx, const chmy_grid_desc* g, int n, chmy_field* const* fs, double* const* src, double* const* dst,
+                     cudaStream_t st) {
+    if (n <= 0) return CHMY_OK;
+    CHMY_REQUIRE(n <= 6, "too many fields for one 2D frame copy");
+    Frame2Batch b;
+    memset(&b, 0, sizeof(b));
+    for (int a = 0; a < 2; ++a) b.nn[a] = (int)g->n[a];
+    for (int q = 0; q < n; ++q) {
+        b.f[q].src = src[q]; b.f[q].dst = dst[q];
+        b.f[q].sy = (int)fs[q]->stride[1];
+        for (int a = 0; a < 2; ++a) b.f[q].d[a] = (int)fs[q]->d[a];
+    }
+    k_frame_copy2<<<dim3(32, 4, (unsigned)n), 256, 0, st>>>(b);
+    ctx->n_launches++;
+    CHMY_CUDA(cudaGetLastError());
+    return CHMY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static int g_f2_cy = 64, g_f2_unroll = 4;   // rows per y-chunk, rows per load group (kinds 2 and 3); untuned defaults
+static bool g_f2_env = false;
+static void f2_env() {
+    if (g_f2_env) return;
+    g_f2_env = true;
+    const char* a = getenv("CHMY_FUSE2D_CY");
+    const char* b = getenv("CHMY_FUSE2D_UNROLL");
+    if (a) { const int v = atoi(a); if (v >= 1) g_f2_cy = v; }
+    if (b) { const int v = atoi(b); if (v == 1 || v == 2 || v == 4) g_f2_unroll = v; }
+}
+
+extern "C" int chmy_set_fused2d_tuning(int rows_per_chunk, int unroll) {
+    f2_env();
+    if (rows_per_chunk > 0) g_f2_cy = rows_per_chunk;
+    if (unroll > 0) {
+        CHMY_REQUIRE(unroll == 1 || unroll == 2 || unroll == 4, "unroll must be 1, 2 or 4");
+        g_f2_unroll = unroll;
+    }
+    return CHMY_OK;
+}
+
+static inline bool fits_int(const chmy_field* f) { return f->stride[1] * f->sd[1] < (1ll << 31); }
+
+// Which fused 2D sweep can run the deferred launch `dp` together with `dc`?  0 = none.  Descriptor layouts (ops.cu):
+//   stress  : tau[3] Pr divV V[2] tau_old[3]  scalars eta eta_ve G dt dtau_Pr dtau_r ; velocity: V[2] r_V[2] Pr tau[3] rho_g|NULL
+//   compute_q: q.x q.y C  scalars chi        ; update_C: C q.x q.y  scalars dt
+//   thermal_flux: qT[2] T V[2]  scalars lambda ; thermal: T T_old qT[2]  scalars dt
+int chmy_fused2d_kind(const chmy_launch_desc* dp, const chmy_launch_desc* dc) {
+    if (chmy_fast_disabled()) return 0;
+    if (dp->grid.ndims != 2 || dc->grid.ndims != 2 || dp->has_bc) return 0;
+    for (int a = 0; a < 2; ++a)
+        if (dp->grid.n[a] != dc->grid.n[a] || dp->grid.inv_spacing[a] != dc->grid.inv_spacing[a]) return 0;
+    chmy_field* const* P = dp->fields;
+    chmy_field* const* Q = dc->fields;
+    for (int q = 0; q < dp->nfields; ++q)
+        if (!P[q] || !aligned16(P[q]) || !fits_int(P[q])) return 0;
+    for (int q = 0; q < dc->nfields; ++q)
+        if (Q[q] && (!aligned16(Q[q]) || !fits_int(Q[q]))) return 0;
+    if (dp->op == CHMY_OP_UPDATE_STRESS && dc->op == CHMY_OP_UPDATE_VELOCITY) {
+        for (int c = 0; c < 3; ++c)
+            if (P[c] != Q[5 + c]) return 0;
+        if (P[3] != Q[4] || P[5] != Q[0] || P[6] != Q[1]) return 0;
+        if (dp->scalars[1] != dc->scalars[0]) return 0;        // eta_ve
+        const chmy_field *CC = P[0], *VC = P[5], *CV = P[6], *rho = Q[8];
+        if (!same_strides(P[1], CC) || !same_strides(P[3], CC) || !same_strides(P[4], CC) || !same_strides(Q[2], VC) ||
+            !same_strides(Q[3], CV) || (rho && !same_strides(rho, CV)))
+            return 0;
+        for (int c = 0; c < 3; ++c)
+            if (!same_strides(P[7 + c], P[c])) return 0;
+        return 1;
+    }
+    if (dp->op == CHMY_OP_COMPUTE_Q && dc->op == CHMY_OP_UPDATE_C) {
+        if (P[0] != Q[1] || P[1] != Q[2] || P[2] != Q[0]) return 0;
+        return 2;
+    }
+    if (dp->op == CHMY_OP_UPDATE_THERMAL_FLUX && dc->op == CHMY_OP_UPDATE_THERMAL) {
+        if (P[0] != Q[2] || P[1] != Q[3] || P[2] != Q[0]) return 0;
+        if (!same_strides(Q[1], Q[0]) || !same_strides(P[3], P[0]) || !same_strides(P[4], P[1])) return 0;
+        if (Q[1] == Q[0]) return 0;                             // T_old must not alias T
+        return 3;
+    }
+    return 0;
+}
+
+// the fields a sweep of `kind` writes through shadow buffers: tau[3] Pr V[2] | C | T
+int chmy_fused2d_pingpong(int kind, const chmy_launch_desc* dp, const chmy_launch_desc* dc, chmy_field** pp) {
+    if (kind == 1) {
+        for (int c = 0; c < 3; ++c) pp[c] = dp->fields[c];
+        pp[3] = dp->fields[3];
+        pp[4] = dc->fields[0]; pp[5] = dc->fields[1];
+        return 6;
+    }
+    pp[0] = dc->fields[0];
+    return 1;
+}
+
+template <int KIND>
+static int launch_q2(const FusedQ2P& p, int gx, dim3 grid, cudaStream_t st) {
+    switch (g_f2_unroll) {
+    case 1: k_fused_q2<KIND, 1><<<grid, dim3(FSV_LANES, F2_WARPS, 1), 0, st>>>(p, gx); break;
+    case 2: k_fused_q2<KIND, 2><<<grid, dim3(FSV_LANES, F2_WARPS, 1), 0, st>>>(p, gx); break;
+    default: k_fused_q2<KIND, 4><<<grid, dim3(FSV_LANES, F2_WARPS, 1), 0, st>>>(p, gx); break;
+    }
+    CHMY_CUDA(cudaGetLastError());
+    return CHMY_OK;
+}
+
+// One sub-box of a fused 2D sweep.  cur / shadow: buffers of the ping-pong fields in chmy_fused2d_pingpong order (the
+// caller has already swapped the fields' storage).
+int chmy_run_fused2d(chmy_ctx* ctx, int kind, const chmy_launch_desc* dp, const chmy_launch_desc* dc, const Box& box,
+                     double* const* cur, double* const* shadow, cudaStream_t st) {
+    if (box.n[0] <= 0 || box.n[1] <= 0) return CHMY_OK;
+    f2_env();
+    CHMY_REQUIRE((box.lo[0] & 1) == 0, "fused sweep needs an even x origin");
+    chmy_field* const* P = dp->fields;
+    chmy_field* const* Q = dc->fields;
+    const double* id = dp->grid.inv_spacing;
+    const int gx = (box.n[0] + FSV_XI - 1) / FSV_XI;
+    int cy = g_f2_cy;
+    while ((box.n[1] + cy - 1) / cy > 65535) cy *= 2;
+    const int nch = (box.n[1] + cy - 1) / cy;
+    cy = (box.n[1] + nch - 1) / nch;                            // balanced chunks
+    const dim3 grid((unsigned)((gx + F2_WARPS - 1) / F2_WARPS), (unsigned)((box.n[1] + cy - 1) / cy), 1);
+    if (kind == 1) {
+        const double* s = dp->scalars;
+        Fused2P p;
+        memset(&p, 0, sizeof(p));
+        for (int c = 0; c < 3; ++c) { p.tc[c] = cur[c]; p.tn[c] = shadow[c]; p.to[c] = P[7 + c]->p0; }
+        p.Prc = cur[3]; p.Prn = shadow[3];
+        for (int c = 0; c < 2; ++c) { p.Vc[c] = cur[4 + c]; p.Vn[c] = shadow[4 + c]; p.r[c] = Q[2 + c]->p0; }
+        p.dV = P[4]->p0;
+        const chmy_field* rho = Q[8];
+        p.rho = rho ? rho->p0 : nullptr;
+        p.s_cc = (int)P[0]->stride[1]; p.s_vv = (int)P[2]->stride[1]; p.s_vc = (int)P[5]->stride[1]; p.s_cv = (int)P[6]->stride[1];
+        for (int a = 0; a < 2; ++a) {
+            p.lo[a] = box.lo[a]; p.hi[a] = box.lo[a] + box.n[a];
+            p.flo[a] = 0; p.fhi[a] = (int)dp->grid.n[a] + 2;
+        }
+        p.idx = id[0]; p.idy = id[1];
+        p.eta_ve = s[1]; p.dtau_Pr = s[4]; p.dtau_r = s[5]; p.nudtau = dc->scalars[1];
+        const double Gdt = s[2] * s[3];
+        p.Gdt = DivC{Gdt, 1.0 / Gdt}; p.eta = DivC{s[0], 1.0 / s[0]}; p.three = DivC{3.0, 1.0 / 3.0};
+        p.eve = DivC{s[1], 1.0 / s[1]};
+        if (!rho) {
+            p.inc.active = 1; p.inc.nd = 2;
+            for (int a = 0; a < 2; ++a) {
+                p.inc.loc[a] = dc->rho_g.loc[a]; p.inc.origin[a] = dc->grid.origin[a];
+                p.inc.spacing[a] = dc->grid.spacing[a]; p.inc.c0[a] = dc->rho_g.c0[a];
+            }
+            p.inc.r2 = dc->rho_g.r * dc->rho_g.r; p.inc.in = dc->rho_g.in; p.inc.out = dc->rho_g.out;
+        }
+        p.cy = cy;
+        const bool td = chmy_force_true_div() || !markstein_ok(Gdt) || !markstein_ok(s[0]) || !markstein_ok(s[1]);
+        const dim3 blk(FSV_LANES, F2_WARPS, 1);
+        if (rho) { if (td) k_fused_sv2<true, false><<<grid, blk, 0, st>>>(p, gx); else k_fused_sv2<false, false><<<grid, blk, 0, st>>>(p, gx); }
+        else     { if (td) k_fused_sv2<true, true><<<grid, blk, 0, st>>>(p, gx);  else k_fused_sv2<false, true><<<grid, blk, 0, st>>>(p, gx); }
+        CHMY_CUDA(cudaGetLastError());
+    } else {
+        FusedQ2P p;
+        memset(&p, 0, sizeof(p));
+        p.Cc = cur[0]; p.Cn = shadow[0];
+        if (kind == 2) {
+            p.qx = P[0]->p0; p.qy = P[1]->p0;
+            p.coef = dp->scalars[0]; p.dt = dc->scalars[0];
+        } else {
+            p.qx = P[0]->p0; p.qy = P[1]->p0; p.Vx = P[3]->p0; p.Vy = P[4]->p0; p.base = Q[1]->p0;
+            p.coef = dp->scalars[0]; p.dt = dc->scalars[0];
+        }
+        p.s_cc = (int)Q[0]->stride[1]; p.s_vc = (int)P[0]->stride[1]; p.s_cv = (int)P[1]->stride[1];
+        for (int a = 0; a < 2; ++a) {
+            p.lo[a] = box.lo[a]; p.hi[a] = box.lo[a] + box.n[a];
+            p.flo[a] = 0; p.fhi[a] = (int)dp->grid.n[a] + 2;
+        }
+        p.idx = id[0]; p.idy = id[1];
+        p.cy = cy;
+        if (kind == 2) CHMY_TRY(launch_q2<0>(p, gx, grid, st)); else CHMY_TRY(launch_q2<1>(p, gx, grid, st));
+    }
+    ctx->n_launches++;
+    return CHMY_OK;
+}

@@ -216,7 +216,12 @@ int chmy_set_tuning(int disable_fast_kernels, int force_true_division);
  * passes).  Any other call executes the deferred launch first, so results are identical with and without fusion.
  * The sweep writes tau, Pr and V into shadow buffers that are swapped with the fields' storage afterwards:
  * pointers obtained from chmy_field_get_info are invalidated by a fused launch (PITCHED layout only; DENSE fields
- * and anything the sweep cannot handle fall back to the two kernels). */
+ * and anything the sweep cannot handle fall back to the two kernels).
+ * `enable`: 0 = off; 1 = the 3D pair above (measured on B200: profiles/); 3 = additionally the EXPERIMENTAL 2D sweeps
+ * (same deferred-launch protocol, same results; bit-exact in the host emulation, not yet run on a GPU):
+ *   update_stress! + update_velocity! 2D            stokes_2d_inc_ve_T.jl:146-147   24 -> 18 array passes
+ *   compute_q! + update_C!                          diffusion_2d_perf.jl:28-29       7 ->  4
+ *   update_thermal_flux! + update_thermal! 2D       stokes_2d_inc_ve_T.jl:151-152    9 ->  7                    */
 int chmy_set_fusion(chmy_ctx* ctx, int enable);
 int chmy_fused_count(const chmy_ctx* ctx, uint64_t* sweeps);          /* fused sweeps launched so far            */
 /* rows of a CTA (2|4|8|16), CTAs per thread-block cluster along y (1|2|4|8), planes per z-chunk (0 keeps a setting);
@@ -224,6 +229,9 @@ int chmy_fused_count(const chmy_ctx* ctx, uint64_t* sweeps);          /* fused s
  *          bit 1 = EXPERIMENTAL software-pipelined phase A (2- and 4-row CTAs only) (-1 keeps).
  * Env: CHMY_FUSE_TYB, CHMY_FUSE_CL, CHMY_FUSE_CZ, CHMY_FUSE_VARIANT. */
 int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_chunk, int variant);
+/* 2D sweeps: rows per y-chunk of a warp; rows whose operands are requested ahead of the arithmetic (1|2|4, flux pairs)
+ * (0 keeps a setting).  Env: CHMY_FUSE2D_CY, CHMY_FUSE2D_UNROLL. */
+int chmy_set_fused2d_tuning(int rows_per_chunk, int unroll);
 
 /* halo slab pack/unpack exposed for bit-exact parity tests of src/Distributed/communication_views.jl:1-34 */
 int chmy_halo_slab_len(const chmy_field* f, int dim, int64_t* len);
