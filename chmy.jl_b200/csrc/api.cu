@@ -275,6 +275,27 @@ extern "C" int chmy_field_copy_to_host(chmy_ctx* ctx, const chmy_field* f, doubl
     return copy_box_host(ctx, f, dst, lo, hi, true);
 }
 
+extern "C" int chmy_host_alloc(chmy_ctx* ctx, size_t bytes, void** out) {
+    CHMY_REQUIRE(ctx && out && bytes > 0, "bad argument");
+    *out = nullptr;
+    CHMY_CUDA(cudaSetDevice(ctx->device));
+    const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();      // an allocation failure is not sticky: leave the context usable
+        *out = nullptr;
+        chmy_set_error("cudaHostAlloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return CHMY_ERR_NOMEM;
+    }
+    return CHMY_OK;
+}
+
+extern "C" int chmy_host_free(chmy_ctx* ctx, void* p) {
+    if (!p) return CHMY_OK;
+    if (ctx && ctx_alive(ctx)) cudaSetDevice(ctx->device);
+    CHMY_CUDA(cudaFreeHost(p));
+    return CHMY_OK;
+}
+
 static InclDev incl_from(const chmy_grid_desc* g, const chmy_inclusion* inc, const int* loc) {
     InclDev q;
     memset(&q, 0, sizeof(q));

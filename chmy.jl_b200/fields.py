@@ -69,9 +69,12 @@ class Field(AbstractField):
         hi = [d + pad for d in self.dims]
         return lo, hi
 
-    def to_host(self, lo, hi) -> np.ndarray:
+    def to_host(self, lo, hi, out: np.ndarray | None = None) -> np.ndarray:
         shape = tuple(h - l + 1 for l, h in zip(lo, hi))
-        out = np.empty(shape, dtype=np.float64, order="F")
+        if out is None:
+            out = np.empty(shape, dtype=np.float64, order="F")
+        elif out.shape != shape or out.dtype != np.float64 or not out.flags.f_contiguous:
+            raise ValueError(f"to_host(out=...): need a Fortran-contiguous float64 array of shape {shape}")
         L.check(L.lib().chmy_field_copy_to_host(self.arch.ctx, self.handle, out.ctypes.data_as(C.c_void_p),
                                                 L.i64x3(lo), L.i64x3(hi)))
         return out
@@ -99,9 +102,38 @@ def location(f, dim=None):
     return f.loc if dim is None else f.loc[dim - 1]
 
 
-def interior(f: Field, with_halo: bool = False) -> np.ndarray:
-    """Array(interior(f; with_halo)) -- field.jl:33-37 (host copy; the reference returns a device view)."""
-    return f.to_host(*f._box(1 if with_halo else 0))
+def interior(f: Field, with_halo: bool = False, out: np.ndarray | None = None) -> np.ndarray:
+    """Array(interior(f; with_halo)) -- field.jl:33-37 (host copy; the reference returns a device view).
+    `out`: copy into this (e.g. pinned, see `pinned_array`) host array instead of allocating one."""
+    return f.to_host(*f._box(1 if with_halo else 0), out=out)
+
+
+class _PinnedOwner:
+    """Keeps a chmy_host_alloc buffer alive for as long as a numpy view of it exists."""
+
+    def __init__(self, arch, ptr):
+        self.arch, self.ptr = arch, ptr
+
+    def __del__(self):
+        try:
+            if self.ptr and getattr(self.arch, "_ctx", True) is not None:
+                L.lib().chmy_host_free(self.arch.ctx, self.ptr)
+        except Exception:
+            pass
+        self.ptr = None
+
+
+def pinned_array(arch, shape) -> np.ndarray:
+    """Fortran-ordered Float64 host array in page-locked memory (chmy_host_alloc): the fast host side of
+    set!(f, A) / Array(interior(f)).  Freed when the last numpy view of it is garbage-collected."""
+    shape = tuple(int(s) for s in shape)
+    n = int(np.prod(shape, dtype=np.int64))
+    p = C.c_void_p()
+    L.check(L.lib().chmy_host_alloc(arch.ctx, n * 8, C.byref(p)))
+    owner = _PinnedOwner(arch, p)
+    buf = (C.c_double * n).from_address(p.value)
+    buf._chmy_owner = owner                    # the ctypes object is the numpy array's base: ties the lifetimes
+    return np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape, order="F")
 
 
 def parent(f: Field) -> np.ndarray:
