@@ -22,3 +22,5 @@ from .distributed import (CartesianTopology, TorchDistComm, dims_create, exchang
                           global_size, node_size, PROC_NULL)
 from .ops import (KernelOp, compute_q_, update_C_, update_old_, update_stress_, update_velocity_,
                   update_thermal_flux_, update_thermal_)
+from .grid_operators import (left_, right_, delta_, partial_, partial2_, dkd_, dx_, dy_, dz_, d2x_, d2y_, d2z_, lerp_, hlerp_,
+                             divg_, lapl_, divg_grad_, vmag_, grad_, kgrad_)

@@ -23,7 +23,10 @@ LAYOUT_PITCHED, LAYOUT_DENSE = 0, 1
 LAUNCH_ASYNC, LAUNCH_BLOCKING, LAUNCH_EXACT_SPLIT = 0, 1, 2
 
 OP_NONE, OP_COMPUTE_Q, OP_UPDATE_C, OP_UPDATE_OLD, OP_UPDATE_STRESS, OP_UPDATE_VELOCITY, OP_UPDATE_THERMAL_FLUX, \
-    OP_UPDATE_THERMAL = range(8)
+    OP_UPDATE_THERMAL, OP_OPERATOR = range(9)
+# chmy_operator
+OPER_LEFT, OPER_RIGHT, OPER_DELTA, OPER_PARTIAL, OPER_PARTIAL2, OPER_DKD, OPER_LERP, OPER_HLERP, OPER_DIVG, OPER_LAPL, \
+    OPER_DIVG_GRAD, OPER_VMAG, OPER_GRAD, OPER_KGRAD = range(1, 15)
 
 
 class ChmyError(RuntimeError):
@@ -53,7 +56,8 @@ class LaunchDesc(C.Structure):
                 ("nfields", C.c_int32), ("nscalars", C.c_int32),
                 ("fields", C.c_void_p * MAX_OP_FIELDS), ("scalars", C.c_double * MAX_SCALARS),
                 ("rho_g", Inclusion), ("has_bc", C.c_int32), ("has_outer_width", C.c_int32),
-                ("outer_width", C.c_int64 * MAX_DIMS), ("bc", (BatchDesc * 2) * MAX_DIMS)]
+                ("outer_width", C.c_int64 * MAX_DIMS), ("bc", (BatchDesc * 2) * MAX_DIMS),
+                ("oper", C.c_int32), ("oper_dim", C.c_int32)]
 
 
 class FieldInfo(C.Structure):
@@ -111,7 +115,7 @@ SYMBOLS = {
     "chmy_halo_unpack": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 

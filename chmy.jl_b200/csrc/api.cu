@@ -370,6 +370,7 @@ extern "C" int chmy_halo_unpack(chmy_ctx* ctx, chmy_field* f, int dim, int side,
 // ---------------------------------------------------------------------------------------------- launch
 static int run_op(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st) {
     if (box.n[0] <= 0 || box.n[1] <= 0 || box.n[2] <= 0) return CHMY_OK;
+    if (d->op == CHMY_OP_OPERATOR) return chmy_run_op_generic(ctx, d, box, st);   // no tuned variants
     int handled = 0;
     CHMY_TRY(chmy_run_op_fast(ctx, d, box, st, &handled));
     if (handled) return CHMY_OK;

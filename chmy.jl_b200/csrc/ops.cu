@@ -11,6 +11,7 @@
 // This translation unit holds the *generic* one-thread-per-cell kernels (any box, any layout); the tuned
 // z-marching / vectorised kernels for the headline configs live in ops_fast.cu and are selected in chmy_run_op.
 #include "common.cuh"
+#include "operators.cuh"
 
 // ---------------------------------------------------------------------------------------------- generic box kernel
 template <class F>
@@ -241,6 +242,93 @@ static int expect_vector(const chmy_launch_desc* d, int first, int nd) {
     return CHMY_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- grid operators
+// CHMY_OP_OPERATOR (operators.cuh): every field must sit where the reference's operator reads / produces it.
+static int expect_size(const chmy_launch_desc* d, int idx) {
+    const chmy_field* f = d->fields[idx];
+    for (int a = 0; a < d->grid.ndims; ++a)
+        CHMY_REQUIRE(f->d[a] == d->grid.n[a] + (f->loc[a] == CHMY_VERTEX ? 1 : 0),
+                     "operator %d: field %d size %lld along dim %d does not match the grid", d->oper, idx, f->d[a], a + 1);
+    return CHMY_OK;
+}
+static bool loc_is(const chmy_field* f, const chmy_field* src, int nd, int flip_dim) {   // loc(f) == flipped(loc(src), flip_dim)
+    for (int a = 0; a < nd; ++a)
+        if (f->loc[a] != (a == flip_dim ? 1 - src->loc[a] : src->loc[a])) return false;
+    return true;
+}
+
+static int validate_operator(const chmy_launch_desc* d) {
+    const int nd = d->grid.ndims, op = d->oper;
+    CHMY_REQUIRE(op >= CHMY_OPER_LEFT && op <= CHMY_OPER_KGRAD, "unknown operator id %d", op);
+    CHMY_REQUIRE(d->nscalars == 0, "operator %d takes no scalars", op);
+    int nf = 2;
+    if (op == CHMY_OPER_DKD || op == CHMY_OPER_DIVG_GRAD) nf = 3;
+    if (op == CHMY_OPER_DIVG || op == CHMY_OPER_VMAG || op == CHMY_OPER_GRAD) nf = nd + 1;
+    if (op == CHMY_OPER_KGRAD) nf = nd + 2;
+    CHMY_REQUIRE(d->nfields == nf, "operator %d expects %d fields on a %dD grid, got %d", op, nf, nd, d->nfields);
+    for (int i = 0; i < nf; ++i) {
+        CHMY_REQUIRE(d->fields[i] != nullptr, "operator %d: field %d is NULL", op, i);
+        CHMY_REQUIRE(d->fields[i]->nd == nd, "operator %d: field %d has %d dims, grid has %d", op, i, d->fields[i]->nd, nd);
+        CHMY_TRY(expect_size(d, i));
+    }
+    chmy_field* const* F = d->fields;
+    const int nout = (op == CHMY_OPER_GRAD || op == CHMY_OPER_KGRAD) ? nd : 1;
+    for (int o = 0; o < nout; ++o)
+        for (int i = nout; i < nf; ++i)
+            CHMY_REQUIRE(F[o] != F[i], "operator %d: the destination must not alias a source (neighbouring points are read)", op);
+    if (op <= CHMY_OPER_DKD) CHMY_REQUIRE(d->oper_dim >= 0 && d->oper_dim < nd, "operator %d: dim %d out of range", op, d->oper_dim + 1);
+    switch (op) {
+    case CHMY_OPER_LEFT: case CHMY_OPER_RIGHT: case CHMY_OPER_DELTA: case CHMY_OPER_PARTIAL:
+        CHMY_REQUIRE(loc_is(F[0], F[1], nd, d->oper_dim), "operator %d: dst must be located at flipped(location(f), dim)", op);
+        break;
+    case CHMY_OPER_PARTIAL2: case CHMY_OPER_DKD: case CHMY_OPER_LAPL: case CHMY_OPER_DIVG_GRAD:
+        CHMY_REQUIRE(loc_is(F[0], F[1], nd, -1), "operator %d: dst must be located at location(f)", op);
+        break;
+    case CHMY_OPER_DIVG:
+        for (int c = 0; c < nd; ++c)
+            CHMY_REQUIRE(loc_is(F[0], F[1 + c], nd, c), "divg: dst must be located at flipped(location(V.%c), %d)", "xyz"[c], c + 1);
+        break;
+    case CHMY_OPER_VMAG:
+        for (int a = 0; a < nd; ++a) CHMY_REQUIRE(F[0]->loc[a] == CHMY_CENTER, "vmag: dst must be located at Center()");
+        break;
+    case CHMY_OPER_GRAD: case CHMY_OPER_KGRAD:
+        for (int c = 0; c < nd; ++c)
+            CHMY_REQUIRE(loc_is(F[c], F[nd], nd, c), "operator %d: V.%c must be located at flipped(location(f), %d)", op, "xyz"[c], c + 1);
+        break;
+    default: break;   // LERP / HLERP: any two locations
+    }
+    return CHMY_OK;
+}
+
+struct OperatorF {
+    OprArgs g;
+    __device__ void operator()(int i, int j, int k) const { opr_apply(g, i, j, k); }
+};
+
+static OprField opr_view(const chmy_field* f) {
+    OprField v;
+    v.p = f->p0; v.sy = f->nd > 1 ? f->stride[1] : 0; v.sz = f->nd > 2 ? f->stride[2] : 0;
+    for (int a = 0; a < 3; ++a) v.loc[a] = f->loc[a];
+    return v;
+}
+
+static int run_operator(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st) {
+    const int nd = d->grid.ndims, op = d->oper;
+    chmy_field* const* F = d->fields;
+    OperatorF f;
+    memset(&f, 0, sizeof(f));
+    f.g.oper = op; f.g.dim = d->oper_dim; f.g.nd = nd;
+    for (int a = 0; a < 3; ++a) f.g.id[a] = a < nd ? d->grid.inv_spacing[a] : 0.0;
+    const int nout = (op == CHMY_OPER_GRAD || op == CHMY_OPER_KGRAD) ? nd : 1;
+    f.g.ndst = nout;
+    for (int o = 0; o < nout; ++o) f.g.dst[o] = opr_view(F[o]);
+    const bool vec = op == CHMY_OPER_DIVG || op == CHMY_OPER_VMAG;
+    for (int c = 0; c < (vec ? nd : 1); ++c) f.g.a[c] = opr_view(F[nout + c]);
+    if (op == CHMY_OPER_DKD || op == CHMY_OPER_DIVG_GRAD || op == CHMY_OPER_KGRAD) f.g.k = opr_view(F[nout + 1]);
+    for (int o = 0; o < nout; ++o) F[o]->frame_synced = false;   // not a ping-pong op: a shadow copy of dst goes stale
+    return launch_box(ctx, f, box, st);
+}
+
 int chmy_validate_op(const chmy_launch_desc* d) {
     const int nd = d->grid.ndims;
     const int nt = nd == 2 ? 3 : 6;
@@ -298,6 +386,7 @@ int chmy_validate_op(const chmy_launch_desc* d) {
         CHMY_TRY(expect_loc(d, 0, C_, C_, C_));
         CHMY_TRY(expect_loc(d, 1, C_, C_, C_));
         return expect_vector(d, 2, nd);
+    case CHMY_OP_OPERATOR: return validate_operator(d);
     default: chmy_set_error("unknown op id %d", d->op); return CHMY_ERR_ARG;
     }
 }
@@ -326,6 +415,7 @@ int chmy_run_op_generic(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box
     const double* s  = d->scalars;
     chmy_field* const* F = d->fields;
     switch (d->op) {
+    case CHMY_OP_OPERATOR: return run_operator(ctx, d, box, st);
     case CHMY_OP_COMPUTE_Q: {
         ComputeQ f{F[0]->view(), F[1]->view(), F[2]->view(), s[0], id[0], id[1]};
         return launch_box(ctx, f, box, st);

@@ -39,6 +39,7 @@ class Launcher:
         fields, scalars, ffield = op.flatten(args)
         d = L.LaunchDesc()
         d.op = op.op_id
+        d.oper, d.oper_dim = op.oper, op.oper_dim
         d.flags = (L.LAUNCH_BLOCKING if self.blocking else L.LAUNCH_ASYNC) | (L.LAUNCH_EXACT_SPLIT if self.exact_split else 0)
         d.grid = grid.desc()
         if len(fields) > L.MAX_OP_FIELDS or len(scalars) > L.MAX_SCALARS:

@@ -12,8 +12,9 @@ from .fields import Field, FieldTuple, FunctionField
 
 
 class KernelOp:
-    def __init__(self, name: str, op_id: int, flatten):
+    def __init__(self, name: str, op_id: int, flatten, oper: int = 0, oper_dim: int = 0):
         self.name, self.op_id, self._flatten = name, op_id, flatten
+        self.oper, self.oper_dim = oper, oper_dim       # CHMY_OP_OPERATOR only (grid_operators.py)
 
     def flatten(self, args):
         return self._flatten(*args)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CHMY_ABI_VERSION 2
+#define CHMY_ABI_VERSION 3
 
 #define CHMY_MAX_DIMS 3
 #define CHMY_MAX_BATCH_FIELDS 8
@@ -69,8 +69,31 @@ typedef enum {
     CHMY_OP_UPDATE_VELOCITY = 5, /* stokes_3d_inc_ve_T.jl:48-57       fields: V[nd] r_V[nd] Pr tau[nt] rho_g|NULL
                                                                        scalars: eta_ve nudtau                       */
     CHMY_OP_UPDATE_THERMAL_FLUX = 6, /* stokes_3d_inc_ve_T.jl:59-71   fields: qT[nd] T V[nd]     scalars: lambda   */
-    CHMY_OP_UPDATE_THERMAL = 7   /* stokes_3d_inc_ve_T.jl:73-77       fields: T T_old qT[nd]     scalars: dt       */
+    CHMY_OP_UPDATE_THERMAL = 7,  /* stokes_3d_inc_ve_T.jl:73-77       fields: T T_old qT[nd]     scalars: dt       */
+    CHMY_OP_OPERATOR = 8         /* dst[I] = OPERATOR(src...)[I]: chmy_launch_desc::oper / oper_dim, see chmy_operator */
 } chmy_op;                       /* nd = grid.ndims; nt = 3 (2D: xx yy xy) or 6 (3D: xx yy zz xy xz yz)            */
+
+/* The staggered-grid operators of src/GridOperators as field-level kernels (CHMY_OP_OPERATOR, ABI v3).  The reference
+ * exposes them as point functions called from user `@kernel`s (test/test_grid_operators.jl:21-126,
+ * test/test_interpolations.jl:22-70); a C library cannot JIT those kernels, so each operator is offered as
+ * `dst[I] = OP(src...)[I]` over the usual launch range I in [0, n+1]^N.  `dim` = chmy_launch_desc::oper_dim (0-based).
+ * Locations are checked: the result of an operator lives where the reference's operator puts it.               */
+typedef enum {
+    CHMY_OPER_LEFT = 1,       /* left(f, dim, I)   GridOperators.jl:23-33, field_operators.jl:2-6    fields: dst f   dst at flipped(loc(f), dim) */
+    CHMY_OPER_RIGHT = 2,      /* right(f, dim, I)  field_operators.jl:8-12                            fields: dst f   "                          */
+    CHMY_OPER_DELTA = 3,      /* δ(f, dim, I)      partial_derivatives.jl:2                           fields: dst f   "                          */
+    CHMY_OPER_PARTIAL = 4,    /* ∂(f, grid, dim, I) partial_derivatives.jl:5                          fields: dst f   "                          */
+    CHMY_OPER_PARTIAL2 = 5,   /* ∂²(f, grid, dim, I) partial_derivatives.jl:7-12                      fields: dst f   dst at loc(f)              */
+    CHMY_OPER_DKD = 6,        /* ∂k∂(f, k, grid, dim, I) partial_derivatives.jl:14-21                 fields: dst f k dst at loc(f), k anywhere  */
+    CHMY_OPER_LERP = 7,       /* lerp(f, location(dst), grid, I) interpolation.jl:14,63-87            fields: dst f   any two locations          */
+    CHMY_OPER_HLERP = 8,      /* hlerp(f, location(dst), grid, I) interpolation.jl:15,94              fields: dst f   "                          */
+    CHMY_OPER_DIVG = 9,       /* divg(V, grid, I)  field_operators.jl:50-55                           fields: dst V[nd]  dst at flipped(loc(V.d), d) for every d */
+    CHMY_OPER_LAPL = 10,      /* lapl(f, grid, I)  field_operators.jl:72-77                           fields: dst f   dst at loc(f)              */
+    CHMY_OPER_DIVG_GRAD = 11, /* divg_grad(f, k, grid, I) field_operators.jl:95-100                   fields: dst f k dst at loc(f)              */
+    CHMY_OPER_VMAG = 12,      /* vmag(V, grid, I)  field_operators.jl:116-121                         fields: dst V[nd]  dst at Center           */
+    CHMY_OPER_GRAD = 13,      /* V.d[I] = ∂_d(f)   test_grid_operators.jl:24-30 (divg1!)              fields: V[nd] f  V.d at flipped(loc(f), d) */
+    CHMY_OPER_KGRAD = 14      /* V.d[I] = lerp(k, location(V.d)) * ∂_d(f) test_grid_operators.jl:76-82 fields: V[nd] f k                         */
+} chmy_operator;
 
 /* UniformGrid: the numbers src/Grids/structured_grid.jl:27-39 (+ distributed_grid.jl:19-36) produces. */
 typedef struct {
@@ -126,6 +149,8 @@ typedef struct {
     int32_t         has_outer_width;                        /* Launcher built with outer_width            */
     int64_t         outer_width[CHMY_MAX_DIMS];
     chmy_batch_desc bc[CHMY_MAX_DIMS][2];
+    int32_t         oper;                                   /* chmy_operator (CHMY_OP_OPERATOR only; ABI v3) */
+    int32_t         oper_dim;                               /* 0-based dim of LEFT..DKD                      */
 } chmy_launch_desc;
 
 typedef struct {

@@ -61,9 +61,12 @@ struct LaunchDesc                     # chmy_launch_desc
     has_outer_width::Int32
     outer_width::NTuple{3,Int64}
     bc::NTuple{6,BatchDesc}           # [dim][side]
+    oper::Int32                       # chmy_operator (op == 8 only; ABI v3)
+    oper_dim::Int32                   # 0-based
 end
 
 function __init__()
+    ccall((:chmy_abi_version, libchmy), Cint, ()) == 3 || error("ChmyB200Ext: libchmy_b200.so ABI version mismatch (need 3)")
     for (i, T) in enumerate((GridDesc, BatchDesc, Inclusion, LaunchDesc))
         want = ccall((:chmy_struct_size, libchmy), Csize_t, (Cint,), i - 1)
         want == sizeof(T) || error("ChmyB200Ext: layout of $T ($(sizeof(T)) B) differs from the library ($want B)")
@@ -210,17 +213,43 @@ function Inclusion(f::FunctionField{T,N}) where {T,N}                  # Functio
     Inclusion(1, pad3(map(l -> Int32(l isa Vertex), location(f)), 0), pad3f(Tuple(p)[1:N]), p.r, p.in, p.out)
 end
 
+# GridOperators as kernels (include/chmy_b200.h: chmy_operator).  User `@kernel`s that call ∂x/lerp/divg/... at an index
+# cannot cross the C ABI; the B200 backend offers each operator as a callable kernel object instead:
+#     launch(arch, grid, OperatorKernel(:partial, Dim(1)) => (dst, f, grid))        # dst[I] = ∂x(f, grid, I)
+#     launch(arch, grid, OperatorKernel(:divg) => (C, V, grid))                      # C[I]   = divg(V, grid, I)
+const OPERATORS = Dict(:left => 1, :right => 2, :δ => 3, :∂ => 4, :partial => 4, :∂² => 5, :∂k∂ => 6, :lerp => 7, :hlerp => 8,
+                       :divg => 9, :lapl => 10, :divg_grad => 11, :vmag => 12, :grad => 13, :kgrad => 14)
+struct OperatorKernel
+    oper::Int32
+    dim::Int32
+end
+OperatorKernel(name::Symbol, ::Dim{D}=Dim(1)) where {D} = OperatorKernel(OPERATORS[name], D - 1)
+Base.nameof(::OperatorKernel) = :operator!
+OPS[:operator!] = 8
+operator_of(k::OperatorKernel) = (k.oper, k.dim)
+operator_of(_) = (Int32(0), Int32(0))
+
+# Page-locked host arrays for set!(f, A) / Array(interior(f)) at full host-link rate (chmy_host_alloc).
+function pinned_array(arch, dims::NTuple{N,Int}) where {N}
+    ref = Ref{Ptr{Cvoid}}()
+    check(ccall((:chmy_host_alloc, libchmy), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), ctx(arch), prod(dims) * 8, ref))
+    A = unsafe_wrap(Array, Ptr{Float64}(ref[]), dims)
+    finalizer(a -> ccall((:chmy_host_free, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), C_NULL, pointer(a)), A)
+    return A
+end
+
 # ------------------------------------------------------------------------------------------------ the hot entry points
 function (launcher::Launcher)(arch::SingleDeviceArchitecture{B200Backend}, grid, kernel_and_args::Pair; bc=nothing)   # KernelLaunch.jl:105-119
     kernel, args = kernel_and_args
     op = get(OPS, nameof(kernel), 0)
-    op == 0 && error("the B200 backend runs the named solver kernels $(keys(OPS)); got $(nameof(kernel))")
+    op == 0 && error("the B200 backend runs the named solver kernels $(keys(OPS)) and the operator kernels; got $(nameof(kernel))")
     fields, scalars, incl = flatten(args)
+    oper, oper_dim = operator_of(kernel)
     ow = outer_width(launcher)
     desc = LaunchDesc(op, 1 #= BLOCKING: KernelLaunch.jl:117 =#, GridDesc(grid), length(fields), length(scalars),
                       ntuple(i -> i <= length(fields) ? fields[i] : C_NULL, 24), ntuple(i -> i <= length(scalars) ? scalars[i] : 0.0, 8),
                       incl, bc === nothing ? 0 : 1, ow === nothing ? 0 : 1, ow === nothing ? (0, 0, 0) : pad3(ow, 0),
-                      bc === nothing ? ntuple(_ -> EMPTY_BATCH, 6) : batchset(arch, grid, bc))
+                      bc === nothing ? ntuple(_ -> EMPTY_BATCH, 6) : batchset(arch, grid, bc), oper, oper_dim)
     check(ccall((:chmy_launch, libchmy), Cint, (Ptr{Cvoid}, Ref{LaunchDesc}), ctx(arch), desc))
     return
 end

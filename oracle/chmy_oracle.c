@@ -115,7 +115,11 @@ double og_partial2(const og_grid* g, const og_field* f, int dim, int64_t i, int6
 
 /* interpolation.jl:14 (Linear rule = muladd(t, b-a, a)), :19-25 (recursion: last differing dim outermost),
  * :29-33 (uniform weights 0.5), :53-56 (knots: il/ir with loc = field location, from = target location) */
-static double lerp_rec(const og_field* f, const int32_t* to, int top, int64_t* I) {
+static inline double itp_rule(int harmonic, double t, double a, double b) {
+    if (!harmonic) return fma(t, b - a, a);                       /* Linear:         muladd(t, b - a, a)              */
+    return 1.0 / fma(t, 1.0 / b - 1.0 / a, 1.0 / a);              /* HarmonicLinear: inv(muladd(t, inv(b)-inv(a), inv(a))) */
+}
+static double itp_rec(const og_field* f, const int32_t* to, int top, int64_t* I, int harmonic) {
     int d = top;
     while (d >= 0 && f->loc[d] == to[d]) --d;
     if (d < 0) return AT(f, I[0], I[1], I[2]);
@@ -123,17 +127,24 @@ static double lerp_rec(const og_field* f, const int32_t* to, int top, int64_t* I
     /* field Center -> target Vertex: (I-1, I) ; field Vertex -> target Center: (I, I+1) */
     int64_t il = (f->loc[d] == OG_CENTER) ? save - 1 : save;
     int64_t ir = (f->loc[d] == OG_CENTER) ? save : save + 1;
-    I[d] = il; double a = lerp_rec(f, to, d - 1, I);
-    I[d] = ir; double b = lerp_rec(f, to, d - 1, I);
+    I[d] = il; double a = itp_rec(f, to, d - 1, I, harmonic);
+    I[d] = ir; double b = itp_rec(f, to, d - 1, I, harmonic);
     I[d] = save;
-    return fma(0.5, b - a, a);
+    return itp_rule(harmonic, 0.5, a, b);
 }
-double og_lerp(const og_grid* g, const og_field* f, const int32_t* to, int64_t i, int64_t j, int64_t k) {
+static double og_itp(const og_grid* g, const og_field* f, const int32_t* to, int harmonic, int64_t i, int64_t j, int64_t k) {
     int64_t I[3] = {i, j, k};
     int32_t to3[3] = {0, 0, 0};
     for (int d = 0; d < g->nd; ++d) to3[d] = to[d];
     for (int d = g->nd; d < 3; ++d) to3[d] = f->loc[d];
-    return lerp_rec(f, to3, g->nd - 1, I);
+    return itp_rec(f, to3, g->nd - 1, I, harmonic);
+}
+double og_lerp(const og_grid* g, const og_field* f, const int32_t* to, int64_t i, int64_t j, int64_t k) {
+    return og_itp(g, f, to, 0, i, j, k);
+}
+/* interpolation.jl:15,94 */
+double og_hlerp(const og_grid* g, const og_field* f, const int32_t* to, int64_t i, int64_t j, int64_t k) {
+    return og_itp(g, f, to, 1, i, j, k);
 }
 
 /* partial_derivatives.jl:14-21 : (lerp(k,floc,Ir)*d(f,Ir) - lerp(k,floc,Il)*d(f,Il)) * inv_spacing */
@@ -145,6 +156,59 @@ double og_dkd(const og_grid* g, const og_field* f, const og_field* kf, int dim, 
     double a = og_lerp(g, kf, floc, Ir[0], Ir[1], Ir[2]) * f_d(g, f, dim, Ir[0], Ir[1], Ir[2]);
     double b = og_lerp(g, kf, floc, Il[0], Il[1], Il[2]) * f_d(g, f, dim, Il[0], Il[1], Il[2]);
     return (a - b) * g->inv_spacing[dim];
+}
+
+/* Field-level application of one operator over a box: dst[I] = OP(src...)[I] (test/test_grid_operators.jl:21-126 run
+ * such bodies over I in [0, n+1]^N).  kind: 1 left 2 right 3 delta 4 partial 5 partial2 6 dkd 7 lerp 8 hlerp 9 divg
+ * 10 lapl 11 divg_grad 12 vmag 13 grad (dst[d] = d_d f) 14 kgrad (dst[d] = lerp(k, loc(dst[d])) * d_d f).
+ * src: f (or the nd vector components for divg / vmag); sums fold left (field_operators.jl:50-121). */
+void og_apply_operator(const og_grid* g, int kind, int dim, og_field* const* dst, const og_field* const* src,
+                       const og_field* kf, const int64_t* lo, const int64_t* hi) {
+    const int nd = g->nd;
+    const int32_t ctr[3] = {OG_CENTER, OG_CENTER, OG_CENTER};
+    int64_t l3[3] = {0, 0, 0}, h3[3] = {0, 0, 0};
+    for (int d = 0; d < nd; ++d) { l3[d] = lo[d]; h3[d] = hi[d]; }
+    for (int64_t k = l3[2]; k <= h3[2]; ++k)
+        for (int64_t j = l3[1]; j <= h3[1]; ++j)
+            for (int64_t i = l3[0]; i <= h3[0]; ++i) {
+                double s = 0.0;
+                switch (kind) {
+                case 1: AT(dst[0], i, j, k) = f_left(src[0], dim, i, j, k); break;
+                case 2: AT(dst[0], i, j, k) = f_right(src[0], dim, i, j, k); break;
+                case 3: AT(dst[0], i, j, k) = f_right(src[0], dim, i, j, k) - f_left(src[0], dim, i, j, k); break;
+                case 4: AT(dst[0], i, j, k) = og_partial(g, src[0], dim, i, j, k); break;
+                case 5: AT(dst[0], i, j, k) = og_partial2(g, src[0], dim, i, j, k); break;
+                case 6: AT(dst[0], i, j, k) = og_dkd(g, src[0], kf, dim, i, j, k); break;
+                case 7: AT(dst[0], i, j, k) = og_lerp(g, src[0], dst[0]->loc, i, j, k); break;
+                case 8: AT(dst[0], i, j, k) = og_hlerp(g, src[0], dst[0]->loc, i, j, k); break;
+                case 9:
+                    s = og_partial(g, src[0], 0, i, j, k);
+                    for (int d = 1; d < nd; ++d) s = s + og_partial(g, src[d], d, i, j, k);
+                    AT(dst[0], i, j, k) = s; break;
+                case 10:
+                    s = og_partial2(g, src[0], 0, i, j, k);
+                    for (int d = 1; d < nd; ++d) s = s + og_partial2(g, src[0], d, i, j, k);
+                    AT(dst[0], i, j, k) = s; break;
+                case 11:
+                    s = og_dkd(g, src[0], kf, 0, i, j, k);
+                    for (int d = 1; d < nd; ++d) s = s + og_dkd(g, src[0], kf, d, i, j, k);
+                    AT(dst[0], i, j, k) = s; break;
+                case 12: {
+                    double c = og_lerp(g, src[0], ctr, i, j, k);
+                    s = c * c;
+                    for (int d = 1; d < nd; ++d) { c = og_lerp(g, src[d], ctr, i, j, k); s = s + c * c; }
+                    AT(dst[0], i, j, k) = sqrt(s); break;
+                }
+                case 13:
+                    for (int d = 0; d < nd; ++d) AT(dst[d], i, j, k) = og_partial(g, src[0], d, i, j, k);
+                    break;
+                case 14:
+                    for (int d = 0; d < nd; ++d)
+                        AT(dst[d], i, j, k) = og_lerp(g, kf, dst[d]->loc, i, j, k) * og_partial(g, src[0], d, i, j, k);
+                    break;
+                default: break;
+                }
+            }
 }
 
 /* Julia Base max/min on Float64: NaN if either is NaN; max(-0.0,+0.0) = +0.0, min = -0.0 */

@@ -115,6 +115,10 @@ double og_partial(const og_grid* g, const og_field* f, int dim, int64_t i, int64
 double og_partial2(const og_grid* g, const og_field* f, int dim, int64_t i, int64_t j, int64_t k);
 double og_lerp(const og_grid* g, const og_field* f, const int32_t* to, int64_t i, int64_t j, int64_t k);
 double og_dkd(const og_grid* g, const og_field* f, const og_field* kf, int dim, int64_t i, int64_t j, int64_t k);
+double og_hlerp(const og_grid* g, const og_field* f, const int32_t* to, int64_t i, int64_t j, int64_t k);
+/* dst[I] = OP(src...)[I] over the box [lo, hi]; kind as documented at the definition (field_operators.jl:2-121) */
+void og_apply_operator(const og_grid* g, int kind, int dim, og_field* const* dst, const og_field* const* src,
+                       const og_field* kf, const int64_t* lo, const int64_t* hi);
 
 int og_num_threads(void);
 

@@ -106,6 +106,9 @@ def lib():
         L.og_lerp.restype = C.c_double
         L.og_dkd.argtypes = [P(_CGrid), FP, FP, C.c_int, C.c_int64, C.c_int64, C.c_int64]
         L.og_dkd.restype = C.c_double
+        L.og_hlerp.argtypes = L.og_lerp.argtypes
+        L.og_hlerp.restype = C.c_double
+        L.og_apply_operator.argtypes = [P(_CGrid), C.c_int, C.c_int, FPP, FPP, FP] + box
         L.og_num_threads.restype = C.c_int
     return _lib
 
@@ -674,3 +677,25 @@ def lerp(grid, f, to, *I):
 def dkd(grid, f, kf, dim, *I):
     I = list(I) + [0] * (3 - len(I))
     return float(lib().og_dkd(C.byref(grid.c), C.byref(f.c), C.byref(kf.c), dim, *I))
+
+
+def hlerp(grid, f, to, *I):
+    to = expand_loc(grid.nd, to)
+    I = list(I) + [0] * (3 - len(I))
+    return float(lib().og_hlerp(C.byref(grid.c), C.byref(f.c), (C.c_int32 * 3)(*(list(to) + [0] * (3 - grid.nd))), *I))
+
+
+# field-level operators: dst[I] = OP(src...)[I] over [lo, hi] (default: the launch range [0, n+1]^N, KernelLaunch.jl:41,109)
+OPER = {"left": 1, "right": 2, "delta": 3, "partial": 4, "partial2": 5, "dkd": 6, "lerp": 7, "hlerp": 8, "divg": 9,
+        "lapl": 10, "divg_grad": 11, "vmag": 12, "grad": 13, "kgrad": 14}
+
+
+def apply_operator(grid, kind, dst, src, k=None, dim=0, lo=None, hi=None):
+    """dst / src: a Field or a sequence of Fields (vector components in x, y, z order)."""
+    dst = [dst] if isinstance(dst, Field) else list(dst)
+    src = [src] if isinstance(src, Field) else list(src)
+    lo = [0] * grid.nd if lo is None else lo
+    hi = [n + 1 for n in grid.n] if hi is None else hi
+    blo, bhi = _box(grid.nd, lo, hi)
+    lib().og_apply_operator(C.byref(grid.c), OPER[kind] if isinstance(kind, str) else int(kind), int(dim), _fparr(dst),
+                            _fparr(src), None if k is None else C.byref(k.c), blo, bhi)

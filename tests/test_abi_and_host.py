@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(L.SYMBOLS), declared ^ set(L.SYMBOLS)
     L.lib()                                   # also verifies ABI version and struct layouts
-    assert L.lib().chmy_abi_version() == L.ABI_VERSION == 2
+    assert L.lib().chmy_abi_version() == L.ABI_VERSION == 3
 
 
 def test_no_fallback_without_gpu():

@@ -303,3 +303,70 @@ def test_valued_bc_field_and_function_oracle(oracle):
         assert f.data[1, j + 1] == math.fma(dx, -qv, before[2, j + 1]) if hasattr(math, "fma") else True
         assert np.isclose(f.data[1, j + 1], before[2, j + 1] - dx * qv, rtol=1e-15, atol=0)
         assert np.isclose(f.data[n[0] + 2, j + 1], before[n[0] + 1, j + 1] + dx * qv, rtol=1e-15, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------ field-level operators
+def test_hlerp_is_the_harmonic_rule(oracle):
+    """interpolation.jl:15 and the docstring at :92: rule(t, v0, v1) = 1/(1/v0 + t*(1/v1 - 1/v0)), t = 0.5 on uniform
+    axes -> the harmonic mean; nested per dimension like lerp."""
+    import math
+    o = oracle
+    g = o.Grid((0.0, 0.0), (1.0, 1.0), (2, 2))
+    fc = o.Field(g, o.CENTER)
+    fc.set(np.array([[1.0, 3.0], [2.0, 4.0]]))
+    h = lambda a, b: 1.0 / math.fma(0.5, 1.0 / b - 1.0 / a, 1.0 / a) if hasattr(math, "fma") else 1.0 / (0.5 * (1.0 / b - 1.0 / a) + 1.0 / a)
+    v = o.hlerp(g, fc, (o.VERTEX, o.CENTER), 2, 1)                        # between C[1,1]=1 and C[2,1]=2
+    assert math.isclose(v, 2 * 1.0 * 2.0 / 3.0, rel_tol=1e-15) and math.isclose(v, h(1.0, 2.0), rel_tol=1e-15)
+    v = o.hlerp(g, fc, o.VERTEX, 2, 2)                                    # x innermost, y outermost (:19-25)
+    assert math.isclose(v, h(h(1.0, 2.0), h(3.0, 4.0)), rel_tol=1e-15)
+    assert o.hlerp(g, fc, o.CENTER, 1, 2) == 3.0                          # same location: f[I] (:65-67)
+
+
+def test_apply_operator_is_the_point_functions_over_the_launch_range(oracle):
+    """og_apply_operator == the pinned point functions (og_partial, og_partial2, og_lerp, og_dkd) evaluated at every
+    I in [0, n+1]^N, with the left-folded sums of field_operators.jl:50-121."""
+    import math
+    o = oracle
+    g = o.Grid((-1.0, 0.5, 0.0), (2.0, 1.7, 1.1), (5, 4, 3))
+    rng = np.random.default_rng(8)
+
+    def rnd(loc):
+        f = o.Field(g, loc)
+        f.data[...] = rng.random(f.sdims) - 0.5
+        return f
+    f, k = rnd((0, 1, 0)), rnd((1, 1, 0))
+    V = [rnd((1, 0, 0)), rnd((0, 1, 0)), rnd((0, 0, 1))]
+    rngI = [(i, j, kk) for kk in range(0, 5) for j in range(0, 6) for i in range(0, 7)]
+    at = lambda F, I: F.data[I[0] + 1, I[1] + 1, I[2] + 1]
+    for dim in range(3):
+        dloc = tuple(1 - l if a == dim else l for a, l in enumerate(f.loc))
+        d = rnd(dloc)
+        o.apply_operator(g, "partial", d, f, dim=dim)
+        assert all(at(d, I) == o.partial(g, f, dim, *I) for I in rngI)
+        d = rnd(f.loc)
+        o.apply_operator(g, "partial2", d, f, dim=dim)
+        assert all(at(d, I) == o.partial2(g, f, dim, *I) for I in rngI)
+        o.apply_operator(g, "dkd", d, f, k=k, dim=dim)
+        assert all(at(d, I) == o.dkd(g, f, k, dim, *I) for I in rngI)
+    d = rnd(f.loc)
+    o.apply_operator(g, "lapl", d, f)
+    assert all(at(d, I) == (o.partial2(g, f, 0, *I) + o.partial2(g, f, 1, *I)) + o.partial2(g, f, 2, *I) for I in rngI)
+    o.apply_operator(g, "divg_grad", d, f, k=k)
+    assert all(at(d, I) == (o.dkd(g, f, k, 0, *I) + o.dkd(g, f, k, 1, *I)) + o.dkd(g, f, k, 2, *I) for I in rngI)
+    c = rnd((0, 0, 0))
+    o.apply_operator(g, "divg", c, V)
+    assert all(at(c, I) == (o.partial(g, V[0], 0, *I) + o.partial(g, V[1], 1, *I)) + o.partial(g, V[2], 2, *I) for I in rngI)
+    o.apply_operator(g, "vmag", c, V)
+    sq = lambda x: x * x
+    assert all(at(c, I) == math.sqrt((sq(o.lerp(g, V[0], 0, *I)) + sq(o.lerp(g, V[1], 0, *I))) + sq(o.lerp(g, V[2], 0, *I)))
+               for I in rngI)
+    t = rnd((1, 0, 1))
+    o.apply_operator(g, "lerp", t, f)
+    assert all(at(t, I) == o.lerp(g, f, t.loc, *I) for I in rngI)
+    # cells outside the launch range are untouched
+    before = rnd((0, 0, 0))
+    keep = before.data.copy()
+    o.apply_operator(g, "divg", before, V)
+    mask = np.ones(before.sdims, bool)
+    mask[1:-1, 1:-1, 1:-1] = False
+    assert np.array_equal(before.data[mask], keep[mask]) and not np.array_equal(before.data, keep)

@@ -1,0 +1,210 @@
+"""
+GPU tests of entry points added after the round's last GPU session (they have not run on a B200 yet, so this file
+sorts after every measured suite: a surprise here cannot hide the results of the suites before it).
+Same bar as tests/test_b200_parity.py: through the C ABI, against the CPU oracle, bit-exact unless stated.
+"""
+import numpy as np
+import pytest
+
+from helpers import assert_same, fill_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ch():
+    import chmy_b200
+    return chmy_b200
+
+
+@pytest.fixture(scope="module")
+def arch(ch):
+    a = ch.Arch(ch.B200Backend())
+    yield a
+    a.close()
+
+
+def mk_grids(ch, o, arch, n):
+    nd = len(n)
+    origin = tuple(-1.0 - 0.1 * d for d in range(nd))
+    extent = tuple(2.0 + 0.3 * d for d in range(nd))
+    return o.Grid(origin, extent, n), ch.UniformGrid(arch, origin=origin, extent=extent, dims=n)
+
+
+# ------------------------------------------------------------------------------------------------ pinned host arrays
+@pytest.mark.parametrize("n,loc", [((33, 18), (0, 1)), ((12, 10, 8), (1, 0, 1))])
+def test_pinned_host_array_roundtrip(ch, arch, oracle, n, loc):
+    """set!(f, A) / Array(interior(f)) with A in page-locked memory (chmy_host_alloc): same bits as pageable memory."""
+    og, bg = mk_grids(ch, oracle, arch, n)
+    of = oracle.Field(og, loc)
+    bf = ch.Field(arch, bg, tuple(ch.Vertex() if l else ch.Center() for l in loc))
+    rng = np.random.default_rng(11)
+    a = ch.pinned_array(arch, bf.dims)
+    assert a.shape == tuple(bf.dims) and a.flags.f_contiguous and a.flags.writeable
+    a[...] = rng.random(bf.dims)
+    of.set(a)
+    ch.set_(bf, a)
+    assert_same(of, bf, "set!(f, pinned A)")
+    out = ch.pinned_array(arch, bf.dims)
+    got = ch.interior(bf, out=out)
+    assert got is out and np.array_equal(out, a)
+    with pytest.raises(ValueError):
+        ch.interior(bf, out=np.zeros(tuple(d + 1 for d in bf.dims), order="F"))
+    del a, out, got          # frees the pinned buffers (finalizer -> chmy_host_free)
+
+
+# ------------------------------------------------------------------------------------------------ grid operators
+import itertools
+
+
+def flip(loc, d):
+    return tuple(1 - l if a == d else l for a, l in enumerate(loc))
+
+
+def bloc(ch, loc):
+    return tuple(ch.Vertex() if l else ch.Center() for l in loc)
+
+
+def pair(ch, oracle, arch, og, bg, loc, rng, positive=False, layout=0):
+    of = oracle.Field(og, loc)
+    bf = ch.Field(arch, bg, bloc(ch, loc), layout=layout)
+    a = (rng.random(of.sdims) + 0.5) if positive else (rng.random(of.sdims) - 0.5)
+    of.data[...] = a                                                   # interior, halo AND padding
+    bf.from_host(a, [-1] * len(of.dims), [d + 2 for d in of.dims])
+    return of, bf
+
+
+KOP = {"left": "left_", "right": "right_", "delta": "delta_", "partial": "partial_", "partial2": "partial2_", "dkd": "dkd_"}
+
+
+def both(ch, oracle, arch, og, bg, kind, dst, src, k=None, dim=0):
+    """run `kind` through the oracle and through launch(arch, grid, op => (dst, src..., grid)); compare full padded arrays"""
+    dst = dst if isinstance(dst, list) else [dst]
+    src = src if isinstance(src, list) else [src]
+    oracle.apply_operator(og, kind, [d[0] for d in dst], [s[0] for s in src], k=None if k is None else k[0], dim=dim)
+    op = getattr(ch, KOP[kind])(dim + 1) if kind in KOP else getattr(ch, kind + "_")
+    bd = [d[1] for d in dst]
+    bs = [s[1] for s in src]
+    args = (bd[0] if len(bd) == 1 else bd, bs[0] if len(bs) == 1 else bs) + (() if k is None else (k[1],)) + (bg,)
+    ch.Launcher(arch, bg)(arch, bg, (op, args))
+    for q, (of, bf) in enumerate(dst):
+        assert_same(of, bf, f"{kind} dim={dim} dst{q}")
+    for of, bf in src:
+        assert_same(of, bf, f"{kind}: source modified")
+
+
+@pytest.mark.parametrize("n,layout", [((9,), 0), ((7, 5), 0), ((7, 5), 1), ((6, 5, 4), 0), ((70, 9, 5), 0)])
+def test_grid_operators_every_location_bit_exact(ch, arch, oracle, n, layout):
+    nd = len(n)
+    og, bg = mk_grids(ch, oracle, arch, n)
+    rng = np.random.default_rng(5)
+    mk = lambda loc, positive=False: pair(ch, oracle, arch, og, bg, loc, rng, positive, layout)
+    locs = list(itertools.product((0, 1), repeat=nd))
+    for loc in locs:
+        f = mk(loc)
+        for dim in range(nd):
+            for kind in ("left", "right", "delta", "partial"):
+                both(ch, oracle, arch, og, bg, kind, mk(flip(loc, dim)), f, dim=dim)
+            both(ch, oracle, arch, og, bg, "partial2", mk(loc), f, dim=dim)
+            for kloc in (locs[0], locs[-1], locs[len(locs) // 2]):
+                both(ch, oracle, arch, og, bg, "dkd", mk(loc), f, k=mk(kloc), dim=dim)
+        both(ch, oracle, arch, og, bg, "lapl", mk(loc), f)
+        for kloc in locs:
+            both(ch, oracle, arch, og, bg, "divg_grad", mk(loc), f, k=mk(kloc))
+        fpos = mk(loc, True)
+        for to in locs:
+            both(ch, oracle, arch, og, bg, "lerp", mk(to), f)
+            both(ch, oracle, arch, og, bg, "hlerp", mk(to), fpos)
+    ctr, vtx = (0,) * nd, (1,) * nd
+    V = [mk(flip(ctr, d)) for d in range(nd)]
+    both(ch, oracle, arch, og, bg, "divg", mk(ctr), V)
+    both(ch, oracle, arch, og, bg, "vmag", mk(ctr), V)
+    for floc in (ctr, vtx):
+        f = mk(floc)
+        both(ch, oracle, arch, og, bg, "grad", [mk(flip(floc, d)) for d in range(nd)], f)
+        both(ch, oracle, arch, og, bg, "kgrad", [mk(flip(floc, d)) for d in range(nd)], f, k=mk(locs[-1]))
+
+
+def test_reference_operator_identities(ch, arch):
+    """test/test_grid_operators.jl:13-131 on the B200 path: divg == sum of partials (`==`, :41), lapl == sum of second
+    derivatives (`==`, :61), divg_grad ≈ divg(lerp(χ) grad) for χ at Center and Vertex (:98,:110), vmag of (2,2,2) (:130)."""
+    grid = ch.UniformGrid(arch, origin=(-5.0, -5.0, -5.0), extent=(10.0, 10.0, 10.0), dims=(12, 10, 8))
+    launch = ch.Launcher(arch, grid)
+    gauss = lambda x, y, z: np.exp(-x ** 2 - y ** 2 - z ** 2)
+    F = lambda loc=None: ch.Field(arch, grid, loc if loc is not None else ch.Center())
+    Ci, C1, C2, P = F(), F(), F(), F()
+    V = ch.VectorField(arch, grid)
+    ch.set_(Ci, grid, gauss)
+    launch(arch, grid, (ch.grad_, (V, Ci, grid)))                                   # divg1!
+    acc = None
+    for d, c in enumerate(V):
+        launch(arch, grid, (ch.partial_(d + 1), (P, c, grid)))
+        acc = ch.interior(P) if acc is None else acc + ch.interior(P)
+    launch(arch, grid, (ch.divg_, (C2, V, grid)))
+    assert np.array_equal(ch.interior(C2), acc) and np.abs(acc).max() > 1e-3       # :41
+    acc = None
+    for d in range(3):
+        launch(arch, grid, (ch.partial2_(d + 1), (P, Ci, grid)))
+        acc = ch.interior(P) if acc is None else acc + ch.interior(P)
+    launch(arch, grid, (ch.lapl_, (C2, Ci, grid)))
+    assert np.array_equal(ch.interior(C2), acc)                                     # :61
+    for chi in (F(), F(ch.Vertex())):                                               # :86-111
+        ch.set_(chi, grid, gauss)
+        ch.set_(C1, 0.0); ch.set_(C2, 0.0)
+        launch(arch, grid, (ch.kgrad_, (V, Ci, chi, grid)))                         # divg_grad1!
+        launch(arch, grid, (ch.divg_, (C1, V, grid)))
+        launch(arch, grid, (ch.divg_grad_, (C2, Ci, chi, grid)))
+        assert np.allclose(ch.interior(C2), ch.interior(C1), rtol=1.5e-8, atol=0.0) or \
+            np.allclose(ch.interior(C2), ch.interior(C1), rtol=1.5e-8, atol=1e-14)
+    for c in V:
+        ch.set_(c, 2.0)
+    launch(arch, grid, (ch.vmag_, (C1, V, grid)))
+    v = ch.interior(C1)
+    assert np.all(np.vectorize(lambda x: float(f"{x:.5g}"))(v) == 3.4641)           # :130
+
+
+def test_reference_interpolations(ch, arch):
+    """test/test_interpolations.jl:15-74 through lerp_: c2v, c2c, c2cv, c2vc, v2c, v2v, v2cv, v2vc on the 2x2 grid."""
+    grid = ch.UniformGrid(arch, origin=(0.0, 0.0), extent=(1.0, 1.0), dims=(2, 2))
+    launch = ch.Launcher(arch, grid)
+    av4 = lambda A: 0.25 * (A[:-1, :-1] + A[1:, :-1] + A[1:, 1:] + A[:-1, 1:])
+    avx = lambda A: 0.5 * (A[:-1, :] + A[1:, :])
+    avy = lambda A: 0.5 * (A[:, :-1] + A[:, 1:])
+    Cn, Vx = ch.Center(), ch.Vertex()
+
+    def interp(src, to):
+        dst = ch.Field(arch, grid, to)
+        launch(arch, grid, (ch.lerp_, (dst, src, grid)))
+        return ch.interior(dst)
+
+    fc = ch.Field(arch, grid, Cn)
+    ch.set_(fc, np.arange(1, 5, dtype=float).reshape((2, 2), order="F"))
+    fci = ch.interior(fc)
+    assert np.allclose(interp(fc, Vx)[1:-1, 1:-1], av4(fci))
+    assert np.allclose(interp(fc, Cn), fci)
+    assert np.allclose(interp(fc, (Cn, Vx))[:, 1:-1], avy(fci))
+    assert np.allclose(interp(fc, (Vx, Cn))[1:-1, :], avx(fci))
+    fv = ch.Field(arch, grid, Vx)
+    ch.set_(fv, np.arange(1, 10, dtype=float).reshape((3, 3), order="F"))
+    fvi = ch.interior(fv)
+    assert np.allclose(interp(fv, Cn), av4(fvi))
+    assert np.allclose(interp(fv, Vx), fvi)
+    assert np.allclose(interp(fv, (Cn, Vx)), avx(fvi))
+    assert np.allclose(interp(fv, (Vx, Cn)), avy(fvi))
+
+
+def test_operator_location_checks(ch, arch):
+    """the library refuses operands that do not sit where the reference's operator reads / produces them"""
+    grid = ch.UniformGrid(arch, origin=(0.0, 0.0), extent=(1.0, 1.0), dims=(6, 5))
+    launch = ch.Launcher(arch, grid)
+    c, c2, v = ch.Field(arch, grid, ch.Center()), ch.Field(arch, grid, ch.Center()), ch.Field(arch, grid, ch.Vertex())
+    with pytest.raises(ch.ChmyError):
+        launch(arch, grid, (ch.partial_(1), (c2, c, grid)))          # ∂x of a Center field lives at (Vertex, Center)
+    with pytest.raises(ch.ChmyError):
+        launch(arch, grid, (ch.lapl_, (v, c, grid)))
+    with pytest.raises(ch.ChmyError):
+        launch(arch, grid, (ch.lerp_, (c, c, grid)))                 # dst aliases the source
+    with pytest.raises(ch.ChmyError):
+        launch(arch, grid, (ch.partial_(3), (c2, c, grid)))          # Dim(3) on a 2D grid
+    with pytest.raises(ValueError):
+        ch.partial_(0)
