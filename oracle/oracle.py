@@ -28,7 +28,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libchmy_oracle.so")
+_LIB_PATH = os.path.join(_HERE, "libchmy_oracle.so")            # og_real = double (the solvers' element type)
+_LIB_PATH_F32 = os.path.join(_HERE, "libchmy_oracle_f32.so")    # og_real = float  (the Float32 rows of the reference's tests)
 
 CENTER, VERTEX = 0, 1
 BOUNDED, CONNECTED = 0, 1
@@ -37,80 +38,96 @@ AXES = ("x", "y", "z")
 
 
 def build(force: bool = False) -> str:
-    """Compile chmy_oracle.c with the committed Makefile (gcc, -ffp-contract=off)."""
+    """Compile chmy_oracle.c with the committed Makefile (gcc, -ffp-contract=off): the Float64 and the Float32 build."""
     src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("chmy_oracle.c", "chmy_oracle.h", "Makefile"))
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < src_m:
-        subprocess.run(["make", "-C", _HERE, "-B", "libchmy_oracle.so"], check=True, capture_output=True)
+    for path in (_LIB_PATH, _LIB_PATH_F32):
+        if force or not os.path.exists(path) or os.path.getmtime(path) < src_m:
+            subprocess.run(["make", "-C", _HERE, "-B", os.path.basename(path)], check=True, capture_output=True)
     return _LIB_PATH
 
 
-class _CGrid(C.Structure):
-    _fields_ = [("nd", C.c_int32), ("n", C.c_int64 * 3), ("origin", C.c_double * 3), ("extent", C.c_double * 3),
-                ("spacing", C.c_double * 3), ("inv_spacing", C.c_double * 3), ("conn", (C.c_int32 * 2) * 3)]
+class _Binding:
+    """ctypes view of one build of chmy_oracle.c: struct layouts and prototypes in its element type."""
+
+    def __init__(self, dtype):
+        self.dtype = np.dtype(dtype)
+        assert self.dtype in (np.dtype(np.float64), np.dtype(np.float32))
+        R = self.R = C.c_double if self.dtype == np.float64 else C.c_float
+        path = _LIB_PATH if self.dtype == np.float64 else _LIB_PATH_F32
+
+        class CGrid(C.Structure):
+            _fields_ = [("nd", C.c_int32), ("n", C.c_int64 * 3), ("origin", R * 3), ("extent", R * 3),
+                        ("spacing", R * 3), ("inv_spacing", R * 3), ("conn", (C.c_int32 * 2) * 3)]
+
+        class CField(C.Structure):
+            _fields_ = [("nd", C.c_int32), ("loc", C.c_int32 * 3), ("d", C.c_int64 * 3), ("sd", C.c_int64 * 3),
+                        ("o", C.c_int64 * 3), ("data", C.POINTER(R))]
+
+        class CIncl(C.Structure):
+            _fields_ = [("active", C.c_int32), ("loc", C.c_int32 * 3), ("c0", R * 3), ("r", R), ("inn", R), ("out", R)]
+
+        self.CGrid, self.CField, self.CIncl = CGrid, CField, CIncl
+        try:
+            build()
+            L = C.CDLL(path)
+        except OSError:
+            build(force=True)
+            L = C.CDLL(path)
+        self.lib = L
+        P = C.POINTER
+        L.og_real_bytes.restype = C.c_int
+        assert L.og_real_bytes() == C.sizeof(R)
+        L.og_grid_init.argtypes = [P(CGrid), C.c_int, P(C.c_int64), P(R), P(R)]
+        L.og_coord.argtypes = [P(CGrid), C.c_int, C.c_int, C.c_int64]
+        L.og_coord.restype = R
+        L.og_field_init.argtypes = [P(CField), P(CGrid), P(C.c_int32), P(R)]
+        L.og_field_storage_len.argtypes = [P(CGrid), P(C.c_int32)]
+        L.og_field_storage_len.restype = C.c_int64
+        L.og_set_inclusion.argtypes = [P(CGrid), P(CField), P(CIncl)]
+        L.og_maxabs_interior.argtypes = [P(CField)]
+        L.og_maxabs_interior.restype = R
+        box = [P(C.c_int64), P(C.c_int64)]
+        FP, FPP = P(CField), P(P(CField))
+        L.og_compute_q.argtypes = [P(CGrid), FP, FP, FP, R] + box
+        L.og_update_C.argtypes = [P(CGrid), FP, FP, FP, R] + box
+        L.og_update_old.argtypes = [P(CGrid), C.c_int, FPP, FPP] + box
+        for nm in ("og_update_stress2", "og_update_stress3"):
+            getattr(L, nm).argtypes = [P(CGrid), FPP, FP, FP, FPP, FPP] + [R] * 6 + box
+        for nm in ("og_update_velocity2", "og_update_velocity3"):
+            getattr(L, nm).argtypes = [P(CGrid), FPP, FPP, FP, FPP, FP, P(CIncl), R, R] + box
+        L.og_update_thermal_flux.argtypes = [P(CGrid), FPP, FP, FPP, R] + box
+        L.og_update_thermal.argtypes = [P(CGrid), FP, FP, FPP, R] + box
+        L.og_bc_apply.argtypes = [P(CGrid), FP, C.c_int, C.c_int, C.c_int, R]
+        L.og_bc_apply_field.argtypes = [P(CGrid), FP, C.c_int, C.c_int, C.c_int, R, FP]
+        L.og_slab_len.argtypes = [FP, C.c_int]
+        L.og_slab_len.restype = C.c_int64
+        L.og_pack_send.argtypes = [FP, C.c_int, C.c_int, P(R)]
+        L.og_unpack_recv.argtypes = [FP, C.c_int, C.c_int, P(R)]
+        for nm in ("og_partial", "og_partial2"):
+            getattr(L, nm).argtypes = [P(CGrid), FP, C.c_int, C.c_int64, C.c_int64, C.c_int64]
+            getattr(L, nm).restype = R
+        for nm in ("og_lerp", "og_hlerp"):
+            getattr(L, nm).argtypes = [P(CGrid), FP, P(C.c_int32), C.c_int64, C.c_int64, C.c_int64]
+            getattr(L, nm).restype = R
+        L.og_dkd.argtypes = [P(CGrid), FP, FP, C.c_int, C.c_int64, C.c_int64, C.c_int64]
+        L.og_dkd.restype = R
+        L.og_apply_operator.argtypes = [P(CGrid), C.c_int, C.c_int, FPP, FPP, FP] + box
+        L.og_num_threads.restype = C.c_int
 
 
-class _CField(C.Structure):
-    _fields_ = [("nd", C.c_int32), ("loc", C.c_int32 * 3), ("d", C.c_int64 * 3), ("sd", C.c_int64 * 3),
-                ("o", C.c_int64 * 3), ("data", C.POINTER(C.c_double))]
+_bindings: Dict[str, _Binding] = {}
 
 
-class _CIncl(C.Structure):
-    _fields_ = [("active", C.c_int32), ("loc", C.c_int32 * 3), ("c0", C.c_double * 3),
-                ("r", C.c_double), ("inn", C.c_double), ("out", C.c_double)]
-
-
-_lib = None
+def binding(dtype=np.float64) -> _Binding:
+    key = np.dtype(dtype).name
+    if key not in _bindings:
+        _bindings[key] = _Binding(dtype)
+    return _bindings[key]
 
 
 def lib():
-    global _lib
-    if _lib is None:
-        try:
-            build()
-            _lib = C.CDLL(_LIB_PATH)
-        except OSError:
-            build(force=True)
-            _lib = C.CDLL(_LIB_PATH)
-        L = _lib
-        P = C.POINTER
-        L.og_grid_init.argtypes = [P(_CGrid), C.c_int, P(C.c_int64), P(C.c_double), P(C.c_double)]
-        L.og_coord.argtypes = [P(_CGrid), C.c_int, C.c_int, C.c_int64]
-        L.og_coord.restype = C.c_double
-        L.og_field_init.argtypes = [P(_CField), P(_CGrid), P(C.c_int32), P(C.c_double)]
-        L.og_field_storage_len.argtypes = [P(_CGrid), P(C.c_int32)]
-        L.og_field_storage_len.restype = C.c_int64
-        L.og_set_inclusion.argtypes = [P(_CGrid), P(_CField), P(_CIncl)]
-        L.og_maxabs_interior.argtypes = [P(_CField)]
-        L.og_maxabs_interior.restype = C.c_double
-        box = [P(C.c_int64), P(C.c_int64)]
-        FP, FPP = P(_CField), P(P(_CField))
-        L.og_compute_q.argtypes = [P(_CGrid), FP, FP, FP, C.c_double] + box
-        L.og_update_C.argtypes = [P(_CGrid), FP, FP, FP, C.c_double] + box
-        L.og_update_old.argtypes = [P(_CGrid), C.c_int, FPP, FPP] + box
-        for nm in ("og_update_stress2", "og_update_stress3"):
-            getattr(L, nm).argtypes = [P(_CGrid), FPP, FP, FP, FPP, FPP] + [C.c_double] * 6 + box
-        for nm in ("og_update_velocity2", "og_update_velocity3"):
-            getattr(L, nm).argtypes = [P(_CGrid), FPP, FPP, FP, FPP, FP, P(_CIncl), C.c_double, C.c_double] + box
-        L.og_update_thermal_flux.argtypes = [P(_CGrid), FPP, FP, FPP, C.c_double] + box
-        L.og_update_thermal.argtypes = [P(_CGrid), FP, FP, FPP, C.c_double] + box
-        L.og_bc_apply.argtypes = [P(_CGrid), FP, C.c_int, C.c_int, C.c_int, C.c_double]
-        L.og_bc_apply_field.argtypes = [P(_CGrid), FP, C.c_int, C.c_int, C.c_int, C.c_double, FP]
-        L.og_slab_len.argtypes = [FP, C.c_int]
-        L.og_slab_len.restype = C.c_int64
-        L.og_pack_send.argtypes = [FP, C.c_int, C.c_int, P(C.c_double)]
-        L.og_unpack_recv.argtypes = [FP, C.c_int, C.c_int, P(C.c_double)]
-        for nm in ("og_partial", "og_partial2"):
-            getattr(L, nm).argtypes = [P(_CGrid), FP, C.c_int, C.c_int64, C.c_int64, C.c_int64]
-            getattr(L, nm).restype = C.c_double
-        L.og_lerp.argtypes = [P(_CGrid), FP, P(C.c_int32), C.c_int64, C.c_int64, C.c_int64]
-        L.og_lerp.restype = C.c_double
-        L.og_dkd.argtypes = [P(_CGrid), FP, FP, C.c_int, C.c_int64, C.c_int64, C.c_int64]
-        L.og_dkd.restype = C.c_double
-        L.og_hlerp.argtypes = L.og_lerp.argtypes
-        L.og_hlerp.restype = C.c_double
-        L.og_apply_operator.argtypes = [P(_CGrid), C.c_int, C.c_int, FPP, FPP, FP] + box
-        L.og_num_threads.restype = C.c_int
-    return _lib
+    """The Float64 build (the element type of every solver on this path)."""
+    return binding(np.float64).lib
 
 
 def num_threads() -> int:
@@ -130,14 +147,16 @@ def expand_loc(nd: int, loc) -> Tuple[int, ...]:
 class Grid:
     """UniformGrid(arch; origin, extent, dims, topology)  -- src/Grids/structured_grid.jl:27-39."""
 
-    def __init__(self, origin, extent, dims, conn=None):
+    def __init__(self, origin, extent, dims, conn=None, dtype=np.float64):
         nd = len(dims)
         self.nd = nd
-        self.c = _CGrid()
+        self.B = binding(dtype)                 # eltype(grid): Float64 | Float32 (test/common.jl:9)
+        self.dtype = self.B.dtype
+        self.c = self.B.CGrid()
         n = (C.c_int64 * 3)(*([int(x) for x in dims] + [1] * (3 - nd)))
-        o = (C.c_double * 3)(*([float(x) for x in origin] + [0.0] * (3 - nd)))
-        e = (C.c_double * 3)(*([float(x) for x in extent] + [0.0] * (3 - nd)))
-        lib().og_grid_init(C.byref(self.c), nd, n, o, e)
+        o = (self.B.R * 3)(*([float(x) for x in origin] + [0.0] * (3 - nd)))
+        e = (self.B.R * 3)(*([float(x) for x in extent] + [0.0] * (3 - nd)))
+        self.B.lib.og_grid_init(C.byref(self.c), nd, n, o, e)
         self.conn = [[BOUNDED, BOUNDED] for _ in range(nd)] if conn is None else [list(c) for c in conn]
         for d in range(nd):
             for s in range(2):
@@ -170,11 +189,11 @@ class Grid:
 
     def coord(self, dim: int, loc: int, i: int) -> float:
         """coord(grid, loc, Dim(dim+1), i) with 1-based i -- uniform_axis.jl:18-19."""
-        return float(lib().og_coord(C.byref(self.c), dim, loc, int(i)))
+        return float(self.B.lib.og_coord(C.byref(self.c), dim, loc, int(i)))
 
     def coords(self, dim: int, loc: int) -> np.ndarray:
         d = self.n[dim] + (1 if loc == VERTEX else 0)
-        return np.array([self.coord(dim, loc, i) for i in range(1, d + 1)])
+        return np.array([self.coord(dim, loc, i) for i in range(1, d + 1)], dtype=self.dtype)
 
     # abstract_axis.jl:23-36 / uniform_axis.jl:21-25
     def origin_at(self, dim, loc):
@@ -197,11 +216,12 @@ class Field:
         self.loc = expand_loc(grid.nd, loc)
         self.dims = grid.size(self.loc)
         self.sdims = tuple(d + 4 for d in self.dims)
-        self.data = np.zeros(self.sdims, dtype=np.float64, order="F")
-        self.c = _CField()
+        self.B, self.dtype = grid.B, grid.dtype
+        self.data = np.zeros(self.sdims, dtype=self.dtype, order="F")
+        self.c = self.B.CField()
         locs = (C.c_int32 * 3)(*(list(self.loc) + [0] * (3 - self.nd)))
-        lib().og_field_init(C.byref(self.c), C.byref(grid.c), locs,
-                            self.data.ctypes.data_as(C.POINTER(C.c_double)))
+        self.B.lib.og_field_init(C.byref(self.c), C.byref(grid.c), locs,
+                                 self.data.ctypes.data_as(C.POINTER(self.B.R)))
 
     def interior(self, with_halo: bool = False) -> np.ndarray:
         """interior(f; with_halo) -- field.jl:33-37 (a view)."""
@@ -219,7 +239,7 @@ class Field:
         self.interior()[...] = fun(*mesh, *params)
 
     def maxabs(self) -> float:
-        return float(lib().og_maxabs_interior(C.byref(self.c)))
+        return float(self.B.lib.og_maxabs_interior(C.byref(self.c)))
 
     def at(self, *I):
         """logical (reference, 1-based) indexing f[I...] -- field.jl:18."""
@@ -249,8 +269,8 @@ class Inclusion:
     inn: float
     out: float
 
-    def cstruct(self) -> _CIncl:
-        s = _CIncl()
+    def cstruct(self, B: Optional[_Binding] = None):
+        s = (B or binding()).CIncl()
         s.active = 1
         for d in range(len(self.loc)):
             s.loc[d] = self.loc[d]
@@ -260,8 +280,8 @@ class Inclusion:
 
 
 def set_inclusion(f: Field, inc: Inclusion):
-    cs = inc.cstruct()
-    lib().og_set_inclusion(C.byref(f.grid.c), C.byref(f.c), C.byref(cs))
+    cs = inc.cstruct(f.B)
+    f.B.lib.og_set_inclusion(C.byref(f.grid.c), C.byref(f.c), C.byref(cs))
 
 
 # ------------------------------------------------------------------------------------------------ BCs
@@ -358,14 +378,14 @@ def bc_side(grid: Grid, D: int, S: int, b):
             if isinstance(v, BoundaryFunction):
                 v = boundary_value_field(grid, f, bc, D, S)
             if isinstance(v, Field):
-                lib().og_bc_apply_field(C.byref(grid.c), C.byref(f.c), D, S, bc.kind, 0.0, C.byref(v.c))
+                grid.B.lib.og_bc_apply_field(C.byref(grid.c), C.byref(f.c), D, S, bc.kind, 0.0, C.byref(v.c))
             else:
-                lib().og_bc_apply(C.byref(grid.c), C.byref(f.c), D, S, bc.kind, 0.0 if v is None else float(v))
+                grid.B.lib.og_bc_apply(C.byref(grid.c), C.byref(f.c), D, S, bc.kind, 0.0 if v is None else float(v))
 
 
 def transverse_grid(grid: Grid, D: int) -> Grid:
     keep = [a for a in range(grid.nd) if a != D]
-    return Grid([grid.origin[a] for a in keep], [grid.extent[a] for a in keep], [grid.n[a] for a in keep])
+    return Grid([grid.origin[a] for a in keep], [grid.extent[a] for a in keep], [grid.n[a] for a in keep], dtype=grid.dtype)
 
 
 def boundary_value_field(grid: Grid, f: Field, bc: BC, D: int, S: int) -> Field:
@@ -458,32 +478,32 @@ class Topology:
         return r
 
 
-def local_grid(global_origin, global_extent, global_dims, topo: Topology) -> Grid:
+def local_grid(global_origin, global_extent, global_dims, topo: Topology, dtype=np.float64) -> Grid:
     """StructuredGrid{C}(arch::DistributedArchitecture, axes...) -- distributed_grid.jl:1-36.
     local_n = cld(global_n, dims); offset = coords*local_n; origin = vertex(ax, offset+1);
     extent = spacing*local_n; then UniformAxis recomputes spacing = extent/local_n."""
     nd = len(global_dims)
-    g = Grid(global_origin, global_extent, global_dims)
+    g = Grid(global_origin, global_extent, global_dims, dtype=dtype)
     ln = [-(-global_dims[d] // topo.dims[d]) for d in range(nd)]
     off = [topo.coords[d] * ln[d] for d in range(nd)]
     new_origin = [g.coord(d, VERTEX, off[d] + 1) for d in range(nd)]
     new_extent = [g.c.spacing[d] * ln[d] for d in range(nd)]
     conn = [[CONNECTED if topo.neighbors[d][s] >= 0 else BOUNDED for s in range(2)] for d in range(nd)]
-    return Grid(new_origin, new_extent, ln, conn)
+    return Grid(new_origin, new_extent, ln, conn, dtype=dtype)
 
 
 # ------------------------------------------------------------------------------------------------ halo exchange
 
 def pack_send(f: Field, D: int, S: int) -> np.ndarray:
-    n = int(lib().og_slab_len(C.byref(f.c), D))
-    buf = np.empty(n, dtype=np.float64)
-    lib().og_pack_send(C.byref(f.c), D, S, buf.ctypes.data_as(C.POINTER(C.c_double)))
+    n = int(f.B.lib.og_slab_len(C.byref(f.c), D))
+    buf = np.empty(n, dtype=f.dtype)
+    f.B.lib.og_pack_send(C.byref(f.c), D, S, buf.ctypes.data_as(C.POINTER(f.B.R)))
     return buf
 
 
 def unpack_recv(f: Field, D: int, S: int, buf: np.ndarray):
-    assert buf.size == int(lib().og_slab_len(C.byref(f.c), D))
-    lib().og_unpack_recv(C.byref(f.c), D, S, buf.ctypes.data_as(C.POINTER(C.c_double)))
+    assert buf.size == int(f.B.lib.og_slab_len(C.byref(f.c), D)) and buf.dtype == f.dtype
+    f.B.lib.og_unpack_recv(C.byref(f.c), D, S, buf.ctypes.data_as(C.POINTER(f.B.R)))
 
 
 # ------------------------------------------------------------------------------------------------ launcher
@@ -495,7 +515,7 @@ def _box(nd, lo, hi):
 
 
 def _fparr(fs: Sequence[Field]):
-    arr = (C.POINTER(_CField) * len(fs))(*[C.pointer(f.c) for f in fs])
+    arr = (C.POINTER(fs[0].B.CField) * len(fs))(*[C.pointer(f.c) for f in fs])
     return arr
 
 
@@ -504,17 +524,26 @@ def _names(nd):
 
 
 # op bodies: (grid, args, lo, hi) -> None.  Argument order follows the reference kernels' signatures.
+def _need_f64(g):
+    """The example solvers are Float64 programs (their Float64 literals would promote Float32 fields): chmy_oracle.h."""
+    if g.dtype != np.float64:
+        raise TypeError("the solver ops of this path are Float64-only (as the reference's example drivers)")
+
+
 def compute_q(g, args, lo, hi):
+    _need_f64(g)
     q, Cf, chi = args
     lib().og_compute_q(C.byref(g.c), C.byref(q["x"].c), C.byref(q["y"].c), C.byref(Cf.c), chi, *_box(g.nd, lo, hi))
 
 
 def update_C(g, args, lo, hi):
+    _need_f64(g)
     Cf, q, dt = args
     lib().og_update_C(C.byref(g.c), C.byref(Cf.c), C.byref(q["x"].c), C.byref(q["y"].c), dt, *_box(g.nd, lo, hi))
 
 
 def update_old(g, args, lo, hi):
+    _need_f64(g)
     T, tau, T_old, tau_old = args
     tn, _ = _names(g.nd)
     dst = [T_old] + [tau_old[c] for c in tn]
@@ -523,6 +552,7 @@ def update_old(g, args, lo, hi):
 
 
 def update_stress(g, args, lo, hi):
+    _need_f64(g)
     tau, Pr, divV, V, tau_old, eta, eta_ve, G, dt, dtau_Pr, dtau_r = args
     tn, vn = _names(g.nd)
     fn = lib().og_update_stress2 if g.nd == 2 else lib().og_update_stress3
@@ -531,6 +561,7 @@ def update_stress(g, args, lo, hi):
 
 
 def update_velocity(g, args, lo, hi):
+    _need_f64(g)
     V, rV, Pr, tau, rhog, eta_ve, nudtau = args
     tn, vn = _names(g.nd)
     fn = lib().og_update_velocity2 if g.nd == 2 else lib().og_update_velocity3
@@ -544,6 +575,7 @@ def update_velocity(g, args, lo, hi):
 
 
 def update_thermal_flux(g, args, lo, hi):
+    _need_f64(g)
     qT, T, V, lam = args
     _, vn = _names(g.nd)
     lib().og_update_thermal_flux(C.byref(g.c), _fparr([qT[c] for c in vn]), C.byref(T.c),
@@ -551,6 +583,7 @@ def update_thermal_flux(g, args, lo, hi):
 
 
 def update_thermal(g, args, lo, hi):
+    _need_f64(g)
     T, T_old, qT, dt = args
     _, vn = _names(g.nd)
     lib().og_update_thermal(C.byref(g.c), C.byref(T.c), C.byref(T_old.c), _fparr([qT[c] for c in vn]), dt,
@@ -660,29 +693,29 @@ def bc_(grid: Grid, *field_bcs, exchange=None):
 
 def partial(grid, f, dim, *I):
     I = list(I) + [0] * (3 - len(I))
-    return float(lib().og_partial(C.byref(grid.c), C.byref(f.c), dim, *I))
+    return float(grid.B.lib.og_partial(C.byref(grid.c), C.byref(f.c), dim, *I))
 
 
 def partial2(grid, f, dim, *I):
     I = list(I) + [0] * (3 - len(I))
-    return float(lib().og_partial2(C.byref(grid.c), C.byref(f.c), dim, *I))
+    return float(grid.B.lib.og_partial2(C.byref(grid.c), C.byref(f.c), dim, *I))
 
 
 def lerp(grid, f, to, *I):
     to = expand_loc(grid.nd, to)
     I = list(I) + [0] * (3 - len(I))
-    return float(lib().og_lerp(C.byref(grid.c), C.byref(f.c), (C.c_int32 * 3)(*(list(to) + [0] * (3 - grid.nd))), *I))
+    return float(grid.B.lib.og_lerp(C.byref(grid.c), C.byref(f.c), (C.c_int32 * 3)(*(list(to) + [0] * (3 - grid.nd))), *I))
 
 
 def dkd(grid, f, kf, dim, *I):
     I = list(I) + [0] * (3 - len(I))
-    return float(lib().og_dkd(C.byref(grid.c), C.byref(f.c), C.byref(kf.c), dim, *I))
+    return float(grid.B.lib.og_dkd(C.byref(grid.c), C.byref(f.c), C.byref(kf.c), dim, *I))
 
 
 def hlerp(grid, f, to, *I):
     to = expand_loc(grid.nd, to)
     I = list(I) + [0] * (3 - len(I))
-    return float(lib().og_hlerp(C.byref(grid.c), C.byref(f.c), (C.c_int32 * 3)(*(list(to) + [0] * (3 - grid.nd))), *I))
+    return float(grid.B.lib.og_hlerp(C.byref(grid.c), C.byref(f.c), (C.c_int32 * 3)(*(list(to) + [0] * (3 - grid.nd))), *I))
 
 
 # field-level operators: dst[I] = OP(src...)[I] over [lo, hi] (default: the launch range [0, n+1]^N, KernelLaunch.jl:41,109)
@@ -697,5 +730,5 @@ def apply_operator(grid, kind, dst, src, k=None, dim=0, lo=None, hi=None):
     lo = [0] * grid.nd if lo is None else lo
     hi = [n + 1 for n in grid.n] if hi is None else hi
     blo, bhi = _box(grid.nd, lo, hi)
-    lib().og_apply_operator(C.byref(grid.c), OPER[kind] if isinstance(kind, str) else int(kind), int(dim), _fparr(dst),
+    grid.B.lib.og_apply_operator(C.byref(grid.c), OPER[kind] if isinstance(kind, str) else int(kind), int(dim), _fparr(dst),
                             _fparr(src), None if k is None else C.byref(k.c), blo, bhi)

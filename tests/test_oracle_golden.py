@@ -8,13 +8,21 @@ import numpy as np
 import pytest
 
 PI = math.pi
+DTYPES = [np.float64, np.float32]            # TEST_TYPES of the reference (test/common.jl:9)
+
+
+def tol(dtype):
+    """Julia's `≈`: rtol = sqrt(eps(T))"""
+    return dict(rtol=float(np.sqrt(np.finfo(dtype).eps)), atol=float(np.sqrt(np.finfo(dtype).eps)) * 1e-3)
 
 
 # ------------------------------------------------------------------ test_grids.jl:11-148
-def test_grid_sizes_bounds_spacing(oracle):
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_grid_sizes_bounds_spacing(oracle, dtype):
     o = oracle
     nx, ny = 5, 20
-    g = o.Grid((-1.0, -2.0), (2.0, 4.0), (nx, ny))
+    g = o.Grid((-1.0, -2.0), (2.0, 4.0), (nx, ny), dtype=dtype)
+    assert g.dtype == dtype and np.asarray(g.coords(0, o.CENTER)).dtype == dtype
     assert g.size(o.CENTER) == (nx, ny)                                   # :31-39
     assert g.size(o.VERTEX) == (nx + 1, ny + 1)
     assert g.size((o.CENTER, o.VERTEX)) == (nx, ny + 1)
@@ -36,11 +44,12 @@ def test_grid_sizes_bounds_spacing(oracle):
 
 
 # ------------------------------------------------------------------ test_fields.jl:19-55 (exact == in the reference)
-def test_set_continuous_exact(oracle):
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_set_continuous_exact(oracle, dtype):
     o = oracle
-    g = o.Grid((0.0, 0.0, 0.0), (1.0, 1.0, 1.0), (2, 2, 2))
+    g = o.Grid((0.0, 0.0, 0.0), (1.0, 1.0, 1.0), (2, 2, 2), dtype=dtype)
     f = o.Field(g, (o.CENTER, o.VERTEX, o.CENTER))
-    assert f.dims == (2, 3, 2)
+    assert f.dims == (2, 3, 2) and f.data.dtype == dtype
     f.data[...] = np.nan
     f.set_fun(lambda x, y, z: y)
     exp_y = np.zeros((2, 3, 2))
@@ -73,12 +82,15 @@ def _face(a, dim, idx):
     return a[tuple(sl)]
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("n,loc", CASES)
-def test_bc_known_answers(oracle, n, loc):
+def test_bc_known_answers(oracle, n, loc, dtype):
     o = oracle
     nd = len(n)
-    g = o.Grid((-PI,) * nd, (2 * PI,) * nd, n)
+    g = o.Grid((-PI,) * nd, (2 * PI,) * nd, n, dtype=dtype)
     f = o.Field(g, loc)
+    assert f.data.dtype == dtype
+    allclose = lambda a, b: np.allclose(a, b, **tol(dtype))
 
     def run(bc):
         f.data[...] = 0.0
@@ -89,26 +101,26 @@ def test_bc_known_answers(oracle, n, loc):
     a = run(o.Dirichlet())
     for d in range(nd):
         if loc[d] == o.CENTER:
-            assert np.allclose(_face(a, d, 0), -_face(a, d, 1)) and np.allclose(_face(a, d, -1), -_face(a, d, -2))
+            assert allclose(_face(a, d, 0), -_face(a, d, 1)) and allclose(_face(a, d, -1), -_face(a, d, -2))
         else:
-            assert np.allclose(_face(a, d, 1), 0.0) and np.allclose(_face(a, d, -2), 0.0)
+            assert allclose(_face(a, d, 1), 0.0) and allclose(_face(a, d, -2), 0.0)
     a = run(o.Neumann())
     for d in range(nd):
-        assert np.allclose(_face(a, d, 0), _face(a, d, 1)) and np.allclose(_face(a, d, -1), _face(a, d, -2))
+        assert allclose(_face(a, d, 0), _face(a, d, 1)) and allclose(_face(a, d, -1), _face(a, d, -2))
     v = 2.0
     a = run(o.Dirichlet(v))
     for d in range(nd):
         if loc[d] == o.CENTER:
-            assert np.allclose(_face(a, d, 0), -_face(a, d, 1) + 2 * v)
-            assert np.allclose(_face(a, d, -1), -_face(a, d, -2) + 2 * v)
+            assert allclose(_face(a, d, 0), -_face(a, d, 1) + 2 * v)
+            assert allclose(_face(a, d, -1), -_face(a, d, -2) + 2 * v)
         else:
-            assert np.allclose(_face(a, d, 1), v) and np.allclose(_face(a, d, -2), v)
+            assert allclose(_face(a, d, 1), v) and allclose(_face(a, d, -2), v)
     q = 2.0
     a = run(o.Neumann(q))
     for d in range(nd):
         h = g.spacing[d]
-        assert np.allclose((_face(a, d, 1) - _face(a, d, 0)) / h, q)
-        assert np.allclose((_face(a, d, -1) - _face(a, d, -2)) / h, q)
+        assert allclose((_face(a, d, 1) - _face(a, d, 0)) / h, q)
+        assert allclose((_face(a, d, -1) - _face(a, d, -2)) / h, q)
 
 
 # ------------------------------------------------------------------ test_grid_operators.jl:13-131
@@ -190,9 +202,10 @@ def test_vmag_constant(oracle):
 
 
 # ------------------------------------------------------------------ test_interpolations.jl:15-74
-def test_lerp_known_answers(oracle):
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_lerp_known_answers(oracle, dtype):
     o = oracle
-    g = o.Grid((0.0, 0.0), (1.0, 1.0), (2, 2))
+    g = o.Grid((0.0, 0.0), (1.0, 1.0), (2, 2), dtype=dtype)
     av4 = lambda A: 0.25 * (A[:-1, :-1] + A[1:, :-1] + A[1:, 1:] + A[:-1, 1:])
     avx = lambda A: 0.5 * (A[:-1, :] + A[1:, :])
     avy = lambda A: 0.5 * (A[:, :-1] + A[:, 1:])
@@ -370,3 +383,41 @@ def test_apply_operator_is_the_point_functions_over_the_launch_range(oracle):
     mask = np.ones(before.sdims, bool)
     mask[1:-1, 1:-1, 1:-1] = False
     assert np.array_equal(before.data[mask], keep[mask]) and not np.array_equal(before.data, keep)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_operator_identities_both_element_types(oracle, dtype):
+    """test/test_grid_operators.jl:13-131 for T in (Float32, Float64) through the field-level operators: divg == sum of
+    the partial derivatives (`==`, :41), lapl == sum of second derivatives (`==`, :61), divg_grad ≈ divg(lerp(χ) grad)
+    (:98,:110), vmag of (2,2,2) rounds to 3.4641 (:130).  Every result stays in the element type."""
+    o = oracle
+    g = o.Grid((-5.0,) * 3, (10.0,) * 3, (12, 10, 8), dtype=dtype)
+    gauss = lambda x, y, z: np.exp(-x ** 2 - y ** 2 - z ** 2)
+    Ci, C1, C2, P = (o.Field(g, 0) for _ in range(4))
+    Ci.set_fun(gauss)
+    V = [o.Field(g, tuple(1 if a == d else 0 for a in range(3))) for d in range(3)]
+    o.apply_operator(g, "grad", V, Ci)
+    o.apply_operator(g, "divg", C2, V)
+    acc = None
+    for d in range(3):
+        o.apply_operator(g, "partial", P, V[d], dim=d)
+        acc = P.interior().copy() if acc is None else acc + P.interior()
+    assert acc.dtype == dtype and np.array_equal(C2.interior(), acc) and np.abs(acc).max() > 1e-3
+    o.apply_operator(g, "lapl", C2, Ci)
+    acc = None
+    for d in range(3):
+        o.apply_operator(g, "partial2", P, Ci, dim=d)
+        acc = P.interior().copy() if acc is None else acc + P.interior()
+    assert np.array_equal(C2.interior(), acc)
+    for chi_loc in (0, 1):
+        chi = o.Field(g, chi_loc)
+        chi.set_fun(gauss)
+        o.apply_operator(g, "kgrad", V, Ci, k=chi)
+        o.apply_operator(g, "divg", C1, V)
+        o.apply_operator(g, "divg_grad", C2, Ci, k=chi)
+        assert np.allclose(C2.interior(), C1.interior(), **tol(dtype))
+    for c in V:
+        c.set(2.0)
+    o.apply_operator(g, "vmag", C1, V)
+    assert C1.data.dtype == dtype
+    assert np.all(np.vectorize(lambda x: float(f"{x:.5g}"))(C1.interior().astype(np.float64)) == 3.4641)

