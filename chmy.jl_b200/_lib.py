@@ -20,6 +20,7 @@ BOUNDED, CONNECTED = 0, 1
 DIRICHLET, NEUMANN = 0, 1
 BATCH_EMPTY, BATCH_FIELD, BATCH_EXCHANGE = 0, 1, 2
 LAYOUT_PITCHED, LAYOUT_DENSE = 0, 1
+F64, F32 = 0, 1
 LAUNCH_ASYNC, LAUNCH_BLOCKING, LAUNCH_EXACT_SPLIT = 0, 1, 2
 
 OP_NONE, OP_COMPUTE_Q, OP_UPDATE_C, OP_UPDATE_OLD, OP_UPDATE_STRESS, OP_UPDATE_VELOCITY, OP_UPDATE_THERMAL_FLUX, \
@@ -63,7 +64,8 @@ class LaunchDesc(C.Structure):
 class FieldInfo(C.Structure):
     _fields_ = [("ndims", C.c_int32), ("layout", C.c_int32), ("loc", C.c_int32 * MAX_DIMS),
                 ("dims", C.c_int64 * MAX_DIMS), ("stride", C.c_int64 * MAX_DIMS),
-                ("origin_ptr", C.c_void_p), ("base_ptr", C.c_void_p), ("bytes", C.c_size_t)]
+                ("origin_ptr", C.c_void_p), ("base_ptr", C.c_void_p), ("bytes", C.c_size_t),
+                ("dtype", C.c_int32), ("_pad", C.c_int32)]
 
 
 # every symbol include/chmy_b200.h declares: (name, restype, argtypes)
@@ -90,6 +92,7 @@ SYMBOLS = {
     "chmy_allreduce_max": (C.c_int, [_vp, _dp, C.c_int]),
     "chmy_barrier": (C.c_int, [_vp]),
     "chmy_field_create": (C.c_int, [_vp, C.c_int, _i64p, _i32p, C.c_int, _P(_vp)]),
+    "chmy_field_create_typed": (C.c_int, [_vp, C.c_int, _i64p, _i32p, C.c_int, C.c_int, _P(_vp)]),
     "chmy_field_destroy": (C.c_int, [_vp]),
     "chmy_field_get_info": (C.c_int, [_vp, _P(FieldInfo)]),
     "chmy_field_fill": (C.c_int, [_vp, _vp, C.c_double, _i64p, _i64p]),

@@ -92,10 +92,10 @@ def boundary_value_field(arch, grid: StructuredGrid, f: Field, bc: FirstOrderBC,
     N = grid.ndims()
     taxes = [ax for a, ax in enumerate(grid.axes) if a != D]
     tgrid = StructuredGrid(taxes, [c for a, c in enumerate(grid.connectivity_) if a != D])
-    vf = Field(arch, tgrid, Vertex())                         # d_t = n_t + 1: logical indices -1..n_t+3 exist
+    vf = Field(arch, tgrid, Vertex(), f.dtype)                # d_t = n_t + 1: logical indices -1..n_t+3 exist
     ext = [ax.length + 3 for ax in taxes]                     # indices 0..n_t+2
     import numpy as np
-    vals = np.empty(ext, dtype=np.float64, order="F")
+    vals = np.empty(ext, dtype=f.dtype, order="F")
     for J in np.ndindex(*ext):
         I = insert_dim(D + 1, tuple(int(j) for j in J), idx)
         vals[J] = bf(grid, loc, D + 1, *I)

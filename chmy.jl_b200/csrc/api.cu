@@ -10,6 +10,7 @@ int chmy_box_from(const chmy_field* f, const int64_t* lo, const int64_t* hi, Box
 int chmy_fill_box(chmy_ctx* ctx, chmy_field* f, double v, const Box& b, cudaStream_t st);
 int chmy_copy_box(chmy_ctx* ctx, chmy_field* d, const chmy_field* s, const Box& b, cudaStream_t st);
 int chmy_incl_box(chmy_ctx* ctx, chmy_field* f, const InclDev& q, const Box& b, cudaStream_t st);
+int chmy_incl_box_f32(chmy_ctx* ctx, chmy_field* f, const InclDevT<float>& q, const Box& b, cudaStream_t st);
 int chmy_maxabs_box(chmy_ctx* ctx, const chmy_field* f, const Box& b, unsigned long long* d_out, cudaStream_t st);
 int chmy_run_op_generic(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st);
 int chmy_run_op_fast(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st, int* handled);
@@ -160,39 +161,51 @@ static inline long long round_up(long long x, long long m) { return (x + m - 1) 
 
 extern "C" int chmy_field_create(chmy_ctx* ctx, int ndims, const int64_t* dims, const int32_t* loc, int layout,
                                  chmy_field** out) {
+    return chmy_field_create_typed(ctx, ndims, dims, loc, layout, CHMY_F64, out);
+}
+
+extern "C" int chmy_field_create_typed(chmy_ctx* ctx, int ndims, const int64_t* dims, const int32_t* loc, int layout,
+                                       int dtype, chmy_field** out) {
     CHMY_REQUIRE(ctx && dims && loc && out, "NULL argument");
     CHMY_REQUIRE(ndims >= 1 && ndims <= 3, "ndims %d not in 1..3", ndims);
     CHMY_REQUIRE(layout == CHMY_LAYOUT_PITCHED || layout == CHMY_LAYOUT_DENSE, "bad layout %d", layout);
+    CHMY_REQUIRE(dtype == CHMY_F64 || dtype == CHMY_F32, "bad element type %d", dtype);
+    for (int a = 0; a < ndims; ++a) {
+        CHMY_REQUIRE(dims[a] >= 1 && dims[a] < (1ll << 30), "bad field size %lld along dim %d", (long long)dims[a], a + 1);
+        CHMY_REQUIRE(loc[a] == CHMY_CENTER || loc[a] == CHMY_VERTEX, "bad location along dim %d", a + 1);
+    }
     chmy_field* f = (chmy_field*)calloc(1, sizeof(chmy_field));
     if (!f) { chmy_set_error("out of host memory"); return CHMY_ERR_NOMEM; }
     f->ctx = ctx; f->nd = ndims; f->layout = layout;
+    f->dtype = dtype; f->esize = dtype == CHMY_F32 ? 4 : 8;
     for (int a = 0; a < 3; ++a) {
         if (a < ndims) {
-            CHMY_REQUIRE(dims[a] >= 1 && dims[a] < (1ll << 30), "bad field size %lld along dim %d", (long long)dims[a], a + 1);
-            CHMY_REQUIRE(loc[a] == CHMY_CENTER || loc[a] == CHMY_VERTEX, "bad location along dim %d", a + 1);
             f->loc[a] = loc[a]; f->d[a] = dims[a]; f->sd[a] = dims[a] + 4;   // field.jl:58 (halo = 1)
         } else {
             f->loc[a] = CHMY_CENTER; f->d[a] = 1; f->sd[a] = 1;
         }
     }
-    // PITCHED: row pitch a multiple of 16 doubles and a 15-element lead-in, so that logical index 0 of every row
-    // sits on a 128-byte boundary (storage element 0 is logical -1).
-    const long long pitch = layout == CHMY_LAYOUT_PITCHED ? round_up(f->sd[0], 16) : f->sd[0];
-    f->lead      = layout == CHMY_LAYOUT_PITCHED ? 15 : 0;
+    // PITCHED: row pitch a multiple of 128 bytes (16 doubles | 32 floats) and a lead-in of one element less, so that
+    // logical index 0 of every row sits on a 128-byte boundary (storage element 0 is logical -1).
+    const long long per128 = 128 / f->esize;
+    const long long pitch = layout == CHMY_LAYOUT_PITCHED ? round_up(f->sd[0], per128) : f->sd[0];
+    f->lead      = layout == CHMY_LAYOUT_PITCHED ? per128 - 1 : 0;
     f->stride[0] = 1;
     f->stride[1] = pitch;
     f->stride[2] = pitch * f->sd[1];
-    const long long elems = f->lead + pitch * f->sd[1] * f->sd[2] + 32;
-    f->bytes = (size_t)elems * sizeof(double);
+    const long long elems = f->lead + pitch * f->sd[1] * f->sd[2] + 2 * per128;
+    f->bytes = (size_t)elems * (size_t)f->esize;
     CHMY_CUDA(cudaSetDevice(ctx->device));
     cudaError_t e = cudaMalloc(&f->alloc, f->bytes);
     if (e != cudaSuccess) {
         free(f);
-        chmy_set_error("cudaMalloc of %zu bytes failed: %s", (size_t)elems * 8, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        chmy_set_error("cudaMalloc of %zu bytes failed: %s", (size_t)elems * (size_t)(dtype == CHMY_F32 ? 4 : 8), cudaGetErrorString(e));
         return CHMY_ERR_NOMEM;
     }
     CHMY_CUDA(cudaMemsetAsync(f->alloc, 0, f->bytes, ctx->s_main));   // KernelAbstractions.zeros, field.jl:59
-    f->p0 = f->alloc + f->lead + 1 + (ndims > 1 ? f->stride[1] : 0) + (ndims > 2 ? f->stride[2] : 0);
+    f->p0 = reinterpret_cast<double*>(reinterpret_cast<char*>(f->alloc) + (size_t)f->esize *
+                (size_t)(f->lead + 1 + (ndims > 1 ? f->stride[1] : 0) + (ndims > 2 ? f->stride[2] : 0)));
     *out = f;
     return CHMY_OK;
 }
@@ -216,9 +229,10 @@ extern "C" int chmy_field_get_info(const chmy_field* f, chmy_field_info* out) {
     memset(out, 0, sizeof(*out));
     out->ndims = f->nd; out->layout = f->layout;
     for (int a = 0; a < 3; ++a) { out->loc[a] = f->loc[a]; out->dims[a] = f->d[a]; out->stride[a] = f->stride[a]; }
-    out->origin_ptr = (void*)f->at(1, 1, 1);
-    out->base_ptr   = (void*)f->at(-1, -1, -1);
+    out->origin_ptr = (void*)f->at_bytes(1, f->nd > 1 ? 1 : 0, f->nd > 2 ? 1 : 0);
+    out->base_ptr   = (void*)f->at_bytes(-1, f->nd > 1 ? -1 : 0, f->nd > 2 ? -1 : 0);
     out->bytes      = f->bytes;
+    out->dtype      = f->dtype;
     return CHMY_OK;
 }
 
@@ -234,6 +248,7 @@ extern "C" int chmy_field_fill(chmy_ctx* ctx, chmy_field* f, double v, const int
 extern "C" int chmy_field_copy(chmy_ctx* ctx, chmy_field* dst, const chmy_field* src, const int64_t* lo, const int64_t* hi) {
     CHMY_REQUIRE(ctx && dst && src && lo && hi, "NULL argument");
     CHMY_REQUIRE(dst->nd == src->nd, "set!(f, other): dimensionality mismatch");
+    CHMY_REQUIRE(dst->dtype == src->dtype, "set!(f, other): element types differ");
     Box b, b2;
     CHMY_TRY(chmy_box_from(dst, lo, hi, &b));
     CHMY_TRY(chmy_box_from(src, lo, hi, &b2));
@@ -242,19 +257,20 @@ extern "C" int chmy_field_copy(chmy_ctx* ctx, chmy_field* dst, const chmy_field*
     return chmy_copy_box(ctx, dst, src, b, ctx->s_main);
 }
 
-static int copy_box_host(chmy_ctx* ctx, const chmy_field* f, double* host, const int64_t* lo, const int64_t* hi, bool to_host) {
+// `host` holds elements of the field's type (Array{Float64} | Array{Float32} in the reference's set!/Array)
+static int copy_box_host(chmy_ctx* ctx, const chmy_field* f, void* host, const int64_t* lo, const int64_t* hi, bool to_host) {
     Box b;
     CHMY_TRY(chmy_box_from(f, lo, hi, &b));
     if (b.n[0] <= 0 || b.n[1] <= 0 || b.n[2] <= 0) return CHMY_OK;
     CHMY_TRY(chmy_flush(ctx));
     if (!to_host) const_cast<chmy_field*>(f)->frame_synced = false;
     CHMY_CUDA(cudaSetDevice(ctx->device));
-    double* dev = f->at(b.lo[0], f->nd > 1 ? b.lo[1] : 0, f->nd > 2 ? b.lo[2] : 0);
+    char* dev = f->at_bytes(b.lo[0], f->nd > 1 ? b.lo[1] : 0, f->nd > 2 ? b.lo[2] : 0);
     cudaMemcpy3DParms p;
     memset(&p, 0, sizeof(p));
-    const size_t w = (size_t)b.n[0] * sizeof(double);
+    const size_t w = (size_t)b.n[0] * (size_t)f->esize;
     cudaPitchedPtr hp = make_cudaPitchedPtr(host, w, (size_t)b.n[0], (size_t)b.n[1]);
-    cudaPitchedPtr dp = make_cudaPitchedPtr(dev, (size_t)f->stride[1] * sizeof(double), (size_t)f->sd[0], (size_t)f->sd[1]);
+    cudaPitchedPtr dp = make_cudaPitchedPtr(dev, (size_t)f->stride[1] * (size_t)f->esize, (size_t)f->sd[0], (size_t)f->sd[1]);
     p.srcPtr = to_host ? dp : hp;
     p.dstPtr = to_host ? hp : dp;
     p.extent = make_cudaExtent(w, (size_t)b.n[1], (size_t)b.n[2]);
@@ -265,12 +281,12 @@ static int copy_box_host(chmy_ctx* ctx, const chmy_field* f, double* host, const
     return CHMY_OK;
 }
 
-extern "C" int chmy_field_copy_from_host(chmy_ctx* ctx, chmy_field* f, const double* src, const int64_t* lo, const int64_t* hi) {
+extern "C" int chmy_field_copy_from_host(chmy_ctx* ctx, chmy_field* f, const void* src, const int64_t* lo, const int64_t* hi) {
     CHMY_REQUIRE(ctx && f && src && lo && hi, "NULL argument");
-    return copy_box_host(ctx, f, const_cast<double*>(src), lo, hi, false);
+    return copy_box_host(ctx, f, const_cast<void*>(src), lo, hi, false);
 }
 
-extern "C" int chmy_field_copy_to_host(chmy_ctx* ctx, const chmy_field* f, double* dst, const int64_t* lo, const int64_t* hi) {
+extern "C" int chmy_field_copy_to_host(chmy_ctx* ctx, const chmy_field* f, void* dst, const int64_t* lo, const int64_t* hi) {
     CHMY_REQUIRE(ctx && f && dst && lo && hi, "NULL argument");
     return copy_box_host(ctx, f, dst, lo, hi, true);
 }
@@ -296,14 +312,15 @@ extern "C" int chmy_host_free(chmy_ctx* ctx, void* p) {
     return CHMY_OK;
 }
 
-static InclDev incl_from(const chmy_grid_desc* g, const chmy_inclusion* inc, const int* loc) {
-    InclDev q;
+template <class T>
+static InclDevT<T> incl_from(const chmy_grid_desc* g, const chmy_inclusion* inc, const int* loc) {
+    InclDevT<T> q;
     memset(&q, 0, sizeof(q));
     q.active = 1; q.nd = g->ndims;
     for (int a = 0; a < 3; ++a) {
-        q.loc[a] = loc[a]; q.origin[a] = g->origin[a]; q.spacing[a] = g->spacing[a]; q.c0[a] = inc->c0[a];
+        q.loc[a] = loc[a]; q.origin[a] = (T)g->origin[a]; q.spacing[a] = (T)g->spacing[a]; q.c0[a] = (T)inc->c0[a];
     }
-    q.r2 = inc->r * inc->r; q.in = inc->in; q.out = inc->out;
+    q.r2 = (T)inc->r * (T)inc->r; q.in = (T)inc->in; q.out = (T)inc->out;      // r^2 in the element type
     return q;
 }
 
@@ -315,7 +332,8 @@ extern "C" int chmy_field_set_inclusion(chmy_ctx* ctx, chmy_field* f, const chmy
     CHMY_TRY(chmy_box_from(f, lo, hi, &b));
     CHMY_TRY(chmy_flush(ctx));
     CHMY_CUDA(cudaSetDevice(ctx->device));
-    return chmy_incl_box(ctx, f, incl_from(g, inc, f->loc), b, ctx->s_main);
+    if (f->dtype == CHMY_F32) return chmy_incl_box_f32(ctx, f, incl_from<float>(g, inc, f->loc), b, ctx->s_main);
+    return chmy_incl_box(ctx, f, incl_from<double>(g, inc, f->loc), b, ctx->s_main);
 }
 
 extern "C" int chmy_field_maxabs(chmy_ctx* ctx, const chmy_field* f, const int64_t* lo, const int64_t* hi, double* out) {
@@ -329,7 +347,14 @@ extern "C" int chmy_field_maxabs(chmy_ctx* ctx, const chmy_field* f, const int64
     if (b.n[0] > 0 && b.n[1] > 0 && b.n[2] > 0) CHMY_TRY(chmy_maxabs_box(ctx, f, b, ctx->d_red, ctx->s_main));
     CHMY_CUDA(cudaMemcpyAsync(ctx->h_red, ctx->d_red, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->s_main));
     CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));
-    memcpy(out, ctx->h_red, sizeof(double));
+    if (f->dtype == CHMY_F32) {      // the reduction ran on binary32 bit patterns
+        const unsigned int bits = (unsigned int)ctx->h_red[0];
+        float v;
+        memcpy(&v, &bits, sizeof(v));
+        *out = (double)v;
+    } else {
+        memcpy(out, ctx->h_red, sizeof(double));
+    }
     return CHMY_OK;
 }
 
@@ -339,11 +364,11 @@ extern "C" int chmy_halo_slab_len(const chmy_field* f, int dim, int64_t* len) {
     return CHMY_OK;
 }
 
-static int halo_host(chmy_ctx* ctx, chmy_field* f, int dim, int side, double* host, bool pack) {
+static int halo_host(chmy_ctx* ctx, chmy_field* f, int dim, int side, void* host, bool pack) {
     CHMY_REQUIRE(ctx && f && host && dim >= 0 && dim < f->nd && (side == 0 || side == 1), "bad argument");
-    const size_t bytes = (size_t)chmy_slab_len(f, dim) * sizeof(double);
+    const size_t bytes = (size_t)chmy_slab_len(f, dim) * (size_t)f->esize;
     CHMY_TRY(chmy_flush(ctx));
-    double* dbuf = nullptr;
+    void* dbuf = nullptr;
     CHMY_CUDA(cudaSetDevice(ctx->device));
     CHMY_CUDA(cudaMalloc(&dbuf, bytes));
     int rc = CHMY_OK;
@@ -360,11 +385,11 @@ static int halo_host(chmy_ctx* ctx, chmy_field* f, int dim, int side, double* ho
     return rc;
 }
 
-extern "C" int chmy_halo_pack(chmy_ctx* ctx, const chmy_field* f, int dim, int side, double* host_buf) {
+extern "C" int chmy_halo_pack(chmy_ctx* ctx, const chmy_field* f, int dim, int side, void* host_buf) {
     return halo_host(ctx, const_cast<chmy_field*>(f), dim, side, host_buf, true);
 }
-extern "C" int chmy_halo_unpack(chmy_ctx* ctx, chmy_field* f, int dim, int side, const double* host_buf) {
-    return halo_host(ctx, f, dim, side, const_cast<double*>(host_buf), false);
+extern "C" int chmy_halo_unpack(chmy_ctx* ctx, chmy_field* f, int dim, int side, const void* host_buf) {
+    return halo_host(ctx, f, dim, side, const_cast<void*>(host_buf), false);
 }
 
 // ---------------------------------------------------------------------------------------------- launch

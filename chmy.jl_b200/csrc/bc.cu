@@ -9,34 +9,37 @@
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------- BC batches
+template <class T>
 struct BcEntry {
-    FV     f;
+    FVT<T> f;
     int    kind;      // chmy_bc_kind
     int    vertex;    // location of the field along the BC dim
     int    d;         // logical size of the field along the BC dim
     int    side;      // 0 | 1
-    double value;
-    const double* vp; // Field-valued condition: logical (0[,0]) of the (N-1)-dimensional value field, else nullptr
-    long long     vsy;
+    T      value;
+    const T*  vp;     // Field-valued condition: logical (0[,0]) of the (N-1)-dimensional value field, else nullptr
+    long long vsy;
 };
 
+template <class T>
 struct BcBatchDev {
-    int     n;                                   // entries (both sides of one dim)
-    int     dim;
-    int     nt[2];                               // transverse extents (n_t + 3 points each; 1 when absent)
-    double  spacing;
-    BcEntry e[2 * CHMY_MAX_BATCH_FIELDS];
+    int        n;                                // entries (both sides of one dim)
+    int        dim;
+    int        nt[2];                            // transverse extents (n_t + 3 points each; 1 when absent)
+    T          spacing;
+    BcEntry<T> e[2 * CHMY_MAX_BATCH_FIELDS];
 };
 
 // One thread per face point; both sides and all fields of a dimension in one launch.  Entries of different sides
 // touch disjoint cells and different fields are independent, so the reference's sequential order
 // (side 1 then 2, fields in batch order) is preserved per cell.
-__global__ void __launch_bounds__(256) k_bc_dim(const BcBatchDev b) {
+template <class T>
+__global__ void __launch_bounds__(256) k_bc_dim(const BcBatchDev<T> b) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;   // first transverse index  (0..nt0-1)
     const int c = blockIdx.y;                              // second transverse index (0..nt1-1)
     if (a >= b.nt[0]) return;
     for (int q = 0; q < b.n; ++q) {
-        const BcEntry& e = b.e[q];
+        const BcEntry<T>& e = b.e[q];
         int I[3], N[3];
         // insert_dim(dim, (a, c), idx)  -- src/utils.jl:47-51
         int t = 0;
@@ -48,27 +51,28 @@ __global__ void __launch_bounds__(256) k_bc_dim(const BcBatchDev b) {
             else { I[dd] = N[dd] = (t < 2 ? tr[t] : 0); ++t; }
         }
         // value(bc, grid, loc, dim, I...): Number | bc.value[remove_dim(dim, I)...]  (first_order_boundary_condition.jl:34-40)
-        const double val = e.vp ? e.vp[(long long)a + (long long)c * e.vsy] : e.value;
+        const T val = e.vp ? e.vp[(long long)a + (long long)c * e.vsy] : e.value;
         if (e.kind == CHMY_DIRICHLET) {
             if (e.vertex) {
                 fv_st(e.f, N[0], N[1], N[2], val);
             } else {
-                const double nb = fv_ld(e.f, N[0], N[1], N[2]);
-                fv_st(e.f, I[0], I[1], I[2], fma(2.0, val - nb, nb));
+                const T nb = fv_ld(e.f, N[0], N[1], N[2]);
+                fv_st(e.f, I[0], I[1], I[2], fma((T)2.0, val - nb, nb));
             }
         } else {
-            const double qs = e.side == 0 ? -val : val;
+            const T qs = e.side == 0 ? -val : val;
             fv_st(e.f, I[0], I[1], I[2], fma(b.spacing, qs, fv_ld(e.f, N[0], N[1], N[2])));
         }
     }
 }
 
-int chmy_run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_batch_desc* left,
-                    const chmy_batch_desc* right, cudaStream_t st) {
-    BcBatchDev b;
+template <class T>
+static int run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_batch_desc* left,
+                      const chmy_batch_desc* right, int dtype, cudaStream_t st) {
+    BcBatchDev<T> b;
     memset(&b, 0, sizeof(b));
     b.dim     = dim;
-    b.spacing = g->spacing[dim];
+    b.spacing = (T)g->spacing[dim];
     const chmy_batch_desc* sides[2] = {left, right};
     for (int s = 0; s < 2; ++s) {
         const chmy_batch_desc* bd = sides[s];
@@ -78,13 +82,14 @@ int chmy_run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_
         for (int q = 0; q < bd->nfields; ++q) {
             const chmy_field* f = bd->fields[q];
             CHMY_REQUIRE(f != nullptr && f->nd == g->ndims, "FieldBatch: bad field %d", q);
+            CHMY_REQUIRE(f->dtype == dtype, "FieldBatch: the fields of one dimension's batches must share an element type");
             CHMY_REQUIRE(bd->bc_kind[q] == CHMY_DIRICHLET || bd->bc_kind[q] == CHMY_NEUMANN, "FieldBatch: bad bc kind");
             for (int a = 0; a < g->ndims; ++a)
                 CHMY_REQUIRE(f->d[a] == g->n[a] + (f->loc[a] == CHMY_VERTEX ? 1 : 0), "FieldBatch: field/grid size mismatch");
             bd->fields[q]->frame_synced = false;      // a halo of a Vertex field lies outside the ops' index range
-            BcEntry& e = b.e[b.n++];
-            e.f = f->view(); e.kind = bd->bc_kind[q]; e.vertex = f->loc[dim] == CHMY_VERTEX; e.d = (int)f->d[dim];
-            e.side = s; e.value = bd->value[q];
+            BcEntry<T>& e = b.e[b.n++];
+            e.f = f->viewT<T>(); e.kind = bd->bc_kind[q]; e.vertex = f->loc[dim] == CHMY_VERTEX; e.d = (int)f->d[dim];
+            e.side = s; e.value = (T)bd->value[q];
             e.vp = nullptr; e.vsy = 0;
             if (const chmy_field* vf = bd->value_field[q]) {
                 CHMY_REQUIRE(g->ndims >= 2 && vf->nd == g->ndims - 1, "Field-valued condition: the value field must have %d dims", g->ndims - 1);
@@ -94,7 +99,8 @@ int chmy_run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_
                     CHMY_REQUIRE(vf->d[t] >= g->n[a], "Field-valued condition: value field too small along transverse dim %d", t + 1);
                     ++t;
                 }
-                e.vp = vf->p0; e.vsy = vf->nd > 1 ? vf->stride[1] : 0;
+                CHMY_REQUIRE(vf->dtype == dtype, "Field-valued condition: the value field must have the field's element type");
+                e.vp = reinterpret_cast<const T*>(vf->p0); e.vsy = vf->nd > 1 ? vf->stride[1] : 0;
             }
         }
     }
@@ -105,10 +111,21 @@ int chmy_run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_
         if (a != dim) b.nt[t++] = (int)g->n[a] + 3;      // remove_dim(dim, nvertices + 2), batch.jl:181
     const dim3 blk(128, 1, 1);
     const dim3 grd((b.nt[0] + 127) / 128, b.nt[1], 1);
-    k_bc_dim<<<grd, blk, 0, st>>>(b);
+    k_bc_dim<T><<<grd, blk, 0, st>>>(b);
     ctx->n_launches++;
     CHMY_CUDA(cudaGetLastError());
     return CHMY_OK;
+}
+
+int chmy_run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_batch_desc* left,
+                    const chmy_batch_desc* right, cudaStream_t st) {
+    int dtype = CHMY_F64;        // element type of the first field decides; run_bc_dim checks the rest against it
+    const chmy_batch_desc* sides[2] = {left, right};
+    for (int s = 1; s >= 0; --s)
+        if (sides[s] && sides[s]->kind == CHMY_BATCH_FIELD && sides[s]->nfields > 0 && sides[s]->fields[0])
+            dtype = sides[s]->fields[0]->dtype;
+    if (dtype == CHMY_F32) return run_bc_dim<float>(ctx, g, dim, left, right, dtype, st);
+    return run_bc_dim<double>(ctx, g, dim, left, right, dtype, st);
 }
 
 // ---------------------------------------------------------------------------------------------- halo slabs
@@ -121,20 +138,22 @@ long long chmy_slab_len(const chmy_field* f, int dim) {
     return len;
 }
 
+template <class T>
 struct SlabEntry {
-    FV        f;
+    FVT<T>    f;
     int       idx;        // logical index of the slab along dim
     int       e0, e1;     // transverse extents (sd_t), 1 when absent
     long long off;        // element offset of this field's slab in the buffer
 };
+template <class T>
 struct SlabBatch {
-    int       n, dim, nd;
-    SlabEntry e[CHMY_MAX_BATCH_FIELDS];
+    int          n, dim, nd;
+    SlabEntry<T> e[CHMY_MAX_BATCH_FIELDS];
 };
 
-template <bool PACK>
-__global__ void __launch_bounds__(256) k_slab(const SlabBatch b, double* __restrict__ buf) {
-    const SlabEntry& e = b.e[blockIdx.z];
+template <bool PACK, class T>
+__global__ void __launch_bounds__(256) k_slab(const SlabBatch<T> b, T* __restrict__ buf) {
+    const SlabEntry<T>& e = b.e[blockIdx.z];
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y * blockDim.y + threadIdx.y;
     if (a >= e.e0 || c >= e.e1) return;
@@ -150,9 +169,10 @@ __global__ void __launch_bounds__(256) k_slab(const SlabBatch b, double* __restr
     else fv_st(e.f, I[0], I[1], I[2], buf[p]);
 }
 
-static int make_slab_batch(int dim, int side, int nf, chmy_field* const* fs, bool send, SlabBatch* out) {
+template <class T>
+static int make_slab_batch(int dim, int side, int nf, chmy_field* const* fs, bool send, SlabBatch<T>* out) {
     CHMY_REQUIRE(nf >= 1 && nf <= CHMY_MAX_BATCH_FIELDS, "exchange with %d fields (max %d)", nf, CHMY_MAX_BATCH_FIELDS);
-    SlabBatch& b = *out;
+    SlabBatch<T>& b = *out;
     memset(&b, 0, sizeof(b));
     b.n = nf; b.dim = dim; b.nd = fs[0] ? fs[0]->nd : 0;
     long long off = 0;
@@ -160,8 +180,8 @@ static int make_slab_batch(int dim, int side, int nf, chmy_field* const* fs, boo
         const chmy_field* f = fs[q];
         CHMY_REQUIRE(f != nullptr && dim < f->nd, "exchange: bad field %d", q);
         const int ov = f->loc[dim] == CHMY_VERTEX ? 1 : 0;
-        SlabEntry& e = b.e[q];
-        e.f   = f->view();
+        SlabEntry<T>& e = b.e[q];
+        e.f   = f->viewT<T>();
         e.idx = send ? (side == 0 ? 1 + ov : (int)f->d[dim] - ov) : (side == 0 ? 0 : (int)f->d[dim] + 1);
         int t = 0, ext[2] = {1, 1};
         for (int a = 0; a < f->nd; ++a)
@@ -173,44 +193,52 @@ static int make_slab_batch(int dim, int side, int nf, chmy_field* const* fs, boo
     return CHMY_OK;
 }
 
-template <bool PACK>
-static int run_slab(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, double* dbuf, cudaStream_t st) {
-    SlabBatch b;
+template <bool PACK, class T>
+static int run_slab(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, T* dbuf, cudaStream_t st) {
+    SlabBatch<T> b;
     for (int q = 0; q < nf; ++q)
-        CHMY_REQUIRE(fs[q] != nullptr && fs[q]->nd >= 2 && fs[q]->nd == fs[0]->nd,
-                     "halo exchange needs fields of equal dimensionality >= 2 on this path");
-    CHMY_TRY(make_slab_batch(dim, side, nf, fs, PACK, &b));
+        CHMY_REQUIRE(fs[q] != nullptr && fs[q]->nd >= 2 && fs[q]->nd == fs[0]->nd && fs[q]->dtype == fs[0]->dtype,
+                     "halo exchange needs fields of equal dimensionality >= 2 and one element type on this path");
+    CHMY_TRY(make_slab_batch<T>(dim, side, nf, fs, PACK, &b));
     int m0 = 1, m1 = 1;
     for (int q = 0; q < nf; ++q) { m0 = b.e[q].e0 > m0 ? b.e[q].e0 : m0; m1 = b.e[q].e1 > m1 ? b.e[q].e1 : m1; }
     const dim3 blk(64, m1 > 1 ? 4 : 1, 1);
     const dim3 grd((m0 + blk.x - 1) / blk.x, (m1 + blk.y - 1) / blk.y, nf);
-    k_slab<PACK><<<grd, blk, 0, st>>>(b, dbuf);
+    k_slab<PACK, T><<<grd, blk, 0, st>>>(b, dbuf);
     ctx->n_launches++;
     CHMY_CUDA(cudaGetLastError());
     return CHMY_OK;
 }
 
-int chmy_pack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, double* dbuf, cudaStream_t st) {
-    return run_slab<true>(ctx, dim, side, nf, fs, dbuf, st);
+int chmy_pack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, void* dbuf, cudaStream_t st) {
+    CHMY_REQUIRE(nf >= 1 && fs && fs[0], "exchange: no fields");
+    if (fs[0]->dtype == CHMY_F32) return run_slab<true, float>(ctx, dim, side, nf, fs, static_cast<float*>(dbuf), st);
+    return run_slab<true, double>(ctx, dim, side, nf, fs, static_cast<double*>(dbuf), st);
 }
-int chmy_unpack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, const double* dbuf,
+int chmy_unpack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, const void* dbuf,
                        cudaStream_t st) {
+    CHMY_REQUIRE(nf >= 1 && fs && fs[0], "exchange: no fields");
     for (int q = 0; q < nf; ++q)
         if (fs[q]) fs[q]->frame_synced = false;
-    return run_slab<false>(ctx, dim, side, nf, fs, const_cast<double*>(dbuf), st);
+    if (fs[0]->dtype == CHMY_F32)
+        return run_slab<false, float>(ctx, dim, side, nf, fs, static_cast<float*>(const_cast<void*>(dbuf)), st);
+    return run_slab<false, double>(ctx, dim, side, nf, fs, static_cast<double*>(const_cast<void*>(dbuf)), st);
 }
 
 // ---------------------------------------------------------------------------------------------- field utilities
+template <class T>
 struct FillF {
-    FV f; double v;
+    FVT<T> f; T v;
     __device__ void operator()(int i, int j, int k) const { fv_st(f, i, j, k, v); }
 };
+template <class T>
 struct CopyF {
-    FV d, s;
+    FVT<T> d, s;
     __device__ void operator()(int i, int j, int k) const { fv_st(d, i, j, k, fv_ld(s, i, j, k)); }
 };
+template <class T>
 struct InclF {
-    FV f; InclDev q;
+    FVT<T> f; InclDevT<T> q;
     __device__ void operator()(int i, int j, int k) const { fv_st(f, i, j, k, incl_eval(q, i, j, k)); }
 };
 
@@ -249,21 +277,32 @@ int chmy_box_from(const chmy_field* f, const int64_t* lo, const int64_t* hi, Box
 
 int chmy_fill_box(chmy_ctx* ctx, chmy_field* f, double v, const Box& b, cudaStream_t st) {
     f->frame_synced = false;
-    return launch_util(ctx, FillF{f->view(), v}, b, st);
+    if (f->dtype == CHMY_F32) return launch_util(ctx, FillF<float>{f->viewT<float>(), (float)v}, b, st);
+    return launch_util(ctx, FillF<double>{f->view(), v}, b, st);
 }
 int chmy_copy_box(chmy_ctx* ctx, chmy_field* d, const chmy_field* s, const Box& b, cudaStream_t st) {
     d->frame_synced = false;
-    return launch_util(ctx, CopyF{d->view(), s->view()}, b, st);
+    if (d->dtype == CHMY_F32) return launch_util(ctx, CopyF<float>{d->viewT<float>(), s->viewT<float>()}, b, st);
+    return launch_util(ctx, CopyF<double>{d->view(), s->view()}, b, st);
 }
 int chmy_incl_box(chmy_ctx* ctx, chmy_field* f, const InclDev& q, const Box& b, cudaStream_t st) {
     f->frame_synced = false;
-    return launch_util(ctx, InclF{f->view(), q}, b, st);
+    return launch_util(ctx, InclF<double>{f->view(), q}, b, st);
+}
+int chmy_incl_box_f32(chmy_ctx* ctx, chmy_field* f, const InclDevT<float>& q, const Box& b, cudaStream_t st) {
+    f->frame_synced = false;
+    return launch_util(ctx, InclF<float>{f->viewT<float>(), q}, b, st);
 }
 
 // ---------------------------------------------------------------------------------------------- max |f|
 // maximum(abs.(interior(f))): exact and order-independent.  |x| is compared through its bit pattern as an unsigned
-// integer (monotone for non-negative doubles; NaN patterns compare above +Inf, so a NaN propagates as in Julia).
-__global__ void __launch_bounds__(256) k_maxabs(const FV f, const Box b, unsigned long long* __restrict__ out) {
+// integer (monotone for non-negative values of either element type; NaN patterns compare above +Inf, so a NaN propagates
+// as in Julia).  Float32 fields reduce their 32-bit patterns; chmy_field_maxabs converts the winner back.
+__device__ __forceinline__ unsigned long long abs_bits(double x) { return (unsigned long long)__double_as_longlong(fabs(x)); }
+__device__ __forceinline__ unsigned long long abs_bits(float x) { return (unsigned long long)__float_as_uint(fabsf(x)); }
+
+template <class T>
+__global__ void __launch_bounds__(256) k_maxabs(const FVT<T> f, const Box b, unsigned long long* __restrict__ out) {
     unsigned long long m = 0ull;
     const long long rows   = (long long)b.n[1] * b.n[2];
     const int       lane   = threadIdx.x & 31;
@@ -273,7 +312,7 @@ __global__ void __launch_bounds__(256) k_maxabs(const FV f, const Box b, unsigne
         const int j = b.lo[1] + (int)(r % b.n[1]);
         const int k = b.lo[2] + (int)(r / b.n[1]);
         for (int i = lane; i < b.n[0]; i += 32) {
-            const unsigned long long v = (unsigned long long)__double_as_longlong(fabs(fv_ld(f, b.lo[0] + i, j, k)));
+            const unsigned long long v = abs_bits(fv_ld(f, b.lo[0] + i, j, k));
             m = v > m ? v : m;
         }
     }
@@ -302,7 +341,8 @@ int chmy_maxabs_box(chmy_ctx* ctx, const chmy_field* f, const Box& b, unsigned l
     const long long cap = (long long)ctx->sm_count * 8;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
-    k_maxabs<<<(unsigned)want, 256, 0, st>>>(f->view(), b, d_out);
+    if (f->dtype == CHMY_F32) k_maxabs<float><<<(unsigned)want, 256, 0, st>>>(f->viewT<float>(), b, d_out);
+    else k_maxabs<double><<<(unsigned)want, 256, 0, st>>>(f->view(), b, d_out);
     ctx->n_launches++;
     CHMY_CUDA(cudaGetLastError());
     return CHMY_OK;

@@ -230,6 +230,7 @@ int chmy_exchange_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int D, const chmy_
     chmy_comm* c = ctx->comm;
     if (!c) { chmy_set_error("halo exchange requested but the architecture has no topology"); return CHMY_ERR_STATE; }
     size_t len[2] = {0, 0};
+    ncclDataType_t ty[2] = {ncclDouble, ncclDouble};      // slabs travel in the fields' element type
     for (int s = 0; s < 2; ++s) {
         if (!side[s] || side[s]->kind != CHMY_BATCH_EXCHANGE) continue;
         if (c->nb[D][s] < 0) { chmy_set_error("no neighbor to communicate (dim %d, side %d)", D + 1, s + 1); return CHMY_ERR_STATE; }  // exchange_halo.jl:19
@@ -238,6 +239,7 @@ int chmy_exchange_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int D, const chmy_
             CHMY_REQUIRE(side[s]->fields[q] != nullptr, "ExchangeBatch: NULL field");
             len[s] += (size_t)chmy_slab_len(side[s]->fields[q], D);
         }
+        if (side[s]->fields[0]->dtype == CHMY_F32) ty[s] = ncclFloat;    // chmy_pack_fields checks that the batch is uniform
         CHMY_TRY(ensure_bufs(c, s, len[s]));
         CHMY_TRY(chmy_pack_fields(ctx, D, s, side[s]->nfields, side[s]->fields, c->sbuf[s], st));
     }
@@ -245,8 +247,8 @@ int chmy_exchange_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int D, const chmy_
     CHMY_NCCL(g_nccl.GroupStart());
     for (int s = 0; s < 2; ++s) {
         if (!len[s]) continue;
-        CHMY_NCCL(g_nccl.Recv(c->rbuf[s], len[s], ncclDouble, c->nb[D][s], c->nccl, st));
-        CHMY_NCCL(g_nccl.Send(c->sbuf[s], len[s], ncclDouble, c->nb[D][s], c->nccl, st));
+        CHMY_NCCL(g_nccl.Recv(c->rbuf[s], len[s], ty[s], c->nb[D][s], c->nccl, st));
+        CHMY_NCCL(g_nccl.Send(c->sbuf[s], len[s], ty[s], c->nb[D][s], c->nccl, st));
     }
     CHMY_NCCL(g_nccl.GroupEnd());
     for (int s = 0; s < 2; ++s)

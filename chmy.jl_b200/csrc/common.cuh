@@ -39,15 +39,21 @@ void chmy_set_error(const char* fmt, ...);
 
 // View of a Field on the device.  p addresses logical index 0 of every active dimension
 // (reference indexing: f[I] = data[I + 2H], src/Fields/field.jl:18); x stride is 1.
-struct FV {
-    double* __restrict__ p;
+// The solvers are Float64 programs (FV); the element-type-generic pieces (fields, bc!, halo slabs, grid operators)
+// are instantiated for Float32 as well, as the reference's tests are (test/common.jl:9).
+template <class T>
+struct FVT {
+    T* __restrict__ p;
     long long sy, sz;   // element strides of dims 2 and 3 (0 when inactive)
 };
+using FV = FVT<double>;
 
-__device__ __forceinline__ double fv_ld(const FV& f, int i, int j, int k) {
+template <class T>
+__device__ __forceinline__ T fv_ld(const FVT<T>& f, int i, int j, int k) {
     return f.p[(long long)i + (long long)j * f.sy + (long long)k * f.sz];
 }
-__device__ __forceinline__ void fv_st(const FV& f, int i, int j, int k, double v) {
+template <class T>
+__device__ __forceinline__ void fv_st(const FVT<T>& f, int i, int j, int k, T v) {
     f.p[(long long)i + (long long)j * f.sy + (long long)k * f.sz] = v;
 }
 
@@ -57,27 +63,31 @@ struct Box {
 };
 
 // FunctionField `init_incl` evaluated in-kernel (function_field.jl:49-59; uniform_axis.jl:18-19).
-struct InclDev {
-    int    active;
-    int    nd;
-    int    loc[3];
-    double origin[3], spacing[3], c0[3];
-    double r2, in, out;
+template <class T>
+struct InclDevT {
+    int active;
+    int nd;
+    int loc[3];
+    T   origin[3], spacing[3], c0[3];
+    T   r2, in, out;
 };
+using InclDev = InclDevT<double>;
 
-__device__ __forceinline__ double coord_dev(double origin, double spacing, int loc, int i) {
-    const double im1 = (double)(i - 1);
-    return loc == CHMY_VERTEX ? fma(im1, spacing, origin) : fma(im1, spacing, fma(0.5, spacing, origin));
+template <class T>
+__device__ __forceinline__ T coord_dev(T origin, T spacing, int loc, int i) {
+    const T im1 = (T)(i - 1);
+    return loc == CHMY_VERTEX ? fma(im1, spacing, origin) : fma(im1, spacing, fma((T)0.5, spacing, origin));
 }
 
-__device__ __forceinline__ double incl_eval(const InclDev& q, int i, int j, int k) {
+template <class T>
+__device__ __forceinline__ T incl_eval(const InclDevT<T>& q, int i, int j, int k) {
     const int I[3] = {i, j, k};
-    double s = 0.0;
+    T s = (T)0.0;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         if (d < q.nd) {
-            const double c  = coord_dev(q.origin[d], q.spacing[d], q.loc[d], I[d]) - q.c0[d];
-            const double c2 = c * c;
+            const T c  = coord_dev(q.origin[d], q.spacing[d], q.loc[d], I[d]) - q.c0[d];
+            const T c2 = c * c;
             s = (d == 0) ? c2 : s + c2;
         }
     }
@@ -98,6 +108,8 @@ struct chmy_field {
     chmy_ctx* ctx;
     int       nd;
     int       layout;
+    int       dtype;       // chmy_dtype; strides, lead and offsets below count ELEMENTS of that type
+    int       esize;       // 8 | 4
     int       loc[3];
     long long d[3];        // logical dims (1 for inactive)
     long long sd[3];       // logical storage dims d+4 (1 for inactive)
@@ -105,7 +117,8 @@ struct chmy_field {
     long long lead;        // elements between the allocation base and storage element (-1,-1,-1)
     double*   alloc;       // cudaMalloc'ed base
     size_t    bytes;
-    double*   p0;          // address of logical (0,0,0) over active dims
+    double*   p0;          // address of logical (0,0,0) over active dims (a float* in disguise for CHMY_F32 fields:
+                           // only viewT<float>() / at_bytes() may touch those)
     // ping-pong shadow of the fused stress+velocity sweep (ops_fused.cu): lazily allocated twin of `alloc`; the two
     // are swapped after every fused launch.  frame_synced: the cells outside the ops' index range [0, n+1]^N hold the
     // same values in both buffers (cleared by everything that may write such cells: fill/copy/set!/bc!/halo unpack).
@@ -114,9 +127,14 @@ struct chmy_field {
     double*   alt_p0() const { return alt_alloc + (p0 - alloc); }
     void      swap_buffers() { double* a = alloc; const ptrdiff_t o = p0 - alloc; alloc = alt_alloc; alt_alloc = a; p0 = alloc + o; }
 
-    FV view() const { return FV{p0, nd > 1 ? stride[1] : 0, nd > 2 ? stride[2] : 0}; }
-    double* at(long long i, long long j, long long k) const {
+    FV view() const { return FV{p0, nd > 1 ? stride[1] : 0, nd > 2 ? stride[2] : 0}; }      // Float64 fields only
+    template <class T>
+    FVT<T> viewT() const { return FVT<T>{reinterpret_cast<T*>(p0), nd > 1 ? stride[1] : 0, nd > 2 ? stride[2] : 0}; }
+    double* at(long long i, long long j, long long k) const {                                // Float64 fields only
         return p0 + i + (nd > 1 ? j * stride[1] : 0) + (nd > 2 ? k * stride[2] : 0);
+    }
+    char* at_bytes(long long i, long long j, long long k) const {
+        return reinterpret_cast<char*>(p0) + (size_t)esize * (size_t)(i + (nd > 1 ? j * stride[1] : 0) + (nd > 2 ? k * stride[2] : 0));
     }
 };
 
@@ -174,7 +192,8 @@ int chmy_run_fused2d(chmy_ctx* ctx, int kind, const chmy_launch_desc* dp, const 
 int chmy_frame_copy2(chmy_ctx* ctx, const chmy_grid_desc* g, int n, chmy_field* const* fs, double* const* src,
                      double* const* dst, cudaStream_t st);
 // bc.cu (halo slabs)
-int chmy_pack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, double* dbuf, cudaStream_t st);
-int chmy_unpack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, const double* dbuf,
+// dbuf holds the slabs in the fields' element type (all fields of one call share it)
+int chmy_pack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, void* dbuf, cudaStream_t st);
+int chmy_unpack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, const void* dbuf,
                        cudaStream_t st);
 long long chmy_slab_len(const chmy_field* f, int dim);

@@ -207,6 +207,8 @@ static int expect_fields(const chmy_launch_desc* d, int nf, int ns, int allow_nu
         }
         CHMY_REQUIRE(d->fields[i]->nd == d->grid.ndims, "op %d: field %d has %d dims, grid has %d", d->op, i,
                      d->fields[i]->nd, d->grid.ndims);
+        // the example solvers are Float64 programs (their Float64 literals would promote Float32 fields in the reference too)
+        CHMY_REQUIRE(d->fields[i]->dtype == CHMY_F64, "op %d: field %d is not Float64 (the solver ops are Float64-only)", d->op, i);
     }
     return CHMY_OK;
 }
@@ -269,6 +271,7 @@ static int validate_operator(const chmy_launch_desc* d) {
     for (int i = 0; i < nf; ++i) {
         CHMY_REQUIRE(d->fields[i] != nullptr, "operator %d: field %d is NULL", op, i);
         CHMY_REQUIRE(d->fields[i]->nd == nd, "operator %d: field %d has %d dims, grid has %d", op, i, d->fields[i]->nd, nd);
+        CHMY_REQUIRE(d->fields[i]->dtype == d->fields[0]->dtype, "operator %d: the fields must share one element type", op);
         CHMY_TRY(expect_size(d, i));
     }
     chmy_field* const* F = d->fields;
@@ -300,33 +303,41 @@ static int validate_operator(const chmy_launch_desc* d) {
     return CHMY_OK;
 }
 
+template <class T>
 struct OperatorF {
-    OprArgs g;
+    OprArgsT<T> g;
     __device__ void operator()(int i, int j, int k) const { opr_apply(g, i, j, k); }
 };
 
-static OprField opr_view(const chmy_field* f) {
-    OprField v;
-    v.p = f->p0; v.sy = f->nd > 1 ? f->stride[1] : 0; v.sz = f->nd > 2 ? f->stride[2] : 0;
+template <class T>
+static OprFieldT<T> opr_view(const chmy_field* f) {
+    OprFieldT<T> v;
+    v.p = reinterpret_cast<T*>(f->p0); v.sy = f->nd > 1 ? f->stride[1] : 0; v.sz = f->nd > 2 ? f->stride[2] : 0;
     for (int a = 0; a < 3; ++a) v.loc[a] = f->loc[a];
     return v;
 }
 
-static int run_operator(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st) {
+template <class T>
+static int run_operator_t(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st) {
     const int nd = d->grid.ndims, op = d->oper;
     chmy_field* const* F = d->fields;
-    OperatorF f;
+    OperatorF<T> f;
     memset(&f, 0, sizeof(f));
     f.g.oper = op; f.g.dim = d->oper_dim; f.g.nd = nd;
-    for (int a = 0; a < 3; ++a) f.g.id[a] = a < nd ? d->grid.inv_spacing[a] : 0.0;
+    for (int a = 0; a < 3; ++a) f.g.id[a] = a < nd ? (T)d->grid.inv_spacing[a] : (T)0.0;
     const int nout = (op == CHMY_OPER_GRAD || op == CHMY_OPER_KGRAD) ? nd : 1;
     f.g.ndst = nout;
-    for (int o = 0; o < nout; ++o) f.g.dst[o] = opr_view(F[o]);
+    for (int o = 0; o < nout; ++o) f.g.dst[o] = opr_view<T>(F[o]);
     const bool vec = op == CHMY_OPER_DIVG || op == CHMY_OPER_VMAG;
-    for (int c = 0; c < (vec ? nd : 1); ++c) f.g.a[c] = opr_view(F[nout + c]);
-    if (op == CHMY_OPER_DKD || op == CHMY_OPER_DIVG_GRAD || op == CHMY_OPER_KGRAD) f.g.k = opr_view(F[nout + 1]);
+    for (int c = 0; c < (vec ? nd : 1); ++c) f.g.a[c] = opr_view<T>(F[nout + c]);
+    if (op == CHMY_OPER_DKD || op == CHMY_OPER_DIVG_GRAD || op == CHMY_OPER_KGRAD) f.g.k = opr_view<T>(F[nout + 1]);
     for (int o = 0; o < nout; ++o) F[o]->frame_synced = false;   // not a ping-pong op: a shadow copy of dst goes stale
     return launch_box(ctx, f, box, st);
+}
+
+static int run_operator(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st) {
+    if (d->fields[0]->dtype == CHMY_F32) return run_operator_t<float>(ctx, d, box, st);
+    return run_operator_t<double>(ctx, d, box, st);
 }
 
 int chmy_validate_op(const chmy_launch_desc* d) {

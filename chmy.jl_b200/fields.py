@@ -20,18 +20,22 @@ class Field(AbstractField):
     """Field(backend|arch, grid, loc; halo=1) -- field.jl:56-74.  Storage is allocated (zero-filled) by
     chmy_field_create; logical indexing follows field.jl:18-22."""
 
-    def __init__(self, arch, grid: StructuredGrid, loc=None, *, halo: int = 1, layout: int = L.LAYOUT_PITCHED):
+    def __init__(self, arch, grid: StructuredGrid, loc=None, dtype=None, *, halo: int = 1, layout: int = L.LAYOUT_PITCHED):
         if halo != 1:
             raise NotImplementedError("this path implements the default halo=1 of the reference")
         loc = Center() if loc is None else loc
         self.arch = arch
         self.grid = grid
+        # Field(backend, grid, loc, type=eltype(grid)) -- field.jl:56-57
+        self.dtype = np.dtype(grid.eltype() if dtype is None else dtype)
+        if self.dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise TypeError("eltype(field) must be Float64 or Float32 on this path")
         self.loc = expand_loc(grid.ndims(), loc)
         self.dims = grid.size(self.loc)
         nd = len(self.dims)
         h = C.c_void_p()
-        L.check(L.lib().chmy_field_create(arch.ctx, nd, L.i64x3(self.dims, 1), L.i32x3([l.code for l in self.loc]),
-                                          layout, C.byref(h)))
+        L.check(L.lib().chmy_field_create_typed(arch.ctx, nd, L.i64x3(self.dims, 1), L.i32x3([l.code for l in self.loc]),
+                                                layout, L.F32 if self.dtype == np.float32 else L.F64, C.byref(h)))
         self._h = h
 
     # ------------------------------------------------------------------ handles
@@ -72,16 +76,16 @@ class Field(AbstractField):
     def to_host(self, lo, hi, out: np.ndarray | None = None) -> np.ndarray:
         shape = tuple(h - l + 1 for l, h in zip(lo, hi))
         if out is None:
-            out = np.empty(shape, dtype=np.float64, order="F")
-        elif out.shape != shape or out.dtype != np.float64 or not out.flags.f_contiguous:
-            raise ValueError(f"to_host(out=...): need a Fortran-contiguous float64 array of shape {shape}")
+            out = np.empty(shape, dtype=self.dtype, order="F")
+        elif out.shape != shape or out.dtype != self.dtype or not out.flags.f_contiguous:
+            raise ValueError(f"to_host(out=...): need a Fortran-contiguous {self.dtype} array of shape {shape}")
         L.check(L.lib().chmy_field_copy_to_host(self.arch.ctx, self.handle, out.ctypes.data_as(C.c_void_p),
                                                 L.i64x3(lo), L.i64x3(hi)))
         return out
 
     def from_host(self, arr: np.ndarray, lo, hi):
         shape = tuple(h - l + 1 for l, h in zip(lo, hi))
-        a = np.asfortranarray(np.broadcast_to(np.asarray(arr, dtype=np.float64), shape))
+        a = np.asfortranarray(np.broadcast_to(np.asarray(arr, dtype=self.dtype), shape))
         L.check(L.lib().chmy_field_copy_from_host(self.arch.ctx, self.handle, a.ctypes.data_as(C.c_void_p),
                                                   L.i64x3(lo), L.i64x3(hi)))
 
@@ -123,17 +127,18 @@ class _PinnedOwner:
         self.ptr = None
 
 
-def pinned_array(arch, shape) -> np.ndarray:
-    """Fortran-ordered Float64 host array in page-locked memory (chmy_host_alloc): the fast host side of
+def pinned_array(arch, shape, dtype=np.float64) -> np.ndarray:
+    """Fortran-ordered host array in page-locked memory (chmy_host_alloc): the fast host side of
     set!(f, A) / Array(interior(f)).  Freed when the last numpy view of it is garbage-collected."""
     shape = tuple(int(s) for s in shape)
+    dtype = np.dtype(dtype)
     n = int(np.prod(shape, dtype=np.int64))
     p = C.c_void_p()
-    L.check(L.lib().chmy_host_alloc(arch.ctx, n * 8, C.byref(p)))
+    L.check(L.lib().chmy_host_alloc(arch.ctx, n * dtype.itemsize, C.byref(p)))
     owner = _PinnedOwner(arch, p)
-    buf = (C.c_double * n).from_address(p.value)
+    buf = (C.c_byte * (n * dtype.itemsize)).from_address(p.value)
     buf._chmy_owner = owner                    # the ctypes object is the numpy array's base: ties the lifetimes
-    return np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape, order="F")
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape, order="F")
 
 
 def parent(f: Field) -> np.ndarray:
@@ -191,7 +196,7 @@ def set_(f, *args, discrete: bool = False, parameters=()):
         elif np.isscalar(a):                                                 # field.jl:87
             L.check(L.lib().chmy_field_fill(f.arch.ctx, f.handle, float(a), L.i64x3(lo), L.i64x3(hi)))
         else:                                                                # field.jl:98
-            a = np.asarray(a, dtype=np.float64)
+            a = np.asarray(a, dtype=f.dtype)
             if a.shape != tuple(f.dims):
                 raise ValueError(f"set!(f, A): A has shape {a.shape}, interior is {f.dims}")
             f.from_host(a, lo, hi)
@@ -209,7 +214,7 @@ def set_(f, *args, discrete: bool = False, parameters=()):
     cs = [coords(grid, f.loc, d + 1) for d in range(grid.ndims())]
     mesh = np.meshgrid(*cs, indexing="ij")
     params = tuple(parameters.values()) if isinstance(parameters, dict) else tuple(parameters)
-    f.from_host(np.asarray(fun(*mesh, *params), dtype=np.float64), lo, hi)
+    f.from_host(np.asarray(fun(*mesh, *params), dtype=f.dtype), lo, hi)
 
 
 class FieldTuple:

@@ -8,7 +8,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib as L
-from .utils import fma
+from .utils import fma_t
 
 
 class Location:
@@ -69,14 +69,18 @@ def expand_loc(nd: int, loc):
 
 
 class UniformAxis:
-    """uniform_axis.jl:1-12."""
+    """UniformAxis{T} (uniform_axis.jl:1-12).  Every number is a numpy scalar of the element type T (Float64 by default,
+    Float32 as in the reference's tests) so that the host arithmetic rounds exactly where Julia's does."""
 
-    def __init__(self, origin: float, extent: float, length: int):
-        self.origin = float(origin)
-        self.extent = float(extent)
+    def __init__(self, origin: float, extent: float, length: int, dtype=np.float64):
+        T = self.T = np.dtype(dtype).type
+        if T not in (np.float64, np.float32):
+            raise TypeError("eltype(grid) must be Float64 or Float32 on this path")
+        self.origin = T(origin)
+        self.extent = T(extent)
         self.length = int(length)
-        self.spacing = self.extent / self.length          # :8
-        self.inv_spacing = 1.0 / self.spacing             # :9  inv(spacing)
+        self.spacing = self.extent / T(self.length)       # :8
+        self.inv_spacing = T(1.0) / self.spacing          # :9  inv(spacing)
 
     def nvertices(self):
         return self.length + 1
@@ -85,16 +89,16 @@ class UniformAxis:
         return self.length + 1 if loc is _V else self.length
 
     def vertex(self, i: int) -> float:                    # :18
-        return fma(float(i - 1), self.spacing, self.origin)
+        return self.T(fma_t(self.T(i - 1), self.spacing, self.origin, self.T))
 
     def center(self, i: int) -> float:                    # :19
-        return fma(float(i - 1), self.spacing, fma(0.5, self.spacing, self.origin))
+        return self.T(fma_t(self.T(i - 1), self.spacing, fma_t(self.T(0.5), self.spacing, self.origin, self.T), self.T))
 
     def coord(self, loc, i: int) -> float:
         return self.vertex(i) if loc is _V else self.center(i)
 
     def origin_at(self, loc):                             # :21-22
-        return self.origin if loc is _V else fma(0.5, self.spacing, self.origin)
+        return self.origin if loc is _V else self.T(fma_t(self.T(0.5), self.spacing, self.origin, self.T))
 
     def extent_at(self, loc):                             # :24-25
         return self.extent if loc is _V else self.extent - self.spacing
@@ -106,6 +110,12 @@ class StructuredGrid:
     def __init__(self, axes, connectivity):
         self.axes = tuple(axes)
         self.connectivity_ = tuple(tuple(c) for c in connectivity)
+        if len({ax.T for ax in self.axes}) != 1:
+            raise TypeError("all axes of a grid share one element type")
+
+    def eltype(self):
+        """eltype(grid) (structured_grid.jl:6): numpy float64 | float32."""
+        return self.axes[0].T
 
     # --- reference accessors
     def ndims(self):
@@ -121,22 +131,25 @@ class StructuredGrid:
         g.ndims = self.ndims()
         for d, ax in enumerate(self.axes):
             g.n[d] = ax.length
-            g.origin[d], g.extent[d], g.spacing[d], g.inv_spacing[d] = ax.origin, ax.extent, ax.spacing, ax.inv_spacing
+            # Float32 numbers widen exactly; the library rounds them back to the fields' element type
+            g.origin[d], g.extent[d], g.spacing[d], g.inv_spacing[d] = (float(ax.origin), float(ax.extent), float(ax.spacing),
+                                                                          float(ax.inv_spacing))
             for s in range(2):
                 g.connectivity[d][s] = self.connectivity_[d][s].code
         return g
 
 
-def UniformGrid(arch, *, origin, extent, dims, topology=None) -> StructuredGrid:
+def UniformGrid(arch, *, origin, extent, dims, topology=None, dtype=np.float64) -> StructuredGrid:
     """UniformGrid(arch; origin, extent, dims, topology) -- structured_grid.jl:27-39.  On a distributed
-    architecture `dims` is the GLOBAL size and the local sub-grid is returned (distributed_grid.jl:19-36)."""
+    architecture `dims` is the GLOBAL size and the local sub-grid is returned (distributed_grid.jl:19-36).
+    `dtype` stands for the type of the origin/extent numbers the Julia caller passes (`T(-5)`, test_grid_operators.jl:11)."""
     from .architectures import DistributedArchitecture
     N = len(dims)
     if not (len(origin) == len(extent) == N):
         raise ValueError("origin, extent and dims must have the same length")
     if topology is None:
         topology = tuple((Bounded(), Bounded()) for _ in range(N))
-    axes = [UniformAxis(float(o), float(e), int(n)) for o, e, n in zip(origin, extent, dims)]
+    axes = [UniformAxis(o, e, int(n), dtype) for o, e, n in zip(origin, extent, dims)]
     if not isinstance(arch, DistributedArchitecture):
         return StructuredGrid(axes, topology)
     topo = arch.topology
@@ -144,7 +157,7 @@ def UniformGrid(arch, *, origin, extent, dims, topology=None) -> StructuredGrid:
     offsets = [c * l for c, l in zip(topo.cart_coords, local_dims)]                    # :26
     local_axes = []
     for ax, off, ln in zip(axes, offsets, local_dims):                                 # subaxis :1-5
-        local_axes.append(UniformAxis(ax.vertex(off + 1), ax.spacing * ln, ln))
+        local_axes.append(UniformAxis(ax.vertex(off + 1), ax.spacing * ax.T(ln), ln, ax.T))
     conn = tuple(tuple(Connected() if topo.has_neighbor(D + 1, S + 1) else topology[D][S] for S in range(2))
                  for D in range(N))                                                    # overwrite_connectivity :12-17
     return StructuredGrid(local_axes, conn)
@@ -177,7 +190,7 @@ def coord(grid, loc, dim: int, i: int) -> float:
 def coords(grid, loc, dim: int) -> np.ndarray:
     loc = expand_loc(grid.ndims(), loc)
     ax = grid.axes[dim - 1]
-    return np.array([ax.coord(loc[dim - 1], i) for i in range(1, ax.size(loc[dim - 1]) + 1)])
+    return np.array([ax.coord(loc[dim - 1], i) for i in range(1, ax.size(loc[dim - 1]) + 1)], dtype=ax.T)
 
 
 def centers(grid, dim=None):

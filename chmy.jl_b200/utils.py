@@ -23,6 +23,22 @@ def fma(a: float, b: float, c: float) -> float:
     return float(Fraction(a) * Fraction(b) + Fraction(c))
 
 
+def fma_t(a, b, c, dtype):
+    """muladd in the element type `dtype` (numpy float64 | float32): the exact a*b+c rounded ONCE to that type."""
+    import numpy as np
+    dtype = np.dtype(dtype)
+    x = Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c))
+    d = float(x)                                   # nearest binary64
+    if dtype == np.float64:
+        return np.float64(d)
+    f = np.float32(d)
+    if Fraction(d) == x:                           # exact in binary64: one (ties-to-even) rounding to binary32
+        return f
+    # d was itself rounded: pick the binary32 neighbour nearest to the exact value (no double rounding)
+    cands = (np.nextafter(f, np.float32(-np.inf)), f, np.nextafter(f, np.float32(np.inf)))
+    return min(cands, key=lambda t: abs(Fraction(float(t)) - x))
+
+
 def remove_dim(D: int, A):
     """remove_dim(Dim(D), A) (src/utils.jl:27-32); D is 1-based."""
     return tuple(a for i, a in enumerate(A, start=1) if i != D)

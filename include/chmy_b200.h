@@ -13,7 +13,11 @@
  *   - one chmy_ctx per GPU / rank process, used by one host thread at a time.
  *   - logical indices are the reference's: 1-based, I in 1..d is the interior, 0 and d+1 the halo, -1 and d+2
  *     zero padding (src/Fields/field.jl:18-22,56-62).  Boxes are inclusive [lo, hi] in logical indices.
- *   - Float64 only on this path (the reference also instantiates Float32: "next" row in DESIGN.md).
+ *   - the solver ops (CHMY_OP_COMPUTE_Q .. CHMY_OP_UPDATE_THERMAL) are Float64 programs, like the reference's example
+ *     drivers.  Fields, set!/copies, maxabs, bc!, halo exchange and the grid operators (CHMY_OP_OPERATOR) exist for
+ *     Float32 as well (chmy_field_create_typed), as the reference's tests instantiate them (test/common.jl:9).  Host
+ *     buffers of the copy / halo entry points hold elements of the field's type; scalar arguments stay `double` (a
+ *     Float32 value converts exactly) and are rounded to the field's type where the reference's would have it.
  *   - all work is stream-ordered on the context's streams; results are visible to the host after a blocking
  *     launch (CHMY_LAUNCH_BLOCKING, the reference's semantics, KernelLaunch.jl:117), any copy_to_host /
  *     maxabs call, or chmy_synchronize().
@@ -57,6 +61,7 @@ typedef enum { CHMY_BATCH_EMPTY = 0, CHMY_BATCH_FIELD = 1, CHMY_BATCH_EXCHANGE =
  * aligned (vector loads, TMA-legal strides).  DENSE: exactly the reference's dense column-major
  * array of dims+4 (field.jl:58-59).  Logical contents are identical; kernels accept both. */
 typedef enum { CHMY_LAYOUT_PITCHED = 0, CHMY_LAYOUT_DENSE = 1 } chmy_layout;
+typedef enum { CHMY_F64 = 0, CHMY_F32 = 1 } chmy_dtype;                /* eltype(field): TEST_TYPES, test/common.jl:9 */
 
 /* The ops `launch` can run: the @kernel functions of the named example solvers. */
 typedef enum {
@@ -162,6 +167,8 @@ typedef struct {
     void*   origin_ptr;                /* device address of logical index (1,1,1)                          */
     void*   base_ptr;                  /* device address of storage element (-1,-1,-1)                     */
     size_t  bytes;                     /* allocation size                                                  */
+    int32_t dtype;                     /* chmy_dtype; strides count elements of this type (ABI v3)         */
+    int32_t _pad;
 } chmy_field_info;
 
 /* ---- library ------------------------------------------------------------------------------------------ */
@@ -199,13 +206,15 @@ int chmy_barrier(chmy_ctx* ctx);                                /* MPI.Barrier(c
 /* ---- Fields: Field(backend, grid, loc; halo=1) src/Fields/field.jl:56-62 ------------------------------ */
 int chmy_field_create(chmy_ctx* ctx, int ndims, const int64_t* dims, const int32_t* loc, int layout,
                       chmy_field** out);                              /* zero-initialised                  */
+int chmy_field_create_typed(chmy_ctx* ctx, int ndims, const int64_t* dims, const int32_t* loc, int layout, int dtype,
+                            chmy_field** out);                        /* Field(backend, grid, loc, T) field.jl:56 */
 int chmy_field_destroy(chmy_field* f);
 int chmy_field_get_info(const chmy_field* f, chmy_field_info* out);
 int chmy_field_fill(chmy_ctx* ctx, chmy_field* f, double value, const int64_t* lo, const int64_t* hi);
                        /* fill!(parent(f),v): lo=-1,hi=d+2 ; set!(f,v) field.jl:87: lo=1,hi=d               */
-int chmy_field_copy_from_host(chmy_ctx* ctx, chmy_field* f, const double* src, const int64_t* lo, const int64_t* hi);
-                       /* set!(f, A) field.jl:98: dense column-major host box                               */
-int chmy_field_copy_to_host(chmy_ctx* ctx, const chmy_field* f, double* dst, const int64_t* lo, const int64_t* hi);
+int chmy_field_copy_from_host(chmy_ctx* ctx, chmy_field* f, const void* src, const int64_t* lo, const int64_t* hi);
+                       /* set!(f, A) field.jl:98: dense column-major host box of eltype(f)                  */
+int chmy_field_copy_to_host(chmy_ctx* ctx, const chmy_field* f, void* dst, const int64_t* lo, const int64_t* hi);
                        /* Array(interior(f; with_halo)) field.jl:33-37                                      */
 int chmy_field_copy(chmy_ctx* ctx, chmy_field* dst, const chmy_field* src, const int64_t* lo, const int64_t* hi);
                        /* set!(f, other) field.jl:109-119                                                   */
@@ -265,8 +274,8 @@ int chmy_set_fused2d_tuning(int rows_per_chunk, int unroll);
 
 /* halo slab pack/unpack exposed for bit-exact parity tests of src/Distributed/communication_views.jl:1-34 */
 int chmy_halo_slab_len(const chmy_field* f, int dim, int64_t* len);
-int chmy_halo_pack(chmy_ctx* ctx, const chmy_field* f, int dim, int side, double* host_buf);
-int chmy_halo_unpack(chmy_ctx* ctx, chmy_field* f, int dim, int side, const double* host_buf);
+int chmy_halo_pack(chmy_ctx* ctx, const chmy_field* f, int dim, int side, void* host_buf);      /* elements of the field's type */
+int chmy_halo_unpack(chmy_ctx* ctx, chmy_field* f, int dim, int side, const void* host_buf);
 
 #ifdef __cplusplus
 }

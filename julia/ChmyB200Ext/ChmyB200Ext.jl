@@ -100,23 +100,25 @@ ctx(arch) = get_device(arch).ctx
 
 # ------------------------------------------------------------------------------------------------ fields
 """Device storage handle standing where the `CuArray` stands in `Field{T,N,L,H,A}` (src/Fields/field.jl:6-11)."""
-mutable struct B200Array{N} <: AbstractArray{Float64,N}
+mutable struct B200Array{T<:Union{Float64,Float32},N} <: AbstractArray{T,N}
     handle::Ptr{Cvoid}
     dims::NTuple{N,Int}               # padded dims (dims .+ 4)
     arch
 end
 Base.size(a::B200Array) = a.dims
+dtype_code(::Type{Float64}) = Cint(0)                                  # chmy_dtype
+dtype_code(::Type{Float32}) = Cint(1)
 
-function Fields.Field(arch::SingleDeviceArchitecture{B200Backend}, grid::StructuredGrid{N}, loc, ::Type{Float64}=Float64;
-                      halo=1) where {N}                                # field.jl:56-74
+function Fields.Field(arch::SingleDeviceArchitecture{B200Backend}, grid::StructuredGrid{N}, loc, ::Type{T}=eltype(grid);
+                      halo=1) where {N,T<:Union{Float64,Float32}}      # field.jl:56-74
     halo == 1 || error("the B200 path implements halo = 1")
     loc  = Fields.expand_loc(Val(N), loc)
     dims = size(grid, loc)
     ref  = Ref{Ptr{Cvoid}}()
-    check(ccall((:chmy_field_create, libchmy), Cint,
-                (Ptr{Cvoid}, Cint, Ref{NTuple{3,Int64}}, Ref{NTuple{3,Int32}}, Cint, Ref{Ptr{Cvoid}}),
-                ctx(arch), N, pad3(dims, 1), pad3(map(l -> Int32(l isa Vertex), loc), 0), 0, ref))
-    data = B200Array{N}(ref[], dims .+ 4, arch)
+    check(ccall((:chmy_field_create_typed, libchmy), Cint,
+                (Ptr{Cvoid}, Cint, Ref{NTuple{3,Int64}}, Ref{NTuple{3,Int32}}, Cint, Cint, Ref{Ptr{Cvoid}}),
+                ctx(arch), N, pad3(dims, 1), pad3(map(l -> Int32(l isa Vertex), loc), 0), 0, dtype_code(T), ref))
+    data = B200Array{T,N}(ref[], dims .+ 4, arch)
     finalizer(a -> ccall((:chmy_field_destroy, libchmy), Cint, (Ptr{Cvoid},), a.handle), data)
     return Field{typeof(loc),1}(data, dims)
 end
@@ -125,24 +127,24 @@ pad3(t::NTuple{N}, fill) where {N} = ntuple(i -> i <= N ? Int64(t[i]) : Int64(fi
 handle(f::Field) = parent(f).handle
 
 # Array(interior(f)) / set!(f, A) / maximum(abs, interior(f)):  sub-box copies and the fused reduction
-function Base.Array(f::Field{Float64,N,L,H,<:B200Array}; with_halo=false) where {N,L,H}
+function Base.Array(f::Field{T,N,L,H,<:B200Array}; with_halo=false) where {T,N,L,H}     # host buffers hold eltype(f)
     lo = ntuple(_ -> with_halo ? 0 : 1, N); hi = size(f) .+ (with_halo ? 1 : 0)
-    out = Array{Float64,N}(undef, (hi .- lo .+ 1)...)
-    check(ccall((:chmy_field_copy_to_host, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ref{NTuple{3,Int64}}, Ref{NTuple{3,Int64}}),
+    out = Array{T,N}(undef, (hi .- lo .+ 1)...)
+    check(ccall((:chmy_field_copy_to_host, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{NTuple{3,Int64}}, Ref{NTuple{3,Int64}}),
                 ctx(parent(f).arch), handle(f), out, pad3(lo, 0), pad3(hi, 0)))
     return out
 end
-function Fields.set!(f::Field{Float64,N,L,H,<:B200Array}, A::AbstractArray) where {N,L,H}     # field.jl:98
-    host = Array{Float64,N}(A)
-    check(ccall((:chmy_field_copy_from_host, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ref{NTuple{3,Int64}}, Ref{NTuple{3,Int64}}),
+function Fields.set!(f::Field{T,N,L,H,<:B200Array}, A::AbstractArray) where {T,N,L,H}     # field.jl:98
+    host = Array{T,N}(A)
+    check(ccall((:chmy_field_copy_from_host, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{NTuple{3,Int64}}, Ref{NTuple{3,Int64}}),
                 ctx(parent(f).arch), handle(f), host, pad3(ntuple(_ -> 1, N), 0), pad3(size(f), 0)))
     return
 end
-function maxabs(f::Field{Float64,N,L,H,<:B200Array}) where {N,L,H}                             # drivers: maximum(abs.(interior(f)))
-    out = Ref{Float64}()
+function maxabs(f::Field{T,N,L,H,<:B200Array}) where {T,N,L,H}                                 # drivers: maximum(abs.(interior(f)))
+    out = Ref{Float64}()                                                                           # exact widening for Float32 fields
     check(ccall((:chmy_field_maxabs, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{NTuple{3,Int64}}, Ref{NTuple{3,Int64}}, Ref{Float64}),
                 ctx(parent(f).arch), handle(f), pad3(ntuple(_ -> 1, N), 0), pad3(size(f), 0), out))
-    return out[]
+    return T(out[])
 end
 
 # ------------------------------------------------------------------------------------------------ descriptors
@@ -173,11 +175,11 @@ function boundary_value_field(arch, grid::StructuredGrid{N}, f::Field, c::FirstO
                                                          (flip(loc_f), S == 1 ? 0 : d + 1)
         tgrid = UniformGrid(arch; origin=remove_dim(dim, origin(grid, Vertex())), extent=remove_dim(dim, extent(grid, Vertex())),
                             dims=remove_dim(dim, size(grid, Center())))
-        vf   = Field(arch, tgrid, Vertex())
+        vf   = Field(arch, tgrid, Vertex(), eltype(f))
         ext  = remove_dim(dim, size(grid, Vertex()) .+ 2)                  # face points 0..n_t+2 (batch.jl:180-181)
         vals = [c.value(grid, loc, dim, insert_dim(dim, Tuple(J) .- 1, idx)...) for J in CartesianIndices(ext)]
-        check(ccall((:chmy_field_copy_from_host, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ref{NTuple{3,Int64}}, Ref{NTuple{3,Int64}}),
-                    ctx(arch), handle(vf), Float64.(vals), pad3(ntuple(_ -> 0, N - 1), 0), pad3(ext .- 1, 0)))
+        check(ccall((:chmy_field_copy_from_host, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{NTuple{3,Int64}}, Ref{NTuple{3,Int64}}),
+                    ctx(arch), handle(vf), eltype(f).(vals), pad3(ntuple(_ -> 0, N - 1), 0), pad3(ext .- 1, 0)))
         vf
     end
 end

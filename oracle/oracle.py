@@ -200,11 +200,13 @@ class Grid:
         return self.coord(dim, loc, 1) if loc == CENTER else self.c.origin[dim]
 
     def extent_at(self, dim, loc):
-        return self.c.extent[dim] if loc == VERTEX else self.c.extent[dim] - self.c.spacing[dim]
+        T = self.dtype.type                   # extent(ax, ::Center) = extent - spacing in eltype(ax) (uniform_axis.jl:25)
+        return float(self.c.extent[dim]) if loc == VERTEX else float(T(self.c.extent[dim]) - T(self.c.spacing[dim]))
 
     def bounds(self, dim, loc):
+        T = self.dtype.type
         o = self.origin_at(dim, loc)
-        return (o, o + self.extent_at(dim, loc))
+        return (o, float(T(o) + T(self.extent_at(dim, loc))))
 
 
 class Field:

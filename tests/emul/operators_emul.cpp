@@ -11,4 +11,12 @@ extern "C" int operators_emul_run(const OprArgs* g, const int* lo, const int* hi
     return 0;
 }
 
-extern "C" int operators_emul_sizeof_args(void) { return (int)sizeof(OprArgs); }
+// the Float32 instantiation (fields, inv_spacing and every operation in binary32)
+extern "C" int operators_emul_run_f32(const OprArgsT<float>* g, const int* lo, const int* hi) {
+    for (int k = lo[2]; k <= hi[2]; ++k)
+        for (int j = lo[1]; j <= hi[1]; ++j)
+            for (int i = lo[0]; i <= hi[0]; ++i) opr_apply(*g, i, j, k);
+    return 0;
+}
+
+extern "C" int operators_emul_sizeof_args(int f32) { return f32 ? (int)sizeof(OprArgsT<float>) : (int)sizeof(OprArgs); }

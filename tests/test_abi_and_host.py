@@ -160,3 +160,42 @@ def test_batch_normalisation_matches_oracle(oracle):
     V = ch.FieldTuple(x=vx, y=vy, z=vz)
     bs3 = batch(g, exchange=V)
     assert [f.name for f in bs3[0][1].fields] == ["vx"] and [f.name for f in bs3[1][1].fields] == ["vy"]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_grid_numbers_match_oracle_in_both_element_types(oracle, dtype):
+    """UniformAxis{T} on the host mirror rounds exactly where the oracle's (and Julia's) arithmetic does: spacing,
+    inv_spacing, vertex/center coordinates (muladd -> one rounding in T), sub-axis arithmetic."""
+    import chmy_b200 as ch
+    g = ch.UniformGrid(_FakeArch(), origin=(-5.0, -0.3, 1.0), extent=(10.0, 9.1, 0.7), dims=(12, 10, 7), dtype=dtype)
+    og = oracle.Grid((-5.0, -0.3, 1.0), (10.0, 9.1, 0.7), (12, 10, 7), dtype=dtype)
+    assert g.eltype() == dtype
+    for d in range(3):
+        ax = g.axes[d]
+        assert isinstance(ax.spacing, dtype) and float(ax.spacing) == og.spacing[d] and float(ax.inv_spacing) == og.inv_spacing[d]
+        for loc, lc in ((ch.Vertex(), 1), (ch.Center(), 0)):
+            for i in range(-1, 16):
+                assert float(ax.coord(loc, i)) == og.coord(d, lc, i), (d, lc, i)
+            assert float(ax.origin_at(loc)) == og.origin_at(d, lc) and float(ax.extent_at(loc)) == og.extent_at(d, lc)
+    desc = g.desc()
+    assert desc.spacing[1] == og.spacing[1] and desc.inv_spacing[2] == og.inv_spacing[2]
+
+
+def test_fma_in_binary32_rounds_once():
+    """fma_t(..., float32) is the exact a*b+c rounded once to binary32 (no double rounding through binary64)."""
+    from fractions import Fraction
+    from chmy_b200.utils import fma_t
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        a, b, c = (np.float32(x) for x in (rng.standard_normal(3) * 10.0 ** rng.integers(-3, 4)))
+        x = Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c))
+        r = fma_t(a, b, c, np.float32)
+        lo, hi = np.nextafter(r, np.float32(-np.inf)), np.nextafter(r, np.float32(np.inf))
+        assert isinstance(r, np.float32)
+        assert abs(Fraction(float(r)) - x) <= min(abs(Fraction(float(lo)) - x), abs(Fraction(float(hi)) - x))
+    # a constructed double-rounding trap: exact value just above a binary32 midpoint that binary64 rounds ONTO the midpoint
+    a, b = np.float32(1.0 + 2.0 ** -23), np.float32(1.0 + 2.0 ** -23)          # a*b = 1 + 2^-22 + 2^-46
+    c = np.float32(2.0 ** -24)                                                   # sum = 1 + 2^-22 + 2^-24 + 2^-46
+    x = Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c))
+    r = fma_t(a, b, c, np.float32)
+    assert abs(Fraction(float(r)) - x) < Fraction(1, 2 ** 24)                    # strictly nearest

@@ -30,13 +30,21 @@ class OprArgs(C.Structure):
                 ("a", OprField * 3), ("k", OprField), ("id", C.c_double * 3)]
 
 
+class OprArgsF32(C.Structure):
+    _fields_ = [("oper", C.c_int), ("dim", C.c_int), ("nd", C.c_int), ("ndst", C.c_int), ("dst", OprField * 3),
+                ("a", OprField * 3), ("k", OprField), ("id", C.c_float * 3)]
+
+
+DTYPES = [np.float64, np.float32]            # TEST_TYPES of the reference (test/common.jl:9)
+
+
 @pytest.fixture(scope="module")
 def emul():
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-march=x86-64-v3", "-shared", "-fPIC", "-Wall",
                                "-Wno-unknown-pragmas", "-o", LIB, SRC])
     lib = C.CDLL(LIB)
-    assert lib.operators_emul_sizeof_args() == C.sizeof(OprArgs)
+    assert lib.operators_emul_sizeof_args(0) == C.sizeof(OprArgs) and lib.operators_emul_sizeof_args(1) == C.sizeof(OprArgsF32)
     return lib
 
 
@@ -46,9 +54,11 @@ class Pitched:
     def __init__(self, of):
         sd = tuple(of.sdims) + (1,) * (3 - of.nd)
         self.nd, self.sd, self.loc = of.nd, sd, tuple(of.loc) + (0,) * (3 - of.nd)
-        self.pitch = (sd[0] + 15) // 16 * 16
-        self.lead = 15
-        self.flat = np.full(self.lead + self.pitch * sd[1] * sd[2] + 32, 777.25)     # slack cells hold junk
+        self.es = of.data.dtype.itemsize
+        per128 = 128 // self.es                                  # 16 doubles | 32 floats per 128-byte line
+        self.pitch = (sd[0] + per128 - 1) // per128 * per128
+        self.lead = per128 - 1
+        self.flat = np.full(self.lead + self.pitch * sd[1] * sd[2] + 2 * per128, 777.25, dtype=of.data.dtype)  # slack = junk
         self.view()[...] = of.data.reshape(sd, order="F")
         self.sy = self.pitch if of.nd > 1 else 0
         self.sz = self.pitch * sd[1] if of.nd > 2 else 0
@@ -61,7 +71,7 @@ class Pitched:
     def opr(self):
         f = OprField()
         # logical 0 of every active dim = storage index 1 (field.jl:18 with halo 1)
-        f.p = self.flat.ctypes.data + 8 * (self.lead + 1 + self.sy + self.sz)
+        f.p = self.flat.ctypes.data + self.es * (self.lead + 1 + self.sy + self.sz)
         f.sy, f.sz = self.sy, self.sz
         for a in range(3):
             f.loc[a] = self.loc[a]
@@ -82,7 +92,8 @@ def run_both(o, emul, g, kind, dst_o, src_o, k_o=None, dim=0):
     pd = [Pitched(f) for f in dst_o]
     ps = [Pitched(f) for f in src_o]
     pk = Pitched(k_o) if k_o is not None else None
-    a = OprArgs()
+    f32 = g.dtype == np.float32
+    a = OprArgsF32() if f32 else OprArgs()
     a.oper, a.dim, a.nd, a.ndst = o.OPER[kind], dim, g.nd, len(pd)
     for c, f in enumerate(pd):
         a.dst[c] = f.opr()
@@ -94,7 +105,7 @@ def run_both(o, emul, g, kind, dst_o, src_o, k_o=None, dim=0):
         a.id[d] = g.inv_spacing[d]
     lo = (C.c_int * 3)(0, 0, 0)
     hi = (C.c_int * 3)(*([n + 1 for n in g.n] + [0] * (3 - g.nd)))
-    assert emul.operators_emul_run(C.byref(a), lo, hi) == 0
+    assert (emul.operators_emul_run_f32 if f32 else emul.operators_emul_run)(C.byref(a), lo, hi) == 0
     o.apply_operator(g, kind, dst_o, src_o, k=k_o, dim=dim)
     for c, (fo, fp) in enumerate(zip(dst_o, pd)):
         got = fp.dense(g.nd)
@@ -108,16 +119,18 @@ def run_both(o, emul, g, kind, dst_o, src_o, k_o=None, dim=0):
 def rnd_field(o, g, loc, rng, positive=False):
     f = o.Field(g, loc)
     f.data[...] = rng.random(f.sdims) + 0.5 if positive else rng.random(f.sdims) - 0.5      # interior, halo AND padding
+    assert f.data.dtype == g.dtype
     return f
 
 
 GRIDS = [((-1.0,), (2.0,), (9,)), ((-1.0, 0.5), (2.0, 1.7), (7, 5)), ((-5.0, -5.0, -5.0), (10.0, 9.0, 8.0), (6, 5, 4))]
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("origin,extent,n", GRIDS)
-def test_single_field_operators_every_location(oracle, emul, origin, extent, n):
+def test_single_field_operators_every_location(oracle, emul, origin, extent, n, dtype):
     o, nd = oracle, len(n)
-    g = o.Grid(origin, extent, n)
+    g = o.Grid(origin, extent, n, dtype=dtype)
     rng = np.random.default_rng(3)
     for loc in itertools.product((0, 1), repeat=nd):
         f = rnd_field(o, g, loc, rng)
@@ -136,10 +149,11 @@ def test_single_field_operators_every_location(oracle, emul, origin, extent, n):
             run_both(o, emul, g, "hlerp", rnd_field(o, g, to, rng), fpos)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("origin,extent,n", GRIDS)
-def test_vector_operators(oracle, emul, origin, extent, n):
+def test_vector_operators(oracle, emul, origin, extent, n, dtype):
     o, nd = oracle, len(n)
-    g = o.Grid(origin, extent, n)
+    g = o.Grid(origin, extent, n, dtype=dtype)
     rng = np.random.default_rng(4)
     ctr = (0,) * nd
     V = [rnd_field(o, g, flip(ctr, d), rng) for d in range(nd)]               # VectorField locations (field.jl:148)
@@ -157,11 +171,12 @@ def test_vector_operators(oracle, emul, origin, extent, n):
                      k_o=rnd_field(o, g, kloc, rng))
 
 
-def test_reference_identities_through_the_kernel_functions(oracle, emul):
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_reference_identities_through_the_kernel_functions(oracle, emul, dtype):
     """test/test_grid_operators.jl:21-61 with the operator kernels' own code: divg(grad C) == sum of the three partial
     derivatives with `==` (:41) and lapl == sum of second derivatives with `==` (:61)."""
     o = oracle
-    g = o.Grid((-5.0, -5.0, -5.0), (10.0, 10.0, 10.0), (12, 10, 8))
+    g = o.Grid((-5.0, -5.0, -5.0), (10.0, 10.0, 10.0), (12, 10, 8), dtype=dtype)
     Ci = o.Field(g, 0)
     Ci.set_fun(lambda x, y, z: np.exp(-x ** 2 - y ** 2 - z ** 2))
     V = [o.Field(g, flip((0, 0, 0), d)) for d in range(3)]

@@ -211,3 +211,162 @@ def test_operator_location_checks(ch, arch):
         launch(arch, grid, (ch.partial_(3), (c2, c, grid)))          # Dim(3) on a 2D grid
     with pytest.raises(ValueError):
         ch.partial_(0)
+
+
+# ------------------------------------------------------------------------------------------------ Float32 instantiation
+# The reference's tests run for T in (Float32, Float64) (test/common.jl:9).  Fields, set!/copies, maxabs, bc!, halo
+# slabs and the grid operators exist in Float32 on this path; the solver ops are Float64 programs.
+F32 = np.float32
+
+
+def mk_grids32(ch, o, arch, n, origin=None, extent=None):
+    nd = len(n)
+    origin = origin or tuple(-1.0 - 0.1 * d for d in range(nd))
+    extent = extent or tuple(2.0 + 0.3 * d for d in range(nd))
+    return o.Grid(origin, extent, n, dtype=F32), ch.UniformGrid(arch, origin=origin, extent=extent, dims=n, dtype=F32)
+
+
+def fill_pair32(rng, of, bf, scale=1.0):
+    a = ((rng.random(of.sdims) - 0.5) * scale).astype(F32)
+    of.data[...] = a
+    bf.from_host(a, [-1] * len(of.dims), [d + 2 for d in of.dims])
+    return a
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("n,loc", [((7,), (1,)), ((33, 18), (0, 1)), ((12, 10, 8), (1, 0, 1)), ((70, 5, 3), (0, 0, 0))])
+def test_f32_field_roundtrip_fill_copy_maxabs(ch, arch, oracle, n, loc, layout):
+    og, bg = mk_grids32(ch, oracle, arch, n)
+    for d in range(len(n)):                                              # host grid numbers == oracle, in binary32
+        assert float(ch.spacing(bg)[d]) == og.spacing[d] and float(ch.inv_spacing(bg)[d]) == og.inv_spacing[d]
+    of = oracle.Field(og, loc)
+    bf = ch.Field(arch, bg, bloc(ch, loc), layout=layout)
+    assert bf.dtype == F32 and bf.dims == of.dims and bf.info().dtype == 1
+    assert np.array_equal(bf.parent(), np.zeros(of.sdims, F32)) and bf.parent().dtype == F32
+    if layout == 0:
+        assert (bf.info().origin_ptr - 4) % 128 == 0                     # logical index 0 of each row is 128 B aligned
+    rng = np.random.default_rng(21)
+    a = fill_pair32(rng, of, bf)
+    assert_same(of, bf, "roundtrip f32")
+    assert np.array_equal(ch.interior(bf, with_halo=True), of.interior(with_halo=True))
+    assert ch.maxabs(bf) == of.maxabs() == float(np.abs(of.interior()).max())
+    ch.set_(bf, 3.5); of.set(3.5)
+    assert_same(of, bf, "set scalar f32")
+    A = rng.random(of.dims).astype(F32)
+    ch.set_(bf, A); of.set(A)
+    assert_same(of, bf, "set array f32")
+    bf2 = ch.Field(arch, bg, bloc(ch, loc), layout=layout)
+    ch.set_(bf2, bf)
+    assert np.array_equal(ch.interior(bf2), of.interior()) and np.array_equal(bf2.parent()[0], np.zeros_like(bf2.parent()[0]))
+    a[tuple(3 for _ in n)] = np.nan
+    bf.from_host(a, [-1] * len(n), [d + 2 for d in of.dims])
+    assert np.isnan(ch.maxabs(bf))
+    f64 = ch.Field(arch, ch.UniformGrid(arch, origin=(0.0,) * len(n), extent=(1.0,) * len(n), dims=n), bloc(ch, loc))
+    with pytest.raises(ch.ChmyError):
+        ch.set_(f64, bf)                                                  # element types differ
+
+
+@pytest.mark.parametrize("n", [(40, 27), (19, 14, 11)])
+def test_f32_set_inclusion(ch, arch, oracle, n):
+    nd = len(n)
+    og, bg = mk_grids32(ch, oracle, arch, n, origin=(-1.0,) * nd, extent=(2.0,) * nd)
+    for loc in [(0,) * nd, tuple(1 if d == nd - 1 else 0 for d in range(nd))]:
+        of, bf = oracle.Field(og, loc), ch.Field(arch, bg, bloc(ch, loc))
+        oracle.set_inclusion(of, oracle.Inclusion(loc, (0.05,) * nd, 0.31, 1.0, 0.1))
+        par = dict(zip(("x0", "y0", "z0"), (0.05,) * nd))
+        ch.set_(bf, bg, ch.init_incl, parameters={**par, "r": 0.31, "in": 1.0, "out": 0.1})
+        assert_same(of, bf, "inclusion f32")
+        assert 0 < (of.interior() == 1.0).sum() < of.interior().size
+
+
+@pytest.mark.parametrize("n,loc", [((8,), (0,)), ((8,), (1,)), ((8, 8), (0, 1)), ((8, 8, 6), (0, 1, 0)), ((13, 7, 5), (1, 1, 0))])
+def test_f32_bc_matches_oracle_bit_exact(ch, arch, oracle, n, loc):
+    """test/test_boundary_conditions.jl for T = Float32: every touched cell equals the binary32 oracle."""
+    import math
+    nd = len(n)
+    og, bg = mk_grids32(ch, oracle, arch, n, origin=(-math.pi,) * nd, extent=(2 * math.pi,) * nd)
+    of, bf = oracle.Field(og, loc), ch.Field(arch, bg, bloc(ch, loc))
+    rng = np.random.default_rng(7)
+    for mk_o, mk_b in [(oracle.Dirichlet, ch.Dirichlet), (oracle.Neumann, ch.Neumann)]:
+        for val in (None, 2.0, 0.3):
+            fill_pair32(rng, of, bf)
+            oracle.bc_(og, (of, mk_o(val)))
+            ch.bc_(arch, bg, (bf, mk_b(val)))
+            assert_same(of, bf, f"bc f32 {mk_o.__name__}({val})")
+    if nd >= 2:
+        D = 0
+        tg_o = oracle.transverse_grid(og, D)
+        keep = [a for a in range(nd) if a != D]
+        tg_b = ch.UniformGrid(arch, origin=[og.origin[a] for a in keep], extent=[og.extent[a] for a in keep],
+                              dims=[n[a] for a in keep], dtype=F32)
+        vo, vb = oracle.Field(tg_o, oracle.VERTEX), ch.Field(arch, tg_b, ch.Vertex())
+        fill_pair32(rng, vo, vb)
+        fill_pair32(rng, of, bf)
+        oracle.bc_(og, (of, {"x": oracle.Neumann(vo)}))
+        ch.bc_(arch, bg, (bf, {"x": ch.Neumann(vb)}))
+        assert_same(of, bf, "field-valued Neumann f32")
+
+
+@pytest.mark.parametrize("n,loc", [((9, 6), (1, 0)), ((11, 7, 5), (0, 1, 1))])
+def test_f32_halo_pack_unpack_bit_exact(ch, arch, oracle, n, loc):
+    import ctypes as C
+    from chmy_b200 import _lib as L
+    og, bg = mk_grids32(ch, oracle, arch, n)
+    of, bf = oracle.Field(og, loc), ch.Field(arch, bg, bloc(ch, loc))
+    enc = (np.arange(of.data.size, dtype=np.float64).reshape(of.sdims, order="F") + 1e3).astype(F32)
+    of.data[...] = enc
+    bf.from_host(enc, [-1] * len(n), [d + 2 for d in of.dims])
+    for D in range(len(n)):
+        for S in range(2):
+            ref = oracle.pack_send(of, D, S)
+            buf = np.empty(ref.size, dtype=F32)
+            L.check(L.lib().chmy_halo_pack(arch.ctx, bf.handle, D, S, buf.ctypes.data_as(C.c_void_p)))
+            assert ref.dtype == F32 and np.array_equal(buf, ref), (D, S)
+            msg = (-ref[::-1]).copy()
+            oracle.unpack_recv(of, D, S, msg)
+            L.check(L.lib().chmy_halo_unpack(arch.ctx, bf.handle, D, S, msg.ctypes.data_as(C.c_void_p)))
+            assert_same(of, bf, f"unpack f32 {D},{S}")
+
+
+@pytest.mark.parametrize("n", [(9,), (7, 5), (6, 5, 4)])
+def test_f32_grid_operators_bit_exact(ch, arch, oracle, n):
+    nd = len(n)
+    og, bg = mk_grids32(ch, oracle, arch, n)
+    rng = np.random.default_rng(6)
+
+    def mk(loc, positive=False):
+        of, bf = oracle.Field(og, loc), ch.Field(arch, bg, bloc(ch, loc))
+        a = (rng.random(of.sdims) + (0.5 if positive else -0.5)).astype(F32)
+        of.data[...] = a
+        bf.from_host(a, [-1] * nd, [d + 2 for d in of.dims])
+        return of, bf
+    locs = list(itertools.product((0, 1), repeat=nd))
+    for loc in locs:
+        f = mk(loc)
+        for dim in range(nd):
+            both(ch, oracle, arch, og, bg, "partial", mk(flip(loc, dim)), f, dim=dim)
+            both(ch, oracle, arch, og, bg, "partial2", mk(loc), f, dim=dim)
+            both(ch, oracle, arch, og, bg, "dkd", mk(loc), f, k=mk(locs[-1]), dim=dim)
+        both(ch, oracle, arch, og, bg, "lapl", mk(loc), f)
+        both(ch, oracle, arch, og, bg, "divg_grad", mk(loc), f, k=mk(locs[0]))
+        fpos = mk(loc, True)
+        for to in locs:
+            both(ch, oracle, arch, og, bg, "lerp", mk(to), f)
+            both(ch, oracle, arch, og, bg, "hlerp", mk(to), fpos)
+    ctr = (0,) * nd
+    V = [mk(flip(ctr, d)) for d in range(nd)]
+    both(ch, oracle, arch, og, bg, "divg", mk(ctr), V)
+    both(ch, oracle, arch, og, bg, "vmag", mk(ctr), V)
+    both(ch, oracle, arch, og, bg, "kgrad", [mk(flip(ctr, d)) for d in range(nd)], mk(ctr), k=mk(locs[-1]))
+
+
+def test_f32_fields_are_refused_by_the_solver_ops(ch, arch):
+    """the example solvers are Float64 programs: a Float32 field in their argument list is an error, not a conversion"""
+    g = ch.UniformGrid(arch, origin=(0.0, 0.0), extent=(1.0, 1.0), dims=(8, 6), dtype=F32)
+    C, q = ch.Field(arch, g, ch.Center()), ch.VectorField(arch, g)
+    assert C.dtype == F32 and q.x.dtype == F32
+    with pytest.raises(ch.ChmyError):
+        ch.Launcher(arch, g)(arch, g, (ch.compute_q_, (q, C, 1.0, g)))
+    f64 = ch.Field(arch, ch.UniformGrid(arch, origin=(0.0, 0.0), extent=(1.0, 1.0), dims=(8, 6)), ch.Center())
+    with pytest.raises(ch.ChmyError):
+        ch.Launcher(arch, g)(arch, g, (ch.lapl_, (C, f64, g)))           # operators need one element type
