@@ -61,15 +61,7 @@ static bool ctx_alive(const chmy_ctx* c) {
     return false;
 }
 
-extern "C" int chmy_ctx_create(int device_id, chmy_ctx** out) {
-    CHMY_REQUIRE(out != nullptr, "out is NULL");
-    int ndev = 0;
-    CHMY_CUDA(cudaGetDeviceCount(&ndev));
-    // the reference's device ids are 1-based: CuDevice(id - 1)  (ext/ChmyCUDAExt/ChmyCUDAExt.jl:17)
-    CHMY_REQUIRE(device_id >= 1 && device_id <= ndev, "device_id %d out of range 1..%d", device_id, ndev);
-    chmy_ctx* c = (chmy_ctx*)calloc(1, sizeof(chmy_ctx));
-    if (!c) { chmy_set_error("out of host memory"); return CHMY_ERR_NOMEM; }
-    c->device = device_id - 1;
+static int ctx_init(chmy_ctx* c) {
     CHMY_CUDA(cudaSetDevice(c->device));
     int lo = 0, hi = 0;   // numerically lowest value = highest priority
     CHMY_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -81,6 +73,30 @@ extern "C" int chmy_ctx_create(int device_id, chmy_ctx** out) {
     CHMY_CUDA(cudaMalloc(&c->d_red, 64 * sizeof(unsigned long long)));
     CHMY_CUDA(cudaMallocHost(&c->h_red, 64 * sizeof(unsigned long long)));
     CHMY_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+    return CHMY_OK;
+}
+
+extern "C" int chmy_ctx_create(int device_id, chmy_ctx** out) {
+    CHMY_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    CHMY_CUDA(cudaGetDeviceCount(&ndev));
+    // the reference's device ids are 1-based: CuDevice(id - 1)  (ext/ChmyCUDAExt/ChmyCUDAExt.jl:17)
+    CHMY_REQUIRE(device_id >= 1 && device_id <= ndev, "device_id %d out of range 1..%d", device_id, ndev);
+    chmy_ctx* c = (chmy_ctx*)calloc(1, sizeof(chmy_ctx));
+    if (!c) { chmy_set_error("out of host memory"); return CHMY_ERR_NOMEM; }
+    c->device = device_id - 1;
+    const int rc = ctx_init(c);
+    if (rc != CHMY_OK) {           // release whatever was created before the failing call; the error text stays
+        if (c->h_red) cudaFreeHost(c->h_red);
+        if (c->d_red) cudaFree(c->d_red);
+        if (c->ev_join) cudaEventDestroy(c->ev_join);
+        if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+        if (c->s_bnd) cudaStreamDestroy(c->s_bnd);
+        if (c->s_main) cudaStreamDestroy(c->s_main);
+        free(c);
+        return rc;
+    }
     ctx_register(c);
     *out = c;
     return CHMY_OK;
