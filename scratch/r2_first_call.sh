@@ -8,6 +8,9 @@ set +e
 echo "== 1. pending tests (operators, Float32, pinned arrays): xfail -> must all XPASS"
 timeout 300 python -m pytest tests/test_zz_b200_round2.py -q -rxX 2>&1 | tail -45 | tee gpurun_out/r2_pending_tests.log
 
+echo "== 1b. full-size property parity (767^3 / 8191^2 / 16383^2): xfail -> must all XPASS"
+timeout 600 python -m pytest tests/test_zy_b200_fullsize.py -q -rxX 2>&1 | tail -15 | tee gpurun_out/r2_fullsize_tests.log
+
 echo "== 2. experimental kernels (2D fused sweeps, 2-row CTAs, pipelined phase A): gated tests"
 CHMY_EXPERIMENTAL=1 timeout 420 python -m pytest tests/test_b200_fused.py tests/test_b200_fused2d.py -x -q 2>&1 | tail -15 | tee gpurun_out/r2_experimental_tests.log
 
