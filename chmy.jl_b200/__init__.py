@@ -5,13 +5,13 @@ Julia `f!` is spelled `f_` here; `op => args` is the tuple `(op, args)`; 1-based
 Everything computes through libchmy_b200.so (hand-written CUDA for sm_100a, include/chmy_b200.h).
 """
 from ._lib import ChmyError, LIB_PATH, lib as load_library
-from .utils import Dim, Side, Left, Right, remove_dim, insert_dim
+from .utils import Dim, Side, Left, Right, remove_dim, insert_dim, DoubleBuffer, swap_, front, back
 from .architectures import (Architecture, SingleDeviceArchitecture, DistributedArchitecture, B200Backend, Arch,
-                            get_backend, get_device, activate_, synchronize, launch_count, topology,
+                            get_backend, get_device, activate_, set_device_, is_gpu_aware, synchronize, launch_count, topology,
                             event_record, event_elapsed_ms, set_fusion, fused_count, set_fused_tuning, set_fused2d_tuning)
 from .grids import (Location, Center, Vertex, flip, Bounded, Connected, UniformAxis, StructuredGrid, UniformGrid,
                     connectivity, spacing, inv_spacing, coord, coords, centers, vertices, origin, extent, bounds,
-                    axes_names)
+                    axes_names, expand_loc, nvertices, ncenters, axis, vertex, center, direction, volume, inv_volume)
 from .fields import (AbstractField, Field, FieldTuple, VectorField, TensorField, FunctionField, init_incl, set_,
                      interior, parent, fill_parent_, halo, location, maxabs, vector_location, pinned_array)
 from .boundary_conditions import (BoundaryFunction, FirstOrderBC, Dirichlet, Neumann, EmptyBatch, FieldBatch, ExchangeBatch, batch, bc_)
@@ -19,7 +19,7 @@ from .kernel_launch import (Launcher, worksize, outer_width, inner_worksize, inn
                             outer_offset)
 from .distributed import (CartesianTopology, TorchDistComm, dims_create, exchange_halo_, allreduce_max, barrier, gather_,
                           global_rank, shared_rank, node_name, dims, cart_coords, neighbors, neighbor, has_neighbor,
-                          global_size, node_size, PROC_NULL)
+                          global_size, node_size, cart_comm, shared_comm, PROC_NULL)
 from .ops import (KernelOp, compute_q_, update_C_, update_old_, update_stress_, update_velocity_,
                   update_thermal_flux_, update_thermal_)
 from .grid_operators import (left_, right_, delta_, partial_, partial2_, dkd_, dx_, dy_, dz_, d2x_, d2y_, d2z_, lerp_, hlerp_,

@@ -98,6 +98,17 @@ def get_device(arch: Architecture):
     return arch.device_id
 
 
+def set_device_(arch_or_dev):
+    """set_device!(dev) (ext/ChmyCUDAExt/ChmyCUDAExt.jl:15): every C entry point selects its context's device itself
+    (cudaSetDevice at entry), so there is no process-wide current device to switch; kept for source compatibility."""
+    return None
+
+
+def is_gpu_aware(arch) -> bool:
+    """is_gpu_aware(arch) (distributed_architecture.jl:75): device buffers go straight into NCCL."""
+    return bool(getattr(arch, "gpu_aware", True))
+
+
 def activate_(arch: Architecture, priority: str = "normal"):
     """activate!(arch; priority) (Architectures.jl:71-74).  Stream priorities are fixed inside the context
     (main = normal, boundary = high), so this only validates its argument."""

@@ -141,6 +141,17 @@ def global_size(t):
     return t.nprocs
 
 
+def cart_comm(t):
+    """cart_comm(topo) (topology.jl:66): the bootstrap communicator in Cartesian rank order (ranks are row-major over
+    `dims`, exactly MPI.Cart_create's numbering without reordering); the data path uses the NCCL communicator."""
+    return t.comm
+
+
+def shared_comm(t):
+    """shared_comm(topo) (topology.jl:73): the ranks of this node, as (node-local rank, size) of the bootstrap communicator."""
+    return (t.shared_rank, t.node_size_)
+
+
 def node_size(t):
     return t.node_size_
 

@@ -222,3 +222,49 @@ def bounds(grid, loc, dim: int):
 
 def axes_names(grid):
     return ("x", "y", "z")[:grid.ndims()]
+
+
+# --- the remaining host-side accessors the reference exports (src/Grids/Grids.jl:8-12); pure numbers
+def nvertices(grid_or_axis, dim: int | None = None):
+    """nvertices(ax) = length + 1 (uniform_axis.jl:16; abstract_axis.jl:10)."""
+    return grid_or_axis.nvertices() if dim is None else grid_or_axis.axes[dim - 1].nvertices()
+
+
+def ncenters(grid_or_axis, dim: int | None = None):
+    """ncenters(ax) = nvertices(ax) - 1 (abstract_axis.jl:11)."""
+    return grid_or_axis.length if dim is None else grid_or_axis.axes[dim - 1].length
+
+
+def axis(grid, dim: int) -> UniformAxis:
+    """axis(grid, Dim(dim)) (structured_grid.jl:93)."""
+    return grid.axes[dim - 1]
+
+
+def vertex(grid, dim: int, i: int):
+    """vertex(grid, Dim(dim), i) (structured_grid.jl:124)."""
+    return grid.axes[dim - 1].vertex(i)
+
+
+def center(grid, dim: int, i: int):
+    """center(grid, Dim(dim), i) (structured_grid.jl:127)."""
+    return grid.axes[dim - 1].center(i)
+
+
+def direction(grid, name: str) -> int:
+    """direction(grid, Val(:x)) = Dim(1) ... (structured_grid.jl:222-224); 1-based."""
+    return ("x", "y", "z").index(name) + 1
+
+
+def volume(grid, loc, *I):
+    """volume(grid, loc, I...) = prod of the spacings (structured_grid.jl:248-268); folds left in eltype(grid)."""
+    v = grid.axes[0].spacing
+    for ax in grid.axes[1:]:
+        v = v * ax.spacing
+    return v
+
+
+def inv_volume(grid, loc, *I):
+    v = grid.axes[0].inv_spacing
+    for ax in grid.axes[1:]:
+        v = v * ax.inv_spacing
+    return v

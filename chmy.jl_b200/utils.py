@@ -49,3 +49,24 @@ def insert_dim(D: int, A, v):
     A = list(A)
     A.insert(D - 1, v)
     return tuple(A)
+
+
+class DoubleBuffer:
+    """DoubleBuffer{T} (src/DoubleBuffers.jl:5-16): two handles and a swap.  (The fused sweeps ping-pong INSIDE the
+    library, behind one Field handle; this is the user-level helper the reference exports.)"""
+
+    def __init__(self, front, back):
+        self.front, self.back = front, back
+
+
+def swap_(db: DoubleBuffer):
+    db.front, db.back = db.back, db.front
+    return db.front, db.back
+
+
+def front(db: DoubleBuffer):
+    return db.front
+
+
+def back(db: DoubleBuffer):
+    return db.back

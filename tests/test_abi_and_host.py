@@ -199,3 +199,26 @@ def test_fma_in_binary32_rounds_once():
     x = Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c))
     r = fma_t(a, b, c, np.float32)
     assert abs(Fraction(float(r)) - x) < Fraction(1, 2 ** 24)                    # strictly nearest
+
+
+def test_host_api_surface_matches_the_reference_exports():
+    """Every host-side name the reference exports for this path (src/*/…jl `export` lists) exists on the mirror, `!` spelled `_`."""
+    import chmy_b200 as ch
+    names = ("Architecture SingleDeviceArchitecture Arch get_backend get_device activate_ set_device_ DoubleBuffer swap_ front "
+             "back Launcher worksize outer_width inner_worksize inner_offset outer_worksize outer_offset FirstOrderBC Dirichlet "
+             "Neumann bc_ BoundaryFunction FieldBatch ExchangeBatch EmptyBatch batch CartesianTopology global_rank shared_rank "
+             "node_name cart_comm shared_comm dims cart_coords neighbors neighbor has_neighbor global_size node_size "
+             "DistributedArchitecture topology is_gpu_aware exchange_halo_ gather_ AbstractField Field VectorField TensorField "
+             "FunctionField location halo interior set_ Location Center Vertex flip Bounded Connected UniformAxis "
+             "StructuredGrid UniformGrid nvertices ncenters spacing inv_spacing volume inv_volume coord coords center vertex "
+             "centers vertices origin extent bounds axis direction axes_names expand_loc connectivity "
+             "left_ right_ delta_ partial_ partial2_ dkd_ lerp_ hlerp_ divg_ divg_grad_ lapl_ vmag_").split()
+    missing = [n for n in names if not hasattr(ch, n)]
+    assert not missing, missing
+    g = ch.UniformGrid(_FakeArch(), origin=(0.0, 0.0), extent=(1.0, 2.0), dims=(4, 5))
+    assert (ch.nvertices(g, 1), ch.ncenters(g, 2)) == (5, 5) and ch.axis(g, 2) is g.axes[1]
+    assert ch.vertex(g, 1, 2) == 0.25 and ch.center(g, 2, 1) == 0.2 and ch.direction(g, "y") == 2
+    assert ch.volume(g, ch.Center(), 1, 1) == 0.25 * 0.4 and ch.inv_volume(g, ch.Vertex(), 1, 1) == 4.0 * 2.5
+    db = ch.DoubleBuffer("a", "b")
+    ch.swap_(db)
+    assert (ch.front(db), ch.back(db)) == ("b", "a")
