@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fused", type=int, default=1, choices=[0, 1, 3],
                     help="3D Stokes: lazily fuse update_stress! + update_velocity! into one sweep (chmy_set_fusion); "
-                         "0 = the two tuned kernels; 3 = additionally the EXPERIMENTAL 2D sweeps (2D workloads)")
+                         "0 = the two tuned kernels; 3 = additionally the EXPERIMENTAL sweeps (2D workloads; 3D thermal pair)")
     return ap.parse_args()
 
 
@@ -215,8 +215,9 @@ def run_b200(args):
     wl = args.workload
     n = tuple(args.n) if args.n else WORKLOADS[wl][0]
     fused2d = args.fused == 3 and not wl.startswith("stokes3d")      # EXPERIMENTAL 2D sweeps (ops_fused2d.cu)
+    fused_t3 = args.fused == 3 and wl == "stokes3d_thermal"          # EXPERIMENTAL 3D thermal sweep (fused_thermal3.cuh)
     fused = (bool(args.fused) and wl.startswith("stokes3d")) or fused2d
-    ch.set_fusion(arch, 3 if fused2d else int(fused))
+    ch.set_fusion(arch, 3 if (fused2d or fused_t3) else int(fused))
     if wl == "diffusion2d":
         sol = BD.Diffusion2D(arch, n, outer_width=(128, 8), C0=None, blocking=False)
         # uniform [0,1) initial condition generated on the host in strips (the reference uses rand())
@@ -256,7 +257,7 @@ def run_b200(args):
             sub += [("update_thermal_flux!", lambda: sol.launch(arch, g, (ch.update_thermal_flux_, (sol.qT, sol.T, sol.V, sol.lam, g)))),
                     ("update_thermal!", lambda: sol.launch(arch, g, (ch.update_thermal_, (sol.T, sol.T_old, sol.qT, sol.dt, g)),
                                                            bc=ch.batch(g, *sol.bc_T, exchange=sol.T)))]
-            if fused2d:
+            if fused2d or fused_t3:
                 t0_, t1_ = sub[-2][1], sub[-1][1]
                 sub = sub[:-2] + [("update_thermal_flux!+update_thermal! (fused sweep)", lambda: (t0_(), t1_()))]
         metric_field = sol.divV

@@ -619,12 +619,14 @@ static int run_fused2d(chmy_ctx* ctx, int kind, const chmy_launch_desc* dp, cons
     int nfr = 0;
     for (int q = 0; q < npp; ++q)
         if (!pp[q]->frame_synced) { fr[nfr] = pp[q]; fsrc[nfr] = pp[q]->p0; fdst[nfr] = pp[q]->alt_p0(); ++nfr; pp[q]->frame_synced = true; }
-    CHMY_TRY(chmy_frame_copy2(ctx, &dp->grid, nfr, fr, fsrc, fdst, ctx->s_main));
+    if (dp->grid.ndims == 3) CHMY_TRY(chmy_frame_copy(ctx, &dp->grid, nfr, fr, fsrc, fdst, ctx->s_main));
+    else CHMY_TRY(chmy_frame_copy2(ctx, &dp->grid, nfr, fr, fsrc, fdst, ctx->s_main));
     double *cur[6], *shadow[6];
     for (int q = 0; q < npp; ++q) { cur[q] = pp[q]->p0; shadow[q] = pp[q]->alt_p0(); }
     for (int q = 0; q < npp; ++q) pp[q]->swap_buffers();
     ctx->n_fused++;
-    const int pref[3] = {60, 0, 0};      // x slabs of a split launch: one 60-cell row segment; y slabs as asked
+    // x slabs of a split launch: one row segment (60 interior cells in 2D, 64 cells in the 3D thermal sweep); y, z as asked
+    const int pref[3] = {kind == 4 ? 64 : 60, 0, 0};
     return orchestrate(ctx, dc, [&](const Box& b, cudaStream_t st) { return chmy_run_fused2d(ctx, kind, dp, dc, b, cur, shadow, st); }, pref);
 }
 
@@ -645,7 +647,7 @@ extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
         CHMY_TRY(run_plain(ctx, &ctx->pending));    // no memory for the shadow buffers: two kernels
         return run_plain(ctx, d);
     }
-    if (ctx->has_pending && (ctx->fuse & 2) && g->ndims == 2 && !odd_exact_split) {
+    if (ctx->has_pending && (ctx->fuse & 2) && !odd_exact_split) {       // EXPERIMENTAL pairs: 2D kinds 1-3, 3D thermal kind 4
         const int kind = chmy_fused2d_kind(&ctx->pending, d);
         if (kind) {
             ctx->has_pending = 0;
@@ -656,13 +658,14 @@ extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
         }
     }
     CHMY_TRY(chmy_flush(ctx));
-    if (ctx->fuse && d->op == CHMY_OP_UPDATE_STRESS && g->ndims == 3 && !d->has_bc) {
+    if ((ctx->fuse & 1) && d->op == CHMY_OP_UPDATE_STRESS && g->ndims == 3 && !d->has_bc) {
         ctx->pending = *d;
         ctx->has_pending = 1;
         return CHMY_OK;
     }
-    if ((ctx->fuse & 2) && g->ndims == 2 && !d->has_bc &&
-        (d->op == CHMY_OP_UPDATE_STRESS || d->op == CHMY_OP_COMPUTE_Q || d->op == CHMY_OP_UPDATE_THERMAL_FLUX)) {
+    if ((ctx->fuse & 2) && !d->has_bc &&
+        ((g->ndims == 2 && (d->op == CHMY_OP_UPDATE_STRESS || d->op == CHMY_OP_COMPUTE_Q || d->op == CHMY_OP_UPDATE_THERMAL_FLUX)) ||
+         (g->ndims == 3 && d->op == CHMY_OP_UPDATE_THERMAL_FLUX))) {
         ctx->pending = *d;
         ctx->has_pending = 1;
         return CHMY_OK;

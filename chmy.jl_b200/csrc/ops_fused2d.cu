@@ -3,12 +3,16 @@
 //   kind 1  update_stress! + update_velocity!        (fused_sv2d.cuh;   24 -> 18 array passes)
 //   kind 2  compute_q! + update_C!                   (fused_pairs2d.cuh; 7 ->  4)
 //   kind 3  update_thermal_flux! + update_thermal!   (fused_pairs2d.cuh; 9 ->  7)
+// and of the 3D thermal pair
+//   kind 4  update_thermal_flux! + update_thermal! 3D (fused_thermal3.cuh; 12 -> 9; emulation: tests/emul/fused_emul_t3.cpp)
 // Design and data flow: the two headers.  One warp = one 64-cell row segment (60 interior cells) marching along y over
 // one y-chunk; warps are independent (no shared memory, no barrier), a CTA is just F2_WARPS consecutive segments.
 #include "fused_sv2d.cuh"
 #include "fused_pairs2d.cuh"
+#include "fused_thermal3.cuh"
 
 constexpr int F2_WARPS = 4;
+constexpr int FT3_ROWS = 8;      // rows (warps) per CTA of the 3D thermal sweep, as the tuned kernels' TY
 
 template <bool TD, bool FUN>
 __global__ void __launch_bounds__(FSV_LANES* F2_WARPS, 4) k_fused_sv2(const Fused2P p, const int gx) {
@@ -51,6 +55,21 @@ __global__ void __launch_bounds__(FSV_LANES* F2_WARPS, (KIND == 0 ? 8 : 4)) k_fu
                 fq2_phase_b<KIND>(s, p, jg + r, sn, qx_ip2);
             }
         }
+    }
+}
+
+// 3D thermal pair: one warp = one 64-cell row segment of one row, FT3_ROWS rows per CTA, one z-chunk per CTA; warps are
+// independent (no shared memory, no barrier).  All 32 lanes run the loop: its bounds depend on blockIdx.z only.
+__global__ void __launch_bounds__(FSV_LANES* FT3_ROWS, 2) k_fused_t3(const FusedT3P p) {
+    FusedT3T s;
+    ft3_init(s, p, threadIdx.x, blockIdx.x, blockIdx.y * FT3_ROWS + threadIdx.y, blockIdx.z);
+    for (int k = s.k0; k < s.k1; ++k) {
+        FusedT3L L;
+        ft3_load(s, p, k, L);
+        const double t_left   = __shfl_up_sync(FULL, s.t_k.y, 1);
+        const double t_right  = __shfl_down_sync(FULL, s.t_k.x, 1);
+        const double vx_right = __shfl_down_sync(FULL, L.vx.x, 1);
+        ft3_compute(s, p, k, L, t_left, t_right, vx_right);
     }
 }
 
@@ -131,9 +150,34 @@ static inline bool fits_int(const chmy_field* f) { return f->stride[1] * f->sd[1
 //   stress  : tau[3] Pr divV V[2] tau_old[3]  scalars eta eta_ve G dt dtau_Pr dtau_r ; velocity: V[2] r_V[2] Pr tau[3] rho_g|NULL
 //   compute_q: q.x q.y C  scalars chi        ; update_C: C q.x q.y  scalars dt
 //   thermal_flux: qT[2] T V[2]  scalars lambda ; thermal: T T_old qT[2]  scalars dt
+static inline bool fits_int3(const chmy_field* f) { return f->stride[2] * f->sd[2] < (1ll << 40) && f->stride[2] < (1ll << 31); }
+
+// 3D thermal pair (kind 4).  thermal_flux: qT[3] T V[3]  scalars lambda ; thermal: T T_old qT[3]  scalars dt
+static int fused_t3_kind(const chmy_launch_desc* dp, const chmy_launch_desc* dc) {
+    if (dp->op != CHMY_OP_UPDATE_THERMAL_FLUX || dc->op != CHMY_OP_UPDATE_THERMAL) return 0;
+    chmy_field* const* P = dp->fields;
+    chmy_field* const* Q = dc->fields;
+    for (int a = 0; a < 3; ++a)
+        if (dp->grid.n[a] != dc->grid.n[a] || dp->grid.inv_spacing[a] != dc->grid.inv_spacing[a]) return 0;
+    for (int q = 0; q < 7; ++q)
+        if (!P[q] || !aligned16(P[q]) || !fits_int3(P[q])) return 0;
+    for (int q = 0; q < 5; ++q)
+        if (!Q[q] || !aligned16(Q[q]) || !fits_int3(Q[q])) return 0;
+    if (P[0] != Q[2] || P[1] != Q[3] || P[2] != Q[4] || P[3] != Q[0]) return 0;       // same qT, same T
+    if (Q[1] == Q[0]) return 0;                                                         // T_old must not alias T
+    const chmy_field *T = Q[0];
+    // storage classes: CC T T_old V.z q.z ; VC V.x q.x ; CV V.y q.y
+    if (!same_strides(Q[1], T) || !same_strides(P[2], T) || !same_strides(P[6], T) || !same_strides(P[4], P[0]) ||
+        !same_strides(P[5], P[1]))
+        return 0;
+    return 4;
+}
+
 int chmy_fused2d_kind(const chmy_launch_desc* dp, const chmy_launch_desc* dc) {
     if (chmy_fast_disabled()) return 0;
-    if (dp->grid.ndims != 2 || dc->grid.ndims != 2 || dp->has_bc) return 0;
+    if (dp->has_bc) return 0;
+    if (dp->grid.ndims == 3 && dc->grid.ndims == 3) return fused_t3_kind(dp, dc);
+    if (dp->grid.ndims != 2 || dc->grid.ndims != 2) return 0;
     for (int a = 0; a < 2; ++a)
         if (dp->grid.n[a] != dc->grid.n[a] || dp->grid.inv_spacing[a] != dc->grid.inv_spacing[a]) return 0;
     chmy_field* const* P = dp->fields;
@@ -193,8 +237,42 @@ static int launch_q2(const FusedQ2P& p, int gx, dim3 grid, cudaStream_t st) {
 
 // One sub-box of a fused 2D sweep.  cur / shadow: buffers of the ping-pong fields in chmy_fused2d_pingpong order (the
 // caller has already swapped the fields' storage).
+static int g_t3_cz = 16;      // planes per z-chunk of the 3D thermal sweep (the tuned kernels' measured optimum; untuned here)
+
+static int run_fused_t3(chmy_ctx* ctx, const chmy_launch_desc* dp, const chmy_launch_desc* dc, const Box& box,
+                        double* const* cur, double* const* shadow, cudaStream_t st) {
+    if (box.n[0] <= 0 || box.n[1] <= 0 || box.n[2] <= 0) return CHMY_OK;
+    CHMY_REQUIRE((box.lo[0] & 1) == 0, "fused sweep needs an even x origin");
+    chmy_field* const* P = dp->fields;
+    chmy_field* const* Q = dc->fields;
+    FusedT3P p;
+    memset(&p, 0, sizeof(p));
+    p.Tc = cur[0]; p.Tn = shadow[0]; p.To = Q[1]->p0;
+    p.qx = P[0]->p0; p.qy = P[1]->p0; p.qz = P[2]->p0;
+    p.Vx = P[4]->p0; p.Vy = P[5]->p0; p.Vz = P[6]->p0;
+    p.cc = strides_of(Q[0]); p.vc = strides_of(P[0]); p.cv = strides_of(P[1]);
+    for (int a = 0; a < 3; ++a) {
+        p.lo[a] = box.lo[a]; p.hi[a] = box.lo[a] + box.n[a];
+        p.flo[a] = 0; p.fhi[a] = (int)dp->grid.n[a] + 2;
+    }
+    p.lam = dp->scalars[0]; p.dt = dc->scalars[0];
+    p.idx = dp->grid.inv_spacing[0]; p.idy = dp->grid.inv_spacing[1]; p.idz = dp->grid.inv_spacing[2];
+    const char* e = getenv("CHMY_FUSE_T3_CZ");
+    int cz = e && atoi(e) >= 1 ? atoi(e) : g_t3_cz;
+    while ((box.n[2] + cz - 1) / cz > 65535) cz *= 2;
+    const int nch = (box.n[2] + cz - 1) / cz;
+    p.cz = (box.n[2] + nch - 1) / nch;                          // balanced chunks
+    const dim3 grid((unsigned)((box.n[0] + 2 * FSV_LANES - 1) / (2 * FSV_LANES)), (unsigned)((box.n[1] + FT3_ROWS - 1) / FT3_ROWS),
+                    (unsigned)((box.n[2] + p.cz - 1) / p.cz));
+    k_fused_t3<<<grid, dim3(FSV_LANES, FT3_ROWS, 1), 0, st>>>(p);
+    CHMY_CUDA(cudaGetLastError());
+    ctx->n_launches++;
+    return CHMY_OK;
+}
+
 int chmy_run_fused2d(chmy_ctx* ctx, int kind, const chmy_launch_desc* dp, const chmy_launch_desc* dc, const Box& box,
                      double* const* cur, double* const* shadow, cudaStream_t st) {
+    if (kind == 4) return run_fused_t3(ctx, dp, dc, box, cur, shadow, st);
     if (box.n[0] <= 0 || box.n[1] <= 0) return CHMY_OK;
     f2_env();
     CHMY_REQUIRE((box.lo[0] & 1) == 0, "fused sweep needs an even x origin");

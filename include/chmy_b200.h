@@ -260,7 +260,8 @@ int chmy_set_tuning(int disable_fast_kernels, int force_true_division);
  * (same deferred-launch protocol, same results; bit-exact in the host emulation, not yet run on a GPU):
  *   update_stress! + update_velocity! 2D            stokes_2d_inc_ve_T.jl:146-147   24 -> 18 array passes
  *   compute_q! + update_C!                          diffusion_2d_perf.jl:28-29       7 ->  4
- *   update_thermal_flux! + update_thermal! 2D       stokes_2d_inc_ve_T.jl:151-152    9 ->  7                    */
+ *   update_thermal_flux! + update_thermal! 2D       stokes_2d_inc_ve_T.jl:151-152    9 ->  7
+ *   update_thermal_flux! + update_thermal! 3D       stokes_3d_inc_ve_T.jl:167-168   12 ->  9                    */
 int chmy_set_fusion(chmy_ctx* ctx, int enable);
 int chmy_fused_count(const chmy_ctx* ctx, uint64_t* sweeps);          /* fused sweeps launched so far            */
 /* rows of a CTA (2|4|8|16), CTAs per thread-block cluster along y (1|2|4|8), planes per z-chunk (0 keeps a setting);

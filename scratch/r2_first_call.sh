@@ -36,6 +36,19 @@ PY
   done
 done
 
+echo "== 5b. 3D Stokes + thermal sub-step: tuned thermal pair vs the experimental 3D thermal sweep"
+for fu in 1 3; do
+  timeout 300 python bench.py --workload stokes3d_thermal --fused $fu --steps 20 --warmup 4 --no-e2e --no-cpu-baseline > gpurun_out/r2_stokes3d_thermal_f${fu}.json 2> gpurun_out/r2_stokes3d_thermal_f${fu}.err
+  python - "$fu" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(f"gpurun_out/r2_stokes3d_thermal_f{sys.argv[1]}.json").read().strip().splitlines()[-1])
+    print("stokes3d_thermal --fused", sys.argv[1], round(d["ms_per_step"], 3), "ms", round(d["T_eff_per_gpu"], 1), "GB/s", d["roofline"]["step_kernels_ms"])
+except Exception as e:
+    print("stokes3d_thermal", sys.argv[1], "no line:", e)
+PY
+done
+
 echo "== 6. roofline.traffic of the fused sweep at 767^3 (dram bytes of ONE launch; cold-cache, serialised: shares only)"
 timeout 400 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
     -k regex:k_fused_sv -c 2 --csv --log-file gpurun_out/r2_fused_767_dram_bytes.csv python scratch/run_fused_once.py 767 767 767 2 > gpurun_out/r2_ncu_run.log 2>&1

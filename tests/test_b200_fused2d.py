@@ -122,3 +122,37 @@ def test_deferred_2d_launch_is_flushed_before_it_can_be_observed(ch, oracle):
         a.close()
     _same(outs[1][0], outs[0][0], "q.x")
     _same(outs[1][1], outs[0][1], "C")
+
+
+# ------------------------------------------------------------------------------------------------ 3D thermal pair (kind 4)
+@pytest.mark.parametrize("n,fun,ow,exact", [((70, 37, 9), True, None, False), ((126, 40, 20), False, (16, 8, 4), True),
+                                            ((17, 9, 5), False, None, False), ((130, 24, 11), True, (6, 4, 3), True),
+                                            ((125, 30, 12), False, (8, 4, 3), True)])
+def test_fused_thermal3_equals_two_kernels_and_oracle(ch, oracle, n, fun, ow, exact):
+    """3D Stokes + thermal sub-step with chmy_set_fusion(ctx, 3): the mechanics pair runs as k_fused_sv (measured path) and
+    update_thermal_flux! + update_thermal! as k_fused_t3 (fused_thermal3.cuh; proven by tests/test_fused_emulation_t3.py).
+    Fields and residual histories must be bit-identical to the two-kernel path and agree with the oracle's driver."""
+    from chmy_b200 import drivers as BD
+    import drivers as OD
+    res, hist = [], []
+    for mode in (3, 0):
+        a = ch.Arch(ch.B200Backend())
+        ch.set_fusion(a, mode)
+        s = BD.Stokes(a, n, rho_g_function=fun, outer_width=ow, exact_split=exact)
+        hist.append(s.run(2, 10, 5, eps=0.0))
+        if mode:
+            # 20 mechanics sweeps + 10 thermal sweeps (it = 2); odd literal splits take the two-kernel path
+            assert ch.fused_count(a) == (0 if _odd(n, ow, exact) else 20 + 10), ch.fused_count(a)
+        res.append({k: f.parent() for k, f in s.fields().items()})
+        a.close()
+    assert hist[0] == hist[1]
+    for k in res[0]:
+        _same(res[1][k], res[0][k], k)
+    o = OD.Stokes(n, rho_g_function=fun, outer_width=ow)
+    ho = o.run(2, 10, 5, eps=0.0)
+    assert len(ho) == len(hist[0])
+    for x, y in zip(ho, hist[0]):
+        assert x[:2] == y[:2] and np.allclose(x[2:], y[2:], rtol=1e-12, atol=0.0)
+    for k, f in o.fields().items():
+        err = float(np.abs(f.data - res[0][k]).max() / max(np.abs(f.data).max(), 1e-300))
+        assert err <= 1e-12, (k, err)
