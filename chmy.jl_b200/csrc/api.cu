@@ -465,6 +465,23 @@ extern "C" int chmy_bc(chmy_ctx* ctx, const chmy_grid_desc* g, const chmy_batch_
     return CHMY_OK;
 }
 
+// Split policy of launches that carry an exchange: 1 (default) = inner region on the main stream overlapped with slabs +
+// batches on the boundary stream, as the reference does; 0 = one full-range kernel followed by the batches on one stream
+// (outer_width is a hint: results cannot depend on it).  Over NVLink a halo exchange costs tens of microseconds against
+// ~20 ms of compute at the headline size, so the unsplit order may win; round 2 measures it (bench.py --no-split).
+static int g_split_policy = -1;
+static int split_policy() {
+    if (g_split_policy < 0) {
+        const char* e = getenv("CHMY_SPLIT");
+        g_split_policy = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_split_policy;
+}
+extern "C" int chmy_set_launch_tuning(int split_launches) {
+    if (split_launches >= 0) g_split_policy = split_launches ? 1 : 0;
+    return CHMY_OK;
+}
+
 // Region orchestration of `launch` (KernelLaunch.jl:105-183); RUN(box, stream) executes the op on one region.
 // pref: slab widths the op's kernel prefers (outer_width is a hint unless EXACT_SPLIT), or nullptr
 template <class RUN>
@@ -490,6 +507,7 @@ static int orchestrate(chmy_ctx* ctx, const chmy_launch_desc* d, const RUN& run,
             // outer_width is a scheduling hint (results do not depend on it, the ops are pointwise): without a
             // neighbour to talk to there is nothing to overlap, so run one full-range kernel.
             if (!any_ex && !(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) split = false;
+            if (!split_policy() && !(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) split = false;
         }
         if (!split) {   // KernelLaunch.jl:156-159
             CHMY_TRY(run(full, ctx->s_main));

@@ -246,6 +246,10 @@ int chmy_selftest_division(chmy_ctx* ctx, double c, long long n, unsigned long l
 /* -1 keeps a setting.  disable_fast_kernels: run every op with the generic one-thread-per-cell kernels (A/B
  * parity of the tuned kernels); force_true_division: div.rn.f64 everywhere.  Env: CHMY_NO_FAST=1, CHMY_TRUE_DIV=1. */
 int chmy_set_tuning(int disable_fast_kernels, int force_true_division);
+/* -1 keeps.  split_launches: 1 (default) = launches that carry an exchange overlap their inner region with the slabs +
+ * batches on the boundary stream (KernelLaunch.jl:160-181); 0 = one full-range kernel, then the batches (outer_width is
+ * a hint; results are identical).  Env: CHMY_SPLIT=0. */
+int chmy_set_launch_tuning(int split_launches);
 
 /* ---- lazily fused update_stress! -> update_velocity! (cross-launch fusion) -----------------
  * The reference runs the two kernels of a PT iteration as two `launch` calls (stokes_3d_inc_ve_T.jl:163-165); the

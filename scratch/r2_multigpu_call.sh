@@ -1,0 +1,22 @@
+#!/bin/bash
+# Round 2, multi-GPU call (N = 2 first, then 8):  /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'bash scratch/r2_multigpu_call.sh 2'
+# A/B of the split policy on connected ranks: overlapped inner + slabs (the reference's order, 94.7 % weak-scaling
+# efficiency in round 1) vs one full-range sweep followed by the batches / exchange (bench.py --no-split).
+N=${1:-2}
+mkdir -p gpurun_out
+set +e
+for mode in split nosplit; do
+  flag=""; [ "$mode" = nosplit ] && flag="--no-split"
+  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+      bench.py --gpus $N --steps 30 --warmup 5 --no-e2e $flag > gpurun_out/r2_bench_${N}gpu_${mode}.json 2> gpurun_out/r2_bench_${N}gpu_${mode}.err
+  python - "$N" "$mode" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(f"gpurun_out/r2_bench_{sys.argv[1]}gpu_{sys.argv[2]}.json").read().strip().splitlines()[-1])
+    print(sys.argv[1], "GPUs", sys.argv[2], round(d["ms_per_step"], 3), "ms/iter", round(d["T_eff_per_gpu"], 1), "GB/s/GPU", d["config"]["proc_dims"])
+except Exception as e:
+    print(sys.argv[1], sys.argv[2], "no line:", e)
+    print(open(f"gpurun_out/r2_bench_{sys.argv[1]}gpu_{sys.argv[2]}.err").read()[-1500:])
+PY
+done
+CHMY_SPLIT=0 timeout 400 python -m pytest tests/test_z_b200_multigpu.py -x -q -k "${N}gpu" 2>&1 | tail -4
