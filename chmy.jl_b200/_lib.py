@@ -93,6 +93,7 @@ SYMBOLS = {
     "chmy_barrier": (C.c_int, [_vp]),
     "chmy_field_create": (C.c_int, [_vp, C.c_int, _i64p, _i32p, C.c_int, _P(_vp)]),
     "chmy_field_create_typed": (C.c_int, [_vp, C.c_int, _i64p, _i32p, C.c_int, C.c_int, _P(_vp)]),
+    "chmy_field_create_shell": (C.c_int, [C.c_int, _i64p, _i32p, C.c_int, C.c_int, _P(_vp)]),
     "chmy_field_destroy": (C.c_int, [_vp]),
     "chmy_field_get_info": (C.c_int, [_vp, _P(FieldInfo)]),
     "chmy_field_fill": (C.c_int, [_vp, _vp, C.c_double, _i64p, _i64p]),
@@ -104,6 +105,7 @@ SYMBOLS = {
     "chmy_host_alloc": (C.c_int, [_vp, C.c_size_t, _P(_vp)]),
     "chmy_host_free": (C.c_int, [_vp, _vp]),
     "chmy_launch": (C.c_int, [_vp, _P(LaunchDesc)]),
+    "chmy_validate_launch": (C.c_int, [_P(LaunchDesc)]),
     "chmy_bc": (C.c_int, [_vp, _P(GridDesc), _P(BatchDesc * 2), C.c_int]),
     "chmy_exchange_halo": (C.c_int, [_vp, _P(GridDesc), C.c_int, C.c_int, C.c_int, _P(_vp), C.c_int]),
     "chmy_exchange_halo_all": (C.c_int, [_vp, _P(GridDesc), C.c_int, _P(_vp), C.c_int]),

@@ -180,9 +180,9 @@ extern "C" int chmy_field_create(chmy_ctx* ctx, int ndims, const int64_t* dims, 
     return chmy_field_create_typed(ctx, ndims, dims, loc, layout, CHMY_F64, out);
 }
 
-extern "C" int chmy_field_create_typed(chmy_ctx* ctx, int ndims, const int64_t* dims, const int32_t* loc, int layout,
-                                       int dtype, chmy_field** out) {
-    CHMY_REQUIRE(ctx && dims && loc && out, "NULL argument");
+// validates the description and computes the storage layout; no device storage yet
+static int field_describe(int ndims, const int64_t* dims, const int32_t* loc, int layout, int dtype, chmy_field** out) {
+    CHMY_REQUIRE(dims && loc && out, "NULL argument");
     CHMY_REQUIRE(ndims >= 1 && ndims <= 3, "ndims %d not in 1..3", ndims);
     CHMY_REQUIRE(layout == CHMY_LAYOUT_PITCHED || layout == CHMY_LAYOUT_DENSE, "bad layout %d", layout);
     CHMY_REQUIRE(dtype == CHMY_F64 || dtype == CHMY_F32, "bad element type %d", dtype);
@@ -192,7 +192,7 @@ extern "C" int chmy_field_create_typed(chmy_ctx* ctx, int ndims, const int64_t* 
     }
     chmy_field* f = (chmy_field*)calloc(1, sizeof(chmy_field));
     if (!f) { chmy_set_error("out of host memory"); return CHMY_ERR_NOMEM; }
-    f->ctx = ctx; f->nd = ndims; f->layout = layout;
+    f->nd = ndims; f->layout = layout;
     f->dtype = dtype; f->esize = dtype == CHMY_F32 ? 4 : 8;
     for (int a = 0; a < 3; ++a) {
         if (a < ndims) {
@@ -211,19 +211,41 @@ extern "C" int chmy_field_create_typed(chmy_ctx* ctx, int ndims, const int64_t* 
     f->stride[2] = pitch * f->sd[1];
     const long long elems = f->lead + pitch * f->sd[1] * f->sd[2] + 2 * per128;
     f->bytes = (size_t)elems * (size_t)f->esize;
-    CHMY_CUDA(cudaSetDevice(ctx->device));
-    cudaError_t e = cudaMalloc(&f->alloc, f->bytes);
+    *out = f;
+    return CHMY_OK;
+}
+
+extern "C" int chmy_field_create_typed(chmy_ctx* ctx, int ndims, const int64_t* dims, const int32_t* loc, int layout,
+                                       int dtype, chmy_field** out) {
+    CHMY_REQUIRE(ctx && out, "NULL argument");
+    *out = nullptr;
+    chmy_field* f = nullptr;
+    CHMY_TRY(field_describe(ndims, dims, loc, layout, dtype, &f));
+    f->ctx = ctx;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess) e = cudaMalloc(&f->alloc, f->bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->alloc, 0, f->bytes, ctx->s_main);   // KernelAbstractions.zeros, field.jl:59
     if (e != cudaSuccess) {
-        free(f);
         (void)cudaGetLastError();
-        chmy_set_error("cudaMalloc of %zu bytes failed: %s", (size_t)elems * (size_t)(dtype == CHMY_F32 ? 4 : 8), cudaGetErrorString(e));
+        chmy_set_error("allocating a field of %zu bytes failed: %s", f->bytes, cudaGetErrorString(e));
+        if (f->alloc) cudaFree(f->alloc);
+        free(f);
         return CHMY_ERR_NOMEM;
     }
-    CHMY_CUDA(cudaMemsetAsync(f->alloc, 0, f->bytes, ctx->s_main));   // KernelAbstractions.zeros, field.jl:59
     f->p0 = reinterpret_cast<double*>(reinterpret_cast<char*>(f->alloc) + (size_t)f->esize *
                 (size_t)(f->lead + 1 + (ndims > 1 ? f->stride[1] : 0) + (ndims > 2 ? f->stride[2] : 0)));
     *out = f;
     return CHMY_OK;
+}
+
+// Descriptor-only field: location, sizes, layout and element type, but no device storage.  chmy_validate_launch accepts
+// it; every entry point that would touch storage refuses it.  Lets a binding (and the CPU test-suite) check the
+// flattening of `op => args` against the library's own argument rules without a GPU.
+extern "C" int chmy_field_create_shell(int ndims, const int64_t* dims, const int32_t* loc, int layout, int dtype,
+                                       chmy_field** out) {
+    CHMY_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    return field_describe(ndims, dims, loc, layout, dtype, out);
 }
 
 extern "C" int chmy_field_destroy(chmy_field* f) {
@@ -234,7 +256,7 @@ extern "C" int chmy_field_destroy(chmy_field* f) {
         cudaStreamSynchronize(f->ctx->s_bnd);
         cudaStreamSynchronize(f->ctx->s_main);
     }
-    cudaFree(f->alloc);
+    if (f->alloc) cudaFree(f->alloc);
     if (f->alt_alloc) cudaFree(f->alt_alloc);
     free(f);
     return CHMY_OK;
@@ -245,8 +267,10 @@ extern "C" int chmy_field_get_info(const chmy_field* f, chmy_field_info* out) {
     memset(out, 0, sizeof(*out));
     out->ndims = f->nd; out->layout = f->layout;
     for (int a = 0; a < 3; ++a) { out->loc[a] = f->loc[a]; out->dims[a] = f->d[a]; out->stride[a] = f->stride[a]; }
-    out->origin_ptr = (void*)f->at_bytes(1, f->nd > 1 ? 1 : 0, f->nd > 2 ? 1 : 0);
-    out->base_ptr   = (void*)f->at_bytes(-1, f->nd > 1 ? -1 : 0, f->nd > 2 ? -1 : 0);
+    if (f->alloc) {        // a descriptor-only field has no addresses
+        out->origin_ptr = (void*)f->at_bytes(1, f->nd > 1 ? 1 : 0, f->nd > 2 ? 1 : 0);
+        out->base_ptr   = (void*)f->at_bytes(-1, f->nd > 1 ? -1 : 0, f->nd > 2 ? -1 : 0);
+    }
     out->bytes      = f->bytes;
     out->dtype      = f->dtype;
     return CHMY_OK;
@@ -648,12 +672,29 @@ static int run_fused2d(chmy_ctx* ctx, int kind, const chmy_launch_desc* dp, cons
     return orchestrate(ctx, dc, [&](const Box& b, cudaStream_t st) { return chmy_run_fused2d(ctx, kind, dp, dc, b, cur, shadow, st); }, pref);
 }
 
+// The argument checks of chmy_launch, without a device (fields may be descriptor-only, chmy_field_create_shell).
+extern "C" int chmy_validate_launch(const chmy_launch_desc* d) {
+    CHMY_REQUIRE(d != nullptr, "NULL argument");
+    CHMY_TRY(validate_grid(&d->grid));
+    CHMY_REQUIRE(d->nfields >= 0 && d->nfields <= CHMY_MAX_OP_FIELDS && d->nscalars >= 0 && d->nscalars <= CHMY_MAX_SCALARS,
+                 "bad field / scalar count");
+    CHMY_TRY(chmy_validate_op(d));
+    CHMY_REQUIRE(d->op != CHMY_OP_NONE, "chmy_launch needs an op (use chmy_bc for a bare batch set)");
+    if (d->has_bc) {
+        bool any_ex = false;
+        CHMY_TRY(validate_batches(&d->grid, d->bc, &any_ex));
+    }
+    if (d->has_outer_width)
+        for (int a = 0; a < d->grid.ndims; ++a) CHMY_REQUIRE(d->outer_width[a] >= 0, "negative outer_width");
+    return CHMY_OK;
+}
+
 extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
     CHMY_REQUIRE(ctx && d, "NULL argument");
     const chmy_grid_desc* g = &d->grid;
-    CHMY_TRY(validate_grid(g));
-    CHMY_TRY(chmy_validate_op(d));
-    CHMY_REQUIRE(d->op != CHMY_OP_NONE, "chmy_launch needs an op (use chmy_bc for a bare batch set)");
+    CHMY_TRY(chmy_validate_launch(d));
+    for (int q = 0; q < d->nfields; ++q)
+        CHMY_REQUIRE(!d->fields[q] || d->fields[q]->alloc, "field %d is descriptor-only (chmy_field_create_shell): it has no storage", q);
     CHMY_CUDA(cudaSetDevice(ctx->device));
     // a literal split (EXACT_SPLIT) whose x slabs do not start on even indices cannot feed the sweep's aligned cell pairs
     const bool odd_exact_split = (d->flags & CHMY_LAUNCH_EXACT_SPLIT) && d->has_bc && d->has_outer_width &&

@@ -81,7 +81,7 @@ static int run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chm
                      bd->nfields, CHMY_MAX_BATCH_FIELDS);
         for (int q = 0; q < bd->nfields; ++q) {
             const chmy_field* f = bd->fields[q];
-            CHMY_REQUIRE(f != nullptr && f->nd == g->ndims, "FieldBatch: bad field %d", q);
+            CHMY_REQUIRE(f != nullptr && f->alloc != nullptr && f->nd == g->ndims, "FieldBatch: bad field %d", q);
             CHMY_REQUIRE(f->dtype == dtype, "FieldBatch: the fields of one dimension's batches must share an element type");
             CHMY_REQUIRE(bd->bc_kind[q] == CHMY_DIRICHLET || bd->bc_kind[q] == CHMY_NEUMANN, "FieldBatch: bad bc kind");
             for (int a = 0; a < g->ndims; ++a)
@@ -178,7 +178,7 @@ static int make_slab_batch(int dim, int side, int nf, chmy_field* const* fs, boo
     long long off = 0;
     for (int q = 0; q < nf; ++q) {
         const chmy_field* f = fs[q];
-        CHMY_REQUIRE(f != nullptr && dim < f->nd, "exchange: bad field %d", q);
+        CHMY_REQUIRE(f != nullptr && f->alloc != nullptr && dim < f->nd, "exchange: bad field %d", q);
         const int ov = f->loc[dim] == CHMY_VERTEX ? 1 : 0;
         SlabEntry<T>& e = b.e[q];
         e.f   = f->viewT<T>();
@@ -261,6 +261,7 @@ static int launch_util(chmy_ctx* ctx, const F& f, const Box& b, cudaStream_t st)
 }
 
 int chmy_box_from(const chmy_field* f, const int64_t* lo, const int64_t* hi, Box* out) {
+    CHMY_REQUIRE(f->alloc != nullptr, "the field is descriptor-only (chmy_field_create_shell): it has no storage");
     for (int a = 0; a < 3; ++a) {
         if (a < f->nd) {
             CHMY_REQUIRE(lo[a] >= -1 && hi[a] <= f->d[a] + 2, "box [%lld,%lld] outside the padded field along dim %d",

@@ -38,6 +38,23 @@ class Field(AbstractField):
                                                 layout, L.F32 if self.dtype == np.float32 else L.F64, C.byref(h)))
         self._h = h
 
+    @classmethod
+    def shell(cls, grid: StructuredGrid, loc=None, dtype=None, *, layout: int = L.LAYOUT_PITCHED) -> "Field":
+        """Descriptor-only Field (chmy_field_create_shell): location, sizes, layout and element type without an
+        architecture or device storage.  Good for `Launcher.validate` -- checking `op => args` against the library's
+        argument rules on a machine without a GPU -- and refused by everything that touches storage."""
+        self = cls.__new__(cls)
+        loc = Center() if loc is None else loc
+        self.arch, self.grid = None, grid
+        self.dtype = np.dtype(grid.eltype() if dtype is None else dtype)
+        self.loc = expand_loc(grid.ndims(), loc)
+        self.dims = grid.size(self.loc)
+        h = C.c_void_p()
+        L.check(L.lib().chmy_field_create_shell(len(self.dims), L.i64x3(self.dims, 1), L.i32x3([l.code for l in self.loc]),
+                                                layout, L.F32 if self.dtype == np.float32 else L.F64, C.byref(h)))
+        self._h = h
+        return self
+
     # ------------------------------------------------------------------ handles
     @property
     def handle(self):

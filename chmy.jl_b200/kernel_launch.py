@@ -33,6 +33,17 @@ class Launcher:
 
     def __call__(self, arch, grid: StructuredGrid, kernel_and_args, *, bc=None):
         """launcher(arch, grid, op => args; bc) -- KernelLaunch.jl:105-119."""
+        d = self.describe(arch, grid, kernel_and_args, bc=bc)
+        L.check(L.lib().chmy_launch(arch.ctx, C.byref(d)))
+
+    def validate(self, grid: StructuredGrid, kernel_and_args, *, bc=None, arch=None):
+        """Run chmy_launch's argument checks only (chmy_validate_launch): op id, field count / order / staggered locations
+        / sizes / element types, batches.  Needs no device; fields may be `Field.shell`s."""
+        d = self.describe(arch, grid, kernel_and_args, bc=bc)
+        L.check(L.lib().chmy_validate_launch(C.byref(d)))
+
+    def describe(self, arch, grid: StructuredGrid, kernel_and_args, *, bc=None) -> L.LaunchDesc:
+        """Flatten `op => args` (+ bc, outer_width) into the POD chmy_launch_desc."""
         op, args = kernel_and_args
         if not isinstance(op, KernelOp):
             raise TypeError("the B200 path runs the named kernels of chmy_b200.ops, not arbitrary closures")
@@ -60,7 +71,7 @@ class Launcher:
             d.has_outer_width = 1
             for a, w in enumerate(self.outer_width_):
                 d.outer_width[a] = w
-        L.check(L.lib().chmy_launch(arch.ctx, C.byref(d)))
+        return d
 
 
 def worksize(l: Launcher):

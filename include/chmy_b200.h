@@ -208,6 +208,10 @@ int chmy_field_create(chmy_ctx* ctx, int ndims, const int64_t* dims, const int32
                       chmy_field** out);                              /* zero-initialised                  */
 int chmy_field_create_typed(chmy_ctx* ctx, int ndims, const int64_t* dims, const int32_t* loc, int layout, int dtype,
                             chmy_field** out);                        /* Field(backend, grid, loc, T) field.jl:56 */
+/* Descriptor-only field (no context, no device storage): accepted by chmy_validate_launch and chmy_field_get_info /
+ * chmy_halo_slab_len, refused by everything that would touch storage.  Lets a binding check its flattening of
+ * `op => args` against the library's own rules on a machine without a GPU. */
+int chmy_field_create_shell(int ndims, const int64_t* dims, const int32_t* loc, int layout, int dtype, chmy_field** out);
 int chmy_field_destroy(chmy_field* f);
 int chmy_field_get_info(const chmy_field* f, chmy_field_info* out);
 int chmy_field_fill(chmy_ctx* ctx, chmy_field* f, double value, const int64_t* lo, const int64_t* hi);
@@ -230,6 +234,9 @@ int chmy_host_free(chmy_ctx* ctx, void* p);
 
 /* ---- the hot entry points ----------------------------------------------------------------------------- */
 int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* desc);           /* src/KernelLaunch.jl:105-119       */
+int chmy_validate_launch(const chmy_launch_desc* desc);                 /* chmy_launch's argument checks only: op id, field
+                                                                           count / order / staggered locations / sizes /
+                                                                           element types, batches; needs no device */
 int chmy_bc(chmy_ctx* ctx, const chmy_grid_desc* grid,                  /* bc!(arch, grid, batchset)         */
             const chmy_batch_desc bc[CHMY_MAX_DIMS][2], int flags);     /*   src/BoundaryConditions/batch.jl:20-29 */
 int chmy_exchange_halo(chmy_ctx* ctx, const chmy_grid_desc* grid, int dim, int side,   /* exchange_halo.jl:13-61 */
