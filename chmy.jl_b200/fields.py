@@ -278,20 +278,55 @@ def TensorField(arch, grid: StructuredGrid, **kw) -> FieldTuple:
 
 
 class FunctionField(AbstractField):
-    """FunctionField(func, grid, loc; parameters) -- function_field.jl:12-43.  Values are computed in-kernel from
-    coordinates; the only body available on the device is `init_incl` (the one the named solvers use)."""
+    """FunctionField(func, grid, loc; discrete=false, parameters) -- function_field.jl:12-59: a field whose value at I is
+    `func(coord(grid, loc, I)..., params...)` (continuous) or `func(grid, loc, I..., params...)` (discrete).
+
+    A closure cannot cross the C ABI.  The drivers' `init_incl` (the one body the named solvers use, mpi_perf.jl:141-142)
+    is evaluated IN-KERNEL from coordinates (chmy_inclusion) and needs no storage; any other function is evaluated on the
+    host at the exact (muladd) coordinates of every index a kernel can read -- 0..d+1 per dim -- and uploaded once into a
+    stored Field that takes the FunctionField's place in the launch (same values, one field of memory)."""
 
     def __init__(self, func, grid: StructuredGrid, loc, *, discrete: bool = False, parameters=None):
-        if discrete or func is not init_incl:
-            raise NotImplementedError("only FunctionField(init_incl, ...; discrete=false) exists on the B200 path")
         self.func = func
         self.grid = grid
         self.loc = expand_loc(grid.ndims(), loc)
-        self.parameters = dict(parameters or {})
+        self.discrete = bool(discrete)
+        self.parameters = dict(parameters) if isinstance(parameters, dict) else parameters
         self.dims = grid.size(self.loc)
+        self._stored = None
+
+    def in_kernel(self) -> bool:
+        return self.func is init_incl and not self.discrete
 
     def inclusion(self) -> L.Inclusion:
-        return _incl_struct(self.grid.ndims(), self.loc, self.parameters)
+        return _incl_struct(self.grid.ndims(), self.loc, self.parameters or {})
+
+    def _params(self):
+        p = self.parameters
+        if p is None:
+            return ()
+        return tuple(p.values()) if isinstance(p, dict) else (tuple(p) if isinstance(p, (tuple, list)) else (p,))
+
+    def values(self) -> np.ndarray:
+        """func at logical indices 0..d+1 of every dim (interior + halo), in eltype(grid)."""
+        from .grids import coord
+        nd, T = self.grid.ndims(), self.grid.eltype()
+        idx = [range(0, d + 2) for d in self.dims]
+        if self.discrete:                                                    # function_field.jl:53-59
+            out = np.empty([d + 2 for d in self.dims], dtype=T, order="F")
+            for I in np.ndindex(*out.shape):
+                out[I] = self.func(self.grid, self.loc, *[int(i) for i in I], *self._params())
+            return out
+        cs = [np.array([self.grid.axes[d].coord(self.loc[d], i) for i in idx[d]], dtype=T) for d in range(nd)]
+        mesh = np.meshgrid(*cs, indexing="ij")                               # function_field.jl:49-51
+        return np.asfortranarray(np.broadcast_to(np.asarray(self.func(*mesh, *self._params()), dtype=T), mesh[0].shape))
+
+    def materialize(self, arch) -> "Field":
+        if self._stored is None or self._stored.arch is not arch:
+            f = Field(arch, self.grid, self.loc)
+            f.from_host(self.values(), [0] * len(self.dims), [d + 1 for d in self.dims])
+            self._stored = f
+        return self._stored
 
 
 def maxabs(f: Field, with_halo: bool = False) -> float:

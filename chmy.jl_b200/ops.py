@@ -44,6 +44,8 @@ def _update_stress(tau, Pr, divV, V, tau_old, eta, eta_ve, G, dt, dtau_Pr, dtau_
 
 
 def _update_velocity(V, r_V, Pr, tau, rhog, eta_ve, nudtau, g):
+    if isinstance(rhog, FunctionField) and not rhog.in_kernel():
+        rhog = rhog.materialize(Pr.arch)          # any other function body: host-evaluated once into a stored Field
     if isinstance(rhog, FunctionField):
         return _t(V) + _t(r_V) + [Pr] + _t(tau) + [None], [eta_ve, nudtau], rhog
     return _t(V) + _t(r_V) + [Pr] + _t(tau) + [rhog], [eta_ve, nudtau], None

@@ -222,3 +222,26 @@ def test_host_api_surface_matches_the_reference_exports():
     db = ch.DoubleBuffer("a", "b")
     ch.swap_(db)
     assert (ch.front(db), ch.back(db)) == ("b", "a")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_function_field_host_values(oracle, dtype):
+    """FunctionField with an arbitrary body (function_field.jl:49-59): the host evaluation that stands in for the in-kernel
+    closure covers every index a kernel can read (0..d+1) at the oracle's coordinates; discrete bodies get (grid, loc, I...)."""
+    import chmy_b200 as ch
+    g = ch.UniformGrid(_FakeArch(), origin=(-1.0, 0.5), extent=(2.0, 1.5), dims=(6, 5), dtype=dtype)
+    og = oracle.Grid((-1.0, 0.5), (2.0, 1.5), (6, 5), dtype=dtype)
+    loc = (ch.Center(), ch.Vertex())
+    ff = ch.FunctionField(lambda x, y, a: a * x + y * y, g, loc, parameters=(3.0,))
+    assert not ff.in_kernel() and ff.dims == (6, 6)
+    v = ff.values()
+    assert v.shape == (8, 8) and v.dtype == dtype and v.flags.f_contiguous
+    for i in (0, 1, 3, 7):
+        for j in (0, 2, 7):
+            x, y = dtype(og.coord(0, 0, i)), dtype(og.coord(1, 1, j))
+            assert v[i, j] == dtype(3.0) * x + y * y
+    dff = ch.FunctionField(lambda grid, l, i, j, s: s * (10 * i + j), g, loc, discrete=True, parameters=(0.5,))
+    w = dff.values()
+    assert w[3, 4] == 0.5 * 34 and w[0, 7] == 0.5 * 7 and w.dtype == dtype
+    inc = ch.FunctionField(ch.init_incl, g, loc, parameters={"x0": 0.0, "y0": 1.0, "r": 0.3, "in": 1.0, "out": 0.0})
+    assert inc.in_kernel() and inc.inclusion().r == 0.3

@@ -370,3 +370,27 @@ def test_f32_fields_are_refused_by_the_solver_ops(ch, arch):
     f64 = ch.Field(arch, ch.UniformGrid(arch, origin=(0.0, 0.0), extent=(1.0, 1.0), dims=(8, 6)), ch.Center())
     with pytest.raises(ch.ChmyError):
         ch.Launcher(arch, g)(arch, g, (ch.lapl_, (C, f64, g)))           # operators need one element type
+
+
+# ------------------------------------------------------------------------------------------------ FunctionField, any body
+@pytest.mark.parametrize("n", [(24, 18), (14, 10, 8)])
+def test_function_field_with_an_arbitrary_body(ch, arch, oracle, n):
+    """function_field.jl:49-59 with a body other than the drivers' init_incl: update_velocity! with
+    rho_g = FunctionField(f, grid, loc; parameters) must equal the oracle run with a stored field holding f at the
+    coordinates of every index the kernel reads (the reference evaluates f in-kernel at those coordinates)."""
+    o, nd = oracle, len(n)
+    og, bg = mk_grids(ch, o, arch, n)
+    rng = np.random.default_rng(12)
+    rl = tuple(1 if d == nd - 1 else 0 for d in range(nd))
+    body = (lambda x, y, a: a * x - y * y) if nd == 2 else (lambda x, y, z, a: a * x - y * y + 0.5 * z)
+    ff = ch.FunctionField(body, bg, bloc(ch, rl), parameters=(0.75,))
+    rho_o = o.Field(og, rl)
+    rho_o.data[tuple(slice(1, -1) for _ in n)] = ff.values()                  # logical 0..d+1
+    Vo, rVo, tauo, Pro = o.VectorField(og), o.VectorField(og), o.TensorField(og), o.Field(og, 0)
+    Vb, rVb, taub, Prb = ch.VectorField(arch, bg), ch.VectorField(arch, bg), ch.TensorField(arch, bg), ch.Field(arch, bg)
+    for fo, fb in list(zip(Vo.values(), Vb)) + list(zip(rVo.values(), rVb)) + list(zip(tauo.values(), taub)) + [(Pro, Prb)]:
+        fill_pair(rng, fo, fb)
+    o.launch(o.Launcher(og), og, o.update_velocity, (Vo, rVo, Pro, tauo, rho_o, 0.737, 0.00931))
+    ch.Launcher(arch, bg)(arch, bg, (ch.update_velocity_, (Vb, rVb, Prb, taub, ff, 0.737, 0.00931, bg)))
+    for fo, fb in list(zip(Vo.values(), Vb)) + list(zip(rVo.values(), rVb)):
+        assert_same(fo, fb, "update_velocity!(FunctionField with an arbitrary body)")
