@@ -1,5 +1,29 @@
 """Shared helpers of the parity tests: seeded inputs pushed identically into the oracle and the CUDA path."""
+import ctypes
+import glob
+import os
+import subprocess
+
 import numpy as np
+
+_EMUL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
+_CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "chmy.jl_b200", "csrc")
+
+
+def build_emul(name):
+    """Compile tests/emul/<name>.cpp (a host emulation of a kernel: it #includes the kernel's own .cuh) and load it.
+    CHMY_EMUL_SANITIZE=1 builds with AddressSanitizer + UBSan instead (tests/test_emulation_sanitizers.py runs the
+    emulation suites that way, in a child process that preloads the sanitizer runtimes): every load / store of the
+    kernels' phase functions is then checked against the bounds of the PITCHED arrays the tests hand them."""
+    san = os.environ.get("CHMY_EMUL_SANITIZE", "0") == "1"
+    src = os.path.join(_EMUL, name + ".cpp")
+    lib = os.path.join(_EMUL, f"lib{name}{'_san' if san else ''}.so")
+    deps = [src] + glob.glob(os.path.join(_CSRC, "*.cuh"))
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
+        flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"] if san else ["-O2"]
+        subprocess.check_call(["g++"] + flags + ["-ffp-contract=off", "-march=x86-64-v3", "-shared", "-fPIC", "-Wall",
+                                                 "-Wno-unknown-pragmas", "-Wno-unused-function", "-o", lib, src])
+    return ctypes.CDLL(lib)
 
 
 def fill_pair(rng, of, bf, scale=1.0):

@@ -24,10 +24,8 @@ HDR = os.path.join(HERE, "..", "chmy.jl_b200", "csrc", "fused_sv.cuh")
 
 @pytest.fixture(scope="module")
 def emul():
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
-        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-march=x86-64-v3", "-shared", "-fPIC", "-Wall",
-                               "-Wno-unknown-pragmas", "-o", LIB, SRC])
-    lib = C.CDLL(LIB)
+    from helpers import build_emul
+    lib = build_emul("fused_emul")
     lib.fused_emul_run.restype = C.c_int
     return lib
 

@@ -23,10 +23,8 @@ HDRS = [os.path.join(HERE, "..", "chmy.jl_b200", "csrc", h) for h in ("fused_sv.
 
 @pytest.fixture(scope="module")
 def emul2():
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(f) for f in [SRC] + HDRS):
-        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-march=x86-64-v3", "-shared", "-fPIC", "-Wall",
-                               "-Wno-unknown-pragmas", "-o", LIB, SRC])
-    lib = C.CDLL(LIB)
+    from helpers import build_emul
+    lib = build_emul("fused_emul2d")
     lib.fused_emul2d_run.restype = C.c_int
     lib.fused_emul2d_pair_run.restype = C.c_int
     return lib

@@ -24,10 +24,8 @@ HDRS = [os.path.join(HERE, "..", "chmy.jl_b200", "csrc", h) for h in ("fused_the
 
 @pytest.fixture(scope="module")
 def emul3():
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(f) for f in [SRC] + HDRS):
-        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-march=x86-64-v3", "-shared", "-fPIC", "-Wall",
-                               "-Wno-unknown-pragmas", "-Wno-unused-function", "-o", LIB, SRC])
-    lib = C.CDLL(LIB)
+    from helpers import build_emul
+    lib = build_emul("fused_emul_t3")
     lib.fused_emul_t3_run.restype = C.c_int
     return lib
 

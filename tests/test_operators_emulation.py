@@ -40,10 +40,8 @@ DTYPES = [np.float64, np.float32]            # TEST_TYPES of the reference (test
 
 @pytest.fixture(scope="module")
 def emul():
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
-        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-march=x86-64-v3", "-shared", "-fPIC", "-Wall",
-                               "-Wno-unknown-pragmas", "-o", LIB, SRC])
-    lib = C.CDLL(LIB)
+    from helpers import build_emul
+    lib = build_emul("operators_emul")
     assert lib.operators_emul_sizeof_args(0) == C.sizeof(OprArgs) and lib.operators_emul_sizeof_args(1) == C.sizeof(OprArgsF32)
     return lib
 
