@@ -14,7 +14,9 @@
  * test_boundary_conditions.jl, test_grid_operators.jl, test_interpolations.jl) -- see
  * tests/test_oracle_golden.py.  Halo exchange, Launcher splitting and the example solvers have
  * NO golden vectors in the reference ("parity unpinned" for those rows); they
- * are checked through invariants (split == unsplit, N ranks == 1 rank, pack/unpack round trip).
+ * are checked through invariants (split == unsplit, N ranks == 1 rank, pack/unpack round trip); the solver kernels'
+ * flattened arithmetic is additionally pinned bit-for-bit on a literal transliteration of the reference's kernel source
+ * over the pinned point operators (tests/test_oracle_transliteration.py).
  *
  * Conventions (src/Fields/field.jl:6-22,56-62): a Field of logical size d[] is stored as a dense
  * column-major array of d[]+4 elements per active dimension; logical index I (1-based, as in the
