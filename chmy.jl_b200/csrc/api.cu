@@ -506,6 +506,59 @@ extern "C" int chmy_set_launch_tuning(int split_launches) {
     return CHMY_OK;
 }
 
+// Does a launch with boundary batches split into inner region + slabs, and how wide are the slabs per side?
+// outer_width is a scheduling hint (results cannot depend on it: the ops are pointwise writers): unless EXACT_SPLIT is set
+// the widths follow the kernel's preference `pref` (or nullptr) and the x widths are nudged so that the inner region and
+// the right slab start on even x indices (the tuned kernels own aligned pairs of cells); every cell is still computed
+// exactly once.  Pure function of the descriptor (exported as chmy_launch_split_plan for the CPU tests).
+static int plan_split(const chmy_launch_desc* d, const int* pref, bool* split_out, int wl[3], int wr[3]) {
+    const chmy_grid_desc* g = &d->grid;
+    const int N = g->ndims;
+    int fulln[3];
+    for (int a = 0; a < 3; ++a) fulln[a] = a < N ? (int)g->n[a] + 2 : 1;
+    bool any_ex = false;
+    CHMY_TRY(validate_batches(g, d->bc, &any_ex));
+    bool split = d->has_outer_width != 0;
+    if (split) {
+        for (int a = 0; a < N; ++a) {
+            CHMY_REQUIRE(d->outer_width[a] >= 0, "negative outer_width");
+            // the slabs must contain everything the batches touch: halo, first/last interior and send planes
+            if (d->outer_width[a] < 3 || 2 * d->outer_width[a] > g->n[a] + 2) split = false;
+        }
+        // without a neighbour to talk to there is nothing to overlap, so run one full-range kernel
+        if (!any_ex && !(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) split = false;
+        if (!split_policy() && !(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) split = false;
+    }
+    *split_out = split;
+    for (int a = 0; a < 3; ++a) wl[a] = wr[a] = 0;
+    if (!split) return CHMY_OK;
+    for (int a = 0; a < N; ++a) wl[a] = wr[a] = (int)d->outer_width[a];
+    if (!(d->flags & CHMY_LAUNCH_EXACT_SPLIT) && pref) {
+        for (int a = 0; a < N; ++a)
+            if (pref[a] >= 3 && 2 * pref[a] + 2 <= fulln[a]) wl[a] = wr[a] = pref[a];
+    }
+    if (!(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) {
+        wl[0] += wl[0] & 1;
+        wr[0] -= (fulln[0] - wr[0]) & 1;            // the right slab starts on an even index; never wider than asked
+        if (wr[0] < 3) wr[0] += 2;
+        if (wl[0] + wr[0] > fulln[0]) { wl[0] = (int)d->outer_width[0]; wr[0] = (int)d->outer_width[0]; }
+    }
+    return CHMY_OK;
+}
+
+extern "C" int chmy_launch_split_plan(const chmy_launch_desc* d, const int32_t* pref, int32_t* split, int32_t wl[3], int32_t wr[3]) {
+    CHMY_REQUIRE(d && split && wl && wr, "NULL argument");
+    CHMY_TRY(validate_grid(&d->grid));
+    CHMY_REQUIRE(d->has_bc, "a launch without bc is one full-range kernel (KernelLaunch.jl:121-126)");
+    bool s = false;
+    int l[3], r[3], p[3] = {0, 0, 0};
+    if (pref) for (int a = 0; a < 3; ++a) p[a] = pref[a];
+    CHMY_TRY(plan_split(d, pref ? p : nullptr, &s, l, r));
+    *split = s ? 1 : 0;
+    for (int a = 0; a < 3; ++a) { wl[a] = l[a]; wr[a] = r[a]; }
+    return CHMY_OK;
+}
+
 // Region orchestration of `launch` (KernelLaunch.jl:105-183); RUN(box, stream) executes the op on one region.
 // pref: slab widths the op's kernel prefers (outer_width is a hint unless EXACT_SPLIT), or nullptr
 template <class RUN>
@@ -519,39 +572,13 @@ static int orchestrate(chmy_ctx* ctx, const chmy_launch_desc* d, const RUN& run,
     if (!d->has_bc) {   // launch_without_bc: one full-range kernel even when the Launcher has an outer_width (:121-126)
         CHMY_TRY(run(full, ctx->s_main));
     } else {
-        bool any_ex = false;
-        CHMY_TRY(validate_batches(g, d->bc, &any_ex));
-        bool split = d->has_outer_width != 0;
-        if (split) {
-            for (int a = 0; a < N; ++a) {
-                CHMY_REQUIRE(d->outer_width[a] >= 0, "negative outer_width");
-                // the slabs must contain everything the batches touch: halo, first/last interior and send planes
-                if (d->outer_width[a] < 3 || 2 * d->outer_width[a] > g->n[a] + 2) split = false;
-            }
-            // outer_width is a scheduling hint (results do not depend on it, the ops are pointwise): without a
-            // neighbour to talk to there is nothing to overlap, so run one full-range kernel.
-            if (!any_ex && !(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) split = false;
-            if (!split_policy() && !(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) split = false;
-        }
+        bool split = false;
+        int wl[3] = {0, 0, 0}, wr[3] = {0, 0, 0};
+        CHMY_TRY(plan_split(d, pref, &split, wl, wr));
         if (!split) {   // KernelLaunch.jl:156-159
             CHMY_TRY(run(full, ctx->s_main));
             for (int D = N - 1; D >= 0; --D) CHMY_TRY(bc_dim(ctx, g, D, &d->bc[D][0], &d->bc[D][1], ctx->s_main));
         } else {        // KernelLaunch.jl:160-181: inner region on the main stream, slabs + batches on the boundary stream
-            // Slab widths per side.  outer_width is a hint (see above): unless EXACT_SPLIT is set the x widths are
-            // nudged so that the inner region and the right slab start on even x indices (the tuned kernels own
-            // aligned pairs of cells); every cell is still computed exactly once.
-            int wl[3] = {0, 0, 0}, wr[3] = {0, 0, 0};
-            for (int a = 0; a < N; ++a) wl[a] = wr[a] = (int)d->outer_width[a];
-            if (!(d->flags & CHMY_LAUNCH_EXACT_SPLIT) && pref) {
-                for (int a = 0; a < N; ++a)
-                    if (pref[a] >= 3 && 2 * pref[a] + 2 <= full.n[a]) wl[a] = wr[a] = pref[a];
-            }
-            if (!(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) {
-                wl[0] += wl[0] & 1;
-                wr[0] -= (full.n[0] - wr[0]) & 1;           // the right slab starts on an even index; never wider than asked
-                if (wr[0] < 3) wr[0] += 2;
-                if (wl[0] + wr[0] > full.n[0]) { wl[0] = (int)d->outer_width[0]; wr[0] = (int)d->outer_width[0]; }
-            }
             CHMY_CUDA(cudaEventRecord(ctx->ev_fork, ctx->s_main));
             CHMY_CUDA(cudaStreamWaitEvent(ctx->s_bnd, ctx->ev_fork, 0));
             for (int D = N - 1; D >= 0; --D) {

@@ -257,6 +257,11 @@ int chmy_set_tuning(int disable_fast_kernels, int force_true_division);
  * batches on the boundary stream (KernelLaunch.jl:160-181); 0 = one full-range kernel, then the batches (outer_width is
  * a hint; results are identical).  Env: CHMY_SPLIT=0. */
 int chmy_set_launch_tuning(int split_launches);
+/* The split decision of a launch with boundary batches, without launching: *split = 0 -> one full-range kernel followed by
+ * the batches; 1 -> inner region [wl, n+2-wr) per dim on the main stream and, for D = N..1, the two slabs of widths
+ * wl[D] / wr[D] on the boundary stream (KernelLaunch.jl:63-87 with outer_width replaced by wl / wr).  pref: the slab widths
+ * the op's kernel prefers ({60, 6, 0} for the fused 3D sweep) or NULL.  Pure function of the descriptor. */
+int chmy_launch_split_plan(const chmy_launch_desc* desc, const int32_t* pref, int32_t* split, int32_t wl[3], int32_t wr[3]);
 
 /* ---- lazily fused update_stress! -> update_velocity! (cross-launch fusion) -----------------
  * The reference runs the two kernels of a PT iteration as two `launch` calls (stokes_3d_inc_ve_T.jl:163-165); the

@@ -1,0 +1,123 @@
+"""
+CPU-only: the split decision of `launch(...; bc)` in the LIBRARY (chmy_launch_split_plan = the function chmy_launch's
+region orchestration calls), for the BASELINE sizes and the slab-width preferences of every kernel family.
+
+  * EXACT_SPLIT: the widths are the Launcher's outer_width, i.e. the regions are literally KernelLaunch.jl:56-87;
+  * hint mode (default on connected ranks): whatever the widths, the inner region and the 2N slabs built from them with
+    the reference's region formulas tile the launch range [0, n+1]^N exactly once, every slab is at least 3 wide (halo,
+    boundary node and send plane of every batch lie inside the slabs, so the batches may run before the inner region has
+    finished), and the inner region and the right x slab start on even x indices (the tuned kernels own aligned pairs);
+  * no neighbour, an outer_width too small / too large, or the no-split policy: one full-range kernel.
+"""
+import ctypes as C
+import itertools
+
+import numpy as np
+import pytest
+
+
+class _NoArch:
+    pass
+
+
+@pytest.fixture(scope="module")
+def ch():
+    import chmy_b200
+    chmy_b200.load_library()
+    return chmy_b200
+
+
+def desc(ch, n, ow, connected, exact=False):
+    """update_thermal!-shaped launch (T Neumann everywhere, exchange T) on a grid whose `connected` sides have neighbours"""
+    from chmy_b200 import _lib as L
+    nd = len(n)
+    topo = tuple(tuple(ch.Connected() if (D, S) in connected else ch.Bounded() for S in range(2)) for D in range(nd))
+    g = ch.UniformGrid(_NoArch(), origin=(0.0,) * nd, extent=(1.0,) * nd, dims=n, topology=topo)
+    T, To = ch.Field.shell(g), ch.Field.shell(g)
+    q = ch.FieldTuple(**{"xyz"[D]: ch.Field.shell(g, ch.vector_location(D + 1, nd)) for D in range(nd)})
+    la = ch.Launcher(_NoArch(), g, outer_width=ow, exact_split=exact)
+    d = la.describe(None, g, (ch.update_thermal_, (T, To, q, 0.1, g)), bc=ch.batch(g, (T, ch.Neumann()), exchange=T))
+    L.check(L.lib().chmy_validate_launch(C.byref(d)))
+    return d, (T, To, q)
+
+
+def plan(ch, d, pref):
+    from chmy_b200 import _lib as L
+    split, wl, wr = C.c_int32(), (C.c_int32 * 3)(), (C.c_int32 * 3)()
+    p = None if pref is None else (C.c_int32 * 3)(*pref)
+    L.check(L.lib().chmy_launch_split_plan(C.byref(d), p, C.byref(split), wl, wr))
+    return bool(split.value), list(wl), list(wr)
+
+
+def regions(n, wl, wr):
+    """KernelLaunch.jl:60-87 with outer_width -> (wl, wr): inner + for D = N..1 the two slabs; boxes as (lo, size)"""
+    N, ws = len(n), [x + 2 for x in n]
+    out = [([wl[a] for a in range(N)], [ws[a] - wl[a] - wr[a] for a in range(N)])]
+    for D in reversed(range(N)):
+        for S in range(2):
+            lo = [0 if a < D else ((0 if S == 0 else ws[a] - wr[a]) if a == D else wl[a]) for a in range(N)]
+            sz = [ws[a] if a < D else ((wl[a] if S == 0 else wr[a]) if a == D else ws[a] - wl[a] - wr[a]) for a in range(N)]
+            out.append((lo, sz))
+    return out
+
+
+def tiles_once(n, regs):
+    """exact cover of [0, n+1]^N, checked per dimension-product without materialising 770^3 cells: total volume equals the
+    range's volume and the boxes are pairwise disjoint"""
+    ws = [x + 2 for x in n]
+    vol = sum(int(np.prod(sz)) for _, sz in regs)
+    if vol != int(np.prod(ws)):
+        return False
+    for (la, sa), (lb, sb) in itertools.combinations(regs, 2):
+        if all(la[a] < lb[a] + sb[a] and lb[a] < la[a] + sa[a] for a in range(len(n))):
+            return False
+    return all(all(l >= 0 and l + s <= w and s > 0 for l, s, w in zip(lo, sz, ws)) for lo, sz in regs)
+
+
+SIZES = [((767, 767, 767), (128, 8, 4)), ((766, 767, 765), (128, 8, 4)), ((8191, 8191), (128, 8)), ((16383, 16383), (128, 8)),
+         ((256, 256), (16, 8)), ((30, 22, 14), (4, 3, 3)), ((125, 64, 20), (9, 4, 3)), ((62, 130), (7, 5))]
+PREFS = [None, (60, 6, 0), (64, 0, 0), (60, 0, 0)]       # generic/tuned, fused 3D sweep, 3D thermal sweep, 2D sweeps
+
+
+@pytest.mark.parametrize("n,ow", SIZES)
+def test_hint_mode_tiles_the_range_with_even_x_starts(ch, n, ow):
+    nd = len(n)
+    for conn in ({(0, 1)}, {(0, 0), (0, 1), (1, 0)}, {(D, S) for D in range(nd) for S in range(2)}):
+        d, keep = desc(ch, n, ow, conn)
+        for pref in PREFS:
+            split, wl, wr = plan(ch, d, pref if pref is None else list(pref)[:3])
+            assert split, (n, ow, conn, pref)
+            wl, wr = wl[:nd], wr[:nd]
+            assert all(w >= 3 for w in wl + wr), (wl, wr)
+            assert wl[0] % 2 == 0 and (n[0] + 2 - wr[0]) % 2 == 0, (wl, wr)
+            assert tiles_once(n, regions(n, wl, wr)), (n, ow, pref, wl, wr)
+            if pref is None:
+                assert all(abs(a - b) <= 1 for a, b in zip(wl, ow)) and all(b - 1 <= a <= b + 2 for a, b in zip(wr, ow))
+
+
+@pytest.mark.parametrize("n,ow", SIZES)
+def test_exact_split_is_the_reference_region_algebra(ch, n, ow):
+    d, keep = desc(ch, n, ow, set(), exact=True)                     # honoured even without a neighbour (tests, A/B)
+    for pref in PREFS:
+        split, wl, wr = plan(ch, d, pref)
+        assert split and wl[:len(n)] == list(ow) and wr[:len(n)] == list(ow)
+        assert tiles_once(n, regions(n, ow, ow))
+
+
+def test_when_there_is_no_split(ch):
+    from chmy_b200 import _lib as L
+    n, ow = (767, 767, 767), (128, 8, 4)
+    assert plan(ch, desc(ch, n, ow, set())[0], (60, 6, 0))[0] is False                 # no neighbour: nothing to overlap
+    assert plan(ch, desc(ch, n, None, {(0, 1)})[0], None)[0] is False                  # Launcher without outer_width
+    assert plan(ch, desc(ch, n, (128, 2, 4), {(0, 1)})[0], None)[0] is False           # a slab thinner than halo+node+send plane
+    assert plan(ch, desc(ch, (30, 22, 14), (17, 8, 4), {(0, 1)})[0], None)[0] is False  # the two x slabs would overlap
+    assert plan(ch, desc(ch, (30, 22, 14), (16, 8, 4), {(0, 1)})[0], None)[0] is True   # they just touch: an empty inner region
+    d, keep = desc(ch, n, ow, {(0, 1)})
+    try:
+        L.check(L.lib().chmy_set_launch_tuning(0))                                     # bench.py --no-split
+        assert plan(ch, d, (60, 6, 0))[0] is False
+        de, keep2 = desc(ch, n, ow, {(0, 1)}, exact=True)
+        assert plan(ch, de, None)[0] is True                                           # a literal split stays literal
+    finally:
+        L.check(L.lib().chmy_set_launch_tuning(1))
+    assert plan(ch, d, (60, 6, 0))[0] is True
