@@ -129,6 +129,26 @@ class ClockSampler:
         return out
 
 
+def host_mem_available():
+    """bytes of host memory this process may still take: the smaller of the system's available memory and the cgroup's
+    remaining allowance (a container limit is what an out-of-memory kill enforces).  None if nothing can be read."""
+    vals = []
+    try:
+        import psutil
+        vals.append(int(psutil.virtual_memory().available))
+    except Exception:
+        pass
+    for lim, cur in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                     ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            l = open(lim).read().strip()
+            if l != "max" and int(l) < (1 << 60):
+                vals.append(int(l) - int(open(cur).read().strip()))
+        except Exception:
+            pass
+    return min(vals) if vals else None
+
+
 def a_eff_bytes(workload, n_local):
     return WORKLOADS[workload][1] * 8.0 * float(math.prod(n_local))
 
@@ -347,6 +367,12 @@ def run_b200(args):
                        "read-back per step; fields resident in HBM (host-buffer segment failed, see `host_segment_error`)"}
         views, host_kind, err = None, None, None
         try:
+            # every rank of the node holds its own copy of the state in host memory: refuse rather than push the box into
+            # an out-of-memory kill
+            need = world * sum(8 * int(np.prod(f.dims, dtype=np.int64)) for f in state)
+            avail = host_mem_available()
+            if avail is not None and avail < 1.5 * need:
+                raise MemoryError(f"host-buffer segment needs {need / 1e9:.1f} GB of host memory on this node, {avail / 1e9:.1f} GB available")
             try:
                 views, host_kind = [ch.pinned_array(arch, f.dims) for f in state], "pinned (chmy_host_alloc)"
             except ch.ChmyError:

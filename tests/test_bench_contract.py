@@ -175,3 +175,21 @@ def test_reference_arm_runs_on_the_cpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, env=env, timeout=60)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_host_segment_is_refused_when_host_memory_is_short(monkeypatch):
+    calls = {"h2d": 0, "d2h": 0}
+    ch, real_lib, drivers = _fake_api(3, calls)
+    monkeypatch.setitem(sys.modules, "chmy_b200", ch)
+    monkeypatch.setitem(sys.modules, "chmy_b200._lib", real_lib)
+    monkeypatch.setitem(sys.modules, "chmy_b200.drivers", drivers)
+    for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    bench = _load_bench()
+    monkeypatch.setattr(bench, "host_mem_available", lambda: 1000)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--n", "8", "8", "8", "--steps", "3", "--no-cpu-baseline"])
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        bench.run_b200(bench.parse())
+    j = json.loads(buf.getvalue().strip())
+    assert "host memory" in j["e2e"]["host_segment_error"] and j["e2e"]["value"] > 0 and calls == {"h2d": 0, "d2h": 0}
