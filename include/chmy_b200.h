@@ -17,7 +17,10 @@
  *     drivers.  Fields, set!/copies, maxabs, bc!, halo exchange and the grid operators (CHMY_OP_OPERATOR) exist for
  *     Float32 as well (chmy_field_create_typed), as the reference's tests instantiate them (test/common.jl:9).  Host
  *     buffers of the copy / halo entry points hold elements of the field's type; scalar arguments stay `double` (a
- *     Float32 value converts exactly) and are rounded to the field's type where the reference's would have it.
+ *     Float32 value converts exactly) and are rounded to the field's type where the reference's would have it.  A
+ *     condition value is therefore taken in eltype(field), as the reference's tests pass it (`Dirichlet(T(2.0))`,
+ *     test/test_boundary_conditions.jl:34); a Float64 value given for a Float32 field is rounded first, where Julia would
+ *     promote that one muladd to Float64 and round its result.
  *   - all work is stream-ordered on the context's streams; results are visible to the host after a blocking
  *     launch (CHMY_LAUNCH_BLOCKING, the reference's semantics, KernelLaunch.jl:117), any copy_to_host /
  *     maxabs call, or chmy_synchronize().
