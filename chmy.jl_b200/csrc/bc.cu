@@ -197,8 +197,8 @@ template <bool PACK, class T>
 static int run_slab(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* const* fs, T* dbuf, cudaStream_t st) {
     SlabBatch<T> b;
     for (int q = 0; q < nf; ++q)
-        CHMY_REQUIRE(fs[q] != nullptr && fs[q]->nd >= 2 && fs[q]->nd == fs[0]->nd && fs[q]->dtype == fs[0]->dtype,
-                     "halo exchange needs fields of equal dimensionality >= 2 and one element type on this path");
+        CHMY_REQUIRE(fs[q] != nullptr && fs[q]->nd == fs[0]->nd && fs[q]->dtype == fs[0]->dtype,
+                     "the fields of one halo exchange must share dimensionality and element type");
     CHMY_TRY(make_slab_batch<T>(dim, side, nf, fs, PACK, &b));
     int m0 = 1, m1 = 1;
     for (int q = 0; q < nf; ++q) { m0 = b.e[q].e0 > m0 ? b.e[q].e0 : m0; m1 = b.e[q].e1 > m1 ? b.e[q].e1 : m1; }

@@ -394,3 +394,27 @@ def test_function_field_with_an_arbitrary_body(ch, arch, oracle, n):
     ch.Launcher(arch, bg)(arch, bg, (ch.update_velocity_, (Vb, rVb, Prb, taub, ff, 0.737, 0.00931, bg)))
     for fo, fb in list(zip(Vo.values(), Vb)) + list(zip(rVo.values(), rVb)):
         assert_same(fo, fb, "update_velocity!(FunctionField with an arbitrary body)")
+
+
+# ------------------------------------------------------------------------------------------------ 1D halo slabs
+@pytest.mark.parametrize("loc", [(0,), (1,)])
+def test_halo_pack_unpack_1d(ch, arch, oracle, loc):
+    """communication_views.jl:1-34 on a 1D field: the slab is a single element (send index 1+overlap | d-overlap, recv
+    index 0 | d+1)."""
+    import ctypes as C
+    from chmy_b200 import _lib as L
+    og, bg = mk_grids(ch, oracle, arch, (9,))
+    of, bf = oracle.Field(og, loc), ch.Field(arch, bg, bloc(ch, loc))
+    enc = np.arange(of.data.size, dtype=np.float64) + 1e3
+    of.data[...] = enc
+    bf.from_host(enc, [-1], [of.dims[0] + 2])
+    for S in range(2):
+        ref = oracle.pack_send(of, 0, S)
+        assert ref.size == 1
+        buf = np.empty(1)
+        L.check(L.lib().chmy_halo_pack(arch.ctx, bf.handle, 0, S, buf.ctypes.data_as(C.c_void_p)))
+        assert np.array_equal(buf, ref)
+        msg = -ref
+        oracle.unpack_recv(of, 0, S, msg)
+        L.check(L.lib().chmy_halo_unpack(arch.ctx, bf.handle, 0, S, msg.ctypes.data_as(C.c_void_p)))
+        assert_same(of, bf, f"1D unpack side {S}")
