@@ -219,8 +219,13 @@ def set_(f, *args, discrete: bool = False, parameters=()):
             f.from_host(a, lo, hi)
         return
     grid, fun = args
-    if discrete:
-        raise NotImplementedError("set!(...; discrete=true) needs in-kernel Julia closures: not on this path")
+    params = tuple(parameters.values()) if isinstance(parameters, dict) else tuple(parameters)
+    if discrete:                                                             # field.jl:126-129: fun(grid, loc, I..., params...)
+        vals = np.empty(tuple(f.dims), dtype=f.dtype, order="F")
+        for I in np.ndindex(*vals.shape):
+            vals[I] = fun(grid, f.loc, *[int(i) + 1 for i in I], *params)
+        f.from_host(vals, lo, hi)
+        return
     if fun is init_incl:                                                     # device kernel, bit-identical coords
         inc = _incl_struct(grid.ndims(), f.loc, parameters)
         g = grid.desc()
@@ -230,7 +235,6 @@ def set_(f, *args, discrete: bool = False, parameters=()):
     from .grids import coords
     cs = [coords(grid, f.loc, d + 1) for d in range(grid.ndims())]
     mesh = np.meshgrid(*cs, indexing="ij")
-    params = tuple(parameters.values()) if isinstance(parameters, dict) else tuple(parameters)
     f.from_host(np.asarray(fun(*mesh, *params), dtype=f.dtype), lo, hi)
 
 

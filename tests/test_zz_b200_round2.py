@@ -418,3 +418,21 @@ def test_halo_pack_unpack_1d(ch, arch, oracle, loc):
         oracle.unpack_recv(of, 0, S, msg)
         L.check(L.lib().chmy_halo_unpack(arch.ctx, bf.handle, 0, S, msg.ctypes.data_as(C.c_void_p)))
         assert_same(of, bf, f"1D unpack side {S}")
+
+
+# ------------------------------------------------------------------------------------------------ set!(...; discrete=true)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_set_discrete_known_answers(ch, arch, dtype):
+    """test/test_fields.jl:21-38 (discrete bodies get (grid, loc, ix, iy, iz, params...)) for both element types, `==`."""
+    g = ch.UniformGrid(arch, origin=(0.0, 0.0, 0.0), extent=(1.0, 1.0, 1.0), dims=(2, 2, 2), dtype=dtype)
+    f = ch.Field(arch, g, (ch.Center(), ch.Vertex(), ch.Center()))
+    exp_y = np.zeros((2, 3, 2), dtype); exp_y[:, 1, :], exp_y[:, 2, :] = 0.5, 1.0
+    exp_x = np.zeros((2, 3, 2), dtype); exp_x[0], exp_x[1] = 0.25, 0.75
+    ch.fill_parent_(f, float("nan"))
+    ch.set_(f, g, lambda grid, loc, ix, iy, iz: ch.coord(grid, loc, 2, iy), discrete=True)
+    assert np.array_equal(ch.interior(f), exp_y) and ch.interior(f).dtype == dtype
+    ch.set_(f, g, lambda grid, loc, ix, iy, iz: ch.coord(grid, loc, 1, ix), discrete=True)
+    assert np.array_equal(ch.interior(f), exp_x)
+    ch.set_(f, g, lambda grid, loc, ix, iy, iz, sc: ch.coord(grid, loc, 2, iy) * sc, discrete=True, parameters=(dtype(2.0),))
+    assert np.array_equal(ch.interior(f), 2 * exp_y)
+    assert np.isnan(f.parent()[0]).all()                                # halo / padding untouched
