@@ -333,6 +333,51 @@ class FunctionField(AbstractField):
         return self._stored
 
 
+class ConstantField(AbstractField):
+    """ConstantField{T} (src/Fields/constant_field.jl:1-41): a 0-dimensional field with the same value at every index.
+    As the `rho_g` argument of update_velocity! it travels as a chmy_inclusion whose inside and outside values coincide
+    (evaluated in-kernel, no storage)."""
+
+    def __init__(self, value, dtype=np.float64):
+        self.dtype = np.dtype(dtype)
+        self.value = self.dtype.type(value)
+
+    def size(self):
+        return ()
+
+    def ndims(self):
+        return 0
+
+    def __getitem__(self, I):
+        return self.value
+
+    def inclusion_at(self, grid: StructuredGrid, loc) -> L.Inclusion:
+        s = L.Inclusion()
+        s.active = 1
+        for d, l in enumerate(expand_loc(grid.ndims(), loc)):
+            s.loc[d] = l.code
+            s.c0[d] = 0.0
+        s.r, s.inn, s.out = 0.0, float(self.value), float(self.value)      # sum((x - c0)^2) < 0 never holds -> `out`
+        return s
+
+    def __repr__(self):
+        return f"{type(self).__name__}{{{self.dtype.name}}}({self.value})"
+
+
+class ZeroField(ConstantField):
+    def __init__(self, dtype=np.float64):
+        super().__init__(0.0, dtype)
+
+
+class OneField(ConstantField):
+    def __init__(self, dtype=np.float64):
+        super().__init__(1.0, dtype)
+
+
+class ValueField(ConstantField):
+    pass
+
+
 def maxabs(f: Field, with_halo: bool = False) -> float:
     """maximum(abs.(interior(f))) fused into one reduction kernel (drivers: stokes_3d_inc_ve_T.jl:158,172-175)."""
     lo, hi = f._box(1 if with_halo else 0)

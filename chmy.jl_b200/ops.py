@@ -8,7 +8,7 @@ Argument tuples are exactly the reference's, including the trailing `grid`:
 from __future__ import annotations
 
 from . import _lib as L
-from .fields import Field, FieldTuple, FunctionField
+from .fields import ConstantField, Field, FieldTuple, FunctionField
 
 
 class KernelOp:
@@ -43,7 +43,21 @@ def _update_stress(tau, Pr, divV, V, tau_old, eta, eta_ve, G, dt, dtau_Pr, dtau_
     return _t(tau) + [Pr, divV] + _t(V) + _t(tau_old), [eta, eta_ve, G, dt, dtau_Pr, dtau_r], None
 
 
+class _InclusionOf:
+    """adapter: anything that can hand the launch a chmy_inclusion"""
+
+    def __init__(self, inc):
+        self._inc = inc
+
+    def inclusion(self):
+        return self._inc
+
+
 def _update_velocity(V, r_V, Pr, tau, rhog, eta_ve, nudtau, g):
+    if isinstance(rhog, ConstantField):           # ZeroField / OneField / ValueField: a constant body force
+        N = g.ndims()
+        loc = _t(V)[N - 1].loc                    # rho_g lives where the last velocity component lives
+        return _t(V) + _t(r_V) + [Pr] + _t(tau) + [None], [eta_ve, nudtau], _InclusionOf(rhog.inclusion_at(g, loc))
     if isinstance(rhog, FunctionField) and not rhog.in_kernel():
         rhog = rhog.materialize(Pr.arch)          # any other function body: host-evaluated once into a stored Field
     if isinstance(rhog, FunctionField):

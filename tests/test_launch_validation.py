@@ -147,3 +147,22 @@ def test_descriptor_only_fields_are_refused_by_everything_that_touches_storage(c
                L.lib().chmy_field_maxabs(None, f.handle, lo, hi, C.byref(out))):
         assert rc != 0                       # NULL context / no storage: an error code, never a crash
     f.free()
+
+
+def test_constant_fields(ch):
+    """test/test_fields.jl:56-75, and a ConstantField as the body force of update_velocity! (a chmy_inclusion whose inside
+    and outside values coincide)."""
+    z, o, v = ch.ZeroField(), ch.OneField(), ch.ValueField(2.0)
+    for f, want in ((z, 0.0), (o, 1.0), (v, 2.0)):
+        assert f[1, 1, 1] == want and f[2, 2, 2] == want and f.size() == ()
+    assert ch.ValueField(0.1, np.float32)[3] == np.float32(0.1)
+    for n in ((12, 10), (12, 10, 8)):
+        g = grid(ch, n)
+        nd = len(n)
+        L = ch.Launcher(_NoArch(), g)
+        V, rV, tau, Pr = vec(ch, g), vec(ch, g), ten(ch, g), F(ch, g)
+        d = L.describe(None, g, (ch.update_velocity_, (V, rV, Pr, tau, ch.ValueField(9.81), 0.1, 0.01, g)))
+        assert d.rho_g.active == 1 and d.rho_g.inn == d.rho_g.out == 9.81 and d.rho_g.r == 0.0
+        assert [d.rho_g.loc[a] for a in range(nd)] == [1 if a == nd - 1 else 0 for a in range(nd)]
+        L.validate(g, (ch.update_velocity_, (V, rV, Pr, tau, ch.ValueField(9.81), 0.1, 0.01, g)))
+        L.validate(g, (ch.update_velocity_, (V, rV, Pr, tau, ch.ZeroField(), 0.1, 0.01, g)))

@@ -436,3 +436,23 @@ def test_set_discrete_known_answers(ch, arch, dtype):
     ch.set_(f, g, lambda grid, loc, ix, iy, iz, sc: ch.coord(grid, loc, 2, iy) * sc, discrete=True, parameters=(dtype(2.0),))
     assert np.array_equal(ch.interior(f), 2 * exp_y)
     assert np.isnan(f.parent()[0]).all()                                # halo / padding untouched
+
+
+@pytest.mark.parametrize("n", [(24, 18), (14, 10, 8), (70, 20, 9)])
+def test_constant_field_body_force(ch, arch, oracle, n):
+    """rho_g = ValueField(c) (src/Fields/constant_field.jl): update_velocity! must equal the oracle run with a stored field
+    that holds c everywhere (tuned and generic kernels, FunctionField code path with coinciding in/out values)."""
+    o, nd = oracle, len(n)
+    og, bg = mk_grids(ch, o, arch, n)
+    rng = np.random.default_rng(13)
+    rl = tuple(1 if d == nd - 1 else 0 for d in range(nd))
+    rho_o = o.Field(og, rl)
+    rho_o.data[...] = 0.37
+    Vo, rVo, tauo, Pro = o.VectorField(og), o.VectorField(og), o.TensorField(og), o.Field(og, 0)
+    Vb, rVb, taub, Prb = ch.VectorField(arch, bg), ch.VectorField(arch, bg), ch.TensorField(arch, bg), ch.Field(arch, bg)
+    for fo, fb in list(zip(Vo.values(), Vb)) + list(zip(rVo.values(), rVb)) + list(zip(tauo.values(), taub)) + [(Pro, Prb)]:
+        fill_pair(rng, fo, fb)
+    o.launch(o.Launcher(og), og, o.update_velocity, (Vo, rVo, Pro, tauo, rho_o, 0.737, 0.00931))
+    ch.Launcher(arch, bg)(arch, bg, (ch.update_velocity_, (Vb, rVb, Prb, taub, ch.ValueField(0.37), 0.737, 0.00931, bg)))
+    for fo, fb in list(zip(Vo.values(), Vb)) + list(zip(rVo.values(), rVb)):
+        assert_same(fo, fb, "update_velocity!(ValueField)")
