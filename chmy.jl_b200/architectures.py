@@ -25,7 +25,9 @@ class Architecture:
 class SingleDeviceArchitecture(Architecture):
     """SingleDeviceArchitecture{B,D} (Architectures.jl:21-28): owns the device context and its streams."""
 
-    def __init__(self, backend: B200Backend, device_id: int = 1):
+    def __init__(self, backend, device_id: int = 1):
+        if isinstance(backend, SingleDeviceArchitecture):      # SingleDeviceArchitecture(arch::Architecture), Architectures.jl:30
+            backend, device_id = backend.backend, backend.device_id
         if not isinstance(backend, B200Backend):
             raise TypeError("this path has a single backend: B200Backend()")
         self.backend = backend
@@ -39,6 +41,11 @@ class SingleDeviceArchitecture(Architecture):
         if self._ctx is None:
             raise L.ChmyError("architecture was destroyed")
         return self._ctx
+
+    @property
+    def device(self):
+        """arch.device (Architectures.jl:23): the reference's 1-based device id"""
+        return self.device_id
 
     def close(self):
         if getattr(self, "_ctx", None) is not None:
@@ -72,6 +79,10 @@ class DistributedArchitecture(Architecture):
     def device_id(self):
         return self.child_arch.device_id
 
+    @property
+    def device(self):
+        return self.child_arch.device_id
+
     def close(self):
         self.child_arch.close()
 
@@ -100,8 +111,9 @@ def get_device(arch: Architecture):
 
 def set_device_(arch_or_dev):
     """set_device!(dev) (ext/ChmyCUDAExt/ChmyCUDAExt.jl:15): every C entry point selects its context's device itself
-    (cudaSetDevice at entry), so there is no process-wide current device to switch; kept for source compatibility."""
-    return None
+    (cudaSetDevice at entry), so there is no process-wide current device to switch; returns the device like the
+    reference's method does (test/test_architectures.jl:24)."""
+    return arch_or_dev.device_id if isinstance(arch_or_dev, Architecture) else arch_or_dev
 
 
 def is_gpu_aware(arch) -> bool:

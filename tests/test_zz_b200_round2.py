@@ -456,3 +456,20 @@ def test_constant_field_body_force(ch, arch, oracle, n):
     ch.Launcher(arch, bg)(arch, bg, (ch.update_velocity_, (Vb, rVb, Prb, taub, ch.ValueField(0.37), 0.737, 0.00931, bg)))
     for fo, fb in list(zip(Vo.values(), Vb)) + list(zip(rVo.values(), rVb)):
         assert_same(fo, fb, "update_velocity!(ValueField)")
+
+
+def test_architectures_known_answers(ch):
+    """test/test_architectures.jl:5-27 on the B200 backend."""
+    backend = ch.B200Backend()
+    arch = ch.SingleDeviceArchitecture(backend, 1)
+    try:
+        assert isinstance(arch, ch.SingleDeviceArchitecture) and arch.backend is backend and arch.device == 1
+        arch2 = ch.SingleDeviceArchitecture(arch)
+        try:
+            assert arch2.backend is arch.backend and arch2.device == arch.device
+        finally:
+            arch2.close()
+        assert ch.get_backend(arch) is backend and ch.get_device(arch) == 1 and ch.set_device_(arch.device) == 1
+        assert ch.is_gpu_aware(arch) is True
+    finally:
+        arch.close()
