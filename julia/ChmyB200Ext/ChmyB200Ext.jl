@@ -232,10 +232,10 @@ operator_of(k::OperatorKernel) = (k.oper, k.dim)
 operator_of(_) = (Int32(0), Int32(0))
 
 # Page-locked host arrays for set!(f, A) / Array(interior(f)) at full host-link rate (chmy_host_alloc).
-function pinned_array(arch, dims::NTuple{N,Int}) where {N}
+function pinned_array(arch, dims::NTuple{N,Int}, ::Type{T}=Float64) where {N,T<:Union{Float64,Float32}}
     ref = Ref{Ptr{Cvoid}}()
-    check(ccall((:chmy_host_alloc, libchmy), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), ctx(arch), prod(dims) * 8, ref))
-    A = unsafe_wrap(Array, Ptr{Float64}(ref[]), dims)
+    check(ccall((:chmy_host_alloc, libchmy), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), ctx(arch), prod(dims) * sizeof(T), ref))
+    A = unsafe_wrap(Array, Ptr{T}(ref[]), dims)
     finalizer(a -> ccall((:chmy_host_free, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), C_NULL, pointer(a)), A)
     return A
 end
