@@ -58,9 +58,11 @@ def parse():
     ap.add_argument("--n", type=int, nargs="*", default=None, help="override the local grid size (parity/debug runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-split", action="store_true",
-                    help="multi-GPU: one full-range kernel followed by the boundary batches / halo exchange instead of the "
-                         "overlapped inner + slab launches (A/B of the split overhead; results are identical)")
+    ap.add_argument("--split", default="auto", choices=["auto", "on", "off"],
+                    help="multi-GPU: order of launches that carry a halo exchange -- on = inner region overlapped with slabs + "
+                         "batches (the reference's order), off = one full-range kernel then batches + exchange, auto = the "
+                         "library times both on the first launches and keeps the faster (results are identical)")
+    ap.add_argument("--no-split", action="store_true", help="same as --split off")
     ap.add_argument("--fused", type=int, default=1, choices=[0, 1, 3],
                     help="3D Stokes: lazily fuse update_stress! + update_velocity! into one sweep (chmy_set_fusion); "
                          "0 = the two tuned kernels; 3 = additionally the EXPERIMENTAL sweeps (2D workloads; 3D thermal pair)")
@@ -237,8 +239,8 @@ def run_b200(args):
 
     wl = args.workload
     n = tuple(args.n) if args.n else WORKLOADS[wl][0]
-    if args.no_split:
-        ch.set_launch_split(False)
+    split_mode = "off" if args.no_split else args.split
+    ch.set_launch_split({"auto": "auto", "on": True, "off": False}[split_mode])
     fused2d = args.fused == 3 and not wl.startswith("stokes3d")      # EXPERIMENTAL 2D sweeps (ops_fused2d.cu)
     fused_t3 = args.fused == 3 and wl == "stokes3d_thermal"          # EXPERIMENTAL 3D thermal sweep (fused_thermal3.cuh)
     fused = (bool(args.fused) and wl.startswith("stokes3d")) or fused2d
@@ -430,7 +432,7 @@ def run_b200(args):
             "ms_per_step": t_it * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[wl][2], "n_local": list(n), "proc_dims": list(pdims) if pdims else [1] * len(n),
-                       "nIO": WORKLOADS[wl][1], "fused_sweep": fused, "split_launches": not args.no_split, "A_eff_GB_per_gpu": a_eff_bytes(wl, n) / 1e9,
+                       "nIO": WORKLOADS[wl][1], "fused_sweep": fused, "split_launches": split_mode, "A_eff_GB_per_gpu": a_eff_bytes(wl, n) / 1e9,
                        "l2": "inputs larger than L2 (every field >= 2 GB; 126 MB L2), no flush needed",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "T_eff_per_gpu": teff_gpu, "frac_of_hbm_peak": teff_gpu / peak, "hbm_peak": peak, "hbm_peak_source": peak_src,

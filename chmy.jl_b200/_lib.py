@@ -112,6 +112,7 @@ SYMBOLS = {
     "chmy_selftest_division": (C.c_int, [_vp, C.c_double, C.c_longlong, C.c_ulonglong, _P(C.c_ulonglong), _P(C.c_int)]),
     "chmy_set_tuning": (C.c_int, [C.c_int, C.c_int]),
     "chmy_set_launch_tuning": (C.c_int, [C.c_int]),
+    "chmy_selftest_split_tuner": (C.c_int, [_P(C.c_float), C.c_int, _i32p, _P(C.c_int32)]),
     "chmy_launch_split_plan": (C.c_int, [_P(LaunchDesc), _i32p, _P(C.c_int32), _i32p, _i32p]),
     "chmy_set_fusion": (C.c_int, [_vp, C.c_int]),
     "chmy_fused_count": (C.c_int, [_vp, _P(C.c_uint64)]),

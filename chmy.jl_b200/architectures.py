@@ -160,10 +160,11 @@ def set_fused2d_tuning(rows_per_chunk: int = 0, unroll: int = 0):
     L.check(L.lib().chmy_set_fused2d_tuning(int(rows_per_chunk), int(unroll)))
 
 
-def set_launch_split(split: bool = True):
-    """Overlap the inner region of exchanging launches with the boundary stream (True, the reference's order) or run one
-    full-range kernel followed by the batches (False).  Results are identical (include/chmy_b200.h: chmy_set_launch_tuning)."""
-    L.check(L.lib().chmy_set_launch_tuning(1 if split else 0))
+def set_launch_split(split="auto"):
+    """Order of launches that carry an exchange: True = inner region overlapped with the boundary stream (the reference's
+    order), False = one full-range kernel followed by the batches, "auto" (default) = time both on the first launches and
+    keep the faster.  Results are identical (include/chmy_b200.h: chmy_set_launch_tuning)."""
+    L.check(L.lib().chmy_set_launch_tuning(2 if split == "auto" else (1 if split else 0)))
 
 
 def topology(arch: DistributedArchitecture):

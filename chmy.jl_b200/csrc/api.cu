@@ -117,6 +117,8 @@ extern "C" int chmy_ctx_destroy(chmy_ctx* c) {
     }
     cudaEventDestroy(c->ev_fork);
     cudaEventDestroy(c->ev_join);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     cudaStreamDestroy(c->s_main);
     cudaStreamDestroy(c->s_bnd);
     free(c);
@@ -493,16 +495,53 @@ extern "C" int chmy_bc(chmy_ctx* ctx, const chmy_grid_desc* g, const chmy_batch_
 // batches on the boundary stream, as the reference does; 0 = one full-range kernel followed by the batches on one stream
 // (outer_width is a hint: results cannot depend on it).  Over NVLink a halo exchange costs tens of microseconds against
 // ~20 ms of compute at the headline size, so the unsplit order may win; round 2 measures it (bench.py --no-split).
+//   2 (default) = measure both on the first launches of each (op, kernel family, grid) and keep the faster (SplitTuner).
 static int g_split_policy = -1;
 static int split_policy() {
     if (g_split_policy < 0) {
         const char* e = getenv("CHMY_SPLIT");
-        g_split_policy = (e && e[0] == '0') ? 0 : 1;
+        g_split_policy = (e && e[0] == '0') ? 0 : (e && e[0] == '1') ? 1 : 2;
     }
     return g_split_policy;
 }
 extern "C" int chmy_set_launch_tuning(int split_launches) {
-    if (split_launches >= 0) g_split_policy = split_launches ? 1 : 0;
+    if (split_launches >= 0) g_split_policy = split_launches > 2 ? 2 : split_launches;
+    return CHMY_OK;
+}
+
+// ---- the tuner's state machine (pure; chmy_selftest_split_tuner drives it on the CPU)
+// launches 0,1: split ; 2,3: unsplit ; the first launch of each order warms caches / allocations / NCCL connections and
+// is not compared.  Afterwards: whichever order's second launch was faster (ties keep the reference's overlapped order).
+static int tuner_policy(const SplitTuner* t) { return t->decided >= 0 ? t->decided : (t->calls < 2 ? 1 : 0); }
+static void tuner_report(SplitTuner* t, float ms) {
+    if (t->decided >= 0 || t->calls >= 4) return;
+    t->ms[t->calls++] = ms;
+    if (t->calls == 4) t->decided = (t->ms[1] <= t->ms[3]) ? 1 : 0;
+}
+static SplitTuner* tuner_for(chmy_ctx* ctx, const chmy_launch_desc* d, int family) {
+    for (int q = 0; q < ctx->ntuners; ++q) {
+        SplitTuner* t = &ctx->tuners[q];
+        if (t->op == d->op && t->family == family && t->n[0] == d->grid.n[0] && t->n[1] == d->grid.n[1] && t->n[2] == d->grid.n[2])
+            return t;
+    }
+    if (ctx->ntuners >= 8) return nullptr;       // more distinct launches than slots: those keep the overlapped order
+    SplitTuner* t = &ctx->tuners[ctx->ntuners++];
+    memset(t, 0, sizeof(*t));
+    t->op = d->op; t->family = family; t->decided = -1;
+    for (int a = 0; a < 3; ++a) t->n[a] = d->grid.n[a];
+    return t;
+}
+// ms: the times the timed launches would report, in order.  policies[i] = order chosen for launch i (1 split, 0 unsplit)
+extern "C" int chmy_selftest_split_tuner(const float* ms, int n, int32_t* policies, int32_t* decided) {
+    CHMY_REQUIRE(ms && policies && decided && n >= 0, "bad argument");
+    SplitTuner t;
+    memset(&t, 0, sizeof(t));
+    t.decided = -1;
+    for (int i = 0; i < n; ++i) {
+        policies[i] = tuner_policy(&t);
+        if (t.decided < 0) tuner_report(&t, ms[i]);
+    }
+    *decided = t.decided;
     return CHMY_OK;
 }
 
@@ -575,6 +614,23 @@ static int orchestrate(chmy_ctx* ctx, const chmy_launch_desc* d, const RUN& run,
         bool split = false;
         int wl[3] = {0, 0, 0}, wr[3] = {0, 0, 0};
         CHMY_TRY(plan_split(d, pref, &split, wl, wr));
+        // self-tuning order: while undecided, time this launch (alone on an idle device) in the order the tuner asks for
+        SplitTuner* tn = nullptr;
+        bool timing = false;
+        if (split && split_policy() == 2 && !(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) {
+            tn = tuner_for(ctx, d, pref ? pref[0] * 1000 + pref[1] : 0);
+            if (tn) {
+                timing = tn->decided < 0;
+                if (!tuner_policy(tn)) split = false;
+            }
+        }
+        if (timing) {
+            if (!ctx->ev_t0) CHMY_CUDA(cudaEventCreate(&ctx->ev_t0));
+            if (!ctx->ev_t1) CHMY_CUDA(cudaEventCreate(&ctx->ev_t1));
+            CHMY_CUDA(cudaStreamSynchronize(ctx->s_bnd));
+            CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));
+            CHMY_CUDA(cudaEventRecord(ctx->ev_t0, ctx->s_main));
+        }
         if (!split) {   // KernelLaunch.jl:156-159
             CHMY_TRY(run(full, ctx->s_main));
             for (int D = N - 1; D >= 0; --D) CHMY_TRY(bc_dim(ctx, g, D, &d->bc[D][0], &d->bc[D][1], ctx->s_main));
@@ -602,6 +658,13 @@ static int orchestrate(chmy_ctx* ctx, const chmy_launch_desc* d, const RUN& run,
             CHMY_TRY(run(in, ctx->s_main));
             CHMY_CUDA(cudaEventRecord(ctx->ev_join, ctx->s_bnd));
             CHMY_CUDA(cudaStreamWaitEvent(ctx->s_main, ctx->ev_join, 0));
+        }
+        if (timing) {
+            float ms = 0.0f;
+            CHMY_CUDA(cudaEventRecord(ctx->ev_t1, ctx->s_main));
+            CHMY_CUDA(cudaEventSynchronize(ctx->ev_t1));
+            CHMY_CUDA(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+            tuner_report(tn, ms);
         }
     }
     if (d->flags & CHMY_LAUNCH_BLOCKING) CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));   // KernelLaunch.jl:117

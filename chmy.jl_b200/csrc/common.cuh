@@ -140,6 +140,16 @@ struct chmy_field {
 
 struct chmy_comm;   // comm.cu
 
+// Self-tuning split policy (api.cu): for one (op, kernel family, grid) with an exchange, the first launches are timed in
+// both orders -- overlapped inner + slabs, then one full-range kernel followed by the batches -- and the faster one is kept.
+struct SplitTuner {
+    int       op, family;     // chmy_op ; slab-width preference of the kernel family (0 = none)
+    long long n[3];
+    int       calls;          // timed launches so far: 0,1 split ; 2,3 unsplit
+    float     ms[4];
+    int       decided;        // -1 undecided, 0 unsplit, 1 split
+};
+
 struct chmy_ctx {
     int          device;        // 0-based CUDA ordinal
     cudaStream_t s_main;        // inner-domain work
@@ -158,6 +168,10 @@ struct chmy_ctx {
     int               has_pending;
     chmy_launch_desc  pending;
     uint64_t          n_fused;       // fused sweeps launched so far
+    // self-tuning split policy: per (op, family, grid) state + the two timing events (created on first use)
+    SplitTuner        tuners[8];
+    int               ntuners;
+    cudaEvent_t       ev_t0, ev_t1;
 };
 
 // api.cu: runs a deferred update_stress! launch now (every entry point that reads or writes device state calls it)

@@ -256,10 +256,14 @@ int chmy_selftest_division(chmy_ctx* ctx, double c, long long n, unsigned long l
 /* -1 keeps a setting.  disable_fast_kernels: run every op with the generic one-thread-per-cell kernels (A/B
  * parity of the tuned kernels); force_true_division: div.rn.f64 everywhere.  Env: CHMY_NO_FAST=1, CHMY_TRUE_DIV=1. */
 int chmy_set_tuning(int disable_fast_kernels, int force_true_division);
-/* -1 keeps.  split_launches: 1 (default) = launches that carry an exchange overlap their inner region with the slabs +
- * batches on the boundary stream (KernelLaunch.jl:160-181); 0 = one full-range kernel, then the batches (outer_width is
- * a hint; results are identical).  Env: CHMY_SPLIT=0. */
+/* -1 keeps.  split_launches: 1 = launches that carry an exchange overlap their inner region with the slabs + batches on
+ * the boundary stream (KernelLaunch.jl:160-181); 0 = one full-range kernel, then the batches (outer_width is a hint;
+ * results are identical); 2 (default) = self-tuning: the first four such launches of each (op, kernel family, grid) are
+ * timed, two in each order, and the faster order is kept.  Env: CHMY_SPLIT=0|1|2. */
 int chmy_set_launch_tuning(int split_launches);
+/* the tuner's state machine on the CPU: ms[i] = the time launch i would report; policies[i] = the order it runs in
+ * (1 overlapped, 0 unsplit); *decided = -1 while fewer than four launches were timed */
+int chmy_selftest_split_tuner(const float* ms, int n, int32_t* policies, int32_t* decided);
 /* The split decision of a launch with boundary batches, without launching: *split = 0 -> one full-range kernel followed by
  * the batches; 1 -> inner region [wl, n+2-wr) per dim on the main stream and, for D = N..1, the two slabs of widths
  * wl[D] / wr[D] on the boundary stream (KernelLaunch.jl:63-87 with outer_width replaced by wl / wr).  pref: the slab widths

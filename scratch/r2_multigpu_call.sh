@@ -1,12 +1,12 @@
 #!/bin/bash
 # Round 2, multi-GPU call (N = 2 first, then 8):  /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'bash scratch/r2_multigpu_call.sh 2'
-# A/B of the split policy on connected ranks: overlapped inner + slabs (the reference's order, 94.7 % weak-scaling
-# efficiency in round 1) vs one full-range sweep followed by the batches / exchange (bench.py --no-split).
+# A/B of the launch order on connected ranks: overlapped inner + slabs (the reference's order, 94.7 % weak-scaling
+# efficiency in round 1), one full-range sweep followed by the batches / exchange, and the library's self-tuning default.
 N=${1:-2}
 mkdir -p gpurun_out
 set +e
-for mode in split nosplit; do
-  flag=""; [ "$mode" = nosplit ] && flag="--no-split"
+for mode in auto on off; do
+  flag="--split $mode"
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
       bench.py --gpus $N --steps 30 --warmup 5 --no-e2e $flag > gpurun_out/r2_bench_${N}gpu_${mode}.json 2> gpurun_out/r2_bench_${N}gpu_${mode}.err
   python - "$N" "$mode" <<'PY'

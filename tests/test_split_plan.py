@@ -118,6 +118,29 @@ def test_when_there_is_no_split(ch):
         assert plan(ch, d, (60, 6, 0))[0] is False
         de, keep2 = desc(ch, n, ow, {(0, 1)}, exact=True)
         assert plan(ch, de, None)[0] is True                                           # a literal split stays literal
+        L.check(L.lib().chmy_set_launch_tuning(1))                                     # always overlapped
+        assert plan(ch, d, (60, 6, 0))[0] is True
     finally:
-        L.check(L.lib().chmy_set_launch_tuning(1))
-    assert plan(ch, d, (60, 6, 0))[0] is True
+        L.check(L.lib().chmy_set_launch_tuning(2))                                     # the default: self-tuning
+    assert plan(ch, d, (60, 6, 0))[0] is True                                          # the plan when the tuner asks for the overlapped order
+
+
+def test_split_tuner_state_machine(ch):
+    """Self-tuning order of exchanging launches: launches 0,1 overlapped, 2,3 unsplit (each launch timed alone on an idle
+    device), then the order whose SECOND launch was faster, for good; ties keep the reference's overlapped order."""
+    from chmy_b200 import _lib as L
+
+    def run(ms):
+        arr = (C.c_float * len(ms))(*ms)
+        pol, dec = (C.c_int32 * len(ms))(), C.c_int32()
+        L.check(L.lib().chmy_selftest_split_tuner(arr, len(ms), pol, C.byref(dec)))
+        return list(pol), dec.value
+
+    pol, dec = run([30.0, 22.4, 25.0, 21.5, 21.5, 21.5, 21.5])      # unsplit wins (first launches of each order are warm-up)
+    assert pol == [1, 1, 0, 0, 0, 0, 0] and dec == 0
+    pol, dec = run([30.0, 21.0, 19.0, 21.5, 99.0, 1.0])             # overlapped wins; later times are never looked at
+    assert pol == [1, 1, 0, 0, 1, 1] and dec == 1
+    pol, dec = run([5.0, 21.0, 5.0, 21.0, 0.0])                     # tie -> the reference's order
+    assert pol == [1, 1, 0, 0, 1] and dec == 1
+    assert run([1.0, 2.0, 3.0]) == ([1, 1, 0], -1)                  # undecided until four launches were timed
+    assert run([]) == ([], -1)
