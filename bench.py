@@ -159,6 +159,9 @@ def a_eff_bytes(workload, n_local):
 def cpu_arm(workload, n_full, steps, warmup, budget_s=20.0):
     """The oracle (C restatement, OpenMP, all host threads) on a bounded slab of the same workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    # worker threads spin between the (many, short) parallel regions of a step instead of sleeping: on virtualised hosts a
+    # sleeping team can take milliseconds to wake up, which would be charged to the CPU arm (read by libgomp when it loads)
+    os.environ.setdefault("OMP_WAIT_POLICY", "active")
     import numpy as np
     import oracle as o
     import drivers as OD
