@@ -24,6 +24,11 @@ from .ops import (compute_q_, update_C_, update_old_, update_stress_, update_the
                   update_velocity_)
 
 
+
+def _sq(x):
+    """Julia's x^2 is x*x (Base.literal_pow); Python's x ** 2 is libm pow(x, 2.0), which is not always the same double."""
+    return x * x
+
 def _gmax(arch, *vals):
     """max_mpi (stokes_3d_inc_ve_T_mpi_perf.jl:16-19): identity on a single device."""
     if isinstance(arch, DistributedArchitecture):
@@ -42,7 +47,7 @@ class Diffusion2D:
         self.grid = grid = UniformGrid(arch, origin=(-1, -1), extent=(2, 2), dims=dims_g)
         self.launch = Launcher(arch, grid, outer_width=outer_width, blocking=blocking, exact_split=exact_split)
         self.chi = 1.0
-        self.dt = min(spacing(grid)) ** 2 / self.chi / grid.ndims() / 2.1          # diffusion_2d.jl:29
+        self.dt = _sq(min(spacing(grid))) / self.chi / grid.ndims() / 2.1          # diffusion_2d.jl:29
         self.C = Field(arch, grid, Center())
         self.q = VectorField(arch, grid)
         if C0 is not None:
@@ -77,7 +82,7 @@ class Stokes:
         self.psc = self.G
         self.tsc = self.eta / self.psc
         self.T0, self.Ta = 1.0, 0.1
-        self.lam = 1e-4 * l[-1] ** 2 / self.tsc                                    # stokes_3d_inc_ve_T.jl:93
+        self.lam = 1e-4 * _sq(l[-1]) / self.tsc                                    # stokes_3d_inc_ve_T.jl:93
         dist = isinstance(arch, DistributedArchitecture)
         dims_g = tuple(a * p for a, p in zip(n, arch.topology.dims)) if dist else tuple(n)
         self.grid = grid = UniformGrid(arch, origin=tuple(-x / 2 for x in l), extent=l, dims=dims_g)
@@ -124,7 +129,7 @@ class Stokes:
         A, g, N = self.arch, self.grid, self.N
         self.launch(A, g, (update_old_, (self.T, self.tau, self.T_old, self.tau_old)))
         d = self.d
-        dt_diff = min(d) ** 2 / self.lam / N / 2.1
+        dt_diff = _sq(min(d)) / self.lam / N / 2.1
         vm = _gmax(A, *[maxabs(v) for v in self.V])
         with np.errstate(divide="ignore"):
             dt_adv = self.adv_coef * min(np.float64(dd) / np.float64(m) for dd, m in zip(d, vm)) / N / 2.1

@@ -12,6 +12,11 @@ import numpy as np
 import oracle as o
 
 
+
+def _sq(x):
+    """Julia's x^2 is x*x (Base.literal_pow); Python's x ** 2 is libm pow(x, 2.0), which is not always the same double."""
+    return x * x
+
 def _world(n_local, proc_dims):
     nd = len(n_local)
     P = int(np.prod(proc_dims)) if proc_dims else 1
@@ -28,7 +33,7 @@ class Diffusion2D:
         self.launchers = [o.Launcher(g, outer_width) for g in self.grids]
         self.chi = 1.0
         g0 = self.grids[0]
-        self.dt = min(g0.spacing) ** 2 / self.chi / 2 / 2.1
+        self.dt = _sq(min(g0.spacing)) / self.chi / 2 / 2.1
         self.C = [o.Field(g, o.CENTER) for g in self.grids]
         self.q = [o.VectorField(g) for g in self.grids]
         if C0 is not None:
@@ -61,7 +66,7 @@ class Stokes:
         self.psc = self.G
         self.tsc = self.eta / self.psc
         self.T0, self.Ta = 1.0, 0.1
-        self.lam = 1e-4 * l[-1] ** 2 / self.tsc
+        self.lam = 1e-4 * _sq(l[-1]) / self.tsc
         dims_g = tuple(a * p for a, p in zip(n, pd))
         self.grids = [o.local_grid(tuple(-x / 2 for x in l), l, dims_g, t) for t in self.topos]
         self.launchers = [o.Launcher(g, outer_width) for g in self.grids]
@@ -118,7 +123,7 @@ class Stokes:
         o.launch_world(self.launchers, self.grids, o.update_old,
                        [(self.T[r], self.tau[r], self.T_old[r], self.tau_old[r]) for r in range(P)])
         d = self.d
-        dt_diff = min(d) ** 2 / self.lam / N / 2.1
+        dt_diff = _sq(min(d)) / self.lam / N / 2.1
         vm = [max(self.V[r][a].maxabs() for r in range(P)) for a in self.ax]
         with np.errstate(divide="ignore"):
             dt_adv = self.adv_coef * min(np.float64(dd) / np.float64(m) for dd, m in zip(d, vm)) / N / 2.1
