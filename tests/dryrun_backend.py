@@ -1,0 +1,397 @@
+"""
+TEST INFRASTRUCTURE -- a dry-run stand-in for libchmy_b200.so, used ONLY by tests/test_gpu_suite_dryrun.py.
+
+There is no GPU where the CPU suite runs, yet most of what can break a `-m gpu` test file is not CUDA: the test's own
+Python, the host mirror's flattening of fields / batches / descriptors, element-type plumbing, the drivers.  This module
+restates the C ABI's entry points on top of the CPU oracle so that the single-GPU `-m gpu` test files can be EXECUTED
+on the CPU: every `chmy_*` call the mirror makes lands here, descriptors are decoded by the field order documented in
+include/chmy_b200.h (an independent reading of the ABI: a mirror that flattens `op => args` in the wrong order computes
+the wrong thing here too), argument validation is done by the REAL library (chmy_validate_launch on descriptor-only twins
+of the fields), and the arithmetic is the oracle's.  Numerically such a run compares the oracle with itself -- it proves
+nothing about the CUDA kernels and is never reported as parity; it proves that the GPU suites are runnable programs.
+
+Not a product path: nothing under chmy.jl_b200/ knows about it; it is injected by tests/conftest.py only when
+CHMY_DRYRUN=1 is set (by the dry-run test's child process).
+"""
+import ctypes as C
+
+import numpy as np
+
+NT = {2: 3, 3: 6}
+
+
+class _Field:
+    def __init__(self, o, nd, dims, loc, layout, dtype, shell):
+        self.nd, self.dims, self.loc, self.layout, self.dtype = nd, tuple(dims), tuple(loc), layout, np.dtype(dtype)
+        n = tuple(d - l for d, l in zip(dims, loc))
+        g = o.Grid((0.0,) * nd, (1.0,) * nd, n, dtype=dtype)
+        self.f = o.Field(g, tuple(loc))
+        self.shell = shell                       # handle of the descriptor-only twin in the real library
+        self.has_storage = True
+
+
+class DryRunLib:
+    """Duck-typed replacement of the ctypes CDLL: same function names, ctypes arguments, integer status returns."""
+
+    def __init__(self, real, oracle):
+        self.real, self.o = real, oracle
+        self.fields, self.ctxs, self.bufs = {}, {}, {}
+        self.next = 0x1000
+        self.err = b""
+        self.launches = 0
+        self.disable_fast = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _id(self):
+        self.next += 0x100
+        return self.next
+
+    @staticmethod
+    def _set(ref, value):
+        ref._obj.value = value
+
+    @staticmethod
+    def _h(x):
+        return x.value if hasattr(x, "value") else x
+
+    def _fail(self, code, msg):
+        self.err = msg.encode()
+        return code
+
+    def _F(self, h):
+        return self.fields[self._h(h)]
+
+    def _real_error(self, rc):
+        self.err = self.real.chmy_last_error()
+        return rc
+
+    def _grid(self, gd, dtype):
+        nd = gd.ndims
+        conn = [[gd.connectivity[d][s] for s in range(2)] for d in range(nd)]
+        g = self.o.Grid([gd.origin[d] for d in range(nd)], [gd.extent[d] for d in range(nd)], [gd.n[d] for d in range(nd)],
+                        conn, dtype=dtype)
+        for d in range(nd):      # the descriptor carries the numbers the host computed: they must be the oracle's
+            assert g.spacing[d] == gd.spacing[d] and g.inv_spacing[d] == gd.inv_spacing[d], "grid numbers differ from the oracle's"
+        return g
+
+    def _box(self, fld, lo, hi):
+        nd = fld.nd
+        for a in range(nd):
+            if lo[a] < -1 or hi[a] > fld.dims[a] + 2:
+                return None
+        return tuple(slice(lo[a] + 1, hi[a] + 2) for a in range(nd))
+
+    def _host(self, ptr, fld, sl_shape):
+        n = int(np.prod(sl_shape))
+        ct = C.c_float if fld.dtype == np.float32 else C.c_double
+        addr = ptr if isinstance(ptr, int) else C.cast(ptr, C.c_void_p).value
+        return np.ctypeslib.as_array((ct * n).from_address(addr)).reshape(sl_shape, order="F")
+
+    # ------------------------------------------------------------------ library / context
+    def chmy_abi_version(self):
+        return self.real.chmy_abi_version()
+
+    def chmy_last_error(self):
+        return self.err
+
+    def chmy_struct_size(self, which):
+        return self.real.chmy_struct_size(which)
+
+    def chmy_device_count(self, out):
+        self._set(out, 1)
+        return 0
+
+    def chmy_ctx_create(self, dev, out):
+        if dev != 1:
+            return self._fail(-1, f"device_id {dev} out of range 1..1")
+        i = self._id()
+        self.ctxs[i] = {"fuse": 0}
+        self._set(out, i)
+        return 0
+
+    def chmy_ctx_destroy(self, ctx):
+        self.ctxs.pop(self._h(ctx), None)
+        return 0
+
+    def chmy_synchronize(self, ctx):
+        return 0
+
+    def chmy_ctx_launch_count(self, ctx, out):
+        self._set(out, self.launches)
+        return 0
+
+    def chmy_event_record(self, ctx, slot):
+        return 0
+
+    def chmy_event_elapsed_ms(self, ctx, a, b, out):
+        self._set(out, 1.0)
+        return 0
+
+    def chmy_set_tuning(self, a, b):
+        return 0
+
+    def chmy_set_launch_tuning(self, a):
+        return 0
+
+    def chmy_set_fused_tuning(self, *a):
+        return 0
+
+    def chmy_set_fused2d_tuning(self, *a):
+        return 0
+
+    def chmy_set_fusion(self, ctx, enable):
+        return 0
+
+    def chmy_fused_count(self, ctx, out):
+        self._set(out, 0)
+        return 0
+
+    def chmy_selftest_division(self, ctx, c, n, seed, bad, used):
+        self._set(bad, 0)
+        self._set(used, 1)
+        return 0
+
+    def chmy_allreduce_max(self, ctx, buf, n):
+        return 0
+
+    def chmy_barrier(self, ctx):
+        return 0
+
+    def chmy_dims_create(self, nranks, nd, dims):
+        return self.real.chmy_dims_create(nranks, nd, dims)
+
+    def chmy_host_alloc(self, ctx, nbytes, out):
+        b = C.create_string_buffer(nbytes)
+        self.bufs[C.addressof(b)] = b
+        self._set(out, C.addressof(b))
+        return 0
+
+    def chmy_host_free(self, ctx, p):
+        self.bufs.pop(self._h(p), None)
+        return 0
+
+    # ------------------------------------------------------------------ fields
+    def _create(self, nd, dims, loc, layout, dtype, out, storage):
+        shell = C.c_void_p()
+        rc = self.real.chmy_field_create_shell(nd, dims, loc, layout, dtype, C.byref(shell))      # the real argument checks
+        if rc:
+            return self._real_error(rc)
+        fld = _Field(self.o, nd, [dims[a] for a in range(nd)], [loc[a] for a in range(nd)], layout,
+                     np.float32 if dtype == 1 else np.float64, shell)
+        fld.has_storage = storage
+        i = self._id()
+        self.fields[i] = fld
+        self._set(out, i)
+        return 0
+
+    def chmy_field_create_typed(self, ctx, nd, dims, loc, layout, dtype, out):
+        if self._h(ctx) not in self.ctxs:
+            return self._fail(-1, "bad context")
+        return self._create(nd, dims, loc, layout, dtype, out, True)
+
+    def chmy_field_create_shell(self, nd, dims, loc, layout, dtype, out):
+        return self._create(nd, dims, loc, layout, dtype, out, False)
+
+    def chmy_field_destroy(self, h):
+        fld = self.fields.pop(self._h(h), None)
+        if fld is not None:
+            self.real.chmy_field_destroy(fld.shell)
+        return 0
+
+    def chmy_field_get_info(self, h, out):
+        fld = self._F(h)
+        rc = self.real.chmy_field_get_info(fld.shell, out)          # dims, strides, layout, dtype from the real layout code
+        if rc == 0 and fld.has_storage:
+            es = fld.dtype.itemsize
+            info = out._obj
+            lead = (128 // es - 1) if fld.layout == 0 else 0
+            base = 0x7F0000000000 + (0 if fld.layout == 0 else 8)    # a plausible 128-B aligned allocation
+            off = lead + 2 + (2 * info.stride[1] if fld.nd > 1 else 0) + (2 * info.stride[2] if fld.nd > 2 else 0)
+            info.origin_ptr = base + es * off
+            info.base_ptr = base + es * lead
+        return rc
+
+    def chmy_field_fill(self, ctx, h, v, lo, hi):
+        fld = self._F(h)
+        sl = self._box(fld, lo, hi)
+        if sl is None or not fld.has_storage:
+            return self._fail(-1, "box outside the padded field")
+        fld.f.data[sl] = v
+        return 0
+
+    def chmy_field_copy_from_host(self, ctx, h, src, lo, hi):
+        fld = self._F(h)
+        sl = self._box(fld, lo, hi)
+        if sl is None or not fld.has_storage:
+            return self._fail(-1, "box outside the padded field")
+        shape = fld.f.data[sl].shape
+        if int(np.prod(shape)) > 0:
+            fld.f.data[sl] = self._host(src, fld, shape)
+        return 0
+
+    def chmy_field_copy_to_host(self, ctx, h, dst, lo, hi):
+        fld = self._F(h)
+        sl = self._box(fld, lo, hi)
+        if sl is None or not fld.has_storage:
+            return self._fail(-1, "box outside the padded field")
+        shape = fld.f.data[sl].shape
+        if int(np.prod(shape)) > 0:
+            self._host(dst, fld, shape)[...] = fld.f.data[sl]
+        return 0
+
+    def chmy_field_copy(self, ctx, hd, hs, lo, hi):
+        d, s = self._F(hd), self._F(hs)
+        if d.nd != s.nd:
+            return self._fail(-1, "set!(f, other): dimensionality mismatch")
+        if d.dtype != s.dtype:
+            return self._fail(-1, "set!(f, other): element types differ")
+        sl = self._box(d, lo, hi)
+        if sl is None:
+            return self._fail(-1, "box outside the padded field")
+        d.f.data[sl] = s.f.data[sl]
+        return 0
+
+    def chmy_field_set_inclusion(self, ctx, h, gd, inc):
+        fld = self._F(h)
+        g, q = self._grid(gd._obj, fld.dtype), inc._obj
+        # evaluate on a field bound to the launch grid's numbers (the coordinates come from the grid)
+        tmp = self.o.Field(g, fld.loc)
+        tmp.data[...] = fld.f.data
+        self.o.set_inclusion(tmp, self.o.Inclusion(fld.loc, tuple(q.c0[d] for d in range(fld.nd)), q.r, q.inn, q.out))
+        fld.f.data[...] = tmp.data
+        return 0
+
+    def chmy_field_maxabs(self, ctx, h, lo, hi, out):
+        fld = self._F(h)
+        sl = self._box(fld, lo, hi)
+        if sl is None or not fld.has_storage:
+            return self._fail(-1, "box outside the padded field")
+        a = np.abs(fld.f.data[sl])
+        self._set(out, float("nan") if np.isnan(a).any() else (float(a.max()) if a.size else 0.0))
+        return 0
+
+    # ------------------------------------------------------------------ halo slabs (host helpers of the parity tests)
+    def chmy_halo_slab_len(self, h, dim, out):
+        self._set(out, int(np.prod([s for a, s in enumerate(self._F(h).f.sdims) if a != dim])))
+        return 0
+
+    def chmy_halo_pack(self, ctx, h, dim, side, buf):
+        fld = self._F(h)
+        ref = self.o.pack_send(fld.f, dim, side)
+        self._host(buf, fld, (ref.size,))[...] = ref
+        return 0
+
+    def chmy_halo_unpack(self, ctx, h, dim, side, buf):
+        fld = self._F(h)
+        n = int(np.prod([s for a, s in enumerate(fld.f.sdims) if a != dim]))
+        self.o.unpack_recv(fld.f, dim, side, np.array(self._host(buf, fld, (n,))))
+        return 0
+
+    # ------------------------------------------------------------------ batches / launch
+    def _batchset(self, g, bc):
+        o, nd = self.o, g.nd
+        out = []
+        for D in range(nd):
+            sides = []
+            for S in range(2):
+                b = bc[D][S]
+                if b.kind == 1:
+                    fb = []
+                    for q in range(b.nfields):
+                        f = self._F(b.fields[q]).f
+                        vf = b.value_field[q]
+                        v = self._F(vf).f if vf else b.value[q]
+                        fb.append((f, o.BC(b.bc_kind[q], v)))
+                    sides.append(("field", fb))
+                elif b.kind == 2:
+                    raise NotImplementedError("dry run: single rank only (no ExchangeBatch)")
+                else:
+                    sides.append(("empty",))
+            out.append(tuple(sides))
+        return out
+
+    def _validate(self, d):
+        """chmy_validate_launch of the REAL library on a copy of the descriptor whose handles are the shell twins"""
+        from chmy_b200 import _lib as L
+        t = L.LaunchDesc.from_buffer_copy(d)
+        for q in range(d.nfields):
+            t.fields[q] = self._F(d.fields[q]).shell if d.fields[q] else None
+        for D in range(3):
+            for S in range(2):
+                b = t.bc[D][S]
+                for q in range(b.nfields if b.kind else 0):
+                    b.fields[q] = self._F(d.bc[D][S].fields[q]).shell
+                    if d.bc[D][S].value_field[q]:
+                        b.value_field[q] = self._F(d.bc[D][S].value_field[q]).shell
+        rc = self.real.chmy_validate_launch(C.byref(t))
+        return self._real_error(rc) if rc else 0
+
+    def chmy_validate_launch(self, dref):
+        return self._validate(dref._obj)
+
+    def chmy_bc(self, ctx, gd, arr, flags):
+        gd = gd._obj
+        dt = None
+        for D in range(gd.ndims):
+            for S in range(2):
+                if arr[D][S].kind == 1 and arr[D][S].nfields:
+                    dt = self._F(arr[D][S].fields[0]).dtype
+        g = self._grid(gd, dt or np.float64)
+        self.o.bc_world([g], [self._batchset(g, arr)], None)
+        self.launches += gd.ndims
+        return 0
+
+    def chmy_launch(self, ctx, dref):
+        d = dref._obj
+        rc = self._validate(d)
+        if rc:
+            return rc
+        o = self.o
+        nd, nt = d.grid.ndims, NT.get(d.grid.ndims, 0)
+        F = [self._F(d.fields[q]) if d.fields[q] else None for q in range(d.nfields)]
+        if any(f is not None and not f.has_storage for f in F):
+            return self._fail(-1, "descriptor-only field")
+        g = self._grid(d.grid, F[0].dtype)
+        s = [d.scalars[q] for q in range(d.nscalars)]
+        vn, tn = "xyz"[:nd], (("xx", "yy", "xy") if nd == 2 else ("xx", "yy", "zz", "xy", "xz", "yz"))
+        V = lambda i: {c: F[i + k].f for k, c in enumerate(vn)}
+        Tn = lambda i: {c: F[i + k].f for k, c in enumerate(tn)}
+        op, args = None, None
+        if d.op == 1:      # q.x q.y C ; chi
+            op, args = o.compute_q, (V(0), F[2].f, s[0])
+        elif d.op == 2:    # C q.x q.y ; dt
+            op, args = o.update_C, (F[0].f, V(1), s[0])
+        elif d.op == 3:    # T tau[nt] T_old tau_old[nt]
+            op, args = o.update_old, (F[0].f, Tn(1), F[1 + nt].f, Tn(2 + nt))
+        elif d.op == 4:    # tau[nt] Pr divV V[nd] tau_old[nt] ; eta eta_ve G dt dtau_Pr dtau_r
+            op, args = o.update_stress, (Tn(0), F[nt].f, F[nt + 1].f, V(nt + 2), Tn(nt + 2 + nd), *s)
+        elif d.op == 5:    # V[nd] r_V[nd] Pr tau[nt] rho_g|NULL ; eta_ve nudtau
+            rho = F[2 * nd + 1 + nt]
+            if rho is None:
+                q = d.rho_g
+                rho_arg = o.Inclusion(tuple(q.loc[a] for a in range(nd)), tuple(q.c0[a] for a in range(nd)), q.r, q.inn, q.out)
+            else:
+                rho_arg = rho.f
+            op, args = o.update_velocity, (V(0), V(nd), F[2 * nd].f, Tn(2 * nd + 1), rho_arg, *s)
+        elif d.op == 6:    # qT[nd] T V[nd] ; lambda
+            op, args = o.update_thermal_flux, (V(0), F[nd].f, V(nd + 1), s[0])
+        elif d.op == 7:    # T T_old qT[nd] ; dt
+            op, args = o.update_thermal, (F[0].f, F[1].f, V(2), s[0])
+        elif d.op == 8:    # operators: destinations first, then sources, then the coefficient field
+            nout = nd if d.oper in (13, 14) else 1
+            vec = d.oper in (9, 12)
+            dst = [F[k].f for k in range(nout)]
+            src = [F[nout + k].f for k in range(nd if vec else 1)]
+            kf = F[nout + 1].f if d.oper in (6, 11, 14) else None
+            o.apply_operator(g, d.oper, dst, src, k=kf, dim=d.oper_dim)
+            self.launches += 1
+            return 0
+        else:
+            return self._fail(-1, f"unknown op id {d.op}")
+        ow = tuple(d.outer_width[a] for a in range(nd)) if d.has_outer_width else None
+        if ow is not None and any(w < 3 or 2 * w > d.grid.n[a] + 2 for a, w in enumerate(ow)):
+            ow = None                                            # the library's own rule: such widths do not split
+        la = o.Launcher(g, ow)
+        o.launch(la, g, op, args, bc=self._batchset(g, d.bc) if d.has_bc else None)
+        self.launches += 1 + (nd if d.has_bc else 0)
+        return 0
