@@ -17,14 +17,15 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-FILES = ["tests/test_b200_parity.py", "tests/test_golden_fixtures.py", "tests/test_zz_b200_round2.py"]
-# not in the dry run: the fused-sweep suites (they assert the library's sweep counters), the full-size suite (767^3 is
-# beyond the oracle), the multi-GPU suite (needs ranks), and the device self-test of the exact-division sequence
+FILES = ["tests/test_b200_parity.py", "tests/test_golden_fixtures.py", "tests/test_b200_fused.py", "tests/test_b200_fused2d.py",
+         "tests/test_zy_b200_fullsize.py", "tests/test_zz_b200_round2.py"]
+# not in the dry run: the multi-GPU suite (needs ranks) and the device self-test of the exact-division sequence.  The
+# fused-sweep suites run with their gated (CHMY_EXPERIMENTAL) cases; the full-size suite runs at sizes the oracle can hold.
 DESELECT = "not test_exact_division_by_uniform_scalar"
 
 
 def test_single_gpu_suites_run_on_the_dry_run_backend():
-    env = dict(os.environ, CHMY_DRYRUN="1")
+    env = dict(os.environ, CHMY_DRYRUN="1", CHMY_EXPERIMENTAL="1")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider", "-k", DESELECT] + FILES,
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=1700)
     tail = (r.stdout + r.stderr)[-4000:]
