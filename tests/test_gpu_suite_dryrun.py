@@ -33,3 +33,45 @@ def test_single_gpu_suites_run_on_the_dry_run_backend():
     last = r.stdout.strip().splitlines()[-1]
     assert " passed" in last and "failed" not in last and "error" not in last, tail
     assert int(last.split(" passed")[0].split()[-1]) >= 100, last          # the files really ran (not everything deselected)
+
+
+_CHILD = r"""
+import os, sys, json, io
+from contextlib import redirect_stdout
+ROOT = sys.argv[1]
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import chmy_b200
+from chmy_b200 import _lib
+import oracle as o
+from dryrun_backend import DryRunLib
+fake = DryRunLib(_lib.lib(), o)
+_lib.lib = lambda: fake
+chmy_b200.load_library = _lib.lib
+import __graft_entry__ as g
+g.smoke()                                            # the driver's smoke(): fused 3D Stokes vs the oracle, sweep counter
+import importlib.util
+spec = importlib.util.spec_from_file_location("bench_dry", os.path.join(ROOT, "bench.py"))
+bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+for wl, n in (("stokes3d", "20 16 12"), ("stokes3d_thermal", "20 16 12"), ("stokes2d", "40 30"), ("diffusion2d", "40 30")):
+    for fused in ("1", "3"):
+        sys.argv = ["bench.py", "--workload", wl, "--n", *n.split(), "--steps", "4", "--warmup", "3", "--fused", fused, "--no-cpu-baseline"]
+        buf = io.StringIO()
+        with redirect_stdout(buf):
+            bench.run_b200(bench.parse())
+        j = json.loads(buf.getvalue().strip().splitlines()[-1])
+        assert j["value"] > 0 and "host_segment_error" not in j["e2e"], j["e2e"]
+        assert j["e2e"]["h2d_bytes_per_step"] > 1000 and j["roofline"]["frac"] > 0
+        print("bench ok", wl, fused, j["fused_sweeps"], j["gpu_launches"])
+"""
+
+
+def test_smoke_and_bench_run_on_the_dry_run_backend():
+    """__graft_entry__.smoke() and bench.py's B200 arm (every workload, default and experimental fusion modes) executed end
+    to end -- real drivers, real host mirror, real descriptor validation -- with the dry-run backend in place of the device.
+    Timings and throughputs printed by such a run are meaningless; the point is that the scripts the driver runs on the GPU
+    box are runnable."""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([sys.executable, "-c", _CHILD, ROOT], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0, tail
+    assert r.stdout.count("bench ok") == 8 and "smoke ok" in r.stdout, tail
