@@ -14,13 +14,8 @@ def pytest_configure(config):
     if os.environ.get("CHMY_DRYRUN") == "1":
         # tests/test_gpu_suite_dryrun.py's child process: execute the single-GPU `-m gpu` files on the CPU against
         # tests/dryrun_backend.py (the C ABI restated over the oracle).  Never set on the GPU box.
-        import chmy_b200
-        from chmy_b200 import _lib
-        import oracle as o
-        from dryrun_backend import DryRunLib
-        fake = DryRunLib(_lib.lib(), o)
-        _lib.lib = lambda: fake
-        chmy_b200.load_library = _lib.lib
+        from helpers import install_dryrun_if_requested
+        install_dryrun_if_requested()
 
 
 @pytest.fixture(scope="session")

@@ -40,6 +40,8 @@ class DryRunLib:
         self.err = b""
         self.launches = 0
         self.disable_fast = 0
+        import os
+        self.ndev = int(os.environ.get("CHMY_DRYRUN_NGPU", "1"))     # "devices" the multi-rank dry run pretends to have
 
     # ------------------------------------------------------------------ helpers
     def _id(self):
@@ -98,12 +100,12 @@ class DryRunLib:
         return self.real.chmy_struct_size(which)
 
     def chmy_device_count(self, out):
-        self._set(out, 1)
+        self._set(out, self.ndev)
         return 0
 
     def chmy_ctx_create(self, dev, out):
-        if dev != 1:
-            return self._fail(-1, f"device_id {dev} out of range 1..1")
+        if not 1 <= dev <= self.ndev:
+            return self._fail(-1, f"device_id {dev} out of range 1..{self.ndev}")
         i = self._id()
         self.ctxs[i] = {"fuse": 0}
         self._set(out, i)
@@ -189,10 +191,105 @@ class DryRunLib:
         self._set(used, 1)
         return 0
 
+    # ---- ranks: the bootstrap group the tests / bench create (torch.distributed, gloo) carries the dry run's "NCCL" traffic
+    @staticmethod
+    def _dist():
+        import torch.distributed as dist
+        return dist if dist.is_available() and dist.is_initialized() else None
+
+    def chmy_comm_unique_id(self, out):
+        return 0
+
+    def chmy_topo_create(self, ctx, nranks, rank, nd, dims, uid):
+        d = [dims[a] for a in range(nd)]
+        t = self.o.Topology(nranks, tuple(d), rank)
+        self.ctxs[self._h(ctx)]["topo"] = t
+        return 0
+
+    def chmy_topo_coords(self, ctx, out):
+        t = self.ctxs[self._h(ctx)]["topo"]
+        for a, c in enumerate(t.coords):
+            out[a] = c
+        return 0
+
+    def chmy_topo_neighbors(self, ctx, out):
+        t = self.ctxs[self._h(ctx)]["topo"]
+        for a, (l, r) in enumerate(t.neighbors):
+            out[a][0], out[a][1] = l, r
+        return 0
+
     def chmy_allreduce_max(self, ctx, buf, n):
+        self._flush_all()
+        dist = self._dist()
+        if dist is not None and dist.get_world_size() > 1:
+            import torch
+            t = torch.tensor([buf[i] for i in range(n)], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            for i in range(n):
+                buf[i] = float(t[i])
         return 0
 
     def chmy_barrier(self, ctx):
+        self._flush_all()
+        dist = self._dist()
+        if dist is not None and dist.get_world_size() > 1:
+            dist.barrier()
+        return 0
+
+    def _exchange_dim(self, ctx, D, sides):
+        """exchange_halo.jl:13-61 for both sides of one dim: my side S talks to the neighbour's side 1-S"""
+        import torch
+        dist, topo = self._dist(), self.ctxs[self._h(ctx)].get("topo")
+        if dist is None or topo is None:
+            raise RuntimeError("halo exchange requested but the architecture has no topology")
+        reqs, recv = [], {}
+        for S, fields in sides.items():
+            nb = topo.neighbors[D][S]
+            if nb < 0:
+                raise RuntimeError("no neighbor to communicate")
+            msg = np.concatenate([np.asarray(self.o.pack_send(f, D, S), dtype=np.float64) for f in fields])
+            reqs.append(dist.isend(torch.from_numpy(msg.copy()), nb, tag=2 * D + (1 - S)))
+            recv[S] = torch.empty(msg.size, dtype=torch.float64)
+            reqs.append(dist.irecv(recv[S], nb, tag=2 * D + S))
+        for r in reqs:
+            r.wait()
+        for S, fields in sides.items():
+            off = 0
+            for f in fields:
+                n = int(np.prod([s for a, s in enumerate(f.sdims) if a != D]))
+                self.o.unpack_recv(f, D, S, recv[S][off:off + n].numpy().astype(f.dtype))
+                off += n
+
+    def _apply_batches(self, ctx, g, bc):
+        """bc!(arch, grid, batchset): D = N..1; FieldBatch sides first, then the exchange of that dim (batch.jl:20-29)"""
+        for D in reversed(range(g.nd)):
+            ex = {}
+            for S in range(2):
+                b = bc[D][S]
+                if b.kind == 1:
+                    fb = []
+                    for q in range(b.nfields):
+                        vf = b.value_field[q]
+                        fb.append((self._F(b.fields[q]).f, self.o.BC(b.bc_kind[q], self._F(vf).f if vf else b.value[q])))
+                    self.o.bc_side(g, D, S, ("field", fb))
+                elif b.kind == 2:
+                    ex[S] = [self._F(b.fields[q]).f for q in range(b.nfields)]
+            if ex:
+                self._exchange_dim(ctx, D, ex)
+
+    def chmy_exchange_halo(self, ctx, gd, dim, side, nf, fields, flags):
+        self._flush_all()
+        self._exchange_dim(ctx, dim, {side: [self._F(fields[q]).f for q in range(nf)]})
+        return 0
+
+    def chmy_exchange_halo_all(self, ctx, gd, nf, fields, flags):
+        self._flush_all()
+        gd = gd._obj
+        fs = [self._F(fields[q]).f for q in range(nf)]
+        for D in reversed(range(gd.ndims)):
+            ex = {S: fs for S in range(2) if gd.connectivity[D][S] == 1}
+            if ex:
+                self._exchange_dim(ctx, D, ex)
         return 0
 
     def chmy_dims_create(self, nranks, nd, dims):
@@ -336,28 +433,6 @@ class DryRunLib:
         return 0
 
     # ------------------------------------------------------------------ batches / launch
-    def _batchset(self, g, bc):
-        o, nd = self.o, g.nd
-        out = []
-        for D in range(nd):
-            sides = []
-            for S in range(2):
-                b = bc[D][S]
-                if b.kind == 1:
-                    fb = []
-                    for q in range(b.nfields):
-                        f = self._F(b.fields[q]).f
-                        vf = b.value_field[q]
-                        v = self._F(vf).f if vf else b.value[q]
-                        fb.append((f, o.BC(b.bc_kind[q], v)))
-                    sides.append(("field", fb))
-                elif b.kind == 2:
-                    raise NotImplementedError("dry run: single rank only (no ExchangeBatch)")
-                else:
-                    sides.append(("empty",))
-            out.append(tuple(sides))
-        return out
-
     def _validate(self, d):
         """chmy_validate_launch of the REAL library on a copy of the descriptor whose handles are the shell twins"""
         from chmy_b200 import _lib as L
@@ -385,8 +460,12 @@ class DryRunLib:
             for S in range(2):
                 if arr[D][S].kind == 1 and arr[D][S].nfields:
                     dt = self._F(arr[D][S].fields[0]).dtype
+        for D in range(gd.ndims):
+            for S in range(2):
+                if dt is None and arr[D][S].kind == 2 and arr[D][S].nfields:
+                    dt = self._F(arr[D][S].fields[0]).dtype
         g = self._grid(gd, dt or np.float64)
-        self.o.bc_world([g], [self._batchset(g, arr)], None)
+        self._apply_batches(ctx, g, arr)
         self.launches += gd.ndims
         return 0
 
@@ -441,7 +520,10 @@ class DryRunLib:
         ow = tuple(d.outer_width[a] for a in range(nd)) if d.has_outer_width else None
         if ow is not None and any(w < 3 or 2 * w > d.grid.n[a] + 2 for a, w in enumerate(ow)):
             ow = None                                            # the library's own rule: such widths do not split
+        # the ops are pointwise writers: regions + per-dim batches in the reference's order == full range, then the batches
         la = o.Launcher(g, ow)
-        o.launch(la, g, op, args, bc=self._batchset(g, d.bc) if d.has_bc else None)
+        o.launch(la, g, op, args, bc=None)
+        if d.has_bc:
+            self._apply_batches(ctx, g, d.bc)
         self.launches += 1 + (nd if d.has_bc else 0)
         return 0

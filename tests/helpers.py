@@ -50,3 +50,24 @@ def assert_same(of, bf, name="", tol=0.0):
         scale = max(np.abs(a).max(), 1e-300)
         err = np.abs(a - b).max() / scale
         assert err <= tol, f"{name}: relative error {err:.3e} > {tol:.1e}"
+
+
+def install_dryrun_if_requested():
+    """Child processes of the dry run (tests/test_gpu_suite_dryrun.py) that import chmy_b200 on their own -- the ranks the
+    multi-GPU suite spawns -- put tests/dryrun_backend.py in the library's place.  No-op unless CHMY_DRYRUN=1."""
+    if os.environ.get("CHMY_DRYRUN") != "1":
+        return False
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), os.path.join(os.path.dirname(here), "oracle"), here):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import chmy_b200
+    from chmy_b200 import _lib
+    import oracle as o
+    from dryrun_backend import DryRunLib
+    if not isinstance(_lib.lib(), DryRunLib):
+        fake = DryRunLib(_lib.lib(), o)
+        _lib.lib = lambda: fake
+        chmy_b200.load_library = _lib.lib
+    return True

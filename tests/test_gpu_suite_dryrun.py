@@ -75,3 +75,47 @@ def test_smoke_and_bench_run_on_the_dry_run_backend():
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     assert r.stdout.count("bench ok") == 8 and "smoke ok" in r.stdout, tail
+
+
+def _free_port():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_multi_rank_suites_and_bench_run_on_the_dry_run_backend():
+    """world_size 2 (and 4) over gloo: the multi-GPU parity file (exchange, decomposed solvers, fused path) and bench.py
+    launched exactly as the driver launches it for N > 1 (torch.distributed.run, one rank per "GPU"), with the dry-run
+    backend's halo exchange / reductions travelling over the bootstrap group.  Checks the ranks' control flow (nobody
+    enters a collective alone, rank 0 alone prints ONE line, both arms) -- not the NCCL path, which only GPUs can run."""
+    env = dict(os.environ, CHMY_DRYRUN="1", CHMY_DRYRUN_NGPU="4", OMP_NUM_THREADS="2")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider", "-k", "2gpu or 4gpu-exchange",
+                        "tests/test_z_b200_multigpu.py"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0 and " passed" in r.stdout, tail
+    import json
+    for extra in ("--n 24 20 16", "--workload diffusion2d --n 48 40"):
+        # the driver's launch line for N > 1, with the dry-run main in bench.py's place
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dryrun_bench_main.py"), "--gpus", "2", "--steps", "6",
+               "--warmup", "3"]
+        r = subprocess.run(cmd, cwd=ROOT, env=dict(env, DRYRUN_BENCH_ARGS=extra), capture_output=True, text=True, timeout=600)
+        tail = (r.stdout + r.stderr)[-3000:]
+        assert r.returncode == 0, tail
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        assert len(lines) == 1, tail                                   # rank 0 alone prints, ONE line
+        j = json.loads(lines[0])
+        assert j["n_gpus"] == 2 and j["scaling"] == "weak" and j["value"] > 0 and j["config"]["proc_dims"][0] == 2
+        assert "host_segment_error" not in j["e2e"] and j["cpu_baseline"] is None
+    # the reference arm under torchrun: rank 0 alone works and prints
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
+           "--warmup", "1"]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0 and len(lines) == 1 and json.loads(lines[0])["impl"] == "reference", (r.stdout + r.stderr)[-2000:]

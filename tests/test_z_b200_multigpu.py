@@ -61,6 +61,9 @@ def _worker(rank, world, port, case, q):
     os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import install_dryrun_if_requested
+    install_dryrun_if_requested()       # tests/test_gpu_suite_dryrun.py only (CHMY_DRYRUN=1); never on the GPU box
     import torch.distributed as dist
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     arch = None
