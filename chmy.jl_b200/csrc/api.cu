@@ -211,6 +211,14 @@ static int field_describe(int ndims, const int64_t* dims, const int32_t* loc, in
     f->stride[0] = 1;
     f->stride[1] = pitch;
     f->stride[2] = pitch * f->sd[1];
+    // 64-bit element counts: refuse sizes whose padded volume cannot be a real allocation instead of wrapping around
+    const long double volume = (long double)pitch * (long double)f->sd[1] * (long double)f->sd[2];
+    if (volume > 1.0e13L) {
+        free(f);
+        chmy_set_error("field of %lld x %lld x %lld elements is too large", (long long)dims[0], ndims > 1 ? (long long)dims[1] : 1ll,
+                       ndims > 2 ? (long long)dims[2] : 1ll);
+        return CHMY_ERR_ARG;
+    }
     const long long elems = f->lead + pitch * f->sd[1] * f->sd[2] + 2 * per128;
     f->bytes = (size_t)elems * (size_t)f->esize;
     *out = f;

@@ -166,3 +166,22 @@ def test_constant_fields(ch):
         assert [d.rho_g.loc[a] for a in range(nd)] == [1 if a == nd - 1 else 0 for a in range(nd)]
         L.validate(g, (ch.update_velocity_, (V, rV, Pr, tau, ch.ValueField(9.81), 0.1, 0.01, g)))
         L.validate(g, (ch.update_velocity_, (V, rV, Pr, tau, ch.ZeroField(), 0.1, 0.01, g)))
+
+
+def test_field_sizes_that_cannot_exist_are_refused(ch):
+    import ctypes as C
+    from chmy_b200 import _lib as L
+    h = C.c_void_p()
+    big = L.i64x3([1 << 29, 1 << 29, 1 << 29])
+    assert L.lib().chmy_field_create_shell(3, big, L.i32x3([0, 0, 0]), 0, 0, C.byref(h)) != 0      # 2^87 elements would wrap around
+    assert b"too large" in L.lib().chmy_last_error()
+    assert L.lib().chmy_field_create_shell(3, L.i64x3([767, 767, 767]), L.i32x3([0, 0, 0]), 0, 0, C.byref(h)) == 0
+    info = L.FieldInfo()
+    L.check(L.lib().chmy_field_get_info(h, C.byref(info)))
+    assert info.bytes == 8 * (15 + 784 * 771 * 771 + 32) and info.stride[1] == 784 and info.stride[2] == 784 * 771
+    L.lib().chmy_field_destroy(h)
+    assert L.lib().chmy_field_create_shell(4, big, L.i32x3([0, 0, 0]), 0, 0, C.byref(h)) != 0
+    assert L.lib().chmy_field_create_shell(2, L.i64x3([8, 0]), L.i32x3([0, 0]), 0, 0, C.byref(h)) != 0
+    assert L.lib().chmy_field_create_shell(2, L.i64x3([8, 8]), L.i32x3([0, 2]), 0, 0, C.byref(h)) != 0
+    assert L.lib().chmy_field_create_shell(2, L.i64x3([8, 8]), L.i32x3([0, 1]), 7, 0, C.byref(h)) != 0
+    assert L.lib().chmy_field_create_shell(2, L.i64x3([8, 8]), L.i32x3([0, 1]), 0, 9, C.byref(h)) != 0
