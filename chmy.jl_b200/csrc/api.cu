@@ -482,6 +482,7 @@ static int validate_batches(const chmy_grid_desc* g, const chmy_batch_desc bc[CH
                 CHMY_REQUIRE(g->connectivity[D][s] == CHMY_CONNECTED, "ExchangeBatch on a Bounded side");
                 *any_exchange = true;
             }
+            CHMY_TRY(chmy_validate_batch(g, D, &b));
         }
     return CHMY_OK;
 }

@@ -66,6 +66,34 @@ __global__ void __launch_bounds__(256) k_bc_dim(const BcBatchDev<T> b) {
     }
 }
 
+// Everything a batch must satisfy, checked BEFORE the launch it belongs to starts (chmy_validate_launch / chmy_bc): a
+// descriptor that is wrong in its batches must not leave a half-executed launch behind.  Needs no device.
+int chmy_validate_batch(const chmy_grid_desc* g, int dim, const chmy_batch_desc* b) {
+    if (!b || b->kind == CHMY_BATCH_EMPTY) return CHMY_OK;
+    CHMY_REQUIRE(b->nfields >= 0 && b->nfields <= CHMY_MAX_BATCH_FIELDS, "batch with %d fields (max %d)", b->nfields, CHMY_MAX_BATCH_FIELDS);
+    if (b->kind == CHMY_BATCH_EXCHANGE) CHMY_REQUIRE(b->nfields >= 1, "ExchangeBatch without fields");
+    for (int q = 0; q < b->nfields; ++q) {
+        const chmy_field* f = b->fields[q];
+        CHMY_REQUIRE(f != nullptr && f->nd == g->ndims, "batch (dim %d): bad field %d", dim + 1, q);
+        CHMY_REQUIRE(f->dtype == b->fields[0]->dtype, "batch (dim %d): the fields must share one element type", dim + 1);
+        for (int a = 0; a < g->ndims; ++a)
+            CHMY_REQUIRE(f->d[a] == g->n[a] + (f->loc[a] == CHMY_VERTEX ? 1 : 0), "batch (dim %d): field %d does not match the grid", dim + 1, q);
+        if (b->kind != CHMY_BATCH_FIELD) continue;
+        CHMY_REQUIRE(b->bc_kind[q] == CHMY_DIRICHLET || b->bc_kind[q] == CHMY_NEUMANN, "FieldBatch: bad bc kind");
+        if (const chmy_field* vf = b->value_field[q]) {
+            CHMY_REQUIRE(g->ndims >= 2 && vf->nd == g->ndims - 1, "Field-valued condition: the value field must have %d dims", g->ndims - 1);
+            CHMY_REQUIRE(vf->dtype == f->dtype, "Field-valued condition: the value field must have the field's element type");
+            int t = 0;
+            for (int a = 0; a < g->ndims; ++a) {
+                if (a == dim) continue;
+                CHMY_REQUIRE(vf->d[t] >= g->n[a], "Field-valued condition: value field too small along transverse dim %d", t + 1);
+                ++t;
+            }
+        }
+    }
+    return CHMY_OK;
+}
+
 template <class T>
 static int run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_batch_desc* left,
                       const chmy_batch_desc* right, int dtype, cudaStream_t st) {

@@ -186,6 +186,7 @@ static inline dim3 grid_for(const Box& b, dim3 blk) {
 int chmy_run_op(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st);
 int chmy_validate_op(const chmy_launch_desc* d);
 // bc.cu
+int chmy_validate_batch(const chmy_grid_desc* g, int dim, const chmy_batch_desc* b);
 int chmy_run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_batch_desc* left,
                     const chmy_batch_desc* right, cudaStream_t st);
 // comm.cu

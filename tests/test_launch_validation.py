@@ -185,3 +185,36 @@ def test_field_sizes_that_cannot_exist_are_refused(ch):
     assert L.lib().chmy_field_create_shell(2, L.i64x3([8, 8]), L.i32x3([0, 2]), 0, 0, C.byref(h)) != 0
     assert L.lib().chmy_field_create_shell(2, L.i64x3([8, 8]), L.i32x3([0, 1]), 7, 0, C.byref(h)) != 0
     assert L.lib().chmy_field_create_shell(2, L.i64x3([8, 8]), L.i32x3([0, 1]), 0, 9, C.byref(h)) != 0
+
+
+def test_batches_are_validated_before_the_launch_starts(ch):
+    """A descriptor that is wrong in its boundary batches is refused by chmy_validate_launch (= before chmy_launch touches
+    the device): field of another grid, Field-valued condition of the wrong dimensionality / element type, mixed element
+    types in one batch, an ExchangeBatch on a Bounded side."""
+    import ctypes as C
+    from chmy_b200 import _lib as L
+    g = grid(ch, (12, 10, 8))
+    la = ch.Launcher(_NoArch(), g)
+    T, To, q = F(ch, g), F(ch, g), vec(ch, g)
+    op = (ch.update_thermal_, (T, To, q, 0.1, g))
+    la.validate(g, op, bc=ch.batch(g, (T, ch.Neumann())))
+    other = F(ch, grid(ch, (13, 10, 8)))
+    with pytest.raises(ch.ChmyError, match="does not match the grid"):
+        la.validate(g, op, bc=ch.batch(g, (other, ch.Neumann())))
+    g2 = grid(ch, (10, 8))                                       # transverse grid of dim x
+    la.validate(g, op, bc=ch.batch(g, (T, {"x": ch.Dirichlet(ch.Field.shell(g2, ch.Vertex()))})))
+    with pytest.raises(ValueError):                              # a 3D value field for a 3D grid: the mirror refuses it itself
+        la.validate(g, op, bc=ch.batch(g, (T, {"x": ch.Dirichlet(F(ch, g))})))
+    d = la.describe(None, g, op, bc=ch.batch(g, (T, {"x": ch.Dirichlet(ch.Field.shell(g2, ch.Vertex()))})))
+    d.bc[0][0].value_field[0] = T.handle                         # ... and so does the library for a hand-made descriptor
+    assert L.lib().chmy_validate_launch(C.byref(d)) != 0 and b"value field must have 2 dims" in L.lib().chmy_last_error()
+    with pytest.raises(ch.ChmyError, match="element type"):
+        la.validate(g, op, bc=ch.batch(g, (T, {"x": ch.Dirichlet(ch.Field.shell(g2, ch.Vertex(), np.float32))})))
+    with pytest.raises(ch.ChmyError, match="too small"):
+        la.validate(g, op, bc=ch.batch(g, (T, {"x": ch.Dirichlet(ch.Field.shell(grid(ch, (5, 8)), ch.Vertex()))})))
+    T32 = F(ch, grid(ch, (12, 10, 8), np.float32))
+    with pytest.raises(ch.ChmyError, match="element type"):
+        la.validate(g, op, bc=ch.batch(g, (T, ch.Neumann()), (T32, ch.Neumann())))
+    d = la.describe(None, g, op, bc=ch.batch(g, (T, ch.Neumann())))
+    d.bc[0][1].kind = L.BATCH_EXCHANGE                           # a hand-made ExchangeBatch on a Bounded side
+    assert L.lib().chmy_validate_launch(C.byref(d)) != 0 and b"Bounded" in L.lib().chmy_last_error()
