@@ -107,11 +107,16 @@ def test_exact_split_is_the_reference_region_algebra(ch, n, ow):
 def test_when_there_is_no_split(ch):
     from chmy_b200 import _lib as L
     n, ow = (767, 767, 767), (128, 8, 4)
-    assert plan(ch, desc(ch, n, ow, set())[0], (60, 6, 0))[0] is False                 # no neighbour: nothing to overlap
-    assert plan(ch, desc(ch, n, None, {(0, 1)})[0], None)[0] is False                  # Launcher without outer_width
-    assert plan(ch, desc(ch, n, (128, 2, 4), {(0, 1)})[0], None)[0] is False           # a slab thinner than halo+node+send plane
-    assert plan(ch, desc(ch, (30, 22, 14), (17, 8, 4), {(0, 1)})[0], None)[0] is False  # the two x slabs would overlap
-    assert plan(ch, desc(ch, (30, 22, 14), (16, 8, 4), {(0, 1)})[0], None)[0] is True   # they just touch: an empty inner region
+
+    def split_of(n_, ow_, conn, pref):
+        d_, keep_ = desc(ch, n_, ow_, conn)          # the fields must outlive the descriptor that points at them
+        return plan(ch, d_, pref)[0]
+
+    assert split_of(n, ow, set(), (60, 6, 0)) is False                   # no neighbour: nothing to overlap
+    assert split_of(n, None, {(0, 1)}, None) is False                    # Launcher without outer_width
+    assert split_of(n, (128, 2, 4), {(0, 1)}, None) is False             # a slab thinner than halo + node + send plane
+    assert split_of((30, 22, 14), (17, 8, 4), {(0, 1)}, None) is False   # the two x slabs would overlap
+    assert split_of((30, 22, 14), (16, 8, 4), {(0, 1)}, None) is True    # they just touch: an empty inner region
     d, keep = desc(ch, n, ow, {(0, 1)})
     try:
         L.check(L.lib().chmy_set_launch_tuning(0))                                     # bench.py --no-split
