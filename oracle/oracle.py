@@ -28,8 +28,11 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libchmy_oracle.so")            # og_real = double (the solvers' element type)
-_LIB_PATH_F32 = os.path.join(_HERE, "libchmy_oracle_f32.so")    # og_real = float  (the Float32 rows of the reference's tests)
+# CHMY_ORACLE_SANITIZE=1 (tests/test_emulation_sanitizers.py's child process, which preloads the sanitizer runtimes) loads
+# AddressSanitizer + UBSan builds of the same source instead
+_SAN = "_san" if os.environ.get("CHMY_ORACLE_SANITIZE") == "1" else ""
+_LIB_PATH = os.path.join(_HERE, f"libchmy_oracle{_SAN}.so")            # og_real = double (the solvers' element type)
+_LIB_PATH_F32 = os.path.join(_HERE, f"libchmy_oracle_f32{_SAN}.so")    # og_real = float  (the Float32 rows of the reference's tests)
 
 CENTER, VERTEX = 0, 1
 BOUNDED, CONNECTED = 0, 1
