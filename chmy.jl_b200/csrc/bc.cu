@@ -7,63 +7,21 @@
 // Face range: src/BoundaryConditions/batch.jl:159-184 -- transverse index I_t = J-1 in 0..n_t+2, fields of a batch
 // applied in batch order.  Halo slabs: src/Distributed/communication_views.jl:1-34.
 #include "common.cuh"
+#include "bc_kernels.cuh"      // BcEntry, BcBatchDev, bc_point ; SlabEntry, SlabBatch, slab_point (shared with the host emulation)
+
+template <class T>
+static BckView<T> bck_view(const chmy_field* f) {
+    return BckView<T>{reinterpret_cast<T*>(f->p0), f->nd > 1 ? f->stride[1] : 0, f->nd > 2 ? f->stride[2] : 0};
+}
 
 // ---------------------------------------------------------------------------------------------- BC batches
-template <class T>
-struct BcEntry {
-    FVT<T> f;
-    int    kind;      // chmy_bc_kind
-    int    vertex;    // location of the field along the BC dim
-    int    d;         // logical size of the field along the BC dim
-    int    side;      // 0 | 1
-    T      value;
-    const T*  vp;     // Field-valued condition: logical (0[,0]) of the (N-1)-dimensional value field, else nullptr
-    long long vsy;
-};
-
-template <class T>
-struct BcBatchDev {
-    int        n;                                // entries (both sides of one dim)
-    int        dim;
-    int        nt[2];                            // transverse extents (n_t + 3 points each; 1 when absent)
-    T          spacing;
-    BcEntry<T> e[2 * CHMY_MAX_BATCH_FIELDS];
-};
-
-// One thread per face point; both sides and all fields of a dimension in one launch.  Entries of different sides
-// touch disjoint cells and different fields are independent, so the reference's sequential order
-// (side 1 then 2, fields in batch order) is preserved per cell.
+// One thread per face point; both sides and all fields of a dimension in one launch (bc_point).
 template <class T>
 __global__ void __launch_bounds__(256) k_bc_dim(const BcBatchDev<T> b) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;   // first transverse index  (0..nt0-1)
     const int c = blockIdx.y;                              // second transverse index (0..nt1-1)
     if (a >= b.nt[0]) return;
-    for (int q = 0; q < b.n; ++q) {
-        const BcEntry<T>& e = b.e[q];
-        int I[3], N[3];
-        // insert_dim(dim, (a, c), idx)  -- src/utils.jl:47-51
-        int t = 0;
-        const int tr[2] = {a, c};
-        const int bnode = e.side == 0 ? 1 : e.d;
-        const int hnode = e.side == 0 ? 0 : e.d + 1;
-        for (int dd = 0; dd < 3; ++dd) {
-            if (dd == b.dim) { I[dd] = hnode; N[dd] = bnode; }
-            else { I[dd] = N[dd] = (t < 2 ? tr[t] : 0); ++t; }
-        }
-        // value(bc, grid, loc, dim, I...): Number | bc.value[remove_dim(dim, I)...]  (first_order_boundary_condition.jl:34-40)
-        const T val = e.vp ? e.vp[(long long)a + (long long)c * e.vsy] : e.value;
-        if (e.kind == CHMY_DIRICHLET) {
-            if (e.vertex) {
-                fv_st(e.f, N[0], N[1], N[2], val);
-            } else {
-                const T nb = fv_ld(e.f, N[0], N[1], N[2]);
-                fv_st(e.f, I[0], I[1], I[2], fma((T)2.0, val - nb, nb));
-            }
-        } else {
-            const T qs = e.side == 0 ? -val : val;
-            fv_st(e.f, I[0], I[1], I[2], fma(b.spacing, qs, fv_ld(e.f, N[0], N[1], N[2])));
-        }
-    }
+    bc_point(b, a, c);
 }
 
 // Everything a batch must satisfy, checked BEFORE the launch it belongs to starts (chmy_validate_launch / chmy_bc): a
@@ -116,7 +74,7 @@ static int run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chm
                 CHMY_REQUIRE(f->d[a] == g->n[a] + (f->loc[a] == CHMY_VERTEX ? 1 : 0), "FieldBatch: field/grid size mismatch");
             bd->fields[q]->frame_synced = false;      // a halo of a Vertex field lies outside the ops' index range
             BcEntry<T>& e = b.e[b.n++];
-            e.f = f->viewT<T>(); e.kind = bd->bc_kind[q]; e.vertex = f->loc[dim] == CHMY_VERTEX; e.d = (int)f->d[dim];
+            e.f = bck_view<T>(f); e.kind = bd->bc_kind[q]; e.vertex = f->loc[dim] == CHMY_VERTEX; e.d = (int)f->d[dim];
             e.side = s; e.value = (T)bd->value[q];
             e.vp = nullptr; e.vsy = 0;
             if (const chmy_field* vf = bd->value_field[q]) {
@@ -157,8 +115,7 @@ int chmy_run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_
 }
 
 // ---------------------------------------------------------------------------------------------- halo slabs
-// send index: side 1 -> 1+overlap, side 2 -> d-overlap (overlap = 1 for Vertex, 0 for Center);
-// recv index: side 1 -> 0, side 2 -> d+1; every other dimension spans the whole padded extent -1..d+2.
+// (geometry and per-element body: bc_kernels.cuh)
 long long chmy_slab_len(const chmy_field* f, int dim) {
     long long len = 1;
     for (int a = 0; a < f->nd; ++a)
@@ -166,35 +123,9 @@ long long chmy_slab_len(const chmy_field* f, int dim) {
     return len;
 }
 
-template <class T>
-struct SlabEntry {
-    FVT<T>    f;
-    int       idx;        // logical index of the slab along dim
-    int       e0, e1;     // transverse extents (sd_t), 1 when absent
-    long long off;        // element offset of this field's slab in the buffer
-};
-template <class T>
-struct SlabBatch {
-    int          n, dim, nd;
-    SlabEntry<T> e[CHMY_MAX_BATCH_FIELDS];
-};
-
 template <bool PACK, class T>
 __global__ void __launch_bounds__(256) k_slab(const SlabBatch<T> b, T* __restrict__ buf) {
-    const SlabEntry<T>& e = b.e[blockIdx.z];
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = blockIdx.y * blockDim.y + threadIdx.y;
-    if (a >= e.e0 || c >= e.e1) return;
-    int I[3], t = 0;
-    const int tr[2] = {a - 1, c - 1};           // storage 0 <-> logical -1
-    for (int dd = 0; dd < 3; ++dd) {
-        if (dd == b.dim) I[dd] = e.idx;
-        else if (dd >= b.nd) I[dd] = 0;          // inactive dimension
-        else { I[dd] = tr[t]; ++t; }
-    }
-    const long long p = e.off + (long long)a + (long long)c * e.e0;
-    if (PACK) buf[p] = fv_ld(e.f, I[0], I[1], I[2]);
-    else fv_st(e.f, I[0], I[1], I[2], buf[p]);
+    slab_point<PACK, T>(b, buf, blockIdx.z, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y);
 }
 
 template <class T>
@@ -209,7 +140,7 @@ static int make_slab_batch(int dim, int side, int nf, chmy_field* const* fs, boo
         CHMY_REQUIRE(f != nullptr && f->alloc != nullptr && dim < f->nd, "exchange: bad field %d", q);
         const int ov = f->loc[dim] == CHMY_VERTEX ? 1 : 0;
         SlabEntry<T>& e = b.e[q];
-        e.f   = f->viewT<T>();
+        e.f   = bck_view<T>(f);
         e.idx = send ? (side == 0 ? 1 + ov : (int)f->d[dim] - ov) : (side == 0 ? 0 : (int)f->d[dim] + 1);
         int t = 0, ext[2] = {1, 1};
         for (int a = 0; a < f->nd; ++a)
