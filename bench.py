@@ -63,6 +63,10 @@ def parse():
                          "batches (the reference's order), off = one full-range kernel then batches + exchange, auto = the "
                          "library times both on the first launches and keeps the faster (results are identical)")
     ap.add_argument("--no-split", action="store_true", help="same as --split off")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                    help="multi-GPU: transport of the halo exchange -- nccl = pack + ncclSend/ncclRecv + unpack (the measured path), "
+                         "peer = EXPERIMENTAL: the pack kernels store into the neighbour's HBM over NVLink, sequence flags instead "
+                         "of the NCCL group (chmy_set_exchange_mode; results are identical)")
     ap.add_argument("--fused", type=int, default=1, choices=[0, 1, 3],
                     help="3D Stokes: lazily fuse update_stress! + update_velocity! into one sweep (chmy_set_fusion); "
                          "0 = the two tuned kernels; 3 = additionally the EXPERIMENTAL sweeps (2D workloads; 3D thermal pair)")
@@ -236,6 +240,7 @@ def run_b200(args):
         nd = len(WORKLOADS[args.workload][0])
         arch = ch.Arch(backend, ch.TorchDistComm(), (0,) * nd, device_id=local_rank + 1)
         pdims = arch.topology.dims
+        ch.set_exchange_mode(arch, args.exchange)
     else:
         arch = ch.Arch(backend, device_id=local_rank + 1)
         pdims = None
@@ -312,6 +317,7 @@ def run_b200(args):
     ms_local = ch.event_elapsed_ms(arch, 0, 1)
     l1 = ch.launch_count(arch)
     nfused = ch.fused_count(arch)
+    xstats = dict(zip(("peer", "nccl"), ch.exchange_stats(arch))) if world > 1 else None     # rank 0's messages so far
     clocks = sampler.stop() if rank == 0 else None
     ch.barrier(arch)
     (ms_max,) = ch.allreduce_max(arch, ms_local) if world > 1 else (ms_local,)
@@ -444,11 +450,11 @@ def run_b200(args):
             "ms_per_step": t_it * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[wl][2], "n_local": list(n), "proc_dims": list(pdims) if pdims else [1] * len(n),
-                       "nIO": WORKLOADS[wl][1], "fused_sweep": fused, "split_launches": split_mode, "A_eff_GB_per_gpu": a_eff_bytes(wl, n) / 1e9,
+                       "nIO": WORKLOADS[wl][1], "fused_sweep": fused, "split_launches": split_mode, "exchange": (args.exchange if world > 1 else None), "A_eff_GB_per_gpu": a_eff_bytes(wl, n) / 1e9,
                        "l2": "inputs larger than L2 (every field >= 2 GB; 126 MB L2), no flush needed",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "T_eff_per_gpu": teff_gpu, "frac_of_hbm_peak": teff_gpu / peak, "hbm_peak": peak, "hbm_peak_source": peak_src,
-            "clocks": clocks, "gpu_launches": int(l1 - l0), "fused_sweeps": int(nfused), "roofline": roofline, "e2e": e2e, "cpu_baseline": cb,
+            "clocks": clocks, "gpu_launches": int(l1 - l0), "fused_sweeps": int(nfused), "exchange_msgs": xstats, "roofline": roofline, "e2e": e2e, "cpu_baseline": cb,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -109,6 +109,8 @@ SYMBOLS = {
     "chmy_bc": (C.c_int, [_vp, _P(GridDesc), _P(BatchDesc * 2), C.c_int]),
     "chmy_exchange_halo": (C.c_int, [_vp, _P(GridDesc), C.c_int, C.c_int, C.c_int, _P(_vp), C.c_int]),
     "chmy_exchange_halo_all": (C.c_int, [_vp, _P(GridDesc), C.c_int, _P(_vp), C.c_int]),
+    "chmy_set_exchange_mode": (C.c_int, [_vp, C.c_int]),
+    "chmy_exchange_stats": (C.c_int, [_vp, _P(C.c_uint64), _P(C.c_uint64)]),
     "chmy_selftest_division": (C.c_int, [_vp, C.c_double, C.c_longlong, C.c_ulonglong, _P(C.c_ulonglong), _P(C.c_int)]),
     "chmy_set_tuning": (C.c_int, [C.c_int, C.c_int]),
     "chmy_set_launch_tuning": (C.c_int, [C.c_int]),

@@ -167,6 +167,23 @@ def set_launch_split(split="auto"):
     L.check(L.lib().chmy_set_launch_tuning(2 if split == "auto" else (1 if split else 0)))
 
 
+def set_exchange_mode(arch: Architecture, mode="nccl"):
+    """Transport of the halo exchange on a distributed architecture: "nccl" (default, the measured path) or "peer"
+    (EXPERIMENTAL: the pack kernels store straight into the neighbour's HBM over NVLink, sequence flags instead of
+    ncclSend/ncclRecv).  Every rank must choose the same; results are identical (include/chmy_b200.h: chmy_set_exchange_mode)."""
+    modes = {"nccl": 0, "peer": 1}
+    if mode not in modes:
+        raise ValueError(f"exchange mode must be one of {sorted(modes)}, got {mode!r}")
+    L.check(L.lib().chmy_set_exchange_mode(arch.ctx, modes[mode]))
+
+
+def exchange_stats(arch: Architecture):
+    """(messages sent as peer stores, messages sent through NCCL) so far on this rank."""
+    a, b = C.c_uint64(), C.c_uint64()
+    L.check(L.lib().chmy_exchange_stats(arch.ctx, C.byref(a), C.byref(b)))
+    return int(a.value), int(b.value)
+
+
 def topology(arch: DistributedArchitecture):
     return arch.topology
 

@@ -137,7 +137,7 @@ extern "C" int chmy_synchronize(chmy_ctx* c) {
     CHMY_CUDA(cudaSetDevice(c->device));
     CHMY_CUDA(cudaStreamSynchronize(c->s_bnd));
     CHMY_CUDA(cudaStreamSynchronize(c->s_main));
-    return CHMY_OK;
+    return chmy_comm_check(c->comm);
 }
 
 extern "C" int chmy_ctx_launch_count(const chmy_ctx* c, uint64_t* kernels) {

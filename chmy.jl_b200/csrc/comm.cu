@@ -12,6 +12,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "peer_link.cuh"   // protocol of the peer-store exchange (CHMY_EXCHANGE_PEER), shared with its host emulation
 
 struct NcclApi {
     void* handle;
@@ -75,6 +76,17 @@ struct chmy_comm {
     double*    rbuf[2];
     size_t     cap[2];              // elements
     double*    d_scal;              // scratch for scalar all-reduces
+    // ---- peer-store exchange (CHMY_EXCHANGE_PEER; peer_link.cuh): one link per neighbour
+    int        xmode;               // chmy_exchange_mode
+    PlLink     link[3][2];
+    void*      grave[64];           // blocks replaced by larger ones or never paired: the peer may still have them mapped,
+    int        ngrave;              //   so they are only freed with the communicator
+    char*      d_stage;             // hand-shake staging: 128 B out, 128 B in
+    char*      h_stage;             // pinned twin
+    int*       h_err;               // pinned + mapped: non-zero once a flag wait has timed out
+    int*       d_err;               // device alias of h_err
+    unsigned long long timeout_ns;  // flag waits give up after this long instead of hanging the device
+    uint64_t   n_peer_msgs, n_nccl_msgs;
 };
 
 // ---------------------------------------------------------------------------------------------- topology
@@ -161,6 +173,13 @@ extern "C" int chmy_topo_create(chmy_ctx* ctx, int nranks, int rank, int ndims, 
         }
     }
     CHMY_CUDA(cudaMalloc(&c->d_scal, 64 * sizeof(double)));
+    for (int a = 0; a < 3; ++a)
+        for (int s = 0; s < 2; ++s) { memset(&c->link[a][s], 0, sizeof(PlLink)); c->link[a][s].peer = c->nb[a][s]; }
+    const char* xm = getenv("CHMY_EXCHANGE");
+    c->xmode = (xm && (xm[0] == 'p' || xm[0] == 'P' || xm[0] == '1')) ? CHMY_EXCHANGE_PEER : CHMY_EXCHANGE_NCCL;
+    const char* to = getenv("CHMY_PEER_TIMEOUT_S");
+    const double to_s = to ? atof(to) : 20.0;
+    c->timeout_ns = (unsigned long long)((to_s > 0.0 ? to_s : 20.0) * 1.0e9);
     ctx->comm = c;
     return CHMY_OK;
 }
@@ -169,6 +188,15 @@ int chmy_comm_destroy(chmy_comm* c) {
     if (!c) return CHMY_OK;
     for (int s = 0; s < 2; ++s) { cudaFree(c->sbuf[s]); cudaFree(c->rbuf[s]); }
     cudaFree(c->d_scal);
+    for (int a = 0; a < 3; ++a)
+        for (int s = 0; s < 2; ++s) {
+            if (c->link[a][s].remote) cudaIpcCloseMemHandle(c->link[a][s].remote);
+            if (c->link[a][s].local) cudaFree(c->link[a][s].local);
+        }
+    for (int q = 0; q < c->ngrave; ++q) cudaFree(c->grave[q]);
+    if (c->d_stage) cudaFree(c->d_stage);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_err) cudaFreeHost(c->h_err);
     if (c->nccl) g_nccl.CommDestroy(c->nccl);
     free(c);
     return CHMY_OK;
@@ -221,6 +249,203 @@ static int ensure_bufs(chmy_comm* c, int s, size_t elems) {
     return CHMY_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- peer-store exchange
+// CHMY_EXCHANGE_PEER (opt-in; peer_link.cuh has the protocol): the pack kernel writes straight into the neighbour's HBM over
+// NVLink and one sequence flag per direction replaces ncclSend / ncclRecv.  NCCL is still used once per link to swap the
+// CUDA IPC handles.  A link whose block cannot be mapped on either end falls back to NCCL for good (both ends agree).
+struct PlFlagArgs {
+    uint64_t*          post[2];
+    uint64_t           post_val[2];
+    const uint64_t*    wait[2];
+    uint64_t           wait_val[2];
+    unsigned long long timeout_ns;
+    int*               err;
+};
+
+__device__ __forceinline__ void pl_st_release_sys(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t pl_ld_acquire_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long pl_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// One thread: post the flags (after everything this stream has written, peer memory included), then wait for the local
+// ones.  A wait that outlasts timeout_ns raises *err and returns: a lost neighbour must not hang the device.
+__global__ void k_pl_flags(const PlFlagArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int s = 0; s < 2; ++s)
+        if (a.post[s]) { __threadfence_system(); pl_st_release_sys(a.post[s], a.post_val[s]); }
+    for (int s = 0; s < 2; ++s) {
+        if (!a.wait[s]) continue;
+        const unsigned long long t0 = pl_now_ns();
+        while (pl_ld_acquire_sys(a.wait[s]) < a.wait_val[s]) {
+            if (pl_now_ns() - t0 > a.timeout_ns) {
+                *(volatile int*)a.err = 1 + s;
+                __threadfence_system();
+                return;
+            }
+            __nanosleep(100);
+        }
+    }
+}
+
+int chmy_comm_check(const chmy_comm* c) {
+    if (c && c->h_err && *(volatile int*)c->h_err) {
+        chmy_set_error("peer-store halo exchange: waiting for the neighbour on side %d timed out", *(volatile int*)c->h_err);
+        return CHMY_ERR_STATE;
+    }
+    return CHMY_OK;
+}
+
+static int pl_resources(chmy_comm* c) {
+    if (c->d_stage) return CHMY_OK;
+    CHMY_CUDA(cudaMalloc(&c->d_stage, 256));
+    CHMY_CUDA(cudaHostAlloc(&c->h_stage, 256, cudaHostAllocDefault));
+    CHMY_CUDA(cudaHostAlloc(&c->h_err, sizeof(int), cudaHostAllocMapped));
+    *c->h_err = 0;
+    CHMY_CUDA(cudaHostGetDevicePointer(&c->d_err, c->h_err, 0));
+    return CHMY_OK;
+}
+
+// swap up to 128 bytes with a neighbour (host to host, through the stream and NCCL); blocks until both have theirs
+static int pl_swap(chmy_comm* c, int peer, const void* out, void* in, size_t n, cudaStream_t st) {
+    CHMY_REQUIRE(n <= 128, "hand-shake message too long");
+    memcpy(c->h_stage, out, n);
+    CHMY_CUDA(cudaMemcpyAsync(c->d_stage, c->h_stage, n, cudaMemcpyHostToDevice, st));
+    CHMY_NCCL(g_nccl.GroupStart());
+    CHMY_NCCL(g_nccl.Recv(c->d_stage + 128, n, ncclChar, peer, c->nccl, st));
+    CHMY_NCCL(g_nccl.Send(c->d_stage, n, ncclChar, peer, c->nccl, st));
+    CHMY_NCCL(g_nccl.GroupEnd());
+    CHMY_CUDA(cudaMemcpyAsync(c->h_stage + 128, c->d_stage + 128, n, cudaMemcpyDeviceToHost, st));
+    CHMY_CUDA(cudaStreamSynchronize(st));
+    memcpy(in, c->h_stage + 128, n);
+    return CHMY_OK;
+}
+
+static void pl_bury(chmy_comm* c, void* blk) {
+    if (!blk) return;
+    if (c->ngrave < 64) c->grave[c->ngrave++] = blk;     // beyond that the block leaks until the process ends
+}
+
+struct PlHello {
+    cudaIpcMemHandle_t h;
+    uint64_t           cap;
+    uint64_t           cookie;      // what the block holds at PL_OFF_COOKIE
+    int32_t            ok;
+    int32_t            pad;
+};
+static_assert(sizeof(PlHello) <= 128, "PlHello must fit the staging line");
+
+// Makes link (D, s) ready for a message of need_bytes.  Both ends of a link see the same message sizes, so both get here
+// -- first use, or growth -- in the same exchange and pair their hand-shakes.
+static int pl_link_ensure(chmy_comm* c, int D, int s, size_t need_bytes, cudaStream_t st) {
+    PlLink& l = c->link[D][s];
+    if (l.mode == PL_MODE_NCCL) return CHMY_OK;
+    if (l.mode == PL_MODE_PEER && need_bytes <= l.cap) return CHMY_OK;
+    CHMY_TRY(pl_resources(c));
+    const size_t cap = pl_grow_cap(l.mode == PL_MODE_PEER ? l.cap : 0, need_bytes);
+    PlHello mine, theirs;
+    memset(&mine, 0, sizeof(mine));
+    memset(&theirs, 0, sizeof(theirs));
+    char* blk = nullptr;
+    cudaError_t e = cudaMalloc(&blk, pl_block_bytes(cap));
+    if (e == cudaSuccess) e = cudaMemsetAsync(blk, 0, pl_block_bytes(cap), st);     // flags start at 0; ordered before the swap
+    // the nonce: distinct per rank, link and (re)allocation
+    mine.cookie = 0x9e3779b97f4a7c15ull * (uint64_t)(c->rank + 1) ^ ((uint64_t)(D * 2 + s + 1) << 56) ^ (uint64_t)(uintptr_t)blk ^ (uint64_t)cap;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(blk + PL_OFF_COOKIE, &mine.cookie, sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&mine.h, blk);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    mine.ok = e == cudaSuccess;
+    mine.cap = cap;
+    CHMY_TRY(pl_swap(c, l.peer, &mine, &theirs, sizeof(PlHello), st));
+    char* remote = nullptr;
+    int32_t mapped = 0, peer_mapped = 0;
+    if (mine.ok && theirs.ok && theirs.cap == cap) {
+        e = cudaIpcOpenMemHandle((void**)&remote, theirs.h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); remote = nullptr; }
+        if (remote) {        // does the mapping address the block the peer meant (and can this device read it)?
+            uint64_t got = 0;
+            e = cudaMemcpy(&got, remote + PL_OFF_COOKIE, sizeof(got), cudaMemcpyDefault);
+            if (e != cudaSuccess) (void)cudaGetLastError();
+            if (e != cudaSuccess || got != theirs.cookie) { cudaIpcCloseMemHandle(remote); remote = nullptr; }
+        }
+        mapped = remote != nullptr;
+    }
+    CHMY_TRY(pl_swap(c, l.peer, &mapped, &peer_mapped, sizeof(mapped), st));
+    // retire what the link had: my stores into the old mapping precede the synchronised swaps in stream order
+    if (l.remote) cudaIpcCloseMemHandle(l.remote);
+    pl_bury(c, l.local);
+    l.local = l.remote = nullptr;
+    l.cap = 0;
+    l.seq = 0;
+    if (mapped && peer_mapped) {
+        l.local = blk; l.remote = remote; l.cap = cap; l.mode = PL_MODE_PEER;
+    } else {
+        if (remote) cudaIpcCloseMemHandle(remote);
+        pl_bury(c, blk);
+        l.mode = PL_MODE_NCCL;
+    }
+    return CHMY_OK;
+}
+
+// the three stream operations of pl_exchange_dim (peer_link.cuh) as kernel launches on `st`
+struct CudaPlOps {
+    chmy_ctx*                     ctx;
+    chmy_comm*                    c;
+    int                           D;
+    const chmy_batch_desc* const* side;
+    cudaStream_t                  st;
+
+    int flags(PlFlagArgs& a) const {
+        a.timeout_ns = c->timeout_ns;
+        a.err        = c->d_err;
+        k_pl_flags<<<1, 32, 0, st>>>(a);
+        ctx->n_launches++;
+        CHMY_CUDA(cudaGetLastError());
+        return CHMY_OK;
+    }
+    int push(int s, PlLink& l, int slot) const {
+        c->n_peer_msgs++;
+        return chmy_pack_fields(ctx, D, s, side[s]->nfields, side[s]->fields, l.remote + pl_off_slot(slot, l.cap), st);
+    }
+    int post_and_wait(PlLink* const l[2], const uint64_t k[2]) const {
+        PlFlagArgs a;
+        memset(&a, 0, sizeof(a));
+        for (int s = 0; s < 2; ++s)
+            if (l[s]) {
+                a.post[s] = pl_flag(l[s]->remote, PL_OFF_DATA); a.post_val[s] = k[s];
+                a.wait[s] = pl_flag(l[s]->local, PL_OFF_DATA);  a.wait_val[s] = k[s];
+            }
+        return flags(a);
+    }
+    int unpack(int s, PlLink& l, int slot) const {
+        return chmy_unpack_fields(ctx, D, s, side[s]->nfields, side[s]->fields, l.local + pl_off_slot(slot, l.cap), st);
+    }
+};
+
+extern "C" int chmy_set_exchange_mode(chmy_ctx* ctx, int mode) {
+    CHMY_REQUIRE(ctx != nullptr, "ctx is NULL");
+    CHMY_REQUIRE(mode == CHMY_EXCHANGE_NCCL || mode == CHMY_EXCHANGE_PEER, "bad exchange mode %d", mode);
+    if (!ctx->comm) { chmy_set_error("architecture has no topology"); return CHMY_ERR_STATE; }
+    CHMY_TRY(chmy_flush(ctx));
+    ctx->comm->xmode = mode;
+    return CHMY_OK;
+}
+
+extern "C" int chmy_exchange_stats(const chmy_ctx* ctx, uint64_t* peer_msgs, uint64_t* nccl_msgs) {
+    CHMY_REQUIRE(ctx && peer_msgs && nccl_msgs, "NULL argument");
+    *peer_msgs = ctx->comm ? ctx->comm->n_peer_msgs : 0;
+    *nccl_msgs = ctx->comm ? ctx->comm->n_nccl_msgs : 0;
+    return CHMY_OK;
+}
+
 // Both sides of one dimension: pack -> {send, recv} x sides in one NCCL group -> unpack, all on `st`.
 // Slab geometry: communication_views.jl:1-34; message pairing: my side S talks to the neighbour's side 1-S.
 int chmy_exchange_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int D, const chmy_batch_desc* left,
@@ -229,7 +454,8 @@ int chmy_exchange_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int D, const chmy_
     const chmy_batch_desc* side[2] = {left, right};
     chmy_comm* c = ctx->comm;
     if (!c) { chmy_set_error("halo exchange requested but the architecture has no topology"); return CHMY_ERR_STATE; }
-    size_t len[2] = {0, 0};
+    CHMY_TRY(chmy_comm_check(c));
+    size_t len[2] = {0, 0}, esz[2] = {8, 8};
     ncclDataType_t ty[2] = {ncclDouble, ncclDouble};      // slabs travel in the fields' element type
     for (int s = 0; s < 2; ++s) {
         if (!side[s] || side[s]->kind != CHMY_BATCH_EXCHANGE) continue;
@@ -239,20 +465,40 @@ int chmy_exchange_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int D, const chmy_
             CHMY_REQUIRE(side[s]->fields[q] != nullptr, "ExchangeBatch: NULL field");
             len[s] += (size_t)chmy_slab_len(side[s]->fields[q], D);
         }
-        if (side[s]->fields[0]->dtype == CHMY_F32) ty[s] = ncclFloat;    // chmy_pack_fields checks that the batch is uniform
-        CHMY_TRY(ensure_bufs(c, s, len[s]));
-        CHMY_TRY(chmy_pack_fields(ctx, D, s, side[s]->nfields, side[s]->fields, c->sbuf[s], st));
+        if (side[s]->fields[0]->dtype == CHMY_F32) { ty[s] = ncclFloat; esz[s] = 4; }   // chmy_pack_fields checks that the batch is uniform
     }
     if (len[0] + len[1] == 0) return CHMY_OK;
-    CHMY_NCCL(g_nccl.GroupStart());
+    // links that carry this dimension's messages as peer stores (CHMY_EXCHANGE_PEER); the others go through NCCL
+    PlLink* pl[2] = {nullptr, nullptr};
+    if (c->xmode == CHMY_EXCHANGE_PEER)
+        for (int s = 0; s < 2; ++s) {
+            if (!len[s]) continue;
+            CHMY_TRY(pl_link_ensure(c, D, s, len[s] * esz[s], st));
+            if (c->link[D][s].mode == PL_MODE_PEER) pl[s] = &c->link[D][s];
+        }
+    bool any_nccl = false;
     for (int s = 0; s < 2; ++s) {
-        if (!len[s]) continue;
-        CHMY_NCCL(g_nccl.Recv(c->rbuf[s], len[s], ty[s], c->nb[D][s], c->nccl, st));
-        CHMY_NCCL(g_nccl.Send(c->sbuf[s], len[s], ty[s], c->nb[D][s], c->nccl, st));
+        if (!len[s] || pl[s]) continue;
+        CHMY_TRY(ensure_bufs(c, s, len[s]));
+        CHMY_TRY(chmy_pack_fields(ctx, D, s, side[s]->nfields, side[s]->fields, c->sbuf[s], st));
+        any_nccl = true;
     }
-    CHMY_NCCL(g_nccl.GroupEnd());
+    if (any_nccl) {
+        CHMY_NCCL(g_nccl.GroupStart());
+        for (int s = 0; s < 2; ++s) {
+            if (!len[s] || pl[s]) continue;
+            CHMY_NCCL(g_nccl.Recv(c->rbuf[s], len[s], ty[s], c->nb[D][s], c->nccl, st));
+            CHMY_NCCL(g_nccl.Send(c->sbuf[s], len[s], ty[s], c->nb[D][s], c->nccl, st));
+            c->n_nccl_msgs++;
+        }
+        CHMY_NCCL(g_nccl.GroupEnd());
+    }
+    if (pl[0] || pl[1]) {
+        CudaPlOps ops{ctx, c, D, side, st};
+        CHMY_TRY(pl_exchange_dim(ops, pl));
+    }
     for (int s = 0; s < 2; ++s)
-        if (len[s]) CHMY_TRY(chmy_unpack_fields(ctx, D, s, side[s]->nfields, side[s]->fields, c->rbuf[s], st));
+        if (len[s] && !pl[s]) CHMY_TRY(chmy_unpack_fields(ctx, D, s, side[s]->nfields, side[s]->fields, c->rbuf[s], st));
     return CHMY_OK;
 }
 

@@ -139,6 +139,7 @@ struct chmy_field {
 };
 
 struct chmy_comm;   // comm.cu
+int chmy_comm_check(const chmy_comm* c);   // comm.cu: has a peer-store flag wait timed out?
 
 // Self-tuning split policy (api.cu): for one (op, kernel family, grid) with an exchange, the first launches are timed in
 // both orders -- overlapped inner + slabs, then one full-range kernel followed by the batches -- and the faster one is kept.

@@ -247,6 +247,19 @@ int chmy_exchange_halo(chmy_ctx* ctx, const chmy_grid_desc* grid, int dim, int s
 int chmy_exchange_halo_all(chmy_ctx* ctx, const chmy_grid_desc* grid,                  /* exchange_halo.jl:73-84 */
                            int nfields, chmy_field* const* fields, int flags);
 
+/* ---- transport of the halo exchange (exchange_halo.jl:13-61: Irecv + pack + Isend per field, host poll, unpack) ---------
+ * CHMY_EXCHANGE_NCCL (default; measured on B200, profiles/): one pack kernel per (dim, side) for all fields, both sides of a
+ *   dimension in one ncclSend/ncclRecv group, one unpack kernel per side.
+ * CHMY_EXCHANGE_PEER (EXPERIMENTAL: protocol proven on the CPU by tests/test_peer_protocol.py, not yet run on a GPU): the
+ *   pack kernel stores the slabs straight into a receive slot in the neighbour's HBM (mapped with CUDA IPC, written over
+ *   NVLink) and one sequence flag per direction replaces the NCCL group; NCCL only swaps the IPC handles once per link.
+ *   A link whose memory cannot be mapped on either end keeps using NCCL (both ends agree).  Waits give up after
+ *   CHMY_PEER_TIMEOUT_S (default 20) and the next call on the context reports it.
+ * Every rank of a topology must choose the same mode; results are identical.  Env: CHMY_EXCHANGE=nccl|peer. */
+typedef enum { CHMY_EXCHANGE_NCCL = 0, CHMY_EXCHANGE_PEER = 1 } chmy_exchange_mode;
+int chmy_set_exchange_mode(chmy_ctx* ctx, int mode);
+int chmy_exchange_stats(const chmy_ctx* ctx, uint64_t* peer_msgs, uint64_t* nccl_msgs);   /* messages sent so far per transport */
+
 /* ---- self-test and tuning hooks (used by tests/ and bench.py; not part of the reference's surface) -------- */
 /* counts operands x (n pseudo-random ones from `seed`) for which the exact-division sequence used by the tuned
  * kernels for kernel-uniform divisors differs bitwise from IEEE x / c; *markstein_used = 0 when c is routed to the

@@ -269,6 +269,12 @@ end
 fuse!(arch::SingleDeviceArchitecture{B200Backend}, on::Bool=true) =
     check(ccall((:chmy_set_fusion, libchmy), Cint, (Ptr{Cvoid}, Cint), ctx(arch), on))
 
+# Transport of exchange_halo! on a distributed architecture (include/chmy_b200.h: chmy_set_exchange_mode): :nccl (default) or
+# :peer (EXPERIMENTAL: pack kernels store into the neighbour's HBM over NVLink, sequence flags instead of ncclSend/ncclRecv).
+# Every rank must choose the same; results are identical.
+exchange_mode!(arch, mode::Symbol) =
+    check(ccall((:chmy_set_exchange_mode, libchmy), Cint, (Ptr{Cvoid}, Cint), ctx(arch), mode === :peer ? 1 : 0))
+
 # Distributed: Arch(B200Backend(), comm, dims) builds the CartesianTopology with MPI exactly as the reference does
 # (topology.jl:26-41) and then hands rank/size/dims plus an MPI-broadcast NCCL id to chmy_topo_create; after that
 # exchange_halo! never touches MPI.

@@ -137,6 +137,16 @@ class DryRunLib:
     def chmy_set_launch_tuning(self, a):
         return 0
 
+    def chmy_set_exchange_mode(self, ctx, mode):          # transport only: results cannot depend on it
+        self.ctxs[self._h(ctx)]["xmode"] = int(mode)
+        return 0
+
+    def chmy_exchange_stats(self, ctx, peer, nccl):
+        c = self.ctxs[self._h(ctx)]
+        self._set(peer, c.get("peer_msgs", 0))
+        self._set(nccl, c.get("nccl_msgs", 0))
+        return 0
+
     def chmy_set_fused_tuning(self, *a):
         return 0
 
@@ -248,6 +258,9 @@ class DryRunLib:
             if nb < 0:
                 raise RuntimeError("no neighbor to communicate")
             msg = np.concatenate([np.asarray(self.o.pack_send(f, D, S), dtype=np.float64) for f in fields])
+            c = self.ctxs[self._h(ctx)]           # one message per (dim, side), counted under the chosen transport
+            key = "peer_msgs" if c.get("xmode", 0) == 1 else "nccl_msgs"
+            c[key] = c.get(key, 0) + 1
             reqs.append(dist.isend(torch.from_numpy(msg.copy()), nb, tag=2 * D + (1 - S)))
             recv[S] = torch.empty(msg.size, dtype=torch.float64)
             reqs.append(dist.irecv(recv[S], nb, tag=2 * D + S))

@@ -74,7 +74,11 @@ def _worker(rank, world, port, case, q):
         from chmy_b200 import drivers as BD
         kind, n = case
         nd = len(n)
+        peer = kind.endswith("+peer")        # EXPERIMENTAL transport: peer stores + sequence flags instead of NCCL send/recv
+        kind = kind[:-5] if peer else kind
         arch = ch.Arch(ch.B200Backend(), ch.TorchDistComm(), (0,) * nd, device_id=rank + 1)
+        if peer:
+            ch.set_exchange_mode(arch, "peer")
         pd = arch.topology.dims
         assert pd == o.dims_create(world, (0,) * nd)
         if kind == "exchange":
@@ -96,6 +100,21 @@ def _worker(rank, world, port, case, q):
             ch.exchange_halo_(arch, g, *bfs)
             for f, of, l in zip(bfs, ofs[rank], locs):
                 _cmp(f"exchange loc={l}", of.data, f.parent(), 0.0)
+            if peer:
+                # again, several times, on changed contents: slots alternate, the flags keep counting, nothing stale survives
+                for rep in range(5):
+                    for r in range(world):
+                        for f in ofs[r]:
+                            f.data[...] = _encode(f.sdims, r + 10 * (rep + 1))
+                    for f, of in zip(bfs, ofs[rank]):
+                        f.from_host(of.data.copy(), [-1] * nd, [d + 2 for d in of.dims])
+                    o.bc_world(ogs, [o.batch(ogs[r], exchange=tuple(ofs[r])) for r in range(world)], topos)
+                    ch.exchange_halo_(arch, g, *bfs)
+                    ch.synchronize(arch)
+                    for f, of, l in zip(bfs, ofs[rank], locs):
+                        _cmp(f"exchange rep={rep} loc={l}", of.data, f.parent(), 0.0)
+                sent_peer, sent_nccl = ch.exchange_stats(arch)
+                assert sent_peer > 0 and sent_nccl == 0, (sent_peer, sent_nccl)      # every link mapped: nothing fell back
             q.put((rank, "ok", 0.0))
             return
         if kind == "diffusion":
@@ -122,6 +141,9 @@ def _worker(rank, world, port, case, q):
             assert bsol.dt == osol.dt and bsol.eta_ve == osol.eta_ve
             if kind == "stokes_fused":
                 assert ch.fused_count(arch) == 80
+        if peer:
+            sent_peer, sent_nccl = ch.exchange_stats(arch)
+            assert sent_peer > 0 and sent_nccl == 0, (sent_peer, sent_nccl)
         worst = 0.0
         bf = bsol.fields()
         for k, f in osol.fields(rank).items():
@@ -154,6 +176,20 @@ CASES = [
 ]
 # the fused sweep is the default of the drivers and the bench: it gets every world size
 CASES.sort(key=lambda c: (c[0], c[1][0]))
+# EXPERIMENTAL peer-store transport (comm.cu, CHMY_EXCHANGE_PEER): protocol proven on the CPU (tests/test_peer_protocol.py),
+# never run on a GPU yet -> gated, and after every measured case
+PEER_CASES = [
+    (2, ("exchange+peer", (9, 7, 5))),
+    (2, ("exchange+peer", (12, 9))),
+    (2, ("stokes_fused+peer", (30, 22, 14))),
+    (2, ("diffusion+peer", (64, 48))),
+    (4, ("exchange+peer", (9, 7, 5))),
+    (4, ("stokes_fused+peer", (24, 22, 14))),
+    (8, ("exchange+peer", (9, 7, 5))),
+    (8, ("stokes_fused+peer", (24, 20, 16))),
+]
+if os.environ.get("CHMY_EXPERIMENTAL", "0") == "1":
+    CASES += PEER_CASES
 
 
 @pytest.mark.parametrize("world,case", CASES, ids=[f"{w}gpu-{c[0]}-{'x'.join(map(str, c[1]))}" for w, c in CASES])
