@@ -14,7 +14,7 @@ from .grids import (Location, Center, Vertex, flip, Bounded, Connected, UniformA
                     connectivity, spacing, inv_spacing, coord, coords, centers, vertices, origin, extent, bounds,
                     axes_names, expand_loc, nvertices, ncenters, axis, vertex, center, direction, volume, inv_volume)
 from .fields import (AbstractField, ConstantField, ZeroField, OneField, ValueField, Field, FieldTuple, VectorField, TensorField, FunctionField, init_incl, set_,
-                     interior, parent, fill_parent_, halo, location, maxabs, vector_location, pinned_array)
+                     interior, parent, fill_parent_, halo, location, maxabs, maxabs_many, vector_location, pinned_array)
 from .boundary_conditions import (BoundaryFunction, FirstOrderBC, Dirichlet, Neumann, EmptyBatch, FieldBatch, ExchangeBatch, batch, bc_)
 from .kernel_launch import (Launcher, worksize, outer_width, inner_worksize, inner_offset, outer_worksize,
                             outer_offset)

@@ -408,6 +408,39 @@ extern "C" int chmy_field_maxabs(chmy_ctx* ctx, const chmy_field* f, const int64
     return CHMY_OK;
 }
 
+// The residual check of the drivers (stokes_3d_inc_ve_T.jl:171-175: maximum(abs.(interior(f))) of four fields, each a
+// mapreduce + a host synchronisation in the reference) as ONE round trip: n reductions back to back on the main stream,
+// one device-to-host copy, one synchronisation.  lo / hi: n x CHMY_MAX_DIMS logical bounds.
+extern "C" int chmy_field_maxabs_many(chmy_ctx* ctx, int n, const chmy_field* const* fields, const int64_t* lo, const int64_t* hi,
+                                      double* out) {
+    CHMY_REQUIRE(ctx && fields && lo && hi && out, "NULL argument");
+    CHMY_REQUIRE(n >= 1 && n <= 64, "between 1 and 64 fields per call, got %d", n);
+    Box b[64];
+    for (int q = 0; q < n; ++q) {
+        CHMY_REQUIRE(fields[q] != nullptr, "field %d is NULL", q);
+        CHMY_TRY(chmy_box_from(fields[q], lo + 3 * q, hi + 3 * q, &b[q]));
+    }
+    CHMY_TRY(chmy_flush(ctx));
+    CHMY_CUDA(cudaSetDevice(ctx->device));
+    CHMY_CUDA(cudaStreamSynchronize(ctx->s_bnd));
+    CHMY_CUDA(cudaMemsetAsync(ctx->d_red, 0, (size_t)n * sizeof(unsigned long long), ctx->s_main));
+    for (int q = 0; q < n; ++q)
+        if (b[q].n[0] > 0 && b[q].n[1] > 0 && b[q].n[2] > 0) CHMY_TRY(chmy_maxabs_box(ctx, fields[q], b[q], ctx->d_red + q, ctx->s_main));
+    CHMY_CUDA(cudaMemcpyAsync(ctx->h_red, ctx->d_red, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->s_main));
+    CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));
+    for (int q = 0; q < n; ++q) {
+        if (fields[q]->dtype == CHMY_F32) {      // the reduction ran on binary32 bit patterns
+            const unsigned int bits = (unsigned int)ctx->h_red[q];
+            float v;
+            memcpy(&v, &bits, sizeof(v));
+            out[q] = (double)v;
+        } else {
+            memcpy(&out[q], &ctx->h_red[q], sizeof(double));
+        }
+    }
+    return CHMY_OK;
+}
+
 extern "C" int chmy_halo_slab_len(const chmy_field* f, int dim, int64_t* len) {
     CHMY_REQUIRE(f && len && dim >= 0 && dim < f->nd, "bad argument");
     *len = chmy_slab_len(f, dim);

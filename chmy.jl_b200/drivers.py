@@ -17,7 +17,7 @@ import numpy as np
 from .architectures import DistributedArchitecture, synchronize
 from .boundary_conditions import Dirichlet, Neumann, batch, bc_
 from .distributed import allreduce_max
-from .fields import Field, FunctionField, TensorField, VectorField, init_incl, interior, maxabs, set_
+from .fields import Field, FunctionField, TensorField, VectorField, init_incl, interior, maxabs, maxabs_many, set_
 from .grids import Center, UniformGrid, Vertex, spacing
 from .kernel_launch import Launcher
 from .ops import (compute_q_, update_C_, update_old_, update_stress_, update_thermal_, update_thermal_flux_,
@@ -130,7 +130,7 @@ class Stokes:
         self.launch(A, g, (update_old_, (self.T, self.tau, self.T_old, self.tau_old)))
         d = self.d
         dt_diff = _sq(min(d)) / self.lam / N / 2.1
-        vm = _gmax(A, *[maxabs(v) for v in self.V])
+        vm = _gmax(A, *maxabs_many(*self.V))                      # one device round trip for the N maxima (:158)
         with np.errstate(divide="ignore"):
             dt_adv = self.adv_coef * min(np.float64(dd) / np.float64(m) for dd, m in zip(d, vm)) / N / 2.1
         self.dt = min(dt_diff, float(dt_adv))
@@ -155,7 +155,7 @@ class Stokes:
         A, g, N = self.arch, self.grid, self.N
         ax = ("x", "y", "z")[:N]
         bc_(A, g, *[(rv, {a: Dirichlet()}) for rv, a in zip(self.r_V, ax)])
-        loc = [maxabs(self.divV)] + [maxabs(rv) for rv in self.r_V]
+        loc = maxabs_many(self.divV, *self.r_V)                   # four maxima, one round trip (:172-175)
         glob = _gmax(A, *loc)
         return (glob[0] * self.tsc,) + tuple(x * self.l[-1] / self.psc for x in glob[1:])
 

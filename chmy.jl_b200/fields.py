@@ -384,3 +384,24 @@ def maxabs(f: Field, with_halo: bool = False) -> float:
     out = C.c_double()
     L.check(L.lib().chmy_field_maxabs(f.arch.ctx, f.handle, L.i64x3(lo), L.i64x3(hi), C.byref(out)))
     return float(out.value)
+
+
+def maxabs_many(*fields: Field, with_halo: bool = False):
+    """The maxima of several fields in ONE device round trip (the residual check of the drivers,
+    stokes_3d_inc_ve_T.jl:171-175: four `maximum(abs.(interior(f)))`, each with its own host synchronisation there)."""
+    if not fields:
+        return ()
+    n = len(fields)
+    arch = fields[0].arch
+    lo, hi = (C.c_int64 * (3 * n))(), (C.c_int64 * (3 * n))()
+    hs = (C.c_void_p * n)(*[f.handle for f in fields])
+    for q, f in enumerate(fields):
+        if f.arch is not arch:
+            raise ValueError("maxabs_many: the fields must live on one architecture")
+        l, h = f._box(1 if with_halo else 0)
+        l3, h3 = L.i64x3(l), L.i64x3(h)
+        for a in range(3):
+            lo[3 * q + a], hi[3 * q + a] = l3[a], h3[a]
+    out = (C.c_double * n)()
+    L.check(L.lib().chmy_field_maxabs_many(arch.ctx, n, hs, lo, hi, out))
+    return tuple(float(x) for x in out)

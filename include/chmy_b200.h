@@ -229,6 +229,10 @@ int chmy_field_set_inclusion(chmy_ctx* ctx, chmy_field* f, const chmy_grid_desc*
                        /* set!(f, grid, init_incl; parameters) field.jl:121-142 (interior only)             */
 int chmy_field_maxabs(chmy_ctx* ctx, const chmy_field* f, const int64_t* lo, const int64_t* hi, double* out);
                        /* maximum(abs.(interior(f))) in the drivers, e.g. stokes_3d_inc_ve_T.jl:158,172-175 */
+int chmy_field_maxabs_many(chmy_ctx* ctx, int n, const chmy_field* const* fields, const int64_t* lo, const int64_t* hi,
+                           double* out);
+                       /* the residual check's four maxima (stokes_3d_inc_ve_T.jl:171-175) in ONE round trip: n <= 64
+                          reductions back to back, one copy, one synchronisation; lo / hi are n x CHMY_MAX_DIMS        */
 /* Page-locked host memory for the host side of set!(f, A) / Array(interior(f)) (field.jl:98, :33-37): copies from/to
  * such a buffer run at full PCIe/C2C rate without a staging pass.  Any host pointer is accepted by the copy entry
  * points; these two only provide the fast kind (the Julia glue wraps it with unsafe_wrap(Array, ...)). */

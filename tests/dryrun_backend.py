@@ -426,6 +426,18 @@ class DryRunLib:
         self._set(out, float("nan") if np.isnan(a).any() else (float(a.max()) if a.size else 0.0))
         return 0
 
+    def chmy_field_maxabs_many(self, ctx, n, hs, lo, hi, out):
+        self._flush_all()
+        if not 1 <= n <= 64:
+            return self._fail(-1, "between 1 and 64 fields per call")
+        for q in range(n):
+            one = C.c_double()
+            rc = self.chmy_field_maxabs(ctx, hs[q], (C.c_int64 * 3)(*lo[3 * q:3 * q + 3]), (C.c_int64 * 3)(*hi[3 * q:3 * q + 3]), C.byref(one))
+            if rc:
+                return rc
+            out[q] = one.value
+        return 0
+
     # ------------------------------------------------------------------ halo slabs (host helpers of the parity tests)
     def chmy_halo_slab_len(self, h, dim, out):
         self._set(out, int(np.prod([s for a, s in enumerate(self._F(h).f.sdims) if a != dim])))

@@ -473,3 +473,41 @@ def test_architectures_known_answers(ch):
         assert ch.is_gpu_aware(arch) is True
     finally:
         arch.close()
+
+
+# ------------------------------------------------------------------------------------------------ batched residual maxima
+@pytest.mark.parametrize("n", [(33, 18), (12, 10, 8), (9,)])
+def test_maxabs_many_equals_the_single_reductions_and_the_oracle(ch, arch, oracle, n):
+    """chmy_field_maxabs_many: the residual check's maxima (stokes_3d_inc_ve_T.jl:171-175) in one round trip -- same values
+    as one chmy_field_maxabs per field and as the oracle (max is order-independent: exact), mixed locations and element
+    types, NaN propagated like Julia's maximum."""
+    og, bg = mk_grids(ch, oracle, arch, n)
+    nd = len(n)
+    rng = np.random.default_rng(21)
+    ofs, bfs = [], []
+    for q, loc in enumerate(itertools.islice(itertools.cycle(itertools.product((0, 1), repeat=nd)), 5)):
+        of = oracle.Field(og, loc)
+        bf = ch.Field(arch, bg, tuple(ch.Vertex() if l else ch.Center() for l in loc))
+        fill_pair(rng, of, bf, scale=10.0 ** (q - 2))
+        ofs.append(of)
+        bfs.append(bf)
+    many = ch.maxabs_many(*bfs)
+    assert len(many) == 5
+    for of, bf, m in zip(ofs, bfs, many):
+        assert m == ch.maxabs(bf) == of.maxabs() == float(np.abs(of.interior()).max())
+    halo = ch.maxabs_many(*bfs, with_halo=True)
+    for of, m in zip(ofs, halo):
+        assert m == float(np.abs(of.interior(with_halo=True)).max())
+    # a NaN in the interior of one field shows in that field's maximum only
+    bad = ofs[2].data.copy()
+    bad[tuple(3 for _ in range(nd))] = np.nan
+    bfs[2].from_host(bad, [-1] * nd, [d + 2 for d in ofs[2].dims])
+    many2 = ch.maxabs_many(*bfs)
+    assert np.isnan(many2[2]) and many2[:2] == many[:2] and many2[3:] == many[3:]
+    assert ch.maxabs_many() == ()
+    # Float32 fields ride in the same call
+    bf32 = ch.Field(arch, ch.UniformGrid(arch, origin=(0.0,) * nd, extent=(1.0,) * nd, dims=n, dtype=np.float32), ch.Center())
+    a32 = (rng.random(bf32.dims) - 0.5).astype(np.float32)
+    ch.set_(bf32, a32)
+    both = ch.maxabs_many(bfs[0], bf32)
+    assert both[0] == many[0] and both[1] == float(np.abs(a32).max())
