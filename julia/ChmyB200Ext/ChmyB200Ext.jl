@@ -147,6 +147,19 @@ function maxabs(f::Field{T,N,L,H,<:B200Array}) where {T,N,L,H}                  
     return T(out[])
 end
 
+# several fields, ONE device round trip (the residual check, stokes_3d_inc_ve_T.jl:171-175): maxabs(∇V, r_V.x, r_V.y, r_V.z)
+function maxabs(f1::Field{T,N,L,H,<:B200Array}, fs::Field...) where {T,N,L,H}
+    all = (f1, fs...)
+    n   = length(all)
+    hs  = Ptr{Cvoid}[handle(f) for f in all]
+    lo  = Int64[x for f in all for x in pad3(ntuple(_ -> 1, ndims(f)), 0)]
+    hi  = Int64[x for f in all for x in pad3(size(f), 0)]
+    out = zeros(Float64, n)
+    check(ccall((:chmy_field_maxabs_many, libchmy), Cint, (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+                ctx(parent(f1).arch), n, hs, lo, hi, out))
+    return ntuple(i -> eltype(all[i])(out[i]), n)
+end
+
 # ------------------------------------------------------------------------------------------------ descriptors
 function GridDesc(grid::UniformGrid{N}) where {N}
     conn = ntuple(i -> Int32(connectivity(grid, Dim(cld(i, 2)), Side(2 - i % 2)) isa Connected), 2N)
