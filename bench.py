@@ -48,6 +48,21 @@ def measured_traffic(workload, n, kernel):
         return None
 
 
+def nearest_traffic(workload, kernel):
+    """When no capture exists at the benchmarked size: the committed capture of the same kernel at another size, with its
+    ratio to the algorithmic bytes of THAT size (evidence for how close the kernel's DRAM traffic is to its floor)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        for key, v in t.items():
+            parts = key.split(":", 2)
+            if len(parts) == 3 and parts[0] == workload and parts[2] == kernel and "algorithmic" in v:
+                return {"n": parts[1], "bytes": v["bytes"], "algorithmic": v["algorithmic"],
+                        "ratio": v["bytes"] / v["algorithmic"], "source": v.get("source")}
+    except Exception:
+        pass
+    return None
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -352,6 +367,8 @@ def run_b200(args):
                 "frac": achieved / peak, "traffic": measured_traffic(wl, n, dom_name), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": per[dom_name],
                 "step_kernels_ms": per, "share_of_step": per[dom_name] / sum(per.values())}
+    if roofline["traffic"] is None:
+        roofline["traffic_other_size"] = nearest_traffic(wl, dom_name)
 
     # ---- end to end through the public API (chmy_b200.Launcher / set! / interior) with HOST buffers.
     #      Timed with the host clock: a K-iteration solve segment whose primary unknowns start and end in host memory --
