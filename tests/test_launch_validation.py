@@ -146,6 +146,20 @@ def test_descriptor_only_fields_are_refused_by_everything_that_touches_storage(c
     for rc in (L.lib().chmy_field_fill(None, f.handle, 1.0, lo, hi),
                L.lib().chmy_field_maxabs(None, f.handle, lo, hi, C.byref(out))):
         assert rc != 0                       # NULL context / no storage: an error code, never a crash
+    # the batched reduction, through the real ctypes signature: argument checks first, storage check per field
+    f2 = F(ch, g)
+    hs = (C.c_void_p * 2)(f.handle, f2.handle)
+    lo2, hi2 = (C.c_int64 * 6)(1, 1, 0, 1, 1, 0), (C.c_int64 * 6)(8, 6, 0, 8, 6, 0)
+    out2 = (C.c_double * 2)()
+    fake_ctx = C.c_void_p(8)                 # never dereferenced: every check below fails before the context is used
+    lib = L.lib()
+    assert lib.chmy_field_maxabs_many(None, 2, hs, lo2, hi2, out2) != 0
+    assert lib.chmy_field_maxabs_many(fake_ctx, 0, hs, lo2, hi2, out2) != 0
+    assert lib.chmy_field_maxabs_many(fake_ctx, 65, hs, lo2, hi2, out2) != 0
+    assert lib.chmy_field_maxabs_many(fake_ctx, 2, hs, lo2, hi2, out2) != 0 and b"descriptor-only" in lib.chmy_last_error()
+    hs[1] = None
+    assert lib.chmy_field_maxabs_many(fake_ctx, 2, hs, lo2, hi2, out2) != 0
+    f2.free()
     f.free()
 
 
