@@ -10,7 +10,7 @@ mkdir -p $W/old $W/new
 git archive $BASE chmy.jl_b200/csrc include | tar -x -C $W/old
 git archive HEAD chmy.jl_b200/csrc include | tar -x -C $W/new
 for v in old new; do
-  for f in ops_fast ops_fused ops_fast2d; do
+  for f in ops_fast ops_fused ops_fast2d ops; do
     ( cd $W/$v/chmy.jl_b200/csrc
       /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -prec-div=true \
           -prec-sqrt=true -ccbin /usr/bin/g++ -cubin -o $W/$v/$f.cubin $f.cu
@@ -31,7 +31,7 @@ def split(path):
             d[cur].append(re.sub(r"/\*[0-9a-f]{4}\*/", "", line).strip())
     return d
 bad = 0
-for f in ("ops_fast", "ops_fused", "ops_fast2d"):
+for f in ("ops_fast", "ops_fused", "ops_fast2d", "ops"):
     o, n = split(f"{w}/old/{f}.sass"), split(f"{w}/new/{f}.sass")
     diff = [k for k in o if k in n and o[k] != n[k]]
     gone = [k for k in o if k not in n]
