@@ -158,6 +158,30 @@ def test_host_segment_failure_keeps_the_device_number(monkeypatch):
     assert j["value"] > 0 and "MemoryError" in j["e2e"]["host_segment_error"] and j["e2e"]["value"] > 0
 
 
+def test_failure_inside_the_timed_host_segment_keeps_the_device_number(monkeypatch):
+    """the upload of the segment's initial state (set!(f, A_host)) fails AFTER the buffers were prepared: the line still
+    carries the device-timed value and the steady e2e, plus the reason"""
+    calls = {"h2d": 0, "d2h": 0}
+    ch, real_lib, drivers = _fake_api(3, calls)
+
+    def broken_set(f, a):
+        raise RuntimeError("chmy_b200 error -2: cudaMemcpy3D failed")
+    ch.set_.side_effect = broken_set
+    monkeypatch.setitem(sys.modules, "chmy_b200", ch)
+    monkeypatch.setitem(sys.modules, "chmy_b200._lib", real_lib)
+    monkeypatch.setitem(sys.modules, "chmy_b200.drivers", drivers)
+    for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    bench = _load_bench()
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--n", "8", "8", "8", "--steps", "3", "--no-cpu-baseline"])
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        bench.run_b200(bench.parse())
+    j = json.loads(buf.getvalue().strip())
+    assert j["value"] > 0 and "cudaMemcpy3D" in j["e2e"]["host_segment_error"] and j["e2e"]["value"] > 0
+    assert j["roofline"]["traffic"] is None and j["roofline"]["traffic_other_size"]["n"] == "511x511x511"
+
+
 def test_reference_arm_runs_on_the_cpu():
     env = dict(os.environ)
     env.pop("RANK", None)
