@@ -19,7 +19,7 @@ __device__ __forceinline__ void fsv_cluster_arrive_relaxed() {
 }
 
 template <bool TD, bool FUN, int TYB>
-__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 2 ? 6 : TYB == 4 ? 3 : TYB == 8 ? 2 : 1)) k_fused_sv(const FusedP p, const int cl, const int variant) {
+__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 2 ? 6 : TYB == 4 ? 3 : (TYB == 6 || TYB == 8) ? 2 : 1)) k_fused_sv(const FusedP p, const int cl, const int variant) {
     extern __shared__ __align__(16) double xb[];
     const int lane = threadIdx.x, ty = threadIdx.y;
     int cr = 0;
@@ -121,6 +121,11 @@ __global__ void __launch_bounds__(256) k_frame_copy(const FrameBatch b) {
 // ---------------------------------------------------------------------------------------------- host side
 static int g_fuse_tyb = 4, g_fuse_cl = 4, g_fuse_cz = 64, g_fuse_var = 1;   // measured optimum at 767^3 (profiles/)
 static bool g_fuse_env = false;
+// rows per CTA with an instantiation.  6 and 12 are round-2 candidates (never the default): 6 rows x clusters of 2 and
+// 12 rows without a cluster keep the halo-row share of the shipped 4 x 4 geometry (2 of 12..16 rows) while using clusters of
+// at most 2 CTAs, which pack onto all 148 SMs (clusters of 4 may leave SMs of a GPC unused), at <= 170 registers.
+static bool fsv_tyb_ok(int v) { return v == 2 || v == 4 || v == 6 || v == 8 || v == 12 || v == 16; }
+
 static void fuse_env() {
     if (g_fuse_env) return;
     g_fuse_env = true;
@@ -129,7 +134,7 @@ static void fuse_env() {
     const char* c = getenv("CHMY_FUSE_CZ");
     const char* d = getenv("CHMY_FUSE_VARIANT");
     if (d) g_fuse_var = atoi(d);
-    if (a) { const int v = atoi(a); if (v == 2 || v == 4 || v == 8 || v == 16) g_fuse_tyb = v; }
+    if (a) { const int v = atoi(a); if (fsv_tyb_ok(v)) g_fuse_tyb = v; }
     if (b) { const int v = atoi(b); if (v == 1 || v == 2 || v == 4 || v == 8) g_fuse_cl = v; }
     if (c) { const int v = atoi(c); if (v >= 1) g_fuse_cz = v; }
 }
@@ -138,7 +143,7 @@ extern "C" int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_c
     fuse_env();
     if (variant >= 0) g_fuse_var = variant;
     if (rows_per_cta > 0) {
-        CHMY_REQUIRE(rows_per_cta == 2 || rows_per_cta == 4 || rows_per_cta == 8 || rows_per_cta == 16, "rows_per_cta must be 2, 4, 8 or 16");
+        CHMY_REQUIRE(fsv_tyb_ok(rows_per_cta), "rows_per_cta must be 2, 4, 6, 8, 12 or 16");
         g_fuse_tyb = rows_per_cta;
     }
     if (cluster_size > 0) {
@@ -183,6 +188,8 @@ static int launch_fused_tyb(const FusedP& p, int tyb, int cl, dim3 grid, cudaStr
     switch (tyb) {
     case 2: return launch_fused<TD, FUN, 2>(p, cl, g_fuse_var, grid, st);
     case 4: return launch_fused<TD, FUN, 4>(p, cl, g_fuse_var, grid, st);
+    case 6: return launch_fused<TD, FUN, 6>(p, cl, g_fuse_var, grid, st);
+    case 12: return launch_fused<TD, FUN, 12>(p, cl, g_fuse_var, grid, st);
     case 16: return launch_fused<TD, FUN, 16>(p, cl, g_fuse_var, grid, st);
     default: return launch_fused<TD, FUN, 8>(p, cl, g_fuse_var, grid, st);
     }
@@ -258,7 +265,7 @@ int chmy_run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_
     // geometry: clusters shrink for short boxes (slabs of a split launch)
     int tyb = g_fuse_tyb, cl = g_fuse_cl;
     while (cl > 1 && (cl / 2) * tyb - 2 >= box.n[1]) cl /= 2;
-    while (tyb > 4 && cl == 1 && tyb / 2 - 2 >= box.n[1]) tyb /= 2;
+    while (tyb > 4 && cl == 1 && tyb / 2 - 2 >= box.n[1] && fsv_tyb_ok(tyb / 2)) tyb /= 2;
     if (tyb == 2 && cl == 1) { tyb = 4; }   // a lone 2-row CTA has no interior row
     p.rows_int = cl * tyb - 2;
     const int nch = (box.n[2] + g_fuse_cz - 1) / g_fuse_cz;

@@ -304,7 +304,7 @@ int chmy_launch_split_plan(const chmy_launch_desc* desc, const int32_t* pref, in
  *   update_thermal_flux! + update_thermal! 3D       stokes_3d_inc_ve_T.jl:167-168   12 ->  9                    */
 int chmy_set_fusion(chmy_ctx* ctx, int enable);
 int chmy_fused_count(const chmy_ctx* ctx, uint64_t* sweeps);          /* fused sweeps launched so far            */
-/* rows of a CTA (2|4|8|16), CTAs per thread-block cluster along y (1|2|4|8), planes per z-chunk (0 keeps a setting);
+/* rows of a CTA (2|4|6|8|12|16; 6 and 12 are round-2 candidates), CTAs per thread-block cluster along y (1|2|4|8), planes per z-chunk (0 keeps a setting);
  * variant: bit 0 = relaxed cluster-barrier arrive behind a CTA-scope fence instead of the release arrive,
  *          bit 1 = EXPERIMENTAL software-pipelined phase A (2- and 4-row CTAs only) (-1 keeps).
  * Env: CHMY_FUSE_TYB, CHMY_FUSE_CL, CHMY_FUSE_CZ, CHMY_FUSE_VARIANT. */

@@ -76,7 +76,7 @@ def test_fused_iteration_bit_exact_vs_oracle(ch, arch, oracle, n, geom):
     _set_tuning(0, 0)
 
 
-EXPERIMENTAL = [(2, 8, 64, 1), (2, 4, 16, 0), (4, 4, 64, 3), (4, 2, 5, 2), (2, 8, 64, 3)]
+EXPERIMENTAL = [(2, 8, 64, 1), (2, 4, 16, 0), (4, 4, 64, 3), (4, 2, 5, 2), (2, 8, 64, 3), (6, 2, 64, 1), (12, 1, 64, 1), (6, 4, 7, 0)]
 
 
 @pytest.mark.skipif(__import__("os").environ.get("CHMY_EXPERIMENTAL", "0") != "1",

@@ -147,6 +147,10 @@ CASES = [
     ((66, 30, 5), ((0, 4, 1), (8, 29, 6)), 2, 4, 2),            # left x slab, odd hi
     ((70, 33, 9), None, 4, 2, 8),                               # 64-thread CTAs, cluster of 8 (round-2 candidate)
     ((61, 37, 6), None, 64, 4, 4),                              # the shipped geometry
+    ((70, 33, 9), None, 4, 6, 2),                               # 6-row CTAs, clusters of 2 (round-2 candidate: all SMs, 2 of 12 rows halo)
+    ((61, 37, 6), None, 64, 12, 1),                             # 12-row CTAs, no cluster (round-2 candidate: no cluster barrier at all)
+    ((130, 11, 10), ((0, 0, 0), (132, 13, 4)), 8, 6, 1),        # z slab with 6-row CTAs
+    ((66, 30, 5), ((0, 4, 1), (8, 29, 6)), 2, 6, 4),            # left x slab, 6-row CTAs in clusters of 4
 ]
 
 
