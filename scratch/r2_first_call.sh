@@ -18,8 +18,8 @@ echo "== 3. bench line with the host-buffer e2e (default workload, short)"
 timeout 420 python bench.py --steps 30 --warmup 5 > gpurun_out/r2_bench_stokes3d.json 2> gpurun_out/r2_bench_stokes3d.err
 tail -c 1500 gpurun_out/r2_bench_stokes3d.json; tail -5 gpurun_out/r2_bench_stokes3d.err
 
-echo "== 4. A/B of the fused-sweep candidates at 767^3 (rows, cluster, z-chunk, variant: bit0 relaxed arrive, bit1 pipelined)"
-GEOMS='4,4,64,1;2,8,64,1;2,4,64,1;4,4,64,3;4,2,64,3;2,8,64,3;2,4,64,3' timeout 420 python scratch/tune_fused.py 2>&1 | tee gpurun_out/r2_tune_fused.log
+echo "== 4. A/B of the fused-sweep candidates at 767^3 (rows, cluster, z-chunk, variant: bit0 relaxed arrive, bit1 pipelined); 6- and 12-row CTAs: clusters <= 2 pack onto all SMs"
+GEOMS='4,4,64,1;6,2,64,1;12,1,64,1;6,4,64,1;6,2,96,1;2,8,64,1;2,4,64,1;4,4,64,3;4,2,64,3;2,8,64,3;2,4,64,3' timeout 420 python scratch/tune_fused.py 2>&1 | tee gpurun_out/r2_tune_fused.log
 
 echo "== 5. 2D workloads: two kernels vs the experimental sweeps"
 for wl in stokes2d diffusion2d stokes2d_thermal; do
