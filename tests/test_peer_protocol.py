@@ -29,6 +29,7 @@ HDR = os.path.join(HERE, "..", "chmy.jl_b200", "csrc", "peer_link.cuh")
 VARIANTS = {
     "peer_emul": ["-O2"],
     "peer_emul_tsan": ["-O1", "-g", "-fsanitize=thread"],
+    "peer_emul_asan": ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"],
     "peer_emul_1slot": ["-O2", "-DPL_SLOTS=1"],
     "peer_emul_1slot_tsan": ["-O1", "-g", "-fsanitize=thread", "-DPL_SLOTS=1"],
 }
@@ -99,6 +100,15 @@ def test_thread_sanitizer_sees_no_race_on_the_slots(dims):
         rc, out, err = run("peer_emul_tsan", dims, 150, 5, 20, 128, **kw)
         assert "data race" not in err and "ThreadSanitizer" not in err, err[-3000:]
         assert rc == 0 and out["mismatches"] == 0 and out["timeouts"] == 0, out
+
+
+def test_address_sanitizer_every_slot_access_inside_its_block():
+    """slot offsets (pl_off_slot), capacities (pl_grow_cap) and block sizes (pl_block_bytes) agree: no access outside a
+    block, none to a retired block, for growing messages of odd sizes"""
+    for dims, words, grow in (((2, 2, 2), 96, 30), ((3, 2), 1, 7), ((2,), 33, 5)):
+        rc, out, err = run("peer_emul_asan", dims, 300, 9, 10, words, grow_every=grow)
+        assert "AddressSanitizer" not in err and "runtime error" not in err, err[-3000:]
+        assert rc == 0 and out["mismatches"] == 0 and out["regrows"] > 0, out
 
 
 def test_a_single_slot_fails_as_the_header_says():
