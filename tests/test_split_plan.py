@@ -149,3 +149,47 @@ def test_split_tuner_state_machine(ch):
     assert pol == [1, 1, 0, 0, 1] and dec == 1
     assert run([1.0, 2.0, 3.0]) == ([1, 1, 0], -1)                  # undecided until four launches were timed
     assert run([]) == ([], -1)
+
+
+# ---------------------------------------------------------------------------------------------- fuzz
+def test_fuzz_any_plan_tiles_the_range_exactly_once(ch):
+    """hypothesis over dimensionality, sizes, outer_width, kernel preference, connectivity and the exact flag: whatever the
+    library decides, it never crashes, and a split it reports always tiles [0, n+1]^N exactly once with non-negative boxes
+    (hint mode additionally: slabs >= 3 wide, even x starts) -- i.e. no cell is computed twice or skipped for ANY input."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @st.composite
+    def cases(draw):
+        nd = draw(st.integers(2, 3))                  # the op used by desc() (update_thermal!) exists in 2D and 3D
+        n = tuple(draw(st.integers(1, 900)) for _ in range(nd))
+        ow = tuple(draw(st.integers(0, x + 3)) for x in n)
+        pref = draw(st.one_of(st.none(), st.tuples(st.integers(0, 130), st.integers(0, 20), st.integers(0, 9))))
+        conn = {(D, S) for D in range(nd) for S in range(2) if draw(st.booleans())}
+        return n, ow, pref, conn, draw(st.booleans())
+
+    @settings(max_examples=400, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(cases())
+    def check(case):
+        n, ow, pref, conn, exact = case
+        nd = len(n)
+        d, keep = desc(ch, n, ow, conn, exact=exact)
+        split, wl, wr = plan(ch, d, None if pref is None else list(pref))
+        if not split:
+            assert wl == [0, 0, 0] and wr == [0, 0, 0]
+            return
+        wl, wr = wl[:nd], wr[:nd]
+        ws = [x + 2 for x in n]
+        regs = [(lo, sz) for lo, sz in regions(n, wl, wr)]
+        assert all(s >= 0 for _, sz in regs for s in sz), (case, wl, wr)
+        assert all(l >= 0 and l + s <= w for lo, sz in regs for l, s, w in zip(lo, sz, ws)), (case, wl, wr)
+        full = [(lo, sz) for lo, sz in regs if all(s > 0 for s in sz)]
+        assert sum(int(np.prod(sz)) for _, sz in full) == int(np.prod(ws)), (case, wl, wr)
+        for (la, sa), (lb, sb) in itertools.combinations(full, 2):
+            assert not all(la[a] < lb[a] + sb[a] and lb[a] < la[a] + sa[a] for a in range(nd)), (case, wl, wr)
+        if exact:
+            assert wl == list(ow) and wr == list(ow)
+        else:
+            assert all(w >= 3 for w in wl + wr), (case, wl, wr)
+            assert wl[0] % 2 == 0 and (ws[0] - wr[0]) % 2 == 0, (case, wl, wr)
+
+    check()
