@@ -62,6 +62,16 @@ def test_dims_create_matches_oracle(oracle):
     assert ch.dims_create(8, (0, 4, 0)) == (2, 4, 1)
     with pytest.raises(ch.ChmyError):
         ch.dims_create(7, (2, 0))
+    # every process count up to 512: library == oracle, the factors multiply to nprocs and come in non-increasing order
+    for nprocs in range(1, 513):
+        for nd in (1, 2, 3):
+            d = ch.dims_create(nprocs, (0,) * nd)
+            assert d == oracle.dims_create(nprocs, (0,) * nd) and int(np.prod(d)) == nprocs
+            assert all(a >= b for a, b in zip(d, d[1:])), (nprocs, d)
+        for fixed in (2, 3):
+            if nprocs % fixed == 0:
+                d = ch.dims_create(nprocs, (0, fixed, 0))
+                assert d == oracle.dims_create(nprocs, (0, fixed, 0)) and d[1] == fixed and int(np.prod(d)) == nprocs
 
 
 def test_grid_numbers_match_oracle_and_reference(oracle):
