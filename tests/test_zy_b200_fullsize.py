@@ -16,7 +16,7 @@ kernels (first/last cells, 60-cell row segments, cluster rows, 64-plane z-chunks
 index, every y index and every z index of the launch range is covered by some probe.  A literal split launch
 (outer_width honoured, two streams) must give the same checksums as the single full-range launch.
 
-First GPU run pending (written after the round's GPU budget was spent): non-strict xfail, like tests/test_zz_*.
+Green on the driver's B200 at the end of round 1; enforced (no xfail) since round 2.
 """
 import gc
 import math
@@ -25,7 +25,7 @@ import os
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run pending (added after the round's GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu]
 
 
 # tests/test_gpu_suite_dryrun.py executes this file on the CPU against the dry-run backend: same code, sizes the oracle holds

@@ -1,6 +1,5 @@
 """
-GPU tests of entry points added after the round's last GPU session (they have not run on a B200 yet, so this file
-sorts after every measured suite: a surprise here cannot hide the results of the suites before it).
+GPU tests of the entry points added late in round 1 (operators, Float32 pieces, pinned arrays, batched maxima).
 Same bar as tests/test_b200_parity.py: through the C ABI, against the CPU oracle, bit-exact unless stated.
 """
 import numpy as np
@@ -8,10 +7,8 @@ import pytest
 
 from helpers import assert_same, fill_pair
 
-# Non-strict xfail: these entry points were written after the round's GPU budget was spent.  Their arithmetic is proven
-# on the CPU (tests/test_operators_emulation.py), the launch plumbing is not; until a B200 has run them once a failure
-# here is reported as XFAIL (and a pass as XPASS) instead of turning the measured suites before it red.
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run pending (added after the round's GPU budget was spent)")]
+# Green on the driver's B200 at the end of round 1 (GPUTEST_r01.json: all XPASS) -- enforced since round 2.
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")
