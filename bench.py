@@ -73,6 +73,7 @@ def parse():
     ap.add_argument("--n", type=int, nargs="*", default=None, help="override the local grid size (parity/debug runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="N > 1: skip the untimed multi-rank correctness check")
     ap.add_argument("--split", default="auto", choices=["auto", "on", "off"],
                     help="multi-GPU: order of launches that carry a halo exchange -- on = inner region overlapped with slabs + "
                          "batches (the reference's order), off = one full-range kernel then batches + exchange, auto = the "
@@ -231,6 +232,106 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU self-check
+def _exchange_expected(parents, locs, dims, coords_of, n):
+    """communication_views.jl:1-34 + exchange_halo.jl:73-84 restated on host copies of the padded arrays: for D = N..1,
+    every rank's recv slab (logical 0 | d+1 along D, whole padded transverse extent) := the neighbour's send slab
+    (logical 1+overlap | d-overlap).  parents[r][q]: padded array of field q on rank r (array index = logical + 1)."""
+    import numpy as np
+    nd = len(dims)
+    rank_of = {tuple(c): r for r, c in enumerate(coords_of)}
+    out = [[a.copy() for a in fs] for fs in parents]
+    for D in range(nd - 1, -1, -1):
+        snap = [[a.copy() for a in fs] for fs in out]      # both sides of a dim move concurrently, dims sequentially
+        for r, c in enumerate(coords_of):
+            for side, delta in ((0, -1), (1, +1)):
+                cc = list(c); cc[D] += delta
+                if not (0 <= cc[D] < dims[D]):
+                    continue
+                nb = rank_of[tuple(cc)]
+                for q, loc in enumerate(locs):
+                    ov = 1 if loc[D] else 0
+                    d = n[D] + ov
+                    recv = 1 if side == 0 else d + 2
+                    send = (d - ov + 1) if side == 0 else (2 + ov)     # the neighbour's opposite side
+                    sl_r = [slice(None)] * nd; sl_r[D] = recv
+                    sl_s = [slice(None)] * nd; sl_s[D] = send
+                    out[r][q][tuple(sl_r)] = snap[nb][q][tuple(sl_s)]
+    return out
+
+
+def multi_gpu_check(ch, BD, arch, backend, world, rank, local_rank, fused):
+    """Untimed correctness check of the N-rank path through the product API only (no oracle): (1) exchange_halo! on
+    index-encoded fields (rank*1e6 + linear storage index) must equal the send/recv view algebra bit for bit, corners
+    included; (2) the N-rank decomposed Stokes solve of a small global grid must agree with the same global grid solved on
+    ONE GPU (rank 0, a second single-device context) to <= 1e-12 relative, fields and residual history (SURVEY 8c:
+    not bitwise, the sub-axis spacing is recomputed per rank, distributed_grid.jl:19-36)."""
+    import numpy as np
+    topo = arch.topology
+    pd, comm = topo.dims, topo.comm
+    nd = len(pd)
+    out = {"world": world, "proc_dims": list(pd)}
+    # ---- (1) exchange_halo!, examples/exchange_halo.jl:20-30 with index-encoded contents
+    n = (9, 7, 5)[:nd]
+    n_g = tuple(a * p for a, p in zip(n, pd))
+    g = ch.UniformGrid(arch, origin=(-1.0,) * nd, extent=(2.0,) * nd, dims=n_g)
+    locs = [(0,) * nd, (1,) + (0,) * (nd - 1), (0,) * (nd - 1) + (1,), (1,) * nd]
+    fs = [ch.Field(arch, g, tuple(ch.Vertex() if x else ch.Center() for x in l)) for l in locs]
+    mine = []
+    for f, l in zip(fs, locs):
+        shape = tuple(a + x + 4 for a, x in zip(n, l))
+        a = rank * 1.0e6 + np.arange(int(np.prod(shape)), dtype=np.float64).reshape(shape, order="F")
+        f.from_host(a.copy(), [-1] * nd, [d + 2 for d in f.dims])
+        mine.append(a)
+    allp = comm.allgather_obj((tuple(topo.cart_coords), mine))
+    ch.exchange_halo_(arch, g, *fs)
+    want = _exchange_expected([p for _, p in allp], locs, pd, [c for c, _ in allp], n)[rank]
+    bad = 0
+    for f, w in zip(fs, want):
+        bad += int((f.parent() != w).sum())
+    for f in fs:
+        f.free()
+    (bad_all,) = ch.allreduce_max(arch, float(bad))
+    out["exchange_bit_exact"] = bad_all == 0.0
+    out["exchange_cells_wrong_max_over_ranks"] = int(bad_all)
+    # ---- (2) decomposed solve vs one GPU
+    nl = (24, 20, 16)[:nd]
+    kw = dict(re_m=2.5 * math.pi, rho_g_function=True, adv_coef=0.01, blocking=False)
+    ch.set_fusion(arch, int(bool(fused)))
+    sol = BD.Stokes(arch, nl, outer_width=(8, 4, 3)[:nd], **kw)
+    hist = sol.run(2, 20, 10)
+    blocks = {k: np.asarray(ch.interior(f)) for k, f in sol.fields().items()}
+    allb = comm.allgather_obj((tuple(topo.cart_coords), blocks))
+    worst, worst_name, hist_rel = 0.0, None, 0.0
+    if rank == 0:
+        arch1 = ch.Arch(backend, device_id=local_rank + 1)
+        ch.set_fusion(arch1, int(bool(fused)))
+        ng = tuple(a * p for a, p in zip(nl, pd))
+        ref = BD.Stokes(arch1, ng, outer_width=(8, 4, 3)[:nd], **kw)
+        href = ref.run(2, 20, 10)
+        assert len(href) == len(hist), (len(href), len(hist))
+        for a, b in zip(hist, href):
+            assert a[:2] == b[:2]
+            for x, y in zip(a[2:], b[2:]):
+                hist_rel = max(hist_rel, abs(x - y) / max(abs(y), 1e-300))
+        for k, f in ref.fields().items():
+            G = np.asarray(ch.interior(f))
+            den = max(float(np.abs(G).max()), 1e-300)
+            for c, blk in allb:
+                b = blk[k]
+                sl = tuple(slice(ci * ni, ci * ni + sz) for ci, ni, sz in zip(c, nl, b.shape))
+                e = float(np.abs(G[sl] - b).max()) / den
+                if e > worst:
+                    worst, worst_name = e, f"{k} @ coords {c}"
+        arch1.close()
+    (worst, hist_rel) = ch.allreduce_max(arch, worst, hist_rel)
+    out.update(max_rel=worst, history_max_rel=hist_rel, worst=worst_name, n_local=list(nl), pt_iterations=40,
+               tolerance=1e-12, ok=bool(bad_all == 0.0 and worst <= 1e-12 and hist_rel <= 1e-12),
+               what="N-rank decomposed 3D Stokes (2 outer steps x 20 PT iterations, thermal on in step 2, fused sweep as timed) vs the "
+                    "same global grid on one GPU; exchange_halo! on index-encoded fields vs the send/recv view algebra")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -454,6 +555,13 @@ def run_b200(args):
         del views
         sol.launch.blocking = False
 
+    mgc = None
+    if world > 1 and not args.no_check:
+        try:
+            mgc = multi_gpu_check(ch, BD, arch, backend, world, rank, local_rank, fused and wl.startswith("stokes3d"))
+        except Exception as ex:
+            mgc = {"ok": False, "error": f"{type(ex).__name__}: {ex}"}
+
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -472,6 +580,7 @@ def run_b200(args):
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "T_eff_per_gpu": teff_gpu, "frac_of_hbm_peak": teff_gpu / peak, "hbm_peak": peak, "hbm_peak_source": peak_src,
             "clocks": clocks, "gpu_launches": int(l1 - l0), "fused_sweeps": int(nfused), "exchange_msgs": xstats, "roofline": roofline, "e2e": e2e, "cpu_baseline": cb,
+            "multi_gpu_check": mgc,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -30,6 +30,11 @@
 #include "fast_common.cuh"
 #define FHD __device__ __forceinline__
 typedef double2 d2;
+// streaming (evict-first) flavours: the sweep's stores and its once-read operands must not push the rows that the
+// neighbouring tiles are about to re-read out of L2
+__device__ __forceinline__ double2 ld2s(const double* p) { return __ldcs(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ void st2s(double* p, double2 v) { __stcs(reinterpret_cast<double2*>(p), v); }
+__device__ __forceinline__ void st1s(double* p, double v) { __stcs(p, v); }
 #else
 #include <cmath>
 #include <cstring>
@@ -66,6 +71,9 @@ static inline double coord_dev(double origin, double spacing, int loc, int i) {
 }
 static inline d2 ld2(const double* p) { return d2{p[0], p[1]}; }
 static inline void st2(double* p, d2 v) { p[0] = v.x; p[1] = v.y; }
+static inline d2 ld2s(const double* p) { return ld2(p); }
+static inline void st2s(double* p, d2 v) { st2(p, v); }
+static inline void st1s(double* p, double v) { *p = v; }
 #endif
 
 constexpr int FSV_LANES = 32;
@@ -93,6 +101,7 @@ static inline size_t fsv_smem_bytes(int tyb) { return (size_t)2 * FSV_NF * tyb *
 struct FusedT {
     int  lane, ty, i, j, k0, k1;
     bool s_act;           // this lane loads and computes stresses
+    bool stream;          // this row's once-read operands may be loaded with the streaming policy
     int  nv;              // cells of the pair that are updated and stored (0, 1 or 2)
     bool fx0, fx1, fy;    // cell / row inside the op's index range
     int  jm, jp;          // 1 if row j-1 / j+1 may be addressed (0 on the cluster's first / last row)
@@ -111,8 +120,10 @@ FHD d2 fsv_zero() {
 
 // geometry of a thread: bx = row-segment index along x, grow = row index inside the cluster (0 .. rows_int+1),
 // cyc = cluster index along y, bz = z-chunk index
-FHD void fsv_init(FusedT& s, const FusedP& p, int lane, int ty, int grow, int bx, int cyc, int bz, bool fun) {
+FHD void fsv_init(FusedT& s, const FusedP& p, int lane, int ty, int grow, int bx, int cyc, int bz, bool fun, int hint = 0) {
     s.lane = lane; s.ty = ty;
+    // rows 0, 1 and the last two of a cluster are re-read by the neighbouring cluster (as its halo rows / by its halo rows)
+    s.stream = !(hint & 4) || (grow >= 2 && grow + 2 <= p.rows_int);
     s.i  = p.lo[0] - 2 + bx * FSV_XI + 2 * lane;
     s.j  = p.lo[1] - 1 + cyc * p.rows_int + grow;
     s.k0 = p.lo[2] + bz * p.cz;
@@ -170,7 +181,9 @@ FHD double fsv_from_left(double, const double* p_im1, bool ok) { return ok ? *p_
 #endif
 
 // ---- phase A: stresses of plane kp -> sn[FSV_NF] (new Pr, tau), stores for the cells this thread owns
-template <bool TD>
+// HINT (cache policy, device only): bit 0 = streaming (evict-first) stores, bit 1 = streaming loads of the operands that
+// are read exactly once (tau, tau_old, Pr) -- on every row, or with bit 2 only on the rows no neighbouring tile re-reads
+template <bool TD, int HINT>
 FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
     const d2 z2 = fsv_zero();
     d2 vx = z2, vxjm = z2, vy = z2, vyjp = z2, vzkp = z2, vzjmkp = z2, pr = z2;
@@ -182,12 +195,21 @@ FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
         vyjp   = ld2(p.Vc[1] + s.cv + (long long)s.jp * p.cv.sy);
         vzkp   = ld2(p.Vc[2] + s.cc + p.cc.sz);
         vzjmkp = ld2(p.Vc[2] + s.cc - (long long)s.jm * p.cc.sy + p.cc.sz);
-        pr     = ld2(p.Prc + s.cc);
+        if ((HINT & 2) && s.stream) {
+            pr = ld2s(p.Prc + s.cc);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { t[c] = ld2(p.tc[c] + s.cc); o[c] = ld2(p.to[c] + s.cc); }
-        t[3] = ld2(p.tc[3] + s.vv); o[3] = ld2(p.to[3] + s.vv);
-        t[4] = ld2(p.tc[4] + s.vc); o[4] = ld2(p.to[4] + s.vc);
-        t[5] = ld2(p.tc[5] + s.cv); o[5] = ld2(p.to[5] + s.cv);
+            for (int c = 0; c < 3; ++c) { t[c] = ld2s(p.tc[c] + s.cc); o[c] = ld2s(p.to[c] + s.cc); }
+            t[3] = ld2s(p.tc[3] + s.vv); o[3] = ld2s(p.to[3] + s.vv);
+            t[4] = ld2s(p.tc[4] + s.vc); o[4] = ld2s(p.to[4] + s.vc);
+            t[5] = ld2s(p.tc[5] + s.cv); o[5] = ld2s(p.to[5] + s.cv);
+        } else {
+            pr = ld2(p.Prc + s.cc);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { t[c] = ld2(p.tc[c] + s.cc); o[c] = ld2(p.to[c] + s.cc); }
+            t[3] = ld2(p.tc[3] + s.vv); o[3] = ld2(p.to[3] + s.vv);
+            t[4] = ld2(p.tc[4] + s.vc); o[4] = ld2(p.to[4] + s.vc);
+            t[5] = ld2(p.tc[5] + s.cv); o[5] = ld2(p.to[5] + s.cv);
+        }
     } else {
 #pragma unroll
         for (int c = 0; c < 6; ++c) { t[c] = z2; o[c] = z2; }
@@ -228,13 +250,23 @@ FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
     }
     if (kp >= s.k0 && kp < s.k1) {
         if (s.nv == 2) {
-            st2(p.dV + s.cc, dv);
-            st2(p.Prn + s.cc, prn);
+            if (HINT & 1) {
+                st2s(p.dV + s.cc, dv);
+                st2s(p.Prn + s.cc, prn);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) st2(p.tn[c] + s.cc, tn[c]);
-            st2(p.tn[3] + s.vv, tn[3]);
-            st2(p.tn[4] + s.vc, tn[4]);
-            st2(p.tn[5] + s.cv, tn[5]);
+                for (int c = 0; c < 3; ++c) st2s(p.tn[c] + s.cc, tn[c]);
+                st2s(p.tn[3] + s.vv, tn[3]);
+                st2s(p.tn[4] + s.vc, tn[4]);
+                st2s(p.tn[5] + s.cv, tn[5]);
+            } else {
+                st2(p.dV + s.cc, dv);
+                st2(p.Prn + s.cc, prn);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) st2(p.tn[c] + s.cc, tn[c]);
+                st2(p.tn[3] + s.vv, tn[3]);
+                st2(p.tn[4] + s.vc, tn[4]);
+                st2(p.tn[5] + s.cv, tn[5]);
+            }
         } else if (s.nv == 1) {
             p.dV[s.cc]  = dv.x;
             p.Prn[s.cc] = prn.x;
@@ -251,99 +283,10 @@ FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
     s.vx_k = vx; s.vy_k = vy; s.vz_kp = vzkp; s.vzjm_kp = vzjmkp;
 }
 
-// ---- software-pipelined flavour of phase A (EXPERIMENTAL, variant bit 1; not the default kernel): the operands of
-// plane kp+1 are requested into registers (fsv_load_a) right after the arithmetic of plane kp, so they are in flight
-// during the barrier and phase B; fsv_compute_a is phase A's arithmetic and stores on operands already in registers.
-struct FusedL {
-    d2 vx, vxjm, vy, vyjp, vzkp, vzjmkp, pr, t[6], o[6];
-};
-
-FHD void fsv_load_a(const FusedT& s, const FusedP& p, int dz, FusedL& L) {
-    const d2 z2 = fsv_zero();
-    L.vx = L.vxjm = L.vy = L.vyjp = L.vzkp = L.vzjmkp = L.pr = z2;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) { L.t[c] = z2; L.o[c] = z2; }
-    if (s.s_act) {
-        const long long cc = s.cc + (long long)dz * p.cc.sz, vc = s.vc + (long long)dz * p.vc.sz,
-                        cv = s.cv + (long long)dz * p.cv.sz, vv = s.vv + (long long)dz * p.vv.sz;
-        L.vx     = ld2(p.Vc[0] + vc);
-        L.vxjm   = ld2(p.Vc[0] + vc - (long long)s.jm * p.vc.sy);
-        L.vy     = ld2(p.Vc[1] + cv);
-        L.vyjp   = ld2(p.Vc[1] + cv + (long long)s.jp * p.cv.sy);
-        L.vzkp   = ld2(p.Vc[2] + cc + p.cc.sz);
-        L.vzjmkp = ld2(p.Vc[2] + cc - (long long)s.jm * p.cc.sy + p.cc.sz);
-        L.pr     = ld2(p.Prc + cc);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { L.t[c] = ld2(p.tc[c] + cc); L.o[c] = ld2(p.to[c] + cc); }
-        L.t[3] = ld2(p.tc[3] + vv); L.o[3] = ld2(p.to[3] + vv);
-        L.t[4] = ld2(p.tc[4] + vc); L.o[4] = ld2(p.to[4] + vc);
-        L.t[5] = ld2(p.tc[5] + cv); L.o[5] = ld2(p.to[5] + cv);
-    }
-}
-
-template <bool TD>
-FHD void fsv_compute_a(FusedT& s, const FusedP& p, int kp, const FusedL& L, d2 sn[FSV_NF]) {
-    const d2 z2 = fsv_zero();
-    const bool okr = s.s_act && s.lane < FSV_LANES - 1, okl = s.s_act && s.lane > 0;
-    const double vx_ip2 = fsv_from_right(L.vx.x, p.Vc[0] + s.vc + 2, okr);
-    const double vy_im1 = fsv_from_left(L.vy.y, p.Vc[1] + s.cv - 1, okl);
-    const double vz_im1 = fsv_from_left(s.vz_k.y, p.Vc[2] + s.cc - 1, okl);
-    const bool fz = kp >= p.flo[2] && kp < p.fhi[2];
-    d2 dv = z2, prn = z2, tn[6];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const double a_vx = h ? L.vx.y : L.vx.x, a_vxip = h ? vx_ip2 : L.vx.y, a_vxjm = h ? L.vxjm.y : L.vxjm.x, a_vxkm = h ? s.vx_km.y : s.vx_km.x;
-        const double a_vy = h ? L.vy.y : L.vy.x, a_vyjp = h ? L.vyjp.y : L.vyjp.x, a_vyim = h ? L.vy.x : vy_im1, a_vykm = h ? s.vy_km.y : s.vy_km.x;
-        const double a_vz = h ? s.vz_k.y : s.vz_k.x, a_vzkp = h ? L.vzkp.y : L.vzkp.x, a_vzim = h ? s.vz_k.x : vz_im1, a_vzjm = h ? s.vzjm.y : s.vzjm.x;
-        const double exx = (a_vxip - a_vx) * p.idx;
-        const double eyy = (a_vyjp - a_vy) * p.idy;
-        const double ezz = (a_vzkp - a_vz) * p.idz;
-        const double exy = 0.5 * ((a_vx - a_vxjm) * p.idy + (a_vy - a_vyim) * p.idx);
-        const double exz = 0.5 * ((a_vx - a_vxkm) * p.idz + (a_vz - a_vzim) * p.idx);
-        const double eyz = 0.5 * ((a_vy - a_vykm) * p.idz + (a_vz - a_vzjm) * p.idy);
-        const double d   = (exx + eyy) + ezz;
-        const double d3  = div_u<TD>(d, p.three);
-        const double a_pr = h ? L.pr.y : L.pr.x;
-        const double e2[6] = {2.0 * (exx - d3), 2.0 * (eyy - d3), 2.0 * (ezz - d3), 2.0 * exy, 2.0 * exz, 2.0 * eyz};
-        const bool in = (h ? s.fx1 : s.fx0) && s.fy && fz;
-        const double n_pr = in ? a_pr - (d * p.eta_ve) * p.dtau_Pr : a_pr;
-        if (h) { dv.y = d; prn.y = n_pr; } else { dv.x = d; prn.x = n_pr; }
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            const double tc = h ? L.t[c].y : L.t[c].x;
-            const double r  = in ? fsv_stress_upd<TD>(tc, h ? L.o[c].y : L.o[c].x, e2[c], p) : tc;
-            if (h) tn[c].y = r; else tn[c].x = r;
-        }
-    }
-    if (kp >= s.k0 && kp < s.k1) {
-        if (s.nv == 2) {
-            st2(p.dV + s.cc, dv);
-            st2(p.Prn + s.cc, prn);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) st2(p.tn[c] + s.cc, tn[c]);
-            st2(p.tn[3] + s.vv, tn[3]);
-            st2(p.tn[4] + s.vc, tn[4]);
-            st2(p.tn[5] + s.cv, tn[5]);
-        } else if (s.nv == 1) {
-            p.dV[s.cc]  = dv.x;
-            p.Prn[s.cc] = prn.x;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) p.tn[c][s.cc] = tn[c].x;
-            p.tn[3][s.vv] = tn[3].x;
-            p.tn[4][s.vc] = tn[4].x;
-            p.tn[5][s.cv] = tn[5].x;
-        }
-    }
-    sn[FSV_PR] = prn;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) sn[1 + c] = tn[c];
-    s.vx_k = L.vx; s.vy_k = L.vy; s.vz_kp = L.vzkp; s.vzjm_kp = L.vzjmkp;
-}
-
 // ---- phase B: publish the stresses of plane kp, update the velocity of plane kp-1, rotate the carried planes.
 // own / below / above: exchange buffers (element 0 of [buf][field][row][cell]) of the CTAs holding this thread's
 // row, row j-1 and row j+1; rb / ra: the row numbers of j-1 / j+1 inside those CTAs.
-template <bool TD, bool FUN>
+template <bool TD, bool FUN, int HINT>
 FHD void fsv_phase_b(FusedT& s, const FusedP& p, int kp, const d2 sn[FSV_NF], int tyb, double* own, const double* below,
                      int rb, const double* above, int ra) {
     const int cur = kp & 1, prev = cur ^ 1;
@@ -403,8 +346,13 @@ FHD void fsv_phase_b(FusedT& s, const FusedP& p, int kp, const d2 sn[FSV_NF], in
                 else   { nrx.x = rvx; nry.x = rvy; nrz.x = rvz; nvx.x = ux; nvy.x = uy; nvz.x = uz; }
             }
             if (s.nv == 2) {
-                st2(p.r[0] + vc, nrx); st2(p.r[1] + cv, nry); st2(p.r[2] + cc, nrz);
-                st2(p.Vn[0] + vc, nvx); st2(p.Vn[1] + cv, nvy); st2(p.Vn[2] + cc, nvz);
+                if (HINT & 1) {       // r_V is never re-read by the sweep; the new V only by the next sweep
+                    st2s(p.r[0] + vc, nrx); st2s(p.r[1] + cv, nry); st2s(p.r[2] + cc, nrz);
+                    st2s(p.Vn[0] + vc, nvx); st2s(p.Vn[1] + cv, nvy); st2s(p.Vn[2] + cc, nvz);
+                } else {
+                    st2(p.r[0] + vc, nrx); st2(p.r[1] + cv, nry); st2(p.r[2] + cc, nrz);
+                    st2(p.Vn[0] + vc, nvx); st2(p.Vn[1] + cv, nvy); st2(p.Vn[2] + cc, nvz);
+                }
             } else {
                 p.r[0][vc] = nrx.x; p.r[1][cv] = nry.x; p.r[2][cc] = nrz.x;
                 p.Vn[0][vc] = nvx.x; p.Vn[1][cv] = nvy.x; p.Vn[2][cc] = nvz.x;

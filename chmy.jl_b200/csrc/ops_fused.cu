@@ -3,8 +3,10 @@
 // thread-block cluster whose members read each other's boundary rows through distributed shared memory, so only the
 // first and last row of a cluster recompute stresses for their neighbours.
 #include <cooperative_groups.h>
+#include <cuda.h>        // CUtensorMap (types only: the one driver entry point used is resolved at run time)
 
 #include "fused_sv.cuh"
+#include "fused_tma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -18,8 +20,8 @@ __device__ __forceinline__ void fsv_cluster_arrive_relaxed() {
     asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 }
 
-template <bool TD, bool FUN, int TYB>
-__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 2 ? 6 : TYB == 4 ? 3 : (TYB == 6 || TYB == 8) ? 2 : 1)) k_fused_sv(const FusedP p, const int cl, const int variant) {
+template <bool TD, bool FUN, int TYB, int HINT>
+__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 4 ? 3 : 2)) k_fused_sv(const FusedP p, const int cl, const int variant) {
     extern __shared__ __align__(16) double xb[];
     const int lane = threadIdx.x, ty = threadIdx.y;
     int cr = 0;
@@ -35,28 +37,80 @@ __global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 2 ? 6 : TYB == 4 ? 3 :
     }
     const bool relaxed = (variant & 1) != 0;
     FusedT s;
-    fsv_init(s, p, lane, ty, cr * TYB + ty, blockIdx.x, blockIdx.y / cl, blockIdx.z, FUN);
+    fsv_init(s, p, lane, ty, cr * TYB + ty, blockIdx.x, blockIdx.y / cl, blockIdx.z, FUN, HINT);
     if (cl > 1) fsv_cluster_arrive();
     for (int kp = s.k0 - 1; kp <= s.k1; ++kp) {
         d2 sn[FSV_NF];
-        fsv_phase_a<TD>(s, p, kp, sn);
+        fsv_phase_a<TD, HINT>(s, p, kp, sn);
         // every thread of the cluster has finished reading the buffer that is about to be overwritten, and the
         // stresses of plane kp-1 that phase B reads have been published
         if (cl > 1) fsv_cluster_wait(); else __syncthreads();
-        fsv_phase_b<TD, FUN>(s, p, kp, sn, TYB, xb, below, rb, above, ra);
+        fsv_phase_b<TD, FUN, HINT>(s, p, kp, sn, TYB, xb, below, rb, above, ra);
         if (cl > 1) { if (relaxed) fsv_cluster_arrive_relaxed(); else fsv_cluster_arrive(); }
     }
     if (cl > 1) fsv_cluster_wait();   // no CTA may exit while a neighbour can still read its shared memory
 }
 
-// EXPERIMENTAL (variant bit 1, never the default): the same sweep with phase A software-
-// pipelined through registers -- the 19 operand loads of plane kp+1 are issued right after the arithmetic of plane kp and
-// stay in flight across the barrier and phase B.  Needs ~76 more registers, so 2 CTAs of 128 threads (or 4 of 64) per
-// SM at up to 255 registers.  Proven bit-exact by the host emulation; not yet measured on a GPU.
+// ---------------------------------------------------------------------------------------------- TMA-fed sweep
+// (design: fused_tma.cuh)  mbarrier / bulk-copy primitives, raw PTX for sm_100a
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA unit, SASS UBLKCP); completion is reported to the mbarrier as `bytes` transactions
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+
+// tensor-map flavour of the same row copy: a 64 x 1 x 1 box of a rank-3 tensor map (SASS UTMALDG); out-of-range cells are
+// zero-filled by the TMA unit, and all eleven operands share ONE coordinate triple -- a handful of instructions per row
+struct FtmMaps {
+    CUtensorMap m[FTM_NS];
+};
+__device__ __forceinline__ void tma_row_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* b) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+
+// the elected lane of warp 0 requests the CTA's TYB rows of plane z (tensor coordinate) of all eleven operands into slot `slot`
+template <int TYB>
+__device__ __forceinline__ void ftm_issue(const FtmMaps& maps, double* ring, uint64_t* full, int cx, int cy, int z, int slot) {
+    mbar_expect_tx(full, (uint32_t)(FTM_NS * TYB * 64 * sizeof(double)));
+#pragma unroll
+    for (int op = 0; op < FTM_NS; ++op) tma_row_3d(ring + ftm_ring_off(TYB, slot, op, 0), &maps.m[op], cx, cy, z, full);
+}
+
 template <bool TD, bool FUN, int TYB>
-__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 2 ? 4 : 2)) k_fused_sv_pl(const FusedP p, const int cl, const int variant) {
-    extern __shared__ __align__(16) double xb[];
+__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 4 ? 3 : 2)) k_fused_tma(const FusedP p, const int cl, const __grid_constant__ FtmMaps maps) {
+    extern __shared__ __align__(128) double sm[];
     const int lane = threadIdx.x, ty = threadIdx.y;
+    const int w = __shfl_sync(0xffffffffu, ty, 0);                 // this warp's row, provably warp-uniform
+    double*   ring = sm;
+    double*   xb   = sm + ftm_xch_base(TYB);
+    uint64_t* full  = reinterpret_cast<uint64_t*>(xb + 2 * FSV_NF * TYB * 64);   // [2]: the slot's bytes have landed
+    uint64_t* empty = full + 2;                                                  // [2]: every warp has read the slot
     int cr = 0;
     const double *below = xb, *above = xb;
     int rb = ty, ra = ty;
@@ -68,21 +122,45 @@ __global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 2 ? 4 : 2)) k_fused_sv
         if (ty == 0 && cr > 0) { below = cluster.map_shared_rank(xb, cr - 1); rb = TYB - 1; }
         if (ty == TYB - 1 && cr < cl - 1) { above = cluster.map_shared_rank(xb, cr + 1); ra = 0; }
     }
-    const bool relaxed = (variant & 1) != 0;
-    FusedT s;
-    fsv_init(s, p, lane, ty, cr * TYB + ty, blockIdx.x, blockIdx.y / cl, blockIdx.z, FUN);
-    FusedL L;
-    fsv_load_a(s, p, 0, L);
-    if (cl > 1) fsv_cluster_arrive();
-    for (int kp = s.k0 - 1; kp <= s.k1; ++kp) {
-        d2 sn[FSV_NF];
-        fsv_compute_a<TD>(s, p, kp, L, sn);
-        if (kp < s.k1) fsv_load_a(s, p, 1, L);      // plane kp+1: in flight during the barrier and phase B
-        if (cl > 1) fsv_cluster_wait(); else __syncthreads();
-        fsv_phase_b<TD, FUN>(s, p, kp, sn, TYB, xb, below, rb, above, ra);
-        if (cl > 1) { if (relaxed) fsv_cluster_arrive_relaxed(); else fsv_cluster_arrive(); }
+    FusedM m;
+    ftm_init(m, p, lane, ty, cr * TYB + ty, blockIdx.x, blockIdx.y / cl, blockIdx.z, FUN);
+    const int nit = m.t.k1 - m.t.k0 + 2;          // planes kp = k0-1 .. k1
+    // tensor coordinates of the CTA's first row segment (the maps start at logical (-2, -1, -1))
+    const int cx = p.lo[0] + (int)blockIdx.x * FSV_XI;
+    const int cy = p.lo[1] + (int)(blockIdx.y / cl) * p.rows_int + cr * TYB;
+    const int cz = p.lo[2] + (int)blockIdx.z * p.cz;               // plane k0 - 1
+    const bool leader = elect_one();
+    const bool feeder = leader && w == 0;
+    if (feeder) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_init(&empty[0], TYB);
+        mbar_init(&empty[1], TYB);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ftm_issue<TYB>(maps, ring, &full[0], cx, cy, cz, 0);
+        if (nit > 1) ftm_issue<TYB>(maps, ring, &full[1], cx, cy, cz + 1, 1);
     }
-    if (cl > 1) fsv_cluster_wait();
+    __syncthreads();                               // the barriers exist
+    if (cl > 1) fsv_cluster_arrive();
+    for (int it = 0; it < nit; ++it) {
+        const int kp = m.t.k0 - 1 + it, slot = it & 1;
+        d2 sn[FSV_NF];
+        // plane it+1 goes where plane it-1 was, as soon as every warp of the CTA has read that slot
+        if (feeder && it >= 1 && it + 1 < nit) {
+            mbar_wait(&empty[slot ^ 1], (uint32_t)(((it - 1) >> 1) & 1));
+            ftm_issue<TYB>(maps, ring, &full[slot ^ 1], cx, cy, cz + it + 1, slot ^ 1);
+        }
+        mbar_wait(&full[slot], (uint32_t)((it >> 1) & 1));
+        ftm_phase_a<TD>(m, p, kp, ring, TYB, slot, it + 1 < nit, sn);
+        __syncwarp();                              // every lane of the warp has taken its cells of this slot
+        if (leader) mbar_arrive(&empty[slot]);
+        // every thread of the cluster has finished reading the exchange buffer that is about to be overwritten, and the
+        // stresses of plane kp-1 that phase B reads have been published
+        if (cl > 1) fsv_cluster_wait(); else __syncthreads();
+        fsv_phase_b<TD, FUN, 0>(m.t, p, kp, sn, TYB, xb, below, rb, above, ra);
+        if (cl > 1) fsv_cluster_arrive_relaxed();
+    }
+    if (cl > 1) fsv_cluster_wait();   // no CTA may exit while a neighbour can still read its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------- frame copy
@@ -121,10 +199,9 @@ __global__ void __launch_bounds__(256) k_frame_copy(const FrameBatch b) {
 // ---------------------------------------------------------------------------------------------- host side
 static int g_fuse_tyb = 4, g_fuse_cl = 4, g_fuse_cz = 64, g_fuse_var = 1;   // measured optimum at 767^3 (profiles/)
 static bool g_fuse_env = false;
-// rows per CTA with an instantiation.  6 and 12 are round-2 candidates (never the default): 6 rows x clusters of 2 and
-// 12 rows without a cluster keep the halo-row share of the shipped 4 x 4 geometry (2 of 12..16 rows) while using clusters of
-// at most 2 CTAs, which pack onto all 148 SMs (clusters of 4 may leave SMs of a GPC unused), at <= 170 registers.
-static bool fsv_tyb_ok(int v) { return v == 2 || v == 4 || v == 6 || v == 8 || v == 12 || v == 16; }
+// rows per CTA with an instantiation (profiles/r2_c1_tune_fused_767.log: 2-, 12- and 16-row CTAs and the register-pipelined
+// flavour lost on the B200 and were removed)
+static bool fsv_tyb_ok(int v) { return v == 4 || v == 6 || v == 8; }
 
 static void fuse_env() {
     if (g_fuse_env) return;
@@ -135,7 +212,7 @@ static void fuse_env() {
     const char* d = getenv("CHMY_FUSE_VARIANT");
     if (d) g_fuse_var = atoi(d);
     if (a) { const int v = atoi(a); if (fsv_tyb_ok(v)) g_fuse_tyb = v; }
-    if (b) { const int v = atoi(b); if (v == 1 || v == 2 || v == 4 || v == 8) g_fuse_cl = v; }
+    if (b) { const int v = atoi(b); if (v >= 1 && v <= 8) g_fuse_cl = v; }
     if (c) { const int v = atoi(c); if (v >= 1) g_fuse_cz = v; }
 }
 
@@ -143,31 +220,27 @@ extern "C" int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_c
     fuse_env();
     if (variant >= 0) g_fuse_var = variant;
     if (rows_per_cta > 0) {
-        CHMY_REQUIRE(fsv_tyb_ok(rows_per_cta), "rows_per_cta must be 2, 4, 6, 8, 12 or 16");
+        CHMY_REQUIRE(fsv_tyb_ok(rows_per_cta), "rows_per_cta must be 4, 6 or 8");
         g_fuse_tyb = rows_per_cta;
     }
     if (cluster_size > 0) {
-        CHMY_REQUIRE(cluster_size == 1 || cluster_size == 2 || cluster_size == 4 || cluster_size == 8, "cluster_size must be 1, 2, 4 or 8");
+        CHMY_REQUIRE(cluster_size >= 1 && cluster_size <= 8, "cluster_size must be 1..8 (the portable cluster limit)");
         g_fuse_cl = cluster_size;
     }
     if (z_chunk > 0) g_fuse_cz = z_chunk;
     return CHMY_OK;
 }
 
-template <bool TD, bool FUN, int TYB>
+template <bool TD, bool FUN, int TYB, int HINT>
 static int launch_fused(const FusedP& p, int cl, int variant, dim3 grid, cudaStream_t st) {
-    void (*kern)(const FusedP, const int, const int) = k_fused_sv<TD, FUN, TYB>;
-    if constexpr (TYB <= 4) {
-        if (variant & 2) kern = k_fused_sv_pl<TD, FUN, TYB>;
-    }
+    void (*kern)(const FusedP, const int, const int) = k_fused_sv<TD, FUN, TYB, HINT>;
     const size_t smem = fsv_smem_bytes(TYB);
-    static bool attr_done[2][64] = {};   // per instantiation, flavour and device (function attributes are per device)
+    static bool attr_done[64] = {};   // per instantiation and device (function attributes are per device)
     int dev = 0;
-    const int fl = (variant & 2) ? 1 : 0;
     CHMY_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_done[fl][dev]) {
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (dev >= 0 && dev < 64) attr_done[fl][dev] = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -183,15 +256,90 @@ static int launch_fused(const FusedP& p, int cl, int variant, dim3 grid, cudaStr
     return CHMY_OK;
 }
 
+typedef CUresult (*chmy_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static chmy_encode_tiled_fn encode_tiled() {
+    static chmy_encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (chmy_encode_tiled_fn)f;
+    }
+    return fn;
+}
+
+// rank-3 Float64 map over one buffer of a PITCHED field, origin at logical (-2, -1, -1) (16-byte aligned: logical x = 0 sits
+// on a 128-byte boundary), box = the CTA's tile of one plane: `rows` segments of 64 cells
+static int ftm_make_map(CUtensorMap* map, const chmy_field* f, const double* buf_p0, int rows) {
+    chmy_encode_tiled_fn enc = encode_tiled();
+    CHMY_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+    void* base = (void*)(buf_p0 - 2 - f->stride[1] - f->stride[2]);
+    const cuuint64_t dims[3]    = {(cuuint64_t)f->stride[1], (cuuint64_t)f->sd[1], (cuuint64_t)f->sd[2]};
+    const cuuint64_t strides[2] = {(cuuint64_t)f->stride[1] * 8, (cuuint64_t)f->stride[2] * 8};
+    const cuuint32_t box[3] = {64, (cuuint32_t)rows, 1}, es[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CHMY_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return CHMY_OK;
+}
+
+template <bool TD, bool FUN, int TYB>
+static int launch_fused_tma(const FusedP& p, const FtmMaps& maps, int cl, dim3 grid, cudaStream_t st) {
+    void (*kern)(const FusedP, const int, const FtmMaps) = k_fused_tma<TD, FUN, TYB>;
+    const size_t smem = ftm_smem_bytes(TYB);
+    static bool attr_done[64] = {};
+    int dev = 0;
+    CHMY_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(FSV_LANES, TYB, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = (unsigned)cl; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = cl > 1 ? 1 : 0;
+    CHMY_CUDA(cudaLaunchKernelEx(&cfg, kern, p, cl, maps));
+    return CHMY_OK;
+}
+
+template <bool TD, bool FUN, int TYB>
+static int launch_fused_hint(const FusedP& p, int cl, int variant, dim3 grid, cudaStream_t st) {
+    // cache-policy flavours (variant bits 2..4 -> HINT bits 0..2) exist for the instantiations the headline runs
+    if constexpr (!TD && FUN && (TYB == 4 || TYB == 6)) {
+        switch ((variant >> 2) & 7) {
+        case 1: return launch_fused<TD, FUN, TYB, 1>(p, cl, variant, grid, st);
+        case 2: return launch_fused<TD, FUN, TYB, 2>(p, cl, variant, grid, st);
+        case 3: return launch_fused<TD, FUN, TYB, 3>(p, cl, variant, grid, st);
+        case 6: return launch_fused<TD, FUN, TYB, 6>(p, cl, variant, grid, st);
+        case 7: return launch_fused<TD, FUN, TYB, 7>(p, cl, variant, grid, st);
+        default: break;
+        }
+    }
+    return launch_fused<TD, FUN, TYB, 0>(p, cl, variant, grid, st);
+}
+
 template <bool TD, bool FUN>
-static int launch_fused_tyb(const FusedP& p, int tyb, int cl, dim3 grid, cudaStream_t st) {
+static int launch_fused_tyb(const FusedP& p, const FtmMaps* maps, int tyb, int cl, dim3 grid, cudaStream_t st) {
+    if (maps) {        // the TMA-fed sweep
+        switch (tyb) {
+        case 4: return launch_fused_tma<TD, FUN, 4>(p, *maps, cl, grid, st);
+        case 6: return launch_fused_tma<TD, FUN, 6>(p, *maps, cl, grid, st);
+        default: return launch_fused_tma<TD, FUN, 8>(p, *maps, cl, grid, st);
+        }
+    }
     switch (tyb) {
-    case 2: return launch_fused<TD, FUN, 2>(p, cl, g_fuse_var, grid, st);
-    case 4: return launch_fused<TD, FUN, 4>(p, cl, g_fuse_var, grid, st);
-    case 6: return launch_fused<TD, FUN, 6>(p, cl, g_fuse_var, grid, st);
-    case 12: return launch_fused<TD, FUN, 12>(p, cl, g_fuse_var, grid, st);
-    case 16: return launch_fused<TD, FUN, 16>(p, cl, g_fuse_var, grid, st);
-    default: return launch_fused<TD, FUN, 8>(p, cl, g_fuse_var, grid, st);
+    case 4: return launch_fused_hint<TD, FUN, 4>(p, cl, g_fuse_var, grid, st);
+    case 6: return launch_fused_hint<TD, FUN, 6>(p, cl, g_fuse_var, grid, st);
+    default: return launch_fused_hint<TD, FUN, 8>(p, cl, g_fuse_var, grid, st);
     }
 }
 
@@ -264,17 +412,23 @@ int chmy_run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_
     const bool td = chmy_force_true_div() || !markstein_ok(Gdt) || !markstein_ok(s[0]) || !markstein_ok(s[1]);
     // geometry: clusters shrink for short boxes (slabs of a split launch)
     int tyb = g_fuse_tyb, cl = g_fuse_cl;
-    while (cl > 1 && (cl / 2) * tyb - 2 >= box.n[1]) cl /= 2;
-    while (tyb > 4 && cl == 1 && tyb / 2 - 2 >= box.n[1] && fsv_tyb_ok(tyb / 2)) tyb /= 2;
-    if (tyb == 2 && cl == 1) { tyb = 4; }   // a lone 2-row CTA has no interior row
+    while (cl > 1 && (cl - 1) * tyb - 2 >= box.n[1]) cl -= 1;
+    if (tyb > 4 && cl == 1 && 4 - 2 >= box.n[1]) tyb = 4;
     p.rows_int = cl * tyb - 2;
     const int nch = (box.n[2] + g_fuse_cz - 1) / g_fuse_cz;
     p.cz = (box.n[2] + nch - 1) / nch;
     const dim3 grid((unsigned)((box.n[0] + FSV_XI - 1) / FSV_XI), (unsigned)((box.n[1] + p.rows_int - 1) / p.rows_int * cl),
                     (unsigned)((box.n[2] + p.cz - 1) / p.cz));
+    FtmMaps maps;
+    const FtmMaps* mp = nullptr;
+    if (g_fuse_var & 2) {     // TMA-fed sweep: tensor maps of the eleven ring operands over their CURRENT buffers
+        for (int c = 0; c < 6; ++c) CHMY_TRY(ftm_make_map(&maps.m[c], S[c], cur[c], tyb));
+        for (int c = 0; c < 5; ++c) CHMY_TRY(ftm_make_map(&maps.m[6 + c], S[11 + c], S[11 + c]->p0, tyb));
+        mp = &maps;
+    }
     int rc;
-    if (rho) rc = td ? launch_fused_tyb<true, false>(p, tyb, cl, grid, st) : launch_fused_tyb<false, false>(p, tyb, cl, grid, st);
-    else     rc = td ? launch_fused_tyb<true, true>(p, tyb, cl, grid, st) : launch_fused_tyb<false, true>(p, tyb, cl, grid, st);
+    if (rho) rc = td ? launch_fused_tyb<true, false>(p, mp, tyb, cl, grid, st) : launch_fused_tyb<false, false>(p, mp, tyb, cl, grid, st);
+    else     rc = td ? launch_fused_tyb<true, true>(p, mp, tyb, cl, grid, st) : launch_fused_tyb<false, true>(p, mp, tyb, cl, grid, st);
     CHMY_TRY(rc);
     ctx->n_launches++;
     return CHMY_OK;

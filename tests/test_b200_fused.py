@@ -40,7 +40,7 @@ def _bc_V(ch_or_o, V, names=("x", "y", "z")):
     return tuple((comps[i], {a: (D() if a == names[i] else N()) for a in names}) for i in range(3))
 
 
-GEOMS = [(8, 4, 64), (4, 1, 3), (8, 1, 5), (16, 1, 64), (4, 8, 7), (16, 2, 4), (8, 8, 16), (4, 2, 1)]
+GEOMS = [(8, 4, 64), (4, 1, 3), (8, 1, 5), (6, 4, 64), (4, 8, 7), (6, 3, 4), (8, 8, 16), (4, 2, 1), (6, 5, 9), (6, 1, 2)]
 
 
 @pytest.mark.parametrize("n", [(70, 37, 9), (17, 9, 5), (125, 64, 20), (1, 1, 1), (60, 6, 3)])
@@ -76,12 +76,11 @@ def test_fused_iteration_bit_exact_vs_oracle(ch, arch, oracle, n, geom):
     _set_tuning(0, 0)
 
 
-EXPERIMENTAL = [(2, 8, 64, 1), (2, 4, 16, 0), (4, 4, 64, 3), (4, 2, 5, 2), (2, 8, 64, 3), (6, 2, 64, 1), (12, 1, 64, 1), (6, 4, 7, 0)]
+EXPERIMENTAL = [(4, 4, 64, 3), (6, 4, 64, 3), (4, 6, 7, 3), (6, 2, 5, 3), (8, 1, 4, 3), (4, 1, 3, 2), (6, 5, 64, 3)]
 
 
 @pytest.mark.skipif(__import__("os").environ.get("CHMY_EXPERIMENTAL", "0") != "1",
-                    reason="round-2 candidates (2-row CTAs, software-pipelined phase A): proven by the host emulation, "
-                           "not yet run on a GPU; set CHMY_EXPERIMENTAL=1")
+                    reason="candidates (cache-policy flavours of the loads / stores: variant bits 2..4); set CHMY_EXPERIMENTAL=1")
 @pytest.mark.parametrize("geom", EXPERIMENTAL)
 @pytest.mark.parametrize("n", [(70, 37, 9), (125, 64, 20), (17, 9, 5)])
 def test_experimental_variants_bit_exact_vs_two_kernels(ch, n, geom):

@@ -56,7 +56,7 @@ class Pitched:
         return q
 
 
-def run_case(o, emul, n, box, cz, tyb, cl, td, fun, seed=0, pipelined=0):
+def run_case(o, emul, n, box, cz, tyb, cl, td, fun, seed=0, tma=0):
     rng = np.random.default_rng(seed)
     g = o.Grid((-1.0, -1.1, -1.2), (2.0, 2.3, 2.6), n)
     tau, tau_old, V, rV = o.TensorField(g), o.TensorField(g), o.VectorField(g), o.VectorField(g)
@@ -95,7 +95,7 @@ def run_case(o, emul, n, box, cz, tyb, cl, td, fun, seed=0, pipelined=0):
     sc = (C.c_double * 9)(*g.inv_spacing, eta_ve, dtau_Pr, dtau_r, nudtau, G * dt, eta)
     incv = (C.c_double * 12)(*g.origin, *g.spacing, *inc.c0, inc.r * inc.r, inc.inn, inc.out)
     incloc = (C.c_int * 3)(*inc.loc)
-    rc = emul.fused_emul_run(P, strides, bx, sc, incv, incloc, cz, tyb, cl, int(td), int(pipelined))
+    rc = emul.fused_emul_run(P, strides, bx, sc, incv, incloc, cz, tyb, cl, int(td), int(tma))
     assert rc == 0
 
     def same(a, b, name):
@@ -145,19 +145,20 @@ CASES = [
     ((130, 11, 10), ((0, 0, 0), (132, 13, 4)), 8, 4, 2),        # z slab
     ((66, 30, 5), ((64, 0, 0), (68, 32, 7)), 16, 8, 1),         # right x slab
     ((66, 30, 5), ((0, 4, 1), (8, 29, 6)), 2, 4, 2),            # left x slab, odd hi
-    ((70, 33, 9), None, 4, 2, 8),                               # 64-thread CTAs, cluster of 8 (round-2 candidate)
+    ((70, 33, 9), None, 4, 4, 8),                               # cluster of 8
     ((61, 37, 6), None, 64, 4, 4),                              # the shipped geometry
     ((70, 33, 9), None, 4, 6, 2),                               # 6-row CTAs, clusters of 2 (round-2 candidate: all SMs, 2 of 12 rows halo)
-    ((61, 37, 6), None, 64, 12, 1),                             # 12-row CTAs, no cluster (round-2 candidate: no cluster barrier at all)
+    ((61, 37, 6), None, 64, 6, 3),                              # odd cluster size
+    ((61, 50, 6), None, 64, 6, 5),
     ((130, 11, 10), ((0, 0, 0), (132, 13, 4)), 8, 6, 1),        # z slab with 6-row CTAs
     ((66, 30, 5), ((0, 4, 1), (8, 29, 6)), 2, 6, 4),            # left x slab, 6-row CTAs in clusters of 4
 ]
 
 
 @pytest.mark.parametrize("n,box,cz,tyb,cl", CASES)
-@pytest.mark.parametrize("td,fun,pipelined", [(True, False, 0), (False, True, 0), (False, False, 1), (True, True, 1)])
-def test_fused_sweep_equals_stress_then_velocity(oracle, emul, n, box, cz, tyb, cl, td, fun, pipelined):
-    """pipelined=1: the software-pipelined flavour of phase A (operands of plane kp+1 requested one plane ahead)."""
+@pytest.mark.parametrize("td,fun,tma", [(True, False, 0), (False, True, 0), (False, False, 1), (True, True, 1), (False, True, 1)])
+def test_fused_sweep_equals_stress_then_velocity(oracle, emul, n, box, cz, tyb, cl, td, fun, tma):
+    """tma=1: the TMA-fed flavour (fused_tma.cuh): ring slots filled two planes ahead, register-fed operands one plane ahead."""
     if box is None:
         box = ((0, 0, 0), tuple(x + 2 for x in n))
-    run_case(oracle, emul, n, box, cz, tyb, cl, td, fun, seed=sum(n) + cz, pipelined=pipelined)
+    run_case(oracle, emul, n, box, cz, tyb, cl, td, fun, seed=sum(n) + cz, tma=tma)
