@@ -74,18 +74,20 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the untimed multi-rank correctness check")
-    ap.add_argument("--split", default="auto", choices=["auto", "on", "off"],
-                    help="multi-GPU: order of launches that carry a halo exchange -- on = inner region overlapped with slabs + "
-                         "batches (the reference's order), off = one full-range kernel then batches + exchange, auto = the "
-                         "library times both on the first launches and keeps the faster (results are identical)")
+    ap.add_argument("--split", default="on", choices=["auto", "on", "off"],
+                    help="launches with boundary batches -- on (= auto, the default): the batches and the halo exchange overlap "
+                         "the kernel (fused 3D sweep: boundary tiles first + a retire counter, one launch; plain kernels: the "
+                         "reference's inner region + slabs); off: one kernel, then batches + exchange on one stream "
+                         "(results are identical)")
     ap.add_argument("--no-split", action="store_true", help="same as --split off")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
                     help="multi-GPU: transport of the halo exchange -- nccl = pack + ncclSend/ncclRecv + unpack (the measured path), "
                          "peer = EXPERIMENTAL: the pack kernels store into the neighbour's HBM over NVLink, sequence flags instead "
                          "of the NCCL group (chmy_set_exchange_mode; results are identical)")
-    ap.add_argument("--fused", type=int, default=1, choices=[0, 1, 3],
-                    help="3D Stokes: lazily fuse update_stress! + update_velocity! into one sweep (chmy_set_fusion); "
-                         "0 = the two tuned kernels; 3 = additionally the EXPERIMENTAL sweeps (2D workloads; 3D thermal pair)")
+    ap.add_argument("--fused", type=int, default=3, choices=[0, 1, 3],
+                    help="lazily fuse pairs of launches into one sweep (chmy_set_fusion): 3 (default) = every pair with a sweep "
+                         "(3D stress + velocity; 2D stress + velocity, compute_q + update_C, thermal flux + update in 2D / 3D); "
+                         "1 = only the 3D stress + velocity sweep; 0 = the two tuned kernels")
     return ap.parse_args()
 
 
@@ -364,9 +366,9 @@ def run_b200(args):
     wl = args.workload
     n = tuple(args.n) if args.n else WORKLOADS[wl][0]
     split_mode = "off" if args.no_split else args.split
-    ch.set_launch_split({"auto": "auto", "on": True, "off": False}[split_mode])
-    fused2d = args.fused == 3 and not wl.startswith("stokes3d")      # EXPERIMENTAL 2D sweeps (ops_fused2d.cu)
-    fused_t3 = args.fused == 3 and wl == "stokes3d_thermal"          # EXPERIMENTAL 3D thermal sweep (fused_thermal3.cuh)
+    ch.set_launch_split(arch, split_mode != "off")
+    fused2d = args.fused == 3 and not wl.startswith("stokes3d")      # 2D flux -> update sweeps (ops_fused2d.cu)
+    fused_t3 = args.fused == 3 and wl == "stokes3d_thermal"          # 3D thermal sweep (fused_thermal3.cuh)
     fused = (bool(args.fused) and wl.startswith("stokes3d")) or fused2d
     ch.set_fusion(arch, 3 if (fused2d or fused_t3) else int(fused))
     if wl == "diffusion2d":
@@ -415,8 +417,6 @@ def run_b200(args):
     ch.synchronize(arch)
 
     K, W = args.steps, max(args.warmup, 3)
-    if world > 1 and split_mode == "auto":
-        W = max(W, 5)       # the library times its first 4 launches of each kind (2 per order) before settling: keep them untimed
     for _ in range(W):
         step()
     ch.synchronize(arch)
@@ -433,10 +433,13 @@ def run_b200(args):
     ms_local = ch.event_elapsed_ms(arch, 0, 1)
     l1 = ch.launch_count(arch)
     nfused = ch.fused_count(arch)
+    noverl = ch.overlapped_count(arch)
     xstats = dict(zip(("peer", "nccl"), ch.exchange_stats(arch))) if world > 1 else None     # rank 0's messages so far
     clocks = sampler.stop() if rank == 0 else None
     ch.barrier(arch)
     (ms_max,) = ch.allreduce_max(arch, ms_local) if world > 1 else (ms_local,)
+    # every rank's own device time of the K steps (a slow GPU or a late rank shows up here; the line reports the max)
+    per_rank = list(ch.allreduce_max(arch, *[ms_local / K if r == rank else 0.0 for r in range(world)])) if world > 1 else [ms_local / K]
     t_it = ms_max / K * 1e-3
     teff_gpu = a_eff_bytes(wl, n) / t_it / 1e9
 
@@ -572,14 +575,14 @@ def run_b200(args):
     if rank == 0:
         line = {
             "metric": "T_eff", "value": teff_gpu * world, "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": t_it * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": t_it * 1e3, "ms_per_step_by_rank": per_rank, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[wl][2], "n_local": list(n), "proc_dims": list(pdims) if pdims else [1] * len(n),
                        "nIO": WORKLOADS[wl][1], "fused_sweep": fused, "split_launches": split_mode, "exchange": (args.exchange if world > 1 else None), "A_eff_GB_per_gpu": a_eff_bytes(wl, n) / 1e9,
                        "l2": "inputs larger than L2 (every field >= 2 GB; 126 MB L2), no flush needed",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "T_eff_per_gpu": teff_gpu, "frac_of_hbm_peak": teff_gpu / peak, "hbm_peak": peak, "hbm_peak_source": peak_src,
-            "clocks": clocks, "gpu_launches": int(l1 - l0), "fused_sweeps": int(nfused), "exchange_msgs": xstats, "roofline": roofline, "e2e": e2e, "cpu_baseline": cb,
+            "clocks": clocks, "gpu_launches": int(l1 - l0), "launches_per_step": (l1 - l0) / K, "fused_sweeps": int(nfused), "overlapped_launches": int(noverl), "exchange_msgs": xstats, "roofline": roofline, "e2e": e2e, "cpu_baseline": cb,
             "multi_gpu_check": mgc,
         }
         print(json.dumps(line), flush=True)

@@ -114,13 +114,14 @@ SYMBOLS = {
     "chmy_exchange_stats": (C.c_int, [_vp, _P(C.c_uint64), _P(C.c_uint64)]),
     "chmy_selftest_division": (C.c_int, [_vp, C.c_double, C.c_longlong, C.c_ulonglong, _P(C.c_ulonglong), _P(C.c_int)]),
     "chmy_set_tuning": (C.c_int, [C.c_int, C.c_int]),
-    "chmy_set_launch_tuning": (C.c_int, [C.c_int]),
-    "chmy_selftest_split_tuner": (C.c_int, [_P(C.c_float), C.c_int, _i32p, _P(C.c_int32)]),
-    "chmy_launch_split_plan": (C.c_int, [_P(LaunchDesc), _i32p, _P(C.c_int32), _i32p, _i32p]),
+    "chmy_set_launch_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "chmy_overlapped_count": (C.c_int, [C.c_void_p, _P(C.c_uint64)]),
+    "chmy_launch_split_plan": (C.c_int, [_P(LaunchDesc), _i32p, C.c_int32, _P(C.c_int32), _i32p, _i32p]),
+    "chmy_selftest_tile_order": (C.c_int, [_i32p, _i32p, _i32p, C.c_int32, _i32p]),
     "chmy_set_fusion": (C.c_int, [_vp, C.c_int]),
     "chmy_fused_count": (C.c_int, [_vp, _P(C.c_uint64)]),
-    "chmy_set_fused_tuning": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
-    "chmy_set_fused2d_tuning": (C.c_int, [C.c_int, C.c_int]),
+    "chmy_set_fused_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "chmy_set_fused2d_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "chmy_halo_slab_len": (C.c_int, [_vp, C.c_int, _i64p]),
     "chmy_halo_pack": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "chmy_halo_unpack": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),

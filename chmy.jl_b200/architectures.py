@@ -140,31 +140,43 @@ def launch_count(arch: Architecture) -> int:
 
 
 def set_fusion(arch: Architecture, enable=True):
-    """Lazily fuse `launch(update_stress!)` + `launch(update_velocity!; bc)` of a 3D PT iteration into one sweep
-    (include/chmy_b200.h: chmy_set_fusion).  Results are bit-identical with and without it.
-    `enable=3` additionally turns on the EXPERIMENTAL 2D sweeps (2D Stokes pair, compute_q!+update_C!, 2D thermal pair)."""
-    L.check(L.lib().chmy_set_fusion(arch.ctx, int(enable)))
+    """`fuse!(arch)`: run `launch(update_stress!)` + `launch(update_velocity!; bc)` (3D) and the 2D / thermal flux -> update
+    pairs as ONE sweep each (include/chmy_b200.h: chmy_set_fusion).  Results are identical; the reference has no counterpart.
+    True = every fused sweep (3); 1 = only the 3D stress + velocity sweep; False / 0 = off."""
+    v = 3 if enable is True else int(enable)
+    L.check(L.lib().chmy_set_fusion(arch.ctx, v))
 
 
 def fused_count(arch: Architecture) -> int:
-    n = C.c_uint64()
+    n = C.c_uint64(0)
     L.check(L.lib().chmy_fused_count(arch.ctx, C.byref(n)))
     return int(n.value)
 
 
-def set_fused_tuning(rows_per_cta: int = 0, cluster_size: int = 0, z_chunk: int = 0, variant: int = -1):
-    L.check(L.lib().chmy_set_fused_tuning(int(rows_per_cta), int(cluster_size), int(z_chunk), int(variant)))
+def overlapped_count(arch: Architecture) -> int:
+    """launches whose boundary batches / halo exchange ran behind the boundary tiles of a still-running fused sweep"""
+    n = C.c_uint64(0)
+    L.check(L.lib().chmy_overlapped_count(arch.ctx, C.byref(n)))
+    return int(n.value)
 
 
-def set_fused2d_tuning(rows_per_chunk: int = 0, unroll: int = 0):
-    L.check(L.lib().chmy_set_fused2d_tuning(int(rows_per_chunk), int(unroll)))
+def set_fused_tuning(arch: Architecture, rows_per_cta: int = 0, cluster_size: int = 0, z_chunk: int = 0, variant: int = -1):
+    """tile geometry of the fused 3D sweep of THIS context (0 / -1 keep a setting)"""
+    L.check(L.lib().chmy_set_fused_tuning(arch.ctx, int(rows_per_cta), int(cluster_size), int(z_chunk), int(variant)))
 
 
-def set_launch_split(split="auto"):
-    """Order of launches that carry an exchange: True = inner region overlapped with the boundary stream (the reference's
-    order), False = one full-range kernel followed by the batches, "auto" (default) = time both on the first launches and
-    keep the faster.  Results are identical (include/chmy_b200.h: chmy_set_launch_tuning)."""
-    L.check(L.lib().chmy_set_launch_tuning(2 if split == "auto" else (1 if split else 0)))
+def set_fused2d_tuning(arch: Architecture, rows_per_chunk: int = 0, unroll: int = 0):
+    L.check(L.lib().chmy_set_fused2d_tuning(arch.ctx, int(rows_per_chunk), int(unroll)))
+
+
+def set_launch_split(arch: Architecture, split=True, bc_fold=None):
+    """Launches with boundary batches on this context: split truthy ("auto", "on", True; the default) = the batches and the
+    halo exchange overlap the kernel (KernelLaunch.jl:160-181: inner region + slabs on two streams; boundary tiles first +
+    a retire counter for the fused 3D sweep); False / "off" = one kernel, then the batches, on one stream; "always" = overlap even without a neighbour (tests, A/B).  bc_fold: a batch
+    set without exchange as ONE launch (default) or one launch per dimension.  Results are identical
+    (include/chmy_b200.h: chmy_set_launch_tuning)."""
+    on = 0 if split in (False, 0, "off") else (2 if split in ("always", 2) else 1)
+    L.check(L.lib().chmy_set_launch_tuning(arch.ctx, on, -1 if bc_fold is None else int(bool(bc_fold))))
 
 
 def set_exchange_mode(arch: Architecture, mode="nccl"):

@@ -3,6 +3,9 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 // declared in bc.cu / ops.cu / ops_fast.cu
@@ -48,16 +51,21 @@ extern "C" int chmy_device_count(int* count) {
 // ---------------------------------------------------------------------------------------------- context
 // live contexts: a Field may outlive its Architecture in a garbage-collected host language (finalizer order is not
 // defined), so chmy_field_destroy must not touch a context that is already gone
-static chmy_ctx* g_live[256];
-static int g_nlive = 0;
-static void ctx_register(chmy_ctx* c) { if (g_nlive < 256) g_live[g_nlive++] = c; }
+static std::mutex g_live_mu;
+static std::vector<chmy_ctx*> g_live;
+static void ctx_register(chmy_ctx* c) {
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    g_live.push_back(c);
+}
 static void ctx_unregister(chmy_ctx* c) {
-    for (int i = 0; i < g_nlive; ++i)
-        if (g_live[i] == c) { g_live[i] = g_live[--g_nlive]; return; }
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    for (size_t i = 0; i < g_live.size(); ++i)
+        if (g_live[i] == c) { g_live[i] = g_live.back(); g_live.pop_back(); return; }
 }
 static bool ctx_alive(const chmy_ctx* c) {
-    for (int i = 0; i < g_nlive; ++i)
-        if (g_live[i] == c) return true;
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    for (chmy_ctx* q : g_live)
+        if (q == c) return true;
     return false;
 }
 
@@ -73,6 +81,9 @@ static int ctx_init(chmy_ctx* c) {
     CHMY_CUDA(cudaMalloc(&c->d_red, 64 * sizeof(unsigned long long)));
     CHMY_CUDA(cudaMallocHost(&c->h_red, 64 * sizeof(unsigned long long)));
     CHMY_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+    CHMY_CUDA(cudaMalloc(&c->d_done, 64 * sizeof(unsigned int)));
+    CHMY_CUDA(cudaMemset(c->d_done, 0, 64 * sizeof(unsigned int)));
+    chmy_tuning_defaults(&c->tun);
     return CHMY_OK;
 }
 
@@ -88,6 +99,7 @@ extern "C" int chmy_ctx_create(int device_id, chmy_ctx** out) {
     c->device = device_id - 1;
     const int rc = ctx_init(c);
     if (rc != CHMY_OK) {           // release whatever was created before the failing call; the error text stays
+        if (c->d_done) cudaFree(c->d_done);
         if (c->h_red) cudaFreeHost(c->h_red);
         if (c->d_red) cudaFree(c->d_red);
         if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -110,6 +122,7 @@ extern "C" int chmy_ctx_destroy(chmy_ctx* c) {
     cudaDeviceSynchronize();
     if (c->comm) chmy_comm_destroy(c->comm);
     cudaFree(c->d_red);
+    cudaFree(c->d_done);
     cudaFreeHost(c->h_red);
     if (c->ev_time) {
         for (int i = 0; i < CHMY_MAX_EVENTS; ++i) if (c->ev_time[i]) cudaEventDestroy(c->ev_time[i]);
@@ -117,8 +130,6 @@ extern "C" int chmy_ctx_destroy(chmy_ctx* c) {
     }
     cudaEventDestroy(c->ev_fork);
     cudaEventDestroy(c->ev_join);
-    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
-    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     cudaStreamDestroy(c->s_main);
     cudaStreamDestroy(c->s_bnd);
     free(c);
@@ -313,7 +324,7 @@ static int copy_box_host(chmy_ctx* ctx, const chmy_field* f, void* host, const i
     CHMY_TRY(chmy_box_from(f, lo, hi, &b));
     if (b.n[0] <= 0 || b.n[1] <= 0 || b.n[2] <= 0) return CHMY_OK;
     CHMY_TRY(chmy_flush(ctx));
-    if (!to_host) const_cast<chmy_field*>(f)->frame_synced = false;
+    if (!to_host) const_cast<chmy_field*>(f)->frame_dirty(0);
     CHMY_CUDA(cudaSetDevice(ctx->device));
     char* dev = f->at_bytes(b.lo[0], f->nd > 1 ? b.lo[1] : 0, f->nd > 2 ? b.lo[2] : 0);
     cudaMemcpy3DParms p;
@@ -520,6 +531,44 @@ static int validate_batches(const chmy_grid_desc* g, const chmy_batch_desc bc[CH
     return CHMY_OK;
 }
 
+// 64-bit FNV-1a over everything that decides WHICH cells a batch set writes and from what: a field whose frame (the cells
+// outside the ops' index range) was last written by batch set X needs no carry-over into its ping-pong twin when the next
+// sweep is followed by X again -- X rewrites exactly those cells from cells the sweep has just produced.
+static uint64_t batch_signature(const chmy_grid_desc* g, const chmy_batch_desc bc[CHMY_MAX_DIMS][2]) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&h](const void* p, size_t n) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    };
+    mix(&g->ndims, sizeof(g->ndims));
+    for (int D = 0; D < g->ndims; ++D)
+        for (int s = 0; s < 2; ++s) {
+            const chmy_batch_desc& b = bc[D][s];
+            mix(&b.kind, sizeof(b.kind));
+            if (b.kind == CHMY_BATCH_EMPTY) continue;
+            mix(&b.nfields, sizeof(b.nfields));
+            for (int q = 0; q < b.nfields && q < CHMY_MAX_BATCH_FIELDS; ++q) {
+                mix(&b.fields[q], sizeof(b.fields[q]));
+                if (b.kind != CHMY_BATCH_FIELD) continue;
+                mix(&b.bc_kind[q], sizeof(b.bc_kind[q]));
+                mix(&b.value[q], sizeof(b.value[q]));
+                mix(&b.value_field[q], sizeof(b.value_field[q]));
+            }
+        }
+    return h ? h : 1;
+}
+
+// bc!(arch, grid, batchset): D = N..1, side 1 then 2 (batch.jl:20-29)
+static int run_batches(chmy_ctx* ctx, const chmy_grid_desc* g, const chmy_batch_desc bc[CHMY_MAX_DIMS][2], cudaStream_t st) {
+    ctx->batch_sig = batch_signature(g, bc);
+    int handled = 0;
+    int rc = ctx->tun.bc_fold ? chmy_run_bc_all(ctx, g, bc, st, &handled) : CHMY_OK;   // every dimension in one launch when nothing is exchanged
+    if (!handled)
+        for (int D = g->ndims - 1; D >= 0 && rc == CHMY_OK; --D) rc = bc_dim(ctx, g, D, &bc[D][0], &bc[D][1], st);
+    ctx->batch_sig = 0;
+    return rc;
+}
+
 extern "C" int chmy_bc(chmy_ctx* ctx, const chmy_grid_desc* g, const chmy_batch_desc bc[CHMY_MAX_DIMS][2], int flags) {
     CHMY_REQUIRE(ctx && g && bc, "NULL argument");
     CHMY_TRY(validate_grid(g));
@@ -527,63 +576,26 @@ extern "C" int chmy_bc(chmy_ctx* ctx, const chmy_grid_desc* g, const chmy_batch_
     CHMY_TRY(validate_batches(g, bc, &any_ex));
     CHMY_TRY(chmy_flush(ctx));
     CHMY_CUDA(cudaSetDevice(ctx->device));
-    for (int D = g->ndims - 1; D >= 0; --D)               // D = N..1, side 1 then 2 (batch.jl:20-29)
-        CHMY_TRY(bc_dim(ctx, g, D, &bc[D][0], &bc[D][1], ctx->s_main));
+    CHMY_TRY(run_batches(ctx, g, bc, ctx->s_main));
     if (flags & CHMY_LAUNCH_BLOCKING) CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));
     return CHMY_OK;
 }
 
-// Split policy of launches that carry an exchange: 1 (default) = inner region on the main stream overlapped with slabs +
-// batches on the boundary stream, as the reference does; 0 = one full-range kernel followed by the batches on one stream
-// (outer_width is a hint: results cannot depend on it).  Over NVLink a halo exchange costs tens of microseconds against
-// ~20 ms of compute at the headline size, so the unsplit order may win; round 2 measures it (bench.py --no-split).
-//   2 (default) = measure both on the first launches of each (op, kernel family, grid) and keep the faster (SplitTuner).
-static int g_split_policy = -1;
-static int split_policy() {
-    if (g_split_policy < 0) {
-        const char* e = getenv("CHMY_SPLIT");
-        g_split_policy = (e && e[0] == '0') ? 0 : (e && e[0] == '1') ? 1 : 2;
-    }
-    return g_split_policy;
-}
-extern "C" int chmy_set_launch_tuning(int split_launches) {
-    if (split_launches >= 0) g_split_policy = split_launches > 2 ? 2 : split_launches;
+// Launches with boundary batches: 1 (default) = the batches (and the halo exchange) overlap the kernel -- the reference's
+// inner region + slabs on two streams for the plain kernels, boundary tiles first + a retire counter for the fused sweeps
+// (run_overlapped); 0 = one kernel, then the batches, on one stream.  Results cannot depend on it (outer_width is a hint:
+// the ops are pointwise writers).  Deterministic: no run-time tuning, every rank takes the same order.
+extern "C" int chmy_set_launch_tuning(chmy_ctx* ctx, int overlap, int bc_fold) {
+    CHMY_REQUIRE(ctx != nullptr, "ctx is NULL");
+    CHMY_TRY(chmy_flush(ctx));
+    if (overlap >= 0) ctx->tun.overlap = overlap > 2 ? 2 : overlap;
+    if (bc_fold >= 0) ctx->tun.bc_fold = bc_fold ? 1 : 0;
     return CHMY_OK;
 }
 
-// ---- the tuner's state machine (pure; chmy_selftest_split_tuner drives it on the CPU)
-// launches 0,1: split ; 2,3: unsplit ; the first launch of each order warms caches / allocations / NCCL connections and
-// is not compared.  Afterwards: whichever order's second launch was faster (ties keep the reference's overlapped order).
-static int tuner_policy(const SplitTuner* t) { return t->decided >= 0 ? t->decided : (t->calls < 2 ? 1 : 0); }
-static void tuner_report(SplitTuner* t, float ms) {
-    if (t->decided >= 0 || t->calls >= 4) return;
-    t->ms[t->calls++] = ms;
-    if (t->calls == 4) t->decided = (t->ms[1] <= t->ms[3]) ? 1 : 0;
-}
-static SplitTuner* tuner_for(chmy_ctx* ctx, const chmy_launch_desc* d, int family) {
-    for (int q = 0; q < ctx->ntuners; ++q) {
-        SplitTuner* t = &ctx->tuners[q];
-        if (t->op == d->op && t->family == family && t->n[0] == d->grid.n[0] && t->n[1] == d->grid.n[1] && t->n[2] == d->grid.n[2])
-            return t;
-    }
-    if (ctx->ntuners >= 8) return nullptr;       // more distinct launches than slots: those keep the overlapped order
-    SplitTuner* t = &ctx->tuners[ctx->ntuners++];
-    memset(t, 0, sizeof(*t));
-    t->op = d->op; t->family = family; t->decided = -1;
-    for (int a = 0; a < 3; ++a) t->n[a] = d->grid.n[a];
-    return t;
-}
-// ms: the times the timed launches would report, in order.  policies[i] = order chosen for launch i (1 split, 0 unsplit)
-extern "C" int chmy_selftest_split_tuner(const float* ms, int n, int32_t* policies, int32_t* decided) {
-    CHMY_REQUIRE(ms && policies && decided && n >= 0, "bad argument");
-    SplitTuner t;
-    memset(&t, 0, sizeof(t));
-    t.decided = -1;
-    for (int i = 0; i < n; ++i) {
-        policies[i] = tuner_policy(&t);
-        if (t.decided < 0) tuner_report(&t, ms[i]);
-    }
-    *decided = t.decided;
+extern "C" int chmy_overlapped_count(const chmy_ctx* ctx, uint64_t* n) {
+    CHMY_REQUIRE(ctx && n, "NULL argument");
+    *n = ctx->n_overlapped;
     return CHMY_OK;
 }
 
@@ -591,8 +603,8 @@ extern "C" int chmy_selftest_split_tuner(const float* ms, int n, int32_t* polici
 // outer_width is a scheduling hint (results cannot depend on it: the ops are pointwise writers): unless EXACT_SPLIT is set
 // the widths follow the kernel's preference `pref` (or nullptr) and the x widths are nudged so that the inner region and
 // the right slab start on even x indices (the tuned kernels own aligned pairs of cells); every cell is still computed
-// exactly once.  Pure function of the descriptor (exported as chmy_launch_split_plan for the CPU tests).
-static int plan_split(const chmy_launch_desc* d, const int* pref, bool* split_out, int wl[3], int wr[3]) {
+// exactly once.  Pure function of the descriptor and the policy (exported as chmy_launch_split_plan for the CPU tests).
+static int plan_split(const chmy_launch_desc* d, const int* pref, int overlap, bool* split_out, int wl[3], int wr[3]) {
     const chmy_grid_desc* g = &d->grid;
     const int N = g->ndims;
     int fulln[3];
@@ -606,44 +618,47 @@ static int plan_split(const chmy_launch_desc* d, const int* pref, bool* split_ou
             // the slabs must contain everything the batches touch: halo, first/last interior and send planes
             if (d->outer_width[a] < 3 || 2 * d->outer_width[a] > g->n[a] + 2) split = false;
         }
-        // without a neighbour to talk to there is nothing to overlap, so run one full-range kernel
+        // without a neighbour to talk to there is nothing worth six extra launches, so run one full-range kernel
         if (!any_ex && !(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) split = false;
-        if (!split_policy() && !(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) split = false;
+        if (!overlap && !(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) split = false;
+    }
+    for (int a = 0; a < 3; ++a) wl[a] = wr[a] = 0;
+    if (split) {
+        for (int a = 0; a < N; ++a) wl[a] = wr[a] = (int)d->outer_width[a];
+        if (!(d->flags & CHMY_LAUNCH_EXACT_SPLIT) && pref) {
+            for (int a = 0; a < N; ++a)
+                if (pref[a] >= 3 && 2 * pref[a] + 2 <= fulln[a]) wl[a] = wr[a] = pref[a];
+        }
+        if (!(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) {
+            wl[0] += wl[0] & 1;
+            wr[0] -= (fulln[0] - wr[0]) & 1;            // the right slab starts on an even index; never wider than asked
+            if (wr[0] < 3) wr[0] += 2;
+            // the nudged widths do not fit (tiny grids): one full-range kernel rather than slabs on odd x origins
+            if (wl[0] + wr[0] > fulln[0]) { split = false; for (int a = 0; a < 3; ++a) wl[a] = wr[a] = 0; }
+        }
     }
     *split_out = split;
-    for (int a = 0; a < 3; ++a) wl[a] = wr[a] = 0;
-    if (!split) return CHMY_OK;
-    for (int a = 0; a < N; ++a) wl[a] = wr[a] = (int)d->outer_width[a];
-    if (!(d->flags & CHMY_LAUNCH_EXACT_SPLIT) && pref) {
-        for (int a = 0; a < N; ++a)
-            if (pref[a] >= 3 && 2 * pref[a] + 2 <= fulln[a]) wl[a] = wr[a] = pref[a];
-    }
-    if (!(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) {
-        wl[0] += wl[0] & 1;
-        wr[0] -= (fulln[0] - wr[0]) & 1;            // the right slab starts on an even index; never wider than asked
-        if (wr[0] < 3) wr[0] += 2;
-        if (wl[0] + wr[0] > fulln[0]) { wl[0] = (int)d->outer_width[0]; wr[0] = (int)d->outer_width[0]; }
-    }
     return CHMY_OK;
 }
 
-extern "C" int chmy_launch_split_plan(const chmy_launch_desc* d, const int32_t* pref, int32_t* split, int32_t wl[3], int32_t wr[3]) {
+extern "C" int chmy_launch_split_plan(const chmy_launch_desc* d, const int32_t* pref, int32_t overlap, int32_t* split, int32_t wl[3], int32_t wr[3]) {
     CHMY_REQUIRE(d && split && wl && wr, "NULL argument");
     CHMY_TRY(validate_grid(&d->grid));
     CHMY_REQUIRE(d->has_bc, "a launch without bc is one full-range kernel (KernelLaunch.jl:121-126)");
     bool s = false;
     int l[3], r[3], p[3] = {0, 0, 0};
     if (pref) for (int a = 0; a < 3; ++a) p[a] = pref[a];
-    CHMY_TRY(plan_split(d, pref ? p : nullptr, &s, l, r));
+    CHMY_TRY(plan_split(d, pref ? p : nullptr, overlap ? 1 : 0, &s, l, r));
     *split = s ? 1 : 0;
     for (int a = 0; a < 3; ++a) { wl[a] = l[a]; wr[a] = r[a]; }
     return CHMY_OK;
 }
 
 // Region orchestration of `launch` (KernelLaunch.jl:105-183); RUN(box, stream) executes the op on one region.
-// pref: slab widths the op's kernel prefers (outer_width is a hint unless EXACT_SPLIT), or nullptr
+// pref: slab widths the op's kernel prefers (outer_width is a hint unless EXACT_SPLIT), or nullptr.
+// The split plan is computed by the caller BEFORE anything irreversible (buffer swaps) happens.
 template <class RUN>
-static int orchestrate(chmy_ctx* ctx, const chmy_launch_desc* d, const RUN& run, const int* pref = nullptr) {
+static int orchestrate(chmy_ctx* ctx, const chmy_launch_desc* d, const RUN& run, bool split, const int wl[3], const int wr[3]) {
     const chmy_grid_desc* g = &d->grid;
     const int N = g->ndims;
     // worksize = ncenters + 2, I = J + Offset(-1)  ->  I in 0..n+1   (KernelLaunch.jl:41,109)
@@ -652,62 +667,37 @@ static int orchestrate(chmy_ctx* ctx, const chmy_launch_desc* d, const RUN& run,
 
     if (!d->has_bc) {   // launch_without_bc: one full-range kernel even when the Launcher has an outer_width (:121-126)
         CHMY_TRY(run(full, ctx->s_main));
-    } else {
-        bool split = false;
-        int wl[3] = {0, 0, 0}, wr[3] = {0, 0, 0};
-        CHMY_TRY(plan_split(d, pref, &split, wl, wr));
-        // self-tuning order: while undecided, time this launch (alone on an idle device) in the order the tuner asks for
-        SplitTuner* tn = nullptr;
-        bool timing = false;
-        if (split && split_policy() == 2 && !(d->flags & CHMY_LAUNCH_EXACT_SPLIT)) {
-            tn = tuner_for(ctx, d, pref ? pref[0] * 1000 + pref[1] : 0);
-            if (tn) {
-                timing = tn->decided < 0;
-                if (!tuner_policy(tn)) split = false;
-            }
-        }
-        if (timing) {
-            if (!ctx->ev_t0) CHMY_CUDA(cudaEventCreate(&ctx->ev_t0));
-            if (!ctx->ev_t1) CHMY_CUDA(cudaEventCreate(&ctx->ev_t1));
-            CHMY_CUDA(cudaStreamSynchronize(ctx->s_bnd));
-            CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));
-            CHMY_CUDA(cudaEventRecord(ctx->ev_t0, ctx->s_main));
-        }
-        if (!split) {   // KernelLaunch.jl:156-159
-            CHMY_TRY(run(full, ctx->s_main));
-            for (int D = N - 1; D >= 0; --D) CHMY_TRY(bc_dim(ctx, g, D, &d->bc[D][0], &d->bc[D][1], ctx->s_main));
-        } else {        // KernelLaunch.jl:160-181: inner region on the main stream, slabs + batches on the boundary stream
-            CHMY_CUDA(cudaEventRecord(ctx->ev_fork, ctx->s_main));
-            CHMY_CUDA(cudaStreamWaitEvent(ctx->s_bnd, ctx->ev_fork, 0));
-            for (int D = N - 1; D >= 0; --D) {
-                for (int S = 0; S < 2; ++S) {
-                    Box b;   // outer_worksize / outer_offset, KernelLaunch.jl:63-87
-                    for (int a = 0; a < 3; ++a) {
-                        if (a >= N) { b.lo[a] = 0; b.n[a] = 1; }
-                        else if (a < D) { b.lo[a] = 0; b.n[a] = full.n[a]; }
-                        else if (a == D) { b.lo[a] = S == 0 ? 0 : full.n[a] - wr[a]; b.n[a] = S == 0 ? wl[a] : wr[a]; }
-                        else { b.lo[a] = wl[a]; b.n[a] = full.n[a] - wl[a] - wr[a]; }
-                    }
-                    CHMY_TRY(run(b, ctx->s_bnd));
+    } else if (!split) {   // KernelLaunch.jl:156-159
+        CHMY_TRY(run(full, ctx->s_main));
+        CHMY_TRY(run_batches(ctx, g, d->bc, ctx->s_main));
+    } else {        // KernelLaunch.jl:160-181: inner region on the main stream, slabs + batches on the boundary stream
+        CHMY_CUDA(cudaEventRecord(ctx->ev_fork, ctx->s_main));
+        CHMY_CUDA(cudaStreamWaitEvent(ctx->s_bnd, ctx->ev_fork, 0));
+        ctx->batch_sig = batch_signature(g, d->bc);
+        for (int D = N - 1; D >= 0; --D) {
+            for (int S = 0; S < 2; ++S) {
+                Box b;   // outer_worksize / outer_offset, KernelLaunch.jl:63-87
+                for (int a = 0; a < 3; ++a) {
+                    if (a >= N) { b.lo[a] = 0; b.n[a] = 1; }
+                    else if (a < D) { b.lo[a] = 0; b.n[a] = full.n[a]; }
+                    else if (a == D) { b.lo[a] = S == 0 ? 0 : full.n[a] - wr[a]; b.n[a] = S == 0 ? wl[a] : wr[a]; }
+                    else { b.lo[a] = wl[a]; b.n[a] = full.n[a] - wl[a] - wr[a]; }
                 }
-                CHMY_TRY(bc_dim(ctx, g, D, &d->bc[D][0], &d->bc[D][1], ctx->s_bnd));
+                const int rc = run(b, ctx->s_bnd);
+                if (rc != CHMY_OK) { ctx->batch_sig = 0; return rc; }
             }
-            Box in;      // inner_worksize / inner_offset, KernelLaunch.jl:60-61
-            for (int a = 0; a < 3; ++a) {
-                in.lo[a] = a < N ? wl[a] : 0;
-                in.n[a]  = a < N ? full.n[a] - wl[a] - wr[a] : 1;
-            }
-            CHMY_TRY(run(in, ctx->s_main));
-            CHMY_CUDA(cudaEventRecord(ctx->ev_join, ctx->s_bnd));
-            CHMY_CUDA(cudaStreamWaitEvent(ctx->s_main, ctx->ev_join, 0));
+            const int rc = bc_dim(ctx, g, D, &d->bc[D][0], &d->bc[D][1], ctx->s_bnd);
+            if (rc != CHMY_OK) { ctx->batch_sig = 0; return rc; }
         }
-        if (timing) {
-            float ms = 0.0f;
-            CHMY_CUDA(cudaEventRecord(ctx->ev_t1, ctx->s_main));
-            CHMY_CUDA(cudaEventSynchronize(ctx->ev_t1));
-            CHMY_CUDA(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
-            tuner_report(tn, ms);
+        ctx->batch_sig = 0;
+        Box in;      // inner_worksize / inner_offset, KernelLaunch.jl:60-61
+        for (int a = 0; a < 3; ++a) {
+            in.lo[a] = a < N ? wl[a] : 0;
+            in.n[a]  = a < N ? full.n[a] - wl[a] - wr[a] : 1;
         }
+        CHMY_TRY(run(in, ctx->s_main));
+        CHMY_CUDA(cudaEventRecord(ctx->ev_join, ctx->s_bnd));
+        CHMY_CUDA(cudaStreamWaitEvent(ctx->s_main, ctx->ev_join, 0));
     }
     if (d->flags & CHMY_LAUNCH_BLOCKING) CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));   // KernelLaunch.jl:117
     return CHMY_OK;
@@ -732,7 +722,10 @@ extern "C" int chmy_fused_count(const chmy_ctx* ctx, uint64_t* sweeps) {
 }
 
 static int run_plain(chmy_ctx* ctx, const chmy_launch_desc* d) {
-    return orchestrate(ctx, d, [&](const Box& b, cudaStream_t st) { return run_op(ctx, d, b, st); });
+    bool split = false;
+    int wl[3] = {0, 0, 0}, wr[3] = {0, 0, 0};
+    if (d->has_bc) CHMY_TRY(plan_split(d, nullptr, ctx->tun.overlap, &split, wl, wr));
+    return orchestrate(ctx, d, [&](const Box& b, cudaStream_t st) { return run_op(ctx, d, b, st); }, split, wl, wr);
 }
 
 int chmy_flush(chmy_ctx* ctx) {
@@ -753,10 +746,82 @@ static int ensure_shadow(chmy_ctx* ctx, chmy_field* f) {
     }
     CHMY_CUDA(cudaMemsetAsync(f->alt_alloc, 0, f->bytes, ctx->s_main));
     f->frame_synced = false;
+    f->frame_writer = 0;
+    return CHMY_OK;
+}
+
+// Which ping-pong fields need their frame (cells outside the ops' index range, never produced by a sweep) carried over into
+// the shadow buffer: those whose frame changed since the buffers last agreed -- unless the only writer was the very batch
+// set `sig` that follows this sweep too (it rewrites those cells in the new buffer before anything reads them).
+static int frames_to_carry(chmy_field* const* pp, int npp, uint64_t sig, chmy_field** fr, double** fsrc, double** fdst) {
+    int nfr = 0;
+    for (int q = 0; q < npp; ++q) {
+        chmy_field* f = pp[q];
+        if (f->frame_synced) continue;
+        if (sig != 0 && f->frame_writer == sig) continue;
+        fr[nfr] = f; fsrc[nfr] = f->p0; fdst[nfr] = f->alt_p0(); ++nfr;
+        f->frame_synced = true; f->frame_writer = 0;
+    }
+    return nfr;
+}
+
+// cuStreamWaitValue32: the boundary stream sleeps on the sweep's retire counter without occupying an SM
+typedef int (*chmy_wait_value_fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+static chmy_wait_value_fn wait_value_fn() {
+    static chmy_wait_value_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (chmy_wait_value_fn)f;
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+int chmy_spin_until(chmy_ctx* ctx, const unsigned int* counter, unsigned int target, cudaStream_t st);   // bc.cu: one-thread fallback
+
+// One fused 3D sweep whose boundary batches overlap it WITHOUT splitting the launch: the sweep runs its boundary tiles
+// first and counts them as they retire; the boundary stream (highest priority) carries the frame over, sleeps on that
+// counter, then applies the batches / packs, exchanges and unpacks the halos while the interior tiles are still running.
+// The next launch on the main stream waits for the boundary stream (KernelLaunch.jl:160-181 semantics, one launch).
+static int run_overlapped(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_desc* dv, double* const* cur,
+                          double* const* shadow, int nfr, chmy_field* const* fr, double* const* fsrc, double* const* fdst) {
+    const chmy_grid_desc* g = &dv->grid;
+    Box full;
+    for (int a = 0; a < 3; ++a) { full.lo[a] = 0; full.n[a] = (int)g->n[a] + 2; }
+    unsigned int* done = ctx->d_done + (ctx->n_overlapped & 31);      // a fresh word per launch (zeroed below)
+    CHMY_CUDA(cudaMemsetAsync(done, 0, sizeof(unsigned int), ctx->s_main));
+    CHMY_CUDA(cudaEventRecord(ctx->ev_fork, ctx->s_main));
+    unsigned int target = 0;
+    CHMY_TRY(chmy_run_fused(ctx, ds, dv, full, cur, shadow, ctx->s_main, done, &target));
+    CHMY_CUDA(cudaStreamWaitEvent(ctx->s_bnd, ctx->ev_fork, 0));
+    CHMY_TRY(chmy_frame_copy(ctx, &ds->grid, nfr, fr, fsrc, fdst, ctx->s_bnd));   // frame cells: untouched by the sweep
+    if (chmy_wait_value_fn wv = wait_value_fn()) {
+        const int rc = wv(ctx->s_bnd, (unsigned long long)(uintptr_t)done, target, 0x1u /* CU_STREAM_WAIT_VALUE_GEQ */);
+        CHMY_REQUIRE(rc == 0, "cuStreamWaitValue32 failed (%d)", rc);
+    } else {
+        CHMY_TRY(chmy_spin_until(ctx, done, target, ctx->s_bnd));
+    }
+    CHMY_TRY(run_batches(ctx, g, dv->bc, ctx->s_bnd));
+    CHMY_CUDA(cudaEventRecord(ctx->ev_join, ctx->s_bnd));
+    CHMY_CUDA(cudaStreamWaitEvent(ctx->s_main, ctx->ev_join, 0));
+    ctx->n_overlapped++;
+    if (dv->flags & CHMY_LAUNCH_BLOCKING) CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));   // KernelLaunch.jl:117
     return CHMY_OK;
 }
 
 static int run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_desc* dv) {
+    // everything that can fail for reasons of the descriptor is decided BEFORE the buffers are swapped
+    const bool exact = (dv->flags & CHMY_LAUNCH_EXACT_SPLIT) != 0;
+    bool split = false;
+    int wl[3] = {0, 0, 0}, wr[3] = {0, 0, 0};
+    // slabs of a literal split follow outer_width; otherwise the overlap needs no slabs at all (run_overlapped)
+    bool any_ex = false;
+    if (dv->has_bc) CHMY_TRY(validate_batches(&dv->grid, dv->bc, &any_ex));
+    if (dv->has_bc && exact) CHMY_TRY(plan_split(dv, nullptr, 1, &split, wl, wr));
+    if (split) CHMY_REQUIRE((wl[0] & 1) == 0 && ((dv->grid.n[0] + 2 - wr[0]) & 1) == 0, "fused sweep: x slabs must start on even indices");
     // ping-pong fields: tau[6], Pr, V[3]
     chmy_field* pp[10];
     for (int c = 0; c < 6; ++c) pp[c] = ds->fields[c];
@@ -765,43 +830,47 @@ static int run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launc
     for (int q = 0; q < 10; ++q)
         if (ensure_shadow(ctx, pp[q]) != CHMY_OK) return 1;      // out of memory: the caller falls back to two kernels
     // cells outside [0, n+1]^3 are not produced by the sweep: carry them over where they may have changed
+    const uint64_t sig = dv->has_bc ? batch_signature(&dv->grid, dv->bc) : 0;
     chmy_field* fr[10];
     double *fsrc[10], *fdst[10];
-    int nfr = 0;
-    for (int q = 0; q < 10; ++q)
-        if (!pp[q]->frame_synced) { fr[nfr] = pp[q]; fsrc[nfr] = pp[q]->p0; fdst[nfr] = pp[q]->alt_p0(); ++nfr; pp[q]->frame_synced = true; }
-    CHMY_TRY(chmy_frame_copy(ctx, &ds->grid, nfr, fr, fsrc, fdst, ctx->s_main));
+    const int nfr = frames_to_carry(pp, 10, sig, fr, fsrc, fdst);
     double *cur[10], *shadow[10];
     for (int q = 0; q < 10; ++q) { cur[q] = pp[q]->p0; shadow[q] = pp[q]->alt_p0(); }
     // from here on the fields ARE their new buffers: the boundary batches of this launch act on the new V
     for (int q = 0; q < 10; ++q) pp[q]->swap_buffers();
     ctx->n_fused++;
-    // slabs of a split launch sized to the sweep's tiles: one 60-cell row segment along x, one 2-CTA cluster along y
-    const int pref[3] = {60, 6, 0};
-    return orchestrate(ctx, dv, [&](const Box& b, cudaStream_t st) { return chmy_run_fused(ctx, ds, dv, b, cur, shadow, st); }, pref);
+    // without a neighbour the batches are one small launch: nothing worth hiding (measured: 20.41 vs 20.44 ms at 767^3)
+    if (dv->has_bc && !exact && any_ex && ctx->tun.overlap >= 1) return run_overlapped(ctx, ds, dv, cur, shadow, nfr, fr, fsrc, fdst);
+    if (dv->has_bc && !exact && ctx->tun.overlap == 2) return run_overlapped(ctx, ds, dv, cur, shadow, nfr, fr, fsrc, fdst);
+    CHMY_TRY(chmy_frame_copy(ctx, &ds->grid, nfr, fr, fsrc, fdst, ctx->s_main));
+    return orchestrate(ctx, dv, [&](const Box& b, cudaStream_t st) { return chmy_run_fused(ctx, ds, dv, b, cur, shadow, st); }, split, wl, wr);
 }
 
-// EXPERIMENTAL 2D sweeps (ops_fused2d.cu): same protocol as run_fused -- shadow buffers, frame carry-over, swap, then the
-// usual region orchestration with the sweep as the region kernel.  Returns 1 when the shadow buffers cannot be allocated.
+// 2D sweeps and the 3D thermal sweep (ops_fused2d.cu): same protocol as run_fused -- shadow buffers, frame carry-over, swap,
+// then the usual region orchestration with the sweep as the region kernel.  Returns 1 when the shadow buffers cannot be
+// allocated.
 static int run_fused2d(chmy_ctx* ctx, int kind, const chmy_launch_desc* dp, const chmy_launch_desc* dc) {
+    // x slabs of a split launch: one row segment (60 interior cells in 2D, 64 cells in the 3D thermal sweep); y, z as asked
+    const int pref[3] = {kind == 4 ? 64 : 60, 0, 0};
+    bool split = false;
+    int wl[3] = {0, 0, 0}, wr[3] = {0, 0, 0};
+    if (dc->has_bc) CHMY_TRY(plan_split(dc, pref, ctx->tun.overlap, &split, wl, wr));
+    if (split) CHMY_REQUIRE((wl[0] & 1) == 0 && ((dc->grid.n[0] + 2 - wr[0]) & 1) == 0, "fused sweep: x slabs must start on even indices");
     chmy_field* pp[6];
     const int npp = chmy_fused2d_pingpong(kind, dp, dc, pp);
     for (int q = 0; q < npp; ++q)
         if (ensure_shadow(ctx, pp[q]) != CHMY_OK) return 1;
+    const uint64_t sig = dc->has_bc ? batch_signature(&dc->grid, dc->bc) : 0;
     chmy_field* fr[6];
     double *fsrc[6], *fdst[6];
-    int nfr = 0;
-    for (int q = 0; q < npp; ++q)
-        if (!pp[q]->frame_synced) { fr[nfr] = pp[q]; fsrc[nfr] = pp[q]->p0; fdst[nfr] = pp[q]->alt_p0(); ++nfr; pp[q]->frame_synced = true; }
+    const int nfr = frames_to_carry(pp, npp, sig, fr, fsrc, fdst);
     if (dp->grid.ndims == 3) CHMY_TRY(chmy_frame_copy(ctx, &dp->grid, nfr, fr, fsrc, fdst, ctx->s_main));
     else CHMY_TRY(chmy_frame_copy2(ctx, &dp->grid, nfr, fr, fsrc, fdst, ctx->s_main));
     double *cur[6], *shadow[6];
     for (int q = 0; q < npp; ++q) { cur[q] = pp[q]->p0; shadow[q] = pp[q]->alt_p0(); }
     for (int q = 0; q < npp; ++q) pp[q]->swap_buffers();
     ctx->n_fused++;
-    // x slabs of a split launch: one row segment (60 interior cells in 2D, 64 cells in the 3D thermal sweep); y, z as asked
-    const int pref[3] = {kind == 4 ? 64 : 60, 0, 0};
-    return orchestrate(ctx, dc, [&](const Box& b, cudaStream_t st) { return chmy_run_fused2d(ctx, kind, dp, dc, b, cur, shadow, st); }, pref);
+    return orchestrate(ctx, dc, [&](const Box& b, cudaStream_t st) { return chmy_run_fused2d(ctx, kind, dp, dc, b, cur, shadow, st); }, split, wl, wr);
 }
 
 // The argument checks of chmy_launch, without a device (fields may be descriptor-only, chmy_field_create_shell).

@@ -72,7 +72,7 @@ static int run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chm
             CHMY_REQUIRE(bd->bc_kind[q] == CHMY_DIRICHLET || bd->bc_kind[q] == CHMY_NEUMANN, "FieldBatch: bad bc kind");
             for (int a = 0; a < g->ndims; ++a)
                 CHMY_REQUIRE(f->d[a] == g->n[a] + (f->loc[a] == CHMY_VERTEX ? 1 : 0), "FieldBatch: field/grid size mismatch");
-            bd->fields[q]->frame_synced = false;      // a halo of a Vertex field lies outside the ops' index range
+            bd->fields[q]->frame_dirty(ctx->batch_sig);      // a halo of a Vertex field lies outside the ops' index range
             BcEntry<T>& e = b.e[b.n++];
             e.f = bck_view<T>(f); e.kind = bd->bc_kind[q]; e.vertex = f->loc[dim] == CHMY_VERTEX; e.d = (int)f->d[dim];
             e.side = s; e.value = (T)bd->value[q];
@@ -98,6 +98,109 @@ static int run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chm
     const dim3 blk(128, 1, 1);
     const dim3 grd((b.nt[0] + 127) / 128, b.nt[1], 1);
     k_bc_dim<T><<<grd, blk, 0, st>>>(b);
+    ctx->n_launches++;
+    CHMY_CUDA(cudaGetLastError());
+    return CHMY_OK;
+}
+
+// ---- all dimensions, sides and fields of a batch set in ONE launch (bc_all_point, bc_kernels.cuh)
+template <class T>
+__global__ void __launch_bounds__(128) k_bc_all(const BcAllDev<T> b) {
+    const int z = blockIdx.z, s = z & 1, D = (z >> 1) % 3, q = z / 6;
+    if (D >= b.nd) return;
+    int nt[2] = {1, 1}, t = 0;
+    for (int a = 0; a < b.nd; ++a)
+        if (a != D) nt[t++] = b.n[a] + 3;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (a >= nt[0] || c >= nt[1]) return;
+    bc_all_point(b, q, D, s, a, c);
+}
+
+// Can the batch set run as one launch?  No exchange anywhere (a halo exchange sits between two dimensions), at most
+// BCK_ALL_FIELDS distinct fields of one element type, no field twice in one (dim, side).  Fills the device table.
+template <class T>
+static bool make_bc_all(const chmy_grid_desc* g, const chmy_batch_desc bc[CHMY_MAX_DIMS][2], int dtype, BcAllDev<T>* out,
+                        chmy_field** touched, int* ntouched) {
+    BcAllDev<T>& b = *out;
+    memset(&b, 0, sizeof(b));
+    b.nd = g->ndims;
+    for (int a = 0; a < 3; ++a) { b.n[a] = a < g->ndims ? (int)g->n[a] : 0; b.spacing[a] = a < g->ndims ? (T)g->spacing[a] : (T)0; }
+    for (int q = 0; q < BCK_ALL_FIELDS; ++q)
+        for (int D = 0; D < 3; ++D)
+            for (int s = 0; s < 2; ++s) b.fld[q].r[D][s].kind = -1;
+    chmy_field* fl[BCK_ALL_FIELDS];
+    for (int D = 0; D < g->ndims; ++D)
+        for (int s = 0; s < 2; ++s) {
+            const chmy_batch_desc& bd = bc[D][s];
+            if (bd.kind == CHMY_BATCH_EXCHANGE) return false;
+            if (bd.kind != CHMY_BATCH_FIELD) continue;
+            for (int k = 0; k < bd.nfields; ++k) {
+                chmy_field* f = bd.fields[k];
+                if (!f || !f->alloc || f->dtype != dtype || f->nd != g->ndims) return false;
+                int q = 0;
+                while (q < b.nf && fl[q] != f) ++q;
+                if (q == b.nf) {
+                    if (b.nf == BCK_ALL_FIELDS) return false;
+                    fl[b.nf++] = f;
+                    b.fld[q].f = bck_view<T>(f);
+                    for (int a = 0; a < 3; ++a) { b.fld[q].d[a] = (int)f->d[a]; b.fld[q].vertex[a] = a < f->nd && f->loc[a] == CHMY_VERTEX; }
+                }
+                BcRule<T>& r = b.fld[q].r[D][s];
+                if (r.kind >= 0) return false;                      // the same field twice on one side: keep the sequential order
+                r.kind = bd.bc_kind[k]; r.value = (T)bd.value[k]; r.vp = nullptr; r.vsy = 0;
+                if (const chmy_field* vf = bd.value_field[k]) {
+                    if (vf->dtype != dtype) return false;
+                    r.vp = reinterpret_cast<const T*>(vf->p0); r.vsy = vf->nd > 1 ? vf->stride[1] : 0;
+                }
+            }
+        }
+    for (int q = 0; q < b.nf; ++q) touched[q] = fl[q];
+    *ntouched = b.nf;
+    return b.nf > 0;
+}
+
+template <class T>
+static int run_bc_all_t(chmy_ctx* ctx, const chmy_grid_desc* g, const chmy_batch_desc bc[CHMY_MAX_DIMS][2], int dtype, cudaStream_t st,
+                        int* handled) {
+    BcAllDev<T> b;
+    chmy_field* touched[BCK_ALL_FIELDS];
+    int nt = 0;
+    if (!make_bc_all<T>(g, bc, dtype, &b, touched, &nt)) return CHMY_OK;
+    for (int q = 0; q < nt; ++q) touched[q]->frame_dirty(ctx->batch_sig);
+    int m0 = 1, m1 = 1;        // largest face extents over the dims
+    for (int D = 0; D < g->ndims; ++D) {
+        int e[2] = {1, 1}, t = 0;
+        for (int a = 0; a < g->ndims; ++a)
+            if (a != D) e[t++] = (int)g->n[a] + 3;
+        m0 = e[0] > m0 ? e[0] : m0; m1 = e[1] > m1 ? e[1] : m1;
+    }
+    CHMY_REQUIRE(m1 <= 65535, "face too large for one launch");
+    k_bc_all<T><<<dim3((m0 + 127) / 128, m1, 6 * b.nf), 128, 0, st>>>(b);
+    ctx->n_launches++;
+    CHMY_CUDA(cudaGetLastError());
+    *handled = 1;
+    return CHMY_OK;
+}
+
+// *handled = 1: the whole batch set ran as one launch; 0: the caller applies it dimension by dimension
+int chmy_run_bc_all(chmy_ctx* ctx, const chmy_grid_desc* g, const chmy_batch_desc bc[CHMY_MAX_DIMS][2], cudaStream_t st, int* handled) {
+    *handled = 0;
+    int dtype = -1;
+    for (int D = 0; D < g->ndims && dtype < 0; ++D)
+        for (int s = 0; s < 2 && dtype < 0; ++s)
+            if (bc[D][s].kind == CHMY_BATCH_FIELD && bc[D][s].nfields > 0 && bc[D][s].fields[0]) dtype = bc[D][s].fields[0]->dtype;
+    if (dtype < 0) return CHMY_OK;
+    if (dtype == CHMY_F32) return run_bc_all_t<float>(ctx, g, bc, dtype, st, handled);
+    return run_bc_all_t<double>(ctx, g, bc, dtype, st, handled);
+}
+
+// one thread sleeping on a device counter: the fall-back of cuStreamWaitValue32 (api.cu, run_overlapped)
+__global__ void k_spin_until(const unsigned int* counter, unsigned int target) {
+    while (*reinterpret_cast<const volatile unsigned int*>(counter) < target) __nanosleep(500);
+    __threadfence();
+}
+int chmy_spin_until(chmy_ctx* ctx, const unsigned int* counter, unsigned int target, cudaStream_t st) {
+    k_spin_until<<<1, 1, 0, st>>>(counter, target);
     ctx->n_launches++;
     CHMY_CUDA(cudaGetLastError());
     return CHMY_OK;
@@ -178,7 +281,7 @@ int chmy_unpack_fields(chmy_ctx* ctx, int dim, int side, int nf, chmy_field* con
                        cudaStream_t st) {
     CHMY_REQUIRE(nf >= 1 && fs && fs[0], "exchange: no fields");
     for (int q = 0; q < nf; ++q)
-        if (fs[q]) fs[q]->frame_synced = false;
+        if (fs[q]) fs[q]->frame_dirty(ctx->batch_sig);
     if (fs[0]->dtype == CHMY_F32)
         return run_slab<false, float>(ctx, dim, side, nf, fs, static_cast<float*>(const_cast<void*>(dbuf)), st);
     return run_slab<false, double>(ctx, dim, side, nf, fs, static_cast<double*>(const_cast<void*>(dbuf)), st);
@@ -236,21 +339,21 @@ int chmy_box_from(const chmy_field* f, const int64_t* lo, const int64_t* hi, Box
 }
 
 int chmy_fill_box(chmy_ctx* ctx, chmy_field* f, double v, const Box& b, cudaStream_t st) {
-    f->frame_synced = false;
+    f->frame_dirty(0);
     if (f->dtype == CHMY_F32) return launch_util(ctx, FillF<float>{f->viewT<float>(), (float)v}, b, st);
     return launch_util(ctx, FillF<double>{f->view(), v}, b, st);
 }
 int chmy_copy_box(chmy_ctx* ctx, chmy_field* d, const chmy_field* s, const Box& b, cudaStream_t st) {
-    d->frame_synced = false;
+    d->frame_dirty(0);
     if (d->dtype == CHMY_F32) return launch_util(ctx, CopyF<float>{d->viewT<float>(), s->viewT<float>()}, b, st);
     return launch_util(ctx, CopyF<double>{d->view(), s->view()}, b, st);
 }
 int chmy_incl_box(chmy_ctx* ctx, chmy_field* f, const InclDev& q, const Box& b, cudaStream_t st) {
-    f->frame_synced = false;
+    f->frame_dirty(0);
     return launch_util(ctx, InclF<double>{f->view(), q}, b, st);
 }
 int chmy_incl_box_f32(chmy_ctx* ctx, chmy_field* f, const InclDevT<float>& q, const Box& b, cudaStream_t st) {
-    f->frame_synced = false;
+    f->frame_dirty(0);
     return launch_util(ctx, InclF<float>{f->viewT<float>(), q}, b, st);
 }
 

@@ -86,6 +86,100 @@ BCK_HD void bc_point(const BcBatchDev<T>& b, int a, int c) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------- all dimensions at once
+// bc!(arch, grid, batchset) applies the batches dimension by dimension, D = N..1 (batch.jl:20-29), and a later dimension
+// reads cells an earlier one wrote (faces span the transverse range 0..n_t+2, edges and corners included) -- which is why
+// the per-dimension kernel needs one launch per dimension.  Every rule, though, is a pure function of ONE cell:
+//     f[target] = rule(value, f[neighbour])          (or just `value` for Dirichlet on a Vertex location)
+// so the final content of a cell is a chain of at most N rules ending in a cell NO batch writes.  bc_all_point evaluates
+// that chain for one target cell straight from the untouched cells -- every target is computed independently, nothing
+// written by the kernel is read by it, and all dimensions, sides and fields run as ONE launch with the same bits as
+// the sequential order (tests/test_bc_emulation.py: bit-identical to the oracle's dimension-by-dimension bc!).
+template <class T>
+struct BcRule {
+    int       kind;       // -1: no condition on this (dim, side) ; else chmy_bc_kind
+    T         value;
+    const T*  vp;         // Field-valued condition: logical (0[,0]) of the (N-1)-dimensional value field, else nullptr
+    long long vsy;
+};
+template <class T>
+struct BcAllField {
+    BckView<T> f;
+    int        d[3];          // logical size per dim (1 for inactive dims)
+    int        vertex[3];     // location per dim
+    BcRule<T>  r[3][2];
+};
+#define BCK_ALL_FIELDS 6
+template <class T>
+struct BcAllDev {
+    int           nf, nd;
+    int           n[3];       // grid cells per dim: face points span 0..n+2 in every transverse dim
+    T             spacing[3];
+    BcAllField<T> fld[BCK_ALL_FIELDS];
+};
+
+template <class T>
+BCK_HD int bc_all_target(const BcAllField<T>& F, int D, int s) {
+    const bool node = F.r[D][s].kind == BCK_DIRICHLET && F.vertex[D];
+    return s == 0 ? (node ? 1 : 0) : (node ? F.d[D] : F.d[D] + 1);
+}
+// the side of dim D whose condition writes cell I (or -1): I[D] is that side's target and every other index is a face point
+template <class T>
+BCK_HD int bc_all_side(const BcAllDev<T>& b, const BcAllField<T>& F, int D, const int I[3]) {
+    for (int t = 0; t < b.nd; ++t)
+        if (t != D && (I[t] < 0 || I[t] > b.n[t] + 2)) return -1;
+    for (int s = 0; s < 2; ++s)
+        if (F.r[D][s].kind >= 0 && I[D] == bc_all_target(F, D, s)) return s;
+    return -1;
+}
+template <class T>
+BCK_HD T bc_all_value(const BcAllDev<T>& b, const BcRule<T>& r, int D, const int I[3]) {
+    if (!r.vp) return r.value;
+    int tr[2] = {0, 0}, t = 0;
+    for (int a = 0; a < b.nd; ++a)
+        if (a != D) tr[t++] = I[a];                    // remove_dim(dim, I)
+    return r.vp[(long long)tr[0] + (long long)tr[1] * r.vsy];
+}
+
+// face point (a, c) of (field q, dim D, side s): computes the FINAL content of its target cell unless a dimension that is
+// applied later (D' < D) writes that cell too (then that dimension's thread computes it)
+template <class T>
+BCK_HD void bc_all_point(const BcAllDev<T>& b, int q, int D, int s, int a, int c) {
+    const BcAllField<T>& F = b.fld[q];
+    if (F.r[D][s].kind < 0) return;
+    int I[3] = {0, 0, 0};
+    {
+        const int tr[2] = {a, c};
+        int t = 0;
+        for (int dd = 0; dd < b.nd; ++dd) I[dd] = dd == D ? bc_all_target(F, D, s) : tr[t++];
+    }
+    if (bc_all_side(b, F, D, I) != s) return;          // the other side's target coincides (degenerate sizes): it wins below
+    for (int Dl = 0; Dl < D; ++Dl)
+        if (bc_all_side(b, F, Dl, I) >= 0) return;
+    // walk back through the dimensions in reverse order of application (D, D+1, ...: later applied first)
+    int   cur[3] = {I[0], I[1], I[2]};
+    int   cd[3], cs[3], nc = 0;
+    T     cv[3];
+    bool  terminal = false;
+    T     v = (T)0;
+    for (int De = D; De < b.nd; ++De) {
+        const int se = De == D ? s : bc_all_side(b, F, De, cur);
+        if (se < 0) continue;
+        const BcRule<T>& r = F.r[De][se];
+        const T val = bc_all_value(b, r, De, cur);
+        if (r.kind == BCK_DIRICHLET && F.vertex[De]) { v = val; terminal = true; break; }
+        cd[nc] = De; cs[nc] = se; cv[nc] = val; ++nc;
+        cur[De] = se == 0 ? 1 : F.d[De];               // the neighbour the rule reads
+    }
+    if (!terminal) v = bck_ld(F.f, cur[0], cur[1], cur[2]);
+    for (int k = nc - 1; k >= 0; --k) {
+        const BcRule<T>& r = F.r[cd[k]][cs[k]];
+        if (r.kind == BCK_DIRICHLET) v = (T)fma((T)2.0, cv[k] - v, v);
+        else v = (T)fma(b.spacing[cd[k]], cs[k] == 0 ? -cv[k] : cv[k], v);
+    }
+    bck_st(F.f, I[0], I[1], I[2], v);
+}
+
 // ---------------------------------------------------------------------------------------------- halo slabs
 // send index: side 1 -> 1+overlap, side 2 -> d-overlap (overlap = 1 for Vertex, 0 for Center);
 // recv index: side 1 -> 0, side 2 -> d+1; every other dimension spans the whole padded extent -1..d+2.

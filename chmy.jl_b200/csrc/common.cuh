@@ -124,6 +124,14 @@ struct chmy_field {
     // same values in both buffers (cleared by everything that may write such cells: fill/copy/set!/bc!/halo unpack).
     double*   alt_alloc;
     bool      frame_synced;
+    // who wrote the frame since the buffers last agreed: the signature of ONE boundary-batch set (its cells are rewritten
+    // by the same batch set after the next sweep, so they need no carry-over), or 0 = anything else / several writers
+    uint64_t  frame_writer;
+    void      frame_dirty(uint64_t sig) {
+        if (frame_synced) frame_writer = sig;
+        else if (frame_writer != sig) frame_writer = 0;
+        frame_synced = false;
+    }
     double*   alt_p0() const { return alt_alloc + (p0 - alloc); }
     void      swap_buffers() { double* a = alloc; const ptrdiff_t o = p0 - alloc; alloc = alt_alloc; alt_alloc = a; p0 = alloc + o; }
 
@@ -141,14 +149,12 @@ struct chmy_field {
 struct chmy_comm;   // comm.cu
 int chmy_comm_check(const chmy_comm* c);   // comm.cu: has a peer-store flag wait timed out?
 
-// Self-tuning split policy (api.cu): for one (op, kernel family, grid) with an exchange, the first launches are timed in
-// both orders -- overlapped inner + slabs, then one full-range kernel followed by the batches -- and the faster one is kept.
-struct SplitTuner {
-    int       op, family;     // chmy_op ; slab-width preference of the kernel family (0 = none)
-    long long n[3];
-    int       calls;          // timed launches so far: 0,1 split ; 2,3 unsplit
-    float     ms[4];
-    int       decided;        // -1 undecided, 0 unsplit, 1 split
+// Per-context tuning (set from the environment when the context is created; chmy_set_fused_tuning & co. change it)
+struct chmy_tuning {
+    int fuse_tyb, fuse_cl, fuse_cz, fuse_var;   // fused 3D sweep: rows per CTA, CTAs per cluster, planes per z-chunk, barrier flavour
+    int f2_cy, f2_unroll, t3_cz;                // 2D sweeps: rows per y-chunk, rows per load group; 3D thermal sweep: planes per chunk
+    int overlap;                                // launches with boundary batches: 1 = overlap them with the kernel (default), 0 = one stream
+    int bc_fold;                                // 1 (default): a batch set without exchange runs as ONE launch (k_bc_all); 0: one per dimension
 };
 
 struct chmy_ctx {
@@ -169,10 +175,10 @@ struct chmy_ctx {
     int               has_pending;
     chmy_launch_desc  pending;
     uint64_t          n_fused;       // fused sweeps launched so far
-    // self-tuning split policy: per (op, family, grid) state + the two timing events (created on first use)
-    SplitTuner        tuners[8];
-    int               ntuners;
-    cudaEvent_t       ev_t0, ev_t1;
+    chmy_tuning       tun;
+    unsigned int*     d_done;        // device counter of the boundary-first sweep (ops_fused.cu): CTAs of boundary tiles retired
+    uint64_t          batch_sig;     // signature of the batch set being applied right now (0 outside launch / bc!)
+    uint64_t          n_overlapped;  // launches whose batches ran behind the boundary tiles of a still-running sweep
 };
 
 // api.cu: runs a deferred update_stress! launch now (every entry point that reads or writes device state calls it)
@@ -190,14 +196,18 @@ int chmy_validate_op(const chmy_launch_desc* d);
 int chmy_validate_batch(const chmy_grid_desc* g, int dim, const chmy_batch_desc* b);
 int chmy_run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_batch_desc* left,
                     const chmy_batch_desc* right, cudaStream_t st);
+int chmy_run_bc_all(chmy_ctx* ctx, const chmy_grid_desc* g, const chmy_batch_desc bc[CHMY_MAX_DIMS][2], cudaStream_t st, int* handled);
 // comm.cu
 int chmy_comm_destroy(chmy_comm* c);
 int chmy_exchange_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chmy_batch_desc* left,
                       const chmy_batch_desc* right, cudaStream_t st);
 // ops_fused.cu
 bool chmy_fused_eligible(const chmy_launch_desc* ds, const chmy_launch_desc* dv);
+// done != nullptr: boundary tiles first, each of their CTAs adds 1 to *done when retired; *n_signal = how many will
 int chmy_run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_desc* dv, const Box& box,
-                   double* const* cur, double* const* shadow, cudaStream_t st);
+                   double* const* cur, double* const* shadow, cudaStream_t st, unsigned int* done = nullptr,
+                   unsigned int* n_signal = nullptr);
+void chmy_tuning_defaults(chmy_tuning* t);
 int chmy_frame_copy(chmy_ctx* ctx, const chmy_grid_desc* g, int n, chmy_field* const* fs, double* const* src,
                     double* const* dst, cudaStream_t st);
 // ops_fused2d.cu (EXPERIMENTAL 2D sweeps)

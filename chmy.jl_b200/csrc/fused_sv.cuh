@@ -29,16 +29,13 @@
 #ifdef __CUDACC__
 #include "fast_common.cuh"
 #define FHD __device__ __forceinline__
+#define FHDH __host__ __device__ __forceinline__
 typedef double2 d2;
-// streaming (evict-first) flavours: the sweep's stores and its once-read operands must not push the rows that the
-// neighbouring tiles are about to re-read out of L2
-__device__ __forceinline__ double2 ld2s(const double* p) { return __ldcs(reinterpret_cast<const double2*>(p)); }
-__device__ __forceinline__ void st2s(double* p, double2 v) { __stcs(reinterpret_cast<double2*>(p), v); }
-__device__ __forceinline__ void st1s(double* p, double v) { __stcs(p, v); }
 #else
 #include <cmath>
 #include <cstring>
 #define FHD static inline
+#define FHDH static inline
 struct d2 {
     double x, y;
 };
@@ -71,15 +68,59 @@ static inline double coord_dev(double origin, double spacing, int loc, int i) {
 }
 static inline d2 ld2(const double* p) { return d2{p[0], p[1]}; }
 static inline void st2(double* p, d2 v) { p[0] = v.x; p[1] = v.y; }
-static inline d2 ld2s(const double* p) { return ld2(p); }
-static inline void st2s(double* p, d2 v) { st2(p, v); }
-static inline void st1s(double* p, double v) { *p = v; }
 #endif
 
 constexpr int FSV_LANES = 32;
 constexpr int FSV_XI    = 60;   // interior cells of a 64-cell row segment
 constexpr int FSV_NF    = 7;    // published per plane: Pr xx yy zz xy xz yz
 enum { FSV_PR = 0, FSV_XX, FSV_YY, FSV_ZZ, FSV_XY, FSV_XZ, FSV_YZ };
+
+// Launch order of the tiles (clusters) of one sweep.  Natural order: x fastest, then y, then z -- tiles that run at the
+// same time are neighbours in space and share their halo rows / lanes in L2.  With `tail` set (a launch whose boundary
+// batches / halo exchange overlap the sweep, api.cu run_overlapped) the order is arranged so that every BOUNDARY tile --
+// one that owns cells the batches or the exchange read or write: the first and last tiles along each dimension -- has
+// retired while a last stretch of interior tiles is still running: the last z layer of tiles (all boundary) runs first,
+// the other layers follow in natural order, and inside the final layer the boundary strips go before its interior.
+// Measured on B200 (2 GPUs, 767^3): launching ALL boundary tiles first costs the sweep 0.3 ms of L2 locality; this order
+// keeps the natural one for all but ~1.5 % of the tiles and still leaves ~6 % of the sweep to hide the exchange behind.
+// g: tiles per dim; [i0, i1): interior tile indices per dim (KernelLaunch.jl:160-181 overlaps the same work by splitting
+// the launch into an inner region and six slabs).
+struct TileOrder {
+    int g[3], i0[3], i1[3];
+    int tail;
+};
+FHDH int tile_total(const TileOrder& o) { return o.g[0] * o.g[1] * o.g[2]; }
+FHDH int tile_interior(const TileOrder& o) { return (o.i1[0] - o.i0[0]) * (o.i1[1] - o.i0[1]) * (o.i1[2] - o.i0[2]); }
+// linear index c -> tile (bx, by, bz); returns true for a boundary tile
+FHDH bool tile_decode(const TileOrder& o, int c, int& bx, int& by, int& bz) {
+    const int layer = o.g[0] * o.g[1];
+    const int ci = c / layer;
+    int r = c - ci * layer;
+    if (!o.tail) {
+        bz = ci; bx = r % o.g[0]; by = r / o.g[0];
+    } else {
+        bz = ci == 0 ? o.g[2] - 1 : ci - 1;
+        if (ci < o.g[2] - 1) {
+            bx = r % o.g[0]; by = r / o.g[0];
+        } else {        // the final layer: whole rows of the first / last y tiles, then the first / last x tiles, then the rest
+            const int ix = o.i1[0] - o.i0[0], iy = o.i1[1] - o.i0[1];
+            const int xb = o.g[0] - ix, yb = o.g[1] - iy, py = o.g[0] * yb;
+            int t;
+            if (r < py) {
+                bx = r % o.g[0]; t = r / o.g[0];
+                by = t < o.i0[1] ? t : t - o.i0[1] + o.i1[1];
+            } else if (r - py < xb * iy) {
+                r -= py;
+                t = r % xb; by = o.i0[1] + r / xb;
+                bx = t < o.i0[0] ? t : t - o.i0[0] + o.i1[0];
+            } else {
+                r -= py + xb * iy;
+                bx = o.i0[0] + r % ix; by = o.i0[1] + r / ix;
+            }
+        }
+    }
+    return bx < o.i0[0] || bx >= o.i1[0] || by < o.i0[1] || by >= o.i1[1] || bz < o.i0[2] || bz >= o.i1[2];
+}
 
 struct FusedP {
     const double *tc[6], *to[6], *Prc, *Vc[3], *rho;   // current tau, tau_old, Pr, V ; rho == nullptr -> FunctionField
@@ -92,6 +133,8 @@ struct FusedP {
     InclDev inc;
     int cz;        // planes per z-chunk
     int rows_int;  // interior rows per cluster = CL*TYB - 2
+    TileOrder order;        // linear cluster index -> tile
+    unsigned int* done;     // device counter: every CTA of a boundary tile adds 1 when its stores are visible (or nullptr)
 };
 
 // shared-memory exchange buffer of one CTA: [2 plane parities][FSV_NF][TYB rows][64 cells]
@@ -101,7 +144,6 @@ static inline size_t fsv_smem_bytes(int tyb) { return (size_t)2 * FSV_NF * tyb *
 struct FusedT {
     int  lane, ty, i, j, k0, k1;
     bool s_act;           // this lane loads and computes stresses
-    bool stream;          // this row's once-read operands may be loaded with the streaming policy
     int  nv;              // cells of the pair that are updated and stored (0, 1 or 2)
     bool fx0, fx1, fy;    // cell / row inside the op's index range
     int  jm, jp;          // 1 if row j-1 / j+1 may be addressed (0 on the cluster's first / last row)
@@ -120,10 +162,8 @@ FHD d2 fsv_zero() {
 
 // geometry of a thread: bx = row-segment index along x, grow = row index inside the cluster (0 .. rows_int+1),
 // cyc = cluster index along y, bz = z-chunk index
-FHD void fsv_init(FusedT& s, const FusedP& p, int lane, int ty, int grow, int bx, int cyc, int bz, bool fun, int hint = 0) {
+FHD void fsv_init(FusedT& s, const FusedP& p, int lane, int ty, int grow, int bx, int cyc, int bz, bool fun) {
     s.lane = lane; s.ty = ty;
-    // rows 0, 1 and the last two of a cluster are re-read by the neighbouring cluster (as its halo rows / by its halo rows)
-    s.stream = !(hint & 4) || (grow >= 2 && grow + 2 <= p.rows_int);
     s.i  = p.lo[0] - 2 + bx * FSV_XI + 2 * lane;
     s.j  = p.lo[1] - 1 + cyc * p.rows_int + grow;
     s.k0 = p.lo[2] + bz * p.cz;
@@ -181,9 +221,7 @@ FHD double fsv_from_left(double, const double* p_im1, bool ok) { return ok ? *p_
 #endif
 
 // ---- phase A: stresses of plane kp -> sn[FSV_NF] (new Pr, tau), stores for the cells this thread owns
-// HINT (cache policy, device only): bit 0 = streaming (evict-first) stores, bit 1 = streaming loads of the operands that
-// are read exactly once (tau, tau_old, Pr) -- on every row, or with bit 2 only on the rows no neighbouring tile re-reads
-template <bool TD, int HINT>
+template <bool TD>
 FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
     const d2 z2 = fsv_zero();
     d2 vx = z2, vxjm = z2, vy = z2, vyjp = z2, vzkp = z2, vzjmkp = z2, pr = z2;
@@ -195,21 +233,12 @@ FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
         vyjp   = ld2(p.Vc[1] + s.cv + (long long)s.jp * p.cv.sy);
         vzkp   = ld2(p.Vc[2] + s.cc + p.cc.sz);
         vzjmkp = ld2(p.Vc[2] + s.cc - (long long)s.jm * p.cc.sy + p.cc.sz);
-        if ((HINT & 2) && s.stream) {
-            pr = ld2s(p.Prc + s.cc);
+        pr = ld2(p.Prc + s.cc);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) { t[c] = ld2s(p.tc[c] + s.cc); o[c] = ld2s(p.to[c] + s.cc); }
-            t[3] = ld2s(p.tc[3] + s.vv); o[3] = ld2s(p.to[3] + s.vv);
-            t[4] = ld2s(p.tc[4] + s.vc); o[4] = ld2s(p.to[4] + s.vc);
-            t[5] = ld2s(p.tc[5] + s.cv); o[5] = ld2s(p.to[5] + s.cv);
-        } else {
-            pr = ld2(p.Prc + s.cc);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { t[c] = ld2(p.tc[c] + s.cc); o[c] = ld2(p.to[c] + s.cc); }
-            t[3] = ld2(p.tc[3] + s.vv); o[3] = ld2(p.to[3] + s.vv);
-            t[4] = ld2(p.tc[4] + s.vc); o[4] = ld2(p.to[4] + s.vc);
-            t[5] = ld2(p.tc[5] + s.cv); o[5] = ld2(p.to[5] + s.cv);
-        }
+        for (int c = 0; c < 3; ++c) { t[c] = ld2(p.tc[c] + s.cc); o[c] = ld2(p.to[c] + s.cc); }
+        t[3] = ld2(p.tc[3] + s.vv); o[3] = ld2(p.to[3] + s.vv);
+        t[4] = ld2(p.tc[4] + s.vc); o[4] = ld2(p.to[4] + s.vc);
+        t[5] = ld2(p.tc[5] + s.cv); o[5] = ld2(p.to[5] + s.cv);
     } else {
 #pragma unroll
         for (int c = 0; c < 6; ++c) { t[c] = z2; o[c] = z2; }
@@ -250,23 +279,13 @@ FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
     }
     if (kp >= s.k0 && kp < s.k1) {
         if (s.nv == 2) {
-            if (HINT & 1) {
-                st2s(p.dV + s.cc, dv);
-                st2s(p.Prn + s.cc, prn);
+            st2(p.dV + s.cc, dv);
+            st2(p.Prn + s.cc, prn);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) st2s(p.tn[c] + s.cc, tn[c]);
-                st2s(p.tn[3] + s.vv, tn[3]);
-                st2s(p.tn[4] + s.vc, tn[4]);
-                st2s(p.tn[5] + s.cv, tn[5]);
-            } else {
-                st2(p.dV + s.cc, dv);
-                st2(p.Prn + s.cc, prn);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) st2(p.tn[c] + s.cc, tn[c]);
-                st2(p.tn[3] + s.vv, tn[3]);
-                st2(p.tn[4] + s.vc, tn[4]);
-                st2(p.tn[5] + s.cv, tn[5]);
-            }
+            for (int c = 0; c < 3; ++c) st2(p.tn[c] + s.cc, tn[c]);
+            st2(p.tn[3] + s.vv, tn[3]);
+            st2(p.tn[4] + s.vc, tn[4]);
+            st2(p.tn[5] + s.cv, tn[5]);
         } else if (s.nv == 1) {
             p.dV[s.cc]  = dv.x;
             p.Prn[s.cc] = prn.x;
@@ -286,7 +305,7 @@ FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
 // ---- phase B: publish the stresses of plane kp, update the velocity of plane kp-1, rotate the carried planes.
 // own / below / above: exchange buffers (element 0 of [buf][field][row][cell]) of the CTAs holding this thread's
 // row, row j-1 and row j+1; rb / ra: the row numbers of j-1 / j+1 inside those CTAs.
-template <bool TD, bool FUN, int HINT>
+template <bool TD, bool FUN>
 FHD void fsv_phase_b(FusedT& s, const FusedP& p, int kp, const d2 sn[FSV_NF], int tyb, double* own, const double* below,
                      int rb, const double* above, int ra) {
     const int cur = kp & 1, prev = cur ^ 1;
@@ -346,13 +365,8 @@ FHD void fsv_phase_b(FusedT& s, const FusedP& p, int kp, const d2 sn[FSV_NF], in
                 else   { nrx.x = rvx; nry.x = rvy; nrz.x = rvz; nvx.x = ux; nvy.x = uy; nvz.x = uz; }
             }
             if (s.nv == 2) {
-                if (HINT & 1) {       // r_V is never re-read by the sweep; the new V only by the next sweep
-                    st2s(p.r[0] + vc, nrx); st2s(p.r[1] + cv, nry); st2s(p.r[2] + cc, nrz);
-                    st2s(p.Vn[0] + vc, nvx); st2s(p.Vn[1] + cv, nvy); st2s(p.Vn[2] + cc, nvz);
-                } else {
-                    st2(p.r[0] + vc, nrx); st2(p.r[1] + cv, nry); st2(p.r[2] + cc, nrz);
-                    st2(p.Vn[0] + vc, nvx); st2(p.Vn[1] + cv, nvy); st2(p.Vn[2] + cc, nvz);
-                }
+                st2(p.r[0] + vc, nrx); st2(p.r[1] + cv, nry); st2(p.r[2] + cc, nrz);
+                st2(p.Vn[0] + vc, nvx); st2(p.Vn[1] + cv, nvy); st2(p.Vn[2] + cc, nvz);
             } else {
                 p.r[0][vc] = nrx.x; p.r[1][cv] = nry.x; p.r[2][cc] = nrz.x;
                 p.Vn[0][vc] = nvx.x; p.Vn[1][cv] = nvy.x; p.Vn[2][cc] = nvz.x;

@@ -331,7 +331,7 @@ static int run_operator_t(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& b
     const bool vec = op == CHMY_OPER_DIVG || op == CHMY_OPER_VMAG;
     for (int c = 0; c < (vec ? nd : 1); ++c) f.g.a[c] = opr_view<T>(F[nout + c]);
     if (op == CHMY_OPER_DKD || op == CHMY_OPER_DIVG_GRAD || op == CHMY_OPER_KGRAD) f.g.k = opr_view<T>(F[nout + 1]);
-    for (int o = 0; o < nout; ++o) F[o]->frame_synced = false;   // not a ping-pong op: a shadow copy of dst goes stale
+    for (int o = 0; o < nout; ++o) F[o]->frame_dirty(0);   // not a ping-pong op: a shadow copy of dst goes stale
     return launch_box(ctx, f, box, st);
 }
 

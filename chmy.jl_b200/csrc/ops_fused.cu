@@ -3,10 +3,8 @@
 // thread-block cluster whose members read each other's boundary rows through distributed shared memory, so only the
 // first and last row of a cluster recompute stresses for their neighbours.
 #include <cooperative_groups.h>
-#include <cuda.h>        // CUtensorMap (types only: the one driver entry point used is resolved at run time)
 
 #include "fused_sv.cuh"
-#include "fused_tma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -20,7 +18,7 @@ __device__ __forceinline__ void fsv_cluster_arrive_relaxed() {
     asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 }
 
-template <bool TD, bool FUN, int TYB, int HINT>
+template <bool TD, bool FUN, int TYB>
 __global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 4 ? 3 : 2)) k_fused_sv(const FusedP p, const int cl, const int variant) {
     extern __shared__ __align__(16) double xb[];
     const int lane = threadIdx.x, ty = threadIdx.y;
@@ -36,131 +34,25 @@ __global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 4 ? 3 : 2)) k_fused_sv
         if (ty == TYB - 1 && cr < cl - 1) { above = cluster.map_shared_rank(xb, cr + 1); ra = 0; }
     }
     const bool relaxed = (variant & 1) != 0;
+    int bx, cyc, bz;
+    const bool boundary = tile_decode(p.order, (int)blockIdx.x, bx, cyc, bz);     // grid = (clusters, CTAs per cluster, 1)
     FusedT s;
-    fsv_init(s, p, lane, ty, cr * TYB + ty, blockIdx.x, blockIdx.y / cl, blockIdx.z, FUN, HINT);
+    fsv_init(s, p, lane, ty, cr * TYB + ty, bx, cyc, bz, FUN);
     if (cl > 1) fsv_cluster_arrive();
     for (int kp = s.k0 - 1; kp <= s.k1; ++kp) {
         d2 sn[FSV_NF];
-        fsv_phase_a<TD, HINT>(s, p, kp, sn);
+        fsv_phase_a<TD>(s, p, kp, sn);
         // every thread of the cluster has finished reading the buffer that is about to be overwritten, and the
         // stresses of plane kp-1 that phase B reads have been published
         if (cl > 1) fsv_cluster_wait(); else __syncthreads();
-        fsv_phase_b<TD, FUN, HINT>(s, p, kp, sn, TYB, xb, below, rb, above, ra);
+        fsv_phase_b<TD, FUN>(s, p, kp, sn, TYB, xb, below, rb, above, ra);
         if (cl > 1) { if (relaxed) fsv_cluster_arrive_relaxed(); else fsv_cluster_arrive(); }
     }
     if (cl > 1) fsv_cluster_wait();   // no CTA may exit while a neighbour can still read its shared memory
-}
-
-// ---------------------------------------------------------------------------------------------- TMA-fed sweep
-// (design: fused_tma.cuh)  mbarrier / bulk-copy primitives, raw PTX for sm_100a
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
-}
-// global -> shared bulk copy (TMA unit, SASS UBLKCP); completion is reported to the mbarrier as `bytes` transactions
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
-}
-
-// tensor-map flavour of the same row copy: a 64 x 1 x 1 box of a rank-3 tensor map (SASS UTMALDG); out-of-range cells are
-// zero-filled by the TMA unit, and all eleven operands share ONE coordinate triple -- a handful of instructions per row
-struct FtmMaps {
-    CUtensorMap m[FTM_NS];
-};
-__device__ __forceinline__ void tma_row_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* b) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-
-// the elected lane of warp 0 requests the CTA's TYB rows of plane z (tensor coordinate) of all eleven operands into slot `slot`
-template <int TYB>
-__device__ __forceinline__ void ftm_issue(const FtmMaps& maps, double* ring, uint64_t* full, int cx, int cy, int z, int slot) {
-    mbar_expect_tx(full, (uint32_t)(FTM_NS * TYB * 64 * sizeof(double)));
-#pragma unroll
-    for (int op = 0; op < FTM_NS; ++op) tma_row_3d(ring + ftm_ring_off(TYB, slot, op, 0), &maps.m[op], cx, cy, z, full);
-}
-
-template <bool TD, bool FUN, int TYB>
-__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 4 ? 3 : 2)) k_fused_tma(const FusedP p, const int cl, const __grid_constant__ FtmMaps maps) {
-    extern __shared__ __align__(128) double sm[];
-    const int lane = threadIdx.x, ty = threadIdx.y;
-    const int w = __shfl_sync(0xffffffffu, ty, 0);                 // this warp's row, provably warp-uniform
-    double*   ring = sm;
-    double*   xb   = sm + ftm_xch_base(TYB);
-    uint64_t* full  = reinterpret_cast<uint64_t*>(xb + 2 * FSV_NF * TYB * 64);   // [2]: the slot's bytes have landed
-    uint64_t* empty = full + 2;                                                  // [2]: every warp has read the slot
-    int cr = 0;
-    const double *below = xb, *above = xb;
-    int rb = ty, ra = ty;
-    if (ty > 0) rb = ty - 1;
-    if (ty < TYB - 1) ra = ty + 1;
-    if (cl > 1) {
-        cg::cluster_group cluster = cg::this_cluster();
-        cr = (int)cluster.block_rank();
-        if (ty == 0 && cr > 0) { below = cluster.map_shared_rank(xb, cr - 1); rb = TYB - 1; }
-        if (ty == TYB - 1 && cr < cl - 1) { above = cluster.map_shared_rank(xb, cr + 1); ra = 0; }
+    if (boundary && p.done) {         // tell the boundary stream: this CTA's part of the outer cells is in memory
+        __syncthreads();
+        if (lane == 0 && ty == 0) { __threadfence(); atomicAdd(p.done, 1u); }
     }
-    FusedM m;
-    ftm_init(m, p, lane, ty, cr * TYB + ty, blockIdx.x, blockIdx.y / cl, blockIdx.z, FUN);
-    const int nit = m.t.k1 - m.t.k0 + 2;          // planes kp = k0-1 .. k1
-    // tensor coordinates of the CTA's first row segment (the maps start at logical (-2, -1, -1))
-    const int cx = p.lo[0] + (int)blockIdx.x * FSV_XI;
-    const int cy = p.lo[1] + (int)(blockIdx.y / cl) * p.rows_int + cr * TYB;
-    const int cz = p.lo[2] + (int)blockIdx.z * p.cz;               // plane k0 - 1
-    const bool leader = elect_one();
-    const bool feeder = leader && w == 0;
-    if (feeder) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        mbar_init(&empty[0], TYB);
-        mbar_init(&empty[1], TYB);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        ftm_issue<TYB>(maps, ring, &full[0], cx, cy, cz, 0);
-        if (nit > 1) ftm_issue<TYB>(maps, ring, &full[1], cx, cy, cz + 1, 1);
-    }
-    __syncthreads();                               // the barriers exist
-    if (cl > 1) fsv_cluster_arrive();
-    for (int it = 0; it < nit; ++it) {
-        const int kp = m.t.k0 - 1 + it, slot = it & 1;
-        d2 sn[FSV_NF];
-        // plane it+1 goes where plane it-1 was, as soon as every warp of the CTA has read that slot
-        if (feeder && it >= 1 && it + 1 < nit) {
-            mbar_wait(&empty[slot ^ 1], (uint32_t)(((it - 1) >> 1) & 1));
-            ftm_issue<TYB>(maps, ring, &full[slot ^ 1], cx, cy, cz + it + 1, slot ^ 1);
-        }
-        mbar_wait(&full[slot], (uint32_t)((it >> 1) & 1));
-        ftm_phase_a<TD>(m, p, kp, ring, TYB, slot, it + 1 < nit, sn);
-        __syncwarp();                              // every lane of the warp has taken its cells of this slot
-        if (leader) mbar_arrive(&empty[slot]);
-        // every thread of the cluster has finished reading the exchange buffer that is about to be overwritten, and the
-        // stresses of plane kp-1 that phase B reads have been published
-        if (cl > 1) fsv_cluster_wait(); else __syncthreads();
-        fsv_phase_b<TD, FUN, 0>(m.t, p, kp, sn, TYB, xb, below, rb, above, ra);
-        if (cl > 1) fsv_cluster_arrive_relaxed();
-    }
-    if (cl > 1) fsv_cluster_wait();   // no CTA may exit while a neighbour can still read its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------- frame copy
@@ -197,43 +89,45 @@ __global__ void __launch_bounds__(256) k_frame_copy(const FrameBatch b) {
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static int g_fuse_tyb = 4, g_fuse_cl = 4, g_fuse_cz = 64, g_fuse_var = 1;   // measured optimum at 767^3 (profiles/)
-static bool g_fuse_env = false;
 // rows per CTA with an instantiation (profiles/r2_c1_tune_fused_767.log: 2-, 12- and 16-row CTAs and the register-pipelined
-// flavour lost on the B200 and were removed)
+// flavour lost on the B200 and were removed; so did cache-policy hints and a TMA-fed operand ring, profiles/README.md)
 static bool fsv_tyb_ok(int v) { return v == 4 || v == 6 || v == 8; }
 
-static void fuse_env() {
-    if (g_fuse_env) return;
-    g_fuse_env = true;
-    const char* a = getenv("CHMY_FUSE_TYB");
-    const char* b = getenv("CHMY_FUSE_CL");
-    const char* c = getenv("CHMY_FUSE_CZ");
-    const char* d = getenv("CHMY_FUSE_VARIANT");
-    if (d) g_fuse_var = atoi(d);
-    if (a) { const int v = atoi(a); if (fsv_tyb_ok(v)) g_fuse_tyb = v; }
-    if (b) { const int v = atoi(b); if (v >= 1 && v <= 8) g_fuse_cl = v; }
-    if (c) { const int v = atoi(c); if (v >= 1) g_fuse_cz = v; }
+// defaults: measured optimum at 767^3 (profiles/r2_c2_tune_fused_clusters_hints.log); the environment overrides them
+void chmy_tuning_defaults(chmy_tuning* t) {
+    t->fuse_tyb = 6; t->fuse_cl = 4; t->fuse_cz = 64; t->fuse_var = 1;
+    t->f2_cy = 64; t->f2_unroll = 4; t->t3_cz = 16;
+    t->overlap = 1; t->bc_fold = 1;
+    const char* e;
+    if ((e = getenv("CHMY_FUSE_VARIANT"))) t->fuse_var = atoi(e);
+    if ((e = getenv("CHMY_FUSE_TYB")) && fsv_tyb_ok(atoi(e))) t->fuse_tyb = atoi(e);
+    if ((e = getenv("CHMY_FUSE_CL")) && atoi(e) >= 1 && atoi(e) <= 8) t->fuse_cl = atoi(e);
+    if ((e = getenv("CHMY_FUSE_CZ")) && atoi(e) >= 1) t->fuse_cz = atoi(e);
+    if ((e = getenv("CHMY_FUSE2D_CY")) && atoi(e) >= 1) t->f2_cy = atoi(e);
+    if ((e = getenv("CHMY_FUSE2D_UNROLL")) && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) t->f2_unroll = atoi(e);
+    if ((e = getenv("CHMY_FUSE_T3_CZ")) && atoi(e) >= 1) t->t3_cz = atoi(e);
+    if ((e = getenv("CHMY_OVERLAP")) && (e[0] == '0' || e[0] == '1')) t->overlap = e[0] - '0';
+    if ((e = getenv("CHMY_BC_FOLD")) && (e[0] == '0' || e[0] == '1')) t->bc_fold = e[0] - '0';
 }
 
-extern "C" int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_chunk, int variant) {
-    fuse_env();
-    if (variant >= 0) g_fuse_var = variant;
+extern "C" int chmy_set_fused_tuning(chmy_ctx* ctx, int rows_per_cta, int cluster_size, int z_chunk, int variant) {
+    CHMY_REQUIRE(ctx != nullptr, "ctx is NULL");
+    if (variant >= 0) ctx->tun.fuse_var = variant;
     if (rows_per_cta > 0) {
         CHMY_REQUIRE(fsv_tyb_ok(rows_per_cta), "rows_per_cta must be 4, 6 or 8");
-        g_fuse_tyb = rows_per_cta;
+        ctx->tun.fuse_tyb = rows_per_cta;
     }
     if (cluster_size > 0) {
         CHMY_REQUIRE(cluster_size >= 1 && cluster_size <= 8, "cluster_size must be 1..8 (the portable cluster limit)");
-        g_fuse_cl = cluster_size;
+        ctx->tun.fuse_cl = cluster_size;
     }
-    if (z_chunk > 0) g_fuse_cz = z_chunk;
+    if (z_chunk > 0) ctx->tun.fuse_cz = z_chunk;
     return CHMY_OK;
 }
 
-template <bool TD, bool FUN, int TYB, int HINT>
+template <bool TD, bool FUN, int TYB>
 static int launch_fused(const FusedP& p, int cl, int variant, dim3 grid, cudaStream_t st) {
-    void (*kern)(const FusedP, const int, const int) = k_fused_sv<TD, FUN, TYB, HINT>;
+    void (*kern)(const FusedP, const int, const int) = k_fused_sv<TD, FUN, TYB>;
     const size_t smem = fsv_smem_bytes(TYB);
     static bool attr_done[64] = {};   // per instantiation and device (function attributes are per device)
     int dev = 0;
@@ -256,90 +150,12 @@ static int launch_fused(const FusedP& p, int cl, int variant, dim3 grid, cudaStr
     return CHMY_OK;
 }
 
-typedef CUresult (*chmy_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static chmy_encode_tiled_fn encode_tiled() {
-    static chmy_encode_tiled_fn fn = nullptr;
-    if (!fn) {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = (chmy_encode_tiled_fn)f;
-    }
-    return fn;
-}
-
-// rank-3 Float64 map over one buffer of a PITCHED field, origin at logical (-2, -1, -1) (16-byte aligned: logical x = 0 sits
-// on a 128-byte boundary), box = the CTA's tile of one plane: `rows` segments of 64 cells
-static int ftm_make_map(CUtensorMap* map, const chmy_field* f, const double* buf_p0, int rows) {
-    chmy_encode_tiled_fn enc = encode_tiled();
-    CHMY_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
-    void* base = (void*)(buf_p0 - 2 - f->stride[1] - f->stride[2]);
-    const cuuint64_t dims[3]    = {(cuuint64_t)f->stride[1], (cuuint64_t)f->sd[1], (cuuint64_t)f->sd[2]};
-    const cuuint64_t strides[2] = {(cuuint64_t)f->stride[1] * 8, (cuuint64_t)f->stride[2] * 8};
-    const cuuint32_t box[3] = {64, (cuuint32_t)rows, 1}, es[3] = {1, 1, 1};
-    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CHMY_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return CHMY_OK;
-}
-
-template <bool TD, bool FUN, int TYB>
-static int launch_fused_tma(const FusedP& p, const FtmMaps& maps, int cl, dim3 grid, cudaStream_t st) {
-    void (*kern)(const FusedP, const int, const FtmMaps) = k_fused_tma<TD, FUN, TYB>;
-    const size_t smem = ftm_smem_bytes(TYB);
-    static bool attr_done[64] = {};
-    int dev = 0;
-    CHMY_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        if (dev >= 0 && dev < 64) attr_done[dev] = true;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(FSV_LANES, TYB, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = (unsigned)cl; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = cl > 1 ? 1 : 0;
-    CHMY_CUDA(cudaLaunchKernelEx(&cfg, kern, p, cl, maps));
-    return CHMY_OK;
-}
-
-template <bool TD, bool FUN, int TYB>
-static int launch_fused_hint(const FusedP& p, int cl, int variant, dim3 grid, cudaStream_t st) {
-    // cache-policy flavours (variant bits 2..4 -> HINT bits 0..2) exist for the instantiations the headline runs
-    if constexpr (!TD && FUN && (TYB == 4 || TYB == 6)) {
-        switch ((variant >> 2) & 7) {
-        case 1: return launch_fused<TD, FUN, TYB, 1>(p, cl, variant, grid, st);
-        case 2: return launch_fused<TD, FUN, TYB, 2>(p, cl, variant, grid, st);
-        case 3: return launch_fused<TD, FUN, TYB, 3>(p, cl, variant, grid, st);
-        case 6: return launch_fused<TD, FUN, TYB, 6>(p, cl, variant, grid, st);
-        case 7: return launch_fused<TD, FUN, TYB, 7>(p, cl, variant, grid, st);
-        default: break;
-        }
-    }
-    return launch_fused<TD, FUN, TYB, 0>(p, cl, variant, grid, st);
-}
-
 template <bool TD, bool FUN>
-static int launch_fused_tyb(const FusedP& p, const FtmMaps* maps, int tyb, int cl, dim3 grid, cudaStream_t st) {
-    if (maps) {        // the TMA-fed sweep
-        switch (tyb) {
-        case 4: return launch_fused_tma<TD, FUN, 4>(p, *maps, cl, grid, st);
-        case 6: return launch_fused_tma<TD, FUN, 6>(p, *maps, cl, grid, st);
-        default: return launch_fused_tma<TD, FUN, 8>(p, *maps, cl, grid, st);
-        }
-    }
+static int launch_fused_tyb(const FusedP& p, int tyb, int cl, int variant, dim3 grid, cudaStream_t st) {
     switch (tyb) {
-    case 4: return launch_fused_hint<TD, FUN, 4>(p, cl, g_fuse_var, grid, st);
-    case 6: return launch_fused_hint<TD, FUN, 6>(p, cl, g_fuse_var, grid, st);
-    default: return launch_fused_hint<TD, FUN, 8>(p, cl, g_fuse_var, grid, st);
+    case 4: return launch_fused<TD, FUN, 4>(p, cl, variant, grid, st);
+    case 6: return launch_fused<TD, FUN, 6>(p, cl, variant, grid, st);
+    default: return launch_fused<TD, FUN, 8>(p, cl, variant, grid, st);
     }
 }
 
@@ -374,10 +190,34 @@ bool chmy_fused_eligible(const chmy_launch_desc* ds, const chmy_launch_desc* dv)
 }
 
 // One sub-box of the fused op.  cur/shadow pointers are passed explicitly (the caller swaps the fields' buffers).
+// tiles of [lo, lo + n) of width w along one dim: [i0, i1) are those that stay `m_lo` cells away from index 0 and `m_hi`
+// cells away from index `full` (the op's range is [0, full)); everything else is a boundary tile
+static void interior_tiles(int lo, int n, int w, int full, int m_lo, int m_hi, int* g, int* i0, int* i1) {
+    *g = (n + w - 1) / w;
+    int a = 0, b = *g;
+    while (a < *g && lo + a * w < m_lo) ++a;
+    while (b > a && (lo + b * w < lo + n ? lo + b * w : lo + n) > full - m_hi) --b;
+    *i0 = a; *i1 = b;
+}
+
+extern "C" int chmy_selftest_tile_order(const int32_t g[3], const int32_t i0[3], const int32_t i1[3], int32_t tail, int32_t* out /* 4 per tile */) {
+    CHMY_REQUIRE(g && i0 && i1 && out, "NULL argument");
+    TileOrder o;
+    for (int a = 0; a < 3; ++a) { o.g[a] = g[a]; o.i0[a] = i0[a]; o.i1[a] = i1[a]; }
+    o.tail = tail ? 1 : 0;
+    for (int c = 0; c < tile_total(o); ++c) {
+        int bx, by, bz;
+        const bool bnd = tile_decode(o, c, bx, by, bz);
+        out[4 * c] = bx; out[4 * c + 1] = by; out[4 * c + 2] = bz; out[4 * c + 3] = bnd ? 1 : 0;
+    }
+    return CHMY_OK;
+}
+
 int chmy_run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_desc* dv, const Box& box,
-                   double* const* cur /* tau[6] Pr V[3] */, double* const* shadow, cudaStream_t st) {
+                   double* const* cur /* tau[6] Pr V[3] */, double* const* shadow, cudaStream_t st, unsigned int* done,
+                   unsigned int* n_signal) {
+    if (n_signal) *n_signal = 0;
     if (box.n[0] <= 0 || box.n[1] <= 0 || box.n[2] <= 0) return CHMY_OK;
-    fuse_env();
     CHMY_REQUIRE((box.lo[0] & 1) == 0, "fused sweep needs an even x origin");
     chmy_field* const* S = ds->fields;
     chmy_field* const* V = dv->fields;
@@ -411,24 +251,29 @@ int chmy_run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_
     }
     const bool td = chmy_force_true_div() || !markstein_ok(Gdt) || !markstein_ok(s[0]) || !markstein_ok(s[1]);
     // geometry: clusters shrink for short boxes (slabs of a split launch)
-    int tyb = g_fuse_tyb, cl = g_fuse_cl;
+    int tyb = ctx->tun.fuse_tyb, cl = ctx->tun.fuse_cl;
     while (cl > 1 && (cl - 1) * tyb - 2 >= box.n[1]) cl -= 1;
     if (tyb > 4 && cl == 1 && 4 - 2 >= box.n[1]) tyb = 4;
     p.rows_int = cl * tyb - 2;
-    const int nch = (box.n[2] + g_fuse_cz - 1) / g_fuse_cz;
+    const int nch = (box.n[2] + ctx->tun.fuse_cz - 1) / ctx->tun.fuse_cz;
     p.cz = (box.n[2] + nch - 1) / nch;
-    const dim3 grid((unsigned)((box.n[0] + FSV_XI - 1) / FSV_XI), (unsigned)((box.n[1] + p.rows_int - 1) / p.rows_int * cl),
-                    (unsigned)((box.n[2] + p.cz - 1) / p.cz));
-    FtmMaps maps;
-    const FtmMaps* mp = nullptr;
-    if (g_fuse_var & 2) {     // TMA-fed sweep: tensor maps of the eleven ring operands over their CURRENT buffers
-        for (int c = 0; c < 6; ++c) CHMY_TRY(ftm_make_map(&maps.m[c], S[c], cur[c], tyb));
-        for (int c = 0; c < 5; ++c) CHMY_TRY(ftm_make_map(&maps.m[6 + c], S[11 + c], S[11 + c]->p0, tyb));
-        mp = &maps;
+    // boundary tiles: whatever owns a cell the batches / the exchange read or write -- indices 0..2 and n-2..n+1 of a dim
+    // (halo, boundary node, first/last interior cell, send planes).  Without a counter: natural order, nobody signals.
+    const int tw[3] = {FSV_XI, p.rows_int, p.cz};
+    for (int a = 0; a < 3; ++a) {
+        if (done) interior_tiles(box.lo[a], box.n[a], tw[a], p.fhi[a], 3, 4, &p.order.g[a], &p.order.i0[a], &p.order.i1[a]);
+        else { p.order.g[a] = (box.n[a] + tw[a] - 1) / tw[a]; p.order.i0[a] = 0; p.order.i1[a] = p.order.g[a]; }
     }
+    p.order.tail = done ? 1 : 0;
+    p.done = done;
+    const long long total = (long long)p.order.g[0] * p.order.g[1] * p.order.g[2];
+    CHMY_REQUIRE(total < (1ll << 31), "too many tiles for one sweep");
+    if (n_signal) *n_signal = (unsigned int)((tile_total(p.order) - tile_interior(p.order)) * cl);
+    const dim3 grid((unsigned)total, (unsigned)cl, 1);
     int rc;
-    if (rho) rc = td ? launch_fused_tyb<true, false>(p, mp, tyb, cl, grid, st) : launch_fused_tyb<false, false>(p, mp, tyb, cl, grid, st);
-    else     rc = td ? launch_fused_tyb<true, true>(p, mp, tyb, cl, grid, st) : launch_fused_tyb<false, true>(p, mp, tyb, cl, grid, st);
+    const int var = ctx->tun.fuse_var;
+    if (rho) rc = td ? launch_fused_tyb<true, false>(p, tyb, cl, var, grid, st) : launch_fused_tyb<false, false>(p, tyb, cl, var, grid, st);
+    else     rc = td ? launch_fused_tyb<true, true>(p, tyb, cl, var, grid, st) : launch_fused_tyb<false, true>(p, tyb, cl, var, grid, st);
     CHMY_TRY(rc);
     ctx->n_launches++;
     return CHMY_OK;

@@ -123,23 +123,12 @@ int chmy_frame_copy2(chmy_ctx* ctx, const chmy_grid_desc* g, int n, chmy_field* 
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static int g_f2_cy = 64, g_f2_unroll = 4;   // rows per y-chunk, rows per load group (kinds 2 and 3); untuned defaults
-static bool g_f2_env = false;
-static void f2_env() {
-    if (g_f2_env) return;
-    g_f2_env = true;
-    const char* a = getenv("CHMY_FUSE2D_CY");
-    const char* b = getenv("CHMY_FUSE2D_UNROLL");
-    if (a) { const int v = atoi(a); if (v >= 1) g_f2_cy = v; }
-    if (b) { const int v = atoi(b); if (v == 1 || v == 2 || v == 4) g_f2_unroll = v; }
-}
-
-extern "C" int chmy_set_fused2d_tuning(int rows_per_chunk, int unroll) {
-    f2_env();
-    if (rows_per_chunk > 0) g_f2_cy = rows_per_chunk;
+extern "C" int chmy_set_fused2d_tuning(chmy_ctx* ctx, int rows_per_chunk, int unroll) {
+    CHMY_REQUIRE(ctx != nullptr, "ctx is NULL");
+    if (rows_per_chunk > 0) ctx->tun.f2_cy = rows_per_chunk;
     if (unroll > 0) {
         CHMY_REQUIRE(unroll == 1 || unroll == 2 || unroll == 4, "unroll must be 1, 2 or 4");
-        g_f2_unroll = unroll;
+        ctx->tun.f2_unroll = unroll;
     }
     return CHMY_OK;
 }
@@ -225,8 +214,8 @@ int chmy_fused2d_pingpong(int kind, const chmy_launch_desc* dp, const chmy_launc
 }
 
 template <int KIND>
-static int launch_q2(const FusedQ2P& p, int gx, dim3 grid, cudaStream_t st) {
-    switch (g_f2_unroll) {
+static int launch_q2(const FusedQ2P& p, int gx, dim3 grid, int unroll, cudaStream_t st) {
+    switch (unroll) {
     case 1: k_fused_q2<KIND, 1><<<grid, dim3(FSV_LANES, F2_WARPS, 1), 0, st>>>(p, gx); break;
     case 2: k_fused_q2<KIND, 2><<<grid, dim3(FSV_LANES, F2_WARPS, 1), 0, st>>>(p, gx); break;
     default: k_fused_q2<KIND, 4><<<grid, dim3(FSV_LANES, F2_WARPS, 1), 0, st>>>(p, gx); break;
@@ -237,7 +226,6 @@ static int launch_q2(const FusedQ2P& p, int gx, dim3 grid, cudaStream_t st) {
 
 // One sub-box of a fused 2D sweep.  cur / shadow: buffers of the ping-pong fields in chmy_fused2d_pingpong order (the
 // caller has already swapped the fields' storage).
-static int g_t3_cz = 16;      // planes per z-chunk of the 3D thermal sweep (the tuned kernels' measured optimum; untuned here)
 
 static int run_fused_t3(chmy_ctx* ctx, const chmy_launch_desc* dp, const chmy_launch_desc* dc, const Box& box,
                         double* const* cur, double* const* shadow, cudaStream_t st) {
@@ -257,8 +245,7 @@ static int run_fused_t3(chmy_ctx* ctx, const chmy_launch_desc* dp, const chmy_la
     }
     p.lam = dp->scalars[0]; p.dt = dc->scalars[0];
     p.idx = dp->grid.inv_spacing[0]; p.idy = dp->grid.inv_spacing[1]; p.idz = dp->grid.inv_spacing[2];
-    const char* e = getenv("CHMY_FUSE_T3_CZ");
-    int cz = e && atoi(e) >= 1 ? atoi(e) : g_t3_cz;
+    int cz = ctx->tun.t3_cz;      // planes per z-chunk (default: the tuned kernels' measured optimum)
     while ((box.n[2] + cz - 1) / cz > 65535) cz *= 2;
     const int nch = (box.n[2] + cz - 1) / cz;
     p.cz = (box.n[2] + nch - 1) / nch;                          // balanced chunks
@@ -274,13 +261,12 @@ int chmy_run_fused2d(chmy_ctx* ctx, int kind, const chmy_launch_desc* dp, const 
                      double* const* cur, double* const* shadow, cudaStream_t st) {
     if (kind == 4) return run_fused_t3(ctx, dp, dc, box, cur, shadow, st);
     if (box.n[0] <= 0 || box.n[1] <= 0) return CHMY_OK;
-    f2_env();
     CHMY_REQUIRE((box.lo[0] & 1) == 0, "fused sweep needs an even x origin");
     chmy_field* const* P = dp->fields;
     chmy_field* const* Q = dc->fields;
     const double* id = dp->grid.inv_spacing;
     const int gx = (box.n[0] + FSV_XI - 1) / FSV_XI;
-    int cy = g_f2_cy;
+    int cy = ctx->tun.f2_cy;
     while ((box.n[1] + cy - 1) / cy > 65535) cy *= 2;
     const int nch = (box.n[1] + cy - 1) / cy;
     cy = (box.n[1] + nch - 1) / nch;                            // balanced chunks
@@ -337,7 +323,7 @@ int chmy_run_fused2d(chmy_ctx* ctx, int kind, const chmy_launch_desc* dp, const 
         }
         p.idx = id[0]; p.idy = id[1];
         p.cy = cy;
-        if (kind == 2) CHMY_TRY(launch_q2<0>(p, gx, grid, st)); else CHMY_TRY(launch_q2<1>(p, gx, grid, st));
+        if (kind == 2) CHMY_TRY(launch_q2<0>(p, gx, grid, ctx->tun.f2_unroll, st)); else CHMY_TRY(launch_q2<1>(p, gx, grid, ctx->tun.f2_unroll, st));
     }
     ctx->n_launches++;
     return CHMY_OK;

@@ -273,19 +273,27 @@ int chmy_selftest_division(chmy_ctx* ctx, double c, long long n, unsigned long l
 /* -1 keeps a setting.  disable_fast_kernels: run every op with the generic one-thread-per-cell kernels (A/B
  * parity of the tuned kernels); force_true_division: div.rn.f64 everywhere.  Env: CHMY_NO_FAST=1, CHMY_TRUE_DIV=1. */
 int chmy_set_tuning(int disable_fast_kernels, int force_true_division);
-/* -1 keeps.  split_launches: 1 = launches that carry an exchange overlap their inner region with the slabs + batches on
- * the boundary stream (KernelLaunch.jl:160-181); 0 = one full-range kernel, then the batches (outer_width is a hint;
- * results are identical); 2 (default) = self-tuning: the first four such launches of each (op, kernel family, grid) are
- * timed, two in each order, and the faster order is kept.  Env: CHMY_SPLIT=0|1|2. */
-int chmy_set_launch_tuning(int split_launches);
-/* the tuner's state machine on the CPU: ms[i] = the time launch i would report; policies[i] = the order it runs in
- * (1 overlapped, 0 unsplit); *decided = -1 while fewer than four launches were timed */
-int chmy_selftest_split_tuner(const float* ms, int n, int32_t* policies, int32_t* decided);
+/* Launches with boundary batches (KernelLaunch.jl:152-183).  overlap (-1 keeps): 1 (default) = the batches and the halo
+ * exchange overlap the kernel -- the reference's inner region + slabs on two streams for the plain kernels (only when a
+ * side is Connected: without a neighbour six extra launches buy nothing), boundary tiles first + a retire counter for the
+ * fused 3D sweep (one launch; the boundary stream sleeps on the counter, then runs the batches while the interior tiles are
+ * still computing -- again only when a side is Connected; 2 = also without a neighbour, for tests and A/B); 0 = one kernel,
+ * then the batches, on one stream.  outer_width is a hint; results are identical and
+ * the order is deterministic (no run-time tuning: every rank of a topology takes the same one).
+ * bc_fold (-1 keeps): 1 (default) = a batch set without exchange runs as ONE launch for all dimensions, sides and fields
+ * (same bits as the reference's D = N..1 order, batch.jl:20-29); 0 = one launch per dimension.
+ * Env: CHMY_OVERLAP=0|1, CHMY_BC_FOLD=0|1. */
+int chmy_set_launch_tuning(chmy_ctx* ctx, int overlap, int bc_fold);
+int chmy_overlapped_count(const chmy_ctx* ctx, uint64_t* launches);   /* launches whose batches ran behind a still-running sweep */
 /* The split decision of a launch with boundary batches, without launching: *split = 0 -> one full-range kernel followed by
  * the batches; 1 -> inner region [wl, n+2-wr) per dim on the main stream and, for D = N..1, the two slabs of widths
  * wl[D] / wr[D] on the boundary stream (KernelLaunch.jl:63-87 with outer_width replaced by wl / wr).  pref: the slab widths
- * the op's kernel prefers ({60, 6, 0} for the fused 3D sweep) or NULL.  Pure function of the descriptor. */
-int chmy_launch_split_plan(const chmy_launch_desc* desc, const int32_t* pref, int32_t* split, int32_t wl[3], int32_t wr[3]);
+ * the op's kernel prefers ({60, 0, 0} for the 2D sweeps) or NULL; overlap: the context's policy above.  Pure function. */
+int chmy_launch_split_plan(const chmy_launch_desc* desc, const int32_t* pref, int32_t overlap, int32_t* split, int32_t wl[3], int32_t wr[3]);
+/* the launch order of the fused sweep's tiles: out[4*c .. 4*c+3] = (bx, by, bz, is_boundary) of linear cluster index c, for
+ * g[] tiles per dim with interior index ranges [i0, i1); tail = 1: the order of an overlapped launch (every boundary tile
+ * retires before the last stretch of interior tiles), 0: natural order -- a pure function, for the CPU tests */
+int chmy_selftest_tile_order(const int32_t g[3], const int32_t i0[3], const int32_t i1[3], int32_t tail, int32_t* out);
 
 /* ---- lazily fused update_stress! -> update_velocity! (cross-launch fusion) -----------------
  * The reference runs the two kernels of a PT iteration as two `launch` calls (stokes_3d_inc_ve_T.jl:163-165); the
@@ -296,22 +304,22 @@ int chmy_launch_split_plan(const chmy_launch_desc* desc, const int32_t* pref, in
  * The sweep writes tau, Pr and V into shadow buffers that are swapped with the fields' storage afterwards:
  * pointers obtained from chmy_field_get_info are invalidated by a fused launch (PITCHED layout only; DENSE fields
  * and anything the sweep cannot handle fall back to the two kernels).
- * `enable`: 0 = off; 1 = the 3D pair above (measured on B200: profiles/); 3 = additionally the EXPERIMENTAL 2D sweeps
- * (same deferred-launch protocol, same results; bit-exact in the host emulation, not yet run on a GPU):
+ * `enable`: 0 = off; 1 = the 3D pair above; 3 = additionally the flux -> update pairs below (same deferred-launch
+ * protocol, same results; all measured and bit-exact on B200, profiles/r2_c1_*):
  *   update_stress! + update_velocity! 2D            stokes_2d_inc_ve_T.jl:146-147   24 -> 18 array passes
  *   compute_q! + update_C!                          diffusion_2d_perf.jl:28-29       7 ->  4
  *   update_thermal_flux! + update_thermal! 2D       stokes_2d_inc_ve_T.jl:151-152    9 ->  7
  *   update_thermal_flux! + update_thermal! 3D       stokes_3d_inc_ve_T.jl:167-168   12 ->  9                    */
 int chmy_set_fusion(chmy_ctx* ctx, int enable);
 int chmy_fused_count(const chmy_ctx* ctx, uint64_t* sweeps);          /* fused sweeps launched so far            */
-/* rows of a CTA (2|4|6|8|12|16; 6 and 12 are round-2 candidates), CTAs per thread-block cluster along y (1|2|4|8), planes per z-chunk (0 keeps a setting);
- * variant: bit 0 = relaxed cluster-barrier arrive behind a CTA-scope fence instead of the release arrive,
- *          bit 1 = EXPERIMENTAL software-pipelined phase A (2- and 4-row CTAs only) (-1 keeps).
- * Env: CHMY_FUSE_TYB, CHMY_FUSE_CL, CHMY_FUSE_CZ, CHMY_FUSE_VARIANT. */
-int chmy_set_fused_tuning(int rows_per_cta, int cluster_size, int z_chunk, int variant);
+/* Per-context tile geometry of the fused 3D sweep: rows of a CTA (4|6|8), CTAs per thread-block cluster along y (1..8), planes
+ * per z-chunk (0 keeps a setting); variant: bit 0 = relaxed cluster-barrier arrive behind a CTA-scope fence instead of the
+ * release arrive (-1 keeps).  Defaults 6, 4, 64, 1 = the measured optimum at 767^3 (profiles/README.md).
+ * Env (read when the context is created): CHMY_FUSE_TYB, CHMY_FUSE_CL, CHMY_FUSE_CZ, CHMY_FUSE_VARIANT. */
+int chmy_set_fused_tuning(chmy_ctx* ctx, int rows_per_cta, int cluster_size, int z_chunk, int variant);
 /* 2D sweeps: rows per y-chunk of a warp; rows whose operands are requested ahead of the arithmetic (1|2|4, flux pairs)
  * (0 keeps a setting).  Env: CHMY_FUSE2D_CY, CHMY_FUSE2D_UNROLL. */
-int chmy_set_fused2d_tuning(int rows_per_chunk, int unroll);
+int chmy_set_fused2d_tuning(chmy_ctx* ctx, int rows_per_chunk, int unroll);
 
 /* halo slab pack/unpack exposed for bit-exact parity tests of src/Distributed/communication_views.jl:1-34 */
 int chmy_halo_slab_len(const chmy_field* f, int dim, int64_t* len);

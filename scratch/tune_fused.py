@@ -28,7 +28,7 @@ ch.set_fusion(arch, True)
 geoms = [tuple(int(x) for x in g.split(',')) for g in os.environ.get('GEOMS', '8,2,64,0;8,2,64,1').split(';')]
 out = {}
 for g in geoms:
-    ch.set_fused_tuning(*g)
+    ch.set_fused_tuning(arch, *g)
     try:
         ms = timeit()
     except Exception as e:

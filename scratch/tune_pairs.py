@@ -61,7 +61,7 @@ ch.set_fusion(arch, 3)
 if len(n) == 2:
     for cy in (16, 32, 64, 128, 256):
         for un in ((1, 2, 4) if wl != "stokes2d" else (1,)):
-            ch.set_fused2d_tuning(cy, un)
+            ch.set_fused2d_tuning(arch, cy, un)
             try:
                 show(f"fused cy={cy} unroll={un}", timeit())
             except Exception as e:

@@ -134,7 +134,13 @@ class DryRunLib:
     def chmy_set_tuning(self, a, b):
         return 0
 
-    def chmy_set_launch_tuning(self, a):
+    def chmy_set_launch_tuning(self, ctx, overlap, bc_fold):
+        if overlap >= 0:
+            self.ctxs[self._h(ctx)]["overlap"] = int(overlap)
+        return 0
+
+    def chmy_overlapped_count(self, ctx, out):
+        self._set(out, self.ctxs[self._h(ctx)].get("noverl", 0))
         return 0
 
     def chmy_set_exchange_mode(self, ctx, mode):          # transport only: results cannot depend on it
@@ -191,6 +197,9 @@ class DryRunLib:
                 same = P[:nd] == H[2:2 + nd] and P[nd] == H[0] and H[1] != H[0]
             if same:
                 c["nfused"] = c.get("nfused", 0) + 1
+                any_ex = any(d.bc[D][S].kind == 2 for D in range(nd) for S in range(2))
+                if d.op == 5 and nd == 3 and d.has_bc and not (d.flags & 2) and (c.get("overlap", 1) == 2 or (c.get("overlap", 1) and any_ex)):
+                    c["noverl"] = c.get("noverl", 0) + 1      # api.cu run_overlapped: the batches run behind the boundary tiles
         defer = (not d.has_bc) and pitched and (
             ((fuse & 1) and d.op == 4 and nd == 3) or
             ((fuse & 2) and ((nd == 2 and d.op in (4, 1, 6)) or (nd == 3 and d.op == 6))))

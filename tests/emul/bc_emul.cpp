@@ -37,7 +37,38 @@ static int run_slab(const SlabBatch<T>* b, T* buf, int pack) {
 extern "C" int slab_emul_run(const SlabBatch<double>* b, double* buf, int pack) { return run_slab(b, buf, pack); }
 extern "C" int slab_emul_run_f32(const SlabBatch<float>* b, float* buf, int pack) { return run_slab(b, buf, pack); }
 
+// grid of run_bc_all_t (bc.cu): x = ceil(m0 / 128) blocks of 128 threads, y = m1 (largest face extents over the dims),
+// z = (field, dim, side).  `rev`: visit the threads in reverse order -- the result may not depend on the order, because no
+// thread reads a cell another thread writes.
+template <class T>
+static int run_bc_all(const BcAllDev<T>* b, int rev) {
+    int m0 = 1, m1 = 1;
+    for (int D = 0; D < b->nd; ++D) {
+        int e[2] = {1, 1}, t = 0;
+        for (int a = 0; a < b->nd; ++a)
+            if (a != D) e[t++] = b->n[a] + 3;
+        m0 = e[0] > m0 ? e[0] : m0; m1 = e[1] > m1 ? e[1] : m1;
+    }
+    const int nx = (m0 + 127) / 128 * 128, nz = 6 * b->nf;
+    const long long total = (long long)nz * m1 * nx;
+    for (long long i = 0; i < total; ++i) {
+        const long long t = rev ? total - 1 - i : i;
+        const int a = (int)(t % nx), c = (int)((t / nx) % m1), z = (int)(t / ((long long)nx * m1));
+        const int s = z & 1, D = (z >> 1) % 3, q = z / 6;
+        if (D >= b->nd) continue;
+        int nt[2] = {1, 1}, k = 0;
+        for (int d = 0; d < b->nd; ++d)
+            if (d != D) nt[k++] = b->n[d] + 3;
+        if (a >= nt[0] || c >= nt[1]) continue;      // the kernel's own guards
+        bc_all_point(*b, q, D, s, a, c);
+    }
+    return 0;
+}
+extern "C" int bc_all_emul_run(const BcAllDev<double>* b, int rev) { return run_bc_all(b, rev); }
+extern "C" int bc_all_emul_run_f32(const BcAllDev<float>* b, int rev) { return run_bc_all(b, rev); }
+
 extern "C" int bc_emul_sizeof(int what, int f32) {
     if (what == 0) return f32 ? (int)sizeof(BcBatchDev<float>) : (int)sizeof(BcBatchDev<double>);
+    if (what == 2) return f32 ? (int)sizeof(BcAllDev<float>) : (int)sizeof(BcAllDev<double>);
     return f32 ? (int)sizeof(SlabBatch<float>) : (int)sizeof(SlabBatch<double>);
 }

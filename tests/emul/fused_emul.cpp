@@ -8,7 +8,6 @@
 #include <vector>
 
 #include "../../chmy.jl_b200/csrc/fused_sv.cuh"
-#include "../../chmy.jl_b200/csrc/fused_tma.cuh"
 
 template <bool TD, bool FUN>
 static void run(const FusedP& p, int tyb, int cl) {
@@ -29,7 +28,7 @@ static void run(const FusedP& p, int tyb, int cl) {
                             fsv_init(T[(cr * tyb + ty) * FSV_LANES + lane], p, lane, ty, cr * tyb + ty, bx, cyc, bz, FUN);
                 const int k0 = T[0].k0, k1 = T[0].k1;
                 for (int kp = k0 - 1; kp <= k1; ++kp) {
-                    for (int t = 0; t < nthr; ++t) fsv_phase_a<TD, 0>(T[t], p, kp, &SN[(size_t)t * FSV_NF]);
+                    for (int t = 0; t < nthr; ++t) fsv_phase_a<TD>(T[t], p, kp, &SN[(size_t)t * FSV_NF]);
                     // ---- barrier ----
                     for (int cr = 0; cr < cl; ++cr)
                         for (int ty = 0; ty < tyb; ++ty) {
@@ -42,69 +41,7 @@ static void run(const FusedP& p, int tyb, int cl) {
                             else if (cr < cl - 1) { above = &smem[per_cta * (cr + 1)]; ra = 0; }
                             for (int lane = 0; lane < FSV_LANES; ++lane) {
                                 const int t = (cr * tyb + ty) * FSV_LANES + lane;
-                                fsv_phase_b<TD, FUN, 0>(T[t], p, kp, &SN[(size_t)t * FSV_NF], tyb, own, below, rb, above, ra);
-                            }
-                        }
-                }
-            }
-}
-
-// The TMA-fed flavour (fused_tma.cuh, kernel k_fused_tma): same loop structure as the kernel -- ring slots filled two planes
-// ahead by the "producer warp" (here: memcpy of exactly the bytes ftm_row describes; the rest of the ring stays NaN so that a
-// read of bytes no copy delivered shows up), register-fed operands requested one plane ahead.
-template <bool TD, bool FUN>
-static void run_tma(const FusedP& p, int tyb, int cl) {
-    const int nx = p.hi[0] - p.lo[0], ny = p.hi[1] - p.lo[1], nz = p.hi[2] - p.lo[2];
-    const int gx = (nx + FSV_XI - 1) / FSV_XI, gyc = (ny + p.rows_int - 1) / p.rows_int, gz = (nz + p.cz - 1) / p.cz;
-    const int nthr = cl * tyb * FSV_LANES;
-    const size_t per_cta = fsv_smem_bytes(tyb) / sizeof(double);
-    const size_t ring_cta = (size_t)2 * FTM_NS * tyb * 64;
-    std::vector<FusedM> T(nthr);
-    std::vector<d2> SN((size_t)nthr * FSV_NF);
-    std::vector<double> smem(per_cta * cl), ring(ring_cta * cl);
-    const double nan = std::numeric_limits<double>::quiet_NaN();
-    for (int bz = 0; bz < gz; ++bz)
-        for (int cyc = 0; cyc < gyc; ++cyc)
-            for (int bx = 0; bx < gx; ++bx) {
-                for (auto& v : smem) v = nan;
-                for (auto& v : ring) v = nan;
-                for (int cr = 0; cr < cl; ++cr)
-                    for (int ty = 0; ty < tyb; ++ty)
-                        for (int lane = 0; lane < FSV_LANES; ++lane)
-                            ftm_init(T[(cr * tyb + ty) * FSV_LANES + lane], p, lane, ty, cr * tyb + ty, bx, cyc, bz, FUN);
-                const int k0 = T[0].t.k0, k1 = T[0].t.k1, nit = k1 - k0 + 2;
-                // lane 0 of every warp requests its row: the offsets of its state point at plane k0 - 1 + it
-                auto issue = [&](int it, int dz) {
-                    for (int w = 0; w < cl * tyb; ++w) {
-                        const FusedT& s = T[w * FSV_LANES].t;
-                        const int cr = w / tyb;
-                        for (int op = 0; op < FTM_NS; ++op) {
-                            const FtmRow r = ftm_row(p, s, tyb, op, dz, (it + dz) & 1);
-                            if (r.bytes) memcpy(&ring[ring_cta * cr + r.dst], r.src, (size_t)r.bytes);
-                            for (int q = r.bytes / 8; q < 64; ++q) ring[ring_cta * cr + ftm_ring_off(tyb, (it + dz) & 1, op, s.ty) + q] = nan;
-                        }
-                    }
-                };
-                issue(0, 0);
-                if (nit > 1) issue(0, 1);
-                for (int it = 0; it < nit; ++it) {
-                    const int kp = k0 - 1 + it;
-                    for (int t = 0; t < nthr; ++t)
-                        ftm_phase_a<TD>(T[t], p, kp, &ring[ring_cta * (t / (tyb * FSV_LANES))], tyb, it & 1, it + 1 < nit, &SN[(size_t)t * FSV_NF]);
-                    // ---- __syncwarp; refill of this slot (before phase B advances the offsets); cluster barrier ----
-                    if (it + 2 < nit) issue(it, 2);
-                    for (int cr = 0; cr < cl; ++cr)
-                        for (int ty = 0; ty < tyb; ++ty) {
-                            double* own = &smem[per_cta * cr];
-                            const double *below = own, *above = own;
-                            int rb = ty, ra = ty;
-                            if (ty > 0) rb = ty - 1;
-                            else if (cr > 0) { below = &smem[per_cta * (cr - 1)]; rb = tyb - 1; }
-                            if (ty < tyb - 1) ra = ty + 1;
-                            else if (cr < cl - 1) { above = &smem[per_cta * (cr + 1)]; ra = 0; }
-                            for (int lane = 0; lane < FSV_LANES; ++lane) {
-                                const int t = (cr * tyb + ty) * FSV_LANES + lane;
-                                fsv_phase_b<TD, FUN, 0>(T[t].t, p, kp, &SN[(size_t)t * FSV_NF], tyb, own, below, rb, above, ra);
+                                fsv_phase_b<TD, FUN>(T[t], p, kp, &SN[(size_t)t * FSV_NF], tyb, own, below, rb, above, ra);
                             }
                         }
                 }
@@ -115,7 +52,7 @@ static void run_tma(const FusedP& p, int tyb, int cl) {
 // strides: cc.sy cc.sz vc.sy vc.sz cv.sy cv.sz vv.sy vv.sz ; box: lo[3] hi[3] flo[3] fhi[3]
 // sc: idx idy idz eta_ve dtau_Pr dtau_r nudtau Gdt eta ; inc: origin[3] spacing[3] c0[3] r2 in out
 extern "C" int fused_emul_run(double** ptrs, const int* strides, const int* box, const double* sc, const double* inc,
-                              const int* incloc, int cz, int tyb, int cl, int td, int tma) {
+                              const int* incloc, int cz, int tyb, int cl, int td) {
     FusedP p;
     memset(&p, 0, sizeof(p));
     int q = 0;
@@ -143,11 +80,6 @@ extern "C" int fused_emul_run(double** ptrs, const int* strides, const int* box,
     p.cz = cz; p.rows_int = cl * tyb - 2;
     if (p.lo[0] & 1) return -1;
     const bool fun = p.rho == nullptr;
-    if (tma) {
-        if (td) { if (fun) run_tma<true, true>(p, tyb, cl); else run_tma<true, false>(p, tyb, cl); }
-        else    { if (fun) run_tma<false, true>(p, tyb, cl); else run_tma<false, false>(p, tyb, cl); }
-        return 0;
-    }
     if (td) { if (fun) run<true, true>(p, tyb, cl); else run<true, false>(p, tyb, cl); }
     else    { if (fun) run<false, true>(p, tyb, cl); else run<false, false>(p, tyb, cl); }
     return 0;

@@ -27,8 +27,7 @@ def arch(ch):
     a = ch.Arch(ch.B200Backend())
     ch.set_fusion(a, True)
     yield a
-    ch.set_fused_tuning(4, 4, 64, 1)
-    a.close()
+    a.close()                      # the tile geometry is per context: nothing to restore
 
 
 SC = dict(eta=10.0, eta_ve=0.737, G=1.3, dt=0.0171, dPr=0.0213, dr=0.613, nud=0.00931)
@@ -48,7 +47,7 @@ GEOMS = [(8, 4, 64), (4, 1, 3), (8, 1, 5), (6, 4, 64), (4, 8, 7), (6, 3, 4), (8,
 def test_fused_iteration_bit_exact_vs_oracle(ch, arch, oracle, n, geom):
     o = oracle
     tyb, cl, cz = geom
-    ch.set_fused_tuning(tyb, cl, cz, (tyb + cz + n[0]) % 2)
+    ch.set_fused_tuning(arch, tyb, cl, cz, (tyb + cz + n[0]) % 2)
     fun = (sum(n) + tyb) % 2 == 0
     _set_tuning(disable_fast=0, true_div=(cl + cz) % 2)
     rng = np.random.default_rng(7 + cz)
@@ -76,27 +75,30 @@ def test_fused_iteration_bit_exact_vs_oracle(ch, arch, oracle, n, geom):
     _set_tuning(0, 0)
 
 
-EXPERIMENTAL = [(4, 4, 64, 3), (6, 4, 64, 3), (4, 6, 7, 3), (6, 2, 5, 3), (8, 1, 4, 3), (4, 1, 3, 2), (6, 5, 64, 3)]
+DRIVER_GEOMS = [(6, 4, 64, 1), (4, 4, 64, 0), (6, 5, 7, 1), (8, 2, 5, 1), (4, 6, 64, 1), (6, 1, 3, 0)]
 
 
-@pytest.mark.skipif(__import__("os").environ.get("CHMY_EXPERIMENTAL", "0") != "1",
-                    reason="candidates (cache-policy flavours of the loads / stores: variant bits 2..4); set CHMY_EXPERIMENTAL=1")
-@pytest.mark.parametrize("geom", EXPERIMENTAL)
+@pytest.mark.parametrize("geom", DRIVER_GEOMS)
 @pytest.mark.parametrize("n", [(70, 37, 9), (125, 64, 20), (17, 9, 5)])
-def test_experimental_variants_bit_exact_vs_two_kernels(ch, n, geom):
+@pytest.mark.parametrize("overlap", [True, False])
+def test_fused_solver_bit_exact_vs_two_kernels_any_geometry(ch, n, geom, overlap):
+    """the whole driver (batches folded into one launch, boundary tiles first + retire counter when `overlap`) against the two
+    tuned kernels with one launch per dimension on one stream: same bits in every field"""
     from chmy_b200 import drivers as BD
     res = []
     for fused in (True, False):
         a = ch.Arch(ch.B200Backend())
         ch.set_fusion(a, fused)
-        ch.set_fused_tuning(*geom)
-        s = BD.Stokes(a, n, rho_g_function=(n[0] % 2 == 0))
+        ch.set_fused_tuning(a, *geom)
+        ch.set_launch_split(a, "always" if (fused and overlap) else False, bc_fold=fused)
+        s = BD.Stokes(a, n, rho_g_function=(n[0] % 2 == 0), blocking=False)
         rng = np.random.default_rng(1)
         for f in s.fields().values():
             f.from_host(1e-3 * (rng.random(tuple(d + 4 for d in f.dims)) - 0.5), [-1] * 3, [d + 2 for d in f.dims])
         s.run(1, 7, 7, eps=0.0)
+        if fused:
+            assert ch.fused_count(a) == 7 and ch.overlapped_count(a) == (7 if overlap else 0)
         res.append({k: f.parent() for k, f in s.fields().items()})
-        ch.set_fused_tuning(4, 4, 64, 1)
         a.close()
     for k in res[0]:
         assert ((res[0][k] == res[1][k]) | (np.isnan(res[0][k]) & np.isnan(res[1][k]))).all(), k
@@ -145,7 +147,7 @@ def test_fused_solver_equals_two_kernel_solver(ch, oracle, n, ow, exact):
             f.from_host(1e-3 * (rng.random(tuple(d + 4 for d in f.dims)) - 0.5), [-1] * 3, [d + 2 for d in f.dims])
         c0 = ch.fused_count(a)
         hist.append(s.run(2, 30, 10, eps=0.0))
-        assert (ch.fused_count(a) - c0 == 60) if fused else (ch.fused_count(a) == c0)
+        assert (ch.fused_count(a) - c0 == 60 + 30) if fused else (ch.fused_count(a) == c0)   # 60 mechanics + 30 thermal sweeps
         res.append({k: f.parent() for k, f in s.fields().items()})
         a.close()
     assert hist[0] == hist[1]

@@ -1,5 +1,5 @@
 """
-GPU parity of the EXPERIMENTAL 2D fused sweeps (ops_fused2d.cu, chmy_set_fusion(ctx, 3)) through the C ABI:
+GPU parity of the 2D / thermal fused sweeps (ops_fused2d.cu, chmy_set_fusion(ctx, 3)) through the C ABI:
 update_stress! + update_velocity! (2D), compute_q! + update_C!, update_thermal_flux! + update_thermal! (2D).
 
 Whole solver runs (ping-pong over many iterations, boundary batches and residual checks in between, literal split
@@ -7,18 +7,14 @@ launches on two streams) must be bit-identical to the two-kernel path and agree 
 chunk / load-group setting.  The phase functions are proven on the CPU by tests/test_fused_emulation2d.py; this file
 proves the compiled kernels and the host glue.
 
-Gated: these kernels were written after the round's GPU budget was spent and have NOT run on a GPU yet.  Set
-CHMY_EXPERIMENTAL=1 to run them (tools/r2_gpu_checklist.sh does).
+First run on a B200 in round 2 (profiles/r2_c1_gpu_tests.log: all green); part of the enforced suite since.
 """
 import os
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CHMY_EXPERIMENTAL", "0") != "1",
-                                 reason="round-2 candidates (2D fused sweeps): proven by the host emulation, not yet "
-                                        "run on a GPU; set CHMY_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")
@@ -53,13 +49,12 @@ def test_fused_diffusion_equals_two_kernels_and_oracle(ch, oracle, n, ow, exact,
     for mode in (3, 0):
         a = ch.Arch(ch.B200Backend())
         ch.set_fusion(a, mode)
-        ch.set_fused2d_tuning(*tuning)
+        ch.set_fused2d_tuning(a, *tuning)
         s = BD.Diffusion2D(a, n, outer_width=ow, C0=C0, exact_split=exact)
         s.run(9)
         if mode:
             assert ch.fused_count(a) == (0 if _odd(n, ow, exact) else 9), ch.fused_count(a)
         res.append({k: f.parent() for k, f in s.fields().items()})
-        ch.set_fused2d_tuning(64, 4)
         a.close()
     for k in res[0]:
         _same(res[1][k], res[0][k], k)
@@ -79,14 +74,13 @@ def test_fused_stokes2d_with_thermal_equals_two_kernels(ch, oracle, n, fun, ow, 
     for mode in (3, 0):
         a = ch.Arch(ch.B200Backend())
         ch.set_fusion(a, mode)
-        ch.set_fused2d_tuning(*tuning)
+        ch.set_fused2d_tuning(a, *tuning)
         s = BD.Stokes(a, n, rho_g_function=fun, outer_width=ow, exact_split=exact)
         hist.append(s.run(2, 12, 6, eps=0.0))
         if mode:
             # 24 mechanics sweeps + 12 thermal sweeps (it = 2)
             assert ch.fused_count(a) == (0 if _odd(n, ow, exact) else 24 + 12), ch.fused_count(a)
         res.append({k: f.parent() for k, f in s.fields().items()})
-        ch.set_fused2d_tuning(64, 4)
         a.close()
     assert hist[0] == hist[1]
     for k in res[0]:
@@ -118,7 +112,6 @@ def test_deferred_2d_launch_is_flushed_before_it_can_be_observed(ch, oracle):
         ch.synchronize(a)
         assert ch.fused_count(a) == 0
         outs.append((qx, s.C.parent()))
-        ch.set_fused2d_tuning(64, 4)
         a.close()
     _same(outs[1][0], outs[0][0], "q.x")
     _same(outs[1][1], outs[0][1], "C")

@@ -20,6 +20,7 @@ import pytest
 from test_operators_emulation import Pitched
 
 MAXF = 8          # BCK_MAX_FIELDS == CHMY_MAX_BATCH_FIELDS
+ALLF = 6          # BCK_ALL_FIELDS
 DTYPES = [np.float64, np.float32]
 
 
@@ -35,13 +36,22 @@ def _structs(R):
     class BcBatchDev(C.Structure):
         _fields_ = [("n", C.c_int), ("dim", C.c_int), ("nt", C.c_int * 2), ("spacing", R), ("e", BcEntry * (2 * MAXF))]
 
+    class BcRule(C.Structure):
+        _fields_ = [("kind", C.c_int), ("value", R), ("vp", C.c_void_p), ("vsy", C.c_longlong)]
+
+    class BcAllField(C.Structure):
+        _fields_ = [("f", BckView), ("d", C.c_int * 3), ("vertex", C.c_int * 3), ("r", (BcRule * 2) * 3)]
+
+    class BcAllDev(C.Structure):
+        _fields_ = [("nf", C.c_int), ("nd", C.c_int), ("n", C.c_int * 3), ("spacing", R * 3), ("fld", BcAllField * ALLF)]
+
     class SlabEntry(C.Structure):
         _fields_ = [("f", BckView), ("idx", C.c_int), ("e0", C.c_int), ("e1", C.c_int), ("off", C.c_longlong)]
 
     class SlabBatch(C.Structure):
         _fields_ = [("n", C.c_int), ("dim", C.c_int), ("nd", C.c_int), ("e", SlabEntry * MAXF)]
 
-    return BcBatchDev, SlabBatch
+    return BcBatchDev, SlabBatch, BcAllDev
 
 
 S64 = _structs(C.c_double)
@@ -52,8 +62,9 @@ S32 = _structs(C.c_float)
 def emul():
     from helpers import build_emul
     lib = build_emul("bc_emul")
-    for f32, (B, S) in enumerate((S64, S32)):
+    for f32, (B, S, A) in enumerate((S64, S32)):
         assert lib.bc_emul_sizeof(0, f32) == C.sizeof(B) and lib.bc_emul_sizeof(1, f32) == C.sizeof(S)
+        assert lib.bc_emul_sizeof(2, f32) == C.sizeof(A)
     return lib
 
 
@@ -302,3 +313,107 @@ def test_exchange_between_two_ranks_equals_the_reference_rule(oracle, emul, dtyp
             d, ov = A.dims[D], int(loc[D] == o.VERTEX)
             sl = lambda i: tuple(slice(None) if x != D else i + 1 for x in range(3))      # logical i -> storage i+1
             assert np.array_equal(b[sl(0)], A.data[sl(d - ov)]) and np.array_equal(a[sl(d + 1)], Bf.data[sl(1 + ov)])
+
+
+# ---------------------------------------------------------------------------------------------- all dimensions, one launch
+def run_bc_all_both(o, emul, g, field_bcs, rev):
+    """field_bcs: [(oracle field, {dim: (left bc | None, right bc | None)})].  The oracle applies the batch set the
+    reference's way -- D = N..1, side 1 then side 2 (batch.jl:20-29) -- the emulation runs ONE k_bc_all launch
+    (bc_all_point, bc_kernels.cuh) on PITCHED copies; whole padded arrays must agree bit for bit."""
+    f32 = g.dtype == np.float32
+    A = (S32 if f32 else S64)[2]
+    b = A()
+    b.nf, b.nd = len(field_bcs), g.nd
+    for a in range(g.nd):
+        b.n[a], b.spacing[a] = g.n[a], g.spacing[a]
+    keep, pit = [], []
+    for q, (f, per_dim) in enumerate(field_bcs):
+        p = Pitched(f)
+        pit.append((f, p))
+        F = b.fld[q]
+        F.f = view_of(p)
+        for a in range(3):
+            F.d[a] = f.dims[a] if a < g.nd else 1
+            F.vertex[a] = int(a < g.nd and f.loc[a] == o.VERTEX)
+            for s in range(2):
+                F.r[a][s].kind = -1
+        for D, pair in per_dim.items():
+            for s, bc in enumerate(pair):
+                if bc is None:
+                    continue
+                r = F.r[D][s]
+                r.kind = bc.kind
+                v = bc.value
+                if isinstance(v, o.BoundaryFunction):
+                    v = o.boundary_value_field(g, f, bc, D, s)
+                if isinstance(v, o.Field):
+                    pv = Pitched(v)
+                    keep.append(pv)
+                    ov = pv.opr()
+                    r.value, r.vp, r.vsy = 0.0, ov.p, ov.sy
+                else:
+                    r.value, r.vp, r.vsy = (0.0 if v is None else float(v)), None, 0
+    assert (emul.bc_all_emul_run_f32 if f32 else emul.bc_all_emul_run)(C.byref(b), int(rev)) == 0
+    for D in reversed(range(g.nd)):
+        for s in range(2):
+            lst = [(f, per_dim[D][s]) for f, per_dim in field_bcs if D in per_dim and per_dim[D][s] is not None]
+            if lst:
+                o.bc_side(g, D, s, ("field", lst))
+    for f, p in pit:
+        same = same_bits(f.data, p.dense(g.nd))
+        assert same.all(), f"loc {f.loc}: {np.argwhere(~same)[:4]}"
+    for p in keep + [p for _, p in pit]:
+        body = p.flat[p.lead:p.lead + p.pitch * p.sd[1] * p.sd[2]].reshape(p.sd[2], p.sd[1], p.pitch)
+        assert (body[:, :, p.sd[0]:] == 777.25).all() and (p.flat[:p.lead] == 777.25).all()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("origin,extent,n", GRIDS + [((0.0, 0.0, 0.0), (1.0, 1.0, 1.0), (1, 1, 1)), ((0.0, 0.0), (1.0, 2.0), (1, 2))])
+def test_all_dimensions_in_one_launch_equal_the_sequential_order(oracle, emul, origin, extent, n, dtype):
+    """Every combination that makes the D = N..1 order observable: edges and corners where a later dimension reads what an
+    earlier one wrote, Dirichlet nodes of Vertex fields that a later Neumann face copies, missing sides / dimensions,
+    valued conditions whose value is looked up at the MOVED cell's transverse index -- for every staggered location."""
+    o, nd = oracle, len(n)
+    g = o.Grid(origin, extent, n, dtype=dtype)
+    rng = np.random.default_rng(21)
+    kinds = [o.Dirichlet, o.Neumann]
+    for loc in itertools.product((0, 1), repeat=nd):
+        for trial in range(6):
+            per_dim = {}
+            for D in range(nd):
+                if trial == 5 and D == nd - 1 and nd > 1:
+                    continue                                        # a dimension without any condition
+                pair = []
+                for s in range(2):
+                    mk = kinds[(trial + D + s + loc[D]) % 2]
+                    val = [None, 0.0, 1.75, -3.0e-3, 0.5, -1.25][(trial + 2 * D + s) % 6]
+                    pair.append(None if (trial == 4 and s == D % 2) else mk(val))
+                per_dim[D] = tuple(pair)
+            f = rnd_field(o, g, loc, rng)
+            run_bc_all_both(o, emul, g, [(f, per_dim)], rev=trial % 2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_all_dimensions_in_one_launch_solver_batches_and_valued_conditions(oracle, emul, dtype):
+    o = oracle
+    g = o.Grid((-0.5, -0.5, -0.5), (1.0, 1.0, 1.0), (9, 7, 6), dtype=dtype)
+    rng = np.random.default_rng(22)
+    V = o.VectorField(g)
+    for F in V.values():
+        F.data[...] = rng.random(F.sdims) - 0.5
+    T = rnd_field(o, g, 0, rng)
+    # the velocity batch of the Stokes drivers (stokes_3d_inc_ve_T.jl:130-132) + T Neumann (:133) in ONE launch
+    fb = [(F, {D: ((o.Dirichlet() if c == "xyz"[D] else o.Neumann()),) * 2 for D in range(3)}) for c, F in V.items()]
+    fb.append((T, {D: (o.Neumann(), o.Neumann()) for D in range(3)}))
+    for rev in (0, 1):
+        run_bc_all_both(o, emul, g, fb, rev)
+    # Field- and function-valued conditions on every dimension of one field
+    for loc in itertools.product((0, 1), repeat=3):
+        f = rnd_field(o, g, loc, rng)
+        per_dim = {}
+        for D in range(3):
+            tg = o.transverse_grid(g, D)
+            v1 = rnd_field(o, tg, tuple((loc[a] + D) % 2 for a in range(3) if a != D), rng)
+            cont = o.BoundaryFunction(lambda *x: 0.5 + sum((a + 1) * c for a, c in enumerate(x)))
+            per_dim[D] = (o.Dirichlet(v1) if D != 1 else o.Neumann(v1), o.Neumann(cont) if D != 2 else o.Dirichlet(cont))
+        run_bc_all_both(o, emul, g, [(f, per_dim)], rev=sum(loc) % 2)

@@ -92,7 +92,7 @@ for it in range(int(sys.argv[2])):
     assert isinstance(rc, int) and -5 <= rc <= 0, rc
     ok += rc == 0; err += rc != 0
     pref = None if rng.random() < 0.5 else (C.c_int32 * 3)(*[rng.choice(INTS) for _ in range(3)])
-    rc2 = lib.chmy_launch_split_plan(C.byref(d), pref, C.byref(split), wl, wr)
+    rc2 = lib.chmy_launch_split_plan(C.byref(d), pref, rng.randrange(2), C.byref(split), wl, wr)
     assert isinstance(rc2, int) and -5 <= rc2 <= 0, rc2
     if rc2 == 0 and split.value:
         assert all(0 <= w < (1 << 30) for w in list(wl) + list(wr))

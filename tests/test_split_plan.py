@@ -41,11 +41,11 @@ def desc(ch, n, ow, connected, exact=False):
     return d, (T, To, q)
 
 
-def plan(ch, d, pref):
+def plan(ch, d, pref, overlap=1):
     from chmy_b200 import _lib as L
     split, wl, wr = C.c_int32(), (C.c_int32 * 3)(), (C.c_int32 * 3)()
     p = None if pref is None else (C.c_int32 * 3)(*pref)
-    L.check(L.lib().chmy_launch_split_plan(C.byref(d), p, C.byref(split), wl, wr))
+    L.check(L.lib().chmy_launch_split_plan(C.byref(d), p, overlap, C.byref(split), wl, wr))
     return bool(split.value), list(wl), list(wr)
 
 
@@ -76,7 +76,7 @@ def tiles_once(n, regs):
 
 SIZES = [((767, 767, 767), (128, 8, 4)), ((766, 767, 765), (128, 8, 4)), ((8191, 8191), (128, 8)), ((16383, 16383), (128, 8)),
          ((256, 256), (16, 8)), ((30, 22, 14), (4, 3, 3)), ((125, 64, 20), (9, 4, 3)), ((62, 130), (7, 5))]
-PREFS = [None, (60, 6, 0), (64, 0, 0), (60, 0, 0)]       # generic/tuned, fused 3D sweep, 3D thermal sweep, 2D sweeps
+PREFS = [None, (60, 6, 0), (64, 0, 0), (60, 0, 0)]       # generic/tuned, a 60 x 6 tile, 3D thermal sweep, 2D sweeps
 
 
 @pytest.mark.parametrize("n,ow", SIZES)
@@ -118,37 +118,57 @@ def test_when_there_is_no_split(ch):
     assert split_of((30, 22, 14), (17, 8, 4), {(0, 1)}, None) is False   # the two x slabs would overlap
     assert split_of((30, 22, 14), (16, 8, 4), {(0, 1)}, None) is True    # they just touch: an empty inner region
     d, keep = desc(ch, n, ow, {(0, 1)})
-    try:
-        L.check(L.lib().chmy_set_launch_tuning(0))                                     # bench.py --no-split
-        assert plan(ch, d, (60, 6, 0))[0] is False
-        de, keep2 = desc(ch, n, ow, {(0, 1)}, exact=True)
-        assert plan(ch, de, None)[0] is True                                           # a literal split stays literal
-        L.check(L.lib().chmy_set_launch_tuning(1))                                     # always overlapped
-        assert plan(ch, d, (60, 6, 0))[0] is True
-    finally:
-        L.check(L.lib().chmy_set_launch_tuning(2))                                     # the default: self-tuning
-    assert plan(ch, d, (60, 6, 0))[0] is True                                          # the plan when the tuner asks for the overlapped order
+    assert plan(ch, d, (60, 6, 0), overlap=0)[0] is False                # bench.py --split off: one kernel, then the batches
+    de, keep2 = desc(ch, n, ow, {(0, 1)}, exact=True)
+    assert plan(ch, de, None, overlap=0)[0] is True                      # a literal split stays literal
+    assert plan(ch, d, (60, 6, 0), overlap=1)[0] is True                 # the default: overlapped
 
 
-def test_split_tuner_state_machine(ch):
-    """Self-tuning order of exchanging launches: launches 0,1 overlapped, 2,3 unsplit (each launch timed alone on an idle
-    device), then the order whose SECOND launch was faster, for good; ties keep the reference's overlapped order."""
+def test_tiny_grid_whose_nudged_slabs_do_not_fit_runs_unsplit(ch):
+    """n[0]=4, outer_width[0]=3 -> slabs 4 + 3 wide do not fit 6 cells; the plan must not fall back to slabs on
+    odd x origins (the sweeps own aligned pairs of cells) -- it reports one full-range launch instead."""
+    d, keep = desc(ch, (4, 40, 40), (3, 4, 4), {(0, 1)})
+    split, wl, wr = plan(ch, d, None)
+    assert split is False and wl == [0, 0, 0] and wr == [0, 0, 0]
+
+
+def _tiles(ch, g, i0, i1, tail):
     from chmy_b200 import _lib as L
+    n = g[0] * g[1] * g[2]
+    out = (C.c_int32 * (4 * n))()
+    L.check(L.lib().chmy_selftest_tile_order((C.c_int32 * 3)(*g), (C.c_int32 * 3)(*i0), (C.c_int32 * 3)(*i1), tail, out))
+    return [tuple(out[4 * c:4 * c + 4]) for c in range(n)]
 
-    def run(ms):
-        arr = (C.c_float * len(ms))(*ms)
-        pol, dec = (C.c_int32 * len(ms))(), C.c_int32()
-        L.check(L.lib().chmy_selftest_split_tuner(arr, len(ms), pol, C.byref(dec)))
-        return list(pol), dec.value
 
-    pol, dec = run([30.0, 22.4, 25.0, 21.5, 21.5, 21.5, 21.5])      # unsplit wins (first launches of each order are warm-up)
-    assert pol == [1, 1, 0, 0, 0, 0, 0] and dec == 0
-    pol, dec = run([30.0, 21.0, 19.0, 21.5, 99.0, 1.0])             # overlapped wins; later times are never looked at
-    assert pol == [1, 1, 0, 0, 1, 1] and dec == 1
-    pol, dec = run([5.0, 21.0, 5.0, 21.0, 0.0])                     # tie -> the reference's order
-    assert pol == [1, 1, 0, 0, 1] and dec == 1
-    assert run([1.0, 2.0, 3.0]) == ([1, 1, 0], -1)                  # undecided until four launches were timed
-    assert run([]) == ([], -1)
+@pytest.mark.parametrize("g,i0,i1", [((13, 35, 13), (1, 1, 1), (12, 34, 12)), ((13, 35, 13), (0, 0, 0), (13, 35, 13)),
+                                     ((3, 2, 1), (1, 1, 0), (2, 1, 0)), ((5, 4, 6), (2, 0, 1), (3, 4, 6)), ((1, 1, 1), (0, 0, 0), (0, 0, 0)),
+                                     ((7, 9, 4), (1, 2, 1), (7, 8, 3)), ((6, 1, 5), (1, 0, 2), (5, 1, 4)), ((4, 4, 4), (2, 2, 2), (2, 2, 2)),
+                                     ((13, 35, 2), (1, 1, 1), (12, 34, 1)), ((2, 2, 3), (0, 0, 1), (2, 2, 2))])
+def test_tile_order_of_an_overlapped_sweep(ch, g, i0, i1):
+    """the fused sweep's launch order (tile_decode, fused_sv.cuh): every tile exactly once in either order; boundary tiles --
+    those outside the interior index box -- flagged as such (their CTAs feed the retire counter the boundary stream sleeps
+    on: a tile missing from the count would let the batches start early, one too many would hang); and in the overlapped
+    order no boundary tile is launched after the interior of the final layer (that stretch is what hides the exchange)"""
+    allt = sorted(itertools.product(range(g[0]), range(g[1]), range(g[2])))
+    inside = lambda x: all(i0[a] <= x[a] < i1[a] for a in range(3))
+    nat = _tiles(ch, g, i0, i1, 0)
+    assert [x[:3] for x in nat] == [(x, y, z) for z in range(g[2]) for y in range(g[1]) for x in range(g[0])]
+    t = _tiles(ch, g, i0, i1, 1)
+    for order in (nat, t):
+        assert sorted(x[:3] for x in order) == allt
+        assert all(bool(x[3]) == (not inside(x)) for x in order)
+    flags = [x[3] for x in t]
+    if any(flags):
+        last_b = max(i for i, f in enumerate(flags) if f)
+        tail_z = g[2] - 2 if g[2] >= 2 else 0              # the layer that runs last
+        n_tail_int = sum(1 for x in t if not x[3] and x[2] == tail_z)
+        assert last_b == len(t) - n_tail_int - 1, (last_b, len(t), n_tail_int)
+        assert all(x[2] == tail_z for x in t[last_b + 1:])
+    # everything but the final layer keeps the natural order (neighbours in time are neighbours in space)
+    layer = g[0] * g[1]
+    zs = [g[2] - 1] + list(range(g[2] - 1))
+    for ci, z in enumerate(zs[:-1]):
+        assert [x[:3] for x in t[ci * layer:(ci + 1) * layer]] == [(x, y, z) for y in range(g[1]) for x in range(g[0])]
 
 
 # ---------------------------------------------------------------------------------------------- fuzz
