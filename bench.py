@@ -74,6 +74,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the untimed multi-rank correctness check")
+    ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the other BASELINE configs (extra.workloads)")
     ap.add_argument("--split", default="on", choices=["auto", "on", "off"],
                     help="launches with boundary batches -- on (= auto, the default): the batches and the halo exchange overlap "
                          "the kernel (fused 3D sweep: boundary tiles first + a retire counter, one launch; plain kernels: the "
@@ -178,23 +179,41 @@ def a_eff_bytes(workload, n_local):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_arm(workload, n_full, steps, warmup, budget_s=20.0):
-    """The oracle (C restatement, OpenMP, all host threads) on a bounded slab of the same workload."""
+def cpu_arm(workload, n_full, steps, warmup, *, full, budget_s):
+    """The oracle (C restatement of the reference's kernels, OpenMP) on the host's cores: the stand-in for the reference's
+    KernelAbstractions-CPU path, which cannot run here (no Julia).  Built on this host with -O3 -march=native
+    (-ffp-contract=off: same bits), ALL cores even when a launcher exported OMP_NUM_THREADS=1 for its workers.
+    full: the whole grid when host memory allows (the reference arm), else a bounded slab of it (the in-line baseline)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["CHMY_ORACLE_NATIVE"] = "1"
+    os.environ["OMP_NUM_THREADS"] = str(cores)            # read by libgomp when it loads (torchrun sets it to 1)
     # worker threads spin between the (many, short) parallel regions of a step instead of sleeping: on virtualised hosts a
-    # sleeping team can take milliseconds to wake up, which would be charged to the CPU arm (read by libgomp when it loads)
+    # sleeping team can take milliseconds to wake up, which would be charged to the CPU arm
     os.environ.setdefault("OMP_WAIT_POLICY", "active")
+    os.environ.setdefault("OMP_PROC_BIND", "close")
     import numpy as np
     import oracle as o
     import drivers as OD
-    cores = o.num_threads()
+    cores = o.set_num_threads(cores)
+    os.environ.pop("CHMY_ORACLE_NATIVE", None)            # the binding is loaded: leave the environment as it was found
+    nd = len(n_full)
+    nfields = 3 if workload == "diffusion2d" else (25 if nd == 3 else 19)
+    avail = host_mem_available()
+
+    def fits(n):
+        need = nfields * 8.0 * float(math.prod(x + 4 for x in n))
+        return avail is None or 1.4 * need < avail
+
+    n = tuple(n_full)
+    if not full:          # bounded slab: a quarter of the 3D grid along z, 4096 rows of a 2D grid
+        n = tuple(n_full[:-1]) + (min(n_full[-1], 192 if nd == 3 else 4096),)
+    while not fits(n) and n[-1] > 16:
+        n = tuple(n[:-1]) + (n[-1] // 2,)
     if workload == "diffusion2d":
-        n = (n_full[0], min(n_full[1], 2048))
         sol = OD.Diffusion2D(n, outer_width=(128, 8), C0=np.random.default_rng(0).random(n))
         step = sol.step
-        sample = f"{n[0]}x{n[1]} strip of the {n_full[0]}^2 grid"
     else:
-        n = tuple(n_full[:-1]) + (min(n_full[-1], 24 if len(n_full) == 3 else 1024),)
         sol = OD.Stokes(n, re_m=2.5 * math.pi, rho_g_function=True, adv_coef=0.01)
         sol.begin_time_step()
         if workload.endswith("_thermal"):
@@ -203,19 +222,25 @@ def cpu_arm(workload, n_full, steps, warmup, budget_s=20.0):
                 sol.thermal()
         else:
             step = sol.mechanics
-        sample = "x".join(map(str, n)) + " slab of the " + "x".join(map(str, n_full)) + " grid"
-    for _ in range(max(1, min(warmup, 2))):
+    whole = n == tuple(n_full)
+    sample = ("the whole " + "x".join(map(str, n)) + " grid") if whole else \
+        ("x".join(map(str, n)) + " slab of the " + "x".join(map(str, n_full)) + " grid")
+    t0 = time.perf_counter()
+    wdone = 0
+    while wdone < max(1, warmup) and (wdone < 1 or time.perf_counter() - t0 < 0.25 * budget_s):
         step()
+        wdone += 1
     t0 = time.perf_counter()
     done = 0
-    while done < steps and (done < 3 or time.perf_counter() - t0 < budget_s):
+    while done < steps and (done < 2 or time.perf_counter() - t0 < budget_s):
         step()
         done += 1
     dt = (time.perf_counter() - t0) / done
     teff = a_eff_bytes(workload, n) / dt / 1e9
-    return {"value": teff, "unit": "GB/s", "cores": cores, "kind": "port",
-            "sample": f"{sample}; {done} steps, {dt*1e3:.1f} ms/step; oracle/chmy_oracle.c (gcc -O2 -fopenmp), "
-                      "the Julia reference cannot run in this image"}, dt, done, n
+    return {"value": teff, "unit": "GB/s", "cores": cores, "kind": "port", "n_sample": list(n), "same_config": whole,
+            "steps": done, "warmup": wdone,
+            "sample": f"{sample}; {wdone} warm-up + {done} timed steps, {dt*1e3:.1f} ms/step; oracle/chmy_oracle.c built on this host "
+                      f"(gcc -O3 -march=native -fopenmp -ffp-contract=off), {cores} threads; the Julia reference cannot run in this image"}, dt, done, n
 
 
 def run_reference(args):
@@ -223,17 +248,39 @@ def run_reference(args):
     if rank != 0:
         return
     n_full = tuple(args.n) if args.n else WORKLOADS[args.workload][0]
-    cb, dt, done, n = cpu_arm(args.workload, n_full, args.steps, args.warmup, budget_s=60.0)
+    cb, dt, done, n = cpu_arm(args.workload, n_full, args.steps, args.warmup, full=True, budget_s=150.0)
     line = {
         "impl": "reference", "metric": "T_eff", "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": done, "warmup": min(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": done, "warmup": cb["warmup"], "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][2], "sample": cb["sample"], "nIO": WORKLOADS[args.workload][1]},
+        "config": {"workload": WORKLOADS[args.workload][2], "n_local": list(n), "sample": cb["sample"], "nIO": WORKLOADS[args.workload][1],
+                   "note": "one host process with all cores whatever --gpus says: the CPU stand-in does not shard"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ the other BASELINE configs
+def extra_workloads(steps=50, warmup=10):
+    """BASELINE.json configs 2-4 next to the headline (config 5): each in its own process (the headline alone holds ~130 GB of
+    fields), device-timed like the headline, two-kernel and fused.  Returns the condensed lines."""
+    out = []
+    for wl, fusions in (("diffusion2d", (0, 3)), ("stokes2d", (0, 3)), ("stokes2d_thermal", (0, 3)), ("stokes3d_thermal", (1, 3))):
+        for fu in fusions:
+            cmd = [sys.executable, os.path.abspath(__file__), "--workload", wl, "--fused", str(fu), "--steps", str(steps), "--warmup", str(warmup),
+                   "--no-e2e", "--no-cpu-baseline", "--no-extra"]
+            try:
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+                d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+                out.append({"workload": d["config"]["workload"], "n": d["config"]["n_local"], "nIO": d["config"]["nIO"], "fused": fu,
+                            "steps": d["steps"], "warmup": d["warmup"], "ms_per_step": d["ms_per_step"], "T_eff": d["T_eff_per_gpu"],
+                            "frac_of_hbm_peak": d["frac_of_hbm_peak"], "gpu_launches": d["gpu_launches"],
+                            "roofline": {k: d["roofline"][k] for k in ("kernel", "achieved", "frac", "kernel_ms", "step_kernels_ms")}})
+            except Exception as ex:
+                out.append({"workload": wl, "fused": fu, "error": f"{type(ex).__name__}: {ex}"})
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ multi-GPU self-check
@@ -568,7 +615,7 @@ def run_b200(args):
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cb = cpu_arm(wl, n, 8, 1, budget_s=15.0)[0]
+            cb = cpu_arm(wl, n, 8, 2, full=False, budget_s=15.0)[0]
         except Exception as e:      # the CPU arm must never take the GPU number down
             cb = {"value": None, "unit": "GB/s", "cores": None, "kind": "port", "sample": f"failed: {e}"}
 
@@ -585,12 +632,24 @@ def run_b200(args):
             "clocks": clocks, "gpu_launches": int(l1 - l0), "launches_per_step": (l1 - l0) / K, "fused_sweeps": int(nfused), "overlapped_launches": int(noverl), "exchange_msgs": xstats, "roofline": roofline, "e2e": e2e, "cpu_baseline": cb,
             "multi_gpu_check": mgc,
         }
-        print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+    # release the device (the headline alone holds ~130 GB of fields and shadows) before the other configs run in their own processes
+    metric_field = state = sub = step = None
+    for f in sol.fields().values():
+        f.free()
+    del sol
     arch.close()
+    if rank == 0:
+        if world == 1 and wl == "stokes3d" and not args.no_extra and not args.n:
+            import gc
+            gc.collect()
+            line["extra"] = {"workloads": extra_workloads(),
+                             "what": "BASELINE.json configs 2-4 (+ the 2D thermal sub-step), each in its own process: device-timed "
+                                     "T_eff like the headline (10 warm-up + 50 steps), two tuned kernels (fused 0 | 1) vs the fused sweeps (3)"}
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -44,9 +44,10 @@ struct Strides {
 };
 
 
-// fields the tuned kernels can address with aligned 128-bit accesses
+// fields the tuned kernels can address with aligned 128-bit accesses (they are Float64 kernels: Float32 fields take the
+// element-type-generic kernels of ops.cu)
 static inline bool aligned16(const chmy_field* f) {
-    return f->layout == CHMY_LAYOUT_PITCHED && ((uintptr_t)f->p0 % 16 == 0) && (f->stride[1] % 2 == 0) && (f->stride[2] % 2 == 0) &&
+    return f->dtype == CHMY_F64 && f->layout == CHMY_LAYOUT_PITCHED && ((uintptr_t)f->p0 % 16 == 0) && (f->stride[1] % 2 == 0) && (f->stride[2] % 2 == 0) &&
            f->stride[2] * f->sd[2] < (1ll << 40);
 }
 static inline Strides strides_of(const chmy_field* f) { return Strides{(int)f->stride[1], (int)f->stride[2]}; }

@@ -33,34 +33,48 @@ static int launch_box(chmy_ctx* ctx, const F& f, const Box& b, cudaStream_t st) 
     return CHMY_OK;
 }
 
+// Element type.  The reference's kernels are generic in the element type T of their fields (its suite runs Float32 and
+// Float64, test/common.jl:9) but spell their constants as Float64 literals (0.5, 2.0, 3.0, 0.0).  With T = Float32 Julia
+// promotes exactly the sub-expressions that meet such a literal to Float64 and rounds once when the result is stored into
+// the Float32 array.  The functors below reproduce that operation by operation: values of type T are combined in T, `W`
+// (double) marks the promoted sub-expressions, every store converts to T.  For T = double W == T and this is the plain
+// binary64 arithmetic (pinned, for both element types, by tests/test_oracle_transliteration.py).
+typedef double W;
+
+// Julia Base.max / min with a Float64 zero: both arguments promoted (NaN-propagating, max(-0.0, +0.0) = +0.0)
+__device__ __forceinline__ W jl_max0w(W v) { return (v != v) ? v : fmax(v, 0.0); }
+__device__ __forceinline__ W jl_min0w(W v) { return (v != v) ? v : fmin(v, 0.0); }
+
 // ---------------------------------------------------------------------------------------------- diffusion
 // examples/diffusion_2d.jl:8-13   q.x=(V,C) q.y=(C,V) C=(C,C)
+template <class T>
 struct ComputeQ {
-    FV qx, qy, C;
-    double chi, idx, idy;
+    FVT<T> qx, qy, C;
+    T chi, idx, idy;
     __device__ void operator()(int i, int j, int k) const {
-        const double c = fv_ld(C, i, j, k);
-        fv_st(qx, i, j, k, (-chi) * ((c - fv_ld(C, i - 1, j, k)) * idx));
-        fv_st(qy, i, j, k, (-chi) * ((c - fv_ld(C, i, j - 1, k)) * idy));
+        const T c = fv_ld(C, i, j, k);
+        fv_st(qx, i, j, k, (T)((-chi) * ((c - fv_ld(C, i - 1, j, k)) * idx)));
+        fv_st(qy, i, j, k, (T)((-chi) * ((c - fv_ld(C, i, j - 1, k)) * idy)));
     }
 };
 
 // examples/diffusion_2d.jl:15-19   C -= dt * (dx(q.x) + dy(q.y))
+template <class T>
 struct UpdateC {
-    FV C, qx, qy;
-    double dt, idx, idy;
+    FVT<T> C, qx, qy;
+    T dt, idx, idy;
     __device__ void operator()(int i, int j, int k) const {
-        const double dv = (fv_ld(qx, i + 1, j, k) - fv_ld(qx, i, j, k)) * idx +
-                          (fv_ld(qy, i, j + 1, k) - fv_ld(qy, i, j, k)) * idy;
-        fv_st(C, i, j, k, fv_ld(C, i, j, k) - dt * dv);
+        const T dv = (fv_ld(qx, i + 1, j, k) - fv_ld(qx, i, j, k)) * idx +
+                     (fv_ld(qy, i, j + 1, k) - fv_ld(qy, i, j, k)) * idy;
+        fv_st(C, i, j, k, (T)(fv_ld(C, i, j, k) - dt * dv));
     }
 };
 
 // ---------------------------------------------------------------------------------------------- update_old
 // stokes_3d_inc_ve_T.jl:11-21 / stokes_2d_inc_ve_T.jl:11-18 : same index I for every pair
-template <int NP>
+template <class T, int NP>
 struct UpdateOld {
-    FV dst[NP], src[NP];
+    FVT<T> dst[NP], src[NP];
     __device__ void operator()(int i, int j, int k) const {
 #pragma unroll
         for (int p = 0; p < NP; ++p) fv_st(dst[p], i, j, k, fv_ld(src[p], i, j, k));
@@ -68,131 +82,137 @@ struct UpdateOld {
 };
 
 // ---------------------------------------------------------------------------------------------- stress
-__device__ __forceinline__ double stress_res(double t, double to, double e2, double Gdt, double eta) {
-    // r = -(tau - tau_old)/(G*dt) - tau/eta + 2.0*e      (stokes_3d_inc_ve_T.jl:34-39)
-    return ((-(t - to)) / Gdt - t / eta) + e2;
+template <class T>
+__device__ __forceinline__ W stress_res(T t, T to, W e2, T Gdt, T eta) {
+    // r = -(tau - tau_old)/(G*dt) - tau/eta + 2.0*e      (stokes_3d_inc_ve_T.jl:34-39): the first two terms in T, the sum in W
+    return (W)((-(t - to)) / Gdt - t / eta) + e2;
 }
 
 // stokes_2d_inc_ve_T.jl:20-34   tau.xy=(V,V), V.x=(V,C), V.y=(C,V)
+template <class T>
 struct Stress2 {
-    FV txx, tyy, txy, Pr, dV, Vx, Vy, oxx, oyy, oxy;
-    double idx, idy, eta, eta_ve, Gdt, dtau_Pr, dtau_r;
+    FVT<T> txx, tyy, txy, Pr, dV, Vx, Vy, oxx, oyy, oxy;
+    T idx, idy, eta, eta_ve, Gdt, dtau_Pr, dtau_r;
     __device__ void operator()(int i, int j, int k) const {
-        const double vx = fv_ld(Vx, i, j, k), vy = fv_ld(Vy, i, j, k);
-        const double exx = (fv_ld(Vx, i + 1, j, k) - vx) * idx;
-        const double eyy = (fv_ld(Vy, i, j + 1, k) - vy) * idy;
-        const double exy = 0.5 * ((vx - fv_ld(Vx, i, j - 1, k)) * idy + (vy - fv_ld(Vy, i - 1, j, k)) * idx);
-        const double dv  = exx + eyy;
+        const T vx = fv_ld(Vx, i, j, k), vy = fv_ld(Vy, i, j, k);
+        const T exx = (fv_ld(Vx, i + 1, j, k) - vx) * idx;
+        const T eyy = (fv_ld(Vy, i, j + 1, k) - vy) * idy;
+        const W exy = 0.5 * (W)(T)((vx - fv_ld(Vx, i, j - 1, k)) * idy + (vy - fv_ld(Vy, i - 1, j, k)) * idx);
+        const T dv  = exx + eyy;
         fv_st(dV, i, j, k, dv);
-        fv_st(Pr, i, j, k, fv_ld(Pr, i, j, k) - (dv * eta_ve) * dtau_Pr);
-        const double dv3 = dv / 3.0;
-        const double a = fv_ld(txx, i, j, k), b = fv_ld(tyy, i, j, k), c = fv_ld(txy, i, j, k);
-        const double rxx = stress_res(a, fv_ld(oxx, i, j, k), 2.0 * (exx - dv3), Gdt, eta);
-        const double ryy = stress_res(b, fv_ld(oyy, i, j, k), 2.0 * (eyy - dv3), Gdt, eta);
-        const double rxy = stress_res(c, fv_ld(oxy, i, j, k), 2.0 * exy, Gdt, eta);
-        fv_st(txx, i, j, k, a + (rxx * eta_ve) * dtau_r);
-        fv_st(tyy, i, j, k, b + (ryy * eta_ve) * dtau_r);
-        fv_st(txy, i, j, k, c + (rxy * eta_ve) * dtau_r);
+        fv_st(Pr, i, j, k, (T)(fv_ld(Pr, i, j, k) - (dv * eta_ve) * dtau_Pr));
+        const W dv3 = (W)dv / 3.0;
+        const T a = fv_ld(txx, i, j, k), b = fv_ld(tyy, i, j, k), c = fv_ld(txy, i, j, k);
+        const W rxx = stress_res(a, fv_ld(oxx, i, j, k), 2.0 * ((W)exx - dv3), Gdt, eta);
+        const W ryy = stress_res(b, fv_ld(oyy, i, j, k), 2.0 * ((W)eyy - dv3), Gdt, eta);
+        const W rxy = stress_res(c, fv_ld(oxy, i, j, k), 2.0 * exy, Gdt, eta);
+        fv_st(txx, i, j, k, (T)((W)a + (rxx * (W)eta_ve) * (W)dtau_r));
+        fv_st(tyy, i, j, k, (T)((W)b + (ryy * (W)eta_ve) * (W)dtau_r));
+        fv_st(txy, i, j, k, (T)((W)c + (rxy * (W)eta_ve) * (W)dtau_r));
     }
 };
 
 // stokes_3d_inc_ve_T.jl:23-46
+template <class T>
 struct Stress3 {
-    FV t[6], Pr, dV, Vx, Vy, Vz, o[6];   // xx yy zz xy xz yz
-    double idx, idy, idz, eta, eta_ve, Gdt, dtau_Pr, dtau_r;
+    FVT<T> t[6], Pr, dV, Vx, Vy, Vz, o[6];   // xx yy zz xy xz yz
+    T idx, idy, idz, eta, eta_ve, Gdt, dtau_Pr, dtau_r;
     __device__ void operator()(int i, int j, int k) const {
-        const double vx = fv_ld(Vx, i, j, k), vy = fv_ld(Vy, i, j, k), vz = fv_ld(Vz, i, j, k);
-        const double exx = (fv_ld(Vx, i + 1, j, k) - vx) * idx;
-        const double eyy = (fv_ld(Vy, i, j + 1, k) - vy) * idy;
-        const double ezz = (fv_ld(Vz, i, j, k + 1) - vz) * idz;
-        const double exy = 0.5 * ((vx - fv_ld(Vx, i, j - 1, k)) * idy + (vy - fv_ld(Vy, i - 1, j, k)) * idx);
-        const double exz = 0.5 * ((vx - fv_ld(Vx, i, j, k - 1)) * idz + (vz - fv_ld(Vz, i - 1, j, k)) * idx);
-        const double eyz = 0.5 * ((vy - fv_ld(Vy, i, j, k - 1)) * idz + (vz - fv_ld(Vz, i, j - 1, k)) * idy);
-        const double dv  = (exx + eyy) + ezz;
+        const T vx = fv_ld(Vx, i, j, k), vy = fv_ld(Vy, i, j, k), vz = fv_ld(Vz, i, j, k);
+        const T exx = (fv_ld(Vx, i + 1, j, k) - vx) * idx;
+        const T eyy = (fv_ld(Vy, i, j + 1, k) - vy) * idy;
+        const T ezz = (fv_ld(Vz, i, j, k + 1) - vz) * idz;
+        const W exy = 0.5 * (W)(T)((vx - fv_ld(Vx, i, j - 1, k)) * idy + (vy - fv_ld(Vy, i - 1, j, k)) * idx);
+        const W exz = 0.5 * (W)(T)((vx - fv_ld(Vx, i, j, k - 1)) * idz + (vz - fv_ld(Vz, i - 1, j, k)) * idx);
+        const W eyz = 0.5 * (W)(T)((vy - fv_ld(Vy, i, j, k - 1)) * idz + (vz - fv_ld(Vz, i, j - 1, k)) * idy);
+        const T dv  = (exx + eyy) + ezz;
         fv_st(dV, i, j, k, dv);
-        fv_st(Pr, i, j, k, fv_ld(Pr, i, j, k) - (dv * eta_ve) * dtau_Pr);
-        const double dv3 = dv / 3.0;
-        const double e2[6] = {2.0 * (exx - dv3), 2.0 * (eyy - dv3), 2.0 * (ezz - dv3), 2.0 * exy, 2.0 * exz, 2.0 * eyz};
+        fv_st(Pr, i, j, k, (T)(fv_ld(Pr, i, j, k) - (dv * eta_ve) * dtau_Pr));
+        const W dv3 = (W)dv / 3.0;
+        const W e2[6] = {2.0 * ((W)exx - dv3), 2.0 * ((W)eyy - dv3), 2.0 * ((W)ezz - dv3), 2.0 * exy, 2.0 * exz, 2.0 * eyz};
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
-            const double a = fv_ld(t[c], i, j, k);
-            const double r = stress_res(a, fv_ld(o[c], i, j, k), e2[c], Gdt, eta);
-            fv_st(t[c], i, j, k, a + (r * eta_ve) * dtau_r);
+            const T a = fv_ld(t[c], i, j, k);
+            const W r = stress_res(a, fv_ld(o[c], i, j, k), e2[c], Gdt, eta);
+            fv_st(t[c], i, j, k, (T)((W)a + (r * (W)eta_ve) * (W)dtau_r));
         }
     }
 };
 
 // ---------------------------------------------------------------------------------------------- velocity
-// stokes_2d_inc_ve_T.jl:36-43
+// stokes_2d_inc_ve_T.jl:36-43   (no literal: everything in T)
+template <class T>
 struct Velocity2 {
-    FV Vx, Vy, rx, ry, Pr, txx, tyy, txy, rho;
-    InclDev inc;
-    double idx, idy, eta_ve, nudtau;
+    FVT<T> Vx, Vy, rx, ry, Pr, txx, tyy, txy, rho;
+    InclDevT<T> inc;
+    T idx, idy, eta_ve, nudtau;
     __device__ void operator()(int i, int j, int k) const {
-        const double p = fv_ld(Pr, i, j, k), sxy = fv_ld(txy, i, j, k);
-        const double rvx = ((-((p - fv_ld(Pr, i - 1, j, k)) * idx)) + (fv_ld(txx, i, j, k) - fv_ld(txx, i - 1, j, k)) * idx) +
-                           (fv_ld(txy, i, j + 1, k) - sxy) * idy;
-        const double rg  = inc.active ? incl_eval(inc, i, j, k) : fv_ld(rho, i, j, k);
-        const double rvy = (((-((p - fv_ld(Pr, i, j - 1, k)) * idy)) + (fv_ld(tyy, i, j, k) - fv_ld(tyy, i, j - 1, k)) * idy) +
-                            (fv_ld(txy, i + 1, j, k) - sxy) * idx) - rg;
+        const T p = fv_ld(Pr, i, j, k), sxy = fv_ld(txy, i, j, k);
+        const T rvx = ((-((p - fv_ld(Pr, i - 1, j, k)) * idx)) + (fv_ld(txx, i, j, k) - fv_ld(txx, i - 1, j, k)) * idx) +
+                      (fv_ld(txy, i, j + 1, k) - sxy) * idy;
+        const T rg  = inc.active ? incl_eval(inc, i, j, k) : fv_ld(rho, i, j, k);
+        const T rvy = (((-((p - fv_ld(Pr, i, j - 1, k)) * idy)) + (fv_ld(tyy, i, j, k) - fv_ld(tyy, i, j - 1, k)) * idy) +
+                       (fv_ld(txy, i + 1, j, k) - sxy) * idx) - rg;
         fv_st(rx, i, j, k, rvx);
         fv_st(ry, i, j, k, rvy);
-        fv_st(Vx, i, j, k, fv_ld(Vx, i, j, k) + (rvx * nudtau) / eta_ve);
-        fv_st(Vy, i, j, k, fv_ld(Vy, i, j, k) + (rvy * nudtau) / eta_ve);
+        fv_st(Vx, i, j, k, (T)(fv_ld(Vx, i, j, k) + (rvx * nudtau) / eta_ve));
+        fv_st(Vy, i, j, k, (T)(fv_ld(Vy, i, j, k) + (rvy * nudtau) / eta_ve));
     }
 };
 
 // stokes_3d_inc_ve_T.jl:48-57
+template <class T>
 struct Velocity3 {
-    FV Vx, Vy, Vz, rx, ry, rz, Pr, t[6], rho;   // t: xx yy zz xy xz yz
-    InclDev inc;
-    double idx, idy, idz, eta_ve, nudtau;
+    FVT<T> Vx, Vy, Vz, rx, ry, rz, Pr, t[6], rho;   // t: xx yy zz xy xz yz
+    InclDevT<T> inc;
+    T idx, idy, idz, eta_ve, nudtau;
     __device__ void operator()(int i, int j, int k) const {
-        const double p = fv_ld(Pr, i, j, k);
-        const double sxy = fv_ld(t[3], i, j, k), sxz = fv_ld(t[4], i, j, k), syz = fv_ld(t[5], i, j, k);
-        const double rvx = (((-((p - fv_ld(Pr, i - 1, j, k)) * idx)) + (fv_ld(t[0], i, j, k) - fv_ld(t[0], i - 1, j, k)) * idx) +
-                            (fv_ld(t[3], i, j + 1, k) - sxy) * idy) + (fv_ld(t[4], i, j, k + 1) - sxz) * idz;
-        const double rvy = (((-((p - fv_ld(Pr, i, j - 1, k)) * idy)) + (fv_ld(t[1], i, j, k) - fv_ld(t[1], i, j - 1, k)) * idy) +
-                            (fv_ld(t[3], i + 1, j, k) - sxy) * idx) + (fv_ld(t[5], i, j, k + 1) - syz) * idz;
-        const double rg  = inc.active ? incl_eval(inc, i, j, k) : fv_ld(rho, i, j, k);
-        const double rvz = ((((-((p - fv_ld(Pr, i, j, k - 1)) * idz)) + (fv_ld(t[2], i, j, k) - fv_ld(t[2], i, j, k - 1)) * idz) +
-                             (fv_ld(t[4], i + 1, j, k) - sxz) * idx) + (fv_ld(t[5], i, j + 1, k) - syz) * idy) - rg;
+        const T p = fv_ld(Pr, i, j, k);
+        const T sxy = fv_ld(t[3], i, j, k), sxz = fv_ld(t[4], i, j, k), syz = fv_ld(t[5], i, j, k);
+        const T rvx = (((-((p - fv_ld(Pr, i - 1, j, k)) * idx)) + (fv_ld(t[0], i, j, k) - fv_ld(t[0], i - 1, j, k)) * idx) +
+                       (fv_ld(t[3], i, j + 1, k) - sxy) * idy) + (fv_ld(t[4], i, j, k + 1) - sxz) * idz;
+        const T rvy = (((-((p - fv_ld(Pr, i, j - 1, k)) * idy)) + (fv_ld(t[1], i, j, k) - fv_ld(t[1], i, j - 1, k)) * idy) +
+                       (fv_ld(t[3], i + 1, j, k) - sxy) * idx) + (fv_ld(t[5], i, j, k + 1) - syz) * idz;
+        const T rg  = inc.active ? incl_eval(inc, i, j, k) : fv_ld(rho, i, j, k);
+        const T rvz = ((((-((p - fv_ld(Pr, i, j, k - 1)) * idz)) + (fv_ld(t[2], i, j, k) - fv_ld(t[2], i, j, k - 1)) * idz) +
+                        (fv_ld(t[4], i + 1, j, k) - sxz) * idx) + (fv_ld(t[5], i, j + 1, k) - syz) * idy) - rg;
         fv_st(rx, i, j, k, rvx);
         fv_st(ry, i, j, k, rvy);
         fv_st(rz, i, j, k, rvz);
-        fv_st(Vx, i, j, k, fv_ld(Vx, i, j, k) + (rvx * nudtau) / eta_ve);
-        fv_st(Vy, i, j, k, fv_ld(Vy, i, j, k) + (rvy * nudtau) / eta_ve);
-        fv_st(Vz, i, j, k, fv_ld(Vz, i, j, k) + (rvz * nudtau) / eta_ve);
+        fv_st(Vx, i, j, k, (T)(fv_ld(Vx, i, j, k) + (rvx * nudtau) / eta_ve));
+        fv_st(Vy, i, j, k, (T)(fv_ld(Vy, i, j, k) + (rvy * nudtau) / eta_ve));
+        fv_st(Vz, i, j, k, (T)(fv_ld(Vz, i, j, k) + (rvz * nudtau) / eta_ve));
     }
 };
 
 // ---------------------------------------------------------------------------------------------- thermal
-// stokes_3d_inc_ve_T.jl:59-71 (2D: stokes_2d_inc_ve_T.jl:45-54)
-template <int ND>
+// stokes_3d_inc_ve_T.jl:59-71 (2D: stokes_2d_inc_ve_T.jl:45-54):  -lam * d(T) in T; max(V, 0.0) / min(V, 0.0) and their
+// products with left / right(T) in W; one rounding at the store
+template <class T, int ND>
 struct ThermalFlux {
-    FV q[3], T, V[3];
-    double lam, id[3];
+    FVT<T> q[3], Tf, V[3];
+    T lam, id[3];
     __device__ void operator()(int i, int j, int k) const {
-        const double t = fv_ld(T, i, j, k);
-        const double tm[3] = {fv_ld(T, i - 1, j, k), fv_ld(T, i, j - 1, k), ND > 2 ? fv_ld(T, i, j, k - 1) : 0.0};
+        const T t = fv_ld(Tf, i, j, k);
+        const T tm[3] = {fv_ld(Tf, i - 1, j, k), fv_ld(Tf, i, j - 1, k), ND > 2 ? fv_ld(Tf, i, j, k - 1) : (T)0.0};
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
-            const double v = fv_ld(V[d], i, j, k);
-            fv_st(q[d], i, j, k, ((-lam) * ((t - tm[d]) * id[d]) + jl_max0(v) * tm[d]) + jl_min0(v) * t);
+            const W v = (W)fv_ld(V[d], i, j, k);
+            fv_st(q[d], i, j, k, (T)(((W)(T)((-lam) * ((t - tm[d]) * id[d])) + jl_max0w(v) * (W)tm[d]) + jl_min0w(v) * (W)t));
         }
     }
 };
 
 // stokes_3d_inc_ve_T.jl:73-77
-template <int ND>
+template <class T, int ND>
 struct Thermal {
-    FV T, To, q[3];
-    double dt, id[3];
+    FVT<T> Tf, To, q[3];
+    T dt, id[3];
     __device__ void operator()(int i, int j, int k) const {
-        double dv = (fv_ld(q[0], i + 1, j, k) - fv_ld(q[0], i, j, k)) * id[0] +
-                    (fv_ld(q[1], i, j + 1, k) - fv_ld(q[1], i, j, k)) * id[1];
+        T dv = (fv_ld(q[0], i + 1, j, k) - fv_ld(q[0], i, j, k)) * id[0] +
+               (fv_ld(q[1], i, j + 1, k) - fv_ld(q[1], i, j, k)) * id[1];
         if (ND > 2) dv = dv + (fv_ld(q[2], i, j, k + 1) - fv_ld(q[2], i, j, k)) * id[2];
-        fv_st(T, i, j, k, fv_ld(To, i, j, k) - dt * dv);
+        fv_st(Tf, i, j, k, (T)(fv_ld(To, i, j, k) - dt * dv));
     }
 };
 
@@ -207,8 +227,7 @@ static int expect_fields(const chmy_launch_desc* d, int nf, int ns, int allow_nu
         }
         CHMY_REQUIRE(d->fields[i]->nd == d->grid.ndims, "op %d: field %d has %d dims, grid has %d", d->op, i,
                      d->fields[i]->nd, d->grid.ndims);
-        // the example solvers are Float64 programs (their Float64 literals would promote Float32 fields in the reference too)
-        CHMY_REQUIRE(d->fields[i]->dtype == CHMY_F64, "op %d: field %d is not Float64 (the solver ops are Float64-only)", d->op, i);
+        CHMY_REQUIRE(d->fields[i]->dtype == d->fields[0]->dtype, "op %d: field %d has another element type than field 0", d->op, i);
     }
     return CHMY_OK;
 }
@@ -402,107 +421,118 @@ int chmy_validate_op(const chmy_launch_desc* d) {
     }
 }
 
-static InclDev make_incl(const chmy_launch_desc* d) {
-    InclDev q;
+template <class T>
+static InclDevT<T> make_incl(const chmy_launch_desc* d) {
+    InclDevT<T> q;
     memset(&q, 0, sizeof(q));
     q.active = d->rho_g.active;
     q.nd     = d->grid.ndims;
     for (int a = 0; a < 3; ++a) {
         q.loc[a]     = d->rho_g.loc[a];
-        q.origin[a]  = d->grid.origin[a];
-        q.spacing[a] = d->grid.spacing[a];
-        q.c0[a]      = d->rho_g.c0[a];
+        q.origin[a]  = (T)d->grid.origin[a];
+        q.spacing[a] = (T)d->grid.spacing[a];
+        q.c0[a]      = (T)d->rho_g.c0[a];
     }
-    q.r2  = d->rho_g.r * d->rho_g.r;   // r^2 -> r*r (Base.literal_pow)
-    q.in  = d->rho_g.in;
-    q.out = d->rho_g.out;
+    q.r2  = (T)d->rho_g.r * (T)d->rho_g.r;   // r^2 -> r*r (Base.literal_pow), in the element type
+    q.in  = (T)d->rho_g.in;
+    q.out = (T)d->rho_g.out;
     return q;
 }
 
-int chmy_run_op_generic(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st) {
+// scalars and grid numbers cross the ABI as doubles holding values of the element type (a Float32 widens exactly)
+template <class T>
+static int run_op_generic_t(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st) {
     const int nd = d->grid.ndims;
     const int nt = nd == 2 ? 3 : 6;
-    const double* id = d->grid.inv_spacing;
-    const double* s  = d->scalars;
+    T id[3], s[CHMY_MAX_SCALARS];
+    for (int a = 0; a < 3; ++a) id[a] = (T)d->grid.inv_spacing[a];
+    for (int q = 0; q < CHMY_MAX_SCALARS; ++q) s[q] = q < d->nscalars ? (T)d->scalars[q] : (T)0;
     chmy_field* const* F = d->fields;
+    auto V = [](const chmy_field* f) { return f->viewT<T>(); };
     switch (d->op) {
-    case CHMY_OP_OPERATOR: return run_operator(ctx, d, box, st);
     case CHMY_OP_COMPUTE_Q: {
-        ComputeQ f{F[0]->view(), F[1]->view(), F[2]->view(), s[0], id[0], id[1]};
+        ComputeQ<T> f{V(F[0]), V(F[1]), V(F[2]), s[0], id[0], id[1]};
         return launch_box(ctx, f, box, st);
     }
     case CHMY_OP_UPDATE_C: {
-        UpdateC f{F[0]->view(), F[1]->view(), F[2]->view(), s[0], id[0], id[1]};
+        UpdateC<T> f{V(F[0]), V(F[1]), V(F[2]), s[0], id[0], id[1]};
         return launch_box(ctx, f, box, st);
     }
     case CHMY_OP_UPDATE_OLD: {
         if (nd == 2) {
-            UpdateOld<4> f;
-            for (int p = 0; p < 4; ++p) { f.src[p] = F[p]->view(); f.dst[p] = F[4 + p]->view(); }
+            UpdateOld<T, 4> f;
+            for (int p = 0; p < 4; ++p) { f.src[p] = V(F[p]); f.dst[p] = V(F[4 + p]); }
             return launch_box(ctx, f, box, st);
         }
-        UpdateOld<7> f;
-        for (int p = 0; p < 7; ++p) { f.src[p] = F[p]->view(); f.dst[p] = F[7 + p]->view(); }
+        UpdateOld<T, 7> f;
+        for (int p = 0; p < 7; ++p) { f.src[p] = V(F[p]); f.dst[p] = V(F[7 + p]); }
         return launch_box(ctx, f, box, st);
     }
     case CHMY_OP_UPDATE_STRESS: {
-        const double Gdt = s[2] * s[3];   // G*dt evaluated once per cell in the reference; same value
+        const T Gdt = s[2] * s[3];   // G*dt in the element type; evaluated once per cell in the reference, same value
         if (nd == 2) {
-            Stress2 f{F[0]->view(), F[1]->view(), F[2]->view(), F[3]->view(), F[4]->view(), F[5]->view(), F[6]->view(),
-                      F[7]->view(), F[8]->view(), F[9]->view(), id[0], id[1], s[0], s[1], Gdt, s[4], s[5]};
+            Stress2<T> f{V(F[0]), V(F[1]), V(F[2]), V(F[3]), V(F[4]), V(F[5]), V(F[6]),
+                         V(F[7]), V(F[8]), V(F[9]), id[0], id[1], s[0], s[1], Gdt, s[4], s[5]};
             return launch_box(ctx, f, box, st);
         }
-        Stress3 f;
-        for (int c = 0; c < 6; ++c) { f.t[c] = F[c]->view(); f.o[c] = F[11 + c]->view(); }
-        f.Pr = F[6]->view(); f.dV = F[7]->view();
-        f.Vx = F[8]->view(); f.Vy = F[9]->view(); f.Vz = F[10]->view();
+        Stress3<T> f;
+        for (int c = 0; c < 6; ++c) { f.t[c] = V(F[c]); f.o[c] = V(F[11 + c]); }
+        f.Pr = V(F[6]); f.dV = V(F[7]);
+        f.Vx = V(F[8]); f.Vy = V(F[9]); f.Vz = V(F[10]);
         f.idx = id[0]; f.idy = id[1]; f.idz = id[2];
         f.eta = s[0]; f.eta_ve = s[1]; f.Gdt = Gdt; f.dtau_Pr = s[4]; f.dtau_r = s[5];
         return launch_box(ctx, f, box, st);
     }
     case CHMY_OP_UPDATE_VELOCITY: {
         const chmy_field* rho = F[2 * nd + 1 + nt];
-        const FV rv = rho ? rho->view() : FV{nullptr, 0, 0};
+        const FVT<T> rv = rho ? V(rho) : FVT<T>{nullptr, 0, 0};
         if (nd == 2) {
-            Velocity2 f{F[0]->view(), F[1]->view(), F[2]->view(), F[3]->view(), F[4]->view(), F[5]->view(),
-                        F[6]->view(), F[7]->view(), rv, make_incl(d), id[0], id[1], s[0], s[1]};
+            Velocity2<T> f{V(F[0]), V(F[1]), V(F[2]), V(F[3]), V(F[4]), V(F[5]),
+                           V(F[6]), V(F[7]), rv, make_incl<T>(d), id[0], id[1], s[0], s[1]};
             return launch_box(ctx, f, box, st);
         }
-        Velocity3 f;
-        f.Vx = F[0]->view(); f.Vy = F[1]->view(); f.Vz = F[2]->view();
-        f.rx = F[3]->view(); f.ry = F[4]->view(); f.rz = F[5]->view();
-        f.Pr = F[6]->view();
-        for (int c = 0; c < 6; ++c) f.t[c] = F[7 + c]->view();
-        f.rho = rv; f.inc = make_incl(d);
+        Velocity3<T> f;
+        f.Vx = V(F[0]); f.Vy = V(F[1]); f.Vz = V(F[2]);
+        f.rx = V(F[3]); f.ry = V(F[4]); f.rz = V(F[5]);
+        f.Pr = V(F[6]);
+        for (int c = 0; c < 6; ++c) f.t[c] = V(F[7 + c]);
+        f.rho = rv; f.inc = make_incl<T>(d);
         f.idx = id[0]; f.idy = id[1]; f.idz = id[2]; f.eta_ve = s[0]; f.nudtau = s[1];
         return launch_box(ctx, f, box, st);
     }
     case CHMY_OP_UPDATE_THERMAL_FLUX: {
         if (nd == 2) {
-            ThermalFlux<2> f;
-            for (int c = 0; c < 2; ++c) { f.q[c] = F[c]->view(); f.V[c] = F[3 + c]->view(); f.id[c] = id[c]; }
-            f.T = F[2]->view(); f.lam = s[0];
+            ThermalFlux<T, 2> f;
+            for (int c = 0; c < 2; ++c) { f.q[c] = V(F[c]); f.V[c] = V(F[3 + c]); f.id[c] = id[c]; }
+            f.Tf = V(F[2]); f.lam = s[0];
             return launch_box(ctx, f, box, st);
         }
-        ThermalFlux<3> f;
-        for (int c = 0; c < 3; ++c) { f.q[c] = F[c]->view(); f.V[c] = F[4 + c]->view(); f.id[c] = id[c]; }
-        f.T = F[3]->view(); f.lam = s[0];
+        ThermalFlux<T, 3> f;
+        for (int c = 0; c < 3; ++c) { f.q[c] = V(F[c]); f.V[c] = V(F[4 + c]); f.id[c] = id[c]; }
+        f.Tf = V(F[3]); f.lam = s[0];
         return launch_box(ctx, f, box, st);
     }
     case CHMY_OP_UPDATE_THERMAL: {
         if (nd == 2) {
-            Thermal<2> f;
-            f.T = F[0]->view(); f.To = F[1]->view();
-            for (int c = 0; c < 2; ++c) { f.q[c] = F[2 + c]->view(); f.id[c] = id[c]; }
+            Thermal<T, 2> f;
+            f.Tf = V(F[0]); f.To = V(F[1]);
+            for (int c = 0; c < 2; ++c) { f.q[c] = V(F[2 + c]); f.id[c] = id[c]; }
             f.dt = s[0];
             return launch_box(ctx, f, box, st);
         }
-        Thermal<3> f;
-        f.T = F[0]->view(); f.To = F[1]->view();
-        for (int c = 0; c < 3; ++c) { f.q[c] = F[2 + c]->view(); f.id[c] = id[c]; }
+        Thermal<T, 3> f;
+        f.Tf = V(F[0]); f.To = V(F[1]);
+        for (int c = 0; c < 3; ++c) { f.q[c] = V(F[2 + c]); f.id[c] = id[c]; }
         f.dt = s[0];
         return launch_box(ctx, f, box, st);
     }
     default: chmy_set_error("unknown op id %d", d->op); return CHMY_ERR_ARG;
     }
+}
+
+int chmy_run_op_generic(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st) {
+    if (d->op == CHMY_OP_OPERATOR) return run_operator(ctx, d, box, st);
+    const chmy_field* f0 = d->nfields > 0 ? d->fields[0] : nullptr;
+    if (f0 && f0->dtype == CHMY_F32) return run_op_generic_t<float>(ctx, d, box, st);
+    return run_op_generic_t<double>(ctx, d, box, st);
 }

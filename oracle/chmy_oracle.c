@@ -39,6 +39,14 @@ int og_num_threads(void) {
     return 1;
 #endif
 }
+/* a launcher may have exported OMP_NUM_THREADS=1 for its workers (torchrun does): the CPU arm asks for the cores itself */
+void og_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 
 /* ---------------------------------------------------------------- grid ------------------- */
 
@@ -237,6 +245,17 @@ static inline og_real jl_min(og_real a, og_real b) {
     if (a == b) return signbit(a) ? a : b;
     return a < b ? a : b;
 }
+/* the same on promoted operands: max(x::Float32, 0.0) is max(Float64(x), 0.0) in Julia */
+static inline og_wide jl_maxw(og_wide a, og_wide b) {
+    if (isnan(a) || isnan(b)) return NAN;
+    if (a == b) return signbit(a) ? b : a;
+    return a > b ? a : b;
+}
+static inline og_wide jl_minw(og_wide a, og_wide b) {
+    if (isnan(a) || isnan(b)) return NAN;
+    if (a == b) return signbit(a) ? a : b;
+    return a < b ? a : b;
+}
 
 /* ---------------------------------------------------------------- set / reduce ------------ */
 
@@ -328,12 +347,12 @@ void og_update_stress2(const og_grid* g, og_field* const* tau, og_field* Pr, og_
     LOOP3(lo, hi) {
         og_real exx = f_d(g, V[0], 0, i, j, k);
         og_real eyy = f_d(g, V[1], 1, i, j, k);
-        og_real exy = 0.5 * (f_d(g, V[0], 1, i, j, k) + f_d(g, V[1], 0, i, j, k));
+        og_wide exy = 0.5 * (f_d(g, V[0], 1, i, j, k) + f_d(g, V[1], 0, i, j, k));
         og_real dv  = f_d(g, V[0], 0, i, j, k) + f_d(g, V[1], 1, i, j, k);          /* divg(V) */
         AT(divV, i, j, k) = dv;
         AT(Pr, i, j, k) = AT(Pr, i, j, k) - dv * eta_ve * dtau_Pr;
-        const og_real e[3] = {exx - dv / 3.0, eyy - dv / 3.0, exy};
-        og_real r[3];
+        const og_wide e[3] = {exx - dv / 3.0, eyy - dv / 3.0, exy};
+        og_wide r[3];
         for (int c = 0; c < 3; ++c) {
             og_real t = AT(tau[c], i, j, k), to = AT(tau_old[c], i, j, k);
             r[c] = -(t - to) / (G * dt) - t / eta + 2.0 * e[c];
@@ -352,14 +371,14 @@ void og_update_stress3(const og_grid* g, og_field* const* tau, og_field* Pr, og_
         og_real exx = f_d(g, V[0], 0, i, j, k);
         og_real eyy = f_d(g, V[1], 1, i, j, k);
         og_real ezz = f_d(g, V[2], 2, i, j, k);
-        og_real exy = 0.5 * (f_d(g, V[0], 1, i, j, k) + f_d(g, V[1], 0, i, j, k));
-        og_real exz = 0.5 * (f_d(g, V[0], 2, i, j, k) + f_d(g, V[2], 0, i, j, k));
-        og_real eyz = 0.5 * (f_d(g, V[1], 2, i, j, k) + f_d(g, V[2], 1, i, j, k));
+        og_wide exy = 0.5 * (f_d(g, V[0], 1, i, j, k) + f_d(g, V[1], 0, i, j, k));
+        og_wide exz = 0.5 * (f_d(g, V[0], 2, i, j, k) + f_d(g, V[2], 0, i, j, k));
+        og_wide eyz = 0.5 * (f_d(g, V[1], 2, i, j, k) + f_d(g, V[2], 1, i, j, k));
         og_real dv  = f_d(g, V[0], 0, i, j, k) + f_d(g, V[1], 1, i, j, k) + f_d(g, V[2], 2, i, j, k);
         AT(divV, i, j, k) = dv;
         AT(Pr, i, j, k) = AT(Pr, i, j, k) - dv * eta_ve * dtau_Pr;
-        const og_real e[6] = {exx - dv / 3.0, eyy - dv / 3.0, ezz - dv / 3.0, exy, exz, eyz};
-        og_real r[6];
+        const og_wide e[6] = {exx - dv / 3.0, eyy - dv / 3.0, ezz - dv / 3.0, exy, exz, eyz};
+        og_wide r[6];
         for (int c = 0; c < 6; ++c) {
             og_real t = AT(tau[c], i, j, k), to = AT(tau_old[c], i, j, k);
             r[c] = -(t - to) / (G * dt) - t / eta + 2.0 * e[c];
@@ -417,9 +436,9 @@ void og_update_thermal_flux(const og_grid* g, og_field* const* qT, const og_fiel
     for (int d = 0; d < g->nd; ++d) {
         og_field* q = qT[d]; const og_field* v = V[d];
         LOOP3(lo, hi) {
-            og_real vv = AT(v, i, j, k);
-            AT(q, i, j, k) = (-lambda) * f_d(g, T, d, i, j, k) + jl_max(vv, 0.0) * f_left(T, d, i, j, k)
-                             + jl_min(vv, 0.0) * f_right(T, d, i, j, k);
+            const og_wide vv = AT(v, i, j, k);      /* max(V, 0.0): the Float64 literal promotes both arguments */
+            AT(q, i, j, k) = (og_real)((-lambda) * f_d(g, T, d, i, j, k) + jl_maxw(vv, 0.0) * f_left(T, d, i, j, k)
+                                       + jl_minw(vv, 0.0) * f_right(T, d, i, j, k));
         }
     }
 }

@@ -37,6 +37,11 @@ extern "C" {
  * for the Float32 rows of the reference's tests (grids, fields, boundary conditions, operators, halo views).  In the
  * Float32 build every operation is a binary32 operation where the reference's would be; the example-solver ops keep
  * Float64 literals in the reference (2.0, 3.0, 0.5: they would promote), so they are Float64-only here as well. */
+/* Element type of grids and fields.  The example kernels contain Float64 literals (0.5, 2.0, 3.0, 0.0): in a Float32 run
+ * Julia promotes exactly the sub-expressions that meet one of them to Float64 and rounds once when the result is stored
+ * into the Float32 array (stokes_3d_inc_ve_T.jl:27-45,62-70).  og_wide is the type of those sub-expressions; C's usual
+ * arithmetic conversions then reproduce Julia's promotion operation by operation (FLT_EVAL_METHOD == 0). */
+typedef double og_wide;
 #ifdef OG_F32
 typedef float og_real;
 #else
@@ -134,6 +139,7 @@ void og_apply_operator(const og_grid* g, int kind, int dim, og_field* const* dst
                        const og_field* kf, const int64_t* lo, const int64_t* hi);
 
 int og_num_threads(void);
+void og_set_num_threads(int n);
 int og_real_bytes(void);   /* sizeof(og_real): 8 | 4 */
 
 #ifdef __cplusplus

@@ -40,12 +40,28 @@ DIRICHLET, NEUMANN = 0, 1
 AXES = ("x", "y", "z")
 
 
+def _native_path() -> str:
+    """CHMY_ORACLE_NATIVE=1 (bench.py's CPU arm): the Float64 build compiled -O3 -march=native ON THIS HOST, named after
+    the host's CPU (model + flags) so that a copy built on another machine is never loaded."""
+    import hashlib
+    try:
+        info = open("/proc/cpuinfo").read()
+        key = "".join(l for l in info.splitlines()[:30] if l.startswith(("model name", "flags")))
+    except OSError:
+        key = "unknown"
+    return os.path.join(_HERE, f"libchmy_oracle_native_{hashlib.sha1(key.encode()).hexdigest()[:10]}.so")
+
+
 def build(force: bool = False) -> str:
     """Compile chmy_oracle.c with the committed Makefile (gcc, -ffp-contract=off): the Float64 and the Float32 build."""
     src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("chmy_oracle.c", "chmy_oracle.h", "Makefile"))
     for path in (_LIB_PATH, _LIB_PATH_F32):
         if force or not os.path.exists(path) or os.path.getmtime(path) < src_m:
             subprocess.run(["make", "-C", _HERE, "-B", os.path.basename(path)], check=True, capture_output=True)
+    if os.environ.get("CHMY_ORACLE_NATIVE") == "1":
+        path = _native_path()
+        if force or not os.path.exists(path) or os.path.getmtime(path) < src_m:
+            subprocess.run(["make", "-C", _HERE, "-B", "native", "OUT=" + path], check=True, capture_output=True)
     return _LIB_PATH
 
 
@@ -57,6 +73,8 @@ class _Binding:
         assert self.dtype in (np.dtype(np.float64), np.dtype(np.float32))
         R = self.R = C.c_double if self.dtype == np.float64 else C.c_float
         path = _LIB_PATH if self.dtype == np.float64 else _LIB_PATH_F32
+        if self.dtype == np.float64 and os.environ.get("CHMY_ORACLE_NATIVE") == "1":
+            path = _native_path()
 
         class CGrid(C.Structure):
             _fields_ = [("nd", C.c_int32), ("n", C.c_int64 * 3), ("origin", R * 3), ("extent", R * 3),
@@ -116,6 +134,8 @@ class _Binding:
         L.og_dkd.restype = R
         L.og_apply_operator.argtypes = [P(CGrid), C.c_int, C.c_int, FPP, FPP, FP] + box
         L.og_num_threads.restype = C.c_int
+        L.og_set_num_threads.argtypes = [C.c_int]
+        L.og_set_num_threads.restype = None
 
 
 _bindings: Dict[str, _Binding] = {}
@@ -135,6 +155,11 @@ def lib():
 
 def num_threads() -> int:
     return int(lib().og_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    lib().og_set_num_threads(int(n))
+    return num_threads()
 
 
 # ------------------------------------------------------------------------------------------------ grid
@@ -528,50 +553,41 @@ def _names(nd):
     return (("xx", "yy", "xy"), ("x", "y")) if nd == 2 else (("xx", "yy", "zz", "xy", "xz", "yz"), ("x", "y", "z"))
 
 
-# op bodies: (grid, args, lo, hi) -> None.  Argument order follows the reference kernels' signatures.
-def _need_f64(g):
-    """The example solvers are Float64 programs (their Float64 literals would promote Float32 fields): chmy_oracle.h."""
-    if g.dtype != np.float64:
-        raise TypeError("the solver ops of this path are Float64-only (as the reference's example drivers)")
-
-
+# op bodies: (grid, args, lo, hi) -> None.  Argument order follows the reference kernels' signatures.  Every op runs in the
+# element type of its grid (Float64 | Float32, test/common.jl:9): scalars are converted to that type, Float64 literals inside
+# the kernels promote as in Julia (chmy_oracle.h: og_wide).
 def compute_q(g, args, lo, hi):
-    _need_f64(g)
     q, Cf, chi = args
-    lib().og_compute_q(C.byref(g.c), C.byref(q["x"].c), C.byref(q["y"].c), C.byref(Cf.c), chi, *_box(g.nd, lo, hi))
+    g.B.lib.og_compute_q(C.byref(g.c), C.byref(q["x"].c), C.byref(q["y"].c), C.byref(Cf.c), chi, *_box(g.nd, lo, hi))
 
 
 def update_C(g, args, lo, hi):
-    _need_f64(g)
     Cf, q, dt = args
-    lib().og_update_C(C.byref(g.c), C.byref(Cf.c), C.byref(q["x"].c), C.byref(q["y"].c), dt, *_box(g.nd, lo, hi))
+    g.B.lib.og_update_C(C.byref(g.c), C.byref(Cf.c), C.byref(q["x"].c), C.byref(q["y"].c), dt, *_box(g.nd, lo, hi))
 
 
 def update_old(g, args, lo, hi):
-    _need_f64(g)
     T, tau, T_old, tau_old = args
     tn, _ = _names(g.nd)
     dst = [T_old] + [tau_old[c] for c in tn]
     src = [T] + [tau[c] for c in tn]
-    lib().og_update_old(C.byref(g.c), len(dst), _fparr(dst), _fparr(src), *_box(g.nd, lo, hi))
+    g.B.lib.og_update_old(C.byref(g.c), len(dst), _fparr(dst), _fparr(src), *_box(g.nd, lo, hi))
 
 
 def update_stress(g, args, lo, hi):
-    _need_f64(g)
     tau, Pr, divV, V, tau_old, eta, eta_ve, G, dt, dtau_Pr, dtau_r = args
     tn, vn = _names(g.nd)
-    fn = lib().og_update_stress2 if g.nd == 2 else lib().og_update_stress3
+    fn = g.B.lib.og_update_stress2 if g.nd == 2 else g.B.lib.og_update_stress3
     fn(C.byref(g.c), _fparr([tau[c] for c in tn]), C.byref(Pr.c), C.byref(divV.c), _fparr([V[c] for c in vn]),
        _fparr([tau_old[c] for c in tn]), eta, eta_ve, G, dt, dtau_Pr, dtau_r, *_box(g.nd, lo, hi))
 
 
 def update_velocity(g, args, lo, hi):
-    _need_f64(g)
     V, rV, Pr, tau, rhog, eta_ve, nudtau = args
     tn, vn = _names(g.nd)
-    fn = lib().og_update_velocity2 if g.nd == 2 else lib().og_update_velocity3
+    fn = g.B.lib.og_update_velocity2 if g.nd == 2 else g.B.lib.og_update_velocity3
     if isinstance(rhog, Inclusion):
-        inc, fld = rhog.cstruct(), None
+        inc, fld = rhog.cstruct(g.B), None
     else:
         inc, fld = None, rhog
     fn(C.byref(g.c), _fparr([V[c] for c in vn]), _fparr([rV[c] for c in vn]), C.byref(Pr.c),
@@ -580,18 +596,16 @@ def update_velocity(g, args, lo, hi):
 
 
 def update_thermal_flux(g, args, lo, hi):
-    _need_f64(g)
     qT, T, V, lam = args
     _, vn = _names(g.nd)
-    lib().og_update_thermal_flux(C.byref(g.c), _fparr([qT[c] for c in vn]), C.byref(T.c),
+    g.B.lib.og_update_thermal_flux(C.byref(g.c), _fparr([qT[c] for c in vn]), C.byref(T.c),
                                  _fparr([V[c] for c in vn]), lam, *_box(g.nd, lo, hi))
 
 
 def update_thermal(g, args, lo, hi):
-    _need_f64(g)
     T, T_old, qT, dt = args
     _, vn = _names(g.nd)
-    lib().og_update_thermal(C.byref(g.c), C.byref(T.c), C.byref(T_old.c), _fparr([qT[c] for c in vn]), dt,
+    g.B.lib.og_update_thermal(C.byref(g.c), C.byref(T.c), C.byref(T_old.c), _fparr([qT[c] for c in vn]), dt,
                             *_box(g.nd, lo, hi))
 
 

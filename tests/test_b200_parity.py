@@ -30,11 +30,14 @@ def arch(ch):
 LOCS = {0: "Center", 1: "Vertex"}
 
 
-def mk_grids(ch, o, arch, n, origin=None, extent=None):
+def mk_grids(ch, o, arch, n, origin=None, extent=None, dtype=np.float64):
     nd = len(n)
     origin = origin or tuple(-1.0 - 0.1 * d for d in range(nd))
     extent = extent or tuple(2.0 + 0.3 * d for d in range(nd))
-    return o.Grid(origin, extent, n), ch.UniformGrid(arch, origin=origin, extent=extent, dims=n)
+    return o.Grid(origin, extent, n, dtype=dtype), ch.UniformGrid(arch, origin=origin, extent=extent, dims=n, dtype=dtype)
+
+
+DTYPES = [np.float64, np.float32]        # TEST_TYPES of the reference's suite (test/common.jl:9)
 
 
 def bloc(ch, loc):
@@ -236,8 +239,8 @@ def test_halo_pack_unpack_bit_exact(ch, arch, oracle, n, loc):
 
 
 # ------------------------------------------------------------------------------------------------ single ops
-def _stokes_pair(ch, o, arch, n, rng):
-    og, bg = mk_grids(ch, o, arch, n, origin=(-1.0,) * len(n), extent=(2.0,) * len(n))
+def _stokes_pair(ch, o, arch, n, rng, dtype=np.float64):
+    og, bg = mk_grids(ch, o, arch, n, origin=(-1.0,) * len(n), extent=(2.0,) * len(n), dtype=dtype)
     O = dict(tau=o.TensorField(og), tau_old=o.TensorField(og), V=o.VectorField(og), rV=o.VectorField(og),
              qT=o.VectorField(og), Pr=o.Field(og, 0), dV=o.Field(og, 0), T=o.Field(og, 0), To=o.Field(og, 0))
     B = dict(tau=ch.TensorField(arch, bg), tau_old=ch.TensorField(arch, bg), V=ch.VectorField(arch, bg),
@@ -257,13 +260,16 @@ def _stokes_pair(ch, o, arch, n, rng):
     return og, bg, O, B, pairs
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("n", [(30, 22, 14), (17, 9, 5), (65, 33, 4), (126, 126), (37, 258)])
-def test_every_op_bit_exact(ch, arch, oracle, n):
+def test_every_op_bit_exact(ch, arch, oracle, n, dtype):
+    """every solver kernel against the oracle, bit for bit, in both element types: with Float32 fields the Float64 literals
+    of the kernels promote exactly the sub-expressions Julia would promote (ops.cu `W`, chmy_oracle.h og_wide)"""
     o = oracle
     rng = np.random.default_rng(11)
-    og, bg, O, B, pairs = _stokes_pair(ch, o, arch, n, rng)
+    og, bg, O, B, pairs = _stokes_pair(ch, o, arch, n, rng, dtype)
     Lo, Lb = o.Launcher(og), ch.Launcher(arch, bg)
-    sc = dict(eta=10.0, eta_ve=0.737, G=1.3, dt=0.0171, dPr=0.0213, dr=0.613, nud=0.00931, lam=3.3e-4)
+    sc = {k: dtype(v) for k, v in dict(eta=10.0, eta_ve=0.737, G=1.3, dt=0.0171, dPr=0.0213, dr=0.613, nud=0.00931, lam=3.3e-4).items()}
 
     def check(tag):
         for name, a, b in pairs:
@@ -298,20 +304,22 @@ def test_every_op_bit_exact(ch, arch, oracle, n):
     check("update_thermal")
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("n", [(64, 48), (255, 257)])
-def test_diffusion_ops_bit_exact(ch, arch, oracle, n):
+def test_diffusion_ops_bit_exact(ch, arch, oracle, n, dtype):
     o = oracle
     rng = np.random.default_rng(3)
-    og, bg = mk_grids(ch, o, arch, n)
+    og, bg = mk_grids(ch, o, arch, n, dtype=dtype)
     Co, qo = o.Field(og, 0), o.VectorField(og)
     Cb, qb = ch.Field(arch, bg), ch.VectorField(arch, bg)
     for a, b in [(Co, Cb), (qo["x"], qb.x), (qo["y"], qb.y)]:
         fill_pair(rng, a, b)
     Lo, Lb = o.Launcher(og), ch.Launcher(arch, bg)
-    o.launch(Lo, og, o.compute_q, (qo, Co, 1.7))
-    Lb(arch, bg, (ch.compute_q_, (qb, Cb, 1.7, bg)))
-    o.launch(Lo, og, o.update_C, (Co, qo, 1e-3))
-    Lb(arch, bg, (ch.update_C_, (Cb, qb, 1e-3, bg)))
+    chi, dt = dtype(1.7), dtype(1e-3)
+    o.launch(Lo, og, o.compute_q, (qo, Co, chi))
+    Lb(arch, bg, (ch.compute_q_, (qb, Cb, chi, bg)))
+    o.launch(Lo, og, o.update_C, (Co, qo, dt))
+    Lb(arch, bg, (ch.update_C_, (Cb, qb, dt, bg)))
     for nm, a, b in [("C", Co, Cb), ("qx", qo["x"], qb.x), ("qy", qo["y"], qb.y)]:
         assert_same(a, b, nm)
 
@@ -354,6 +362,50 @@ def test_stokes_solver_fields_and_residual_history(ch, arch, oracle, n, fun):
     bf = bsol.fields()
     for k, f in osol.fields().items():
         assert_same(f, bf[k], k, tol=1e-12)
+
+
+# the parity grids BASELINE.md section 3 / SURVEY.md 8(d) name: odd sizes that straddle every tile edge of the tuned and fused
+# kernels (60-cell row segments, 22-row clusters, 64-plane chunks), long/flat/tall aspect ratios, the 2D sizes
+BASELINE_GRIDS = [(63, 63, 63), (127, 127, 127), (191, 129, 67), (255, 257), (1023, 1023)]
+if __import__("os").environ.get("CHMY_DRYRUN") == "1":       # tests/test_gpu_suite_dryrun.py: same code, oracle-over-oracle sizes
+    BASELINE_GRIDS = [(21, 19, 17), (40, 33)]
+
+
+_ORACLE_RUNS = {}
+
+
+@pytest.mark.parametrize("fusion", [3, 0], ids=["fused", "two-kernel"])
+@pytest.mark.parametrize("n", BASELINE_GRIDS, ids=lambda n: "x".join(map(str, n)))
+def test_baseline_parity_grids_fields_and_residual_history(ch, oracle, n, fusion):
+    """SURVEY.md 8(d) parity runs: the Stokes driver (stokes_3d_inc_ve_T.jl / stokes_2d_inc_ve_T.jl) for 2 outer steps x 110 PT
+    iterations (thermal sub-steps in the second), residual check every 22 iterations -- every field's FULL padded array and
+    the whole residual history within 1e-12 relative of the oracle, with the fused sweeps (the bench path: batches folded,
+    frame carry-over elided) and with the two tuned kernels."""
+    import drivers as OD
+    from chmy_b200 import drivers as BD
+    a = ch.Arch(ch.B200Backend())
+    try:
+        ch.set_fusion(a, fusion)
+        if n not in _ORACLE_RUNS:                                 # one oracle run serves both parametrisations
+            osol = OD.Stokes(n, rho_g_function=True)
+            _ORACLE_RUNS.clear()
+            _ORACLE_RUNS[n] = (osol, osol.run(2, 110, 22))
+        osol, ho = _ORACLE_RUNS[n]
+        bsol = BD.Stokes(a, n, rho_g_function=True, blocking=False)
+        hb = bsol.run(2, 110, 22)
+        assert len(ho) == len(hb) == 10
+        for x, y in zip(ho, hb):
+            assert x[:2] == y[:2]
+            for p, q in zip(x[2:], y[2:]):
+                assert abs(p - q) <= 1e-12 * abs(p), (x, y)
+        assert bsol.dt == osol.dt and bsol.eta_ve == osol.eta_ve
+        if fusion:
+            assert ch.fused_count(a) == 220 + 110            # every mechanics pair and every thermal pair ran as a sweep
+        bf = bsol.fields()
+        for k, f in osol.fields().items():
+            assert_same(f, bf[k], k, tol=1e-12)
+    finally:
+        a.close()
 
 
 def test_stokes_split_equals_unsplit(ch, arch):

@@ -357,14 +357,16 @@ def test_f32_grid_operators_bit_exact(ch, arch, oracle, n):
     both(ch, oracle, arch, og, bg, "kgrad", [mk(flip(ctr, d)) for d in range(nd)], mk(ctr), k=mk(locs[-1]))
 
 
-def test_f32_fields_are_refused_by_the_solver_ops(ch, arch):
-    """the example solvers are Float64 programs: a Float32 field in their argument list is an error, not a conversion"""
+def test_one_launch_is_of_one_element_type(ch, arch):
+    """the kernels are generic in the element type (tests/test_b200_parity.py runs every op in both); mixing the two in one
+    launch is an error, not a conversion"""
     g = ch.UniformGrid(arch, origin=(0.0, 0.0), extent=(1.0, 1.0), dims=(8, 6), dtype=F32)
     C, q = ch.Field(arch, g, ch.Center()), ch.VectorField(arch, g)
     assert C.dtype == F32 and q.x.dtype == F32
-    with pytest.raises(ch.ChmyError):
-        ch.Launcher(arch, g)(arch, g, (ch.compute_q_, (q, C, 1.0, g)))
+    ch.Launcher(arch, g)(arch, g, (ch.compute_q_, (q, C, F32(1.0), g)))
     f64 = ch.Field(arch, ch.UniformGrid(arch, origin=(0.0, 0.0), extent=(1.0, 1.0), dims=(8, 6)), ch.Center())
+    with pytest.raises(ch.ChmyError):
+        ch.Launcher(arch, g)(arch, g, (ch.compute_q_, (q, f64, F32(1.0), g)))
     with pytest.raises(ch.ChmyError):
         ch.Launcher(arch, g)(arch, g, (ch.lapl_, (C, f64, g)))           # operators need one element type
 
