@@ -605,6 +605,28 @@ def run_b200(args):
         del views
         sol.launch.blocking = False
 
+    # ---- N > 1: the halo exchange of one iteration on its own (pack -> transport -> unpack, z then y then x), device-timed
+    xchg = None
+    if world > 1 and wl.startswith("stokes"):
+        try:
+            ch.synchronize(arch); ch.barrier(arch)
+            for _ in range(3):
+                ch.exchange_halo_(arch, sol.grid, *sol.V, blocking=False)
+            ch.synchronize(arch); ch.barrier(arch)
+            ch.event_record(arch, 2)
+            for _ in range(20):
+                ch.exchange_halo_(arch, sol.grid, *sol.V, blocking=False)
+            ch.event_record(arch, 3)
+            ch.synchronize(arch)
+            (xms,) = ch.allreduce_max(arch, ch.event_elapsed_ms(arch, 2, 3) / 20)
+            face = [8.0 * sum(int(np.prod([f.dims[a] + 4 for a in range(len(n)) if a != D])) for f in sol.V) for D in range(len(n))]
+            xchg = {"ms_per_exchange_alone": xms, "connected_dims": [D + 1 for D in range(len(n)) if pdims[D] > 1],
+                    "bytes_per_side_per_dim": face,
+                    "what": "exchange_halo!(arch, grid, V...) alone on an idle device, max over ranks: what one iteration's exchange "
+                            "costs when nothing hides it (the timed loop overlaps it with the sweep unless --split off)"}
+        except Exception as ex:
+            xchg = {"error": f"{type(ex).__name__}: {ex}"}
+
     mgc = None
     if world > 1 and not args.no_check:
         try:
@@ -630,7 +652,7 @@ def run_b200(args):
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "T_eff_per_gpu": teff_gpu, "frac_of_hbm_peak": teff_gpu / peak, "hbm_peak": peak, "hbm_peak_source": peak_src,
             "clocks": clocks, "gpu_launches": int(l1 - l0), "launches_per_step": (l1 - l0) / K, "fused_sweeps": int(nfused), "overlapped_launches": int(noverl), "exchange_msgs": xstats, "roofline": roofline, "e2e": e2e, "cpu_baseline": cb,
-            "multi_gpu_check": mgc,
+            "multi_gpu_check": mgc, "exchange_alone": xchg,
         }
     if world > 1:
         import torch.distributed as dist

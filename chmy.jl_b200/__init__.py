@@ -13,7 +13,7 @@ from .architectures import (Architecture, SingleDeviceArchitecture, DistributedA
 from .grids import (Location, Center, Vertex, flip, Bounded, Connected, UniformAxis, StructuredGrid, UniformGrid,
                     connectivity, spacing, inv_spacing, coord, coords, centers, vertices, origin, extent, bounds,
                     axes_names, expand_loc, nvertices, ncenters, axis, vertex, center, direction, volume, inv_volume)
-from .fields import (AbstractField, ConstantField, ZeroField, OneField, ValueField, Field, FieldTuple, VectorField, TensorField, FunctionField, init_incl, set_,
+from .fields import (AbstractField, ConstantField, ZeroField, OneField, ValueField, Field, FieldTuple, VectorField, TensorField, FunctionField, init_incl, init_gauss, set_,
                      interior, parent, fill_parent_, halo, location, maxabs, maxabs_many, vector_location, pinned_array)
 from .boundary_conditions import (BoundaryFunction, FirstOrderBC, Dirichlet, Neumann, EmptyBatch, FieldBatch, ExchangeBatch, batch, bc_)
 from .kernel_launch import (Launcher, worksize, outer_width, inner_worksize, inner_offset, outer_worksize,

@@ -101,6 +101,7 @@ SYMBOLS = {
     "chmy_field_copy_to_host": (C.c_int, [_vp, _vp, _vp, _i64p, _i64p]),
     "chmy_field_copy": (C.c_int, [_vp, _vp, _vp, _i64p, _i64p]),
     "chmy_field_set_inclusion": (C.c_int, [_vp, _vp, _P(GridDesc), _P(Inclusion)]),
+    "chmy_field_set_gaussian": (C.c_int, [_vp, _vp, _P(GridDesc)]),
     "chmy_field_maxabs": (C.c_int, [_vp, _vp, _i64p, _i64p, _dp]),
     "chmy_field_maxabs_many": (C.c_int, [_vp, C.c_int, _P(_vp), _i64p, _i64p, _dp]),
     "chmy_host_alloc": (C.c_int, [_vp, C.c_size_t, _P(_vp)]),

@@ -23,11 +23,14 @@ class BoundaryFunction:
     `loc` is ONE location (the field's location along the boundary dimension, batch.jl:174) applied to every axis,
     exactly as `coord(grid, loc::Location, I...)` does (structured_grid.jl:103-106).  `dim` is 1-based.
     A closure cannot cross the C ABI: `batch`/`bc!` evaluate it on the host into an (N-1)-dimensional device Field
-    (value_field of chmy_batch_desc)."""
+    (value_field of chmy_batch_desc).  The reference evaluates the function inside every bc! kernel, so a closure over
+    mutable or time-dependent state is re-evaluated here on every `batch` / `bc!` too (only the device buffer is re-used);
+    `static=True` declares the function pure and lets the evaluated values be kept."""
 
-    def __init__(self, fun, *, discrete: bool = False, parameters=None, reduce_dims: bool = True):
+    def __init__(self, fun, *, discrete: bool = False, parameters=None, reduce_dims: bool = True, static: bool = False):
         self.fun, self.discrete, self.parameters, self.reduce_dims = fun, bool(discrete), parameters, bool(reduce_dims)
-        self._cache = {}
+        self.static = bool(static)
+        self._cache = {}          # key -> (weakref to the architecture, value Field)
 
     def _params(self):
         if self.parameters is None:
@@ -85,14 +88,18 @@ def boundary_value_field(arch, grid: StructuredGrid, f: Field, bc: FirstOrderBC,
         loc, idx = Center(), (0 if S == 0 else d + 1)
     else:
         loc, idx = flip(loc_f), (0 if S == 0 else d + 1)
-    key = (id(arch), tuple((ax.origin, ax.extent, ax.length) for ax in grid.axes), D, S, bc.kind, loc.code, idx)
+    import weakref
+    key = (id(arch), f.dtype.name, tuple((ax.origin, ax.extent, ax.length) for ax in grid.axes), D, S, bc.kind, loc.code, idx)
     hit = bf._cache.get(key)
-    if hit is not None:
-        return hit
+    if hit is not None and hit[0]() is not arch:             # id() of a collected architecture re-used by another one
+        hit = None
+    if hit is not None and bf.static:
+        return hit[1]
     N = grid.ndims()
     taxes = [ax for a, ax in enumerate(grid.axes) if a != D]
     tgrid = StructuredGrid(taxes, [c for a, c in enumerate(grid.connectivity_) if a != D])
-    vf = Field(arch, tgrid, Vertex(), f.dtype)                # d_t = n_t + 1: logical indices -1..n_t+3 exist
+    # d_t = n_t + 1: logical indices -1..n_t+3 exist; the device buffer of an earlier evaluation is re-used
+    vf = hit[1] if hit is not None else Field(arch, tgrid, Vertex(), f.dtype)
     ext = [ax.length + 3 for ax in taxes]                     # indices 0..n_t+2
     import numpy as np
     vals = np.empty(ext, dtype=f.dtype, order="F")
@@ -100,7 +107,7 @@ def boundary_value_field(arch, grid: StructuredGrid, f: Field, bc: FirstOrderBC,
         I = insert_dim(D + 1, tuple(int(j) for j in J), idx)
         vals[J] = bf(grid, loc, D + 1, *I)
     vf.from_host(vals, [0] * (N - 1), [e - 1 for e in ext])
-    bf._cache[key] = vf
+    bf._cache[key] = (weakref.ref(arch), vf)
     return vf
 
 

@@ -40,7 +40,9 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libchmy_b200.so")
-    with open(os.path.join(HERE, "build_ptxas.log"), "w") as fh:
+    logdir = os.path.join(HERE, "build")           # git-ignored: ptxas -v output (registers, spills) of the last build
+    os.makedirs(logdir, exist_ok=True)
+    with open(os.path.join(logdir, "ptxas.log"), "w") as fh:
         fh.write(r.stderr)
     return LIB
 

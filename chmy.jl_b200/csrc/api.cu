@@ -14,6 +14,8 @@ int chmy_fill_box(chmy_ctx* ctx, chmy_field* f, double v, const Box& b, cudaStre
 int chmy_copy_box(chmy_ctx* ctx, chmy_field* d, const chmy_field* s, const Box& b, cudaStream_t st);
 int chmy_incl_box(chmy_ctx* ctx, chmy_field* f, const InclDev& q, const Box& b, cudaStream_t st);
 int chmy_incl_box_f32(chmy_ctx* ctx, chmy_field* f, const InclDevT<float>& q, const Box& b, cudaStream_t st);
+int chmy_gauss_box(chmy_ctx* ctx, chmy_field* f, const InclDev& q, const Box& b, cudaStream_t st);
+int chmy_gauss_box_f32(chmy_ctx* ctx, chmy_field* f, const InclDevT<float>& q, const Box& b, cudaStream_t st);
 int chmy_maxabs_box(chmy_ctx* ctx, const chmy_field* f, const Box& b, unsigned long long* d_out, cudaStream_t st);
 int chmy_run_op_generic(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st);
 int chmy_run_op_fast(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st, int* handled);
@@ -395,6 +397,20 @@ extern "C" int chmy_field_set_inclusion(chmy_ctx* ctx, chmy_field* f, const chmy
     CHMY_CUDA(cudaSetDevice(ctx->device));
     if (f->dtype == CHMY_F32) return chmy_incl_box_f32(ctx, f, incl_from<float>(g, inc, f->loc), b, ctx->s_main);
     return chmy_incl_box(ctx, f, incl_from<double>(g, inc, f->loc), b, ctx->s_main);
+}
+
+extern "C" int chmy_field_set_gaussian(chmy_ctx* ctx, chmy_field* f, const chmy_grid_desc* g) {
+    CHMY_REQUIRE(ctx && f && g, "NULL argument");
+    CHMY_REQUIRE(f->nd == g->ndims, "set!: field/grid dimensionality mismatch");
+    int64_t lo[3] = {1, 1, 1}, hi[3] = {f->d[0], f->d[1], f->d[2]};
+    Box b;
+    CHMY_TRY(chmy_box_from(f, lo, hi, &b));
+    CHMY_TRY(chmy_flush(ctx));
+    CHMY_CUDA(cudaSetDevice(ctx->device));
+    chmy_inclusion none;
+    memset(&none, 0, sizeof(none));
+    if (f->dtype == CHMY_F32) return chmy_gauss_box_f32(ctx, f, incl_from<float>(g, &none, f->loc), b, ctx->s_main);
+    return chmy_gauss_box(ctx, f, incl_from<double>(g, &none, f->loc), b, ctx->s_main);
 }
 
 extern "C" int chmy_field_maxabs(chmy_ctx* ctx, const chmy_field* f, const int64_t* lo, const int64_t* hi, double* out) {

@@ -304,6 +304,27 @@ struct InclF {
     __device__ void operator()(int i, int j, int k) const { fv_st(f, i, j, k, incl_eval(q, i, j, k)); }
 };
 
+// set!(C, grid, (x, y[, z]) -> exp(-x^2 - y^2 [- z^2])): the Gaussian initial condition of the diffusion drivers
+// (examples/diffusion_2d_mpi.jl:46, diffusion_2d_mpi_perf.jl:56) evaluated where the field lives -- coordinates as in
+// uniform_axis.jl:18-19 (muladd -> fma), -x^2 - y^2 parsed as (-(x*x)) - (y*y).  exp is CUDA's (<= 1 ulp): agrees with a
+// host evaluation to ~2e-16 relative, not bit for bit.
+template <class T>
+struct GaussF {
+    FVT<T> f; InclDevT<T> q;      // origin / spacing / loc of q are the grid's and the field's; the rest is unused
+    __device__ void operator()(int i, int j, int k) const {
+        const int I[3] = {i, j, k};
+        T s = (T)0.0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (d < q.nd) {
+                const T c = coord_dev(q.origin[d], q.spacing[d], q.loc[d], I[d]);
+                s = (d == 0) ? -(c * c) : s - c * c;
+            }
+        }
+        fv_st(f, i, j, k, (T)exp(s));
+    }
+};
+
 template <class F>
 __global__ void __launch_bounds__(256) k_box_util(const F f, const Box b) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,6 +376,14 @@ int chmy_incl_box(chmy_ctx* ctx, chmy_field* f, const InclDev& q, const Box& b, 
 int chmy_incl_box_f32(chmy_ctx* ctx, chmy_field* f, const InclDevT<float>& q, const Box& b, cudaStream_t st) {
     f->frame_dirty(0);
     return launch_util(ctx, InclF<float>{f->viewT<float>(), q}, b, st);
+}
+int chmy_gauss_box(chmy_ctx* ctx, chmy_field* f, const InclDev& q, const Box& b, cudaStream_t st) {
+    f->frame_dirty(0);
+    return launch_util(ctx, GaussF<double>{f->view(), q}, b, st);
+}
+int chmy_gauss_box_f32(chmy_ctx* ctx, chmy_field* f, const InclDevT<float>& q, const Box& b, cudaStream_t st) {
+    f->frame_dirty(0);
+    return launch_util(ctx, GaussF<float>{f->viewT<float>(), q}, b, st);
 }
 
 // ---------------------------------------------------------------------------------------------- max |f|

@@ -226,6 +226,10 @@ int chmy_field_copy_to_host(chmy_ctx* ctx, const chmy_field* f, void* dst, const
 int chmy_field_copy(chmy_ctx* ctx, chmy_field* dst, const chmy_field* src, const int64_t* lo, const int64_t* hi);
                        /* set!(f, other) field.jl:109-119                                                   */
 int chmy_field_set_inclusion(chmy_ctx* ctx, chmy_field* f, const chmy_grid_desc* grid, const chmy_inclusion* inc);
+/* set!(f, grid, (x, y[, z]) -> exp(-x^2 - y^2 [- z^2])) (field.jl:131-142 with the Gaussian initial condition of
+ * examples/diffusion_2d_mpi.jl:46): evaluated on the device at the field's coordinates; agrees with a host evaluation to
+ * ~1e-16 relative (CUDA's exp), not bit for bit. */
+int chmy_field_set_gaussian(chmy_ctx* ctx, chmy_field* f, const chmy_grid_desc* grid);
                        /* set!(f, grid, init_incl; parameters) field.jl:121-142 (interior only)             */
 int chmy_field_maxabs(chmy_ctx* ctx, const chmy_field* f, const int64_t* lo, const int64_t* hi, double* out);
                        /* maximum(abs.(interior(f))) in the drivers, e.g. stokes_3d_inc_ve_T.jl:158,172-175 */

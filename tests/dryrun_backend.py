@@ -425,6 +425,19 @@ class DryRunLib:
         fld.f.data[...] = tmp.data
         return 0
 
+    def chmy_field_set_gaussian(self, ctx, h, gd):
+        self._flush_all()
+        fld = self._F(h)
+        g = self._grid(gd._obj, fld.dtype)
+        cs = [np.array([g.coord(d, fld.loc[d], i) for i in range(1, fld.f.dims[d] + 1)], dtype=fld.dtype) for d in range(fld.nd)]
+        mesh = np.meshgrid(*cs, indexing="ij")
+        s = None
+        for x in mesh:
+            s = -(x * x) if s is None else s - x * x
+        inner = tuple(slice(2, -2) for _ in range(fld.nd))
+        fld.f.data[inner] = np.exp(s)
+        return 0
+
     def chmy_field_maxabs(self, ctx, h, lo, hi, out):
         self._flush_all()
         fld = self._F(h)

@@ -21,7 +21,10 @@ def build_emul(name):
     deps = [src] + glob.glob(os.path.join(_CSRC, "*.cuh"))
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
         flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"] if san else ["-O2"]
-        subprocess.check_call(["g++"] + flags + ["-ffp-contract=off", "-march=x86-64-v3", "-shared", "-fPIC", "-Wall",
+        import platform
+        # x86-64: AVX2 + FMA so that fma() is one correctly rounded instruction; elsewhere the toolchain's default (aarch64 has fma)
+        arch = ["-march=x86-64-v3"] if platform.machine() in ("x86_64", "AMD64") else []
+        subprocess.check_call(["g++"] + flags + ["-ffp-contract=off"] + arch + ["-shared", "-fPIC", "-Wall",
                                                  "-Wno-unknown-pragmas", "-Wno-unused-function", "-o", lib, src])
     return ctypes.CDLL(lib)
 

@@ -117,6 +117,37 @@ def _worker(rank, world, port, case, q):
                 assert sent_peer > 0 and sent_nccl == 0, (sent_peer, sent_nccl)      # every link mapped: nothing fell back
             q.put((rank, "ok", 0.0))
             return
+        if kind == "gather":
+            # gather!(arch, dst, field) (src/Distributed/gather.jl:36-42): the interiors of every rank's field, block by block in
+            # Cartesian order, on the root -- Center and Vertex locations (a Vertex field's shared boundary vertex appears twice,
+            # as in the reference: size(dst) = size(interior) .* dims)
+            n_g = tuple(a * p for a, p in zip(n, pd))
+            g = ch.UniformGrid(arch, origin=(-1.0,) * nd, extent=(2.0,) * nd, dims=n_g)
+            coords = arch.topology.cart_coords
+            for loc in [(0,) * nd, (1,) + (0,) * (nd - 1), (1,) * nd]:
+                f = ch.Field(arch, g, tuple(ch.Vertex() if x else ch.Center() for x in loc))
+                shape = tuple(f.dims)
+                mine = rank * 1.0e6 + np.arange(int(np.prod(shape)), dtype=np.float64).reshape(shape, order="F")
+                ch.set_(f, mine)
+                for root in (0, world - 1):
+                    dst = np.full(tuple(a * p for a, p in zip(shape, pd)), np.nan, order="F") if rank == root else None
+                    ch.gather_(arch, dst, f, root=root)
+                    if rank == root:
+                        for r in range(world):
+                            c, rr = [], r
+                            for dsz in reversed(pd):
+                                c.append(rr % dsz); rr //= dsz
+                            c = tuple(reversed(c))
+                            want = r * 1.0e6 + np.arange(int(np.prod(shape)), dtype=np.float64).reshape(shape, order="F")
+                            sl = tuple(slice(ci * m, (ci + 1) * m) for ci, m in zip(c, shape))
+                            assert np.array_equal(dst[sl], want), (loc, root, r)
+                if rank == 0:                                    # collective call; the root's destination has the wrong size
+                    with pytest.raises(ValueError):
+                        ch.gather_(arch, np.zeros((1,) * nd), f, root=0)
+                else:
+                    ch.gather_(arch, None, f, root=0)
+            q.put((rank, "ok", 0.0))
+            return
         if kind == "diffusion":
             ow = (16, 8)
             rngs = [np.random.default_rng(100 + r).random(n) for r in range(world)]
@@ -169,6 +200,9 @@ CASES = [
     (4, ("stokes_fused", (24, 22, 14))),
     (8, ("stokes_fused", (24, 20, 16))),
     (2, ("diffusion", (64, 48))),
+    (2, ("gather", (9, 7, 5))),
+    (2, ("gather", (12, 9))),
+    (4, ("gather", (9, 7, 5))),
     (4, ("exchange", (9, 7, 5))),
     (4, ("stokes", (24, 22, 14))),
     (8, ("exchange", (9, 7, 5))),

@@ -510,3 +510,41 @@ def test_maxabs_many_equals_the_single_reductions_and_the_oracle(ch, arch, oracl
     ch.set_(bf32, a32)
     both = ch.maxabs_many(bfs[0], bf32)
     assert both[0] == many[0] and both[1] == float(np.abs(a32).max())
+
+
+# ------------------------------------------------------------------------------------------------ device-side Gaussian set!
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,loc", [((40,), (0,)), ((33, 18), (0, 0)), ((33, 18), (1, 0)), ((14, 10, 8), (0, 1, 0))])
+def test_set_gaussian_on_the_device(ch, arch, n, loc, dtype):
+    """set!(C, grid, (x, y) -> exp(-x^2 - y^2)) (examples/diffusion_2d_mpi.jl:46) evaluated in a kernel at the field's
+    coordinates: equals the host evaluation of the same closure (the generic set! path) to 1e-12 relative (CUDA's exp is
+    within an ulp of the host's, so not bit for bit); halo and padding stay untouched (field.jl:131-142 writes the interior)."""
+    nd = len(n)
+    g = ch.UniformGrid(arch, origin=(-1.0,) * nd, extent=(2.0,) * nd, dims=n, dtype=dtype)
+    L = tuple(ch.Vertex() if l else ch.Center() for l in loc)
+    fd, fh = ch.Field(arch, g, L), ch.Field(arch, g, L)
+    ch.set_(fd, g, ch.init_gauss)                                         # device kernel
+    ch.set_(fh, g, lambda *x: ch.init_gauss(*x))                          # host evaluation, uploaded
+    a, b = fd.parent().astype(np.float64), fh.parent().astype(np.float64)
+    tol = 1e-12 if dtype == np.float64 else 3e-7
+    assert np.abs(a - b).max() <= tol * np.abs(b).max() and b.max() > 0.3
+    inner = tuple(slice(2, -2) for _ in range(nd))
+    m = np.ones(a.shape, bool); m[inner] = False
+    assert (a[m] == 0).all()
+
+
+def test_boundary_function_over_mutable_state_is_re_evaluated(ch, arch):
+    """The reference calls the boundary function inside every bc! kernel (boundary_function.jl:34-44), so a closure over
+    time-dependent state gives the CURRENT value each time; `static=True` declares it pure (values kept)."""
+    g = ch.UniformGrid(arch, origin=(0.0, 0.0), extent=(1.0, 1.0), dims=(6, 5))
+    f = ch.Field(arch, g, (ch.Vertex(), ch.Center()))
+    state = {"t": 1.0}
+    for static, want in ((False, 2.0), (True, 1.0)):
+        state["t"] = 1.0
+        bf = ch.BoundaryFunction(lambda y: state["t"] + 0.0 * y, static=static)
+        ch.set_(f, 0.0)
+        ch.bc_(arch, g, (f, {"x": ch.Dirichlet(bf)}))
+        assert np.all(ch.interior(f)[0, :] == 1.0)
+        state["t"] = 2.0
+        ch.bc_(arch, g, (f, {"x": ch.Dirichlet(bf)}))
+        assert np.all(ch.interior(f)[0, :] == want), (static, ch.interior(f)[0, :])
