@@ -275,15 +275,29 @@ function bc!(arch::SingleDeviceArchitecture{B200Backend}, grid::StructuredGrid, 
     return
 end
 
-# Lazily fused PT iteration (include/chmy_b200.h: chmy_set_fusion): `launch(update_stress!)` is deferred and runs with
-# the following `launch(update_velocity!; bc)` as one sweep; anything else on the context flushes it first, so drivers
-# stay exactly as the reference wrote them.  Device pointers cached from chmy_field_get_info go stale after a fused
-# launch (tau, Pr, V ping-pong between two buffers): B200Array re-queries its pointer instead of caching it.
+# Lazily fused launches (include/chmy_b200.h: chmy_set_fusion): the first launch of a pair (`update_stress!`, `compute_q!`,
+# `update_thermal_flux!`) is deferred and runs with the following launch of its partner as one sweep; anything else on the
+# context flushes it first, so drivers stay exactly as the reference wrote them.  Device pointers cached from
+# chmy_field_get_info go stale after a fused launch (the written fields ping-pong between two buffers): B200Array
+# re-queries its pointer instead of caching it.
 fuse!(arch::SingleDeviceArchitecture{B200Backend}, on::Bool=true) =
-    check(ccall((:chmy_set_fusion, libchmy), Cint, (Ptr{Cvoid}, Cint), ctx(arch), on))
+    check(ccall((:chmy_set_fusion, libchmy), Cint, (Ptr{Cvoid}, Cint), ctx(arch), on ? 3 : 0))
+
+# Launches with boundary batches (include/chmy_b200.h: chmy_set_launch_tuning): overlap the batches / the halo exchange with
+# the kernel (default) or run everything on one stream; results are identical.  -1 keeps the batch-folding setting.
+overlap!(arch, on::Bool=true) =
+    check(ccall((:chmy_set_launch_tuning, libchmy), Cint, (Ptr{Cvoid}, Cint, Cint), ctx(arch), on ? 1 : 0, -1))
+
+# set!(C, grid, init_gauss): the Gaussian initial condition of the diffusion drivers (examples/diffusion_2d_mpi.jl:46)
+# evaluated on the device (chmy_field_set_gaussian)
+init_gauss(x...) = exp(-sum(abs2, x))
+function Fields.set!(f::Field, grid::StructuredGrid, ::typeof(init_gauss))
+    check(ccall((:chmy_field_set_gaussian, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{GridDesc}), ctx(f), handle(f), GridDesc(grid)))
+    return
+end
 
 # Transport of exchange_halo! on a distributed architecture (include/chmy_b200.h: chmy_set_exchange_mode): :nccl (default) or
-# :peer (EXPERIMENTAL: pack kernels store into the neighbour's HBM over NVLink, sequence flags instead of ncclSend/ncclRecv).
+# :peer (opt-in: pack kernels store into the neighbour's HBM over NVLink, sequence flags instead of ncclSend/ncclRecv).
 # Every rank must choose the same; results are identical.
 exchange_mode!(arch, mode::Symbol) =
     check(ccall((:chmy_set_exchange_mode, libchmy), Cint, (Ptr{Cvoid}, Cint), ctx(arch), mode === :peer ? 1 : 0))
