@@ -292,7 +292,7 @@ overlap!(arch, on::Bool=true) =
 # evaluated on the device (chmy_field_set_gaussian)
 init_gauss(x...) = exp(-sum(abs2, x))
 function Fields.set!(f::Field, grid::StructuredGrid, ::typeof(init_gauss))
-    check(ccall((:chmy_field_set_gaussian, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{GridDesc}), ctx(f), handle(f), GridDesc(grid)))
+    check(ccall((:chmy_field_set_gaussian, libchmy), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{GridDesc}), ctx(parent(f).arch), handle(f), GridDesc(grid)))
     return
 end
 
