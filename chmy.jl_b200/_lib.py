@@ -122,7 +122,7 @@ SYMBOLS = {
     "chmy_set_fusion": (C.c_int, [_vp, C.c_int]),
     "chmy_fused_count": (C.c_int, [_vp, _P(C.c_uint64)]),
     "chmy_set_fused_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
-    "chmy_set_fused2d_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "chmy_set_fused2d_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "chmy_halo_slab_len": (C.c_int, [_vp, C.c_int, _i64p]),
     "chmy_halo_pack": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "chmy_halo_unpack": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),

@@ -165,8 +165,8 @@ def set_fused_tuning(arch: Architecture, rows_per_cta: int = 0, cluster_size: in
     L.check(L.lib().chmy_set_fused_tuning(arch.ctx, int(rows_per_cta), int(cluster_size), int(z_chunk), int(variant)))
 
 
-def set_fused2d_tuning(arch: Architecture, rows_per_chunk: int = 0, unroll: int = 0):
-    L.check(L.lib().chmy_set_fused2d_tuning(arch.ctx, int(rows_per_chunk), int(unroll)))
+def set_fused2d_tuning(arch: Architecture, rows_per_chunk: int = 0, unroll: int = 0, thermal3_planes_per_chunk: int = 0):
+    L.check(L.lib().chmy_set_fused2d_tuning(arch.ctx, int(rows_per_chunk), int(unroll), int(thermal3_planes_per_chunk)))
 
 
 def set_launch_split(arch: Architecture, split=True, bc_fold=None):

@@ -96,7 +96,7 @@ static bool fsv_tyb_ok(int v) { return v == 4 || v == 6 || v == 8; }
 // defaults: measured optimum at 767^3 (profiles/r2_c2_tune_fused_clusters_hints.log); the environment overrides them
 void chmy_tuning_defaults(chmy_tuning* t) {
     t->fuse_tyb = 6; t->fuse_cl = 4; t->fuse_cz = 64; t->fuse_var = 1;
-    t->f2_cy = 64; t->f2_unroll = 4; t->t3_cz = 16;
+    t->f2_cy = 0; t->f2_unroll = 0; t->t3_cz = 64;       // 0: per-sweep optimum (ops_fused2d.cu); 64 planes: profiles/r2_c20_*
     t->overlap = 1; t->bc_fold = 1;
     const char* e;
     if ((e = getenv("CHMY_FUSE_VARIANT"))) t->fuse_var = atoi(e);

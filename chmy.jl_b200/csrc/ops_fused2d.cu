@@ -123,9 +123,10 @@ int chmy_frame_copy2(chmy_ctx* ctx, const chmy_grid_desc* g, int n, chmy_field* 
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-extern "C" int chmy_set_fused2d_tuning(chmy_ctx* ctx, int rows_per_chunk, int unroll) {
+extern "C" int chmy_set_fused2d_tuning(chmy_ctx* ctx, int rows_per_chunk, int unroll, int thermal3_planes_per_chunk) {
     CHMY_REQUIRE(ctx != nullptr, "ctx is NULL");
-    if (rows_per_chunk > 0) ctx->tun.f2_cy = rows_per_chunk;
+    if (thermal3_planes_per_chunk > 0) ctx->tun.t3_cz = thermal3_planes_per_chunk;
+    if (rows_per_chunk > 0) ctx->tun.f2_cy = rows_per_chunk;      // (env / default 0: the per-sweep optimum)
     if (unroll > 0) {
         CHMY_REQUIRE(unroll == 1 || unroll == 2 || unroll == 4, "unroll must be 1, 2 or 4");
         ctx->tun.f2_unroll = unroll;
@@ -266,7 +267,10 @@ int chmy_run_fused2d(chmy_ctx* ctx, int kind, const chmy_launch_desc* dp, const 
     chmy_field* const* Q = dc->fields;
     const double* id = dp->grid.inv_spacing;
     const int gx = (box.n[0] + FSV_XI - 1) / FSV_XI;
-    int cy = ctx->tun.f2_cy;
+    // 0 = the measured optimum of the sweep (profiles/r2_c20_tune_pairs_*.log, 8191^2 / 16383^2): compute_q! + update_C!
+    // 16 rows per chunk with 4 rows of loads in flight; 2D Stokes and the 2D thermal pair 32 rows, 1 row in flight
+    int cy = ctx->tun.f2_cy > 0 ? ctx->tun.f2_cy : (kind == 2 ? 16 : 32);
+    const int unroll = ctx->tun.f2_unroll > 0 ? ctx->tun.f2_unroll : (kind == 2 ? 4 : 1);
     while ((box.n[1] + cy - 1) / cy > 65535) cy *= 2;
     const int nch = (box.n[1] + cy - 1) / cy;
     cy = (box.n[1] + nch - 1) / nch;                            // balanced chunks
@@ -323,7 +327,7 @@ int chmy_run_fused2d(chmy_ctx* ctx, int kind, const chmy_launch_desc* dp, const 
         }
         p.idx = id[0]; p.idy = id[1];
         p.cy = cy;
-        if (kind == 2) CHMY_TRY(launch_q2<0>(p, gx, grid, ctx->tun.f2_unroll, st)); else CHMY_TRY(launch_q2<1>(p, gx, grid, ctx->tun.f2_unroll, st));
+        if (kind == 2) CHMY_TRY(launch_q2<0>(p, gx, grid, unroll, st)); else CHMY_TRY(launch_q2<1>(p, gx, grid, unroll, st));
     }
     ctx->n_launches++;
     return CHMY_OK;

@@ -321,9 +321,9 @@ int chmy_fused_count(const chmy_ctx* ctx, uint64_t* sweeps);          /* fused s
  * release arrive (-1 keeps).  Defaults 6, 4, 64, 1 = the measured optimum at 767^3 (profiles/README.md).
  * Env (read when the context is created): CHMY_FUSE_TYB, CHMY_FUSE_CL, CHMY_FUSE_CZ, CHMY_FUSE_VARIANT. */
 int chmy_set_fused_tuning(chmy_ctx* ctx, int rows_per_cta, int cluster_size, int z_chunk, int variant);
-/* 2D sweeps: rows per y-chunk of a warp; rows whose operands are requested ahead of the arithmetic (1|2|4, flux pairs)
- * (0 keeps a setting).  Env: CHMY_FUSE2D_CY, CHMY_FUSE2D_UNROLL. */
-int chmy_set_fused2d_tuning(chmy_ctx* ctx, int rows_per_chunk, int unroll);
+/* 2D sweeps: rows per y-chunk of a warp; rows whose operands are requested ahead of the arithmetic (1|2|4, flux pairs);
+ * 3D thermal sweep: planes per z-chunk (0 keeps a setting).  Env: CHMY_FUSE2D_CY, CHMY_FUSE2D_UNROLL, CHMY_FUSE_T3_CZ. */
+int chmy_set_fused2d_tuning(chmy_ctx* ctx, int rows_per_chunk, int unroll, int thermal3_planes_per_chunk);
 
 /* halo slab pack/unpack exposed for bit-exact parity tests of src/Distributed/communication_views.jl:1-34 */
 int chmy_halo_slab_len(const chmy_field* f, int dim, int64_t* len);

@@ -3,7 +3,7 @@
     python scratch/tune_pairs.py stokes2d|diffusion2d|stokes2d_thermal|stokes3d_thermal [n...]
 
 2D sweeps: rows per y-chunk x rows per load group (chmy_set_fused2d_tuning); 3D thermal sweep: planes per z-chunk
-(CHMY_FUSE_T3_CZ, read at every launch).  Prints ms per PT iteration next to the two-kernel time of the same process.
+(chmy_set_fused2d_tuning).  Prints ms per PT iteration next to the two-kernel time of the same process.
 """
 import math
 import os
@@ -67,8 +67,8 @@ if len(n) == 2:
             except Exception as e:
                 print("FAILED", cy, un, e, flush=True)
 else:
-    for cz in (8, 16, 24, 32, 64):
-        os.environ["CHMY_FUSE_T3_CZ"] = str(cz)
+    for cz in (4, 8, 12, 16, 24, 32, 64):
+        ch.set_fused2d_tuning(arch, 0, 0, cz)
         try:
             show(f"fused thermal sweep cz={cz}", timeit())
         except Exception as e:
