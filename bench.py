@@ -75,7 +75,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the untimed multi-rank correctness check")
     ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the other BASELINE configs (extra.workloads)")
-    ap.add_argument("--split", default="on", choices=["auto", "on", "off"],
+    ap.add_argument("--split", default="on", choices=["auto", "on", "off", "always"],
                     help="launches with boundary batches -- on (= auto, the default): the batches and the halo exchange overlap "
                          "the kernel (fused 3D sweep: boundary tiles first + a retire counter, one launch; plain kernels: the "
                          "reference's inner region + slabs); off: one kernel, then batches + exchange on one stream "
@@ -413,7 +413,7 @@ def run_b200(args):
     wl = args.workload
     n = tuple(args.n) if args.n else WORKLOADS[wl][0]
     split_mode = "off" if args.no_split else args.split
-    ch.set_launch_split(arch, split_mode != "off")
+    ch.set_launch_split(arch, "always" if split_mode == "always" else split_mode != "off")
     fused2d = args.fused == 3 and not wl.startswith("stokes3d")      # 2D flux -> update sweeps (ops_fused2d.cu)
     fused_t3 = args.fused == 3 and wl == "stokes3d_thermal"          # 3D thermal sweep (fused_thermal3.cuh)
     fused = (bool(args.fused) and wl.startswith("stokes3d")) or fused2d

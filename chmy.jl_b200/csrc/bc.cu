@@ -106,8 +106,7 @@ static int run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chm
 // ---- all dimensions, sides and fields of a batch set in ONE launch (bc_all_point, bc_kernels.cuh)
 template <class T>
 __global__ void __launch_bounds__(128) k_bc_all(const BcAllDev<T> b) {
-    const int z = blockIdx.z, s = z & 1, D = (z >> 1) % 3, q = z / 6;
-    if (D >= b.nd) return;
+    const int z = b.act[blockIdx.z], s = z & 1, D = (z >> 1) % 3, q = z / 6;
     int nt[2] = {1, 1}, t = 0;
     for (int a = 0; a < b.nd; ++a)
         if (a != D) nt[t++] = b.n[a] + 3;
@@ -156,7 +155,11 @@ static bool make_bc_all(const chmy_grid_desc* g, const chmy_batch_desc bc[CHMY_M
         }
     for (int q = 0; q < b.nf; ++q) touched[q] = fl[q];
     *ntouched = b.nf;
-    return b.nf > 0;
+    for (int q = 0; q < b.nf; ++q)
+        for (int D = 0; D < g->ndims; ++D)
+            for (int s = 0; s < 2; ++s)
+                if (b.fld[q].r[D][s].kind >= 0) b.act[b.nact++] = (unsigned char)((q * 3 + D) * 2 + s);
+    return b.nact > 0;
 }
 
 template <class T>
@@ -175,7 +178,7 @@ static int run_bc_all_t(chmy_ctx* ctx, const chmy_grid_desc* g, const chmy_batch
         m0 = e[0] > m0 ? e[0] : m0; m1 = e[1] > m1 ? e[1] : m1;
     }
     CHMY_REQUIRE(m1 <= 65535, "face too large for one launch");
-    k_bc_all<T><<<dim3((m0 + 127) / 128, m1, 6 * b.nf), 128, 0, st>>>(b);
+    k_bc_all<T><<<dim3((m0 + 127) / 128, m1, b.nact), 128, 0, st>>>(b);
     ctx->n_launches++;
     CHMY_CUDA(cudaGetLastError());
     *handled = 1;

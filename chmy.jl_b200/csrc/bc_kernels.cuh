@@ -116,6 +116,8 @@ struct BcAllDev {
     int           n[3];       // grid cells per dim: face points span 0..n+2 in every transverse dim
     T             spacing[3];
     BcAllField<T> fld[BCK_ALL_FIELDS];
+    int           nact;                                   // faces that carry a condition ...
+    unsigned char act[6 * BCK_ALL_FIELDS];                // ... as (field * 3 + dim) * 2 + side: one slice of the launch grid each
 };
 
 template <class T>

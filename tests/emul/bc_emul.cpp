@@ -49,13 +49,12 @@ static int run_bc_all(const BcAllDev<T>* b, int rev) {
             if (a != D) e[t++] = b->n[a] + 3;
         m0 = e[0] > m0 ? e[0] : m0; m1 = e[1] > m1 ? e[1] : m1;
     }
-    const int nx = (m0 + 127) / 128 * 128, nz = 6 * b->nf;
+    const int nx = (m0 + 127) / 128 * 128, nz = b->nact;
     const long long total = (long long)nz * m1 * nx;
     for (long long i = 0; i < total; ++i) {
         const long long t = rev ? total - 1 - i : i;
-        const int a = (int)(t % nx), c = (int)((t / nx) % m1), z = (int)(t / ((long long)nx * m1));
+        const int a = (int)(t % nx), c = (int)((t / nx) % m1), z = b->act[(int)(t / ((long long)nx * m1))];
         const int s = z & 1, D = (z >> 1) % 3, q = z / 6;
-        if (D >= b->nd) continue;
         int nt[2] = {1, 1}, k = 0;
         for (int d = 0; d < b->nd; ++d)
             if (d != D) nt[k++] = b->n[d] + 3;

@@ -43,7 +43,8 @@ def _structs(R):
         _fields_ = [("f", BckView), ("d", C.c_int * 3), ("vertex", C.c_int * 3), ("r", (BcRule * 2) * 3)]
 
     class BcAllDev(C.Structure):
-        _fields_ = [("nf", C.c_int), ("nd", C.c_int), ("n", C.c_int * 3), ("spacing", R * 3), ("fld", BcAllField * ALLF)]
+        _fields_ = [("nf", C.c_int), ("nd", C.c_int), ("n", C.c_int * 3), ("spacing", R * 3), ("fld", BcAllField * ALLF),
+                    ("nact", C.c_int), ("act", C.c_ubyte * (6 * ALLF))]
 
     class SlabEntry(C.Structure):
         _fields_ = [("f", BckView), ("idx", C.c_int), ("e0", C.c_int), ("e1", C.c_int), ("off", C.c_longlong)]
@@ -353,6 +354,12 @@ def run_bc_all_both(o, emul, g, field_bcs, rev):
                     r.value, r.vp, r.vsy = 0.0, ov.p, ov.sy
                 else:
                     r.value, r.vp, r.vsy = (0.0 if v is None else float(v)), None, 0
+    for q in range(b.nf):                                 # the faces that carry a condition: one slice of the launch grid each
+        for D in range(g.nd):
+            for sd in range(2):
+                if b.fld[q].r[D][sd].kind >= 0:
+                    b.act[b.nact] = (q * 3 + D) * 2 + sd
+                    b.nact += 1
     assert (emul.bc_all_emul_run_f32 if f32 else emul.bc_all_emul_run)(C.byref(b), int(rev)) == 0
     for D in reversed(range(g.nd)):
         for s in range(2):

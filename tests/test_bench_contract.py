@@ -217,3 +217,28 @@ def test_host_segment_is_refused_when_host_memory_is_short(monkeypatch):
         bench.run_b200(bench.parse())
     j = json.loads(buf.getvalue().strip())
     assert "host memory" in j["e2e"]["host_segment_error"] and j["e2e"]["value"] > 0 and calls == {"h2d": 0, "d2h": 0}
+
+
+@pytest.mark.parametrize("pd,n", [((2, 1, 1), (5, 4, 3)), ((2, 2, 1), (4, 3, 3)), ((2, 2, 2), (4, 3, 3)), ((4, 2), (5, 4)), ((1, 3), (4, 5))])
+def test_bench_exchange_restatement_equals_the_oracle(pd, n):
+    """bench.py's N-rank self-check may not touch the oracle at run time, so it restates the send / recv view algebra
+    (communication_views.jl:1-34, exchange_halo.jl:73-84) in numpy; here that restatement is pinned on the oracle's
+    lock-step world: index-encoded fields at four staggered locations, every process grid shape, corners included."""
+    import oracle as o
+    bench = _load_bench()
+    nd, world = len(pd), int(np.prod(pd))
+    topos = [o.Topology(world, pd, r) for r in range(world)]
+    n_g = tuple(a * p for a, p in zip(n, pd))
+    ogs = [o.local_grid((-1.0,) * nd, (2.0,) * nd, n_g, t) for t in topos]
+    locs = [(0,) * nd, (1,) + (0,) * (nd - 1), (0,) * (nd - 1) + (1,), (1,) * nd]
+    ofs = [[o.Field(og, l) for l in locs] for og in ogs]
+    parents = []
+    for r in range(world):
+        for f in ofs[r]:
+            f.data[...] = r * 1.0e6 + np.arange(f.data.size, dtype=np.float64).reshape(f.sdims, order="F")
+        parents.append([f.data.copy() for f in ofs[r]])
+    o.bc_world(ogs, [o.batch(ogs[r], exchange=tuple(ofs[r])) for r in range(world)], topos)
+    want = bench._exchange_expected(parents, locs, pd, [t.coords for t in topos], n)
+    for r in range(world):
+        for q in range(len(locs)):
+            assert np.array_equal(want[r][q], ofs[r][q].data), (r, locs[q])
