@@ -481,6 +481,7 @@ def run_b200(args):
     l1 = ch.launch_count(arch)
     nfused = ch.fused_count(arch)
     noverl = ch.overlapped_count(arch)
+    nfallback = ch.fusion_fallback_count(arch)
     xstats = dict(zip(("peer", "nccl"), ch.exchange_stats(arch))) if world > 1 else None     # rank 0's messages so far
     clocks = sampler.stop() if rank == 0 else None
     ch.barrier(arch)
@@ -619,8 +620,22 @@ def run_b200(args):
             ch.event_record(arch, 3)
             ch.synchronize(arch)
             (xms,) = ch.allreduce_max(arch, ch.event_elapsed_ms(arch, 2, 3) / 20)
+            per = {}
+            for D in range(len(n)):     # one dimension at a time: both sides of dim D through an exchange-only bc! batch (a collective every rank joins)
+                if pdims[D] == 1:
+                    continue
+                spec = {"xyz"[D]: tuple(sol.V)}
+                ch.bc_(arch, sol.grid, exchange=spec, blocking=False)
+                ch.synchronize(arch); ch.barrier(arch)
+                ch.event_record(arch, 4)
+                for _ in range(10):
+                    ch.bc_(arch, sol.grid, exchange=spec, blocking=False)
+                ch.event_record(arch, 5)
+                ch.synchronize(arch)
+                (t,) = ch.allreduce_max(arch, ch.event_elapsed_ms(arch, 4, 5) / 10)
+                per[f"dim{D + 1}"] = t
             face = [8.0 * sum(int(np.prod([f.dims[a] + 4 for a in range(len(n)) if a != D])) for f in sol.V) for D in range(len(n))]
-            xchg = {"ms_per_exchange_alone": xms, "connected_dims": [D + 1 for D in range(len(n)) if pdims[D] > 1],
+            xchg = {"ms_per_exchange_alone": xms, "ms_per_dim_alone": per, "connected_dims": [D + 1 for D in range(len(n)) if pdims[D] > 1],
                     "bytes_per_side_per_dim": face,
                     "what": "exchange_halo!(arch, grid, V...) alone on an idle device, max over ranks: what one iteration's exchange "
                             "costs when nothing hides it (the timed loop overlaps it with the sweep unless --split off)"}
@@ -651,7 +666,7 @@ def run_b200(args):
                        "l2": "inputs larger than L2 (every field >= 2 GB; 126 MB L2), no flush needed",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "T_eff_per_gpu": teff_gpu, "frac_of_hbm_peak": teff_gpu / peak, "hbm_peak": peak, "hbm_peak_source": peak_src,
-            "clocks": clocks, "gpu_launches": int(l1 - l0), "launches_per_step": (l1 - l0) / K, "fused_sweeps": int(nfused), "overlapped_launches": int(noverl), "exchange_msgs": xstats, "roofline": roofline, "e2e": e2e, "cpu_baseline": cb,
+            "clocks": clocks, "gpu_launches": int(l1 - l0), "launches_per_step": (l1 - l0) / K, "fused_sweeps": int(nfused), "fusion_fallbacks": int(nfallback), "overlapped_launches": int(noverl), "exchange_msgs": xstats, "roofline": roofline, "e2e": e2e, "cpu_baseline": cb,
             "multi_gpu_check": mgc, "exchange_alone": xchg,
         }
     if world > 1:

@@ -121,6 +121,7 @@ SYMBOLS = {
     "chmy_selftest_tile_order": (C.c_int, [_i32p, _i32p, _i32p, C.c_int32, _i32p]),
     "chmy_set_fusion": (C.c_int, [_vp, C.c_int]),
     "chmy_fused_count": (C.c_int, [_vp, _P(C.c_uint64)]),
+    "chmy_fusion_fallback_count": (C.c_int, [_vp, _P(C.c_uint64)]),
     "chmy_set_fused_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "chmy_set_fused2d_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "chmy_halo_slab_len": (C.c_int, [_vp, C.c_int, _i64p]),

@@ -153,6 +153,13 @@ def fused_count(arch: Architecture) -> int:
     return int(n.value)
 
 
+def fusion_fallback_count(arch: Architecture) -> int:
+    """pairs of launches that ran as two kernels because the device had no memory left for the sweeps' shadow buffers"""
+    n = C.c_uint64(0)
+    L.check(L.lib().chmy_fusion_fallback_count(arch.ctx, C.byref(n)))
+    return int(n.value)
+
+
 def overlapped_count(arch: Architecture) -> int:
     """launches whose boundary batches / halo exchange ran behind the boundary tiles of a still-running fused sweep"""
     n = C.c_uint64(0)

@@ -737,6 +737,12 @@ extern "C" int chmy_fused_count(const chmy_ctx* ctx, uint64_t* sweeps) {
     return CHMY_OK;
 }
 
+extern "C" int chmy_fusion_fallback_count(const chmy_ctx* ctx, uint64_t* pairs) {
+    CHMY_REQUIRE(ctx && pairs, "NULL argument");
+    *pairs = ctx->n_fuse_fallback;
+    return CHMY_OK;
+}
+
 static int run_plain(chmy_ctx* ctx, const chmy_launch_desc* d) {
     bool split = false;
     int wl[3] = {0, 0, 0}, wr[3] = {0, 0, 0};
@@ -920,6 +926,7 @@ extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
         ctx->has_pending = 0;
         const int rc = run_fused(ctx, &ctx->pending, d);
         if (rc <= 0) return rc;
+        ctx->n_fuse_fallback++;
         CHMY_TRY(run_plain(ctx, &ctx->pending));    // no memory for the shadow buffers: two kernels
         return run_plain(ctx, d);
     }
@@ -929,6 +936,7 @@ extern "C" int chmy_launch(chmy_ctx* ctx, const chmy_launch_desc* d) {
             ctx->has_pending = 0;
             const int rc = run_fused2d(ctx, kind, &ctx->pending, d);
             if (rc <= 0) return rc;
+            ctx->n_fuse_fallback++;
             CHMY_TRY(run_plain(ctx, &ctx->pending));    // no memory for the shadow buffers: two kernels
             return run_plain(ctx, d);
         }

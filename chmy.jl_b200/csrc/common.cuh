@@ -175,6 +175,7 @@ struct chmy_ctx {
     int               has_pending;
     chmy_launch_desc  pending;
     uint64_t          n_fused;       // fused sweeps launched so far
+    uint64_t          n_fuse_fallback;   // pairs that had to run as two kernels because their shadow buffers could not be allocated
     chmy_tuning       tun;
     unsigned int*     d_done;        // device counter of the boundary-first sweep (ops_fused.cu): CTAs of boundary tiles retired
     uint64_t          batch_sig;     // signature of the batch set being applied right now (0 outside launch / bc!)

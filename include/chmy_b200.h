@@ -316,6 +316,9 @@ int chmy_selftest_tile_order(const int32_t g[3], const int32_t i0[3], const int3
  *   update_thermal_flux! + update_thermal! 3D       stokes_3d_inc_ve_T.jl:167-168   12 ->  9                    */
 int chmy_set_fusion(chmy_ctx* ctx, int enable);
 int chmy_fused_count(const chmy_ctx* ctx, uint64_t* sweeps);          /* fused sweeps launched so far            */
+/* pairs that ran as two kernels because the device had no memory for their shadow buffers (the sweeps write through
+ * ping-pong twins of the fields they update): results are the same, the pair just moves 40 instead of 30 passes */
+int chmy_fusion_fallback_count(const chmy_ctx* ctx, uint64_t* pairs);
 /* Per-context tile geometry of the fused 3D sweep: rows of a CTA (4|6|8), CTAs per thread-block cluster along y (1..8), planes
  * per z-chunk (0 keeps a setting); variant: bit 0 = relaxed cluster-barrier arrive behind a CTA-scope fence instead of the
  * release arrive (-1 keeps).  Defaults 6, 4, 64, 1 = the measured optimum at 767^3 (profiles/README.md).

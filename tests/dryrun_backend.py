@@ -139,6 +139,10 @@ class DryRunLib:
             self.ctxs[self._h(ctx)]["overlap"] = int(overlap)
         return 0
 
+    def chmy_fusion_fallback_count(self, ctx, out):
+        self._set(out, 0)
+        return 0
+
     def chmy_overlapped_count(self, ctx, out):
         self._set(out, self.ctxs[self._h(ctx)].get("noverl", 0))
         return 0

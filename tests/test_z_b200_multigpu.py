@@ -210,8 +210,7 @@ CASES = [
 ]
 # the fused sweep is the default of the drivers and the bench: it gets every world size
 CASES.sort(key=lambda c: (c[0], c[1][0]))
-# EXPERIMENTAL peer-store transport (comm.cu, CHMY_EXCHANGE_PEER): protocol proven on the CPU (tests/test_peer_protocol.py),
-# never run on a GPU yet -> gated, and after every measured case
+# peer-store transport (comm.cu, CHMY_EXCHANGE_PEER; opt-in): protocol proven on the CPU (tests/test_peer_protocol.py)
 PEER_CASES = [
     (2, ("exchange+peer", (9, 7, 5))),
     (2, ("exchange+peer", (12, 9))),
@@ -222,8 +221,7 @@ PEER_CASES = [
     (8, ("exchange+peer", (9, 7, 5))),
     (8, ("stokes_fused+peer", (24, 20, 16))),
 ]
-if os.environ.get("CHMY_EXPERIMENTAL", "0") == "1":
-    CASES += PEER_CASES
+CASES += PEER_CASES          # green on 2-, 4- and 8-GPU boxes since round 2 (profiles/r2_c9_*, r2_c11_*)
 
 
 @pytest.mark.parametrize("world,case", CASES, ids=[f"{w}gpu-{c[0]}-{'x'.join(map(str, c[1]))}" for w, c in CASES])
