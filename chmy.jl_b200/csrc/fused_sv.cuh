@@ -224,98 +224,50 @@ FHD double fsv_from_left(double, const double* p_im1, bool ok) { return ok ? *p_
 #endif
 
 // ---- phase A: stresses of plane kp -> sn[FSV_NF] (new Pr, tau), stores for the cells this thread owns
-// fsv_load_a issues the global loads of the plane, fsv_compute_a consumes them: the sweep either runs them back to back
-// (fsv_phase_a) or puts the velocity update of an earlier plane between them (the lagged march, below).
 // The two halo rows of a cluster load only what their consumers need (the first row feeds Pr and tau_yy to the row above
 // it, the last row tau_xy and tau_yz to the row below; everything else they would compute is never read): 7 resp. 9 of
 // the 19 loads (measured at 767^3: 20.31 -> 20.22 ms, profiles/r2_c13_tune_fused.log).
-struct FusedL {
-    d2 vx, vxjm, vy, vyjp, vzkp, vzjmkp, pr, t[6], o[6];
-};
-
-// Pr, tau, tau_old of the plane
-FHD void fsv_load_tau(const FusedT& s, const FusedP& p, FusedL& L) {
+template <bool TD>
+FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
     const d2 z2 = fsv_zero();
-    L.pr = z2;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) { L.t[c] = z2; L.o[c] = z2; }
-    if (!s.s_act) return;
-    if (s.role == 1) {                  // Pr, tau_yy
-        L.pr   = ld2(p.Prc + s.cc);
-        L.t[1] = ld2(p.tc[1] + s.cc); L.o[1] = ld2(p.to[1] + s.cc);
-    } else if (s.role == 2) {           // tau_xy, tau_yz
-        L.t[3] = ld2(p.tc[3] + s.vv); L.o[3] = ld2(p.to[3] + s.vv);
-        L.t[5] = ld2(p.tc[5] + s.cv); L.o[5] = ld2(p.to[5] + s.cv);
-    } else {
-        L.pr = ld2(p.Prc + s.cc);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { L.t[c] = ld2(p.tc[c] + s.cc); L.o[c] = ld2(p.to[c] + s.cc); }
-        L.t[3] = ld2(p.tc[3] + s.vv); L.o[3] = ld2(p.to[3] + s.vv);
-        L.t[4] = ld2(p.tc[4] + s.vc); L.o[4] = ld2(p.to[4] + s.vc);
-        L.t[5] = ld2(p.tc[5] + s.cv); L.o[5] = ld2(p.to[5] + s.cv);
-    }
-}
-
-// the whole plane, in the order the plain march issues it (measured: calling the two halves above back to back instead costs
-// the plain march 1 % -- another instruction schedule, profiles/r2_c30_tune_lag.log)
-FHD void fsv_load_a(const FusedT& s, const FusedP& p, FusedL& L) {
-    const d2 z2 = fsv_zero();
-    L.vx = z2; L.vxjm = z2; L.vy = z2; L.vyjp = z2; L.vzkp = z2; L.vzjmkp = z2; L.pr = z2;
+    d2 vx = z2, vxjm = z2, vy = z2, vyjp = z2, vzkp = z2, vzjmkp = z2, pr = z2;
+    d2 t[6], o[6];
     if (s.role != 0) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) { L.t[c] = z2; L.o[c] = z2; }
+        for (int c = 0; c < 6; ++c) { t[c] = z2; o[c] = z2; }
         if (s.s_act && s.role == 1) {          // divV (all three normal strain rates), Pr, tau_yy
-            L.vx   = ld2(p.Vc[0] + s.vc);
-            L.vy   = ld2(p.Vc[1] + s.cv);
-            L.vyjp = ld2(p.Vc[1] + s.cv + (long long)s.jp * p.cv.sy);
-            L.vzkp = ld2(p.Vc[2] + s.cc + p.cc.sz);
-            L.pr   = ld2(p.Prc + s.cc);
-            L.t[1] = ld2(p.tc[1] + s.cc); L.o[1] = ld2(p.to[1] + s.cc);
+            vx   = ld2(p.Vc[0] + s.vc);
+            vy   = ld2(p.Vc[1] + s.cv);
+            vyjp = ld2(p.Vc[1] + s.cv + (long long)s.jp * p.cv.sy);
+            vzkp = ld2(p.Vc[2] + s.cc + p.cc.sz);
+            pr   = ld2(p.Prc + s.cc);
+            t[1] = ld2(p.tc[1] + s.cc); o[1] = ld2(p.to[1] + s.cc);
         } else if (s.s_act) {                  // the two shear strain rates with a y index, tau_xy, tau_yz
-            L.vx     = ld2(p.Vc[0] + s.vc);
-            L.vxjm   = ld2(p.Vc[0] + s.vc - (long long)s.jm * p.vc.sy);
-            L.vy     = ld2(p.Vc[1] + s.cv);
-            L.vzkp   = ld2(p.Vc[2] + s.cc + p.cc.sz);
-            L.vzjmkp = ld2(p.Vc[2] + s.cc - (long long)s.jm * p.cc.sy + p.cc.sz);
-            L.t[3] = ld2(p.tc[3] + s.vv); L.o[3] = ld2(p.to[3] + s.vv);
-            L.t[5] = ld2(p.tc[5] + s.cv); L.o[5] = ld2(p.to[5] + s.cv);
+            vx     = ld2(p.Vc[0] + s.vc);
+            vxjm   = ld2(p.Vc[0] + s.vc - (long long)s.jm * p.vc.sy);
+            vy     = ld2(p.Vc[1] + s.cv);
+            vzkp   = ld2(p.Vc[2] + s.cc + p.cc.sz);
+            vzjmkp = ld2(p.Vc[2] + s.cc - (long long)s.jm * p.cc.sy + p.cc.sz);
+            t[3] = ld2(p.tc[3] + s.vv); o[3] = ld2(p.to[3] + s.vv);
+            t[5] = ld2(p.tc[5] + s.cv); o[5] = ld2(p.to[5] + s.cv);
         }
     } else if (s.s_act) {
-        L.vx     = ld2(p.Vc[0] + s.vc);
-        L.vxjm   = ld2(p.Vc[0] + s.vc - (long long)s.jm * p.vc.sy);
-        L.vy     = ld2(p.Vc[1] + s.cv);
-        L.vyjp   = ld2(p.Vc[1] + s.cv + (long long)s.jp * p.cv.sy);
-        L.vzkp   = ld2(p.Vc[2] + s.cc + p.cc.sz);
-        L.vzjmkp = ld2(p.Vc[2] + s.cc - (long long)s.jm * p.cc.sy + p.cc.sz);
-        L.pr = ld2(p.Prc + s.cc);
+        vx     = ld2(p.Vc[0] + s.vc);
+        vxjm   = ld2(p.Vc[0] + s.vc - (long long)s.jm * p.vc.sy);
+        vy     = ld2(p.Vc[1] + s.cv);
+        vyjp   = ld2(p.Vc[1] + s.cv + (long long)s.jp * p.cv.sy);
+        vzkp   = ld2(p.Vc[2] + s.cc + p.cc.sz);
+        vzjmkp = ld2(p.Vc[2] + s.cc - (long long)s.jm * p.cc.sy + p.cc.sz);
+        pr = ld2(p.Prc + s.cc);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { L.t[c] = ld2(p.tc[c] + s.cc); L.o[c] = ld2(p.to[c] + s.cc); }
-        L.t[3] = ld2(p.tc[3] + s.vv); L.o[3] = ld2(p.to[3] + s.vv);
-        L.t[4] = ld2(p.tc[4] + s.vc); L.o[4] = ld2(p.to[4] + s.vc);
-        L.t[5] = ld2(p.tc[5] + s.cv); L.o[5] = ld2(p.to[5] + s.cv);
+        for (int c = 0; c < 3; ++c) { t[c] = ld2(p.tc[c] + s.cc); o[c] = ld2(p.to[c] + s.cc); }
+        t[3] = ld2(p.tc[3] + s.vv); o[3] = ld2(p.to[3] + s.vv);
+        t[4] = ld2(p.tc[4] + s.vc); o[4] = ld2(p.to[4] + s.vc);
+        t[5] = ld2(p.tc[5] + s.cv); o[5] = ld2(p.to[5] + s.cv);
     } else {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) { L.t[c] = z2; L.o[c] = z2; }
+        for (int c = 0; c < 6; ++c) { t[c] = z2; o[c] = z2; }
     }
-}
-
-// EARLY: the part of the stress residual that needs no velocity is evaluated first (the lagged march requests the velocity
-// operands last); same operations in the same order either way.
-template <bool TD, bool EARLY>
-FHD void fsv_compute_a(FusedT& s, const FusedP& p, int kp, const FusedL& L, d2 sn[FSV_NF]) {
-    const d2 z2 = fsv_zero();
-    const d2 *t = L.t, *o = L.o;
-    double ab[2][6];
-    if (EARLY) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int c = 0; c < 6; ++c) {
-                const double tc = h ? t[c].y : t[c].x, oc = h ? o[c].y : o[c].x;
-                ab[h][c] = div_u<TD>(-(tc - oc), p.Gdt) - div_u<TD>(tc, p.eta);
-            }
-    }
-    const d2 vx = L.vx, vxjm = L.vxjm, vy = L.vy, vyjp = L.vyjp, vzkp = L.vzkp, vzjmkp = L.vzjmkp, pr = L.pr;
     // Vx[i+2], Vy[i-1], Vz[i-1]: lanes 31 / 0 get a don't-care value (their outer cell's stresses are never used)
     const bool okr = s.s_act && s.lane < FSV_LANES - 1, okl = s.s_act && s.lane > 0;
     const double vx_ip2 = fsv_from_right(vx.x, p.Vc[0] + s.vc + 2, okr);
@@ -346,7 +298,7 @@ FHD void fsv_compute_a(FusedT& s, const FusedP& p, int kp, const FusedL& L, d2 s
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
             const double tc = h ? t[c].y : t[c].x;
-            const double r  = !in ? tc : EARLY ? tc + ((ab[h][c] + e2[c]) * p.eta_ve) * p.dtau_r : fsv_stress_upd<TD>(tc, h ? o[c].y : o[c].x, e2[c], p);
+            const double r  = in ? fsv_stress_upd<TD>(tc, h ? o[c].y : o[c].x, e2[c], p) : tc;
             if (h) tn[c].y = r; else tn[c].x = r;
         }
     }
@@ -375,87 +327,9 @@ FHD void fsv_compute_a(FusedT& s, const FusedP& p, int kp, const FusedL& L, d2 s
     s.vx_k = vx; s.vy_k = vy; s.vz_kp = vzkp; s.vzjm_kp = vzjmkp;
 }
 
-template <bool TD>
-FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
-    FusedL L;
-    fsv_load_a(s, p, L);
-    fsv_compute_a<TD, false>(s, p, kp, L, sn);
-}
-
-// ---- velocity of plane kv (stokes_3d_inc_ve_T.jl:48-57).  pl / below / above: plane kv of the exchange buffers
-// (element 0 of [field][row][cell]) of the CTAs holding this thread's row, row j-1 and row j+1; rb / ra: the row numbers of
-// j-1 / j+1 inside those CTAs.  The operands of the thread's own column come in registers (FusedVin).
-struct FusedVin {
-    d2 pr, tzz;          // new Pr, tau_zz of plane kv
-    d2 prkm, tzzkm;      // ... of plane kv-1
-    d2 txzkp, tyzkp;     // new tau_xz, tau_yz of plane kv+1
-    d2 vx, vy, vz;       // old velocities of plane kv
-};
-FHD int fsv_poff(int tyb, int f, int row) { return (f * tyb + row) * 64; }
-
-template <bool TD, bool FUN>
-FHD void fsv_velocity(const FusedT& s, const FusedP& p, int kv, const FusedVin& in, long long cc, long long vc, long long cv, int tyb,
-                      const double* pl, const double* below, int rb, const double* above, int ra) {
-    const int c2 = 2 * s.lane;
-    const d2 pr = in.pr, tzz = in.tzz;
-    const d2 txx = ld2(pl + fsv_poff(tyb, FSV_XX, s.ty) + c2);
-    const d2 tyy = ld2(pl + fsv_poff(tyb, FSV_YY, s.ty) + c2);
-    const d2 txy = ld2(pl + fsv_poff(tyb, FSV_XY, s.ty) + c2);
-    const d2 txz = ld2(pl + fsv_poff(tyb, FSV_XZ, s.ty) + c2);
-    const d2 tyz = ld2(pl + fsv_poff(tyb, FSV_YZ, s.ty) + c2);
-    const double pr_im1  = pl[fsv_poff(tyb, FSV_PR, s.ty) + c2 - 1];
-    const double txx_im1 = pl[fsv_poff(tyb, FSV_XX, s.ty) + c2 - 1];
-    const double txy_ip2 = pl[fsv_poff(tyb, FSV_XY, s.ty) + c2 + 2];
-    const double txz_ip2 = pl[fsv_poff(tyb, FSV_XZ, s.ty) + c2 + 2];
-    const d2 prjm  = ld2(below + fsv_poff(tyb, FSV_PR, rb) + c2);
-    const d2 tyyjm = ld2(below + fsv_poff(tyb, FSV_YY, rb) + c2);
-    const d2 txyjp = ld2(above + fsv_poff(tyb, FSV_XY, ra) + c2);
-    const d2 tyzjp = ld2(above + fsv_poff(tyb, FSV_YZ, ra) + c2);
-    d2 rho;
-    if (FUN) {
-        const double cz  = coord_dev(p.inc.origin[2], p.inc.spacing[2], p.inc.loc[2], kv) - p.inc.c0[2];
-        const double cz2 = cz * cz;
-        rho.x = (s.sxy0 + cz2) < p.inc.r2 ? p.inc.in : p.inc.out;
-        rho.y = (s.sxy1 + cz2) < p.inc.r2 ? p.inc.in : p.inc.out;
-    } else if (s.nv == 2) {
-        rho = ld2(p.rho + cc);
-    } else {
-        rho.x = p.rho[cc]; rho.y = 0.0;
-    }
-    d2 nrx, nry, nrz, nvx, nvy, nvz;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const double a_pr = h ? pr.y : pr.x, a_prim = h ? pr.x : pr_im1, a_prjm = h ? prjm.y : prjm.x, a_prkm = h ? in.prkm.y : in.prkm.x;
-        const double a_txx = h ? txx.y : txx.x, a_txxim = h ? txx.x : txx_im1;
-        const double a_tyy = h ? tyy.y : tyy.x, a_tyyjm = h ? tyyjm.y : tyyjm.x;
-        const double a_tzz = h ? tzz.y : tzz.x, a_tzzkm = h ? in.tzzkm.y : in.tzzkm.x;
-        const double a_txy = h ? txy.y : txy.x, a_txyjp = h ? txyjp.y : txyjp.x, a_txyip = h ? txy_ip2 : txy.y;
-        const double a_txz = h ? txz.y : txz.x, a_txzkp = h ? in.txzkp.y : in.txzkp.x, a_txzip = h ? txz_ip2 : txz.y;
-        const double a_tyz = h ? tyz.y : tyz.x, a_tyzkp = h ? in.tyzkp.y : in.tyzkp.x, a_tyzjp = h ? tyzjp.y : tyzjp.x;
-        const double rvx = (((-((a_pr - a_prim) * p.idx)) + (a_txx - a_txxim) * p.idx) + (a_txyjp - a_txy) * p.idy) +
-                           (a_txzkp - a_txz) * p.idz;
-        const double rvy = (((-((a_pr - a_prjm) * p.idy)) + (a_tyy - a_tyyjm) * p.idy) + (a_txyip - a_txy) * p.idx) +
-                           (a_tyzkp - a_tyz) * p.idz;
-        const double rvz = ((((-((a_pr - a_prkm) * p.idz)) + (a_tzz - a_tzzkm) * p.idz) + (a_txzip - a_txz) * p.idx) +
-                            (a_tyzjp - a_tyz) * p.idy) - (h ? rho.y : rho.x);
-        const double ux = (h ? in.vx.y : in.vx.x) + div_u<TD>(rvx * p.nudtau, p.eve);
-        const double uy = (h ? in.vy.y : in.vy.x) + div_u<TD>(rvy * p.nudtau, p.eve);
-        const double uz = (h ? in.vz.y : in.vz.x) + div_u<TD>(rvz * p.nudtau, p.eve);
-        if (h) { nrx.y = rvx; nry.y = rvy; nrz.y = rvz; nvx.y = ux; nvy.y = uy; nvz.y = uz; }
-        else   { nrx.x = rvx; nry.x = rvy; nrz.x = rvz; nvx.x = ux; nvy.x = uy; nvz.x = uz; }
-    }
-    if (s.nv == 2) {
-        st2(p.r[0] + vc, nrx); st2(p.r[1] + cv, nry); st2(p.r[2] + cc, nrz);
-        st2(p.Vn[0] + vc, nvx); st2(p.Vn[1] + cv, nvy); st2(p.Vn[2] + cc, nvz);
-    } else {
-        p.r[0][vc] = nrx.x; p.r[1][cv] = nry.x; p.r[2][cc] = nrz.x;
-        p.Vn[0][vc] = nvx.x; p.Vn[1][cv] = nvy.x; p.Vn[2][cc] = nvz.x;
-    }
-}
-
 // ---- phase B: publish the stresses of plane kp, update the velocity of plane kp-1, rotate the carried planes.
 // own / below / above: exchange buffers (element 0 of [buf][field][row][cell]) of the CTAs holding this thread's
-// row, row j-1 and row j+1.
+// row, row j-1 and row j+1; rb / ra: the row numbers of j-1 / j+1 inside those CTAs.
 template <bool TD, bool FUN>
 FHD void fsv_phase_b(FusedT& s, const FusedP& p, int kp, const d2 sn[FSV_NF], int tyb, double* own, const double* below,
                      int rb, const double* above, int ra) {
@@ -464,113 +338,67 @@ FHD void fsv_phase_b(FusedT& s, const FusedP& p, int kp, const d2 sn[FSV_NF], in
 #pragma unroll
     for (int f = 0; f < FSV_NF; ++f) st2(own + fsv_xoff(tyb, cur, f, s.ty) + c2, sn[f]);
     if (s.nv > 0 && kp >= s.k0) {
-        const int pb = fsv_xoff(tyb, prev, 0, 0);
-        FusedVin in;
-        in.pr  = ld2(own + pb + fsv_poff(tyb, FSV_PR, s.ty) + c2);
-        in.tzz = ld2(own + pb + fsv_poff(tyb, FSV_ZZ, s.ty) + c2);
-        if (kp >= s.k0 + 1) {
-            in.prkm = s.pr_km; in.tzzkm = s.tzz_km; in.txzkp = sn[FSV_XZ]; in.tyzkp = sn[FSV_YZ];
-            in.vx = s.vx_km; in.vy = s.vy_km; in.vz = s.vz_km;
-            fsv_velocity<TD, FUN>(s, p, kp - 1, in, s.cc - p.cc.sz, s.vc - p.vc.sz, s.cv - p.cv.sz, tyb, own + pb, below + pb, rb, above + pb, ra);
+        const d2 pr  = ld2(own + fsv_xoff(tyb, prev, FSV_PR, s.ty) + c2);
+        const d2 tzz = ld2(own + fsv_xoff(tyb, prev, FSV_ZZ, s.ty) + c2);
+        if (kp >= s.k0 + 1) {   // velocity of plane k = kp-1   (stokes_3d_inc_ve_T.jl:48-57)
+            const d2 txx = ld2(own + fsv_xoff(tyb, prev, FSV_XX, s.ty) + c2);
+            const d2 tyy = ld2(own + fsv_xoff(tyb, prev, FSV_YY, s.ty) + c2);
+            const d2 txy = ld2(own + fsv_xoff(tyb, prev, FSV_XY, s.ty) + c2);
+            const d2 txz = ld2(own + fsv_xoff(tyb, prev, FSV_XZ, s.ty) + c2);
+            const d2 tyz = ld2(own + fsv_xoff(tyb, prev, FSV_YZ, s.ty) + c2);
+            const double pr_im1  = own[fsv_xoff(tyb, prev, FSV_PR, s.ty) + c2 - 1];
+            const double txx_im1 = own[fsv_xoff(tyb, prev, FSV_XX, s.ty) + c2 - 1];
+            const double txy_ip2 = own[fsv_xoff(tyb, prev, FSV_XY, s.ty) + c2 + 2];
+            const double txz_ip2 = own[fsv_xoff(tyb, prev, FSV_XZ, s.ty) + c2 + 2];
+            const d2 prjm  = ld2(below + fsv_xoff(tyb, prev, FSV_PR, rb) + c2);
+            const d2 tyyjm = ld2(below + fsv_xoff(tyb, prev, FSV_YY, rb) + c2);
+            const d2 txyjp = ld2(above + fsv_xoff(tyb, prev, FSV_XY, ra) + c2);
+            const d2 tyzjp = ld2(above + fsv_xoff(tyb, prev, FSV_YZ, ra) + c2);
+            const d2 txzkp = sn[FSV_XZ], tyzkp = sn[FSV_YZ];
+            const long long cc = s.cc - p.cc.sz, vc = s.vc - p.vc.sz, cv = s.cv - p.cv.sz;
+            d2 rho;
+            if (FUN) {
+                const double cz  = coord_dev(p.inc.origin[2], p.inc.spacing[2], p.inc.loc[2], kp - 1) - p.inc.c0[2];
+                const double cz2 = cz * cz;
+                rho.x = (s.sxy0 + cz2) < p.inc.r2 ? p.inc.in : p.inc.out;
+                rho.y = (s.sxy1 + cz2) < p.inc.r2 ? p.inc.in : p.inc.out;
+            } else if (s.nv == 2) {
+                rho = ld2(p.rho + cc);
+            } else {
+                rho.x = p.rho[cc]; rho.y = 0.0;
+            }
+            d2 nrx, nry, nrz, nvx, nvy, nvz;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double a_pr = h ? pr.y : pr.x, a_prim = h ? pr.x : pr_im1, a_prjm = h ? prjm.y : prjm.x, a_prkm = h ? s.pr_km.y : s.pr_km.x;
+                const double a_txx = h ? txx.y : txx.x, a_txxim = h ? txx.x : txx_im1;
+                const double a_tyy = h ? tyy.y : tyy.x, a_tyyjm = h ? tyyjm.y : tyyjm.x;
+                const double a_tzz = h ? tzz.y : tzz.x, a_tzzkm = h ? s.tzz_km.y : s.tzz_km.x;
+                const double a_txy = h ? txy.y : txy.x, a_txyjp = h ? txyjp.y : txyjp.x, a_txyip = h ? txy_ip2 : txy.y;
+                const double a_txz = h ? txz.y : txz.x, a_txzkp = h ? txzkp.y : txzkp.x, a_txzip = h ? txz_ip2 : txz.y;
+                const double a_tyz = h ? tyz.y : tyz.x, a_tyzkp = h ? tyzkp.y : tyzkp.x, a_tyzjp = h ? tyzjp.y : tyzjp.x;
+                const double rvx = (((-((a_pr - a_prim) * p.idx)) + (a_txx - a_txxim) * p.idx) + (a_txyjp - a_txy) * p.idy) +
+                                   (a_txzkp - a_txz) * p.idz;
+                const double rvy = (((-((a_pr - a_prjm) * p.idy)) + (a_tyy - a_tyyjm) * p.idy) + (a_txyip - a_txy) * p.idx) +
+                                   (a_tyzkp - a_tyz) * p.idz;
+                const double rvz = ((((-((a_pr - a_prkm) * p.idz)) + (a_tzz - a_tzzkm) * p.idz) + (a_txzip - a_txz) * p.idx) +
+                                    (a_tyzjp - a_tyz) * p.idy) - (h ? rho.y : rho.x);
+                const double ux = (h ? s.vx_km.y : s.vx_km.x) + div_u<TD>(rvx * p.nudtau, p.eve);
+                const double uy = (h ? s.vy_km.y : s.vy_km.x) + div_u<TD>(rvy * p.nudtau, p.eve);
+                const double uz = (h ? s.vz_km.y : s.vz_km.x) + div_u<TD>(rvz * p.nudtau, p.eve);
+                if (h) { nrx.y = rvx; nry.y = rvy; nrz.y = rvz; nvx.y = ux; nvy.y = uy; nvz.y = uz; }
+                else   { nrx.x = rvx; nry.x = rvy; nrz.x = rvz; nvx.x = ux; nvy.x = uy; nvz.x = uz; }
+            }
+            if (s.nv == 2) {
+                st2(p.r[0] + vc, nrx); st2(p.r[1] + cv, nry); st2(p.r[2] + cc, nrz);
+                st2(p.Vn[0] + vc, nvx); st2(p.Vn[1] + cv, nvy); st2(p.Vn[2] + cc, nvz);
+            } else {
+                p.r[0][vc] = nrx.x; p.r[1][cv] = nry.x; p.r[2][cc] = nrz.x;
+                p.Vn[0][vc] = nvx.x; p.Vn[1][cv] = nvy.x; p.Vn[2][cc] = nvz.x;
+            }
         }
-        s.pr_km = in.pr; s.tzz_km = in.tzz;
+        s.pr_km = pr; s.tzz_km = tzz;
     }
     s.vx_km = s.vx_k; s.vy_km = s.vy_k; s.vz_km = s.vz_k; s.vz_k = s.vz_kp; s.vzjm = s.vzjm_kp;
-    s.cc += p.cc.sz; s.vc += p.vc.sz; s.cv += p.cv.sz; s.vv += p.vv.sz;
-}
-
-// ---- the lagged march: the velocity of plane kp-2 is updated while the loads of plane kp are in flight.
-// Iteration kp: issue the loads of plane kp (fsv_load_a) | velocity of plane kp-2 (its operands come from shared memory and two
-// carried pairs, so the registers are free for the loads in flight) | barrier arrive | stresses of plane kp (fsv_compute_a) |
-// barrier wait | publish them in the exchange buffer of plane kp's parity (plane kp-2 has just been consumed).
-// The barrier orders  publish(P) -> arrive(P+1) .. wait(P+1) -> velocity(P) at iteration P+2   (the values are there)  and
-// velocity(P) at P+2 -> arrive(P+2) .. wait(P+2) -> publish(P+2)   (the slot is free); both halves of the split barrier have a
-// phase of work between them, so warps of a cluster may drift by a phase without waiting for each other.
-// Shared memory of one CTA: the exchange buffer of the plain march ([2 parities][FSV_NF][TYB rows][64 cells]) and a
-// thread-private stash of old velocities, [7 entries][threads of the CTA] pairs: VX, VY of planes kp-2 / kp-1 (by plane parity;
-// plane kp replaces kp-2 after the velocity update has read it), VZ of planes kp-2..kp (plane mod 3; kp+1 replaces kp-2).
-// Keeping this footprint small matters: what the sweep does not take as shared memory is L1, which holds the lines of the loads
-// in flight (measured, profiles/r2_c27_carveout.log: the plain march loses 11 % with 92 KB of L1 and 48 % with 60 KB).
-enum { FSV_ST_VX = 0, FSV_ST_VY = 2, FSV_ST_VZ = 4, FSV_ST_N = 7 };
-static inline size_t fsv_lag_smem_bytes(int tyb) {
-    return fsv_smem_bytes(tyb) + (size_t)FSV_ST_N * tyb * FSV_LANES * 2 * sizeof(double);
-}
-FHD int fsv_lag_stash_off(int tyb) { return 2 * FSV_NF * tyb * 64; }
-// stash: element 0 of this thread's entries (stride between entries: 2 * threads per CTA doubles)
-FHD d2 fsv_st_get(const double* st, int tyb, int e) { return ld2(st + (size_t)e * (2 * tyb * FSV_LANES)); }
-FHD void fsv_st_put(double* st, int tyb, int e, d2 v) { st2(st + (size_t)e * (2 * tyb * FSV_LANES), v); }
-
-// before the march: what iteration k0-1 reads from the stash (VX / VY of plane k0-2 are never needed: zeros)
-FHD void fsv_lag_init(FusedT& s, double* st, int tyb, int a /* (k0-1) mod 3 */) {
-    fsv_st_put(st, tyb, FSV_ST_VX + (s.k0 & 1), fsv_zero());
-    fsv_st_put(st, tyb, FSV_ST_VY + (s.k0 & 1), fsv_zero());
-    fsv_st_put(st, tyb, FSV_ST_VZ + a, s.vz_k);
-}
-
-// the velocity operands of plane kp for the lagged march: as fsv_load_v, but Vz of row j-1 is read in plane kp itself (the row
-// below fetched that line one iteration ago as its plane kp+1: an L2 hit) instead of being carried through an iteration
-FHD d2 fsv_lag_load_v(const FusedT& s, const FusedP& p, FusedL& L) {
-    const d2 z2 = fsv_zero();
-    d2 vzjm = z2;
-    L.vx = z2; L.vxjm = z2; L.vy = z2; L.vyjp = z2; L.vzkp = z2; L.vzjmkp = z2;
-    if (!s.s_act) return vzjm;
-    L.vx   = ld2(p.Vc[0] + s.vc);
-    L.vy   = ld2(p.Vc[1] + s.cv);
-    L.vzkp = ld2(p.Vc[2] + s.cc + p.cc.sz);
-    if (s.role != 1) {
-        L.vxjm = ld2(p.Vc[0] + s.vc - (long long)s.jm * p.vc.sy);
-        vzjm   = ld2(p.Vc[2] + s.cc - (long long)s.jm * p.cc.sy);
-    }
-    if (s.role != 2) L.vyjp = ld2(p.Vc[1] + s.cv + (long long)s.jp * p.cv.sy);
-    return vzjm;
-}
-
-// velocity of plane kv = kp-2 (a = kp mod 3).  Plane kv-1's Pr / tau_zz are carried in s.pr_km / s.tzz_km.
-template <bool TD, bool FUN>
-FHD void fsv_lag_velocity(FusedT& s, const FusedP& p, int kp, int a, int tyb, const double* own, const double* below, int rb,
-                          const double* above, int ra, const double* st) {
-    const int kv = kp - 2;
-    if (s.nv == 0 || kv < s.k0 - 1) return;
-    const int c2 = 2 * s.lane;
-    const int pv = fsv_xoff(tyb, kv & 1, 0, 0), pp = fsv_xoff(tyb, (kv & 1) ^ 1, 0, 0);
-    FusedVin in;
-    in.pr  = ld2(own + pv + fsv_poff(tyb, FSV_PR, s.ty) + c2);
-    in.tzz = ld2(own + pv + fsv_poff(tyb, FSV_ZZ, s.ty) + c2);
-    if (kv >= s.k0) {
-        const int ap1 = a == 2 ? 0 : a + 1;
-        in.prkm = s.pr_km; in.tzzkm = s.tzz_km;
-        in.txzkp = ld2(own + pp + fsv_poff(tyb, FSV_XZ, s.ty) + c2);
-        in.tyzkp = ld2(own + pp + fsv_poff(tyb, FSV_YZ, s.ty) + c2);
-        in.vx = fsv_st_get(st, tyb, FSV_ST_VX + (kv & 1));
-        in.vy = fsv_st_get(st, tyb, FSV_ST_VY + (kv & 1));
-        in.vz = fsv_st_get(st, tyb, FSV_ST_VZ + ap1);
-        fsv_velocity<TD, FUN>(s, p, kv, in, s.cc - 2 * (long long)p.cc.sz, s.vc - 2 * (long long)p.vc.sz, s.cv - 2 * (long long)p.cv.sz, tyb,
-                              own + pv, below + pv, rb, above + pv, ra);
-    }
-    s.pr_km = in.pr; s.tzz_km = in.tzz;
-}
-
-// stresses of plane kp from the loads issued earlier (registers only: nothing shared is written)
-template <bool TD>
-FHD void fsv_lag_stress(FusedT& s, const FusedP& p, int kp, int a, const FusedL& L, d2 vzjm, int tyb, const double* st, d2 sn[FSV_NF]) {
-    s.vx_km = fsv_st_get(st, tyb, FSV_ST_VX + ((kp & 1) ^ 1));
-    s.vy_km = fsv_st_get(st, tyb, FSV_ST_VY + ((kp & 1) ^ 1));
-    s.vz_k  = fsv_st_get(st, tyb, FSV_ST_VZ + a);
-    s.vzjm  = vzjm;
-    fsv_compute_a<TD, true>(s, p, kp, L, sn);
-}
-
-// publishes the stresses of plane kp and stashes the velocities later iterations need
-FHD void fsv_lag_publish(const FusedT& s, int kp, int a, const d2 sn[FSV_NF], int tyb, double* own, double* st) {
-    const int ap1 = a == 2 ? 0 : a + 1;
-    const int c2 = 2 * s.lane;
-#pragma unroll
-    for (int f = 0; f < FSV_NF; ++f) st2(own + fsv_xoff(tyb, kp & 1, f, s.ty) + c2, sn[f]);
-    fsv_st_put(st, tyb, FSV_ST_VX + (kp & 1), s.vx_k);
-    fsv_st_put(st, tyb, FSV_ST_VY + (kp & 1), s.vy_k);
-    fsv_st_put(st, tyb, FSV_ST_VZ + ap1, s.vz_kp);
-}
-
-FHD void fsv_lag_advance(FusedT& s, const FusedP& p) {
     s.cc += p.cc.sz; s.vc += p.vc.sz; s.cv += p.cv.sz; s.vv += p.vv.sz;
 }

@@ -18,68 +18,7 @@ __device__ __forceinline__ void fsv_cluster_arrive_relaxed() {
     asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ void fsv_fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
-__device__ __forceinline__ void fsv_cluster_arrive_norel() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
-
-// Neighbour handshake through mbarriers (variant bit 2) instead of the cluster barrier.  A warp synchronises with exactly the
-// warps whose rows it reads or is read by: the other warps of its CTA through one mbarrier every warp of the CTA arrives at
-// and waits for, and -- the first / last warp of a CTA only -- the adjacent warp of the neighbouring CTA through "edge"
-// mbarriers of count 1 in the reader's shared memory (the writer arrives remotely).  An edge barrier is not waited for by the
-// warp that arrives at it, so that warp may be one step ahead of the waiter: edges come in pairs used by alternate steps
-// (step n+2 of the arriver needs step n+1 of the waiter, which follows its wait of step n).
-// Waiting is an acquire at CTA scope: shared memory, local or distributed, is not cached, so nothing has to be invalidated,
-// whereas barrier.cluster.wait.acquire empties L1 every plane (CCTL.IVALL in the SASS) -- the lines of register spills and of
-// the operands a neighbouring row has just fetched included.
-struct FsvHs {
-    unsigned bar;            // shared::cta address of: [0] the CTA barrier, [1..2] edge from below, [3..4] edge from above
-    unsigned lo, hi;         // shared::cluster address of the barrier block of the CTAs below / above (0: none)
-    unsigned na, nw;         // steps arrived / waited
-};
-constexpr int FSV_HS_BYTES = 64;
-__device__ __forceinline__ void fsv_hs_init(FsvHs& h, void* mem, int cr, int cl, int tyb) {
-    h.bar = (unsigned)__cvta_generic_to_shared(mem);
-    h.lo = h.hi = 0u;
-    h.na = h.nw = 0u;
-    if (cr > 0) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(h.lo) : "r"(h.bar), "r"(cr - 1));
-    if (cr < cl - 1) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(h.hi) : "r"(h.bar), "r"(cr + 1));
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(h.bar), "r"((unsigned)tyb));
-        for (unsigned e = 1; e <= 4; ++e) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(h.bar + 8u * e), "r"(1u));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    // nobody arrives at a barrier that is not initialised yet
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// FENCE: the warp's shared-memory writes are performed before the arrive (without it the caller has fenced already)
-template <bool FENCE>
-__device__ __forceinline__ void fsv_hs_arrive(FsvHs& h, int lane, int ty, int tyb) {
-    __syncwarp();
-    if (lane == 0) {
-        if (FENCE) asm volatile("fence.acq_rel.cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(h.bar) : "memory");
-        const unsigned e = h.na & 1u;
-        // my first row is read by (and reads) the last row of the CTA below: I am "from above" there; and vice versa
-        if (ty == 0 && h.lo) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(h.lo + 8u * (3u + e)) : "memory");
-        if (ty == tyb - 1 && h.hi) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(h.hi + 8u * (1u + e)) : "memory");
-    }
-    h.na += 1u;
-}
-__device__ __forceinline__ void fsv_mbar_wait(unsigned bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "FSV_HS_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@!p bra FSV_HS_WAIT;\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fsv_hs_wait(FsvHs& h, int ty, int tyb) {
-    const unsigned n = h.nw, e = n & 1u;
-    fsv_mbar_wait(h.bar, e);
-    if (ty == 0 && h.lo) fsv_mbar_wait(h.bar + 8u * (1u + e), (n >> 1) & 1u);
-    if (ty == tyb - 1 && h.hi) fsv_mbar_wait(h.bar + 8u * (3u + e), (n >> 1) & 1u);
-    h.nw = n + 1u;
-}
-
-template <bool TD, bool FUN, int TYB, bool MB>
+template <bool TD, bool FUN, int TYB>
 __global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 4 ? 3 : 2)) k_fused_sv(const FusedP p, const int cl, const int variant) {
     extern __shared__ __align__(16) double xb[];
     const int lane = threadIdx.x, ty = threadIdx.y;
@@ -99,77 +38,18 @@ __global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 4 ? 3 : 2)) k_fused_sv
     const bool boundary = tile_decode(p.order, (int)blockIdx.x, bx, cyc, bz);     // grid = (clusters, CTAs per cluster, 1)
     FusedT s;
     fsv_init(s, p, lane, ty, cr * TYB + ty, bx, cyc, bz, FUN);
-    FsvHs hs;
-    const bool mb = MB && cl > 1;
-    if (mb) {
-        fsv_hs_init(hs, xb + 2 * FSV_NF * TYB * 64, cr, cl, TYB);
-        fsv_hs_arrive<false>(hs, lane, ty, TYB);
-    } else if (cl > 1) {
-        fsv_cluster_arrive();
-    }
+    if (cl > 1) fsv_cluster_arrive();
     for (int kp = s.k0 - 1; kp <= s.k1; ++kp) {
         d2 sn[FSV_NF];
         fsv_phase_a<TD>(s, p, kp, sn);
         // every thread of the cluster has finished reading the buffer that is about to be overwritten, and the
         // stresses of plane kp-1 that phase B reads have been published
-        if (mb) fsv_hs_wait(hs, ty, TYB); else if (cl > 1) fsv_cluster_wait(); else __syncthreads();
+        if (cl > 1) fsv_cluster_wait(); else __syncthreads();
         fsv_phase_b<TD, FUN>(s, p, kp, sn, TYB, xb, below, rb, above, ra);
-        if (mb) fsv_hs_arrive<true>(hs, lane, ty, TYB);
-        else if (cl > 1) { if (relaxed) fsv_cluster_arrive_relaxed(); else fsv_cluster_arrive(); }
+        if (cl > 1) { if (relaxed) fsv_cluster_arrive_relaxed(); else fsv_cluster_arrive(); }
     }
-    if (mb) { fsv_hs_wait(hs, ty, TYB); fsv_cluster_arrive(); }
     if (cl > 1) fsv_cluster_wait();   // no CTA may exit while a neighbour can still read its shared memory
     if (boundary && p.done) {         // tell the boundary stream: this CTA's part of the outer cells is in memory
-        __syncthreads();
-        if (lane == 0 && ty == 0) { __threadfence(); atomicAdd(p.done, 1u); }
-    }
-}
-
-// The lagged march (fused_sv.cuh): loads of plane kp | velocity of plane kp-2 | arrive | stresses of plane kp | wait | publish.
-template <bool TD, bool FUN, int TYB, bool MB>
-__global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 4 ? 3 : 2)) k_fused_sv_lag(const FusedP p, const int cl, const int variant) {
-    extern __shared__ __align__(16) double xb[];
-    const int lane = threadIdx.x, ty = threadIdx.y;
-    int cr = 0;
-    const double *below = xb, *above = xb;
-    int rb = ty, ra = ty;
-    if (ty > 0) rb = ty - 1;
-    if (ty < TYB - 1) ra = ty + 1;
-    if (cl > 1) {
-        cg::cluster_group cluster = cg::this_cluster();
-        cr = (int)cluster.block_rank();
-        if (ty == 0 && cr > 0) { below = cluster.map_shared_rank(xb, cr - 1); rb = TYB - 1; }
-        if (ty == TYB - 1 && cr < cl - 1) { above = cluster.map_shared_rank(xb, cr + 1); ra = 0; }
-    }
-    int bx, cyc, bz;
-    const bool boundary = tile_decode(p.order, (int)blockIdx.x, bx, cyc, bz);
-    FusedT s;
-    fsv_init(s, p, lane, ty, cr * TYB + ty, bx, cyc, bz, FUN);
-    double* st = xb + fsv_lag_stash_off(TYB) + 2 * (ty * FSV_LANES + lane);
-    int a = (s.k0 - 1) % 3;
-    if (a < 0) a += 3;
-    fsv_lag_init(s, st, TYB, a);
-    FsvHs hs;
-    const bool mb = MB && cl > 1;
-    if (mb) fsv_hs_init(hs, xb + fsv_lag_stash_off(TYB) + FSV_ST_N * TYB * FSV_LANES * 2, cr, cl, TYB);
-    for (int kp = s.k0 - 1; kp <= s.k1 + 1; ++kp) {
-        const bool stress = kp <= s.k1;
-        FusedL L;
-        d2 sn[FSV_NF], vzjm = fsv_zero();
-        if (stress) fsv_load_tau(s, p, L);
-        fsv_lag_velocity<TD, FUN>(s, p, kp, a, TYB, xb, below, rb, above, ra, st);
-        if (stress) vzjm = fsv_lag_load_v(s, p, L);
-        if (mb) fsv_hs_arrive<false>(hs, lane, ty, TYB); else if (cl > 1) fsv_cluster_arrive_norel();
-        if (stress) fsv_lag_stress<TD>(s, p, kp, a, L, vzjm, TYB, st, sn);
-        if (mb) fsv_hs_wait(hs, ty, TYB); else if (cl > 1) fsv_cluster_wait(); else __syncthreads();
-        if (stress) fsv_lag_publish(s, kp, a, sn, TYB, xb, st);
-        if (cl > 1) fsv_fence_cta();      // the published values are in this SM's shared memory before the next arrive
-        fsv_lag_advance(s, p);
-        a = a == 2 ? 0 : a + 1;
-    }
-    if (cl > 1) fsv_cluster_arrive();
-    if (cl > 1) fsv_cluster_wait();   // no CTA may exit while a neighbour can still read its shared memory
-    if (boundary && p.done) {
         __syncthreads();
         if (lane == 0 && ty == 0) { __threadfence(); atomicAdd(p.done, 1u); }
     }
@@ -247,25 +127,14 @@ extern "C" int chmy_set_fused_tuning(chmy_ctx* ctx, int rows_per_cta, int cluste
 
 template <bool TD, bool FUN, int TYB>
 static int launch_fused(const FusedP& p, int cl, int variant, dim3 grid, cudaStream_t st) {
-    const bool lag = (variant & 2) != 0, mbar = (variant & 4) != 0;
-    void (*kern)(const FusedP, const int, const int) =
-        lag ? (mbar ? k_fused_sv_lag<TD, FUN, TYB, true> : k_fused_sv_lag<TD, FUN, TYB, false>)
-            : (mbar ? k_fused_sv<TD, FUN, TYB, true> : k_fused_sv<TD, FUN, TYB, false>);
-    const size_t smem = (lag ? fsv_lag_smem_bytes(TYB) : fsv_smem_bytes(TYB)) + (mbar ? FSV_HS_BYTES : 0);
-    static bool attr_done[4][64] = {};   // per instantiation and device (function attributes are per device)
+    void (*kern)(const FusedP, const int, const int) = k_fused_sv<TD, FUN, TYB>;
+    const size_t smem = fsv_smem_bytes(TYB);
+    static bool attr_done[64] = {};   // per instantiation and device (function attributes are per device)
     int dev = 0;
     CHMY_CUDA(cudaGetDevice(&dev));
-    const int which = (lag ? 1 : 0) + (mbar ? 2 : 0);
-    if (dev < 0 || dev >= 64 || !attr_done[which][dev]) {
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (const char* e = getenv("CHMY_FUSE_CARVEOUT"))      // percent of the SM's shared memory (experiments: what is left is L1)
-            CHMY_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
-        if (getenv("CHMY_DEBUG_OCC")) {
-            int nb = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, FSV_LANES * TYB, smem);
-            fprintf(stderr, "[chmy] fused sweep lag=%d rows=%d smem=%zu B: %d CTAs per SM\n", (int)lag, TYB, smem, nb);
-        }
-        if (dev >= 0 && dev < 64) attr_done[which][dev] = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;

@@ -48,71 +48,11 @@ static void run(const FusedP& p, int tyb, int cl) {
             }
 }
 
-// the lagged march (k_fused_sv_lag): per iteration, every thread loads plane kp, updates the velocity of plane kp-2 and computes
-// the stresses of plane kp | barrier | every thread publishes plane kp (replacing plane kp-3, which nobody reads any more)
-template <bool TD, bool FUN>
-static void run_lag(const FusedP& p, int tyb, int cl) {
-    const int nx = p.hi[0] - p.lo[0], ny = p.hi[1] - p.lo[1], nz = p.hi[2] - p.lo[2];
-    const int gx = (nx + FSV_XI - 1) / FSV_XI, gyc = (ny + p.rows_int - 1) / p.rows_int, gz = (nz + p.cz - 1) / p.cz;
-    const int nthr = cl * tyb * FSV_LANES;
-    const size_t per_cta = fsv_lag_smem_bytes(tyb) / sizeof(double);
-    std::vector<FusedT> T(nthr);
-    std::vector<FusedL> LD(nthr);
-    std::vector<d2> SN((size_t)nthr * FSV_NF);
-    std::vector<double> smem(per_cta * cl);
-    for (int bz = 0; bz < gz; ++bz)
-        for (int cyc = 0; cyc < gyc; ++cyc)
-            for (int bx = 0; bx < gx; ++bx) {
-                for (auto& v : smem) v = std::numeric_limits<double>::quiet_NaN();
-                int a = 0;
-                for (int cr = 0; cr < cl; ++cr)
-                    for (int ty = 0; ty < tyb; ++ty)
-                        for (int lane = 0; lane < FSV_LANES; ++lane) {
-                            FusedT& s = T[(cr * tyb + ty) * FSV_LANES + lane];
-                            fsv_init(s, p, lane, ty, cr * tyb + ty, bx, cyc, bz, FUN);
-                            a = (s.k0 - 1) % 3;
-                            if (a < 0) a += 3;
-                            fsv_lag_init(s, &smem[per_cta * cr] + fsv_lag_stash_off(tyb) + 2 * (ty * FSV_LANES + lane), tyb, a);
-                        }
-                const int k0 = T[0].k0, k1 = T[0].k1;
-                for (int kp = k0 - 1; kp <= k1 + 1; ++kp) {
-                    const bool stress = kp <= k1;
-                    for (int pass = 0; pass < 2; ++pass)        // pass 0: up to the barrier wait, pass 1: after it
-                        for (int cr = 0; cr < cl; ++cr)
-                            for (int ty = 0; ty < tyb; ++ty) {
-                                double* own = &smem[per_cta * cr];
-                                const double *below = own, *above = own;
-                                int rb = ty, ra = ty;
-                                if (ty > 0) rb = ty - 1;
-                                else if (cr > 0) { below = &smem[per_cta * (cr - 1)]; rb = tyb - 1; }
-                                if (ty < tyb - 1) ra = ty + 1;
-                                else if (cr < cl - 1) { above = &smem[per_cta * (cr + 1)]; ra = 0; }
-                                for (int lane = 0; lane < FSV_LANES; ++lane) {
-                                    const int t = (cr * tyb + ty) * FSV_LANES + lane;
-                                    double* st = own + fsv_lag_stash_off(tyb) + 2 * (ty * FSV_LANES + lane);
-                                    if (pass == 0) {
-                                        d2 vzjm = fsv_zero();
-                                        if (stress) fsv_load_tau(T[t], p, LD[t]);
-                                        fsv_lag_velocity<TD, FUN>(T[t], p, kp, a, tyb, own, below, rb, above, ra, st);
-                                        if (stress) vzjm = fsv_lag_load_v(T[t], p, LD[t]);
-                                        if (stress) fsv_lag_stress<TD>(T[t], p, kp, a, LD[t], vzjm, tyb, st, &SN[(size_t)t * FSV_NF]);
-                                    } else {
-                                        if (stress) fsv_lag_publish(T[t], kp, a, &SN[(size_t)t * FSV_NF], tyb, own, st);
-                                        fsv_lag_advance(T[t], p);
-                                    }
-                                }
-                            }
-                    a = a == 2 ? 0 : a + 1;
-                }
-            }
-}
-
 // ptrs: tc[6] to[6] Prc Vc[3] rho tn[6] Prn dV Vn[3] r[3]  (31 pointers at logical (0,0,0); rho may be NULL)
 // strides: cc.sy cc.sz vc.sy vc.sz cv.sy cv.sz vv.sy vv.sz ; box: lo[3] hi[3] flo[3] fhi[3]
 // sc: idx idy idz eta_ve dtau_Pr dtau_r nudtau Gdt eta ; inc: origin[3] spacing[3] c0[3] r2 in out
 extern "C" int fused_emul_run(double** ptrs, const int* strides, const int* box, const double* sc, const double* inc,
-                              const int* incloc, int cz, int tyb, int cl, int flags /* bit 0: true division, bit 1: lagged march */) {
-    const int td = flags & 1, lag = flags & 2;
+                              const int* incloc, int cz, int tyb, int cl, int td) {
     FusedP p;
     memset(&p, 0, sizeof(p));
     int q = 0;
@@ -140,11 +80,6 @@ extern "C" int fused_emul_run(double** ptrs, const int* strides, const int* box,
     p.cz = cz; p.rows_int = cl * tyb - 2;
     if (p.lo[0] & 1) return -1;
     const bool fun = p.rho == nullptr;
-    if (lag) {
-        if (td) { if (fun) run_lag<true, true>(p, tyb, cl); else run_lag<true, false>(p, tyb, cl); }
-        else    { if (fun) run_lag<false, true>(p, tyb, cl); else run_lag<false, false>(p, tyb, cl); }
-        return 0;
-    }
     if (td) { if (fun) run<true, true>(p, tyb, cl); else run<true, false>(p, tyb, cl); }
     else    { if (fun) run<false, true>(p, tyb, cl); else run<false, false>(p, tyb, cl); }
     return 0;

@@ -56,7 +56,7 @@ class Pitched:
         return q
 
 
-def run_case(o, emul, n, box, cz, tyb, cl, td, fun, seed=0, lag=False):
+def run_case(o, emul, n, box, cz, tyb, cl, td, fun, seed=0):
     rng = np.random.default_rng(seed)
     g = o.Grid((-1.0, -1.1, -1.2), (2.0, 2.3, 2.6), n)
     tau, tau_old, V, rV = o.TensorField(g), o.TensorField(g), o.VectorField(g), o.VectorField(g)
@@ -95,7 +95,7 @@ def run_case(o, emul, n, box, cz, tyb, cl, td, fun, seed=0, lag=False):
     sc = (C.c_double * 9)(*g.inv_spacing, eta_ve, dtau_Pr, dtau_r, nudtau, G * dt, eta)
     incv = (C.c_double * 12)(*g.origin, *g.spacing, *inc.c0, inc.r * inc.r, inc.inn, inc.out)
     incloc = (C.c_int * 3)(*inc.loc)
-    rc = emul.fused_emul_run(P, strides, bx, sc, incv, incloc, cz, tyb, cl, int(td) | (2 if lag else 0))
+    rc = emul.fused_emul_run(P, strides, bx, sc, incv, incloc, cz, tyb, cl, int(td))
     assert rc == 0
 
     def same(a, b, name):
@@ -157,8 +157,7 @@ CASES = [
 
 @pytest.mark.parametrize("n,box,cz,tyb,cl", CASES)
 @pytest.mark.parametrize("td,fun", [(True, False), (False, True), (False, False), (True, True)])
-@pytest.mark.parametrize("lag", [False, True], ids=["march", "lagged"])
-def test_fused_sweep_equals_stress_then_velocity(oracle, emul, n, box, cz, tyb, cl, td, fun, lag):
+def test_fused_sweep_equals_stress_then_velocity(oracle, emul, n, box, cz, tyb, cl, td, fun):
     if box is None:
         box = ((0, 0, 0), tuple(x + 2 for x in n))
-    run_case(oracle, emul, n, box, cz, tyb, cl, td, fun, seed=sum(n) + cz, lag=lag)
+    run_case(oracle, emul, n, box, cz, tyb, cl, td, fun, seed=sum(n) + cz)
