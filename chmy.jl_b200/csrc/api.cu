@@ -116,6 +116,8 @@ extern "C" int chmy_ctx_create(int device_id, chmy_ctx** out) {
     return CHMY_OK;
 }
 
+static void upload_release(chmy_ctx* c);     // staged uploads, below
+
 extern "C" int chmy_ctx_destroy(chmy_ctx* c) {
     if (!c || !ctx_alive(c)) return CHMY_OK;
     ctx_unregister(c);
@@ -126,6 +128,7 @@ extern "C" int chmy_ctx_destroy(chmy_ctx* c) {
     cudaFree(c->d_red);
     cudaFree(c->d_done);
     cudaFreeHost(c->h_red);
+    upload_release(c);
     if (c->ev_time) {
         for (int i = 0; i < CHMY_MAX_EVENTS; ++i) if (c->ev_time[i]) cudaEventDestroy(c->ev_time[i]);
         free(c->ev_time);
@@ -320,6 +323,77 @@ extern "C" int chmy_field_copy(chmy_ctx* ctx, chmy_field* dst, const chmy_field*
     return chmy_copy_box(ctx, dst, src, b, ctx->s_main);
 }
 
+// ---- staged upload.  A strided (3D) host->device copy of a dense host box into the padded field moves 41 GB/s on the B200
+// box (rows of a few KB each), a contiguous one 55.6 GB/s (profiles/r2_c35_copy_bandwidth.log): large uploads therefore go
+// piecewise and contiguously into one of two device buffers on a copy stream, and a kernel on the main stream scatters each
+// piece into the field while the next piece is in flight.  Device->host already runs at the link's rate (56.8 GB/s).
+template <class T>
+__global__ void __launch_bounds__(256) k_scatter_rows(T* __restrict__ dst, long long s1, long long s2, const T* __restrict__ src, int n0,
+                                                       int n1, int j0, int rows) {
+    // src: `rows` dense rows of n0 elements, row r = (j, k) with j + k * n1 = j0 + r ; dst: element (0, 0, 0) of the box
+    const int r = blockIdx.y;
+    if (r >= rows) return;
+    const long long q = (long long)j0 + r;
+    const long long j = q % n1, k = q / n1;
+    T* d = dst + j * s1 + k * s2;
+    const T* sr = src + (long long)r * n0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0; i += gridDim.x * blockDim.x) d[i] = sr[i];
+}
+
+static const size_t UP_PIECE = (size_t)64 << 20;
+
+static void upload_release(chmy_ctx* c) {
+    for (int b = 0; b < 2; ++b) {
+        if (c->d_up[b]) cudaFree(c->d_up[b]);
+        if (c->ev_up_copied[b]) cudaEventDestroy(c->ev_up_copied[b]);
+        if (c->ev_up_free[b]) cudaEventDestroy(c->ev_up_free[b]);
+        c->d_up[b] = nullptr; c->ev_up_copied[b] = nullptr; c->ev_up_free[b] = nullptr;
+    }
+    if (c->s_up) cudaStreamDestroy(c->s_up);
+    c->s_up = nullptr;
+    c->d_up_bytes = 0;
+}
+
+// false: no staging buffers (out of device memory) -- the caller takes the strided copy
+static bool upload_ready(chmy_ctx* c) {
+    if (c->d_up_bytes) return true;
+    bool ok = cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking) == cudaSuccess;
+    for (int b = 0; b < 2 && ok; ++b)
+        ok = cudaMalloc((void**)&c->d_up[b], UP_PIECE) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_up_copied[b], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_up_free[b], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { (void)cudaGetLastError(); upload_release(c); return false; }
+    c->d_up_bytes = UP_PIECE;
+    return true;
+}
+
+template <class T>
+static int upload_staged_t(chmy_ctx* ctx, const chmy_field* f, const Box& b, const T* host) {
+    const long long n0 = b.n[0], n1 = b.n[1], rows_total = (long long)b.n[1] * b.n[2];
+    const long long rows_per_piece = (long long)(UP_PIECE / ((size_t)n0 * sizeof(T)));
+    T* dst = reinterpret_cast<T*>(f->at_bytes(b.lo[0], f->nd > 1 ? b.lo[1] : 0, f->nd > 2 ? b.lo[2] : 0));
+    int turn = 0;
+    for (long long r0 = 0; r0 < rows_total; r0 += rows_per_piece, turn ^= 1) {
+        const long long rows = rows_total - r0 < rows_per_piece ? rows_total - r0 : rows_per_piece;
+        CHMY_CUDA(cudaStreamWaitEvent(ctx->s_up, ctx->ev_up_free[turn], 0));        // the scatter that read this buffer last
+        CHMY_CUDA(cudaMemcpyAsync(ctx->d_up[turn], host + r0 * n0, (size_t)(rows * n0) * sizeof(T), cudaMemcpyHostToDevice, ctx->s_up));
+        CHMY_CUDA(cudaEventRecord(ctx->ev_up_copied[turn], ctx->s_up));
+        CHMY_CUDA(cudaStreamWaitEvent(ctx->s_main, ctx->ev_up_copied[turn], 0));
+        for (long long q0 = 0; q0 < rows; q0 += 32768) {                              // gridDim.y <= 65535
+            const int nr = (int)(rows - q0 < 32768 ? rows - q0 : 32768);
+            const dim3 grid((unsigned)((n0 + 1023) / 1024 > 0 ? (n0 + 1023) / 1024 : 1), (unsigned)nr);
+            k_scatter_rows<T><<<grid, 256, 0, ctx->s_main>>>(dst, (long long)f->stride[1], (long long)f->stride[2],
+                                                             reinterpret_cast<const T*>(ctx->d_up[turn]) + q0 * n0, (int)n0, (int)n1,
+                                                             (int)(r0 + q0), nr);
+            ctx->n_launches++;
+        }
+        CHMY_CUDA(cudaGetLastError());
+        CHMY_CUDA(cudaEventRecord(ctx->ev_up_free[turn], ctx->s_main));
+    }
+    CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));
+    return CHMY_OK;
+}
+
 // `host` holds elements of the field's type (Array{Float64} | Array{Float32} in the reference's set!/Array)
 static int copy_box_host(chmy_ctx* ctx, const chmy_field* f, void* host, const int64_t* lo, const int64_t* hi, bool to_host) {
     Box b;
@@ -328,6 +402,13 @@ static int copy_box_host(chmy_ctx* ctx, const chmy_field* f, void* host, const i
     CHMY_TRY(chmy_flush(ctx));
     if (!to_host) const_cast<chmy_field*>(f)->frame_dirty(0);
     CHMY_CUDA(cudaSetDevice(ctx->device));
+    // large strided uploads: contiguous pieces + scatter kernel (rows of at most one piece, row index within int range)
+    const size_t row_bytes = (size_t)b.n[0] * (size_t)f->esize, box_bytes = row_bytes * (size_t)b.n[1] * (size_t)b.n[2];
+    if (!to_host && box_bytes >= ((size_t)32 << 20) && row_bytes <= UP_PIECE && (long long)b.n[1] * b.n[2] < (1ll << 31) &&
+        !getenv("CHMY_NO_STAGED_UPLOAD") && upload_ready(ctx)) {
+        return f->dtype == CHMY_F64 ? upload_staged_t<double>(ctx, f, b, static_cast<const double*>(host))
+                                    : upload_staged_t<float>(ctx, f, b, static_cast<const float*>(host));
+    }
     char* dev = f->at_bytes(b.lo[0], f->nd > 1 ? b.lo[1] : 0, f->nd > 2 ? b.lo[2] : 0);
     cudaMemcpy3DParms p;
     memset(&p, 0, sizeof(p));

@@ -180,6 +180,12 @@ struct chmy_ctx {
     unsigned int*     d_done;        // device counter of the boundary-first sweep (ops_fused.cu): CTAs of boundary tiles retired
     uint64_t          batch_sig;     // signature of the batch set being applied right now (0 outside launch / bc!)
     uint64_t          n_overlapped;  // launches whose batches ran behind the boundary tiles of a still-running sweep
+    // staged uploads (api.cu copy_box_host): two device buffers a dense host box is copied into piecewise, contiguously, while
+    // a kernel scatters the previous piece into the padded field
+    char*             d_up[2];
+    size_t            d_up_bytes;
+    cudaStream_t      s_up;
+    cudaEvent_t       ev_up_copied[2], ev_up_free[2];
 };
 
 // api.cu: runs a deferred update_stress! launch now (every entry point that reads or writes device state calls it)

@@ -548,3 +548,33 @@ def test_boundary_function_over_mutable_state_is_re_evaluated(ch, arch):
         state["t"] = 2.0
         ch.bc_(arch, g, (f, {"x": ch.Dirichlet(bf)}))
         assert np.all(ch.interior(f)[0, :] == want), (static, ch.interior(f)[0, :])
+
+
+# ------------------------------------------------------------------------------------------------ large uploads
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,loc,layout", [((200, 180, 160), (0, 1, 0), 0), ((3000, 2100), (1, 0), 0), ((5, 1500, 1400), (0, 0, 1), 0),
+                                          ((210, 170, 150), (1, 1, 1), 1)])
+def test_large_uploads_take_the_staged_path_and_move_the_same_bytes(ch, arch, n, loc, layout, dtype):
+    """set!(f, A) of tens of MB goes through contiguous pieces + a scatter kernel (api.cu, staged upload): interior, a box
+    that includes the halo and an off-centre sub-box all read back bit for bit, and nothing outside the box changes."""
+    nd = len(n)
+    g = ch.UniformGrid(arch, origin=(0.0,) * nd, extent=(1.0,) * nd, dims=n)
+    f = ch.Field(arch, g, bloc(ch, loc), dtype=dtype, layout=layout)
+    rng = np.random.default_rng(5)
+    whole_lo, whole_hi = [-1] * nd, [d + 2 for d in f.dims]
+    base = (rng.random(tuple(d + 4 for d in f.dims)) - 0.5).astype(dtype)
+    f.from_host(base, whole_lo, whole_hi)                                       # the whole padded array
+    assert np.array_equal(f.to_host(whole_lo, whole_hi), base)
+    a = ch.pinned_array(arch, f.dims, dtype=dtype) if dtype == np.float64 else np.asfortranarray(rng.random(f.dims).astype(dtype))
+    a[...] = rng.random(f.dims)
+    ch.set_(f, a)                                                               # the interior
+    want = base.copy()
+    want[(slice(2, -2),) * nd] = a
+    assert np.array_equal(f.to_host(whole_lo, whole_hi), want)
+    lo = [3, 2, 5][:nd]
+    hi = [d - 4 for d in f.dims]
+    if all(h >= l for l, h in zip(lo, hi)):                                      # an off-centre sub-box
+        sub = rng.random(tuple(h - l + 1 for l, h in zip(lo, hi))).astype(dtype)
+        f.from_host(sub, lo, hi)
+        want[tuple(slice(l + 1, h + 2) for l, h in zip(lo, hi))] = sub
+        assert np.array_equal(f.to_host(whole_lo, whole_hi), want)
