@@ -104,15 +104,18 @@ static int run_bc_dim(chmy_ctx* ctx, const chmy_grid_desc* g, int dim, const chm
 }
 
 // ---- all dimensions, sides and fields of a batch set in ONE launch (bc_all_point, bc_kernels.cuh)
+constexpr int BC_ALL_CY = 8;     // face points per thread along the slower face direction
 template <class T>
 __global__ void __launch_bounds__(128) k_bc_all(const BcAllDev<T> b) {
     const int z = b.act[blockIdx.z], s = z & 1, D = (z >> 1) % 3, q = z / 6;
     int nt[2] = {1, 1}, t = 0;
     for (int a = 0; a < b.nd; ++a)
         if (a != D) nt[t++] = b.n[a] + 3;
-    const int a = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
-    if (a >= nt[0] || c >= nt[1]) return;
-    bc_all_point(b, q, D, s, a, c);
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= nt[0]) return;
+    const int c0 = blockIdx.y * BC_ALL_CY, c1 = c0 + BC_ALL_CY < nt[1] ? c0 + BC_ALL_CY : nt[1];
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c) bc_all_point(b, q, D, s, a, c);      // independent points: a few per thread instead of one
 }
 
 // Can the batch set run as one launch?  No exchange anywhere (a halo exchange sits between two dimensions), at most
@@ -177,8 +180,8 @@ static int run_bc_all_t(chmy_ctx* ctx, const chmy_grid_desc* g, const chmy_batch
             if (a != D) e[t++] = (int)g->n[a] + 3;
         m0 = e[0] > m0 ? e[0] : m0; m1 = e[1] > m1 ? e[1] : m1;
     }
-    CHMY_REQUIRE(m1 <= 65535, "face too large for one launch");
-    k_bc_all<T><<<dim3((m0 + 127) / 128, m1, b.nact), 128, 0, st>>>(b);
+    CHMY_REQUIRE((m1 + BC_ALL_CY - 1) / BC_ALL_CY <= 65535, "face too large for one launch");
+    k_bc_all<T><<<dim3((m0 + 127) / 128, (m1 + BC_ALL_CY - 1) / BC_ALL_CY, b.nact), 128, 0, st>>>(b);
     ctx->n_launches++;
     CHMY_CUDA(cudaGetLastError());
     *handled = 1;
