@@ -6,8 +6,14 @@
 
 // ---------------------------------------------------------------------------------------------- exact division
 struct DivC {
-    double c, rc;   // divisor, RN(1/c)
+    double c, rc, rl;   // divisor, RN(1/c), RN(1/c - rc)
 };
+// 1 - c * rc is exactly representable when rc is the correctly rounded reciprocal, so the fma returns it without error
+static inline DivC divc_of(double c) {
+    DivC d;
+    d.c = c; d.rc = 1.0 / c; d.rl = fma(-c, d.rc, 1.0) / c;
+    return d;
+}
 
 static inline bool markstein_ok(double c) {
     unsigned long long b;
@@ -22,10 +28,11 @@ static inline bool markstein_ok(double c) {
 template <bool TRUE_DIV>
 __device__ __forceinline__ double div_u(double x, const DivC d) {
     if (TRUE_DIV) return x / d.c;
-    double q = x * d.rc;
-    double r = fma(-d.c, q, x);
-    q        = fma(r, d.rc, q);
-    r        = fma(-d.c, q, x);
+    // q = RN(x * (rc + rl)) up to 2^-105: within half an ulp (+ that much) of x / c, i.e. a faithful quotient; the residual of a
+    // faithful quotient is exact in an fma, and Markstein's theorem (rc = RN(1/c), significand of c not all ones) makes the
+    // corrected quotient the correctly rounded one.  Four operations (the reciprocal + two corrections sequence took five).
+    const double q = fma(x, d.rc, x * d.rl);
+    const double r = fma(-d.c, q, x);
     return fma(r, d.rc, q);
 }
 

@@ -40,8 +40,13 @@ struct d2 {
     double x, y;
 };
 struct DivC {
-    double c, rc;
+    double c, rc, rl;
 };
+static inline DivC divc_of(double c) {
+    DivC d;
+    d.c = c; d.rc = 1.0 / c; d.rl = std::fma(-c, d.rc, 1.0) / c;
+    return d;
+}
 struct Strides {
     int sy, sz;
 };
@@ -56,10 +61,8 @@ using std::fma;
 template <bool TRUE_DIV>
 static inline double div_u(double x, const DivC d) {
     if (TRUE_DIV) return x / d.c;
-    double q = x * d.rc;
-    double r = fma(-d.c, q, x);
-    q        = fma(r, d.rc, q);
-    r        = fma(-d.c, q, x);
+    const double q = fma(x, d.rc, x * d.rl);
+    const double r = fma(-d.c, q, x);
     return fma(r, d.rc, q);
 }
 static inline double coord_dev(double origin, double spacing, int loc, int i) {

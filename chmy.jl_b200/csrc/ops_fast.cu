@@ -8,8 +8,8 @@
 //     planes of the stencil operands in registers, so each array element is requested from DRAM once;
 //   * x-neighbours come from warp shuffles (the two edge lanes issue one predicated 8-byte load), y-neighbours from
 //     L1 (the neighbouring row of the same CTA requests the same lines in the same step);
-//   * divisions by kernel-uniform scalars (G*dt, eta, 3.0, eta_ve) use the correctly rounded
-//     reciprocal-plus-two-FMA-corrections sequence (Markstein): bit-identical to IEEE division for every
+//   * divisions by kernel-uniform scalars (G*dt, eta, 3.0, eta_ve) use a double-double reciprocal product plus one
+//     Markstein correction (div_u, fast_common.cuh: 4 operations): bit-identical to IEEE division for every
 //     normal-range operand at ~1/10 of the instruction count of the generic div.rn.f64 subroutine.  Divisors whose
 //     significand is all ones, or that are not normal numbers, take the true-division instantiation.
 //
@@ -47,7 +47,7 @@ extern "C" int chmy_selftest_division(chmy_ctx* ctx, double c, long long n, unsi
     if (!*markstein_used) return CHMY_OK;
     CHMY_CUDA(cudaSetDevice(ctx->device));
     CHMY_CUDA(cudaMemsetAsync(ctx->d_red, 0, sizeof(unsigned long long), ctx->s_main));
-    const DivC d{c, 1.0 / c};
+    const DivC d = divc_of(c);
     k_divcheck<<<ctx->sm_count * 8, 256, 0, ctx->s_main>>>(d, seed, n / 2, 0, ctx->d_red);
     k_divcheck<<<ctx->sm_count * 8, 256, 0, ctx->s_main>>>(d, seed ^ 0xABCDEFull, n - n / 2, 1, ctx->d_red);
     ctx->n_launches += 2;
@@ -498,7 +498,7 @@ int chmy_run_op_fast(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, c
         p.idx = id[0]; p.idy = id[1]; p.idz = id[2];
         p.eta_ve = s[1]; p.dtau_Pr = s[4]; p.dtau_r = s[5];
         const double Gdt = s[2] * s[3];
-        p.Gdt = DivC{Gdt, 1.0 / Gdt}; p.eta = DivC{s[0], 1.0 / s[0]}; p.three = DivC{3.0, 1.0 / 3.0};
+        p.Gdt = divc_of(Gdt); p.eta = divc_of(s[0]); p.three = divc_of(3.0);
         const bool td = g_force_true_div || !markstein_ok(Gdt) || !markstein_ok(s[0]);
         const dim3 blk(TX, TY, 1);
         p.sync = g_sync; p.cz = pick_cz(box.n[2], g_cz > 0 ? g_cz : CZ);
@@ -532,7 +532,7 @@ int chmy_run_op_fast(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, c
         for (int a = 0; a < 3; ++a) { p.lo[a] = box.lo[a]; p.hi[a] = box.lo[a] + box.n[a]; }
         p.idx = id[0]; p.idy = id[1]; p.idz = id[2];
         p.nudtau = s[1];
-        p.eta_ve = DivC{s[0], 1.0 / s[0]};
+        p.eta_ve = divc_of(s[0]);
         memset(&p.inc, 0, sizeof(p.inc));
         if (!rho) {
             p.inc.active = 1; p.inc.nd = 3;

@@ -397,7 +397,7 @@ int chmy_run_op_fast2d(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box,
         p.g = g; p.idx = id[0]; p.idy = id[1];
         p.eta_ve = s[1]; p.dtau_Pr = s[4]; p.dtau_r = s[5];
         const double Gdt = s[2] * s[3];
-        p.Gdt = DivC{Gdt, 1.0 / Gdt}; p.eta = DivC{s[0], 1.0 / s[0]}; p.three = DivC{3.0, 1.0 / 3.0};
+        p.Gdt = divc_of(Gdt); p.eta = divc_of(s[0]); p.three = divc_of(3.0);
         const bool td = chmy_force_true_div() || !markstein_ok(Gdt) || !markstein_ok(s[0]);
         if (td) LAUNCH2(p, k_stress2<true>);
         LAUNCH2(p, k_stress2<false>);
@@ -413,7 +413,7 @@ int chmy_run_op_fast2d(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box,
         p.rho = rho ? rho->p0 : nullptr;
         p.s_cc = (int)CC->stride[1]; p.s_vc = (int)F[0]->stride[1]; p.s_cv = (int)F[1]->stride[1]; p.s_vv = (int)F[7]->stride[1];
         p.g = g; p.idx = id[0]; p.idy = id[1]; p.nudtau = s[1];
-        p.eta_ve = DivC{s[0], 1.0 / s[0]};
+        p.eta_ve = divc_of(s[0]);
         memset(&p.inc, 0, sizeof(p.inc));
         if (!rho) {
             p.inc.active = 1; p.inc.nd = 2;

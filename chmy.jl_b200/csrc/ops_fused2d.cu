@@ -293,8 +293,8 @@ int chmy_run_fused2d(chmy_ctx* ctx, int kind, const chmy_launch_desc* dp, const 
         p.idx = id[0]; p.idy = id[1];
         p.eta_ve = s[1]; p.dtau_Pr = s[4]; p.dtau_r = s[5]; p.nudtau = dc->scalars[1];
         const double Gdt = s[2] * s[3];
-        p.Gdt = DivC{Gdt, 1.0 / Gdt}; p.eta = DivC{s[0], 1.0 / s[0]}; p.three = DivC{3.0, 1.0 / 3.0};
-        p.eve = DivC{s[1], 1.0 / s[1]};
+        p.Gdt = divc_of(Gdt); p.eta = divc_of(s[0]); p.three = divc_of(3.0);
+        p.eve = divc_of(s[1]);
         if (!rho) {
             p.inc.active = 1; p.inc.nd = 2;
             for (int a = 0; a < 2; ++a) {

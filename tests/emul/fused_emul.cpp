@@ -70,8 +70,8 @@ extern "C" int fused_emul_run(double** ptrs, const int* strides, const int* box,
     p.cv = Strides{strides[4], strides[5]}; p.vv = Strides{strides[6], strides[7]};
     for (int a = 0; a < 3; ++a) { p.lo[a] = box[a]; p.hi[a] = box[3 + a]; p.flo[a] = box[6 + a]; p.fhi[a] = box[9 + a]; }
     p.idx = sc[0]; p.idy = sc[1]; p.idz = sc[2]; p.eta_ve = sc[3]; p.dtau_Pr = sc[4]; p.dtau_r = sc[5]; p.nudtau = sc[6];
-    p.Gdt = DivC{sc[7], 1.0 / sc[7]}; p.eta = DivC{sc[8], 1.0 / sc[8]}; p.three = DivC{3.0, 1.0 / 3.0};
-    p.eve = DivC{sc[3], 1.0 / sc[3]};
+    p.Gdt = divc_of(sc[7]); p.eta = divc_of(sc[8]); p.three = divc_of(3.0);
+    p.eve = divc_of(sc[3]);
     p.inc.active = p.rho == nullptr; p.inc.nd = 3;
     for (int a = 0; a < 3; ++a) {
         p.inc.origin[a] = inc[a]; p.inc.spacing[a] = inc[3 + a]; p.inc.c0[a] = inc[6 + a]; p.inc.loc[a] = incloc[a];

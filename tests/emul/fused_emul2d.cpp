@@ -51,8 +51,8 @@ extern "C" int fused_emul2d_run(double** ptrs, const int* strides, const int* bo
     p.s_cc = strides[0]; p.s_vc = strides[1]; p.s_cv = strides[2]; p.s_vv = strides[3];
     for (int a = 0; a < 2; ++a) { p.lo[a] = box[a]; p.hi[a] = box[2 + a]; p.flo[a] = box[4 + a]; p.fhi[a] = box[6 + a]; }
     p.idx = sc[0]; p.idy = sc[1]; p.eta_ve = sc[2]; p.dtau_Pr = sc[3]; p.dtau_r = sc[4]; p.nudtau = sc[5];
-    p.Gdt = DivC{sc[6], 1.0 / sc[6]}; p.eta = DivC{sc[7], 1.0 / sc[7]}; p.three = DivC{3.0, 1.0 / 3.0};
-    p.eve = DivC{sc[2], 1.0 / sc[2]};
+    p.Gdt = divc_of(sc[6]); p.eta = divc_of(sc[7]); p.three = divc_of(3.0);
+    p.eve = divc_of(sc[2]);
     p.inc.active = p.rho == nullptr; p.inc.nd = 2;
     for (int a = 0; a < 2; ++a) {
         p.inc.origin[a] = inc[a]; p.inc.spacing[a] = inc[2 + a]; p.inc.c0[a] = inc[4 + a]; p.inc.loc[a] = incloc[a];

@@ -429,7 +429,7 @@ def _set_tuning(disable_fast=-1, true_div=-1):
 
 @pytest.mark.parametrize("c", [3.0, 10.0, 0.0171 * 1.3, 0.737, 1.0 / 3.0, 6.02e23, 1.7e-19, 1.9999999999999998])
 def test_exact_division_by_uniform_scalar(ch, arch, c):
-    """The reciprocal + 2 FMA-correction sequence must equal IEEE division bit for bit (2^28 operands per divisor:
+    """The exact-division sequence (double-double reciprocal product + one Markstein correction) must equal IEEE division bit for bit (2^28 operands per divisor:
     random significands over 120 binades, exact multiples of c and their 1-ulp neighbours)."""
     import ctypes as C
     from chmy_b200 import _lib as L
