@@ -227,15 +227,44 @@ FHD double fsv_from_left(double, const double* p_im1, bool ok) { return ok ? *p_
 #endif
 
 // ---- phase A: stresses of plane kp -> sn[FSV_NF] (new Pr, tau), stores for the cells this thread owns
-// The two halo rows of a cluster load only what their consumers need (the first row feeds Pr and tau_yy to the row above
-// it, the last row tau_xy and tau_yz to the row below; everything else they would compute is never read): 7 resp. 9 of
-// the 19 loads (measured at 767^3: 20.31 -> 20.22 ms, profiles/r2_c13_tune_fused.log).
+// A thread loads only what somebody consumes.  In y: the two halo rows of a cluster feed Pr and tau_yy to the row above
+// (first row) resp. tau_xy and tau_yz to the row below (last row): 7 resp. 9 of the 19 loads (measured at 767^3: 20.31 ->
+// 20.22 ms, profiles/r2_c13_tune_fused.log).  In z: of the warm-up plane k0-1 only Pr and tau_zz are consumed (by the
+// z-velocity of plane k0) and of the closing plane k1 only tau_xz and tau_yz (by the velocity of plane k1-1), both by the
+// thread itself; besides those a thread requests the velocities the NEXT plane takes from its carried registers.
+enum {
+    FSV_L_VX = 1, FSV_L_VXJM = 2, FSV_L_VY = 4, FSV_L_VYJP = 8, FSV_L_VZKP = 16, FSV_L_VZJMKP = 32, FSV_L_PR = 64,
+    FSV_L_T0 = 128   // tau / tau_old component c: FSV_L_T0 << c
+};
+FHD int fsv_need(int role, bool first, bool last) {
+    const int T = FSV_L_T0;
+    if (last) return role == 0 ? (FSV_L_VX | FSV_L_VY | T << 4 | T << 5) : 0;
+    if (first) {
+        if (role == 0) return FSV_L_VX | FSV_L_VY | FSV_L_VYJP | FSV_L_VZKP | FSV_L_VZJMKP | FSV_L_PR | T << 2;
+        return role == 1 ? FSV_L_VZKP : (FSV_L_VY | FSV_L_VZKP | FSV_L_VZJMKP);
+    }
+    return -1;                      // a plane of the chunk proper: everything the row's role asks for (fsv_phase_a)
+}
+
 template <bool TD>
 FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
     const d2 z2 = fsv_zero();
     d2 vx = z2, vxjm = z2, vy = z2, vyjp = z2, vzkp = z2, vzjmkp = z2, pr = z2;
     d2 t[6], o[6];
-    if (s.role != 0) {
+    if (kp < s.k0 || kp >= s.k1) {             // warm-up / closing plane of the chunk (2 of cz + 2): request by request
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { t[c] = z2; o[c] = z2; }
+        const int need = s.s_act ? fsv_need(s.role, kp < s.k0, kp >= s.k1) : 0;
+        if (need & FSV_L_VX) vx = ld2(p.Vc[0] + s.vc);
+        if (need & FSV_L_VY) vy = ld2(p.Vc[1] + s.cv);
+        if (need & FSV_L_VYJP) vyjp = ld2(p.Vc[1] + s.cv + (long long)s.jp * p.cv.sy);
+        if (need & FSV_L_VZKP) vzkp = ld2(p.Vc[2] + s.cc + p.cc.sz);
+        if (need & FSV_L_VZJMKP) vzjmkp = ld2(p.Vc[2] + s.cc - (long long)s.jm * p.cc.sy + p.cc.sz);
+        if (need & FSV_L_PR) pr = ld2(p.Prc + s.cc);
+        if (need & (FSV_L_T0 << 2)) { t[2] = ld2(p.tc[2] + s.cc); o[2] = ld2(p.to[2] + s.cc); }
+        if (need & (FSV_L_T0 << 4)) { t[4] = ld2(p.tc[4] + s.vc); o[4] = ld2(p.to[4] + s.vc); }
+        if (need & (FSV_L_T0 << 5)) { t[5] = ld2(p.tc[5] + s.cv); o[5] = ld2(p.to[5] + s.cv); }
+    } else if (s.role != 0) {
 #pragma unroll
         for (int c = 0; c < 6; ++c) { t[c] = z2; o[c] = z2; }
         if (s.s_act && s.role == 1) {          // divV (all three normal strain rates), Pr, tau_yy
