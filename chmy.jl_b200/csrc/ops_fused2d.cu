@@ -60,7 +60,11 @@ __global__ void __launch_bounds__(FSV_LANES* F2_WARPS, (KIND == 0 ? 8 : 4)) k_fu
 
 // 3D thermal pair: one warp = one 64-cell row segment of one row, FT3_ROWS rows per CTA, one z-chunk per CTA; warps are
 // independent (no shared memory, no barrier).  All 32 lanes run the loop: its bounds depend on blockIdx.z only.
-__global__ void __launch_bounds__(FSV_LANES* FT3_ROWS, 2) k_fused_t3(const FusedT3P p) {
+// Three resident CTAs per SM: 80 registers and 24 warps instead of 112 and 16 (20 bytes of spills, L1 hits -- this sweep has
+// no cluster barrier that would empty L1): 6.5 -> 5.7 ms at 767^3; four (64 registers, 124 bytes of spills) gives it back
+// (profiles/r2_c45_thermal3_occupancy.log).  The 2D stress+velocity sweep is the other way round: 4 CTAs of 122 registers beat
+// 5 or 6 CTAs with spills (r2_c46_stokes2d_sweep_occupancy.log).
+__global__ void __launch_bounds__(FSV_LANES* FT3_ROWS, 3) k_fused_t3(const FusedT3P p) {
     FusedT3T s;
     ft3_init(s, p, threadIdx.x, blockIdx.x, blockIdx.y * FT3_ROWS + threadIdx.y, blockIdx.z);
     for (int k = s.k0; k < s.k1; ++k) {
