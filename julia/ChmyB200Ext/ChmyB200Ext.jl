@@ -283,6 +283,14 @@ end
 fuse!(arch::SingleDeviceArchitecture{B200Backend}, on::Bool=true) =
     check(ccall((:chmy_set_fusion, libchmy), Cint, (Ptr{Cvoid}, Cint), ctx(arch), on ? 3 : 0))
 
+# sweeps launched / pairs that had to run as two kernels because the device had no room for their shadow buffers
+function fused_counts(arch::SingleDeviceArchitecture{B200Backend})
+    n, m = Ref{UInt64}(0), Ref{UInt64}(0)
+    check(ccall((:chmy_fused_count, libchmy), Cint, (Ptr{Cvoid}, Ref{UInt64}), ctx(arch), n))
+    check(ccall((:chmy_fusion_fallback_count, libchmy), Cint, (Ptr{Cvoid}, Ref{UInt64}), ctx(arch), m))
+    return (fused=n[], fallbacks=m[])
+end
+
 # Launches with boundary batches (include/chmy_b200.h: chmy_set_launch_tuning): overlap the batches / the halo exchange with
 # the kernel (default) or run everything on one stream; results are identical.  -1 keeps the batch-folding setting.
 overlap!(arch, on::Bool=true) =
