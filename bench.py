@@ -70,7 +70,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="stokes3d", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, nargs="*", default=None, help="override the local grid size (parity/debug runs)")
+    ap.add_argument("--n", "--size", type=int, nargs="*", default=None, help="override the local grid size (parity/debug runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the untimed multi-rank correctness check")

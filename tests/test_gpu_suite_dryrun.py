@@ -116,7 +116,7 @@ def test_multi_rank_suites_and_bench_run_on_the_dry_run_backend():
     # the reference arm under torchrun: rank 0 alone works and prints
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
-           "--warmup", "1", "--n", "96", "96", "96"]          # control flow of the ranks, not a measurement: a small grid
+           "--warmup", "1", "--size", "96", "96", "96"]          # control flow of the ranks, not a measurement: a small grid
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert r.returncode == 0 and len(lines) == 1 and json.loads(lines[0])["impl"] == "reference", (r.stdout + r.stderr)[-2000:]
