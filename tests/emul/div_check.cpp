@@ -1,7 +1,7 @@
 // div_check.cpp -- TEST INFRASTRUCTURE.  The exact-division sequence of the tuned / fused kernels (div_u in
 // chmy.jl_b200/csrc/fused_sv.cuh: the host twin of fast_common.cuh's device function) against IEEE division on the host, over
 // the operand families the device self-test uses (chmy_selftest_division): random significands over 120 binades, exact
-// multiples of the divisor and their 1-ulp neighbours.  Returns the number of operands whose quotient differs in any bit.
+// multiples of the divisor and their 1-ulp neighbours, and operands whose quotient lies next to a rounding midpoint.  Returns the number of operands whose quotient differs in any bit.
 #include <cstdint>
 #include <cstring>
 
@@ -30,10 +30,17 @@ extern "C" long long div_check(double c, long long n, unsigned long long seed, i
         if (mode == 0) {
             const uint64_t e = 1023ull - 60ull + (z >> 52) % 121ull;
             x = bits_to_double((z & 0x800FFFFFFFFFFFFFull) | (e << 52));
-        } else {
+        } else if (mode == 1) {
             const double m = (double)(long long)(z >> 12);
             x = m * c;
             if (z & 1) x = bits_to_double(double_to_bits(x) + ((z >> 1) & 3) - 1);
+        } else {           // quotients next to the midpoint of two neighbouring doubles: x ~ c * (q + ulp(q) / 2), and its neighbours
+            const uint64_t e = 1023ull - 30ull + (z >> 52) % 61ull;
+            const double q = bits_to_double((z & 0x800FFFFFFFFFFFFFull) | (e << 52));
+            const double h = bits_to_double(((e - 53ull) << 52));                  // half an ulp of q
+            const long double xl = (long double)c * ((long double)q + (long double)(q < 0 ? -h : h));
+            x = (double)xl;
+            x = bits_to_double(double_to_bits(x) + ((z >> 3) % 5) - 2);
         }
         const double a = x / c, b = div_u<false>(x, d);
         if (double_to_bits(a) != double_to_bits(b) && !(a != a && b != b)) ++bad;

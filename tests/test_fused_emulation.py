@@ -166,10 +166,10 @@ def test_fused_sweep_equals_stress_then_velocity(oracle, emul, n, box, cz, tyb, 
 @pytest.mark.parametrize("c", [3.0, 10.0, 0.0171 * 1.3, 0.737, 1.0 / 3.0, 6.02e23, 1.7e-19, 1.0000000000000002, 1.9999999999999996, 7.0, 1e-3])
 def test_exact_division_sequence_on_the_host(c):
     """div_u (double-double reciprocal product + one Markstein correction: 4 operations) == IEEE division, bit for bit, on
-    2^25 operands per divisor and family (the GPU self-test chmy_selftest_division runs 2^28 on the device)."""
+    2^24 operands per divisor and family (three families) (the GPU self-test chmy_selftest_division runs 2^28 on the device)."""
     from helpers import build_emul
     lib = build_emul("div_check")
     lib.div_check.restype = C.c_longlong
     lib.div_check.argtypes = [C.c_double, C.c_longlong, C.c_ulonglong, C.c_int]
-    for mode in (0, 1):
-        assert lib.div_check(c, 1 << 25, 4711 + mode, mode) == 0, (c, mode)
+    for mode in (0, 1, 2):         # random operands | multiples of c and neighbours | quotients next to a rounding midpoint
+        assert lib.div_check(c, 1 << 24, 4711 + mode, mode) == 0, (c, mode)
