@@ -482,6 +482,9 @@ def run_b200(args):
     nfused = ch.fused_count(arch)
     noverl = ch.overlapped_count(arch)
     nfallback = ch.fusion_fallback_count(arch)
+    # how the fused 3D sweep divided by its uniform scalars (0: four operations, 1: div.rn.f64, 2: two operations, proven exact)
+    divmode = {0: "4 operations (Markstein)", 1: "div.rn.f64", 2: "2 operations (proven exact for these divisors)"}.get(ch.last_division_mode(arch)) \
+        if (fused and wl.startswith("stokes3d")) else None
     xstats = dict(zip(("peer", "nccl"), ch.exchange_stats(arch))) if world > 1 else None     # rank 0's messages so far
     clocks = sampler.stop() if rank == 0 else None
     ch.barrier(arch)
@@ -666,7 +669,7 @@ def run_b200(args):
                        "l2": "inputs larger than L2 (every field >= 2 GB; 126 MB L2), no flush needed",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "T_eff_per_gpu": teff_gpu, "frac_of_hbm_peak": teff_gpu / peak, "hbm_peak": peak, "hbm_peak_source": peak_src,
-            "clocks": clocks, "gpu_launches": int(l1 - l0), "launches_per_step": (l1 - l0) / K, "fused_sweeps": int(nfused), "fusion_fallbacks": int(nfallback), "overlapped_launches": int(noverl), "exchange_msgs": xstats, "roofline": roofline, "e2e": e2e, "cpu_baseline": cb,
+            "clocks": clocks, "gpu_launches": int(l1 - l0), "launches_per_step": (l1 - l0) / K, "fused_sweeps": int(nfused), "fusion_fallbacks": int(nfallback), "division": divmode, "overlapped_launches": int(noverl), "exchange_msgs": xstats, "roofline": roofline, "e2e": e2e, "cpu_baseline": cb,
             "multi_gpu_check": mgc, "exchange_alone": xchg,
         }
     if world > 1:

@@ -122,6 +122,9 @@ SYMBOLS = {
     "chmy_set_fusion": (C.c_int, [_vp, C.c_int]),
     "chmy_fused_count": (C.c_int, [_vp, _P(C.c_uint64)]),
     "chmy_fusion_fallback_count": (C.c_int, [_vp, _P(C.c_uint64)]),
+    "chmy_division_two_op_exact": (C.c_int, [C.c_double, _P(C.c_int32)]),
+    "chmy_last_division_mode": (C.c_int, [_vp, _P(C.c_int32)]),
+    "chmy_selftest_division2": (C.c_int, [_vp, C.c_double, C.c_longlong, C.c_ulonglong, _P(C.c_ulonglong), _P(C.c_int)]),
     "chmy_set_fused_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "chmy_set_fused2d_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "chmy_halo_slab_len": (C.c_int, [_vp, C.c_int, _i64p]),

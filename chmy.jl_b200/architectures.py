@@ -160,6 +160,20 @@ def fusion_fallback_count(arch: Architecture) -> int:
     return int(n.value)
 
 
+def last_division_mode(arch: Architecture) -> int:
+    """how the last fused 3D sweep divided by its uniform scalars: 0 = four operations, 1 = div.rn.f64, 2 = two operations
+    (proven exact for all four divisors of the launch, include/chmy_b200.h: chmy_division_two_op_exact)"""
+    m = C.c_int32(-1)
+    L.check(L.lib().chmy_last_division_mode(arch.ctx, C.byref(m)))
+    return int(m.value)
+
+
+def division_two_op_exact(c: float) -> bool:
+    e = C.c_int32(0)
+    L.check(L.lib().chmy_division_two_op_exact(float(c), C.byref(e)))
+    return bool(e.value)
+
+
 def overlapped_count(arch: Architecture) -> int:
     """launches whose boundary batches / halo exchange ran behind the boundary tiles of a still-running fused sweep"""
     n = C.c_uint64(0)

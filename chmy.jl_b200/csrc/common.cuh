@@ -180,6 +180,11 @@ struct chmy_ctx {
     unsigned int*     d_done;        // device counter of the boundary-first sweep (ops_fused.cu): CTAs of boundary tiles retired
     uint64_t          batch_sig;     // signature of the batch set being applied right now (0 outside launch / bc!)
     uint64_t          n_overlapped;  // launches whose batches ran behind the boundary tiles of a still-running sweep
+    // fused 3D sweep: the division mode of the last launch (0 four operations, 1 div.rn.f64, 2 two operations) and a small
+    // cache of div2_exact() verdicts (fast_common.cuh)
+    int               div_mode, n_div2, div2_next;
+    double            div2_c[8];
+    bool              div2_ok[8];
     // staged uploads (api.cu copy_box_host): two device buffers a dense host box is copied into piecewise, contiguously, while
     // a kernel scatters the previous piece into the padded field
     char*             d_up[2];

@@ -25,6 +25,45 @@ static inline bool markstein_ok(double c) {
     return true;
 }
 
+// Is  fma(x, rc, RN(x * rl))  -- the double-double reciprocal product alone, TWO operations -- the correctly rounded x / c for
+// EVERY normal x?  Decidable per divisor (after Brisebarre & Muller, "Correctly rounded multiplication by arbitrary precision
+// constants"): write c = M * 2^a with M odd and x = X * 2^b with a 53-bit integer X; scaled so that one ulp of the quotient is 1
+// the quotient is Y = X * 2^s / M (s = bits(M) or bits(M) - 1), and the value the fma rounds differs from Y by less than
+// 2^-52 (1 + 2^-51) (the errors of rl and of RN(x * rl)).  The result can only be wrong if a rounding midpoint n + 1/2 lies that
+// close to Y, i.e. if |2^(s+1) X - (2n+1) M| <= 2 M 2^-51 = M 2^-50 < 8: at most eight odd residues N, each a congruence
+// 2^(s+1) X = N (mod M) with a handful of solutions X in [2^52, 2^53) when M has 51+ bits and none needed otherwise.  Every
+// solution is tried against IEEE division here, on the host (fma is exactly specified, the device computes the same bits):
+// if none fails, no operand can.  About 1.3 % of random divisors do have a failing operand (which random testing never finds);
+// they keep the four-operation sequence below.
+static inline bool div2_exact(double c) {
+    if (!markstein_ok(c)) return false;
+    c = fabs(c);
+    int e;
+    const double f = frexp(c, &e);
+    unsigned long long M = (unsigned long long)ldexp(f, 53);
+    while ((M & 1ull) == 0) M >>= 1;
+    if (M == 1) return true;                                   // a power of two: every step is exact
+    const unsigned long long K = M >> 50;                      // |N| <= K
+    if (K == 0) return true;
+    const int L = 64 - __builtin_clzll(M);
+    const DivC d = divc_of(c);
+    const unsigned long long inv2 = (M + 1) >> 1, lo = 1ull << 52, hi = 1ull << 53;
+    for (int s = L - 1; s <= L; ++s) {
+        unsigned long long inv = 1;                            // 2^-(s+1) mod M
+        for (int t = 0; t <= s; ++t) inv = (unsigned long long)((unsigned __int128)inv * inv2 % M);
+        for (unsigned long long N = 1; N <= K; N += 2)
+            for (int sg = 0; sg < 2; ++sg) {
+                const unsigned long long r = sg ? M - N % M : N % M;
+                const unsigned long long X0 = (unsigned long long)((unsigned __int128)(r % M) * inv % M);
+                for (unsigned long long X = X0 >= lo ? X0 : X0 + (lo - X0 + M - 1) / M * M; X < hi; X += M) {
+                    const double x = (double)X;
+                    if (fma(x, d.rc, x * d.rl) != x / c) return false;
+                }
+            }
+    }
+    return true;
+}
+
 template <bool TRUE_DIV>
 __device__ __forceinline__ double div_u(double x, const DivC d) {
     if (TRUE_DIV) return x / d.c;
@@ -34,6 +73,14 @@ __device__ __forceinline__ double div_u(double x, const DivC d) {
     const double q = fma(x, d.rc, x * d.rl);
     const double r = fma(-d.c, q, x);
     return fma(r, d.rc, q);
+}
+
+// division mode of the fused 3D sweep: 0 = the four-operation sequence, 1 = div.rn.f64, 2 = the two-operation sequence (only when
+// div2_exact() holds for every divisor of the launch)
+template <int MODE>
+__device__ __forceinline__ double div_m(double x, const DivC d) {
+    if (MODE == 2) return fma(x, d.rc, x * d.rl);
+    return div_u<MODE == 1>(x, d);
 }
 
 // ---------------------------------------------------------------------------------------------- helpers

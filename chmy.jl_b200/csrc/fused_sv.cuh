@@ -65,6 +65,11 @@ static inline double div_u(double x, const DivC d) {
     const double r = fma(-d.c, q, x);
     return fma(r, d.rc, q);
 }
+template <int MODE>
+static inline double div_m(double x, const DivC d) {
+    if (MODE == 2) return fma(x, d.rc, x * d.rl);
+    return div_u<MODE == 1>(x, d);
+}
 static inline double coord_dev(double origin, double spacing, int loc, int i) {
     const double im1 = (double)(i - 1);
     return loc == 1 ? fma(im1, spacing, origin) : fma(im1, spacing, fma(0.5, spacing, origin));
@@ -210,10 +215,10 @@ FHD void fsv_init(FusedT& s, const FusedP& p, int lane, int ty, int grow, int bx
     }
 }
 
-template <bool TD>
+template <int TD>
 FHD double fsv_stress_upd(double t, double to, double e2, const FusedP& p) {
     // tau + (((-(tau - tau_old))/(G dt) - tau/eta) + 2 e) * eta_ve * dtau_r      (stokes_3d_inc_ve_T.jl:34-45)
-    const double r = (div_u<TD>(-(t - to), p.Gdt) - div_u<TD>(t, p.eta)) + e2;
+    const double r = (div_m<TD>(-(t - to), p.Gdt) - div_m<TD>(t, p.eta)) + e2;
     return t + (r * p.eta_ve) * p.dtau_r;
 }
 
@@ -246,7 +251,7 @@ FHD int fsv_need(int role, bool first, bool last) {
     return -1;                      // a plane of the chunk proper: everything the row's role asks for (fsv_phase_a)
 }
 
-template <bool TD>
+template <int TD>
 FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
     const d2 z2 = fsv_zero();
     d2 vx = z2, vxjm = z2, vy = z2, vyjp = z2, vzkp = z2, vzjmkp = z2, pr = z2;
@@ -320,7 +325,7 @@ FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
         const double exz = 0.5 * ((a_vx - a_vxkm) * p.idz + (a_vz - a_vzim) * p.idx);
         const double eyz = 0.5 * ((a_vy - a_vykm) * p.idz + (a_vz - a_vzjm) * p.idy);
         const double d   = (exx + eyy) + ezz;
-        const double d3  = div_u<TD>(d, p.three);
+        const double d3  = div_m<TD>(d, p.three);
         const double a_pr = h ? pr.y : pr.x;
         const double e2[6] = {2.0 * (exx - d3), 2.0 * (eyy - d3), 2.0 * (ezz - d3), 2.0 * exy, 2.0 * exz, 2.0 * eyz};
         // outside the op's index range update_stress! never ran: the value the velocity update sees is the stored one
@@ -362,7 +367,7 @@ FHD void fsv_phase_a(FusedT& s, const FusedP& p, int kp, d2 sn[FSV_NF]) {
 // ---- phase B: publish the stresses of plane kp, update the velocity of plane kp-1, rotate the carried planes.
 // own / below / above: exchange buffers (element 0 of [buf][field][row][cell]) of the CTAs holding this thread's
 // row, row j-1 and row j+1; rb / ra: the row numbers of j-1 / j+1 inside those CTAs.
-template <bool TD, bool FUN>
+template <int TD, bool FUN>
 FHD void fsv_phase_b(FusedT& s, const FusedP& p, int kp, const d2 sn[FSV_NF], int tyb, double* own, const double* below,
                      int rb, const double* above, int ra) {
     const int cur = kp & 1, prev = cur ^ 1;
@@ -415,9 +420,9 @@ FHD void fsv_phase_b(FusedT& s, const FusedP& p, int kp, const d2 sn[FSV_NF], in
                                    (a_tyzkp - a_tyz) * p.idz;
                 const double rvz = ((((-((a_pr - a_prkm) * p.idz)) + (a_tzz - a_tzzkm) * p.idz) + (a_txzip - a_txz) * p.idx) +
                                     (a_tyzjp - a_tyz) * p.idy) - (h ? rho.y : rho.x);
-                const double ux = (h ? s.vx_km.y : s.vx_km.x) + div_u<TD>(rvx * p.nudtau, p.eve);
-                const double uy = (h ? s.vy_km.y : s.vy_km.x) + div_u<TD>(rvy * p.nudtau, p.eve);
-                const double uz = (h ? s.vz_km.y : s.vz_km.x) + div_u<TD>(rvz * p.nudtau, p.eve);
+                const double ux = (h ? s.vx_km.y : s.vx_km.x) + div_m<TD>(rvx * p.nudtau, p.eve);
+                const double uy = (h ? s.vy_km.y : s.vy_km.x) + div_m<TD>(rvy * p.nudtau, p.eve);
+                const double uz = (h ? s.vz_km.y : s.vz_km.x) + div_m<TD>(rvz * p.nudtau, p.eve);
                 if (h) { nrx.y = rvx; nry.y = rvy; nrz.y = rvz; nvx.y = ux; nvy.y = uy; nvz.y = uz; }
                 else   { nrx.x = rvx; nry.x = rvy; nrz.x = rvz; nvx.x = ux; nvy.x = uy; nvz.x = uz; }
             }

@@ -17,6 +17,7 @@
 #include "fast_common.cuh"
 
 // self-test kernel: counts operands for which the sequence differs from div.rn.f64 (bitwise, NaN == NaN)
+template <int SEQ>      // 0: four operations (div_u), 2: two operations (div_m<2>)
 __global__ void k_divcheck(DivC d, unsigned long long seed, long long n, int mode, unsigned long long* bad) {
     unsigned long long cnt = 0;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
@@ -33,7 +34,7 @@ __global__ void k_divcheck(DivC d, unsigned long long seed, long long n, int mod
             x = m * d.c;
             if (z & 1) x = __longlong_as_double(__double_as_longlong(x) + (long long)((z >> 1) & 3) - 1);
         }
-        const double a = x / d.c, b = div_u<false>(x, d);
+        const double a = x / d.c, b = div_m<SEQ>(x, d);
         if (__double_as_longlong(a) != __double_as_longlong(b) && !(a != a && b != b)) ++cnt;
     }
     if (cnt) atomicAdd(bad, cnt);
@@ -48,8 +49,28 @@ extern "C" int chmy_selftest_division(chmy_ctx* ctx, double c, long long n, unsi
     CHMY_CUDA(cudaSetDevice(ctx->device));
     CHMY_CUDA(cudaMemsetAsync(ctx->d_red, 0, sizeof(unsigned long long), ctx->s_main));
     const DivC d = divc_of(c);
-    k_divcheck<<<ctx->sm_count * 8, 256, 0, ctx->s_main>>>(d, seed, n / 2, 0, ctx->d_red);
-    k_divcheck<<<ctx->sm_count * 8, 256, 0, ctx->s_main>>>(d, seed ^ 0xABCDEFull, n - n / 2, 1, ctx->d_red);
+    k_divcheck<0><<<ctx->sm_count * 8, 256, 0, ctx->s_main>>>(d, seed, n / 2, 0, ctx->d_red);
+    k_divcheck<0><<<ctx->sm_count * 8, 256, 0, ctx->s_main>>>(d, seed ^ 0xABCDEFull, n - n / 2, 1, ctx->d_red);
+    ctx->n_launches += 2;
+    CHMY_CUDA(cudaGetLastError());
+    CHMY_CUDA(cudaMemcpyAsync(ctx->h_red, ctx->d_red, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->s_main));
+    CHMY_CUDA(cudaStreamSynchronize(ctx->s_main));
+    *mismatches = ctx->h_red[0];
+    return CHMY_OK;
+}
+
+// the two-operation sequence on the device, for a divisor div2_exact() has proven (proved = 0: nothing is run)
+extern "C" int chmy_selftest_division2(chmy_ctx* ctx, double c, long long n, unsigned long long seed,
+                                       unsigned long long* mismatches, int* proved) {
+    CHMY_REQUIRE(ctx && mismatches && proved && n >= 0, "bad argument");
+    *proved = div2_exact(c) ? 1 : 0;
+    *mismatches = 0;
+    if (!*proved) return CHMY_OK;
+    CHMY_CUDA(cudaSetDevice(ctx->device));
+    CHMY_CUDA(cudaMemsetAsync(ctx->d_red, 0, sizeof(unsigned long long), ctx->s_main));
+    const DivC d = divc_of(c);
+    k_divcheck<2><<<ctx->sm_count * 8, 256, 0, ctx->s_main>>>(d, seed, n / 2, 0, ctx->d_red);
+    k_divcheck<2><<<ctx->sm_count * 8, 256, 0, ctx->s_main>>>(d, seed ^ 0xABCDEFull, n - n / 2, 1, ctx->d_red);
     ctx->n_launches += 2;
     CHMY_CUDA(cudaGetLastError());
     CHMY_CUDA(cudaMemcpyAsync(ctx->h_red, ctx->d_red, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->s_main));

@@ -18,7 +18,7 @@ __device__ __forceinline__ void fsv_cluster_arrive_relaxed() {
     asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 }
 
-template <bool TD, bool FUN, int TYB>
+template <int TD, bool FUN, int TYB>
 __global__ void __launch_bounds__(FSV_LANES* TYB, (TYB == 4 ? 3 : 2)) k_fused_sv(const FusedP p, const int cl, const int variant) {
     extern __shared__ __align__(16) double xb[];
     const int lane = threadIdx.x, ty = threadIdx.y;
@@ -125,7 +125,7 @@ extern "C" int chmy_set_fused_tuning(chmy_ctx* ctx, int rows_per_cta, int cluste
     return CHMY_OK;
 }
 
-template <bool TD, bool FUN, int TYB>
+template <int TD, bool FUN, int TYB>
 static int launch_fused(const FusedP& p, int cl, int variant, dim3 grid, cudaStream_t st) {
     void (*kern)(const FusedP, const int, const int) = k_fused_sv<TD, FUN, TYB>;
     const size_t smem = fsv_smem_bytes(TYB);
@@ -150,7 +150,7 @@ static int launch_fused(const FusedP& p, int cl, int variant, dim3 grid, cudaStr
     return CHMY_OK;
 }
 
-template <bool TD, bool FUN>
+template <int TD, bool FUN>
 static int launch_fused_tyb(const FusedP& p, int tyb, int cl, int variant, dim3 grid, cudaStream_t st) {
     switch (tyb) {
     case 4: return launch_fused<TD, FUN, 4>(p, cl, variant, grid, st);
@@ -213,6 +213,28 @@ extern "C" int chmy_selftest_tile_order(const int32_t g[3], const int32_t i0[3],
     return CHMY_OK;
 }
 
+// div2_exact() per divisor, remembered per context (the drivers launch with the same four scalars every iteration)
+static bool div2_cached(chmy_ctx* ctx, double c) {
+    for (int q = 0; q < ctx->n_div2; ++q)
+        if (ctx->div2_c[q] == c) return ctx->div2_ok[q];
+    const bool ok = div2_exact(c);
+    const int q = ctx->n_div2 < 8 ? ctx->n_div2++ : (ctx->div2_next++ & 7);
+    ctx->div2_c[q] = c; ctx->div2_ok[q] = ok;
+    return ok;
+}
+
+extern "C" int chmy_division_two_op_exact(double c, int32_t* exact) {
+    CHMY_REQUIRE(exact != nullptr, "NULL argument");
+    *exact = div2_exact(c) ? 1 : 0;
+    return CHMY_OK;
+}
+
+extern "C" int chmy_last_division_mode(const chmy_ctx* ctx, int32_t* mode) {
+    CHMY_REQUIRE(ctx && mode, "NULL argument");
+    *mode = ctx->div_mode;
+    return CHMY_OK;
+}
+
 int chmy_run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_desc* dv, const Box& box,
                    double* const* cur /* tau[6] Pr V[3] */, double* const* shadow, cudaStream_t st, unsigned int* done,
                    unsigned int* n_signal) {
@@ -249,7 +271,12 @@ int chmy_run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_
         }
         p.inc.r2 = dv->rho_g.r * dv->rho_g.r; p.inc.in = dv->rho_g.in; p.inc.out = dv->rho_g.out;
     }
+    // division mode (fast_common.cuh): true division when a divisor is outside Markstein's conditions (or on request), the
+    // two-operation sequence when it is PROVEN exact for all four divisors of this launch, else the four-operation sequence
     const bool td = chmy_force_true_div() || !markstein_ok(Gdt) || !markstein_ok(s[0]) || !markstein_ok(s[1]);
+    static const bool allow2 = !(getenv("CHMY_DIV2") && getenv("CHMY_DIV2")[0] == '0');
+    const int dm = td ? 1 : (allow2 && div2_cached(ctx, Gdt) && div2_cached(ctx, s[0]) && div2_cached(ctx, s[1]) && div2_cached(ctx, 3.0)) ? 2 : 0;
+    ctx->div_mode = dm;
     // geometry: clusters shrink for short boxes (slabs of a split launch)
     int tyb = ctx->tun.fuse_tyb, cl = ctx->tun.fuse_cl;
     while (cl > 1 && (cl - 1) * tyb - 2 >= box.n[1]) cl -= 1;
@@ -272,8 +299,10 @@ int chmy_run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_
     const dim3 grid((unsigned)total, (unsigned)cl, 1);
     int rc;
     const int var = ctx->tun.fuse_var;
-    if (rho) rc = td ? launch_fused_tyb<true, false>(p, tyb, cl, var, grid, st) : launch_fused_tyb<false, false>(p, tyb, cl, var, grid, st);
-    else     rc = td ? launch_fused_tyb<true, true>(p, tyb, cl, var, grid, st) : launch_fused_tyb<false, true>(p, tyb, cl, var, grid, st);
+    if (rho) rc = dm == 1 ? launch_fused_tyb<1, false>(p, tyb, cl, var, grid, st)
+                : dm == 2 ? launch_fused_tyb<2, false>(p, tyb, cl, var, grid, st) : launch_fused_tyb<0, false>(p, tyb, cl, var, grid, st);
+    else     rc = dm == 1 ? launch_fused_tyb<1, true>(p, tyb, cl, var, grid, st)
+                : dm == 2 ? launch_fused_tyb<2, true>(p, tyb, cl, var, grid, st) : launch_fused_tyb<0, true>(p, tyb, cl, var, grid, st);
     CHMY_TRY(rc);
     ctx->n_launches++;
     return CHMY_OK;

@@ -274,6 +274,15 @@ int chmy_exchange_stats(const chmy_ctx* ctx, uint64_t* peer_msgs, uint64_t* nccl
  * true-division instantiation instead. */
 int chmy_selftest_division(chmy_ctx* ctx, double c, long long n, unsigned long long seed,
                            unsigned long long* mismatches, int* markstein_used);
+/* Division by a launch-uniform scalar inside the fused 3D sweep: is the two-operation sequence fma(x, RN(1/c), RN(x * RN(1/c -
+ * RN(1/c)))) the correctly rounded x / c for EVERY normal x?  Decided per divisor by trying the finitely many operands whose
+ * quotient lies within the sequence's error of a rounding midpoint (fast_common.cuh: div2_exact) -- a pure host function.
+ * The sweep uses that sequence only when all four of its divisors (G dt, eta, eta_ve, 3.0) pass, the four-operation sequence
+ * otherwise; chmy_last_division_mode: what the last fused 3D sweep of the context used (0: four operations, 1: div.rn.f64,
+ * 2: two operations).  Env CHMY_DIV2=0 keeps the four-operation sequence. */
+int chmy_division_two_op_exact(double c, int32_t* exact);
+int chmy_selftest_division2(chmy_ctx* ctx, double c, long long n, unsigned long long seed, unsigned long long* mismatches, int* proved);
+int chmy_last_division_mode(const chmy_ctx* ctx, int32_t* mode);
 /* -1 keeps a setting.  disable_fast_kernels: run every op with the generic one-thread-per-cell kernels (A/B
  * parity of the tuned kernels); force_true_division: div.rn.f64 everywhere.  Env: CHMY_NO_FAST=1, CHMY_TRUE_DIV=1. */
 int chmy_set_tuning(int disable_fast_kernels, int force_true_division);

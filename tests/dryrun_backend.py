@@ -132,6 +132,8 @@ class DryRunLib:
         return 0
 
     def chmy_set_tuning(self, a, b):
+        if b >= 0:
+            self.true_div = int(b)
         return 0
 
     def chmy_set_launch_tuning(self, ctx, overlap, bc_fold):
@@ -201,13 +203,30 @@ class DryRunLib:
                 same = P[:nd] == H[2:2 + nd] and P[nd] == H[0] and H[1] != H[0]
             if same:
                 c["nfused"] = c.get("nfused", 0) + 1
+                if d.op == 5 and nd == 3:      # ops_fused.cu: division mode of the sweep (velocity scalars: eta_ve nudtau; stress: eta eta_ve G dt)
+                    S = pend[2]
+                    e = C.c_int32(0)
+                    two = all(self.real.chmy_division_two_op_exact(float(x), C.byref(e)) == 0 and e.value for x in (S[2] * S[3], S[0], S[1], 3.0))
+                    c["div_mode"] = 1 if getattr(self, "true_div", 0) else (2 if two else 0)
                 any_ex = any(d.bc[D][S].kind == 2 for D in range(nd) for S in range(2))
                 if d.op == 5 and nd == 3 and d.has_bc and not (d.flags & 2) and (c.get("overlap", 1) == 2 or (c.get("overlap", 1) and any_ex)):
                     c["noverl"] = c.get("noverl", 0) + 1      # api.cu run_overlapped: the batches run behind the boundary tiles
         defer = (not d.has_bc) and pitched and (
             ((fuse & 1) and d.op == 4 and nd == 3) or
             ((fuse & 2) and ((nd == 2 and d.op in (4, 1, 6)) or (nd == 3 and d.op == 6))))
-        c["pending"] = (d.op, H) if defer else None
+        c["pending"] = (d.op, H, [d.scalars[q] for q in range(d.nscalars)]) if defer else None
+
+    def chmy_selftest_division2(self, ctx, c, n, seed, bad, proved):
+        self._set(bad, 0)
+        self._set(proved, 1)
+        return 0
+
+    def chmy_last_division_mode(self, ctx, out):
+        self._set(out, self.ctxs[self._h(ctx)].get("div_mode", 0))
+        return 0
+
+    def chmy_division_two_op_exact(self, c, out):
+        return self.real.chmy_division_two_op_exact(c, out) if getattr(self, "real", None) is not None else (self._set(out, 1) or 0)
 
     def chmy_selftest_division(self, ctx, c, n, seed, bad, used):
         self._set(bad, 0)

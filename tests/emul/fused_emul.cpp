@@ -9,7 +9,7 @@
 
 #include "../../chmy.jl_b200/csrc/fused_sv.cuh"
 
-template <bool TD, bool FUN>
+template <int TD, bool FUN>
 static void run(const FusedP& p, int tyb, int cl) {
     const int nx = p.hi[0] - p.lo[0], ny = p.hi[1] - p.lo[1], nz = p.hi[2] - p.lo[2];
     const int gx = (nx + FSV_XI - 1) / FSV_XI, gyc = (ny + p.rows_int - 1) / p.rows_int, gz = (nz + p.cz - 1) / p.cz;
@@ -80,7 +80,9 @@ extern "C" int fused_emul_run(double** ptrs, const int* strides, const int* box,
     p.cz = cz; p.rows_int = cl * tyb - 2;
     if (p.lo[0] & 1) return -1;
     const bool fun = p.rho == nullptr;
-    if (td) { if (fun) run<true, true>(p, tyb, cl); else run<true, false>(p, tyb, cl); }
-    else    { if (fun) run<false, true>(p, tyb, cl); else run<false, false>(p, tyb, cl); }
+    // td: division mode of the sweep -- 0 four operations, 1 true division, 2 two operations (fast_common.cuh: div_m)
+    if (td == 1)      { if (fun) run<1, true>(p, tyb, cl); else run<1, false>(p, tyb, cl); }
+    else if (td == 2) { if (fun) run<2, true>(p, tyb, cl); else run<2, false>(p, tyb, cl); }
+    else              { if (fun) run<0, true>(p, tyb, cl); else run<0, false>(p, tyb, cl); }
     return 0;
 }

@@ -70,6 +70,9 @@ def test_fused_iteration_bit_exact_vs_oracle(ch, arch, oracle, n, geom):
         Lb(arch, bg, (ch.update_velocity_, (B["V"], B["rV"], B["Pr"], B["tau"], rho_b, SC["eta_ve"], SC["nud"], bg)),
            bc=ch.batch(bg, *_bc_V(ch, B["V"])))
         assert ch.fused_count(arch) == n0 + it + 1, "the pair of launches did not take the fused path"
+        # division mode of the sweep: div.rn.f64 on request, else two operations when proven exact for all four divisors
+        two = all(ch.division_two_op_exact(c) for c in (SC["G"] * SC["dt"], SC["eta"], SC["eta_ve"], 3.0))
+        assert ch.last_division_mode(arch) == (1 if (cl + cz) % 2 else (2 if two else 0))
         for name, a, b in pairs:
             assert_same(a, b, f"sweep {it}: {name}")
     _set_tuning(0, 0)

@@ -441,6 +441,22 @@ def test_exact_division_by_uniform_scalar(ch, arch, c):
         assert used.value == 1 and bad.value == 0, (c, bad.value)
 
 
+@pytest.mark.parametrize("c", [3.0, 10.0, 0.0171 * 1.3, 0.737, 1.0 / 3.0, 6.02e23, 1.7e-19, 3.8780364835615564, 0.007735422636398862])
+def test_two_operation_division_where_it_is_proven(ch, arch, c):
+    """the fused 3D sweep divides in two operations when div2_exact proves that exact for the divisor (include/chmy_b200.h:
+    chmy_division_two_op_exact); on the device the sequence then equals IEEE division on 2^28 operands, and divisors with a
+    failing operand (the last two: found by the number-theoretic search) are refused"""
+    import ctypes as C
+    from chmy_b200 import _lib as L
+    bad, proved = C.c_ulonglong(1), C.c_int(-1)
+    L.check(L.lib().chmy_selftest_division2(arch.ctx, c, 1 << 28, 54321, C.byref(bad), C.byref(proved)))
+    assert proved.value == int(ch.division_two_op_exact(c))
+    if c in (3.8780364835615564, 0.007735422636398862):
+        assert proved.value == 0
+    else:
+        assert proved.value == 1 and bad.value == 0, (c, bad.value)
+
+
 @pytest.mark.parametrize("n", [(130, 19, 70), (63, 9, 5), (64, 8, 64), (65, 17, 65), (1, 1, 1),
                                (300, 70), (257, 129), (256, 64), (255, 63), (1, 1), (515, 3)])
 @pytest.mark.parametrize("true_div", [0, 1])
