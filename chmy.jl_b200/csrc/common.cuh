@@ -201,6 +201,8 @@ static inline dim3 grid_for(const Box& b, dim3 blk) {
                 (unsigned)((b.n[2] + blk.z - 1) / blk.z));
 }
 
+// ops_fused.cu: div2_exact() (fast_common.cuh) per divisor, remembered per context
+bool chmy_div2_cached(chmy_ctx* ctx, double c);
 // ops.cu
 int chmy_run_op(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st);
 int chmy_validate_op(const chmy_launch_desc* d);

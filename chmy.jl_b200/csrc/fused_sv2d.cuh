@@ -72,14 +72,14 @@ FHD void fsv2_init(Fused2T& s, const Fused2P& p, int lane, int seg, int cyc, boo
     }
 }
 
-template <bool TD>
+template <int TD>
 FHD double fsv2_stress_upd(double t, double to, double e2, const Fused2P& p) {
-    const double r = (div_u<TD>(-(t - to), p.Gdt) - div_u<TD>(t, p.eta)) + e2;   // stokes_2d_inc_ve_T.jl:30-33
+    const double r = (div_m<TD>(-(t - to), p.Gdt) - div_m<TD>(t, p.eta)) + e2;   // stokes_2d_inc_ve_T.jl:30-33
     return t + (r * p.eta_ve) * p.dtau_r;
 }
 
 // ---- phase A: stresses of row jp -> sn[4] = new Pr, xx, yy, xy; stores for the cells this thread owns
-template <bool TD>
+template <int TD>
 FHD void fsv2_phase_a(Fused2T& s, const Fused2P& p, int jp, d2 sn[4]) {
     const d2 z2 = fsv_zero();
     d2 vx = z2, vyjp = z2, pr = z2, t[3], o[3];
@@ -110,7 +110,7 @@ FHD void fsv2_phase_a(Fused2T& s, const Fused2P& p, int jp, d2 sn[4]) {
         const double a_pr = h ? pr.y : pr.x;
         const bool in = (h ? s.fx1 : s.fx0) && fy;
         const double n_pr = in ? a_pr - (d * p.eta_ve) * p.dtau_Pr : a_pr;
-        const double d3  = div_u<TD>(d, p.three);          // the 2D driver also divides by 3.0 (:28-29)
+        const double d3  = div_m<TD>(d, p.three);          // the 2D driver also divides by 3.0 (:28-29)
         const double e2[3] = {2.0 * (exx - d3), 2.0 * (eyy - d3), 2.0 * exy};
         if (h) { dv.y = d; prn.y = n_pr; } else { dv.x = d; prn.x = n_pr; }
 #pragma unroll
@@ -136,7 +136,7 @@ FHD void fsv2_phase_a(Fused2T& s, const Fused2P& p, int jp, d2 sn[4]) {
 // ---- phase B: velocity of row j = jp-1 from the carried new values of rows jp-1 / jp-2, phase A's row jp and the
 // x-neighbours handed in by the caller (warp shuffles on the device: Pr[i-1], tau_xx[i-1] = the left lane's second
 // cell, tau_xy[i+2] = the right lane's first cell, all of row jp-1); then rotate the carried rows.
-template <bool TD, bool FUN>
+template <int TD, bool FUN>
 FHD void fsv2_phase_b(Fused2T& s, const Fused2P& p, int jp, const d2 sn[4], double pr_im1, double txx_im1, double txy_ip2) {
     if (s.nv > 0 && jp >= s.j0 + 1) {   // stokes_2d_inc_ve_T.jl:36-43
         const d2 pr = s.prC, txx = s.txxC, tyy = s.tyyC, txy = s.txyC, txyjp = sn[3];
@@ -162,8 +162,8 @@ FHD void fsv2_phase_b(Fused2T& s, const Fused2P& p, int jp, const d2 sn[4], doub
             const double rvx = ((-((a_pr - a_prim) * p.idx)) + (a_txx - a_txxim) * p.idx) + (a_txyjp - a_txy) * p.idy;
             const double rvy = (((-((a_pr - a_prjm) * p.idy)) + (a_tyy - a_tyyjm) * p.idy) + (a_txyip - a_txy) * p.idx) -
                                (h ? rho.y : rho.x);
-            const double ux = (h ? s.vx_jm.y : s.vx_jm.x) + div_u<TD>(rvx * p.nudtau, p.eve);
-            const double uy = (h ? s.vy_jm.y : s.vy_jm.x) + div_u<TD>(rvy * p.nudtau, p.eve);
+            const double ux = (h ? s.vx_jm.y : s.vx_jm.x) + div_m<TD>(rvx * p.nudtau, p.eve);
+            const double uy = (h ? s.vy_jm.y : s.vy_jm.x) + div_m<TD>(rvy * p.nudtau, p.eve);
             if (h) { nrx.y = rvx; nry.y = rvy; nvx.y = ux; nvy.y = uy; }
             else   { nrx.x = rvx; nry.x = rvy; nvx.x = ux; nvy.x = uy; }
         }

@@ -214,7 +214,7 @@ extern "C" int chmy_selftest_tile_order(const int32_t g[3], const int32_t i0[3],
 }
 
 // div2_exact() per divisor, remembered per context (the drivers launch with the same four scalars every iteration)
-static bool div2_cached(chmy_ctx* ctx, double c) {
+bool chmy_div2_cached(chmy_ctx* ctx, double c) {
     for (int q = 0; q < ctx->n_div2; ++q)
         if (ctx->div2_c[q] == c) return ctx->div2_ok[q];
     const bool ok = div2_exact(c);
@@ -275,7 +275,7 @@ int chmy_run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_
     // two-operation sequence when it is PROVEN exact for all four divisors of this launch, else the four-operation sequence
     const bool td = chmy_force_true_div() || !markstein_ok(Gdt) || !markstein_ok(s[0]) || !markstein_ok(s[1]);
     static const bool allow2 = !(getenv("CHMY_DIV2") && getenv("CHMY_DIV2")[0] == '0');
-    const int dm = td ? 1 : (allow2 && div2_cached(ctx, Gdt) && div2_cached(ctx, s[0]) && div2_cached(ctx, s[1]) && div2_cached(ctx, 3.0)) ? 2 : 0;
+    const int dm = td ? 1 : (allow2 && chmy_div2_cached(ctx, Gdt) && chmy_div2_cached(ctx, s[0]) && chmy_div2_cached(ctx, s[1]) && chmy_div2_cached(ctx, 3.0)) ? 2 : 0;
     ctx->div_mode = dm;
     // geometry: clusters shrink for short boxes (slabs of a split launch)
     int tyb = ctx->tun.fuse_tyb, cl = ctx->tun.fuse_cl;

@@ -14,7 +14,7 @@
 constexpr int F2_WARPS = 4;
 constexpr int FT3_ROWS = 8;      // rows (warps) per CTA of the 3D thermal sweep, as the tuned kernels' TY
 
-template <bool TD, bool FUN>
+template <int TD, bool FUN>      // TD: division mode (fast_common.cuh div_m: 0 four operations, 1 div.rn.f64, 2 two operations)
 __global__ void __launch_bounds__(FSV_LANES* F2_WARPS, 4) k_fused_sv2(const Fused2P p, const int gx) {
     const int lane = threadIdx.x;
     const int seg  = blockIdx.x * F2_WARPS + threadIdx.y;
@@ -310,8 +310,18 @@ int chmy_run_fused2d(chmy_ctx* ctx, int kind, const chmy_launch_desc* dp, const 
         p.cy = cy;
         const bool td = chmy_force_true_div() || !markstein_ok(Gdt) || !markstein_ok(s[0]) || !markstein_ok(s[1]);
         const dim3 blk(FSV_LANES, F2_WARPS, 1);
-        if (rho) { if (td) k_fused_sv2<true, false><<<grid, blk, 0, st>>>(p, gx); else k_fused_sv2<false, false><<<grid, blk, 0, st>>>(p, gx); }
-        else     { if (td) k_fused_sv2<true, true><<<grid, blk, 0, st>>>(p, gx);  else k_fused_sv2<false, true><<<grid, blk, 0, st>>>(p, gx); }
+        static const bool allow2 = !(getenv("CHMY_DIV2") && getenv("CHMY_DIV2")[0] == '0');
+        const int dm = td ? 1 : (allow2 && chmy_div2_cached(ctx, Gdt) && chmy_div2_cached(ctx, s[0]) && chmy_div2_cached(ctx, s[1]) && chmy_div2_cached(ctx, 3.0)) ? 2 : 0;
+        ctx->div_mode = dm;
+        if (rho) {
+            if (dm == 1) k_fused_sv2<1, false><<<grid, blk, 0, st>>>(p, gx);
+            else if (dm == 2) k_fused_sv2<2, false><<<grid, blk, 0, st>>>(p, gx);
+            else k_fused_sv2<0, false><<<grid, blk, 0, st>>>(p, gx);
+        } else {
+            if (dm == 1) k_fused_sv2<1, true><<<grid, blk, 0, st>>>(p, gx);
+            else if (dm == 2) k_fused_sv2<2, true><<<grid, blk, 0, st>>>(p, gx);
+            else k_fused_sv2<0, true><<<grid, blk, 0, st>>>(p, gx);
+        }
         CHMY_CUDA(cudaGetLastError());
     } else {
         FusedQ2P p;

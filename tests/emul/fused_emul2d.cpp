@@ -8,7 +8,7 @@
 #include "../../chmy.jl_b200/csrc/fused_sv2d.cuh"
 #include "../../chmy.jl_b200/csrc/fused_pairs2d.cuh"
 
-template <bool TD, bool FUN>
+template <int TD, bool FUN>
 static void run2(const Fused2P& p) {
     const int nx = p.hi[0] - p.lo[0], ny = p.hi[1] - p.lo[1];
     const int gx = (nx + FSV_XI - 1) / FSV_XI, gy = (ny + p.cy - 1) / p.cy;
@@ -61,8 +61,10 @@ extern "C" int fused_emul2d_run(double** ptrs, const int* strides, const int* bo
     p.cy = cy;
     if (p.lo[0] & 1) return -1;
     const bool fun = p.rho == nullptr;
-    if (td) { if (fun) run2<true, true>(p); else run2<true, false>(p); }
-    else    { if (fun) run2<false, true>(p); else run2<false, false>(p); }
+    // td: division mode -- 0 four operations, 1 true division, 2 two operations (fast_common.cuh: div_m)
+    if (td == 1)      { if (fun) run2<1, true>(p); else run2<1, false>(p); }
+    else if (td == 2) { if (fun) run2<2, true>(p); else run2<2, false>(p); }
+    else              { if (fun) run2<0, true>(p); else run2<0, false>(p); }
     return 0;
 }
 
