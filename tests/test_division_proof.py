@@ -98,3 +98,20 @@ def test_the_library_function_is_that_search_at_53_bits():
         assert chmy_b200.division_two_op_exact(c) == want, (c, want)
         n_refused += not want
     assert n_refused > 0                      # ~1.3 % of divisors have a failing operand: the sample holds some
+
+
+@pytest.mark.parametrize("p", [7, 8, 9, 10])
+def test_the_four_operation_sequence_is_exact_for_every_divisor_markstein_admits(p):
+    """q = RN(x rc + RN(x rl)); r = x - c q (exact in an fma); RN(q + r rc) == RN(x / c) -- exhaustively in a toy format, for
+    every divisor but the all-ones significand (markstein_ok) and every operand"""
+    lo, hi = 1 << (p - 1), 1 << p
+    for c_sig in range(lo, hi - 1):
+        c = Fraction(c_sig)
+        rc = rn(1 / c, p)
+        rl = rn(1 / c - rc, p)
+        for X in range(lo, hi):
+            x = Fraction(X)
+            q = rn(x * rc + rn(x * rl, p), p)
+            r = x - c * q
+            assert rn(r, p) == r, (p, c_sig, X)            # the residual of a faithful quotient is representable
+            assert rn(q + r * rc, p) == rn(x / c, p), (p, c_sig, X)
