@@ -8,7 +8,7 @@ from ._lib import ChmyError, LIB_PATH, lib as load_library
 from .utils import Dim, Side, Left, Right, remove_dim, insert_dim, DoubleBuffer, swap_, front, back
 from .architectures import (Architecture, SingleDeviceArchitecture, DistributedArchitecture, B200Backend, Arch,
                             get_backend, get_device, activate_, set_device_, is_gpu_aware, synchronize, launch_count, topology,
-                            event_record, event_elapsed_ms, set_fusion, fused_count, fusion_fallback_count, last_division_mode, division_two_op_exact, overlapped_count, set_fused_tuning, set_fused2d_tuning, set_launch_split,
+                            event_record, event_elapsed_ms, time_fused_sweep, set_fusion, fused_count, fusion_fallback_count, last_division_mode, division_two_op_exact, overlapped_count, set_fused_tuning, set_fused2d_tuning, set_launch_split,
                             set_exchange_mode, exchange_stats)
 from .grids import (Location, Center, Vertex, flip, Bounded, Connected, UniformAxis, StructuredGrid, UniformGrid,
                     connectivity, spacing, inv_spacing, coord, coords, centers, vertices, origin, extent, bounds,

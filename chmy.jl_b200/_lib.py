@@ -83,6 +83,7 @@ SYMBOLS = {
     "chmy_ctx_launch_count": (C.c_int, [_vp, _P(C.c_uint64)]),
     "chmy_event_record": (C.c_int, [_vp, C.c_int]),
     "chmy_event_elapsed_ms": (C.c_int, [_vp, C.c_int, C.c_int, _P(C.c_float)]),
+    "chmy_time_fused_sweep": (C.c_int, [_vp, C.c_int, C.c_int]),
     "chmy_ctx_streams": (C.c_int, [_vp, _P(_vp), _P(_vp)]),
     "chmy_dims_create": (C.c_int, [C.c_int, C.c_int, _i32p]),
     "chmy_comm_unique_id": (C.c_int, [_P(C.c_uint8)]),

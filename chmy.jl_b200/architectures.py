@@ -226,6 +226,11 @@ def event_record(arch: Architecture, slot: int):
     L.check(L.lib().chmy_event_record(arch.ctx, int(slot)))
 
 
+def time_fused_sweep(arch: Architecture, slot_begin: int = -1, slot_end: int = -1):
+    """record event slot_begin / slot_end right before / after the kernel of every fused 3D sweep (-1, -1: off)"""
+    L.check(L.lib().chmy_time_fused_sweep(arch.ctx, int(slot_begin), int(slot_end)))
+
+
 def event_elapsed_ms(arch: Architecture, start: int, stop: int) -> float:
     ms = C.c_float()
     L.check(L.lib().chmy_event_elapsed_ms(arch.ctx, int(start), int(stop), C.byref(ms)))

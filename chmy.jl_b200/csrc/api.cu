@@ -175,6 +175,26 @@ extern "C" int chmy_event_record(chmy_ctx* c, int slot) {
     return CHMY_OK;
 }
 
+// records timing event `slot` on `st` without flushing a deferred launch (used around the fused sweep, ops_fused.cu)
+int chmy_event_record_on(chmy_ctx* c, int slot, cudaStream_t st) {
+    if (!c->ev_time) {
+        c->ev_time = (cudaEvent_t*)calloc(CHMY_MAX_EVENTS, sizeof(cudaEvent_t));
+        if (!c->ev_time) { chmy_set_error("out of host memory"); return CHMY_ERR_NOMEM; }
+    }
+    if (!c->ev_time[slot]) CHMY_CUDA(cudaEventCreate(&c->ev_time[slot]));
+    CHMY_CUDA(cudaEventRecord(c->ev_time[slot], st));
+    return CHMY_OK;
+}
+
+extern "C" int chmy_time_fused_sweep(chmy_ctx* c, int slot_begin, int slot_end) {
+    CHMY_REQUIRE(c != nullptr, "ctx is NULL");
+    CHMY_REQUIRE((slot_begin < 0 && slot_end < 0) || (slot_begin >= 0 && slot_end >= 0 && slot_begin < CHMY_MAX_EVENTS &&
+                 slot_end < CHMY_MAX_EVENTS && slot_begin != slot_end), "bad event slots");
+    c->sweep_ev0 = slot_begin < 0 ? 0 : slot_begin + 1;      // stored + 1: a zeroed context times nothing
+    c->sweep_ev1 = slot_end < 0 ? 0 : slot_end + 1;
+    return CHMY_OK;
+}
+
 extern "C" int chmy_event_elapsed_ms(chmy_ctx* c, int a, int b, float* ms) {
     CHMY_REQUIRE(c && ms && c->ev_time && a >= 0 && b >= 0 && a < CHMY_MAX_EVENTS && b < CHMY_MAX_EVENTS &&
                      c->ev_time[a] && c->ev_time[b], "event slots not recorded");

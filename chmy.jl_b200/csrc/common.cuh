@@ -185,6 +185,7 @@ struct chmy_ctx {
     int               div_mode, n_div2, div2_next;
     double            div2_c[8];
     bool              div2_ok[8];
+    int               sweep_ev0, sweep_ev1;   // chmy_time_fused_sweep: event slots (+1) recorded right before / after the 3D sweep kernel, 0 = off
     // staged uploads (api.cu copy_box_host): two device buffers a dense host box is copied into piecewise, contiguously, while
     // a kernel scatters the previous piece into the padded field
     char*             d_up[2];
@@ -203,6 +204,8 @@ static inline dim3 grid_for(const Box& b, dim3 blk) {
 
 // ops_fused.cu: div2_exact() (fast_common.cuh) per divisor, remembered per context
 bool chmy_div2_cached(chmy_ctx* ctx, double c);
+// api.cu
+int chmy_event_record_on(chmy_ctx* c, int slot, cudaStream_t st);
 // ops.cu
 int chmy_run_op(chmy_ctx* ctx, const chmy_launch_desc* d, const Box& box, cudaStream_t st);
 int chmy_validate_op(const chmy_launch_desc* d);

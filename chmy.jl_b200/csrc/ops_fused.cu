@@ -299,11 +299,13 @@ int chmy_run_fused(chmy_ctx* ctx, const chmy_launch_desc* ds, const chmy_launch_
     const dim3 grid((unsigned)total, (unsigned)cl, 1);
     int rc;
     const int var = ctx->tun.fuse_var;
+    if (ctx->sweep_ev0) CHMY_TRY(chmy_event_record_on(ctx, ctx->sweep_ev0 - 1, st));
     if (rho) rc = dm == 1 ? launch_fused_tyb<1, false>(p, tyb, cl, var, grid, st)
                 : dm == 2 ? launch_fused_tyb<2, false>(p, tyb, cl, var, grid, st) : launch_fused_tyb<0, false>(p, tyb, cl, var, grid, st);
     else     rc = dm == 1 ? launch_fused_tyb<1, true>(p, tyb, cl, var, grid, st)
                 : dm == 2 ? launch_fused_tyb<2, true>(p, tyb, cl, var, grid, st) : launch_fused_tyb<0, true>(p, tyb, cl, var, grid, st);
     CHMY_TRY(rc);
+    if (ctx->sweep_ev1) CHMY_TRY(chmy_event_record_on(ctx, ctx->sweep_ev1 - 1, st));
     ctx->n_launches++;
     return CHMY_OK;
 }

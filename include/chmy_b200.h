@@ -192,6 +192,10 @@ int chmy_ctx_launch_count(const chmy_ctx* ctx, uint64_t* kernels); /* kernels la
 #define CHMY_MAX_EVENTS 4096
 int chmy_event_record(chmy_ctx* ctx, int slot);
 int chmy_event_elapsed_ms(chmy_ctx* ctx, int slot_start, int slot_stop, float* ms);   /* synchronises on slot_stop */
+/* Measurement aid: record event slot_begin right before and slot_end right after the kernel of every fused 3D sweep, on the
+ * stream it is launched on (a launch with boundary batches is one API call but two kernels: this isolates the sweep).
+ * (-1, -1) switches it off.  bench.py uses it for roofline.kernel_ms. */
+int chmy_time_fused_sweep(chmy_ctx* ctx, int slot_begin, int slot_end);
 /* raw handles for tools that time or capture the context's work (cudaStream_t as void*) */
 int chmy_ctx_streams(const chmy_ctx* ctx, void** main_stream, void** boundary_stream);
 

@@ -127,6 +127,9 @@ class DryRunLib:
         self._flush_all()
         return 0
 
+    def chmy_time_fused_sweep(self, ctx, a, b):
+        return 0
+
     def chmy_event_elapsed_ms(self, ctx, a, b, out):
         self._set(out, 1.0)
         return 0
